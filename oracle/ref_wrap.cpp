@@ -1,0 +1,89 @@
+/*
+ * ref_wrap.cpp -- C-ABI wrapper around the REFERENCE's own hot-path source text.
+ * Test infrastructure only (oracle/_ref/libwn_ref.so); never shipped.
+ *
+ * Built by oracle/Makefile target `ref`, only where /root/reference exists:
+ *   - src/brute-find-pairs.cpp is compiled as its own translation unit, in place;
+ *   - the bodies of switch_function_radius, switch_function_angle, computeEnergy
+ *     (src/waternetwork.cpp:12-66) and make_edges (:182-263) are sliced out of
+ *     waternetwork.cpp into a temporary file at build time (the rest of that file
+ *     needs GROMACS, which is not installed) and pulled in below through
+ *     WN_REF_SLICE.  No reference text is stored in this repository.
+ * CGAL arithmetic comes from oracle/shim (restated semantics, see there).
+ */
+#include "cgal.hpp"              /* reference include/cgal.hpp over the shim   */
+#include "utils.hpp"             /* reference include/utils.hpp                 */
+#include "brute-find-pairs.hpp"  /* reference include/brute-find-pairs.hpp      */
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include WN_REF_SLICE            /* computeEnergy + make_edges, reference text  */
+
+extern "C" {
+
+struct wnref_edge { int32_t i, j; float energy, length, cosine; };
+
+double wnref_switch_function_radius(double r, double on, double off)
+{
+    return switch_function_radius(r, on, off);
+}
+double wnref_switch_function_angle(double a, double on, double off)
+{
+    return switch_function_angle(a, on, off);
+}
+double wnref_compute_energy(double r, double cosine) { return computeEnergy(r, cosine); }
+
+size_t wnref_brute_find_pairs(const double* xyz, int n, int32_t* pairs, size_t cap)
+{
+    std::vector<Point> pts;
+    pts.reserve(n);
+    for (int i = 0; i < n; ++i) pts.push_back(Point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+    BruteFindPairs finder;
+    std::vector<std::pair<int, int>> res = finder.find(pts);
+    for (size_t k = 0; k < res.size() && k < cap; ++k) {
+        pairs[2 * k] = res[k].first;
+        pairs[2 * k + 1] = res[k].second;
+    }
+    return res.size();
+}
+
+size_t wnref_make_edges(const int32_t* pairs, size_t m, const double* site_xyz, int n,
+                        const double* h_xyz, const int32_t* h_off, const uint8_t* site_type,
+                        wnref_edge* out)
+{
+    std::vector<std::pair<int, int>> pv(m);
+    for (size_t k = 0; k < m; ++k) pv[k] = std::pair<int, int>(pairs[2 * k], pairs[2 * k + 1]);
+    std::vector<Point> sitePoints;
+    std::vector<std::vector<Point_ptr>> hydrogens(n);
+    std::vector<SiteInfo_ptr> sites(n);
+    for (int s = 0; s < n; ++s) {
+        sitePoints.push_back(Point(site_xyz[3 * s], site_xyz[3 * s + 1], site_xyz[3 * s + 2]));
+        for (int h = h_off[s]; h < h_off[s + 1]; ++h)
+            hydrogens[s].push_back(std::make_shared<Point>(h_xyz[3 * h], h_xyz[3 * h + 1], h_xyz[3 * h + 2]));
+        SiteInfo info;
+        info.type = (SiteType)site_type[s];
+        info.id = (unsigned)s;           /* id carries the 0-based site index back out */
+        info.atmIndex = (unsigned)s;
+        info.resIndex = 0;
+        info.nbHydrogen = (unsigned short)(h_off[s + 1] - h_off[s]);
+        sites[s] = std::make_shared<SiteInfo>(info);
+    }
+    std::vector<std::pair<int, int>>::iterator b = pv.begin(), e = pv.end();
+    std::vector<HydrogenBond> hb = make_edges(b, e, sitePoints, hydrogens, sites);
+    for (size_t k = 0; k < hb.size(); ++k) {
+        out[k].i = (int32_t)hb[k].sites.first->id;
+        out[k].j = (int32_t)hb[k].sites.second->id;
+        out[k].energy = (float)hb[k].energy;   /* exact: value is a widened float */
+        out[k].length = (float)hb[k].length;
+        out[k].cosine = (float)hb[k].angle;
+    }
+    return hb.size();
+}
+
+} /* extern "C" */

@@ -1,0 +1,277 @@
+/*
+ * wn_oracle.c -- CPU oracle (test infrastructure only; see wn_oracle.h).
+ *
+ * Plain C restatement of the reference hot path.  Every comparison-feeding
+ * value is an IEEE binary64 computed in the reference's association order;
+ * build with -ffp-contract=off so the compiler cannot fuse a*b+c.
+ */
+#include "wn_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- CGAL Cartesian-kernel semantics (restated; CGAL is not in the tree) ---- */
+
+typedef struct { double x, y, z; } v3;
+
+static inline v3 v3_sub(const double* p, const double* q)      /* Point - Point */
+{
+    v3 r; r.x = p[0] - q[0]; r.y = p[1] - q[1]; r.z = p[2] - q[2]; return r;
+}
+static inline double v3_dot(v3 a, v3 b)                         /* Vector * Vector */
+{
+    return a.x * b.x + a.y * b.y + a.z * b.z;                   /* ((xx+yy)+zz) */
+}
+static inline v3 v3_div(v3 a, double c)                         /* Vector / scalar */
+{
+    v3 r; r.x = a.x / c; r.y = a.y / c; r.z = a.z / c; return r;
+}
+static inline v3 v3_scale(double c, v3 a)                       /* scalar * Vector */
+{
+    v3 r; r.x = c * a.x; r.y = c * a.y; r.z = c * a.z; return r;
+}
+
+/* ---- src/waternetwork.cpp:12-28 ---- */
+double wno_switch_function_radius(double r, double r_on, double r_off)
+{
+    double sw = 0.0;
+    if (r_off > r && r > r_on) {
+        sw = pow(pow(r, 2) - pow(r_off, 2), 2);
+        sw *= pow(r_off, 2) + 2 * pow(r, 2) - 3 * pow(r_on, 2);
+        sw /= pow(pow(r_off, 2) - pow(r_on, 2), 3);
+    } else if (r < r_on) {
+        sw = 1.0;
+    }
+    return sw;
+}
+
+/* ---- src/waternetwork.cpp:30-47 ---- */
+double wno_switch_function_angle(double a, double a_on, double a_off)
+{
+    double sw = 0.0;
+    if (a_off < a && a < a_on) {
+        sw = pow(pow(a, 2) - pow(a_off, 2), 2);
+        sw *= pow(a_off, 2) + 2 * pow(a, 2) - 3 * pow(a_on, 2);
+        sw /= pow(pow(a_off, 2) - pow(a_on, 2), 3);
+        sw *= -1.0;
+    } else if (a > a_on) {
+        sw = 1.0;
+    }
+    return sw;
+}
+
+/* ---- src/waternetwork.cpp:49-66 ----
+ * C and D are `static float` in the reference, widened in the divisions.
+ * Note the caller-side argument swap (:59-60): the angle switch receives
+ * (theta_off, theta_on) in its (a_on, a_off) slots. */
+double wno_compute_energy_ex(double r, double cosine, double r_on, double r_off,
+                             double theta_on, double theta_off)
+{
+    static float C = 3855;
+    static float D = 738;
+    double radius_switch = wno_switch_function_radius(r * r, r_on * r_on, r_off * r_off);
+    double angle_switch = wno_switch_function_angle(cosine * cosine, theta_off, theta_on);
+    double energy = ((C / pow(r, 6.0)) - (D / pow(r, 4.0)));
+    energy *= pow(cosine, 4.0);
+    energy *= radius_switch;
+    energy *= angle_switch;
+    return energy;
+}
+
+double wno_compute_energy(double r, double cosine)
+{
+    return wno_compute_energy_ex(r, cosine, 5.5, 6.5, 0.25, 0.0);
+}
+
+/* ---- src/brute-find-pairs.cpp:19-30 ----
+ * float cutoff = 6.5; cutoff *= cutoff;  -> 42.25f, compared as double.
+ * CGAL::squared_distance(p,q) = (dx*dx + dy*dy) + dz*dz. */
+size_t wno_brute_find_pairs_limited(const double* xyz, int n, int first_limit,
+                                    int32_t* pairs, size_t cap, wno_ties* ties)
+{
+    float cutoff = 6.5f;
+    size_t count = 0;
+    int i, j;
+    cutoff *= cutoff;
+    if (first_limit > n) first_limit = n;
+    for (i = 0; i < first_limit; ++i) {
+        const double* p = xyz + 3 * (size_t)i;
+        for (j = i + 1; j < n; ++j) {
+            const double* q = xyz + 3 * (size_t)j;
+            v3 d = v3_sub(p, q);
+            double d2 = v3_dot(d, d);
+            double lhs = 10.0 * d2;
+            if (lhs < cutoff) {
+                if (pairs && count < cap) {
+                    pairs[2 * count] = i;
+                    pairs[2 * count + 1] = j;
+                }
+                ++count;
+            } else if (ties && lhs == (double)cutoff) {
+                ties->pair_cutoff_equal++;
+            }
+        }
+    }
+    return count;
+}
+
+size_t wno_brute_find_pairs(const double* xyz, int n, int32_t* pairs, size_t cap,
+                            wno_ties* ties)
+{
+    return wno_brute_find_pairs_limited(xyz, n, n, pairs, cap, ties);
+}
+
+/* ---- src/waternetwork.cpp:182-263 ---- */
+size_t wno_make_edges(const int32_t* pairs, size_t m,
+                      const double* site_xyz, int n,
+                      const double* h_xyz, const int32_t* h_off,
+                      const uint8_t* site_type,
+                      wno_edge* out, uint64_t* n_evals, wno_ties* ties)
+{
+    size_t count = 0, k;
+    uint64_t evals = 0;
+    float* coss = NULL;
+    float* energies = NULL;
+    int maxh = 0, s;
+    (void)n;
+    for (s = 0; s < n; ++s) {
+        int nh = h_off[s + 1] - h_off[s];
+        if (nh > maxh) maxh = nh;
+    }
+    coss = (float*)malloc(sizeof(float) * (size_t)(2 * maxh + 1));
+    energies = (float*)malloc(sizeof(float) * (size_t)(2 * maxh + 1));
+
+    for (k = 0; k < m; ++k) {
+        const int a = pairs[2 * k], b = pairs[2 * k + 1];
+        const double* pa = site_xyz + 3 * (size_t)a;
+        const double* pb = site_xyz + 3 * (size_t)b;
+        const int nha = h_off[a + 1] - h_off[a];
+        const int nhb = h_off[b + 1] - h_off[b];
+        int isedge = 0;
+        v3 OO = v3_sub(pa, pb);                                   /* :194 */
+        float distance = (float)sqrt(v3_dot(OO, OO));             /* :195 */
+        OO = v3_div(OO, (double)distance);                        /* :196 */
+        distance = (float)((double)distance * 10.0);              /* :197 */
+
+        if (site_type[a] != site_type[b]) isedge = 1;             /* :199 */
+        if (site_type[a] == WNO_WATER && site_type[b] == WNO_WATER) isedge = 1;
+        if (ties && distance == 6.5f) ties->length_equal_cut++;
+        if ((double)distance > 6.5) isedge = 0;                   /* :204 */
+        if (nha == 0 && nhb == 0) isedge = 0;                     /* :205-208 */
+
+        if (isedge) {
+            int nc = 0, h, pos = -1, i;
+            float cosmax = 0.0f;
+            ++evals;
+            for (h = 0; h < nha; ++h) {                           /* :215-225 */
+                v3 DH = v3_sub(h_xyz + 3 * (size_t)(h_off[a] + h), pa);
+                float proj;
+                DH = v3_div(DH, sqrt(v3_dot(DH, DH)));
+                proj = (float)v3_dot(DH, OO);
+                energies[nc] = (float)wno_compute_energy((double)distance, (double)proj);
+                coss[nc] = proj;
+                ++nc;
+            }
+            for (h = 0; h < nhb; ++h) {                           /* :227-237 */
+                v3 DH = v3_sub(h_xyz + 3 * (size_t)(h_off[b] + h), pb);
+                float proj;
+                DH = v3_div(DH, sqrt(v3_dot(DH, DH)));
+                proj = (float)v3_dot(DH, v3_scale(-1.0, OO));
+                energies[nc] = (float)wno_compute_energy((double)distance, (double)proj);
+                coss[nc] = proj;
+                ++nc;
+            }
+            for (i = 0; i < nc; ++i) {                            /* :240-249 */
+                if (coss[i] > cosmax) {
+                    cosmax = coss[i];
+                    pos = i;
+                } else if (ties && cosmax > 0.0f && coss[i] == cosmax) {
+                    ties->cosine_argmax_equal++;
+                }
+            }
+            if (ties && pos == 0) ties->pos_zero++;
+            if (pos > 0) {                                        /* :251-258 */
+                out[count].i = a;
+                out[count].j = b;
+                out[count].energy = energies[pos];
+                out[count].length = distance;
+                out[count].cosine = coss[pos];
+                ++count;
+            }
+        }
+    }
+    free(coss);
+    free(energies);
+    if (n_evals) *n_evals = evals;
+    return count;
+}
+
+/* ---- src/waternetwork.cpp:68-81 (widening) and :538-577 (gather) ---- */
+void wno_gather_sites(const float* frame_xyz, int natoms,
+                      const int32_t* site_atom, const int32_t* h_atom, int hmax, int n,
+                      double* site_xyz, double* h_xyz, int32_t* h_off)
+{
+    int s, h, c, nh_total = 0;
+    (void)natoms;
+    for (s = 0; s < n; ++s) {
+        const float* p = frame_xyz + 3 * (size_t)site_atom[s];
+        for (c = 0; c < 3; ++c) site_xyz[3 * (size_t)s + c] = (double)p[c];
+        h_off[s] = nh_total;
+        for (h = 0; h < hmax; ++h) {
+            int at = h_atom[(size_t)s * hmax + h];
+            if (at < 0) break;
+            for (c = 0; c < 3; ++c)
+                h_xyz[3 * (size_t)nh_total + c] = (double)frame_xyz[3 * (size_t)at + c];
+            ++nh_total;
+        }
+    }
+    h_off[n] = nh_total;
+}
+
+/* ---- src/waternetwork.cpp:564-575: hydrogens.at(i) = solventPoints.at(3*index+i),
+ * i < nbHydrogen (=2 for water, makeSites :155-161), site = solventPoints.at(3*index) */
+void wno_water_site_table(int n_waters, int32_t* site_atom, int32_t* h_atom,
+                          uint8_t* site_type)
+{
+    int w;
+    for (w = 0; w < n_waters; ++w) {
+        site_atom[w] = 3 * w;
+        h_atom[2 * w] = 3 * w;
+        h_atom[2 * w + 1] = 3 * w + 1;
+        site_type[w] = WNO_WATER;
+    }
+}
+
+size_t wno_frame_hbonds(const float* frame_xyz, int natoms,
+                        const int32_t* site_atom, const int32_t* h_atom, int hmax,
+                        const uint8_t* site_type, int n, int first_limit,
+                        wno_edge* edges, size_t cap, double* stats,
+                        uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties)
+{
+    double* site_xyz = (double*)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
+    double* h_xyz = (double*)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1) * (size_t)(hmax > 0 ? hmax : 1));
+    int32_t* h_off = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1));
+    int32_t* pairs = NULL;
+    wno_edge* tmp = NULL;
+    size_t m, ne, k;
+    double sum_e = 0.0;
+
+    wno_gather_sites(frame_xyz, natoms, site_atom, h_atom, hmax, n, site_xyz, h_xyz, h_off);
+    m = wno_brute_find_pairs_limited(site_xyz, n, first_limit, NULL, 0, NULL);
+    pairs = (int32_t*)malloc(sizeof(int32_t) * 2 * (m ? m : 1));
+    wno_brute_find_pairs_limited(site_xyz, n, first_limit, pairs, m, ties);
+    tmp = (wno_edge*)malloc(sizeof(wno_edge) * (m ? m : 1));
+    ne = wno_make_edges(pairs, m, site_xyz, n, h_xyz, h_off, site_type, tmp, n_evals, ties);
+    if (n_pairs) *n_pairs = m;
+    for (k = 0; k < ne; ++k) sum_e += (double)tmp[k].energy;
+    if (stats) {                                     /* :654-666 + extra sum E */
+        stats[0] = (double)n;
+        stats[1] = (double)ne;
+        stats[2] = n > 0 ? 1.0 * (double)ne / (double)n : 0.0;
+        stats[3] = sum_e;
+    }
+    if (ne <= cap && edges) memcpy(edges, tmp, sizeof(wno_edge) * ne);
+    free(tmp); free(pairs); free(h_off); free(h_xyz); free(site_xyz);
+    return ne <= cap ? ne : (size_t)-1;
+}

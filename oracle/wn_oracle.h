@@ -1,0 +1,112 @@
+/*
+ * wn_oracle.h -- CPU oracle for the gmx-waternetwork hydrogen-bond hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing shipped under gmx-acqueduct_b200/ or
+ * include/ may include, link or call this.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs use it, as the checker.
+ *
+ * It is a fresh plain-C restatement of the reference algorithm (SURVEY.md
+ * Appendix A); every function cites the reference file:line it follows
+ * (paths relative to /root/reference).  All point arithmetic that the
+ * reference delegates to CGAL's Cartesian kernel (absent from the reference
+ * tree; "CGAL 4.X", version unpinned, README.md:12) is restated here from
+ * CGAL's published semantics: component-wise subtraction, left-to-right
+ * scalar product, true division, std::sqrt.
+ *
+ * Parity status: the reference holds NO golden vectors, known-answer tests or
+ * fixtures for this path (test/tests.cpp is `int main(){return 0;}`).  The
+ * oracle is pinned instead against oracle/_ref: the reference's own
+ * brute-find-pairs.cpp, make_edges and computeEnergy source text compiled
+ * in place against a CGAL-free arithmetic shim (oracle/Makefile, oracle/shim/).
+ * See DESIGN.md section "Oracle".
+ *
+ * Build: gcc -O2 -ffp-contract=off (reference flags: -O2, x86-64 baseline,
+ * no fast-math, CMakeLists.txt:59).
+ */
+#ifndef WN_ORACLE_H
+#define WN_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* include/utils.hpp:7  enum SiteType {DONOR, ACCEPTOR, WATER} */
+enum { WNO_DONOR = 0, WNO_ACCEPTOR = 1, WNO_WATER = 2 };
+
+/* Compact form of include/utils.hpp:25-32 HydrogenBond: the three doubles of the
+ * reference each hold a float-rounded value (src/waternetwork.cpp:195-197,
+ * 211-212,221-223), so float storage is lossless. */
+typedef struct wno_edge {
+    int32_t i, j;     /* pair.first, pair.second (0-based site indices) */
+    float   energy;   /* energies.at(pos) */
+    float   length;   /* distance, Angstrom */
+    float   cosine;   /* coss.at(pos) */
+} wno_edge;
+
+/* Counters of exact comparison ties, reported next to every parity claim. */
+typedef struct wno_ties {
+    uint64_t pair_cutoff_equal;   /* 10*d2 == 42.25 in the brute test          */
+    uint64_t length_equal_cut;    /* (float)dist == 6.5f in make_edges         */
+    uint64_t cosine_argmax_equal; /* c[k] == cosmax > 0 for a later k          */
+    uint64_t pos_zero;            /* arg-max landed on list index 0 (dropped)  */
+} wno_ties;
+
+/* src/waternetwork.cpp:12-28 */
+double wno_switch_function_radius(double r, double r_on, double r_off);
+/* src/waternetwork.cpp:30-47 */
+double wno_switch_function_angle(double a, double a_on, double a_off);
+/* src/waternetwork.cpp:49-66 with explicit on/off parameters */
+double wno_compute_energy_ex(double r, double cosine, double r_on, double r_off,
+                             double theta_on, double theta_off);
+/* src/waternetwork.cpp:49-66 with the defaults every live call uses (:222,:234) */
+double wno_compute_energy(double r, double cosine);
+
+/* src/brute-find-pairs.cpp:7-32.  xyz is AoS double[n][3].  Writes up to `cap`
+ * pairs as (i,j) int32 couples in loop order; returns the full count. */
+size_t wno_brute_find_pairs(const double* xyz, int n, int32_t* pairs, size_t cap,
+                            wno_ties* ties);
+
+/* Same test restricted to rows i < first_limit (north-star "asymmetric search";
+ * not in the reference).  first_limit >= n gives the reference behaviour. */
+size_t wno_brute_find_pairs_limited(const double* xyz, int n, int first_limit,
+                                    int32_t* pairs, size_t cap, wno_ties* ties);
+
+/* src/waternetwork.cpp:182-263.  Hydrogens of site s are
+ * h_xyz[3*h_off[s] .. 3*h_off[s+1]).  Returns number of edges written to out
+ * (capacity must be >= m).  n_evals counts executions of the `if (isedge)` body. */
+size_t wno_make_edges(const int32_t* pairs, size_t m,
+                      const double* site_xyz, int n,
+                      const double* h_xyz, const int32_t* h_off,
+                      const uint8_t* site_type,
+                      wno_edge* out, uint64_t* n_evals, wno_ties* ties);
+
+/* src/waternetwork.cpp:68-81 (float->double widening) and :538-577 (gather).
+ * site_atom[n]: atom index of each site.  h_atom[n*hmax]: atom indices of its
+ * hydrogens, -1 padded.  Outputs: site_xyz[n*3], h_xyz[(sum nH)*3], h_off[n+1]. */
+void wno_gather_sites(const float* frame_xyz, int natoms,
+                      const int32_t* site_atom, const int32_t* h_atom, int hmax, int n,
+                      double* site_xyz, double* h_xyz, int32_t* h_off);
+
+/* Reference water-site table (src/waternetwork.cpp:564-575): water w is site w,
+ * site atom 3w, hydrogen list [3w+0, 3w+1] (the oxygen itself, then H1). */
+void wno_water_site_table(int n_waters, int32_t* site_atom, int32_t* h_atom /*n*2*/,
+                          uint8_t* site_type);
+
+/* One frame end to end as WaterNetwork::analyzeFrame does it with a
+ * BruteFindPairs finder (src/waternetwork.cpp:516-523,538-577,583,590-633,
+ * 654-666): gather, brute pairs, make_edges, stats.
+ * stats[4] = {num_sites, num_edges, 1.0*num_edges/num_sites, sum of (double)energy}.
+ * Returns number of edges; edges capacity `cap` (returns SIZE_MAX on overflow). */
+size_t wno_frame_hbonds(const float* frame_xyz, int natoms,
+                        const int32_t* site_atom, const int32_t* h_atom, int hmax,
+                        const uint8_t* site_type, int n, int first_limit,
+                        wno_edge* edges, size_t cap, double* stats,
+                        uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
