@@ -1,0 +1,282 @@
+"""ctypes binding of the C ABI in include/wn_b200.h (libwn_b200.so).
+
+Used by tests/, bench.py and __graft_entry__.py to drive the library exactly as a
+host program would: plain pointers and sizes.  There is no CPU fallback here or in
+the library -- if the shared object is missing, or no B200 is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwn_b200.so")
+
+WN_OK = 0
+DONOR, ACCEPTOR, WATER = 0, 1, 2
+MODEL_TIP3P, MODEL_SPC = 0, 1
+
+EDGE_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("energy", "<f4"),
+                       ("length", "<f4"), ("cosine", "<f4")])
+STATS_DTYPE = np.dtype([("num_sites", "<f8"), ("num_edges", "<f8"), ("ratio", "<f8"),
+                        ("sum_energy", "<f8"), ("pair_evals", "<f8")])
+assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
+
+# every symbol include/wn_b200.h declares
+SYMBOLS = [
+    "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_set_sites",
+    "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
+    "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
+    "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
+    "wn_get_timings", "wn_nccl_unique_id", "wn_nccl_init", "wn_stats_reduce",
+]
+
+
+class TieReport(C.Structure):
+    _fields_ = [("pair_cutoff_equal", C.c_uint64), ("length_equal_cut", C.c_uint64),
+                ("cosine_argmax_equal", C.c_uint64), ("pos_zero", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class BatchResult(C.Structure):
+    _fields_ = [("edges", C.c_void_p), ("frame_offsets", C.c_void_p), ("stats", C.c_void_p),
+                ("n_edges", C.c_uint64), ("n_pair_evals", C.c_uint64), ("ties", TieReport),
+                ("n_frames", C.c_int32), ("on_device", C.c_int32)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("bin_ms", C.c_float), ("edges_ms", C.c_float),
+                ("finish_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("launches", C.c_int32), ("passes", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class WnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("wn_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen libwn_b200.so (no compute).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            LIB_PATH + " not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u64, i64 = C.c_void_p, C.c_int32, C.c_uint64, C.c_int64
+    L.wn_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.wn_destroy.argtypes = [vp]
+    L.wn_destroy.restype = None
+    L.wn_last_error.argtypes = [vp]
+    L.wn_last_error.restype = C.c_char_p
+    L.wn_version.restype = C.c_char_p
+    L.wn_find_pairs.argtypes = [vp, vp, i32, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(TieReport)]
+    L.wn_set_sites.argtypes = [vp, i32, vp, vp, i32, vp, i32]
+    L.wn_set_water_sites.argtypes = [vp, i32, i32]
+    L.wn_set_energy_params.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.wn_hbond_batch.argtypes = [vp, vp, i32, i32, C.POINTER(BatchResult)]
+    L.wn_hbond_batch_dev.argtypes = [vp, vp, i32, i32, C.POINTER(BatchResult)]
+    L.wn_set_batch_frames.argtypes = [vp, i32]
+    L.wn_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.wn_dev_free.argtypes = [vp, vp]
+    L.wn_host_alloc_pinned.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.wn_host_free_pinned.argtypes = [vp, vp]
+    L.wn_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.wn_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.wn_synth_frames_dev.argtypes = [vp, i32, u64, i32, i64, i32, vp]
+    L.wn_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.wn_nccl_unique_id.argtypes = [vp]
+    L.wn_nccl_init.argtypes = [vp, vp, i32, i32]
+    L.wn_stats_reduce.argtypes = [vp, vp, i64]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("wn_destroy", "wn_last_error", "wn_version"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+class Context:
+    """One wn_ctx: single caller, one GPU (include/wn_b200.h)."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.wn_create(device, C.byref(h))
+        if rc != WN_OK:
+            raise WnError(rc, self.L.wn_last_error(None).decode())
+        self.h = h
+        self.n_sites = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != WN_OK:
+            raise WnError(rc, self.L.wn_last_error(self.h).decode())
+
+    # ---- FindPairs::find
+    def find_pairs(self, xyz, first_limit=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        n = xyz.shape[0]
+        fl = n if first_limit is None else int(first_limit)
+        p, m, ties = C.c_void_p(), C.c_uint64(), TieReport()
+        self._ck(self.L.wn_find_pairs(self.h, xyz.ctypes.data, n, fl, C.byref(p), C.byref(m), C.byref(ties)))
+        cnt = int(m.value)
+        if cnt == 0:
+            return np.zeros((0, 2), np.int32), ties.as_dict()
+        buf = (C.c_int32 * (2 * cnt)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.int32).reshape(cnt, 2).copy(), ties.as_dict()
+
+    # ---- site tables
+    def set_sites(self, site_atom, h_atom, site_type, first_limit=None):
+        site_atom = np.ascontiguousarray(site_atom, dtype=np.int32)
+        n = len(site_atom)
+        h_atom = np.ascontiguousarray(h_atom, dtype=np.int32).reshape(n, -1) if n else np.zeros((0, 1), np.int32)
+        hmax = h_atom.shape[1]
+        site_type = np.ascontiguousarray(site_type, dtype=np.uint8)
+        fl = n if first_limit is None else int(first_limit)
+        self._ck(self.L.wn_set_sites(self.h, n, site_atom.ctypes.data, h_atom.ctypes.data, hmax,
+                                     site_type.ctypes.data, fl))
+        self.n_sites = n
+
+    def set_water_sites(self, n_waters, first_limit=None):
+        fl = n_waters if first_limit is None else int(first_limit)
+        self._ck(self.L.wn_set_water_sites(self.h, n_waters, fl))
+        self.n_sites = n_waters
+
+    def set_energy_params(self, r_on=5.5, r_off=6.5, theta_on=0.25, theta_off=0.0):
+        self._ck(self.L.wn_set_energy_params(self.h, r_on, r_off, theta_on, theta_off))
+
+    def set_batch_frames(self, n):
+        self._ck(self.L.wn_set_batch_frames(self.h, int(n)))
+
+    # ---- batches
+    def _wrap(self, res, copy=True):
+        nf, ne = res.n_frames, int(res.n_edges)
+        out = {"n_edges": ne, "n_pair_evals": int(res.n_pair_evals), "ties": res.ties.as_dict(),
+               "n_frames": nf}
+        if res.on_device:
+            out["edges_dev"] = res.edges
+            out["frame_offsets_dev"] = res.frame_offsets
+            out["stats_dev"] = res.stats
+            return out
+        if ne:
+            e = np.frombuffer((C.c_char * (ne * 20)).from_address(res.edges), dtype=EDGE_DTYPE)
+        else:
+            e = np.zeros(0, EDGE_DTYPE)
+        fo = np.frombuffer((C.c_uint64 * (nf + 1)).from_address(res.frame_offsets), dtype=np.uint64)
+        st = np.frombuffer((C.c_char * (nf * 40)).from_address(res.stats), dtype=STATS_DTYPE) if nf else \
+            np.zeros(0, STATS_DTYPE)
+        out["edges"] = e.copy() if copy else e
+        out["frame_offsets"] = fo.copy() if copy else fo
+        out["stats"] = st.copy() if copy else st
+        return out
+
+    def hbond_batch(self, frames, copy=True):
+        """frames: host float32 [F][natoms][3] (numpy) or (ptr, n_frames, natoms)."""
+        if isinstance(frames, tuple):
+            ptr, nf, natoms = frames
+        else:
+            frames = np.ascontiguousarray(frames, dtype=np.float32)
+            if frames.ndim == 2:
+                frames = frames[None]
+            nf, natoms = frames.shape[0], frames.shape[1]
+            ptr = frames.ctypes.data
+        res = BatchResult()
+        self._ck(self.L.wn_hbond_batch(self.h, ptr, nf, natoms, C.byref(res)))
+        return self._wrap(res, copy)
+
+    def hbond_batch_dev(self, frames_dev, n_frames, natoms):
+        res = BatchResult()
+        self._ck(self.L.wn_hbond_batch_dev(self.h, frames_dev, n_frames, natoms, C.byref(res)))
+        return self._wrap(res)
+
+    def fetch_dev_result(self, out):
+        """Copy a device-resident batch result to numpy arrays."""
+        nf, ne = out["n_frames"], out["n_edges"]
+        e = np.zeros(ne, EDGE_DTYPE)
+        fo = np.zeros(nf + 1, np.uint64)
+        st = np.zeros(nf, STATS_DTYPE)
+        if ne:
+            self.d2h(e, out["edges_dev"])
+        self.d2h(fo, out["frame_offsets_dev"])
+        if nf:
+            self.d2h(st, out["stats_dev"])
+        return e, fo, st
+
+    def timings(self):
+        t = Timings()
+        self._ck(self.L.wn_get_timings(self.h, C.byref(t)))
+        return t.as_dict()
+
+    # ---- plumbing
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.L.wn_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, ptr):
+        self._ck(self.L.wn_dev_free(self.h, ptr))
+
+    def pinned_array(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._ck(self.L.wn_host_alloc_pinned(self.h, n, C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return arr, p.value
+
+    def pinned_free(self, ptr):
+        self._ck(self.L.wn_host_free_pinned(self.h, ptr))
+
+    def d2h(self, dst_np, src_dev):
+        self._ck(self.L.wn_memcpy_d2h(self.h, dst_np.ctypes.data, src_dev, dst_np.nbytes))
+
+    def h2d(self, dst_dev, src_np):
+        src_np = np.ascontiguousarray(src_np)
+        self._ck(self.L.wn_memcpy_h2d(self.h, dst_dev, src_np.ctypes.data, src_np.nbytes))
+
+    def synth_frames_dev(self, n_waters, frame0, n_frames, frames_dev, seed=1234, model=MODEL_TIP3P):
+        self._ck(self.L.wn_synth_frames_dev(self.h, n_waters, seed, model, frame0, n_frames, frames_dev))
+
+    # ---- multi-GPU statistics
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        rc = self.L.wn_nccl_unique_id(buf)
+        if rc != WN_OK:
+            raise WnError(rc, self.L.wn_last_error(None).decode())
+        return buf.raw
+
+    def nccl_init(self, id128, rank, nranks):
+        self._ck(self.L.wn_nccl_init(self.h, id128, rank, nranks))
+
+    def stats_reduce(self, stats):
+        assert stats.dtype == STATS_DTYPE and stats.flags.c_contiguous
+        self._ck(self.L.wn_stats_reduce(self.h, stats.ctypes.data, len(stats)))
+        return stats
+
+
+def shard_frames(n_frames, rank, world):
+    """Contiguous frame block of `rank`: [floor(r*F/G), floor((r+1)*F/G))."""
+    return (rank * n_frames) // world, ((rank + 1) * n_frames) // world

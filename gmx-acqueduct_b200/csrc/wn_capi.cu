@@ -1,0 +1,750 @@
+/*
+ * wn_capi.cu -- the C ABI of include/wn_b200.h: context, device memory, the batched
+ * pipeline driver and the NCCL statistics reduction.  No kernel lives here.
+ *
+ * Pipeline of one pass (F frames resident per launch), mirroring the stages of
+ * WaterNetwork::analyzeFrame (reference src/waternetwork.cpp:503-667):
+ *   convert+gather (:516-523,:538-577)  -> wn_k_bbox, wn_k_bin, wn_k_cellscan, wn_k_scatter
+ *   find + make_edges (:583,:590-633)   -> wn_k_edges
+ *   edge order, energy, stats (:654-666)-> wn_k_rowscan, wn_k_frameoff, wn_k_copy, wn_k_stats
+ */
+#include "wn_internal.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_create_error;
+
+struct wn_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+
+    /* site table */
+    int n_sites = -1, hs = 1, first_limit = 0, typed = 0, max_atom = -1;
+    int* d_site_atom = nullptr;
+    int* d_hv_atom = nullptr;
+    uint32_t* d_meta = nullptr;
+    WnEnergyParams ep;
+
+    /* per-pass buffers */
+    int user_frames_per_pass = 0;
+    int cap_frames = 0, cap_sites = 0, cap_hs = 0, cell_cap = 0;
+    WnGrid* d_grid = nullptr;
+    int* d_cell_cnt = nullptr;
+    int* d_site_cell = nullptr;
+    int* d_site_rank = nullptr;
+    float4* d_spos = nullptr;
+    uint32_t* d_smeta = nullptr;
+    double* d_sdh = nullptr;
+    uint32_t* d_row_pos = nullptr;
+    uint32_t* d_row_cnt = nullptr;
+    uint32_t* d_row_off = nullptr;
+    unsigned long long* d_frame_total = nullptr;
+    WnFrameCounters* d_counters = nullptr;
+    unsigned long long* d_cursor = nullptr;
+    double* d_block_sums = nullptr;
+    WnTempEdge* d_temp = nullptr;
+    size_t temp_cap = 0;
+    float* d_stage = nullptr;      /* host variant: frames of one pass */
+    size_t stage_cap = 0;
+
+    /* call-wide outputs (device) */
+    wn_edge* d_edges = nullptr;
+    size_t edges_cap = 0;
+    unsigned long long* d_frame_off = nullptr;
+    wn_frame_stats* d_stats = nullptr;
+    WnFrameCounters* d_counters_all = nullptr;
+    size_t out_frames_cap = 0;
+
+    /* call-wide outputs (pinned host) */
+    wn_edge* h_edges = nullptr;
+    size_t h_edges_cap = 0;
+    uint64_t* h_frame_off = nullptr;
+    wn_frame_stats* h_stats = nullptr;
+    WnFrameCounters* h_counters = nullptr;
+    size_t h_frames_cap = 0;
+    unsigned long long* h_scalars = nullptr;   /* pinned scratch for small D2H reads */
+
+    /* pair path */
+    double* d_xyz = nullptr;
+    size_t xyz_cap = 0;
+    uint32_t* d_prow_cnt = nullptr;
+    unsigned long long* d_prow_off = nullptr;
+    size_t prow_cap = 0;
+    int32_t* d_pairs = nullptr;
+    size_t d_pairs_cap = 0;
+    int32_t* h_pairs = nullptr;
+    size_t h_pairs_cap = 0;
+    unsigned long long* d_pair_ties = nullptr;
+
+    /* timing */
+    cudaEvent_t ev[6] = {};
+    wn_timings tm = {};
+
+    /* NCCL (loaded lazily) */
+    void* nccl_lib = nullptr;
+    ncclComm_t comm = nullptr;
+    int nranks = 0, rank = 0;
+    double* d_reduce = nullptr;
+    size_t reduce_cap = 0;
+};
+
+namespace {
+
+int fail(wn_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+int cuda_fail(wn_ctx* c, cudaError_t e, const char* what)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    cudaGetLastError();
+    return fail(c, e == cudaErrorMemoryAllocation ? WN_ERR_OOM : WN_ERR_CUDA, buf);
+}
+
+#define WN_CK(call)                                                     \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);        \
+    } while (0)
+
+template <typename T>
+int dev_ensure(wn_ctx* ctx, T** p, size_t* cap, size_t need, bool preserve = false, size_t used = 0)
+{
+    if (need <= *cap && *p) return WN_OK;
+    size_t ncap = std::max(need, *cap + *cap / 2);
+    if (ncap == 0) ncap = 1;
+    T* np = nullptr;
+    WN_CK(cudaMalloc((void**)&np, ncap * sizeof(T)));
+    if (preserve && *p && used)
+        WN_CK(cudaMemcpyAsync(np, *p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->st));
+    if (*p) { WN_CK(cudaStreamSynchronize(ctx->st)); WN_CK(cudaFree(*p)); }
+    *p = np;
+    *cap = ncap;
+    return WN_OK;
+}
+
+template <typename T>
+int dev_realloc_plain(wn_ctx* ctx, T** p, size_t count)
+{
+    if (*p) { WN_CK(cudaFree(*p)); *p = nullptr; }
+    WN_CK(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return WN_OK;
+}
+
+template <typename T>
+int host_ensure(wn_ctx* ctx, T** p, size_t* cap, size_t need, bool preserve = false, size_t used = 0)
+{
+    if (need <= *cap && *p) return WN_OK;
+    size_t ncap = std::max(need, *cap + *cap / 2);
+    if (ncap == 0) ncap = 1;
+    T* np = nullptr;
+    WN_CK(cudaMallocHost((void**)&np, ncap * sizeof(T)));
+    if (preserve && *p && used) memcpy(np, *p, used * sizeof(T));
+    if (*p) WN_CK(cudaFreeHost(*p));
+    *p = np;
+    *cap = ncap;
+    return WN_OK;
+}
+
+int default_frames_per_pass(int n_sites)
+{
+    const long long target = 8ll << 20;    /* site-frames per pass */
+    long long f = target / std::max(n_sites, 1);
+    return (int)std::min<long long>(std::max<long long>(f, 1), 8192);
+}
+
+/* (re)allocate the per-pass buffers for F frames of the current site table */
+int ensure_pass_buffers(wn_ctx* ctx, int F)
+{
+    const int N = ctx->n_sites;
+    if (F <= ctx->cap_frames && N <= ctx->cap_sites && ctx->hs <= ctx->cap_hs && ctx->d_grid) return WN_OK;
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    const int cf = std::max(F, ctx->cap_frames), cn = std::max(N, ctx->cap_sites), ch = std::max(ctx->hs, ctx->cap_hs);
+    const int cell_cap = cn / 4 + 27;
+    const size_t fn = (size_t)cf * cn;
+    int rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_grid, (size_t)cf))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_cell_cnt, (size_t)cf * (cell_cap + 1)))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_site_cell, fn))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_site_rank, fn))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_spos, fn))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_smeta, fn))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_sdh, fn * ch * 3))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_row_pos, fn))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_row_cnt, fn))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_row_off, fn))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_total, (size_t)cf))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_counters, (size_t)cf))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_block_sums, (size_t)cf * ((cn + 255) / 256 + 1)))) return rc;
+    if (!ctx->d_cursor) { if ((rc = dev_realloc_plain(ctx, &ctx->d_cursor, (size_t)1))) return rc; }
+    ctx->cap_frames = cf; ctx->cap_sites = cn; ctx->cap_hs = ch; ctx->cell_cap = cell_cap;
+    return WN_OK;
+}
+
+int ensure_out_frames(wn_ctx* ctx, size_t n_frames, bool host)
+{
+    if (n_frames + 1 > ctx->out_frames_cap || !ctx->d_frame_off) {
+        const size_t cap = n_frames + 1;
+        int rc;
+        WN_CK(cudaStreamSynchronize(ctx->st));
+        if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_off, cap))) return rc;
+        if ((rc = dev_realloc_plain(ctx, &ctx->d_stats, cap))) return rc;
+        if ((rc = dev_realloc_plain(ctx, &ctx->d_counters_all, cap))) return rc;
+        ctx->out_frames_cap = cap;
+    }
+    if (host || true) {
+        if (n_frames + 1 > ctx->h_frames_cap || !ctx->h_frame_off) {
+            const size_t cap = n_frames + 1;
+            if (ctx->h_frame_off) WN_CK(cudaFreeHost(ctx->h_frame_off));
+            if (ctx->h_stats) WN_CK(cudaFreeHost(ctx->h_stats));
+            if (ctx->h_counters) WN_CK(cudaFreeHost(ctx->h_counters));
+            ctx->h_frame_off = nullptr; ctx->h_stats = nullptr; ctx->h_counters = nullptr;
+            WN_CK(cudaMallocHost((void**)&ctx->h_frame_off, cap * sizeof(uint64_t)));
+            WN_CK(cudaMallocHost((void**)&ctx->h_stats, cap * sizeof(wn_frame_stats)));
+            WN_CK(cudaMallocHost((void**)&ctx->h_counters, cap * sizeof(WnFrameCounters)));
+            ctx->h_frames_cap = cap;
+        }
+    }
+    return WN_OK;
+}
+
+/* Run the pipeline on `nf` device-resident frames; edges land in ctx->d_edges at
+ * offset *edge_base (updated), frame rows at [f0, f0+nf). */
+int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
+             unsigned long long* edge_base)
+{
+    const int N = ctx->n_sites;
+    cudaStream_t st = ctx->st;
+    int rc;
+    if ((rc = ensure_pass_buffers(ctx, nf))) return rc;
+    if (ctx->temp_cap == 0) {
+        if ((rc = dev_ensure(ctx, &ctx->d_temp, &ctx->temp_cap, (size_t)nf * N * 16 + 1024))) return rc;
+    }
+    const int cell_cap = ctx->cell_cap;
+
+    WN_CK(cudaEventRecord(ctx->ev[0], st));
+    wn_launch_bbox(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, st);
+    WN_CK(cudaMemsetAsync(ctx->d_cell_cnt, 0, (size_t)nf * (cell_cap + 1) * sizeof(int), st));
+    wn_launch_bin(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt,
+                  ctx->d_site_cell, ctx->d_site_rank, st);
+    wn_launch_cellscan(nf, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt, st);
+    wn_launch_scatter(d_frames, nf, natoms, ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, N, ctx->hs,
+                      cell_cap, ctx->d_cell_cnt, ctx->d_site_cell, ctx->d_site_rank, ctx->d_spos,
+                      ctx->d_smeta, ctx->d_sdh, st);
+    ctx->tm.launches += 4;
+    WN_CK(cudaEventRecord(ctx->ev[1], st));
+
+    unsigned long long used = 0;
+    for (int attempt = 0;; ++attempt) {
+        WN_CK(cudaMemsetAsync(ctx->d_cursor, 0, sizeof(unsigned long long), st));
+        WN_CK(cudaMemsetAsync(ctx->d_counters, 0, (size_t)nf * sizeof(WnFrameCounters), st));
+        WnEdgeParams p;
+        p.spos = ctx->d_spos; p.smeta = ctx->d_smeta; p.sdh = ctx->d_sdh;
+        p.cell_start = ctx->d_cell_cnt; p.grid = ctx->d_grid;
+        p.temp = ctx->d_temp; p.temp_cursor = ctx->d_cursor; p.temp_cap = ctx->temp_cap;
+        p.row_pos = ctx->d_row_pos; p.row_cnt = ctx->d_row_cnt; p.counters = ctx->d_counters;
+        p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
+        p.typed = ctx->typed;
+        wn_launch_edges(p, nf, st);
+        ctx->tm.launches += 1;
+        WN_CK(cudaGetLastError());
+        WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_cursor, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+        WN_CK(cudaStreamSynchronize(st));
+        used = ctx->h_scalars[0];
+        if (used <= ctx->temp_cap) break;
+        if (used >= (1ull << 32) || attempt > 0)
+            return fail(ctx, WN_ERR_OVERFLOW, "edges of one pass exceed the 32-bit row index space; lower frames_per_pass");
+        if ((rc = dev_ensure(ctx, &ctx->d_temp, &ctx->temp_cap, (size_t)used + (size_t)used / 8))) return rc;
+    }
+    WN_CK(cudaEventRecord(ctx->ev[2], st));
+
+    if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, (size_t)(*edge_base + used), true,
+                         (size_t)*edge_base))) return rc;
+
+    wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off, ctx->d_frame_total, st);
+    wn_launch_frameoff(ctx->d_frame_total, nf, *edge_base, ctx->d_frame_off + f0, st);
+    int n_blocks = 0;
+    wn_launch_copy(ctx->d_temp, ctx->d_row_pos, ctx->d_row_cnt, ctx->d_row_off, ctx->d_frame_off + f0,
+                   nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->d_block_sums, &n_blocks, st);
+    wn_launch_stats(ctx->d_block_sums, n_blocks, ctx->d_frame_total, ctx->d_counters, nf, N,
+                    ctx->d_stats + f0, st);
+    WN_CK(cudaMemcpyAsync(ctx->d_counters_all + f0, ctx->d_counters, (size_t)nf * sizeof(WnFrameCounters),
+                          cudaMemcpyDeviceToDevice, st));
+    ctx->tm.launches += 4;
+    WN_CK(cudaEventRecord(ctx->ev[3], st));
+    WN_CK(cudaGetLastError());
+    WN_CK(cudaStreamSynchronize(st));
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+    ctx->tm.bin_ms += a; ctx->tm.edges_ms += b; ctx->tm.finish_ms += c;
+    ctx->tm.total_ms += a + b + c;
+    ctx->tm.passes += 1;
+    *edge_base += used;
+    return WN_OK;
+}
+
+int batch_common(wn_ctx* ctx, const float* frames, bool host_in, int n_frames, int natoms,
+                 wn_batch_result* out)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (!out || n_frames < 0 || natoms < 0 || (!frames && n_frames > 0 && natoms > 0))
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch: bad argument");
+    if (ctx->n_sites < 0) return fail(ctx, WN_ERR_NO_SITES, "wn_hbond_batch: call wn_set_sites first");
+    if (ctx->max_atom >= natoms && ctx->n_sites > 0)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch: site table refers to atoms beyond natoms");
+    WN_CK(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    ctx->tm = wn_timings{};
+    memset(out, 0, sizeof *out);
+    int rc;
+    if ((rc = ensure_out_frames(ctx, (size_t)n_frames, host_in))) return rc;
+
+    const int N = ctx->n_sites;
+    unsigned long long edge_base = 0;
+    if (N == 0 || n_frames == 0) {
+        /* nothing to search: empty edge lists, zero rows */
+        for (int f = 0; f <= n_frames; ++f) ctx->h_frame_off[f] = 0;
+        for (int f = 0; f < n_frames; ++f) ctx->h_stats[f] = wn_frame_stats{0, 0, 0, 0, 0};
+        if (!host_in && n_frames > 0) {
+            WN_CK(cudaMemsetAsync(ctx->d_frame_off, 0, (size_t)(n_frames + 1) * sizeof(unsigned long long), ctx->st));
+            WN_CK(cudaMemsetAsync(ctx->d_stats, 0, (size_t)n_frames * sizeof(wn_frame_stats), ctx->st));
+            WN_CK(cudaStreamSynchronize(ctx->st));
+        }
+        out->edges = host_in ? ctx->h_edges : ctx->d_edges;
+        out->frame_offsets = host_in ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
+        out->stats = host_in ? ctx->h_stats : ctx->d_stats;
+        out->n_frames = n_frames;
+        out->on_device = host_in ? 0 : 1;
+        return WN_OK;
+    }
+
+    const int fpp = ctx->user_frames_per_pass > 0 ? ctx->user_frames_per_pass : default_frames_per_pass(N);
+    const size_t frame_floats = (size_t)natoms * 3;
+    cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5];
+    for (int f0 = 0; f0 < n_frames; f0 += fpp) {
+        const int nf = std::min(fpp, n_frames - f0);
+        const float* d_in = frames + (size_t)f0 * frame_floats;
+        if (host_in) {
+            if ((rc = dev_ensure(ctx, &ctx->d_stage, &ctx->stage_cap, (size_t)nf * frame_floats))) return rc;
+            WN_CK(cudaEventRecord(e0, ctx->st));
+            WN_CK(cudaMemcpyAsync(ctx->d_stage, d_in, (size_t)nf * frame_floats * sizeof(float),
+                                  cudaMemcpyHostToDevice, ctx->st));
+            WN_CK(cudaEventRecord(e1, ctx->st));
+            d_in = ctx->d_stage;
+        }
+        const unsigned long long before = edge_base;
+        if ((rc = run_pass(ctx, d_in, nf, natoms, (size_t)f0, &edge_base))) return rc;
+        if (host_in) {
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->tm.h2d_ms += ms;
+            /* results of this pass -> pinned host */
+            const size_t need = (size_t)edge_base;
+            if (need > ctx->h_edges_cap) {
+                /* project the whole call from the density seen so far */
+                const double per_frame = (double)edge_base / (double)(f0 + nf);
+                size_t want = (size_t)(per_frame * n_frames * 1.05) + 1024;
+                if ((rc = host_ensure(ctx, &ctx->h_edges, &ctx->h_edges_cap, std::max(want, need), true,
+                                      (size_t)before))) return rc;
+            }
+            WN_CK(cudaEventRecord(e0, ctx->st));
+            if (edge_base > before)
+                WN_CK(cudaMemcpyAsync(ctx->h_edges + before, ctx->d_edges + before,
+                                      (size_t)(edge_base - before) * sizeof(wn_edge), cudaMemcpyDeviceToHost, ctx->st));
+            WN_CK(cudaEventRecord(e1, ctx->st));
+            WN_CK(cudaStreamSynchronize(ctx->st));
+            cudaEventElapsedTime(&ms, e0, e1); ctx->tm.d2h_ms += ms;
+        }
+    }
+    /* small per-frame tables always come back to the host: totals and ties */
+    WN_CK(cudaMemcpyAsync(ctx->h_frame_off, ctx->d_frame_off, (size_t)(n_frames + 1) * sizeof(uint64_t),
+                          cudaMemcpyDeviceToHost, ctx->st));
+    WN_CK(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, (size_t)n_frames * sizeof(wn_frame_stats),
+                          cudaMemcpyDeviceToHost, ctx->st));
+    WN_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters_all, (size_t)n_frames * sizeof(WnFrameCounters),
+                          cudaMemcpyDeviceToHost, ctx->st));
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    if (ctx->h_frame_off[n_frames] != edge_base)
+        return fail(ctx, WN_ERR_CUDA, "internal: edge totals disagree between scan and fused kernel");
+    wn_tie_report ties = {0, 0, 0, 0};
+    unsigned long long evals = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        evals += ctx->h_counters[f].evals;
+        ties.length_equal_cut += ctx->h_counters[f].tie_len;
+        ties.cosine_argmax_equal += ctx->h_counters[f].tie_cos;
+        ties.pos_zero += ctx->h_counters[f].tie_pos0;
+    }
+    out->edges = host_in ? ctx->h_edges : ctx->d_edges;
+    out->frame_offsets = host_in ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
+    out->stats = host_in ? ctx->h_stats : ctx->d_stats;
+    out->n_edges = edge_base;
+    out->n_pair_evals = evals;
+    out->ties = ties;
+    out->n_frames = n_frames;
+    out->on_device = host_in ? 0 : 1;
+    return WN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* wn_version(void) { return "wn_b200 0.1 sm_100a"; }
+
+int wn_create(int device, wn_ctx** out)
+{
+    if (!out) return fail(nullptr, WN_ERR_BAD_ARG, "wn_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, WN_ERR_NO_DEVICE, std::string("wn_create: no CUDA device (") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                    "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, WN_ERR_BAD_ARG, "wn_create: device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, WN_ERR_NO_DEVICE, std::string("wn_create: kernels are built for sm_100a only; device is ") +
+                    prop.name + " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    wn_ctx* ctx = new (std::nothrow) wn_ctx();
+    if (!ctx) return fail(nullptr, WN_ERR_OOM, "wn_create: out of host memory");
+    ctx->device = device;
+    ctx->ep.on2 = 5.5 * 5.5; ctx->ep.off2 = 6.5 * 6.5;
+    ctx->ep.a_on = 0.0; ctx->ep.a_off = 0.25;      /* (theta_off, theta_on): caller-side swap, :59-60 */
+#define WN_CKC(call)                                                            \
+    do {                                                                        \
+        cudaError_t e2_ = (call);                                               \
+        if (e2_ != cudaSuccess) { int rc_ = cuda_fail(nullptr, e2_, #call); delete ctx; return rc_; } \
+    } while (0)
+    WN_CKC(cudaSetDevice(device));
+    WN_CKC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    for (auto& ev : ctx->ev) WN_CKC(cudaEventCreate(&ev));
+    WN_CKC(cudaMallocHost((void**)&ctx->h_scalars, 64 * sizeof(unsigned long long)));
+    WN_CKC(cudaMalloc((void**)&ctx->d_pair_ties, sizeof(unsigned long long)));
+#undef WN_CKC
+    *out = ctx;
+    return WN_OK;
+}
+
+void wn_destroy(wn_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    if (ctx->comm && ctx->nccl_lib) {
+        typedef ncclResult_t (*destroy_t)(ncclComm_t);
+        destroy_t fn = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+        if (fn) fn(ctx->comm);
+    }
+    void* dev[] = {ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, ctx->d_grid, ctx->d_cell_cnt, ctx->d_site_cell,
+                   ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_pos, ctx->d_row_cnt,
+                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_cursor, ctx->d_block_sums,
+                   ctx->d_temp, ctx->d_stage, ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
+                   ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce};
+    for (void* p : dev) if (p) cudaFree(p);
+    void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs};
+    for (void* p : host) if (p) cudaFreeHost(p);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+const char* wn_last_error(const wn_ctx* ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int wn_set_sites(wn_ctx* ctx, int32_t n_sites, const int32_t* site_atom, const int32_t* h_atom,
+                 int32_t hmax, const uint8_t* site_type, int32_t first_limit)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (n_sites < 0 || hmax < 0 || (n_sites > 0 && (!site_atom || !site_type)) ||
+        (n_sites > 0 && hmax > 0 && !h_atom))
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_set_sites: bad argument");
+    if (n_sites >= (1 << 27)) return fail(ctx, WN_ERR_OVERFLOW, "wn_set_sites: more than 2^27-1 sites per frame");
+    WN_CK(cudaSetDevice(ctx->device));
+    /* Statically invalid hydrogens (the site atom itself, SURVEY F8: DH = 0/0 = NaN,
+     * never selected) are dropped here; list positions are kept in the meta word. */
+    int hs = 1, max_atom = -1;
+    bool typed = false;
+    std::vector<uint32_t> meta((size_t)n_sites);
+    std::vector<std::vector<int>> valid((size_t)n_sites);
+    for (int s = 0; s < n_sites; ++s) {
+        if (site_atom[s] < 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_set_sites: negative site atom index");
+        if (site_type[s] > WN_WATER) return fail(ctx, WN_ERR_BAD_ARG, "wn_set_sites: unknown site type");
+        max_atom = std::max(max_atom, site_atom[s]);
+        int nh = 0;
+        bool first0 = false;
+        for (int h = 0; h < hmax; ++h) {
+            const int at = h_atom[(size_t)s * hmax + h];
+            if (at < 0) break;
+            max_atom = std::max(max_atom, at);
+            if (at != site_atom[s]) {
+                if (valid[s].empty() && h == 0) first0 = true;
+                valid[s].push_back(at);
+            }
+            ++nh;
+        }
+        if ((int)valid[s].size() > WN_MAX_VALID_H)
+            return fail(ctx, WN_ERR_BAD_ARG, "wn_set_sites: more than WN_MAX_VALID_H hydrogens on one site");
+        hs = std::max(hs, (int)valid[s].size());
+        meta[s] = (uint32_t)site_type[s] | (nh > 0 ? WN_META_HASH : 0u) | (first0 ? WN_META_FIRST0 : 0u) |
+                  ((uint32_t)valid[s].size() << WN_META_NV_SHIFT);
+        if (site_type[s] != WN_WATER || nh == 0) typed = true;
+    }
+    std::vector<int> hv((size_t)n_sites * hs, -1);
+    for (int s = 0; s < n_sites; ++s)
+        for (size_t v = 0; v < valid[s].size(); ++v) hv[(size_t)s * hs + v] = valid[s][v];
+
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    int rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_site_atom, (size_t)n_sites))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_hv_atom, (size_t)n_sites * hs))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_meta, (size_t)n_sites))) return rc;
+    if (n_sites > 0) {
+        WN_CK(cudaMemcpy(ctx->d_site_atom, site_atom, (size_t)n_sites * sizeof(int), cudaMemcpyHostToDevice));
+        WN_CK(cudaMemcpy(ctx->d_hv_atom, hv.data(), hv.size() * sizeof(int), cudaMemcpyHostToDevice));
+        WN_CK(cudaMemcpy(ctx->d_meta, meta.data(), meta.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    ctx->n_sites = n_sites; ctx->hs = hs; ctx->typed = typed ? 1 : 0; ctx->max_atom = max_atom;
+    ctx->first_limit = first_limit < 0 ? 0 : first_limit;
+    ctx->temp_cap = ctx->temp_cap;   /* buffers are re-sized lazily by the next batch */
+    return WN_OK;
+}
+
+int wn_set_water_sites(wn_ctx* ctx, int32_t n_waters, int32_t first_limit)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (n_waters < 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_set_water_sites: negative count");
+    std::vector<int32_t> sa((size_t)n_waters), ha((size_t)n_waters * 2);
+    std::vector<uint8_t> ty((size_t)n_waters, (uint8_t)WN_WATER);
+    for (int w = 0; w < n_waters; ++w) { sa[w] = 3 * w; ha[2 * w] = 3 * w; ha[2 * w + 1] = 3 * w + 1; }
+    return wn_set_sites(ctx, n_waters, sa.data(), ha.data(), 2, ty.data(), first_limit);
+}
+
+int wn_set_energy_params(wn_ctx* ctx, double r_on, double r_off, double theta_on, double theta_off)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    /* computeEnergy passes (r*r, r_on*r_on, r_off*r_off) to the radial switch and
+     * (cos*cos, theta_off, theta_on) to the angle switch (src/waternetwork.cpp:57-60) */
+    ctx->ep.on2 = r_on * r_on; ctx->ep.off2 = r_off * r_off;
+    ctx->ep.a_on = theta_off; ctx->ep.a_off = theta_on;
+    return WN_OK;
+}
+
+int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (frames_per_pass < 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_set_batch_frames: negative");
+    ctx->user_frames_per_pass = frames_per_pass;
+    return WN_OK;
+}
+
+int wn_hbond_batch(wn_ctx* ctx, const float* frames_host, int32_t n_frames, int32_t natoms,
+                   wn_batch_result* out)
+{
+    return batch_common(ctx, frames_host, true, n_frames, natoms, out);
+}
+
+int wn_hbond_batch_dev(wn_ctx* ctx, const float* frames_dev, int32_t n_frames, int32_t natoms,
+                       wn_batch_result* out)
+{
+    return batch_common(ctx, frames_dev, false, n_frames, natoms, out);
+}
+
+int wn_get_timings(wn_ctx* ctx, wn_timings* out)
+{
+    if (!ctx || !out) return WN_ERR_BAD_ARG;
+    *out = ctx->tm;
+    return WN_OK;
+}
+
+int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
+                  const int32_t** pairs, uint64_t* m, wn_tie_report* ties)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (n < 0 || (n > 0 && !xyz) || !pairs || !m) return fail(ctx, WN_ERR_BAD_ARG, "wn_find_pairs: bad argument");
+    WN_CK(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    *pairs = nullptr; *m = 0;
+    if (ties) *ties = wn_tie_report{0, 0, 0, 0};
+    if (n < 2 || first_limit <= 0) {
+        int rc;
+        if ((rc = host_ensure(ctx, &ctx->h_pairs, &ctx->h_pairs_cap, (size_t)2))) return rc;
+        *pairs = ctx->h_pairs;
+        return WN_OK;
+    }
+    cudaStream_t st = ctx->st;
+    int rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_xyz, &ctx->xyz_cap, (size_t)n * 3))) return rc;
+    if ((size_t)n + 1 > ctx->prow_cap) {
+        WN_CK(cudaStreamSynchronize(st));
+        if ((rc = dev_realloc_plain(ctx, &ctx->d_prow_cnt, (size_t)n + 1))) return rc;
+        if ((rc = dev_realloc_plain(ctx, &ctx->d_prow_off, (size_t)n + 1))) return rc;
+        ctx->prow_cap = (size_t)n + 1;
+    }
+    WN_CK(cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    WN_CK(cudaMemsetAsync(ctx->d_pair_ties, 0, sizeof(unsigned long long), st));
+    wn_launch_pairs_count(ctx->d_xyz, n, first_limit, ctx->d_prow_cnt, ctx->d_pair_ties, st);
+    wn_launch_pairs_scan(ctx->d_prow_cnt, n, ctx->d_prow_off, st);
+    WN_CK(cudaGetLastError());
+    WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_prow_off + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_pair_ties, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaStreamSynchronize(st));
+    const unsigned long long total = ctx->h_scalars[0];
+    if (ties) ties->pair_cutoff_equal = ctx->h_scalars[1];
+    if ((rc = dev_ensure(ctx, &ctx->d_pairs, &ctx->d_pairs_cap, (size_t)total * 2 + 2))) return rc;
+    if ((rc = host_ensure(ctx, &ctx->h_pairs, &ctx->h_pairs_cap, (size_t)total * 2 + 2))) return rc;
+    if (total) {
+        wn_launch_pairs_fill(ctx->d_xyz, n, first_limit, ctx->d_prow_off, ctx->d_pairs, st);
+        WN_CK(cudaGetLastError());
+        WN_CK(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs, (size_t)total * 2 * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, st));
+        WN_CK(cudaStreamSynchronize(st));
+    }
+    *pairs = ctx->h_pairs;
+    *m = total;
+    return WN_OK;
+}
+
+/* ---- plumbing ---- */
+int wn_dev_alloc(wn_ctx* ctx, size_t bytes, void** dev_ptr)
+{
+    if (!ctx || !dev_ptr) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    WN_CK(cudaMalloc(dev_ptr, bytes ? bytes : 1));
+    return WN_OK;
+}
+int wn_dev_free(wn_ctx* ctx, void* dev_ptr)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    WN_CK(cudaFree(dev_ptr));
+    return WN_OK;
+}
+int wn_host_alloc_pinned(wn_ctx* ctx, size_t bytes, void** host_ptr)
+{
+    if (!ctx || !host_ptr) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    WN_CK(cudaMallocHost(host_ptr, bytes ? bytes : 1));
+    return WN_OK;
+}
+int wn_host_free_pinned(wn_ctx* ctx, void* host_ptr)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    WN_CK(cudaFreeHost(host_ptr));
+    return WN_OK;
+}
+int wn_memcpy_d2h(wn_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    WN_CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->st));
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    return WN_OK;
+}
+int wn_memcpy_h2d(wn_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    WN_CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->st));
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    return WN_OK;
+}
+int wn_synth_frames_dev(wn_ctx* ctx, int32_t n_waters, uint64_t seed, int32_t model,
+                        int64_t frame0, int32_t n_frames, float* frames_dev)
+{
+    if (!ctx || n_waters < 0 || n_frames < 0 || (!frames_dev && n_waters > 0 && n_frames > 0))
+        return ctx ? fail(ctx, WN_ERR_BAD_ARG, "wn_synth_frames_dev: bad argument") : WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    wn_launch_synth(n_waters, seed, model, frame0, n_frames, frames_dev, ctx->st);
+    WN_CK(cudaGetLastError());
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    return WN_OK;
+}
+
+/* ---- NCCL statistics reduction ---- */
+static void* nccl_open(std::string* why)
+{
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        void* h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) return h;
+    }
+    if (why) *why = dlerror() ? dlerror() : "libnccl.so.2 not found";
+    return nullptr;
+}
+
+int wn_nccl_unique_id(void* id128)
+{
+    if (!id128) return WN_ERR_BAD_ARG;
+    std::string why;
+    void* lib = nccl_open(&why);
+    if (!lib) return fail(nullptr, WN_ERR_NCCL, "wn_nccl_unique_id: " + why);
+    typedef ncclResult_t (*fn_t)(ncclUniqueId*);
+    fn_t fn = (fn_t)dlsym(lib, "ncclGetUniqueId");
+    if (!fn) return fail(nullptr, WN_ERR_NCCL, "ncclGetUniqueId not found");
+    ncclUniqueId id;
+    if (fn(&id) != ncclSuccess) return fail(nullptr, WN_ERR_NCCL, "ncclGetUniqueId failed");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id128, &id, 128);
+    return WN_OK;
+}
+
+int wn_nccl_init(wn_ctx* ctx, const void* id128, int32_t rank, int32_t nranks)
+{
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    std::string why;
+    if (!ctx->nccl_lib) ctx->nccl_lib = nccl_open(&why);
+    if (!ctx->nccl_lib) return fail(ctx, WN_ERR_NCCL, "wn_nccl_init: " + why);
+    typedef ncclResult_t (*fn_t)(ncclComm_t*, int, ncclUniqueId, int);
+    fn_t fn = (fn_t)dlsym(ctx->nccl_lib, "ncclCommInitRank");
+    if (!fn) return fail(ctx, WN_ERR_NCCL, "ncclCommInitRank not found");
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = fn(&ctx->comm, nranks, id, rank);
+    if (r != ncclSuccess) return fail(ctx, WN_ERR_NCCL, "ncclCommInitRank failed: " + std::to_string((int)r));
+    ctx->nranks = nranks; ctx->rank = rank;
+    return WN_OK;
+}
+
+int wn_stats_reduce(wn_ctx* ctx, wn_frame_stats* stats_host, int64_t n_frames_total)
+{
+    if (!ctx || (!stats_host && n_frames_total > 0) || n_frames_total < 0) return WN_ERR_BAD_ARG;
+    if (!ctx->comm) return fail(ctx, WN_ERR_NCCL, "wn_stats_reduce: call wn_nccl_init first");
+    if (n_frames_total == 0) return WN_OK;
+    WN_CK(cudaSetDevice(ctx->device));
+    const size_t count = (size_t)n_frames_total * (sizeof(wn_frame_stats) / sizeof(double));
+    int rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_reduce, &ctx->reduce_cap, count))) return rc;
+    WN_CK(cudaMemcpyAsync(ctx->d_reduce, stats_host, count * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    typedef ncclResult_t (*fn_t)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    fn_t fn = (fn_t)dlsym(ctx->nccl_lib, "ncclAllReduce");
+    if (!fn) return fail(ctx, WN_ERR_NCCL, "ncclAllReduce not found");
+    ncclResult_t r = fn(ctx->d_reduce, ctx->d_reduce, count, ncclDouble, ncclSum, ctx->comm, ctx->st);
+    if (r != ncclSuccess) return fail(ctx, WN_ERR_NCCL, "ncclAllReduce failed: " + std::to_string((int)r));
+    WN_CK(cudaMemcpyAsync(stats_host, ctx->d_reduce, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    return WN_OK;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,119 @@
+/*
+ * wn_internal.cuh -- shared declarations of the sm_100a kernels and the context.
+ * Not part of the public boundary (that is include/wn_b200.h).
+ */
+#ifndef WN_INTERNAL_CUH
+#define WN_INTERNAL_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "wn_b200.h"
+
+/* ---- per-frame cell grid (open boundary: bounding box of the finite sites) ---- */
+struct WnGrid {
+    double ox, oy, oz;   /* origin (minimum corner)                   */
+    double inv;          /* 1 / cell edge                             */
+    int nx, ny, nz;
+    int ncells;          /* nx*ny*nz <= cell capacity                 */
+};
+
+/* ---- per-frame counters written by the fused kernel ---- */
+struct WnFrameCounters {
+    unsigned long long evals;      /* `if (isedge)` bodies                      */
+    unsigned long long tie_len;    /* (float)dist == 6.5f                       */
+    unsigned long long tie_cos;    /* equal positive cosines in the arg-max     */
+    unsigned long long tie_pos0;   /* arg-max on list index 0                   */
+};
+
+/* ---- site meta word (one per site) ---- */
+#define WN_META_TYPE_MASK 3u
+#define WN_META_HASH      (1u << 2)  /* hydrogen list not empty                       */
+#define WN_META_FIRST0    (1u << 3)  /* first valid hydrogen sits at list position 0  */
+#define WN_META_NV_SHIFT  4          /* number of valid hydrogens, 0..WN_MAX_VALID_H  */
+#define WN_META_NV_MASK   0xFu
+
+/* Edge-length cut of make_edges (src/waternetwork.cpp:204): reject when the float
+ * length in Angstrom is > 6.5.  Any accepted pair has squared distance (nm^2)
+ * <= 0.4225*(1+2.5e-7); the fp32 prefilter and the cell edge carry a margin. */
+#define WN_LEN_CUT_F      6.5f
+#define WN_PREFILTER_D2   (0.4225 * (1.0 + 1.0e-5))
+#define WN_CELL_EDGE      (0.65 * (1.0 + 1.0e-5))
+
+/* Energy parameters in the form the kernels consume (computeEnergy, :49-66). */
+struct WnEnergyParams {
+    double on2, off2;      /* r_on^2, r_off^2 (arguments of the radial switch)   */
+    double a_on, a_off;    /* angle switch slots after the caller-side swap      */
+};
+
+/* temp entry produced by the fused kernel, consumed by the ordered copy */
+struct __align__(16) WnTempEdge {
+    int32_t j;
+    float   length;
+    float   cosine;
+    int32_t pad;
+};
+
+/* ---- fused-path launch parameters ---- */
+struct WnEdgeParams {
+    const float4*   spos;       /* [F][N] sorted: x,y,z, site index bits          */
+    const uint32_t* smeta;      /* [F][N] sorted meta                             */
+    const double*   sdh;        /* [F][N][hs][3] sorted unit D-H vectors          */
+    const int*      cell_start; /* [F][cell_cap+1]                                */
+    const WnGrid*   grid;       /* [F]                                            */
+    WnTempEdge*     temp;       /* [temp_cap]                                     */
+    unsigned long long* temp_cursor;
+    unsigned long long  temp_cap;
+    uint32_t*       row_pos;    /* [F][N] position of the row in temp             */
+    uint32_t*       row_cnt;    /* [F][N] edges owned by the row                  */
+    WnFrameCounters* counters;  /* [F]                                            */
+    int n_sites;
+    int cell_cap;
+    int hs;                     /* valid-hydrogen slots per site                  */
+    int first_limit;
+    int typed;                  /* 0: all sites WATER with hydrogens              */
+};
+
+/* ---- kernel launchers (wn_kernels_*.cu).  All asynchronous on `st`. ---- */
+void wn_launch_bbox(const float* frames, int n_frames, int natoms, const int* site_atom,
+                    int n_sites, int cell_cap, WnGrid* grid, cudaStream_t st);
+void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* site_atom,
+                   int n_sites, int cell_cap, const WnGrid* grid, int* cell_cnt,
+                   int* site_cell, int* site_rank, cudaStream_t st);
+void wn_launch_cellscan(int n_frames, int n_sites, int cell_cap, const WnGrid* grid,
+                        int* cell_cnt, cudaStream_t st);
+void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,
+                       const int* hv_atom, const uint32_t* meta, int n_sites, int hs,
+                       int cell_cap, const int* cell_start, const int* site_cell,
+                       const int* site_rank, float4* spos, uint32_t* smeta, double* sdh,
+                       cudaStream_t st);
+void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st);
+void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
+                       uint32_t* row_off, unsigned long long* frame_total, cudaStream_t st);
+void wn_launch_frameoff(const unsigned long long* frame_total, int n_frames,
+                        unsigned long long base, unsigned long long* frame_off,
+                        cudaStream_t st);
+void wn_launch_copy(const WnTempEdge* temp, const uint32_t* row_pos, const uint32_t* row_cnt,
+                    const uint32_t* row_off, const unsigned long long* frame_off,
+                    int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
+                    unsigned long long edge_cap, double* block_sums, int* n_blocks_out,
+                    cudaStream_t st);
+void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,
+                     const WnFrameCounters* counters, int n_frames, int n_sites,
+                     wn_frame_stats* stats, cudaStream_t st);
+size_t wn_edges_smem_bytes(int hs);
+
+/* brute pair path (wn_kernels_pairs.cu) */
+void wn_launch_pairs_count(const double* xyz, int n, int first_limit, uint32_t* row_cnt,
+                           unsigned long long* ties, cudaStream_t st);
+void wn_launch_pairs_scan(const uint32_t* row_cnt, int n, unsigned long long* row_off,
+                          cudaStream_t st);
+void wn_launch_pairs_fill(const double* xyz, int n, int first_limit,
+                          const unsigned long long* row_off, int32_t* pairs, cudaStream_t st);
+
+/* synthetic frames (wn_synth.cu, compiled with -fmad=false) */
+void wn_launch_synth(int n_waters, uint64_t seed, int model, int64_t frame0, int n_frames,
+                     float* frames, cudaStream_t st);
+
+#endif

