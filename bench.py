@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s and H-bond pair evaluations/s of the fused hydrogen-bond path.
+
+Workload: BASELINE.json configs[2], the configuration the metric is quoted on: a
+periodic-sized 100k-atom box (33,333 TIP3P-like waters, 99,999 atoms), synthetic
+frames (include/wn_synth.h, seed 1234), open boundary as in the reference's
+BruteFindPairs (no PBC, src/brute-find-pairs.cpp:25).  A "step" is one pass of the
+hot path over one batch of --frames-per-step distinct frames; every step reads
+different frames (a step's input, 1.2 MB/frame, is far larger than the 126 MB L2).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework
+  python bench.py --impl reference --steps K --warmup W    # reference CPU path, host cores
+
+Own arm, per rank (one process per GPU, frame-sharded, weak scaling):
+  value  : frames/s with the trajectory shard already resident in HBM
+           (wn_hbond_batch_dev), CUDA-event time on the library's stream, max over ranks
+  e2e    : frames/s through the host-buffer entry point wn_hbond_batch (pinned host
+           frames -> H2D -> kernels -> D2H of edges, offsets, stats), same timing
+  roofline: wn_k_edges (the dominant kernel), algorithmic bytes of SURVEY 8d
+  cpu_baseline (rank 0, N=1): reference sources (oracle/_ref) or oracle port on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_WATERS = 33333
+SEED = 1234
+METRIC = "frames/s (H-bond pair search + energy, 100k-atom water box)"
+
+
+def algorithmic_bytes_per_frame(natoms, edges_per_frame):
+    """read the frame once as delivered, write compact edges + stats."""
+    return 12.0 * natoms + 20.0 * edges_per_frame + 32.0
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smmax, reasons = [], None, set()
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk = float(parts[1]); smmax = float(parts[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:      # timed region shorter than a sample period: use every sample
+            for ts, line in self.lines:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1])); smmax = float(parts[2])
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smmax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- reference (CPU) arm
+def cpu_reference_run(frames_host, threads):
+    """Reference path on the host: brute-find-pairs + make_edges per frame, frames
+    fanned out over `threads` host threads (ctypes releases the GIL).  Uses the
+    reference's own sources (oracle/_ref) when that build is present, else the
+    oracle port.  Returns (seconds, kind, edges_total, evals_total)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import wn_oracle_py as oracle
+    oracle.lib()
+    ref = oracle.ref()
+    kind = "reference" if ref is not None else "port"
+    nf = frames_host.shape[0]
+    n = frames_host.shape[1] // 3
+    sa, ha, ty = oracle.water_site_table(n)
+    results = [None] * nf
+
+    def work(f):
+        if ref is not None:
+            e, npairs = oracle.ref_frame_hbonds_water(frames_host[f])
+            results[f] = (len(e), None)
+        else:
+            e, st, npairs, ev = oracle.frame_hbonds(frames_host[f], sa, ha, ty)
+            results[f] = (len(e), ev)
+
+    t0 = time.perf_counter()
+    pending = list(range(nf))
+    lock = threading.Lock()
+
+    def loop():
+        while True:
+            with lock:
+                if not pending:
+                    return
+                f = pending.pop()
+            work(f)
+
+    ths = [threading.Thread(target=loop) for _ in range(min(threads, nf))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return dt, kind, sum(r[0] for r in results), results
+
+
+def usable_threads():
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    # each in-flight frame holds the 17M-pair list twice (~0.5 GB): bound by memory
+    try:
+        with open("/proc/meminfo") as fh:
+            avail_kb = [int(l.split()[1]) for l in fh if l.startswith("MemAvailable")][0]
+        cores = max(1, min(cores, int(avail_kb / 1e6 / 1.0)))
+    except Exception:
+        pass
+    return cores
+
+
+def host_frames(n_frames, frame0=0):
+    """Synthetic frames on the host for the CPU arms (oracle-side generator)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import wn_oracle_py as oracle
+    box = oracle.synth_box(N_WATERS, seed=SEED)
+    return oracle.synth_frames(box, frame0, n_frames)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = usable_threads()
+    per_step = threads                      # one frame per host thread per step
+    frames = host_frames(per_step)
+    for _ in range(args.warmup):
+        cpu_reference_run(frames[:min(per_step, threads)], threads)
+    t = 0.0
+    kind = "port"
+    for _ in range(args.steps):
+        dt, kind, _, _ = cpu_reference_run(frames, threads)
+        t += dt
+    fps = args.steps * per_step / t
+    sample = "%d frame(s) per step, one per host thread, brute-find-pairs + make_edges" % per_step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: 100k-atom (33,333 TIP3P waters) box, open boundary",
+                   "n_waters": N_WATERS, "natoms": 3 * N_WATERS, "frames_per_step": per_step},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- own arm
+def run_own(args):
+    import wn_pkg
+    capi = wn_pkg.load_capi()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist      # control plane only: barrier + max of timings
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    ctx = capi.Context(local_rank)
+    n_waters, natoms = args.waters, 3 * args.waters
+    F, K, W = args.frames_per_step, args.steps, args.warmup
+    ctx.set_water_sites(n_waters)
+    ctx.set_batch_frames(F)
+
+    if world > 1:
+        ids = [ctx.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.nccl_init(ids[0], rank, world)
+
+    # ---- trajectory shard resident in HBM: (W+K) distinct batches for this rank
+    frame_bytes = natoms * 12
+    n_local = (W + K) * F
+    frames_dev = ctx.dev_alloc(n_local * frame_bytes)
+    frame0 = rank * n_local                    # weak scaling: each rank owns its own frames
+    for s in range(W + K):
+        ctx.synth_frames_dev(n_waters, frame0 + s * F, F, frames_dev + s * F * frame_bytes, seed=SEED)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident leg
+    for s in range(W):
+        ctx.hbond_batch_dev(frames_dev + s * F * frame_bytes, F, natoms)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    edges_total = evals_total = launches = passes = 0
+    edges_ms = bin_ms = finish_ms = 0.0
+    stats_rows = []
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for s in range(W, W + K):
+        out = ctx.hbond_batch_dev(frames_dev + s * F * frame_bytes, F, natoms)
+        edges_total += out["n_edges"]; evals_total += out["n_pair_evals"]
+        tm = ctx.timings()
+        launches += tm["launches"]; passes += tm["passes"]
+        edges_ms += tm["edges_ms"]; bin_ms += tm["bin_ms"]; finish_ms += tm["finish_ms"]
+    dev_ms = ctx.timer_stop()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    barrier()
+    # per-frame statistics of the last step -> NCCL sum over ranks (the only collective)
+    if world > 1:
+        st = np.zeros(world * F, capi.STATS_DTYPE)
+        mine = np.zeros(F, capi.STATS_DTYPE)
+        ctx.d2h(mine, out["stats_dev"])
+        st[rank * F:(rank + 1) * F] = mine
+        ctx.stats_reduce(st)
+        assert np.all(st["num_sites"] == n_waters)
+
+    def allmax(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def allsum(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    dev_ms_max = allmax(dev_ms)
+    frames_all = K * F * world
+    fps = frames_all / (dev_ms_max * 1e-3)
+    evals_all = allsum(float(evals_total))
+    edges_all = allsum(float(edges_total))
+    edges_per_frame = edges_all / frames_all
+
+    # ---- end-to-end leg: pinned host frames -> wn_hbond_batch -> pinned host results
+    ring = min(4, W + K)
+    host_arr, host_ptr = ctx.pinned_array((ring, F, natoms, 3), np.float32)
+    for r in range(ring):
+        ctx.d2h(host_arr[r], frames_dev + r * F * frame_bytes)
+    for s in range(min(W, 2)):
+        ctx.hbond_batch((host_ptr + (s % ring) * F * frame_bytes, F, natoms), copy=False)
+    barrier()
+    ctx.timer_start()
+    e2e_t0 = time.perf_counter()
+    d2h_bytes = 0
+    e2e_launches = 0
+    for s in range(K):
+        res = ctx.hbond_batch((host_ptr + (s % ring) * F * frame_bytes, F, natoms), copy=False)
+        d2h_bytes += res["n_edges"] * 20 + (F + 1) * 8 + F * 40
+        e2e_launches += ctx.timings()["launches"]
+        # the step's result is read on the host: total edge count of the last frame
+        _ = int(res["frame_offsets"][-1])
+    e2e_ms = ctx.timer_stop()
+    e2e_wall = time.perf_counter() - e2e_t0
+    e2e_ms_max = allmax(max(e2e_ms, e2e_wall * 1e3))
+    e2e_fps = frames_all / (e2e_ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (wn_k_edges), this rank
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    bytes_per_launch = algorithmic_bytes_per_frame(natoms, edges_total / (K * F)) * (K * F / max(passes, 1))
+    k_ms = edges_ms / max(passes, 1)
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        if tj.get("n_waters") == n_waters and tj.get("frames_per_launch") == F:
+            traffic = tj.get("wn_k_edges_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "wn_k_edges", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": k_ms,
+                "frames_per_launch": K * F / max(passes, 1),
+                "pipeline_frac": (algorithmic_bytes_per_frame(natoms, edges_per_frame) * fps / world / 1e9) / peak,
+                "stage_ms_per_step": {"bin": bin_ms / K, "edges": edges_ms / K, "finish": finish_ms / K}}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same frames
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = usable_threads()
+        nfr = max(1, min(threads, 64))
+        sample = np.empty((nfr, natoms, 3), np.float32)
+        ctx.d2h(sample, frames_dev)
+        dt, kind, _, _ = cpu_reference_run(sample, threads)
+        cpu = {"value": nfr / dt, "unit": "frames/s", "cores": min(threads, nfr), "kind": kind,
+               "sample": "%d frame(s) of the same 100k-atom workload, one per host thread "
+                         "(brute-find-pairs O(N^2) + make_edges), %.1f s wall" % (nfr, dt)}
+
+    ctx.pinned_free(host_ptr)
+    ctx.dev_free(frames_dev)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: 100k-atom (33,333 TIP3P waters) box, open boundary (reference BruteFindPairs has no PBC)"
+                       if n_waters == N_WATERS else "custom: %d waters" % n_waters,
+                       "n_waters": n_waters, "natoms": natoms, "frames_per_step": F,
+                       "frames_total": frames_all, "seed": SEED,
+                       "l2_policy": "inputs larger than L2: every step reads %d distinct frames (%.0f MB)" % (F, F * frame_bytes / 1e6),
+                       "parallelism": "frame-sharded x%d" % world},
+            "pair_evals_per_s": evals_all / (dev_ms_max * 1e-3),
+            "edges_per_s": edges_all / (dev_ms_max * 1e-3),
+            "pair_evals_per_frame": evals_all / frames_all, "edges_per_frame": edges_per_frame,
+            "wall_ms_per_step": (t1 - t0) * 1e3 / K,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes,
+                    "d2h_bytes_per_step": d2h_bytes / K, "host_ring_batches": ring},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--waters", type=int, default=N_WATERS)
+    ap.add_argument("--frames-per-step", type=int, default=250)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

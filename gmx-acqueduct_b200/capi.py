@@ -28,7 +28,7 @@ SYMBOLS = [
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
-    "wn_get_timings", "wn_nccl_unique_id", "wn_nccl_init", "wn_stats_reduce",
+    "wn_get_timings", "wn_timer_start", "wn_timer_stop", "wn_nccl_unique_id", "wn_nccl_init", "wn_stats_reduce",
 ]
 
 
@@ -96,6 +96,8 @@ def load():
     L.wn_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
     L.wn_synth_frames_dev.argtypes = [vp, i32, u64, i32, i64, i32, vp]
     L.wn_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.wn_timer_start.argtypes = [vp]
+    L.wn_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.wn_nccl_unique_id.argtypes = [vp]
     L.wn_nccl_init.argtypes = [vp, vp, i32, i32]
     L.wn_stats_reduce.argtypes = [vp, vp, i64]
@@ -228,6 +230,14 @@ class Context:
         t = Timings()
         self._ck(self.L.wn_get_timings(self.h, C.byref(t)))
         return t.as_dict()
+
+    def timer_start(self):
+        self._ck(self.L.wn_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.L.wn_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
 
     # ---- plumbing
     def dev_alloc(self, nbytes):

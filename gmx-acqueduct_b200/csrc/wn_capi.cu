@@ -86,7 +86,7 @@ struct wn_ctx {
     unsigned long long* d_pair_ties = nullptr;
 
     /* timing */
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[8] = {};
     wn_timings tm = {};
 
     /* NCCL (loaded lazily) */
@@ -525,7 +525,6 @@ int wn_set_sites(wn_ctx* ctx, int32_t n_sites, const int32_t* site_atom, const i
     }
     ctx->n_sites = n_sites; ctx->hs = hs; ctx->typed = typed ? 1 : 0; ctx->max_atom = max_atom;
     ctx->first_limit = first_limit < 0 ? 0 : first_limit;
-    ctx->temp_cap = ctx->temp_cap;   /* buffers are re-sized lazily by the next batch */
     return WN_OK;
 }
 
@@ -573,6 +572,24 @@ int wn_get_timings(wn_ctx* ctx, wn_timings* out)
 {
     if (!ctx || !out) return WN_ERR_BAD_ARG;
     *out = ctx->tm;
+    return WN_OK;
+}
+
+int wn_timer_start(wn_ctx* ctx)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    WN_CK(cudaEventRecord(ctx->ev[6], ctx->st));
+    return WN_OK;
+}
+
+int wn_timer_stop(wn_ctx* ctx, float* elapsed_ms)
+{
+    if (!ctx || !elapsed_ms) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    WN_CK(cudaEventRecord(ctx->ev[7], ctx->st));
+    WN_CK(cudaEventSynchronize(ctx->ev[7]));
+    WN_CK(cudaEventElapsedTime(elapsed_ms, ctx->ev[6], ctx->ev[7]));
     return WN_OK;
 }
 

@@ -168,6 +168,11 @@ typedef struct wn_timings {
     int32_t passes;        /* internal passes (sub-batches)                     */
 } wn_timings;
 int wn_get_timings(wn_ctx* ctx, wn_timings* out);
+/* A CUDA-event stopwatch on the context's stream (the stream every kernel of this
+ * context is launched on): start records an event, stop records a second one,
+ * synchronises and returns the elapsed device time between them. */
+int wn_timer_start(wn_ctx* ctx);
+int wn_timer_stop(wn_ctx* ctx, float* elapsed_ms);
 
 /* ---- multi-GPU: per-frame statistics reduction (NCCL) ---------------------
  * Frames are sharded across ranks with no data-path exchange; the only

@@ -86,4 +86,49 @@ size_t wnref_make_edges(const int32_t* pairs, size_t m, const double* site_xyz, 
     return hb.size();
 }
 
+/* One frame end to end the way WaterNetwork::analyzeFrame does it for waters
+ * (src/waternetwork.cpp:516-523 widening, :562-575 gather with hydrogens
+ * solventPoints[3*index+i], i < nbHydrogen = 2, :583 find, :590-633 make_edges),
+ * with BruteFindPairs as the finder.  One make_edges call over the whole pair
+ * list (the reference splits it over hardware_concurrency() std::async chunks and
+ * joins in order, which gives the same list).  Used as the CPU baseline. */
+size_t wnref_frame_hbonds_water(const float* frame, int n_waters, wnref_edge* out, size_t cap,
+                                uint64_t* n_pairs)
+{
+    std::vector<Point> solventPoints;
+    solventPoints.reserve(3 * (size_t)n_waters);
+    for (int i = 0; i < 3 * n_waters; ++i)
+        solventPoints.push_back(Point(frame[3 * i], frame[3 * i + 1], frame[3 * i + 2]));
+    std::vector<Point> sitePoints;
+    std::vector<std::vector<Point_ptr>> hydrogenPoints;
+    std::vector<SiteInfo_ptr> siteInfos;
+    for (int index = 0; index < n_waters; ++index) {
+        std::vector<Point_ptr> hydrogens(2);
+        for (unsigned int i = 0; i < 2; i++)
+            hydrogens.at(i) = std::make_shared<Point>(solventPoints.at(3 * index + i));
+        hydrogenPoints.push_back(hydrogens);
+        SiteInfo info;
+        info.type = WATER;
+        info.id = (unsigned)index;
+        info.atmIndex = (unsigned)(3 * index);
+        info.resIndex = (unsigned)index;
+        info.nbHydrogen = 2;
+        siteInfos.push_back(std::make_shared<SiteInfo>(info));
+        sitePoints.push_back(solventPoints.at(3 * index));
+    }
+    BruteFindPairs finder;
+    std::vector<std::pair<int, int>> pairs = finder.find(sitePoints);
+    if (n_pairs) *n_pairs = pairs.size();
+    std::vector<std::pair<int, int>>::iterator b = pairs.begin(), e = pairs.end();
+    std::vector<HydrogenBond> hb = make_edges(b, e, sitePoints, hydrogenPoints, siteInfos);
+    for (size_t k = 0; k < hb.size() && k < cap; ++k) {
+        out[k].i = (int32_t)hb[k].sites.first->id;
+        out[k].j = (int32_t)hb[k].sites.second->id;
+        out[k].energy = (float)hb[k].energy;
+        out[k].length = (float)hb[k].length;
+        out[k].cosine = (float)hb[k].angle;
+    }
+    return hb.size();
+}
+
 } /* extern "C" */

@@ -101,6 +101,8 @@ def ref():
         R.wnref_make_edges.restype = C.c_size_t
         R.wnref_make_edges.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
+        R.wnref_frame_hbonds_water.restype = C.c_size_t
+        R.wnref_frame_hbonds_water.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         _ref = R
     return _ref
 
@@ -221,3 +223,18 @@ def ref_make_edges(pairs, site_xyz, h_xyz, h_off, site_type):
                             site_xyz.shape[0], h_xyz.ctypes.data, h_off.ctypes.data,
                             site_type.ctypes.data, out.ctypes.data)
     return out[:ne].copy()
+
+
+def ref_frame_hbonds_water(frame, cap=None):
+    """Whole-frame reference path for waters (reference sources): edges, n_pairs."""
+    R = ref()
+    frame = np.ascontiguousarray(frame, dtype=np.float32).reshape(-1, 3)
+    n = frame.shape[0] // 3
+    if cap is None:
+        cap = 64 * max(n, 1)
+    out = np.empty(cap, dtype=EDGE_DTYPE)
+    npairs = C.c_uint64(0)
+    ne = R.wnref_frame_hbonds_water(frame.ctypes.data, n, out.ctypes.data, cap, C.byref(npairs))
+    if ne > cap:
+        raise RuntimeError("reference edge capacity overflow")
+    return out[:ne].copy(), int(npairs.value)
