@@ -33,11 +33,12 @@ namespace {
 constexpr int WARPS_PER_CTA = 8;
 constexpr int HC   = 16;     /* home sites per chunk                     */
 constexpr int PCAP = 256;    /* pooled edges per chunk                   */
-constexpr int QCAP = 64;     /* queue: < 32 carried + <= 32 pushed       */
+constexpr int QCAP = 32 + 32 * HC;  /* queue: < 32 carried + one round of pushes */
 constexpr int MAXRUN = 9;
 constexpr unsigned FULL = 0xffffffffu;
 
-struct PoolEntry { int32_t j; int32_t h; float length; float cosine; };
+/* jh = (home row slot << 27) | partner site index (n_sites < 2^27) */
+struct PoolEntry { uint32_t jh; float length; float cosine; };
 
 /* fixed part of the per-warp shared memory */
 struct WarpShared {
@@ -58,7 +59,7 @@ enum { MODE_POOL = 0, MODE_COUNT = 1, MODE_DIRECT = 2 };
 struct ChunkState {
     int pool_len;
     bool overflow;
-    unsigned long long evals, tie_len, tie_cos, tie_pos0;
+    unsigned int evals, tie_len, tie_cos, tie_pos0;
     /* MODE_COUNT / MODE_DIRECT */
     unsigned long long direct_base;
     unsigned int direct_k;
@@ -123,7 +124,10 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, WarpShared& ws, const double*
                 const float cv = -__double2float_rn(
                     __dadd_rn(__dadd_rn(__dmul_rn(bx, ux), __dmul_rn(by, uy)), __dmul_rn(bz, uz)));
                 if (cv > cosmax) {
-                    cosmax = cv; win = true; win0 = false;
+                    /* list index of this hydrogen is nH(first) + its own position: it is
+                     * 0 only when the first site has no hydrogen list at all */
+                    cosmax = cv; win = true;
+                    win0 = (v == 0) && (mb & WN_META_FIRST0) && !(ma & WN_META_HASH);
                 } else if (cosmax > 0.f && cv == cosmax) {
                     t_cos = true;
                 }
@@ -135,16 +139,18 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, WarpShared& ws, const double*
     const unsigned m_cnt = __ballot_sync(FULL, counted);
     const unsigned m_edge = __ballot_sync(FULL, edge);
     cs.evals += __popc(m_cnt);
-    cs.tie_len += __popc(__ballot_sync(FULL, t_len));
-    cs.tie_cos += __popc(__ballot_sync(FULL, t_cos));
-    cs.tie_pos0 += __popc(__ballot_sync(FULL, t_pos0));
+    if (__any_sync(FULL, t_len || t_cos || t_pos0)) {          /* rare */
+        cs.tie_len += __popc(__ballot_sync(FULL, t_len));
+        cs.tie_cos += __popc(__ballot_sync(FULL, t_cos));
+        cs.tie_pos0 += __popc(__ballot_sync(FULL, t_pos0));
+    }
     const int ne = __popc(m_edge);
     if (ne == 0) return;
     const int k = __popc(m_edge & ((1u << lane) - 1u));
     if (mode == MODE_POOL) {
         if (cs.pool_len + ne > PCAP) { cs.overflow = true; return; }
         if (edge) {
-            PoolEntry e; e.j = jidx; e.h = h; e.length = len_f; e.cosine = cosmax;
+            PoolEntry e; e.jh = ((uint32_t)h << 27) | (uint32_t)jidx; e.length = len_f; e.cosine = cosmax;
             ws.pool[cs.pool_len + k] = e;
             atomicAdd(&ws.cnt[h], 1);
         }
@@ -169,15 +175,21 @@ __device__ __forceinline__ void
 wn_sweep(const WnEdgeParams& p, size_t fbase, WarpShared& ws, double* hdh, int hb, int hc,
          int n_runs, int total, int mode, ChunkState& cs, int lane)
 {
-    /* stage the home sites */
+    /* stage the home sites; pad the chunk to a multiple of 4 with unreachable dummies */
+    const int hc4 = (hc + 3) & ~3;
     __syncwarp();
-    if (lane < hc) {
-        float4 a = __ldg(p.spos + fbase + hb + lane);
-        ws.hrow[lane] = __float_as_int(a.w);
-        /* rows >= first_limit own nothing: an index no candidate can exceed */
-        if (__float_as_int(a.w) >= p.first_limit) a.w = __int_as_float(0x7fffffff);
-        ws.hpos[lane] = a;
-        ws.hmeta[lane] = __ldg(p.smeta + fbase + hb + lane);
+    if (lane < hc4) {
+        float4 a = make_float4(1.0e30f, 1.0e30f, 1.0e30f, __int_as_float(0x7fffffff));
+        uint32_t m = 0;
+        int row = -1;
+        if (lane < hc) {
+            a = __ldg(p.spos + fbase + hb + lane);
+            row = __float_as_int(a.w);
+            /* rows >= first_limit own nothing: an index no candidate can exceed */
+            if (row >= p.first_limit) a.w = __int_as_float(0x7fffffff);
+            m = __ldg(p.smeta + fbase + hb + lane);
+        }
+        ws.hpos[lane] = a; ws.hrow[lane] = row; ws.hmeta[lane] = m;
     }
     if (lane < HC) { ws.cnt[lane] = 0; ws.fill[lane] = 0; }
     for (int t = lane; t < hc * p.hs * 3; t += 32)
@@ -186,48 +198,69 @@ wn_sweep(const WnEdgeParams& p, size_t fbase, WarpShared& ws, double* hdh, int h
 
     const float tf = (float)WN_PREFILTER_D2;
     int qlen = 0;
+    int run = 0;
     const int rounds = (total + 31) >> 5;
     for (int r = 0; r < rounds; ++r) {
         const int v = r * 32 + lane;
-        float cx = 1.0e30f, cy = 1.0e30f, cz = 1.0e30f;
+        float cx = -1.0e30f, cy = -1.0e30f, cz = -1.0e30f;
         int cj = -1;
         uint32_t code_c = 0, cm = 0;
         if (v < total) {
-            int run = 0;
-#pragma unroll
-            for (int q = 1; q < MAXRUN; ++q)
-                if (q < n_runs && v >= ws.run_pref[q]) run = q;
+            while (run + 1 < n_runs && v >= ws.run_pref[run + 1]) ++run;
             const int c = ws.run_start[run] + (v - ws.run_pref[run]);
             const float4 b4 = __ldg(p.spos + fbase + c);
             cx = b4.x; cy = b4.y; cz = b4.z; cj = __float_as_int(b4.w);
             code_c = (uint32_t)c;
             if (TYPED) cm = __ldg(p.smeta + fbase + c);
         }
-        for (int h = 0; h < hc; ++h) {
-            const float4 a4 = ws.hpos[h];
-            const float dx = a4.x - cx, dy = a4.y - cy, dz = a4.z - cz;
-            const float d2 = dx * dx + dy * dy + dz * dz;
-            bool pass = (d2 <= tf) && (cj > __float_as_int(a4.w));
-            if (TYPED) {
-                /* type rule (:199-203) and the no-hydrogen rule (:205-208) */
-                const uint32_t am = ws.hmeta[h];
-                const uint32_t ta = am & WN_META_TYPE_MASK, tb = cm & WN_META_TYPE_MASK;
-                const bool typ = (ta != tb) || (ta == WN_WATER && tb == WN_WATER);
-                const bool anyh = ((am | cm) & WN_META_HASH) != 0;
-                pass = pass && typ && anyh;
-            }
-            const unsigned m = __ballot_sync(FULL, pass);
-            if (m) {
-                if (pass) ws.queue[qlen + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)h << 27) | code_c;
-                qlen += __popc(m);
-                if (qlen >= 32) {
-                    __syncwarp();
-                    wn_eval_batch<TYPED>(p, fbase, ws, hdh, qlen - 32, 32, mode, cs, lane);
-                    qlen -= 32;
-                    __syncwarp();
-                    if (cs.overflow) return;
+        /* lane-private hit mask: bit h = home row h is a candidate partner */
+        uint32_t hits = 0;
+#pragma unroll
+        for (int g = 0; g < HC / 4; ++g) {
+            if (g * 4 < hc4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int h = g * 4 + u;
+                    const float4 a4 = ws.hpos[h];
+                    const float dx = a4.x - cx, dy = a4.y - cy, dz = a4.z - cz;
+                    const float d2 = dx * dx + dy * dy + dz * dz;
+                    bool pass = (d2 <= tf) && (cj > __float_as_int(a4.w));
+                    if (TYPED) {
+                        /* type rule (:199-203) and the no-hydrogen rule (:205-208) */
+                        const uint32_t am = ws.hmeta[h];
+                        const uint32_t ta = am & WN_META_TYPE_MASK, tb = cm & WN_META_TYPE_MASK;
+                        const bool typ = (ta != tb) || (ta == WN_WATER && tb == WN_WATER);
+                        const bool anyh = ((am | cm) & WN_META_HASH) != 0;
+                        pass = pass && typ && anyh;
+                    }
+                    if (pass) hits |= (1u << h);
                 }
             }
+        }
+        /* warp scan of the hit counts -> dense queue positions */
+        const int cnt = __popc(hits);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int tot = __shfl_sync(FULL, inc, 31);
+        if (tot) {
+            int pos = qlen + inc - cnt;
+            while (hits) {
+                const int h = __ffs(hits) - 1;
+                hits &= hits - 1;
+                ws.queue[pos++] = ((uint32_t)h << 27) | code_c;
+            }
+            qlen += tot;
+            __syncwarp();
+            while (qlen >= 32) {
+                wn_eval_batch<TYPED>(p, fbase, ws, hdh, qlen - 32, 32, mode, cs, lane);
+                qlen -= 32;
+                if (cs.overflow) return;
+            }
+            __syncwarp();
         }
     }
     if (qlen > 0) {
@@ -262,10 +295,11 @@ wn_commit_pool(const WnEdgeParams& p, size_t fbase, WarpShared& ws, int hc, cons
     __syncwarp();
     for (int e = lane; e < total; e += 32) {
         const PoolEntry pe = ws.pool[e];
-        const int k = atomicAdd(&ws.fill[pe.h], 1);
-        const unsigned long long pos = base + (unsigned long long)(ws.rbase[pe.h] + k);
+        const int ph = (int)(pe.jh >> 27);
+        const int k = atomicAdd(&ws.fill[ph], 1);
+        const unsigned long long pos = base + (unsigned long long)(ws.rbase[ph] + k);
         if (pos < p.temp_cap) {
-            WnTempEdge t; t.j = pe.j; t.length = pe.length; t.cosine = pe.cosine; t.pad = 0;
+            WnTempEdge t; t.j = (int32_t)(pe.jh & 0x07ffffffu); t.length = pe.length; t.cosine = pe.cosine; t.pad = 0;
             p.temp[pos] = t;
         }
     }
@@ -273,7 +307,7 @@ wn_commit_pool(const WnEdgeParams& p, size_t fbase, WarpShared& ws, int hc, cons
 }
 
 template <bool TYPED>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 wn_k_edges(const WnEdgeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -142,7 +142,11 @@ wn_k_frameoff(const unsigned long long* __restrict__ frame_total, int n_frames,
     for (int i = b; i < e; ++i) { frame_off[i] = run; run += frame_total[i]; }
 }
 
-/* ---- ordered copy: thread per row ---- */
+/* ---- ordered copy: one warp per 32 consecutive rows, one lane per edge ----
+ * The 32 rows of a warp are contiguous in the final list, so the warp's output is
+ * one contiguous span: lane e of a chunk takes the e-th temp entry of the span
+ * (row found by a shuffle binary search over the row prefix), ranks it inside its
+ * row by j, evaluates the energy and stores it at span_base + row_prefix + rank. */
 __global__ void __launch_bounds__(COPY_THREADS)
 wn_k_copy(const WnTempEdge* __restrict__ temp, const uint32_t* __restrict__ row_pos,
           const uint32_t* __restrict__ row_cnt, const uint32_t* __restrict__ row_off,
@@ -150,39 +154,63 @@ wn_k_copy(const WnTempEdge* __restrict__ temp, const uint32_t* __restrict__ row_
           wn_edge* __restrict__ edges, unsigned long long edge_cap, unsigned long long edge_base,
           double* __restrict__ block_sums)
 {
+    constexpr unsigned FULL = 0xffffffffu;
     const int f = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t o = (size_t)f * n_sites + (row < n_sites ? row : 0);
+    const uint32_t cnt = row < n_sites ? row_cnt[o] : 0u;
+    const uint32_t pos = row < n_sites ? row_pos[o] : 0u;
+    const uint32_t off = row < n_sites ? row_off[o] : 0u;
+    /* exclusive prefix of the row lengths inside the warp */
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, inc, s);
+        if (lane >= s) inc += t;
+    }
+    const uint32_t pre = inc - cnt;
+    const uint32_t total = __shfl_sync(FULL, inc, 31);
+    /* frame_off carries the offset of this pass inside the call's edge array */
+    const unsigned long long span = frame_off[f] - edge_base + __shfl_sync(FULL, off, 0);
     double sum = 0.0;
-    if (i < n_sites) {
-        const size_t o = (size_t)f * n_sites + i;
-        const uint32_t cnt = row_cnt[o];
-        if (cnt) {
-            const WnTempEdge* row = temp + row_pos[o];
-            /* frame_off carries the offset of this pass inside the call's edge array */
-            const unsigned long long dst0 = frame_off[f] - edge_base + row_off[o];
-            if (dst0 + cnt <= edge_cap) {
-                for (uint32_t e = 0; e < cnt; ++e) {
-                    const WnTempEdge t = row[e];
-                    uint32_t rank = 0;
-                    for (uint32_t k = 0; k < cnt; ++k) rank += (row[k].j < t.j) ? 1u : 0u;
-                    wn_edge out;
-                    out.i = i; out.j = t.j;
-                    /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
-                    out.energy = __double2float_rn(wn_compute_energy((double)t.length, (double)t.cosine, ep));
-                    out.length = t.length;
-                    out.cosine = t.cosine;
-                    edges[dst0 + rank] = out;
-                }
-                /* row sum in j order (own writes, program order) -> deterministic */
-                for (uint32_t e = 0; e < cnt; ++e) sum += (double)edges[dst0 + e].energy;
+    if (total && span + total <= edge_cap) {
+        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+            const uint32_t e = min(e0 + lane, total - 1);
+            /* largest r with pre[r] <= e  (pre is non-decreasing over lanes) */
+            int r = 0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const uint32_t t = __shfl_sync(FULL, pre, r + s);
+                if (t <= e) r += s;
+            }
+            const uint32_t rpre = __shfl_sync(FULL, pre, r);
+            const uint32_t rcnt = __shfl_sync(FULL, cnt, r);
+            const uint32_t rpos = __shfl_sync(FULL, pos, r);
+            if (e0 + lane < total) {
+                const WnTempEdge* rowp = temp + rpos;
+                const WnTempEdge t = rowp[e - rpre];
+                uint32_t rank = 0;
+                for (uint32_t k = 0; k < rcnt; ++k) rank += (rowp[k].j < t.j) ? 1u : 0u;
+                wn_edge out;
+                out.i = blockIdx.x * blockDim.x + warp * 32 + r;
+                out.j = t.j;
+                /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
+                out.energy = __double2float_rn(wn_compute_energy((double)t.length, (double)t.cosine, ep));
+                out.length = t.length;
+                out.cosine = t.cosine;
+                edges[span + rpre + rank] = out;
             }
         }
+        /* energies in final order (own warp's writes, ordered by the barrier):
+         * the summation tree does not depend on arrival order -> deterministic */
+        __syncwarp();
+        for (uint32_t e = lane; e < total; e += 32) sum += (double)edges[span + e].energy;
     }
     /* fixed-tree block reduction */
     __shared__ double s_sum[COPY_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_down_sync(FULL, sum, s);
     if (lane == 0) s_sum[warp] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
