@@ -160,11 +160,11 @@ def usable_threads():
     return cores
 
 
-def host_frames(n_frames, frame0=0):
+def host_frames(n_frames, n_waters, frame0=0):
     """Synthetic frames on the host for the CPU arms (oracle-side generator)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import wn_oracle_py as oracle
-    box = oracle.synth_box(N_WATERS, seed=SEED)
+    box = oracle.synth_box(n_waters, seed=SEED)
     return oracle.synth_frames(box, frame0, n_frames)
 
 
@@ -174,7 +174,7 @@ def run_reference(args):
         return 0
     threads = usable_threads()
     per_step = threads                      # one frame per host thread per step
-    frames = host_frames(per_step)
+    frames = host_frames(per_step, args.waters)
     for _ in range(args.warmup):
         cpu_reference_run(frames[:min(per_step, threads)], threads)
     t = 0.0
@@ -189,8 +189,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2]: 100k-atom (33,333 TIP3P waters) box, open boundary",
-                   "n_waters": N_WATERS, "natoms": 3 * N_WATERS, "frames_per_step": per_step},
+        "config": {"workload": "configs[2]: 100k-atom (33,333 TIP3P waters) box, open boundary (reference BruteFindPairs has no PBC)"
+                   if args.waters == N_WATERS else "custom: %d waters" % args.waters,
+                   "n_waters": args.waters, "natoms": 3 * args.waters, "frames_per_step": per_step,
+                   "seed": SEED},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -1,0 +1,137 @@
+"""CPU tests (-m "not gpu") of the boundary and the host logic: the C-ABI library
+loads and exports every declared symbol, fails loudly without a GPU (no CPU
+fallback), frame sharding and the statistics reduction pattern (gloo, world 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol(capi):
+    import __graft_entry__ as g
+    g.build()
+    L = capi.load()
+    header = open(os.path.join(ROOT, "include", "wn_b200.h")).read()
+    declared = set(re.findall(r"\b(wn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"wn_ctx"}
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.wn_version().decode().endswith("sm_100a")
+
+
+def test_struct_layouts_match_header(capi):
+    assert ctypes.sizeof(capi.TieReport) == 32
+    assert ctypes.sizeof(capi.BatchResult) == 8 * 3 + 8 * 2 + 32 + 8
+    assert capi.EDGE_DTYPE.itemsize == 20 and capi.STATS_DTYPE.itemsize == 40
+    assert ctypes.sizeof(capi.Timings) == 32
+
+
+def test_kernels_are_sm_100a_only():
+    """The shipped object holds sm_100a SASS and nothing else (no multi-arch dispatch)."""
+    lib = os.path.join(ROOT, "gmx-acqueduct_b200", "libwn_b200.so")
+    out = subprocess.run(["cuobjdump", "--list-elf", lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, out
+
+
+def test_no_cpu_fallback_without_gpu(capi):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(capi.WnError) as ei:
+        capi.Context(0)
+    assert ei.value.code == 7 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under gmx-acqueduct_b200/ or include/ may reference oracle/."""
+    bad = []
+    for base in ("gmx-acqueduct_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".o", ".so", ".pyc")):
+                    continue
+                txt = open(os.path.join(dp, fn), errors="ignore").read()
+                if re.search(r"wn_oracle|wno_|oracle/|libwn_ref", txt):
+                    bad.append(os.path.join(dp, fn))
+    assert not bad, bad
+
+
+def test_shard_frames_partition(capi):
+    for F in (0, 1, 7, 10000, 12345):
+        for G in (1, 2, 3, 4, 8):
+            blocks = [capi.shard_frames(F, r, G) for r in range(G)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == F
+            for (a0, a1), (b0, b1) in zip(blocks, blocks[1:]):
+                assert a1 == b0 and a0 <= a1
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import wn_pkg, wn_oracle_py as o
+capi = wn_pkg.load_capi()
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+F, n = 7, 40
+lo, hi = capi.shard_frames(F, rank, world)
+box = o.synth_box(n)
+sa, ha, ty = o.water_site_table(n)
+stats = np.zeros(F, capi.STATS_DTYPE)
+edges = []
+for f in range(lo, hi):                       # this rank's shard, computed by the oracle (CPU stand-in)
+    e, st, npairs, ev = o.frame_hbonds(o.synth_frames(box, f, 1)[0], sa, ha, ty)
+    stats[f] = (st[0], st[1], st[2], st[3], ev)
+    edges.append(e)
+# the reduction pattern of wn_stats_reduce: zero-padded [F][5] fp64, SUM over ranks
+t = torch.from_numpy(stats.view(np.float64).reshape(F, 5).copy())
+dist.all_reduce(t, op=dist.ReduceOp.SUM)
+full = t.numpy()
+if rank == 0:
+    want = np.zeros((F, 5))
+    for f in range(F):
+        e, st, npairs, ev = o.frame_hbonds(o.synth_frames(box, f, 1)[0], sa, ha, ty)
+        want[f] = (st[0], st[1], st[2], st[3], ev)
+    assert np.array_equal(full, want), (full, want)   # each row owned by exactly one rank: exact
+    print("GLOO_OK")
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_frame_sharding_and_stats_reduction_world2_gloo(tmp_path, oracle):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_bench_reference_arm_contract(oracle):
+    """`bench.py --impl reference` prints one JSON line with the required keys (tiny run)."""
+    import json
+    env = dict(os.environ, WN_BENCH_REF_WATERS="300")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--waters", "300"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
