@@ -1,0 +1,122 @@
+// hydrogen-bond-edges.cpp -- HydrogenBondEdges and FrameBatcher over the C ABI
+// (see include/hydrogen-bond-edges.hpp).
+#include "hydrogen-bond-edges.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+namespace {
+[[noreturn]] void raise(const char* what, int rc, const wn_ctx* ctx)
+{
+    throw std::runtime_error(std::string(what) + " failed (status " + std::to_string(rc) + "): " +
+                             wn_last_error(ctx));
+}
+}  // namespace
+
+HydrogenBondEdges::HydrogenBondEdges(int device)
+    : ctx_(nullptr), r_on_(5.5), r_off_(6.5), a_on_(0.25), a_off_(0.0)
+{
+    const int rc = wn_create(device, &ctx_);
+    if (rc != WN_OK) raise("HydrogenBondEdges: wn_create", rc, nullptr);
+}
+
+HydrogenBondEdges::~HydrogenBondEdges() { wn_destroy(ctx_); }
+
+void HydrogenBondEdges::pushParams()
+{
+    const int rc = wn_set_energy_params(ctx_, r_on_, r_off_, a_on_, a_off_);
+    if (rc != WN_OK) raise("HydrogenBondEdges: wn_set_energy_params", rc, ctx_);
+}
+
+void HydrogenBondEdges::setRadiusShift(float r_on, float r_off)
+{
+    r_on_ = r_on; r_off_ = r_off;
+    pushParams();
+}
+
+void HydrogenBondEdges::setAngleShift(float a_on, float a_off)
+{
+    a_on_ = a_on; a_off_ = a_off;
+    pushParams();
+}
+
+void HydrogenBondEdges::setSites(const std::vector<SiteInfo>& sites,
+                                 const std::vector<std::vector<int>>& hydrogens, int first_limit)
+{
+    if (sites.size() != hydrogens.size())
+        throw std::invalid_argument("HydrogenBondEdges::setSites: sites and hydrogens differ in length");
+    const int32_t n = (int32_t)sites.size();
+    size_t hmax = 1;
+    for (const auto& h : hydrogens) hmax = std::max(hmax, h.size());
+    std::vector<int32_t> site_atom((size_t)n), h_atom((size_t)n * hmax, -1);
+    std::vector<uint8_t> type((size_t)n);
+    for (int32_t s = 0; s < n; ++s) {
+        site_atom[s] = (int32_t)sites[s].atmIndex;
+        type[s] = (uint8_t)sites[s].type;
+        for (size_t k = 0; k < hydrogens[s].size(); ++k) h_atom[(size_t)s * hmax + k] = hydrogens[s][k];
+    }
+    const int rc = wn_set_sites(ctx_, n, site_atom.data(), h_atom.data(), (int32_t)hmax, type.data(),
+                                first_limit < 0 ? n : first_limit);
+    if (rc != WN_OK) raise("HydrogenBondEdges::setSites: wn_set_sites", rc, ctx_);
+}
+
+void HydrogenBondEdges::setWaterSites(int n_waters, int first_limit)
+{
+    const int rc = wn_set_water_sites(ctx_, n_waters, first_limit < 0 ? n_waters : first_limit);
+    if (rc != WN_OK) raise("HydrogenBondEdges::setWaterSites: wn_set_water_sites", rc, ctx_);
+}
+
+HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, int n_frames, int natoms)
+{
+    wn_batch_result r;
+    const int rc = wn_hbond_batch(ctx_, frames, n_frames, natoms, &r);
+    if (rc != WN_OK) raise("HydrogenBondEdges::calculate: wn_hbond_batch", rc, ctx_);
+    HydrogenBondBatch b;
+    b.edges = r.edges; b.offsets = r.frame_offsets; b.stats = r.stats;
+    b.n_frames = r.n_frames; b.n_edges = r.n_edges; b.n_pair_evals = r.n_pair_evals; b.ties = r.ties;
+    return b;
+}
+
+std::vector<HydrogenBond> HydrogenBondEdges::toHydrogenBonds(const HydrogenBondBatch& batch, int frame,
+                                                             const std::vector<SiteInfo_ptr>& sites)
+{
+    std::vector<HydrogenBond> out;
+    if (frame < 0 || frame >= batch.n_frames) throw std::out_of_range("toHydrogenBonds: frame");
+    out.reserve((size_t)(batch.offsets[frame + 1] - batch.offsets[frame]));
+    for (uint64_t k = batch.offsets[frame]; k < batch.offsets[frame + 1]; ++k) {
+        const wn_edge& e = batch.edges[k];
+        out.push_back(HydrogenBond{SiteInfoPair(sites.at(e.i), sites.at(e.j)), FORWARD,
+                                   (double)e.length, (double)e.cosine, (double)e.energy});
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------- FrameBatcher
+FrameBatcher::FrameBatcher(HydrogenBondEdges& engine, int natoms, int batch_frames, Sink sink)
+    : engine_(engine), natoms_(natoms), batch_frames_(std::max(batch_frames, 1)), sink_(sink),
+      frames_done_(0)
+{
+    buf_.reserve((size_t)batch_frames_ * natoms_ * 3);
+}
+
+void FrameBatcher::push(int frnr, const float* xyz)
+{
+    buf_.insert(buf_.end(), xyz, xyz + (size_t)natoms_ * 3);
+    frnr_.push_back(frnr);
+    if ((int)frnr_.size() >= batch_frames_) flush();
+}
+
+void FrameBatcher::finish() { flush(); }
+
+void FrameBatcher::flush()
+{
+    if (frnr_.empty()) return;
+    const HydrogenBondBatch b = engine_.calculate(buf_.data(), (int)frnr_.size(), natoms_);
+    for (int f = 0; f < b.n_frames; ++f)
+        sink_(frnr_[f], b.edges + b.offsets[f], (size_t)(b.offsets[f + 1] - b.offsets[f]), b.stats[f]);
+    frames_done_ += (uint64_t)b.n_frames;
+    buf_.clear();
+    frnr_.clear();
+}

@@ -1,7 +1,7 @@
 /*
  * wn_b200.h -- C ABI of the B200-native hydrogen-bond pair-search + energy path.
  *
- * This is the drop-in boundary.  The C++ host classes in include/*.hpp
+ * This is the drop-in boundary.  The C++ host classes under include/ (.hpp)
  * (CudaFindPairs, HydrogenBondEdges, FrameBatcher) are thin wrappers over the
  * entry points below; a maintainer of the reference binds the same entry points
  * from WaterNetwork::analyzeFrame.  Plain pointers and

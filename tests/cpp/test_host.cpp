@@ -1,0 +1,98 @@
+// test_host.cpp -- the C++ host mirror on a GPU, written like the reference's caller:
+// a FindPairs pointer that happens to be a CudaFindPairs, and a frame loop that
+// pushes frames into the batcher the way analyzeFrame would.  Checked against an
+// O(N^2) loop in this file (for pairs) and against self-consistency (batched ==
+// unbatched); bit-exact parity with the oracle is covered by the pytest suite.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <random>
+#include <stdexcept>
+
+#include "cuda-find-pairs.hpp"
+#include "hydrogen-bond-edges.hpp"
+
+#define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "CHECK failed: %s (%s:%d)\n", #c, __FILE__, __LINE__); return 1; } } while (0)
+
+int main()
+{
+    try {
+        std::mt19937 rng(7);
+        std::uniform_real_distribution<float> u(0.f, 3.f);
+        // ---- FindPairs drop-in
+        std::shared_ptr<FindPairs> mp_ = std::make_shared<CudaFindPairs>(0);
+        std::vector<Point> pts;
+        for (int i = 0; i < 500; ++i) pts.push_back(Point(u(rng), u(rng), u(rng)));
+        std::vector<Point> before = pts;
+        std::vector<std::pair<int, int>> pairs = mp_->find(pts);
+        std::vector<std::pair<int, int>> want;
+        for (unsigned i = 0; i < pts.size(); ++i)
+            for (unsigned j = i + 1; j < pts.size(); ++j) {
+                const double dx = pts[i].x() - pts[j].x(), dy = pts[i].y() - pts[j].y(), dz = pts[i].z() - pts[j].z();
+                if (10.0 * (dx * dx + dy * dy + dz * dz) < 42.25) want.push_back(std::make_pair((int)i, (int)j));
+            }
+        CHECK(pairs == want);
+        for (size_t i = 0; i < pts.size(); ++i) CHECK(pts[i].x() == before[i].x());   // input not reordered
+        std::vector<Point> none;
+        CHECK(mp_->find(none).empty());
+
+        // ---- batched edges: FrameBatcher(3 per batch) == one calculate() over all frames
+        const int n_waters = 300, natoms = 900, n_frames = 7;
+        std::vector<float> frames((size_t)n_frames * natoms * 3);
+        std::uniform_real_distribution<float> ub(0.f, 2.1f), uh(-0.06f, 0.06f);
+        for (int f = 0; f < n_frames; ++f)
+            for (int w = 0; w < n_waters; ++w) {
+                float* p = &frames[((size_t)f * natoms + 3 * w) * 3];
+                for (int c = 0; c < 3; ++c) { p[c] = ub(rng); p[3 + c] = p[c] + uh(rng); p[6 + c] = p[c] + uh(rng); }
+            }
+        HydrogenBondEdges hb(0);
+        hb.setRadiusShift(5.5f, 6.5f);
+        hb.setAngleShift(0.25f, 0.0f);
+        hb.setWaterSites(n_waters);
+        HydrogenBondBatch all = hb.calculate(frames.data(), n_frames, natoms);
+        CHECK(all.n_frames == n_frames && all.n_edges > 0);
+        std::vector<wn_edge> ref_edges(all.edges, all.edges + all.n_edges);
+        std::vector<uint64_t> ref_off(all.offsets, all.offsets + n_frames + 1);
+        std::vector<wn_edge> got;
+        std::vector<int> order;
+        FrameBatcher batcher(hb, natoms, 3, [&](int frnr, const wn_edge* e, size_t n, const wn_frame_stats& st) {
+            order.push_back(frnr);
+            if (st.num_edges != (double)n || st.num_sites != n_waters) throw std::runtime_error("stats mismatch");
+            got.insert(got.end(), e, e + n);
+        });
+        for (int f = 0; f < n_frames; ++f) batcher.push(100 + f, &frames[(size_t)f * natoms * 3]);
+        batcher.finish();
+        CHECK(batcher.framesDone() == (uint64_t)n_frames);
+        CHECK(order.size() == (size_t)n_frames);
+        for (int f = 0; f < n_frames; ++f) CHECK(order[f] == 100 + f);
+        CHECK(got.size() == ref_edges.size());
+        for (size_t k = 0; k < got.size(); ++k)
+            CHECK(got[k].i == ref_edges[k].i && got[k].j == ref_edges[k].j && got[k].energy == ref_edges[k].energy &&
+                  got[k].length == ref_edges[k].length && got[k].cosine == ref_edges[k].cosine);
+        // lexicographic order inside a frame
+        for (int f = 0; f < n_frames; ++f)
+            for (uint64_t k = ref_off[f] + 1; k < ref_off[f + 1]; ++k)
+                CHECK(ref_edges[k - 1].i < ref_edges[k].i ||
+                      (ref_edges[k - 1].i == ref_edges[k].i && ref_edges[k - 1].j < ref_edges[k].j));
+        // the reference's container type
+        std::vector<SiteInfo_ptr> infos;
+        for (int w = 0; w < n_waters; ++w) {
+            SiteInfo s; s.type = WATER; s.id = (unsigned)(w + 1); s.atmIndex = 3 * w; s.resIndex = w; s.nbHydrogen = 2;
+            infos.push_back(std::make_shared<SiteInfo>(s));
+        }
+        HydrogenBondBatch again = hb.calculate(frames.data(), 1, natoms);
+        std::vector<HydrogenBond> hbs = HydrogenBondEdges::toHydrogenBonds(again, 0, infos);
+        CHECK(hbs.size() == ref_off[1] && hbs[0].direction == FORWARD);
+        // error behaviour: no exception escapes the C ABI; the C++ layer throws
+        bool threw = false;
+        try { hb.calculate(frames.data(), 1, 10); } catch (const std::runtime_error&) { threw = true; }
+        CHECK(threw);
+        std::printf("test_host OK: %zu pairs, %llu edges in %d frames\n", pairs.size(),
+                    (unsigned long long)all.n_edges, n_frames);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 2;
+    }
+}
