@@ -28,7 +28,7 @@ struct wn_ctx {
     std::string err;
 
     /* site table */
-    int n_sites = -1, hs = 1, first_limit = 0, typed = 0, max_atom = -1;
+    int n_sites = -1, hs = 1, first_limit = 0, simple = 0, max_atom = -1;
     int* d_site_atom = nullptr;
     int* d_hv_atom = nullptr;
     uint32_t* d_meta = nullptr;
@@ -44,15 +44,16 @@ struct wn_ctx {
     float4* d_spos = nullptr;
     uint32_t* d_smeta = nullptr;
     double* d_sdh = nullptr;
-    uint32_t* d_row_pos = nullptr;
     uint32_t* d_row_cnt = nullptr;
     uint32_t* d_row_off = nullptr;
     unsigned long long* d_frame_total = nullptr;
     WnFrameCounters* d_counters = nullptr;
-    unsigned long long* d_cursor = nullptr;
+    uint32_t* d_frame_maxrow = nullptr;
+    unsigned long long* d_pass_info = nullptr;
     double* d_block_sums = nullptr;
-    WnTempEdge* d_temp = nullptr;
-    size_t temp_cap = 0;
+    WnTempEdge* d_rowbuf = nullptr;
+    size_t rowbuf_cap = 0;          /* entries */
+    int row_cap = 32;               /* slots per row; grows (sticky) when a row overflows */
     float* d_stage = nullptr;      /* host variant: frames of one pass */
     size_t stage_cap = 0;
 
@@ -181,14 +182,14 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
     if ((rc = dev_realloc_plain(ctx, &ctx->d_site_rank, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_spos, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_smeta, fn))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_sdh, fn * ch * 3))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_row_pos, fn))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_sdh, fn * ch * 4))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_row_cnt, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_row_off, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_total, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_counters, (size_t)cf))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_maxrow, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_block_sums, (size_t)cf * ((cn + 255) / 256 + 1)))) return rc;
-    if (!ctx->d_cursor) { if ((rc = dev_realloc_plain(ctx, &ctx->d_cursor, (size_t)1))) return rc; }
+    if (!ctx->d_pass_info) { if ((rc = dev_realloc_plain(ctx, &ctx->d_pass_info, (size_t)2))) return rc; }
     ctx->cap_frames = cf; ctx->cap_sites = cn; ctx->cap_hs = ch; ctx->cell_cap = cell_cap;
     return WN_OK;
 }
@@ -220,6 +221,9 @@ int ensure_out_frames(wn_ctx* ctx, size_t n_frames, bool host)
     return WN_OK;
 }
 
+/* Device memory the row buffers of one pass may take (bytes). */
+static const size_t WN_ROWBUF_BUDGET = (size_t)24 << 30;
+
 /* Run the pipeline on `nf` device-resident frames; edges land in ctx->d_edges at
  * offset *edge_base (updated), frame rows at [f0, f0+nf). */
 int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
@@ -228,10 +232,13 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
     const int N = ctx->n_sites;
     cudaStream_t st = ctx->st;
     int rc;
-    if ((rc = ensure_pass_buffers(ctx, nf))) return rc;
-    if (ctx->temp_cap == 0) {
-        if ((rc = dev_ensure(ctx, &ctx->d_temp, &ctx->temp_cap, (size_t)nf * N * 16 + 1024))) return rc;
+    /* a pass whose row buffers would not fit is split (dense inputs after row_cap grew) */
+    if (nf > 1 && (size_t)nf * N * ctx->row_cap * sizeof(WnTempEdge) > WN_ROWBUF_BUDGET) {
+        const int half = nf / 2;
+        if ((rc = run_pass(ctx, d_frames, half, natoms, f0, edge_base))) return rc;
+        return run_pass(ctx, d_frames + (size_t)half * natoms * 3, nf - half, natoms, f0 + half, edge_base);
     }
+    if ((rc = ensure_pass_buffers(ctx, nf))) return rc;
     const int cell_cap = ctx->cell_cap;
 
     WN_CK(cudaEventRecord(ctx->ev[0], st));
@@ -246,55 +253,63 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
     ctx->tm.launches += 4;
     WN_CK(cudaEventRecord(ctx->ev[1], st));
 
-    unsigned long long used = 0;
+    unsigned long long end_off = 0;
     for (int attempt = 0;; ++attempt) {
-        WN_CK(cudaMemsetAsync(ctx->d_cursor, 0, sizeof(unsigned long long), st));
+        if ((rc = dev_ensure(ctx, &ctx->d_rowbuf, &ctx->rowbuf_cap, (size_t)nf * N * ctx->row_cap))) return rc;
+        WN_CK(cudaMemsetAsync(ctx->d_row_cnt, 0, (size_t)nf * N * sizeof(uint32_t), st));
         WN_CK(cudaMemsetAsync(ctx->d_counters, 0, (size_t)nf * sizeof(WnFrameCounters), st));
         WnEdgeParams p;
         p.spos = ctx->d_spos; p.smeta = ctx->d_smeta; p.sdh = ctx->d_sdh;
         p.cell_start = ctx->d_cell_cnt; p.grid = ctx->d_grid;
-        p.temp = ctx->d_temp; p.temp_cursor = ctx->d_cursor; p.temp_cap = ctx->temp_cap;
-        p.row_pos = ctx->d_row_pos; p.row_cnt = ctx->d_row_cnt; p.counters = ctx->d_counters;
+        p.rowbuf = ctx->d_rowbuf; p.row_cnt = ctx->d_row_cnt; p.counters = ctx->d_counters;
         p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
-        p.typed = ctx->typed;
+        p.row_cap = ctx->row_cap; p.simple = ctx->simple;
         wn_launch_edges(p, nf, st);
-        ctx->tm.launches += 1;
         WN_CK(cudaGetLastError());
-        WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_cursor, sizeof(unsigned long long),
+        if (attempt == 0) WN_CK(cudaEventRecord(ctx->ev[2], st));
+        wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off, ctx->d_frame_total, ctx->d_frame_maxrow, st);
+        wn_launch_frameoff(ctx->d_frame_total, ctx->d_frame_maxrow, nf, *edge_base, ctx->d_frame_off + f0,
+                           ctx->d_pass_info, st);
+        ctx->tm.launches += 3;
+        WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_pass_info, 2 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
         WN_CK(cudaStreamSynchronize(st));
-        used = ctx->h_scalars[0];
-        if (used <= ctx->temp_cap) break;
-        if (used >= (1ull << 32) || attempt > 0)
-            return fail(ctx, WN_ERR_OVERFLOW, "edges of one pass exceed the 32-bit row index space; lower frames_per_pass");
-        if ((rc = dev_ensure(ctx, &ctx->d_temp, &ctx->temp_cap, (size_t)used + (size_t)used / 8))) return rc;
+        end_off = ctx->h_scalars[0];
+        const unsigned long long max_row = ctx->h_scalars[1];
+        if (max_row <= (unsigned long long)ctx->row_cap) break;
+        /* a row overflowed its slots: grow the (sticky) row capacity and repeat the search */
+        if (attempt > 0) return fail(ctx, WN_ERR_CUDA, "internal: row capacity still too small after growing");
+        int nc = ctx->row_cap;
+        while ((unsigned long long)nc < max_row) nc *= 2;
+        ctx->row_cap = nc;
+        if (nf > 1 && (size_t)nf * N * nc * sizeof(WnTempEdge) > WN_ROWBUF_BUDGET) {
+            const int half = nf / 2;
+            if ((rc = run_pass(ctx, d_frames, half, natoms, f0, edge_base))) return rc;
+            return run_pass(ctx, d_frames + (size_t)half * natoms * 3, nf - half, natoms, f0 + half, edge_base);
+        }
     }
-    WN_CK(cudaEventRecord(ctx->ev[2], st));
 
-    if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, (size_t)(*edge_base + used), true,
-                         (size_t)*edge_base))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, (size_t)end_off, true, (size_t)*edge_base))) return rc;
 
-    wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off, ctx->d_frame_total, st);
-    wn_launch_frameoff(ctx->d_frame_total, nf, *edge_base, ctx->d_frame_off + f0, st);
     int n_blocks = 0;
-    wn_launch_copy(ctx->d_temp, ctx->d_row_pos, ctx->d_row_cnt, ctx->d_row_off, ctx->d_frame_off + f0,
+    wn_launch_copy(ctx->d_rowbuf, ctx->row_cap, ctx->d_row_cnt, ctx->d_row_off, ctx->d_frame_off + f0,
                    nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->d_block_sums, &n_blocks, st);
     wn_launch_stats(ctx->d_block_sums, n_blocks, ctx->d_frame_total, ctx->d_counters, nf, N,
                     ctx->d_stats + f0, st);
     WN_CK(cudaMemcpyAsync(ctx->d_counters_all + f0, ctx->d_counters, (size_t)nf * sizeof(WnFrameCounters),
                           cudaMemcpyDeviceToDevice, st));
-    ctx->tm.launches += 4;
+    ctx->tm.launches += 2;
     WN_CK(cudaEventRecord(ctx->ev[3], st));
     WN_CK(cudaGetLastError());
     WN_CK(cudaStreamSynchronize(st));
-    float a = 0, b = 0, c = 0;
+    float a = 0, b = 0, c2 = 0;
     cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
-    ctx->tm.bin_ms += a; ctx->tm.edges_ms += b; ctx->tm.finish_ms += c;
-    ctx->tm.total_ms += a + b + c;
+    cudaEventElapsedTime(&c2, ctx->ev[2], ctx->ev[3]);
+    ctx->tm.bin_ms += a; ctx->tm.edges_ms += b; ctx->tm.finish_ms += c2;
+    ctx->tm.total_ms += a + b + c2;
     ctx->tm.passes += 1;
-    *edge_base += used;
+    *edge_base = end_off;
     return WN_OK;
 }
 
@@ -454,9 +469,9 @@ void wn_destroy(wn_ctx* ctx)
         if (fn) fn(ctx->comm);
     }
     void* dev[] = {ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, ctx->d_grid, ctx->d_cell_cnt, ctx->d_site_cell,
-                   ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_pos, ctx->d_row_cnt,
-                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_cursor, ctx->d_block_sums,
-                   ctx->d_temp, ctx->d_stage, ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
+                   ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_cnt,
+                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_pass_info,
+                   ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage, ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs};
@@ -483,7 +498,7 @@ int wn_set_sites(wn_ctx* ctx, int32_t n_sites, const int32_t* site_atom, const i
     /* Statically invalid hydrogens (the site atom itself, SURVEY F8: DH = 0/0 = NaN,
      * never selected) are dropped here; list positions are kept in the meta word. */
     int hs = 1, max_atom = -1;
-    bool typed = false;
+    bool simple = true;     /* every site WATER with exactly one valid hydrogen, not at list position 0 */
     std::vector<uint32_t> meta((size_t)n_sites);
     std::vector<std::vector<int>> valid((size_t)n_sites);
     for (int s = 0; s < n_sites; ++s) {
@@ -507,7 +522,7 @@ int wn_set_sites(wn_ctx* ctx, int32_t n_sites, const int32_t* site_atom, const i
         hs = std::max(hs, (int)valid[s].size());
         meta[s] = (uint32_t)site_type[s] | (nh > 0 ? WN_META_HASH : 0u) | (first0 ? WN_META_FIRST0 : 0u) |
                   ((uint32_t)valid[s].size() << WN_META_NV_SHIFT);
-        if (site_type[s] != WN_WATER || nh == 0) typed = true;
+        if (site_type[s] != WN_WATER || valid[s].size() != 1 || first0) simple = false;
     }
     std::vector<int> hv((size_t)n_sites * hs, -1);
     for (int s = 0; s < n_sites; ++s)
@@ -523,8 +538,9 @@ int wn_set_sites(wn_ctx* ctx, int32_t n_sites, const int32_t* site_atom, const i
         WN_CK(cudaMemcpy(ctx->d_hv_atom, hv.data(), hv.size() * sizeof(int), cudaMemcpyHostToDevice));
         WN_CK(cudaMemcpy(ctx->d_meta, meta.data(), meta.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
-    ctx->n_sites = n_sites; ctx->hs = hs; ctx->typed = typed ? 1 : 0; ctx->max_atom = max_atom;
+    ctx->n_sites = n_sites; ctx->hs = hs; ctx->simple = simple ? 1 : 0; ctx->max_atom = max_atom;
     ctx->first_limit = first_limit < 0 ? 0 : first_limit;
+    ctx->row_cap = 32;      /* a new table is a new system: forget a grown row capacity */
     return WN_OK;
 }
 

@@ -17,6 +17,8 @@ struct WnGrid {
     double inv;          /* 1 / cell edge                             */
     int nx, ny, nz;
     int ncells;          /* nx*ny*nz <= cell capacity                 */
+    float edge;          /* cell edge (fp32 copy, for cell-local frames) */
+    float tf;            /* fp32 prefilter bound on d^2 (superset of the exact test) */
 };
 
 /* ---- per-frame counters written by the fused kernel ---- */
@@ -38,7 +40,6 @@ struct WnFrameCounters {
  * length in Angstrom is > 6.5.  Any accepted pair has squared distance (nm^2)
  * <= 0.4225*(1+2.5e-7); the fp32 prefilter and the cell edge carry a margin. */
 #define WN_LEN_CUT_F      6.5f
-#define WN_PREFILTER_D2   (0.4225 * (1.0 + 1.0e-5))
 #define WN_CELL_EDGE      (0.65 * (1.0 + 1.0e-5))
 
 /* Energy parameters in the form the kernels consume (computeEnergy, :49-66). */
@@ -47,7 +48,7 @@ struct WnEnergyParams {
     double a_on, a_off;    /* angle switch slots after the caller-side swap      */
 };
 
-/* temp entry produced by the fused kernel, consumed by the ordered copy */
+/* row-buffer entry produced by the fused kernel, consumed by the ordered copy */
 struct __align__(16) WnTempEdge {
     int32_t j;
     float   length;
@@ -59,20 +60,18 @@ struct __align__(16) WnTempEdge {
 struct WnEdgeParams {
     const float4*   spos;       /* [F][N] sorted: x,y,z, site index bits          */
     const uint32_t* smeta;      /* [F][N] sorted meta                             */
-    const double*   sdh;        /* [F][N][hs][3] sorted unit D-H vectors          */
+    const double*   sdh;        /* [F][N][hs][4] sorted unit D-H vectors (x,y,z,pad) */
     const int*      cell_start; /* [F][cell_cap+1]                                */
     const WnGrid*   grid;       /* [F]                                            */
-    WnTempEdge*     temp;       /* [temp_cap]                                     */
-    unsigned long long* temp_cursor;
-    unsigned long long  temp_cap;
-    uint32_t*       row_pos;    /* [F][N] position of the row in temp             */
-    uint32_t*       row_cnt;    /* [F][N] edges owned by the row                  */
+    WnTempEdge*     rowbuf;     /* [F][N][row_cap] edges of row i, arrival order  */
+    uint32_t*       row_cnt;    /* [F][N] edges owned by the row (zeroed before)  */
     WnFrameCounters* counters;  /* [F]                                            */
     int n_sites;
     int cell_cap;
     int hs;                     /* valid-hydrogen slots per site                  */
     int first_limit;
-    int typed;                  /* 0: all sites WATER with hydrogens              */
+    int row_cap;
+    int simple;                 /* 1: every site WATER with the list [site atom, H] */
 };
 
 /* ---- kernel launchers (wn_kernels_*.cu).  All asynchronous on `st`. ---- */
@@ -90,11 +89,13 @@ void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int*
                        cudaStream_t st);
 void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st);
 void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
-                       uint32_t* row_off, unsigned long long* frame_total, cudaStream_t st);
-void wn_launch_frameoff(const unsigned long long* frame_total, int n_frames,
+                       uint32_t* row_off, unsigned long long* frame_total, uint32_t* frame_maxrow,
+                       cudaStream_t st);
+/* pass_info[0] = base + total edges of the pass, pass_info[1] = longest row */
+void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* frame_maxrow, int n_frames,
                         unsigned long long base, unsigned long long* frame_off,
-                        cudaStream_t st);
-void wn_launch_copy(const WnTempEdge* temp, const uint32_t* row_pos, const uint32_t* row_cnt,
+                        unsigned long long* pass_info, cudaStream_t st);
+void wn_launch_copy(const WnTempEdge* rowbuf, int row_cap, const uint32_t* row_cnt,
                     const uint32_t* row_off, const unsigned long long* frame_off,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
                     unsigned long long edge_cap, double* block_sums, int* n_blocks_out,

@@ -65,6 +65,7 @@ wn_k_bbox(const float* __restrict__ frames, int natoms, const int* __restrict__ 
         WnGrid g;
         if (!(mn[0] <= mx[0])) {          /* no finite site */
             g.ox = g.oy = g.oz = 0.0; g.inv = 1.0; g.nx = g.ny = g.nz = 1; g.ncells = 1;
+            g.edge = 1.0f; g.tf = 1.0f;
         } else {
             double edge = WN_CELL_EDGE;
             const double ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
@@ -80,6 +81,12 @@ wn_k_bbox(const float* __restrict__ frames, int natoms, const int* __restrict__ 
             g.inv = 1.0 / edge;
             g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
             g.ncells = g.nx * g.ny * g.nz;
+            /* fp32 prefilter bound: exact acceptance needs d2 <= 0.4225*(1+2.5e-7); the
+             * dot-product form on cell-local coordinates (|a| <= sqrt(3) e, |c| <= 2 sqrt(3) e)
+             * errs by <= ~2.2e-6 e^2 + 5.5e-7 e; bound with > 2x head-room, rounded up */
+            const double tfd = 0.4225 * (1.0 + 1.0e-5) + 5.0e-6 * edge * edge + 1.5e-6 * edge;
+            g.edge = (float)edge;
+            g.tf = __double2float_ru(tfd);
         }
         grid[f] = g;
     }
@@ -185,8 +192,9 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
                                                   __dmul_rn(dz, dz)));
             dx = __ddiv_rn(dx, l); dy = __ddiv_rn(dy, l); dz = __ddiv_rn(dz, l);
         }
-        double* d = sdh + (o * hs + v) * 3;
-        d[0] = dx; d[1] = dy; d[2] = dz;
+        double* d = sdh + (o * hs + v) * 4;
+        reinterpret_cast<double2*>(d)[0] = make_double2(dx, dy);
+        reinterpret_cast<double2*>(d)[1] = make_double2(dz, 0.0);
     }
 }
 

@@ -7,83 +7,84 @@
  *   make_edges              reference src/waternetwork.cpp:182-263
  * Every pair that make_edges can turn into an edge has a float length <= 6.5 A
  * (:204), i.e. a squared distance far inside the brute test 10*d2 < 42.25
- * (src/brute-find-pairs.cpp:25), so searching the 27 neighbouring cells of a grid
+ * (src/brute-find-pairs.cpp:25), so searching the neighbouring cells of a grid
  * with edge >= 0.65 nm finds exactly the pairs that matter.
  *
- * Work decomposition: one warp per (frame, home cell).  The warp sweeps the
- * candidates of the 27 neighbouring cells (9 contiguous runs of the cell-sorted
- * site array), lane = candidate, inner loop = home sites (broadcast from shared
- * memory).  An fp32 distance prefilter (superset, margin 1e-5) plus `j > i`
- * selects candidates; their (home, candidate) codes are ballot-compacted into a
- * per-warp queue.  Whenever 32 codes are queued the warp switches to the exact
- * fp64 geometry with all lanes busy (the reference's operation order, explicit
- * round-to-nearest intrinsics, no FMA contraction).  Accepted edges are pooled in
- * shared memory, grouped by owning row at the end of the cell, and written to a
- * batch-wide temp array; wn_k_copy then places every row at its final
- * lexicographic position (edge order == pair order, :621-633).
+ * Work decomposition: one warp per (frame, home cell), HALF SHELL: the warp pairs
+ * its home sites with the sites of the 13 "forward" neighbour cells and with the
+ * later sites of its own cell, so every unordered pair is examined exactly once
+ * (5 contiguous runs of the cell-sorted site array).  lane = candidate, unrolled
+ * inner loop = home sites (broadcast from shared memory).
+ *   search : fp32 prefilter in dot-product form on cell-local coordinates,
+ *            a.c - (|a|^2 - T)/2 >= |c|^2/2   (3 FFMA + 1 FSETP per test),
+ *            a strict superset of the exact test (margin in WnGrid::tf);
+ *            hits go to a lane-private bit mask, then one warp scan per round
+ *            compacts (home, candidate) codes into a per-warp queue.
+ *   geometry: whenever 32 codes are queued, all lanes evaluate the exact fp64
+ *            geometry of make_edges (reference operation order, explicit
+ *            round-to-nearest intrinsics, never contracted to FMA).
+ *   output : the edge belongs to row i = min(site indices); its slot in the row
+ *            buffer comes from one atomicAdd on the row counter.  wn_k_copy later
+ *            orders every row by j and places rows at their lexicographic offset
+ *            (edge order == pair order, :621-633).
+ * Rows longer than the row buffer are counted but not stored; the host then grows
+ * the row capacity and repeats the pass, so arbitrarily dense inputs stay correct.
  *
- * Rows that do not fit the pool fall back to one-row-at-a-time processing and, if
- * a single row is still too long, to a count -> allocate -> direct-write path, so
- * arbitrarily dense inputs stay correct.
+ * Role symmetry used here (exact in IEEE arithmetic): with u = (S_h - S_c)/dist for
+ * a home site h and a candidate c, the cosine of a hydrogen of h is f32(DH_h . u) and
+ * that of a hydrogen of c is -f32(DH_c . u) whichever of the two has the lower site
+ * index (negation commutes with every rounding); only the ORDER of the arg-max scan
+ * (first site's list, then second site's, :215-249) depends on the roles.
  */
 #include "wn_internal.cuh"
 
 namespace {
 
 constexpr int WARPS_PER_CTA = 8;
-constexpr int HC   = 16;     /* home sites per chunk                     */
-constexpr int PCAP = 256;    /* pooled edges per chunk                   */
-constexpr int QCAP = 32 + 32 * HC;  /* queue: < 32 carried + one round of pushes */
-constexpr int MAXRUN = 9;
+constexpr int HC   = 16;                 /* home sites per chunk                      */
+constexpr int QCAP = 32 + 32 * HC;       /* queue: < 32 carried + one round of pushes */
+constexpr int MAXRUN = 5;
 constexpr unsigned FULL = 0xffffffffu;
 
-/* jh = (home row slot << 27) | partner site index (n_sites < 2^27) */
-struct PoolEntry { uint32_t jh; float length; float cosine; };
-
-/* fixed part of the per-warp shared memory */
+/* fixed part of the per-warp shared memory (followed by HC*hs unit D-H vectors) */
 struct WarpShared {
-    float4    hpos[HC];
+    float4    hloc[HC];      /* cell-local x,y,z ; w = (|a|^2 - T)/2            (search)   */
+    float4    hpos[HC];      /* original float x,y,z ; w = site index bits      (geometry) */
     uint32_t  hmeta[HC];
-    int       hrow[HC];      /* real site index of the home row            */
-    int       cnt[HC];
-    int       rbase[HC];
-    int       fill[HC];
     uint32_t  queue[QCAP];
     int       run_start[MAXRUN + 1];
     int       run_pref[MAXRUN + 1];
-    PoolEntry pool[PCAP];
 };
 
-enum { MODE_POOL = 0, MODE_COUNT = 1, MODE_DIRECT = 2 };
+struct Counters { unsigned int evals, tie_len, tie_cos, tie_pos0; };
 
-struct ChunkState {
-    int pool_len;
-    bool overflow;
-    unsigned int evals, tie_len, tie_cos, tie_pos0;
-    /* MODE_COUNT / MODE_DIRECT */
-    unsigned long long direct_base;
-    unsigned int direct_k;
-};
+__device__ __forceinline__ float wn_dot_f32(const double* __restrict__ d, double ux, double uy, double uz)
+{
+    /* float proj = DH*OO : (x*x' + y*y') + z*z' in double, then one rounding to float */
+    return __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(d[0], ux), __dmul_rn(d[1], uy)), __dmul_rn(d[2], uz)));
+}
 
 /* Exact geometry of make_edges for `nb` queued codes (lane < nb active). */
-template <bool TYPED>
+template <bool SIMPLE>
 __device__ __forceinline__ void
-wn_eval_batch(const WnEdgeParams& p, size_t fbase, WarpShared& ws, const double* __restrict__ hdh,
-              int qbase, int nb, int mode, ChunkState& cs, int lane)
+wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const double* __restrict__ hdh,
+              int qbase, int nb, Counters& ct, int lane)
 {
     const bool act = lane < nb;
     bool counted = false, edge = false;
     bool t_len = false, t_cos = false, t_pos0 = false;
     float len_f = 0.f, cosmax = 0.f;
-    int h = 0, jidx = 0;
+    int ih = 0, ic = 0;
     if (act) {
         const uint32_t code = ws.queue[qbase + lane];
-        h = (int)(code >> 27);
+        const int h = (int)(code >> 27);
         const uint32_t c = code & 0x07ffffffu;
         const float4 a4 = ws.hpos[h];
         const float4 b4 = __ldg(p.spos + fbase + c);
-        jidx = __float_as_int(b4.w);
-        /* Vector_3 OO = sitePoints.at(first) - sitePoints.at(second)      (:194) */
+        ih = __float_as_int(a4.w);
+        ic = __float_as_int(b4.w);
+        /* Vector_3 OO = sitePoints.at(first) - sitePoints.at(second)      (:194)
+         * computed here as S_h - S_c; the other role is its exact negation */
         const double ox = __dsub_rn((double)a4.x, (double)b4.x);
         const double oy = __dsub_rn((double)a4.y, (double)b4.y);
         const double oz = __dsub_rn((double)a4.z, (double)b4.z);
@@ -99,214 +100,71 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, WarpShared& ws, const double*
             t_len = (len_f == WN_LEN_CUT_F);
             /* OO /= distance                                               (:196) */
             const double ux = __ddiv_rn(ox, dd), uy = __ddiv_rn(oy, dd), uz = __ddiv_rn(oz, dd);
-            const uint32_t ma = ws.hmeta[h];
-            const uint32_t mb = __ldg(p.smeta + fbase + c);
-            const int nva = (int)((ma >> WN_META_NV_SHIFT) & WN_META_NV_MASK);
-            const int nvb = (int)((mb >> WN_META_NV_SHIFT) & WN_META_NV_MASK);
-            bool win = false, win0 = false;
-            /* hydrogens of the first site: proj = DH*OO                 (:217-225) */
-            for (int v = 0; v < nva; ++v) {
-                const double* d = hdh + ((size_t)h * p.hs + v) * 3;
-                const float cv = __double2float_rn(
-                    __dadd_rn(__dadd_rn(__dmul_rn(d[0], ux), __dmul_rn(d[1], uy)), __dmul_rn(d[2], uz)));
-                if (cv > cosmax) {                                      /* :242-247 */
-                    cosmax = cv; win = true;
-                    win0 = (v == 0) && (ma & WN_META_FIRST0);
-                } else if (cosmax > 0.f && cv == cosmax) {
-                    t_cos = true;
-                }
-            }
-            /* hydrogens of the second site: proj = DH*(-1.0*OO)         (:229-237);
-             * negation commutes with every rounding, so proj = -(DH*OO). */
-            const double* db = p.sdh + ((fbase + c) * (size_t)p.hs) * 3;
-            for (int v = 0; v < nvb; ++v) {
-                const double bx = __ldg(db + 3 * v), by = __ldg(db + 3 * v + 1), bz = __ldg(db + 3 * v + 2);
-                const float cv = -__double2float_rn(
-                    __dadd_rn(__dadd_rn(__dmul_rn(bx, ux), __dmul_rn(by, uy)), __dmul_rn(bz, uz)));
-                if (cv > cosmax) {
-                    /* list index of this hydrogen is nH(first) + its own position: it is
-                     * 0 only when the first site has no hydrogen list at all */
-                    cosmax = cv; win = true;
-                    win0 = (v == 0) && (mb & WN_META_FIRST0) && !(ma & WN_META_HASH);
-                } else if (cosmax > 0.f && cv == cosmax) {
-                    t_cos = true;
-                }
-            }
-            t_pos0 = win && win0;
-            edge = win && !win0;                                   /* if (pos > 0)  :251 */
-        }
-    }
-    const unsigned m_cnt = __ballot_sync(FULL, counted);
-    const unsigned m_edge = __ballot_sync(FULL, edge);
-    cs.evals += __popc(m_cnt);
-    if (__any_sync(FULL, t_len || t_cos || t_pos0)) {          /* rare */
-        cs.tie_len += __popc(__ballot_sync(FULL, t_len));
-        cs.tie_cos += __popc(__ballot_sync(FULL, t_cos));
-        cs.tie_pos0 += __popc(__ballot_sync(FULL, t_pos0));
-    }
-    const int ne = __popc(m_edge);
-    if (ne == 0) return;
-    const int k = __popc(m_edge & ((1u << lane) - 1u));
-    if (mode == MODE_POOL) {
-        if (cs.pool_len + ne > PCAP) { cs.overflow = true; return; }
-        if (edge) {
-            PoolEntry e; e.jh = ((uint32_t)h << 27) | (uint32_t)jidx; e.length = len_f; e.cosine = cosmax;
-            ws.pool[cs.pool_len + k] = e;
-            atomicAdd(&ws.cnt[h], 1);
-        }
-        cs.pool_len += ne;
-    } else if (mode == MODE_COUNT) {
-        cs.direct_k += ne;
-    } else {
-        if (edge) {
-            const unsigned long long pos = cs.direct_base + cs.direct_k + k;
-            if (pos < p.temp_cap) {
-                WnTempEdge t; t.j = jidx; t.length = len_f; t.cosine = cosmax; t.pad = 0;
-                p.temp[pos] = t;
-            }
-        }
-        cs.direct_k += ne;
-    }
-}
-
-/* Sweep all candidates of the neighbourhood against home sites [hb, hb+hc). */
-template <bool TYPED>
-__device__ __forceinline__ void
-wn_sweep(const WnEdgeParams& p, size_t fbase, WarpShared& ws, double* hdh, int hb, int hc,
-         int n_runs, int total, int mode, ChunkState& cs, int lane)
-{
-    /* stage the home sites; pad the chunk to a multiple of 4 with unreachable dummies */
-    const int hc4 = (hc + 3) & ~3;
-    __syncwarp();
-    if (lane < hc4) {
-        float4 a = make_float4(1.0e30f, 1.0e30f, 1.0e30f, __int_as_float(0x7fffffff));
-        uint32_t m = 0;
-        int row = -1;
-        if (lane < hc) {
-            a = __ldg(p.spos + fbase + hb + lane);
-            row = __float_as_int(a.w);
-            /* rows >= first_limit own nothing: an index no candidate can exceed */
-            if (row >= p.first_limit) a.w = __int_as_float(0x7fffffff);
-            m = __ldg(p.smeta + fbase + hb + lane);
-        }
-        ws.hpos[lane] = a; ws.hrow[lane] = row; ws.hmeta[lane] = m;
-    }
-    if (lane < HC) { ws.cnt[lane] = 0; ws.fill[lane] = 0; }
-    for (int t = lane; t < hc * p.hs * 3; t += 32)
-        hdh[t] = __ldg(p.sdh + (fbase + hb) * (size_t)p.hs * 3 + t);
-    __syncwarp();
-
-    const float tf = (float)WN_PREFILTER_D2;
-    int qlen = 0;
-    int run = 0;
-    const int rounds = (total + 31) >> 5;
-    for (int r = 0; r < rounds; ++r) {
-        const int v = r * 32 + lane;
-        float cx = -1.0e30f, cy = -1.0e30f, cz = -1.0e30f;
-        int cj = -1;
-        uint32_t code_c = 0, cm = 0;
-        if (v < total) {
-            while (run + 1 < n_runs && v >= ws.run_pref[run + 1]) ++run;
-            const int c = ws.run_start[run] + (v - ws.run_pref[run]);
-            const float4 b4 = __ldg(p.spos + fbase + c);
-            cx = b4.x; cy = b4.y; cz = b4.z; cj = __float_as_int(b4.w);
-            code_c = (uint32_t)c;
-            if (TYPED) cm = __ldg(p.smeta + fbase + c);
-        }
-        /* lane-private hit mask: bit h = home row h is a candidate partner */
-        uint32_t hits = 0;
-#pragma unroll
-        for (int g = 0; g < HC / 4; ++g) {
-            if (g * 4 < hc4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int h = g * 4 + u;
-                    const float4 a4 = ws.hpos[h];
-                    const float dx = a4.x - cx, dy = a4.y - cy, dz = a4.z - cz;
-                    const float d2 = dx * dx + dy * dy + dz * dz;
-                    bool pass = (d2 <= tf) && (cj > __float_as_int(a4.w));
-                    if (TYPED) {
-                        /* type rule (:199-203) and the no-hydrogen rule (:205-208) */
-                        const uint32_t am = ws.hmeta[h];
-                        const uint32_t ta = am & WN_META_TYPE_MASK, tb = cm & WN_META_TYPE_MASK;
-                        const bool typ = (ta != tb) || (ta == WN_WATER && tb == WN_WATER);
-                        const bool anyh = ((am | cm) & WN_META_HASH) != 0;
-                        pass = pass && typ && anyh;
+            const double* dh = hdh + (size_t)h * p.hs * 4;
+            const double* dc = p.sdh + (fbase + c) * (size_t)p.hs * 4;
+            if (SIMPLE) {
+                /* every site: list [site atom itself (NaN, never wins), H] -> one cosine each;
+                 * arg-max from 0 with strict '>' (:240-249) is max(c_first, c_second) when > 0 */
+                const double2 c01 = __ldg(reinterpret_cast<const double2*>(dc));
+                const double c2 = __ldg(dc + 2);
+                const double dcv[3] = {c01.x, c01.y, c2};
+                const float ch = wn_dot_f32(dh, ux, uy, uz);
+                const float cc = -wn_dot_f32(dcv, ux, uy, uz);
+                if (ch > 0.f) cosmax = ch;
+                t_cos = (ch > 0.f) && (cc == ch);
+                if (cc > cosmax) cosmax = cc;
+                edge = cosmax > 0.f;
+            } else {
+                const uint32_t mh = ws.hmeta[h];
+                const uint32_t mc = __ldg(p.smeta + fbase + c);
+                const bool h_first = ih < ic;
+                const uint32_t m_first = h_first ? mh : mc;
+                bool win = false, win0 = false;
+#pragma unroll 1
+                for (int s = 0; s < 2; ++s) {
+                    const bool use_h = (s == 0) == h_first;
+                    const uint32_t m = use_h ? mh : mc;
+                    const int nv = (int)((m >> WN_META_NV_SHIFT) & WN_META_NV_MASK);
+                    /* list index 0 is the first site's position-0 hydrogen, or the second
+                     * site's when the first site has no hydrogen list at all (:251) */
+                    const bool zero_here = (m & WN_META_FIRST0) && (s == 0 || !(m_first & WN_META_HASH));
+                    for (int v = 0; v < nv; ++v) {
+                        float cv;
+                        if (use_h) {
+                            cv = wn_dot_f32(dh + 4 * v, ux, uy, uz);               /* :219-221 */
+                        } else {
+                            const double dcv[3] = {__ldg(dc + 4 * v), __ldg(dc + 4 * v + 1), __ldg(dc + 4 * v + 2)};
+                            cv = -wn_dot_f32(dcv, ux, uy, uz);                      /* :231-233 */
+                        }
+                        if (cv > cosmax) {                                          /* :242-247 */
+                            cosmax = cv; win = true; win0 = zero_here && (v == 0);
+                        } else if (cosmax > 0.f && cv == cosmax) {
+                            t_cos = true;
+                        }
                     }
-                    if (pass) hits |= (1u << h);
                 }
+                t_pos0 = win && win0;
+                edge = win && !win0;                                                /* if (pos > 0) */
             }
-        }
-        /* warp scan of the hit counts -> dense queue positions */
-        const int cnt = __popc(hits);
-        int inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += t;
-        }
-        const int tot = __shfl_sync(FULL, inc, 31);
-        if (tot) {
-            int pos = qlen + inc - cnt;
-            while (hits) {
-                const int h = __ffs(hits) - 1;
-                hits &= hits - 1;
-                ws.queue[pos++] = ((uint32_t)h << 27) | code_c;
-            }
-            qlen += tot;
-            __syncwarp();
-            while (qlen >= 32) {
-                wn_eval_batch<TYPED>(p, fbase, ws, hdh, qlen - 32, 32, mode, cs, lane);
-                qlen -= 32;
-                if (cs.overflow) return;
-            }
-            __syncwarp();
         }
     }
-    if (qlen > 0) {
-        __syncwarp();
-        wn_eval_batch<TYPED>(p, fbase, ws, hdh, 0, qlen, mode, cs, lane);
+    ct.evals += __popc(__ballot_sync(FULL, counted));
+    if (__any_sync(FULL, t_len || t_cos || t_pos0)) {          /* rare */
+        ct.tie_len += __popc(__ballot_sync(FULL, t_len));
+        ct.tie_cos += __popc(__ballot_sync(FULL, t_cos));
+        ct.tie_pos0 += __popc(__ballot_sync(FULL, t_pos0));
     }
-    __syncwarp();
+    if (edge) {
+        const int i = min(ih, ic), j = max(ih, ic);
+        const uint32_t slot = atomicAdd(p.row_cnt + fbase + i, 1u);
+        if (slot < (uint32_t)p.row_cap) {
+            WnTempEdge t; t.j = j; t.length = len_f; t.cosine = cosmax; t.pad = 0;
+            p.rowbuf[(fbase + i) * (size_t)p.row_cap + slot] = t;
+        }
+    }
 }
 
-/* Publish a pooled chunk: allocate temp space, group the pool by row. */
-__device__ __forceinline__ void
-wn_commit_pool(const WnEdgeParams& p, size_t fbase, WarpShared& ws, int hc, const ChunkState& cs, int lane)
-{
-    const int total = cs.pool_len;
-    unsigned long long base = 0;
-    if (lane == 0 && total > 0) base = atomicAdd(p.temp_cursor, (unsigned long long)total);
-    base = __shfl_sync(FULL, base, 0);
-    /* exclusive scan of the row counts (hc <= 16 <= 32 lanes) */
-    const int c = (lane < hc) ? ws.cnt[lane] : 0;
-    int inc = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane < hc) {
-        ws.rbase[lane] = inc - c;
-        const int idx = ws.hrow[lane];
-        p.row_pos[fbase + idx] = (uint32_t)(base + (unsigned long long)(inc - c));
-        p.row_cnt[fbase + idx] = (uint32_t)c;
-    }
-    __syncwarp();
-    for (int e = lane; e < total; e += 32) {
-        const PoolEntry pe = ws.pool[e];
-        const int ph = (int)(pe.jh >> 27);
-        const int k = atomicAdd(&ws.fill[ph], 1);
-        const unsigned long long pos = base + (unsigned long long)(ws.rbase[ph] + k);
-        if (pos < p.temp_cap) {
-            WnTempEdge t; t.j = (int32_t)(pe.jh & 0x07ffffffu); t.length = pe.length; t.cosine = pe.cosine; t.pad = 0;
-            p.temp[pos] = t;
-        }
-    }
-    __syncwarp();
-}
-
-template <bool TYPED>
+template <bool SIMPLE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 wn_k_edges(const WnEdgeParams p)
 {
@@ -317,7 +175,7 @@ wn_k_edges(const WnEdgeParams p)
     const WnGrid g = p.grid[f];
     if (cell >= g.ncells) return;
 
-    const size_t per_warp = sizeof(WarpShared) + (size_t)HC * p.hs * 3 * sizeof(double);
+    const size_t per_warp = sizeof(WarpShared) + (size_t)HC * p.hs * 4 * sizeof(double);
     WarpShared& ws = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)warp * per_warp);
     double* hdh = reinterpret_cast<double*>(smem_raw + (size_t)warp * per_warp + sizeof(WarpShared));
 
@@ -326,78 +184,148 @@ wn_k_edges(const WnEdgeParams p)
     const int h0 = __ldg(cs_f + cell), h1 = __ldg(cs_f + cell + 1);
     if (h0 == h1) return;
 
-    /* the 9 candidate runs: cells (cx-1..cx+1, cy+dy, cz+dz) are contiguous in x */
+    /* half shell: own cell + 13 forward neighbours as 5 runs contiguous in x
+     *   lane 0: (y  , z  ) cells x .. x+1      (own cell first)
+     *   lane 1: (y+1, z  ) cells x-1 .. x+1
+     *   lane 2..4: (y-1.., z+1) cells x-1 .. x+1                                   */
     const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
     int rs = 0, rl = 0;
-    if (lane < 9) {
-        const int y = cy + (lane % 3) - 1, z = cz + (lane / 3) - 1;
-        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
-            const int xlo = max(cx - 1, 0), xhi = min(cx + 1, g.nx - 1);
+    if (lane < MAXRUN) {
+        const int y = (lane == 0) ? cy : (lane == 1 ? cy + 1 : cy + lane - 3);
+        const int z = (lane < 2) ? cz : cz + 1;
+        if (y >= 0 && y < g.ny && z < g.nz) {
+            const int xlo = (lane == 0) ? cx : max(cx - 1, 0), xhi = min(cx + 1, g.nx - 1);
             const int rowc = (z * g.ny + y) * g.nx;
             rs = __ldg(cs_f + rowc + xlo);
             rl = __ldg(cs_f + rowc + xhi + 1) - rs;
         }
     }
-    /* compact the non-empty runs and prefix their lengths */
-    const unsigned nz = __ballot_sync(FULL, rl > 0);
-    const int n_runs = __popc(nz);
-    const int slot = __popc(nz & ((1u << lane) - 1u));
+    const unsigned nzm = __ballot_sync(FULL, rl > 0);
+    const int n_runs = __popc(nzm);
+    const int slot = __popc(nzm & ((1u << lane) - 1u));
     int inc = rl;
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
+    for (int o = 1; o < 8; o <<= 1) {
         const int t = __shfl_up_sync(FULL, inc, o);
         if (lane >= o) inc += t;
     }
-    const int total = __shfl_sync(FULL, inc, 8);
+    const int total = __shfl_sync(FULL, inc, MAXRUN - 1);
     if (rl > 0) { ws.run_start[slot] = rs; ws.run_pref[slot] = inc - rl; }
-    __syncwarp();
 
-    unsigned long long evals = 0, tie_len = 0, tie_cos = 0, tie_pos0 = 0;
-    /* One sweep call site, driven as a small state machine:
-     *   POOL on a chunk of <= HC rows -> on pool overflow, POOL one row at a time
-     *   -> if a single row still overflows: COUNT it, allocate, then DIRECT-write it. */
-    int hb = h0, hc = min(HC, h1 - h0), mode = MODE_POOL, split_end = -1;
-    unsigned long long direct_base = 0;
-    while (hb < h1) {
-        ChunkState cs = {};
-        cs.direct_base = direct_base;
-        wn_sweep<TYPED>(p, fbase, ws, hdh, hb, hc, n_runs, total, mode, cs, lane);
-        bool advance = false;
-        if (mode == MODE_POOL) {
-            if (!cs.overflow) {
-                wn_commit_pool(p, fbase, ws, hc, cs, lane);
-                evals += cs.evals; tie_len += cs.tie_len; tie_cos += cs.tie_cos; tie_pos0 += cs.tie_pos0;
-                advance = true;
-            } else if (hc > 1) {
-                split_end = hb + hc; hc = 1;
-            } else {
-                mode = MODE_COUNT;
+    /* cell-local frame for the fp32 prefilter: origin = minimum corner of the home cell */
+    const float edge = g.edge;
+    const float orx = (float)g.ox + (float)cx * edge, ory = (float)g.oy + (float)cy * edge,
+                orz = (float)g.oz + (float)cz * edge;
+    const float half_t = 0.5f * g.tf;
+
+    Counters ct = {0u, 0u, 0u, 0u};
+    for (int hb = h0; hb < h1; hb += HC) {
+        const int hc = min(HC, h1 - hb);
+        const int hc4 = (hc + 3) & ~3;
+        /* stage the home chunk; pad to a multiple of 4 with unreachable dummies */
+        __syncwarp();
+        if (lane < hc4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+            float4 l = make_float4(0.f, 0.f, 0.f, 3.0e38f);        /* t >= |c|^2/2 never holds */
+            uint32_t m = 0;
+            if (lane < hc) {
+                a = __ldg(p.spos + fbase + hb + lane);
+                m = __ldg(p.smeta + fbase + hb + lane);
+                const float lx = a.x - orx, ly = a.y - ory, lz = a.z - orz;
+                l = make_float4(lx, ly, lz, 0.5f * (lx * lx + ly * ly + lz * lz) - half_t);
             }
-        } else if (mode == MODE_COUNT) {
-            evals += cs.evals; tie_len += cs.tie_len; tie_cos += cs.tie_cos; tie_pos0 += cs.tie_pos0;
-            unsigned long long base = 0;
-            if (lane == 0) {
-                base = atomicAdd(p.temp_cursor, (unsigned long long)cs.direct_k);
-                p.row_pos[fbase + ws.hrow[0]] = (uint32_t)base;
-                p.row_cnt[fbase + ws.hrow[0]] = cs.direct_k;
-            }
-            direct_base = __shfl_sync(FULL, base, 0);
-            mode = MODE_DIRECT;
-        } else {
-            mode = MODE_POOL;
-            advance = true;
+            ws.hpos[lane] = a; ws.hloc[lane] = l; ws.hmeta[lane] = m;
         }
-        if (advance) {
-            hb += hc;
-            hc = (hb < split_end) ? 1 : min(HC, h1 - hb);
+        for (int t = lane; t < hc * p.hs * 4; t += 32)
+            hdh[t] = __ldg(p.sdh + (fbase + hb) * (size_t)p.hs * 4 + t);
+        __syncwarp();
+        /* rows >= first_limit own nothing: a pair needs min(index) < first_limit */
+        uint32_t low_rows = 0;
+        if (p.first_limit < p.n_sites) {
+            const bool low = lane < hc && __float_as_int(ws.hpos[lane].w) < p.first_limit;
+            low_rows = __ballot_sync(FULL, low);
+        }
+
+        int qlen = 0, run = 0;
+        const int rounds = (total + 31) >> 5;
+        for (int r = 0; r < rounds; ++r) {
+            const int v = r * 32 + lane;
+            float cx_ = 0.f, cy_ = 0.f, cz_ = 0.f, cn = 3.0e38f;      /* dummy: never reached */
+            uint32_t code_c = 0, allow = 0, cm = 0;
+            if (v < total) {
+                while (run + 1 < n_runs && v >= ws.run_pref[run + 1]) ++run;
+                const int c = ws.run_start[run] + (v - ws.run_pref[run]);
+                const float4 b4 = __ldg(p.spos + fbase + c);
+                cx_ = b4.x - orx; cy_ = b4.y - ory; cz_ = b4.z - orz;
+                cn = 0.5f * (cx_ * cx_ + cy_ * cy_ + cz_ * cz_);
+                code_c = (uint32_t)c;
+                /* own cell: only home rows stored before the candidate (each pair once) */
+                const int ahead = c - hb;
+                allow = (c >= h1) ? 0xffffffffu : (ahead >= 32 ? 0xffffffffu : (ahead <= 0 ? 0u : ((1u << ahead) - 1u)));
+                if (p.first_limit < p.n_sites && __float_as_int(b4.w) >= p.first_limit) allow &= low_rows;
+                if (!SIMPLE) cm = __ldg(p.smeta + fbase + c);
+            }
+            /* lane-private hit mask: bit h = home row h is a candidate partner */
+            uint32_t hits = 0;
+#pragma unroll
+            for (int gq = 0; gq < HC / 4; ++gq) {
+                if (gq * 4 < hc4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int h = gq * 4 + u;
+                        const float4 a = ws.hloc[h];
+                        /* d2 <= T  <=>  a.c - (|a|^2 - T)/2 >= |c|^2/2 */
+                        const float t = fmaf(a.z, cz_, fmaf(a.y, cy_, fmaf(a.x, cx_, -a.w)));
+                        bool pass = t >= cn;
+                        if (!SIMPLE) {
+                            /* type rule (:199-203) and the no-hydrogen rule (:205-208) */
+                            const uint32_t am = ws.hmeta[h];
+                            const uint32_t ta = am & WN_META_TYPE_MASK, tb = cm & WN_META_TYPE_MASK;
+                            const bool typ = (ta != tb) || (ta == WN_WATER && tb == WN_WATER);
+                            const bool anyh = ((am | cm) & WN_META_HASH) != 0;
+                            pass = pass && typ && anyh;
+                        }
+                        if (pass) hits |= (1u << h);
+                    }
+                }
+            }
+            hits &= allow;
+            /* warp scan of the hit counts -> dense queue positions */
+            const int cnt = __popc(hits);
+            int pinc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, pinc, o);
+                if (lane >= o) pinc += t;
+            }
+            const int tot = __shfl_sync(FULL, pinc, 31);
+            if (tot) {
+                int pos = qlen + pinc - cnt;
+                while (hits) {
+                    const int h = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    ws.queue[pos++] = ((uint32_t)h << 27) | code_c;
+                }
+                qlen += tot;
+                __syncwarp();
+                while (qlen >= 32) {
+                    wn_eval_batch<SIMPLE>(p, fbase, ws, hdh, qlen - 32, 32, ct, lane);
+                    qlen -= 32;
+                }
+                __syncwarp();
+            }
+        }
+        if (qlen > 0) {
+            __syncwarp();
+            wn_eval_batch<SIMPLE>(p, fbase, ws, hdh, 0, qlen, ct, lane);
         }
     }
     if (lane == 0) {
         WnFrameCounters* fc = p.counters + f;
-        if (evals) atomicAdd(&fc->evals, evals);
-        if (tie_len) atomicAdd(&fc->tie_len, tie_len);
-        if (tie_cos) atomicAdd(&fc->tie_cos, tie_cos);
-        if (tie_pos0) atomicAdd(&fc->tie_pos0, tie_pos0);
+        if (ct.evals) atomicAdd(&fc->evals, (unsigned long long)ct.evals);
+        if (ct.tie_len) atomicAdd(&fc->tie_len, (unsigned long long)ct.tie_len);
+        if (ct.tie_cos) atomicAdd(&fc->tie_cos, (unsigned long long)ct.tie_cos);
+        if (ct.tie_pos0) atomicAdd(&fc->tie_pos0, (unsigned long long)ct.tie_pos0);
     }
 }
 
@@ -405,14 +333,14 @@ wn_k_edges(const WnEdgeParams p)
 
 size_t wn_edges_smem_bytes(int hs)
 {
-    return (size_t)WARPS_PER_CTA * (sizeof(WarpShared) + (size_t)HC * hs * 3 * sizeof(double));
+    return (size_t)WARPS_PER_CTA * (sizeof(WarpShared) + (size_t)HC * hs * 4 * sizeof(double));
 }
 
 void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
     const size_t smem = wn_edges_smem_bytes(p.hs);
     dim3 grid((p.cell_cap + WARPS_PER_CTA - 1) / WARPS_PER_CTA, n_frames);
-    if (p.typed) {
+    if (p.simple) {
         cudaFuncSetAttribute(wn_k_edges<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         wn_k_edges<true><<<grid, WARPS_PER_CTA * 32, smem, st>>>(p);
     } else {

@@ -72,7 +72,7 @@ __device__ __forceinline__ double wn_compute_energy(double r, double cosine, con
 /* ---- per-frame exclusive scan of row counts, one block per frame ---- */
 __global__ void __launch_bounds__(1024)
 wn_k_rowscan(const uint32_t* __restrict__ row_cnt, int n_sites, uint32_t* __restrict__ row_off,
-             unsigned long long* __restrict__ frame_total)
+             unsigned long long* __restrict__ frame_total, uint32_t* __restrict__ frame_maxrow)
 {
     const int f = blockIdx.x;
     const uint32_t* cnt = row_cnt + (size_t)f * n_sites;
@@ -80,8 +80,10 @@ wn_k_rowscan(const uint32_t* __restrict__ row_cnt, int n_sites, uint32_t* __rest
     const int per = (n_sites + blockDim.x - 1) / blockDim.x;
     const int b = min(threadIdx.x * per, n_sites), e = min(b + per, n_sites);
     unsigned long long sum = 0;
-    for (int i = b; i < e; ++i) sum += cnt[i];
+    uint32_t mx = 0;
+    for (int i = b; i < e; ++i) { const uint32_t v = cnt[i]; sum += v; mx = max(mx, v); }
     __shared__ unsigned long long s_w[32];
+    __shared__ uint32_t s_mx[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long inc = sum;
 #pragma unroll
@@ -89,9 +91,15 @@ wn_k_rowscan(const uint32_t* __restrict__ row_cnt, int n_sites, uint32_t* __rest
         const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += v;
     }
-    if (lane == 31) s_w[warp] = inc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 31) { s_w[warp] = inc; s_mx[warp] = mx; }
     __syncthreads();
     if (warp == 0) {
+        uint32_t m2 = (lane < (int)(blockDim.x >> 5)) ? s_mx[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m2 = max(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        if (lane == 0) frame_maxrow[f] = m2;
         const unsigned long long v = (lane < (int)(blockDim.x >> 5)) ? s_w[lane] : 0ull;
         unsigned long long iv = v;
 #pragma unroll
@@ -109,9 +117,18 @@ wn_k_rowscan(const uint32_t* __restrict__ row_cnt, int n_sites, uint32_t* __rest
 
 /* ---- exclusive scan of the frame totals (single block) ---- */
 __global__ void __launch_bounds__(1024)
-wn_k_frameoff(const unsigned long long* __restrict__ frame_total, int n_frames,
-              unsigned long long base, unsigned long long* __restrict__ frame_off)
+wn_k_frameoff(const unsigned long long* __restrict__ frame_total, const uint32_t* __restrict__ frame_maxrow,
+              int n_frames, unsigned long long base, unsigned long long* __restrict__ frame_off,
+              unsigned long long* __restrict__ pass_info)
 {
+    __shared__ uint32_t s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    {
+        uint32_t mx = 0;
+        for (int i = threadIdx.x; i < n_frames; i += blockDim.x) mx = max(mx, frame_maxrow[i]);
+        if (mx) atomicMax(&s_max, mx);
+    }
     const int per = (n_frames + blockDim.x - 1) / blockDim.x;
     const int b = min(threadIdx.x * per, n_frames), e = min(b + per, n_frames);
     unsigned long long sum = 0;
@@ -135,9 +152,10 @@ wn_k_frameoff(const unsigned long long* __restrict__ frame_total, int n_frames,
             if (lane >= o) iv += t;
         }
         s_w[lane] = iv - v;
-        if (lane == 31) frame_off[n_frames] = base + iv;
+        if (lane == 31) { frame_off[n_frames] = base + iv; pass_info[0] = base + iv; }
     }
     __syncthreads();
+    if (threadIdx.x == 0) pass_info[1] = s_max;
     unsigned long long run = base + s_w[warp] + inc - sum;
     for (int i = b; i < e; ++i) { frame_off[i] = run; run += frame_total[i]; }
 }
@@ -148,7 +166,7 @@ wn_k_frameoff(const unsigned long long* __restrict__ frame_total, int n_frames,
  * (row found by a shuffle binary search over the row prefix), ranks it inside its
  * row by j, evaluates the energy and stores it at span_base + row_prefix + rank. */
 __global__ void __launch_bounds__(COPY_THREADS)
-wn_k_copy(const WnTempEdge* __restrict__ temp, const uint32_t* __restrict__ row_pos,
+wn_k_copy(const WnTempEdge* __restrict__ rowbuf, int row_cap,
           const uint32_t* __restrict__ row_cnt, const uint32_t* __restrict__ row_off,
           const unsigned long long* __restrict__ frame_off, int n_sites, WnEnergyParams ep,
           wn_edge* __restrict__ edges, unsigned long long edge_cap, unsigned long long edge_base,
@@ -160,7 +178,6 @@ wn_k_copy(const WnTempEdge* __restrict__ temp, const uint32_t* __restrict__ row_
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t o = (size_t)f * n_sites + (row < n_sites ? row : 0);
     const uint32_t cnt = row < n_sites ? row_cnt[o] : 0u;
-    const uint32_t pos = row < n_sites ? row_pos[o] : 0u;
     const uint32_t off = row < n_sites ? row_off[o] : 0u;
     /* exclusive prefix of the row lengths inside the warp */
     uint32_t inc = cnt;
@@ -186,9 +203,8 @@ wn_k_copy(const WnTempEdge* __restrict__ temp, const uint32_t* __restrict__ row_
             }
             const uint32_t rpre = __shfl_sync(FULL, pre, r);
             const uint32_t rcnt = __shfl_sync(FULL, cnt, r);
-            const uint32_t rpos = __shfl_sync(FULL, pos, r);
             if (e0 + lane < total) {
-                const WnTempEdge* rowp = temp + rpos;
+                const WnTempEdge* rowp = rowbuf + ((size_t)f * n_sites + (blockIdx.x * blockDim.x + warp * 32 + r)) * row_cap;
                 const WnTempEdge t = rowp[e - rpre];
                 uint32_t rank = 0;
                 for (uint32_t k = 0; k < rcnt; ++k) rank += (rowp[k].j < t.j) ? 1u : 0u;
@@ -243,18 +259,20 @@ wn_k_stats(const double* __restrict__ block_sums, int n_blocks,
 }  // namespace
 
 void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
-                       uint32_t* row_off, unsigned long long* frame_total, cudaStream_t st)
+                       uint32_t* row_off, unsigned long long* frame_total, uint32_t* frame_maxrow,
+                       cudaStream_t st)
 {
-    wn_k_rowscan<<<n_frames, 1024, 0, st>>>(row_cnt, n_sites, row_off, frame_total);
+    wn_k_rowscan<<<n_frames, 1024, 0, st>>>(row_cnt, n_sites, row_off, frame_total, frame_maxrow);
 }
 
-void wn_launch_frameoff(const unsigned long long* frame_total, int n_frames,
-                        unsigned long long base, unsigned long long* frame_off, cudaStream_t st)
+void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* frame_maxrow, int n_frames,
+                        unsigned long long base, unsigned long long* frame_off,
+                        unsigned long long* pass_info, cudaStream_t st)
 {
-    wn_k_frameoff<<<1, 1024, 0, st>>>(frame_total, n_frames, base, frame_off);
+    wn_k_frameoff<<<1, 1024, 0, st>>>(frame_total, frame_maxrow, n_frames, base, frame_off, pass_info);
 }
 
-void wn_launch_copy(const WnTempEdge* temp, const uint32_t* row_pos, const uint32_t* row_cnt,
+void wn_launch_copy(const WnTempEdge* rowbuf, int row_cap, const uint32_t* row_cnt,
                     const uint32_t* row_off, const unsigned long long* frame_off,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
                     unsigned long long edge_cap, double* block_sums, int* n_blocks_out,
@@ -262,7 +280,7 @@ void wn_launch_copy(const WnTempEdge* temp, const uint32_t* row_pos, const uint3
 {
     dim3 g((n_sites + COPY_THREADS - 1) / COPY_THREADS, n_frames);
     *n_blocks_out = (int)g.x;
-    wn_k_copy<<<g, COPY_THREADS, 0, st>>>(temp, row_pos, row_cnt, row_off, frame_off, n_sites, ep,
+    wn_k_copy<<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
                                           edges, edge_cap, 0ull, block_sums);
 }
 
