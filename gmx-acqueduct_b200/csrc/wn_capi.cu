@@ -51,11 +51,14 @@ struct wn_ctx {
     uint32_t* d_frame_maxrow = nullptr;
     unsigned long long* d_pass_info = nullptr;
     double* d_block_sums = nullptr;
-    WnTempEdge* d_rowbuf = nullptr;
-    size_t rowbuf_cap = 0;          /* entries */
+    uint32_t* d_rowbuf = nullptr;
+    size_t rowbuf_cap = 0;          /* 32-bit words */
     int row_cap = 32;               /* slots per row; grows (sticky) when a row overflows */
-    float* d_stage = nullptr;      /* host variant: frames of one pass */
-    size_t stage_cap = 0;
+    float* d_stage[2] = {nullptr, nullptr};   /* host variant: frames of one pass, ping-pong */
+    size_t stage_cap[2] = {0, 0};
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;   /* copy streams: PCIe both ways under the kernels */
+    cudaEvent_t ev_stage[2] = {};
+    std::vector<cudaEvent_t> ev_copy;         /* per-pass copy timing events (4 per pass) */
 
     /* call-wide outputs (device) */
     wn_edge* d_edges = nullptr;
@@ -130,7 +133,7 @@ int dev_ensure(wn_ctx* ctx, T** p, size_t* cap, size_t need, bool preserve = fal
     WN_CK(cudaMalloc((void**)&np, ncap * sizeof(T)));
     if (preserve && *p && used)
         WN_CK(cudaMemcpyAsync(np, *p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->st));
-    if (*p) { WN_CK(cudaStreamSynchronize(ctx->st)); WN_CK(cudaFree(*p)); }
+    if (*p) { WN_CK(cudaDeviceSynchronize()); WN_CK(cudaFree(*p)); }   /* rare: copies may be in flight */
     *p = np;
     *cap = ncap;
     return WN_OK;
@@ -152,6 +155,7 @@ int host_ensure(wn_ctx* ctx, T** p, size_t* cap, size_t need, bool preserve = fa
     if (ncap == 0) ncap = 1;
     T* np = nullptr;
     WN_CK(cudaMallocHost((void**)&np, ncap * sizeof(T)));
+    if (*p) WN_CK(cudaDeviceSynchronize());               /* D2H into the old block may be in flight */
     if (preserve && *p && used) memcpy(np, *p, used * sizeof(T));
     if (*p) WN_CK(cudaFreeHost(*p));
     *p = np;
@@ -233,7 +237,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
     cudaStream_t st = ctx->st;
     int rc;
     /* a pass whose row buffers would not fit is split (dense inputs after row_cap grew) */
-    if (nf > 1 && (size_t)nf * N * ctx->row_cap * sizeof(WnTempEdge) > WN_ROWBUF_BUDGET) {
+    if (nf > 1 && (size_t)nf * N * ctx->row_cap * WN_ROW_WORDS * sizeof(uint32_t) > WN_ROWBUF_BUDGET) {
         const int half = nf / 2;
         if ((rc = run_pass(ctx, d_frames, half, natoms, f0, edge_base))) return rc;
         return run_pass(ctx, d_frames + (size_t)half * natoms * 3, nf - half, natoms, f0 + half, edge_base);
@@ -255,7 +259,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
 
     unsigned long long end_off = 0;
     for (int attempt = 0;; ++attempt) {
-        if ((rc = dev_ensure(ctx, &ctx->d_rowbuf, &ctx->rowbuf_cap, (size_t)nf * N * ctx->row_cap))) return rc;
+        if ((rc = dev_ensure(ctx, &ctx->d_rowbuf, &ctx->rowbuf_cap, (size_t)nf * N * ctx->row_cap * WN_ROW_WORDS))) return rc;
         WN_CK(cudaMemsetAsync(ctx->d_row_cnt, 0, (size_t)nf * N * sizeof(uint32_t), st));
         WN_CK(cudaMemsetAsync(ctx->d_counters, 0, (size_t)nf * sizeof(WnFrameCounters), st));
         WnEdgeParams p;
@@ -282,7 +286,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
         int nc = ctx->row_cap;
         while ((unsigned long long)nc < max_row) nc *= 2;
         ctx->row_cap = nc;
-        if (nf > 1 && (size_t)nf * N * nc * sizeof(WnTempEdge) > WN_ROWBUF_BUDGET) {
+        if (nf > 1 && (size_t)nf * N * nc * WN_ROW_WORDS * sizeof(uint32_t) > WN_ROWBUF_BUDGET) {
             const int half = nf / 2;
             if ((rc = run_pass(ctx, d_frames, half, natoms, f0, edge_base))) return rc;
             return run_pass(ctx, d_frames + (size_t)half * natoms * 3, nf - half, natoms, f0 + half, edge_base);
@@ -350,38 +354,54 @@ int batch_common(wn_ctx* ctx, const float* frames, bool host_in, int n_frames, i
 
     const int fpp = ctx->user_frames_per_pass > 0 ? ctx->user_frames_per_pass : default_frames_per_pass(N);
     const size_t frame_floats = (size_t)natoms * 3;
-    cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5];
-    for (int f0 = 0; f0 < n_frames; f0 += fpp) {
-        const int nf = std::min(fpp, n_frames - f0);
-        const float* d_in = frames + (size_t)f0 * frame_floats;
-        if (host_in) {
-            if ((rc = dev_ensure(ctx, &ctx->d_stage, &ctx->stage_cap, (size_t)nf * frame_floats))) return rc;
-            WN_CK(cudaEventRecord(e0, ctx->st));
-            WN_CK(cudaMemcpyAsync(ctx->d_stage, d_in, (size_t)nf * frame_floats * sizeof(float),
-                                  cudaMemcpyHostToDevice, ctx->st));
-            WN_CK(cudaEventRecord(e1, ctx->st));
-            d_in = ctx->d_stage;
+    const int n_pass = (n_frames + fpp - 1) / fpp;
+    if (host_in) {
+        /* Host variant, pipelined: the H2D copy of pass k+1 (st_h2d) and the D2H copy of the
+         * edges of pass k-1 (st_d2h) run under the kernels of pass k (st). */
+        while (ctx->ev_copy.size() < (size_t)4 * n_pass) {
+            cudaEvent_t e; WN_CK(cudaEventCreate(&e)); ctx->ev_copy.push_back(e);
         }
-        const unsigned long long before = edge_base;
-        if ((rc = run_pass(ctx, d_in, nf, natoms, (size_t)f0, &edge_base))) return rc;
-        if (host_in) {
-            float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->tm.h2d_ms += ms;
-            /* results of this pass -> pinned host */
-            const size_t need = (size_t)edge_base;
-            if (need > ctx->h_edges_cap) {
+        auto stage_in = [&](int k) -> int {
+            const int f0 = k * fpp, nf = std::min(fpp, n_frames - f0), b = k & 1;
+            int rc2;
+            if ((rc2 = dev_ensure(ctx, &ctx->d_stage[b], &ctx->stage_cap[b], (size_t)nf * frame_floats))) return rc2;
+            WN_CK(cudaEventRecord(ctx->ev_copy[4 * k], ctx->st_h2d));
+            WN_CK(cudaMemcpyAsync(ctx->d_stage[b], frames + (size_t)f0 * frame_floats,
+                                  (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->st_h2d));
+            WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 1], ctx->st_h2d));
+            WN_CK(cudaEventRecord(ctx->ev_stage[b], ctx->st_h2d));
+            return WN_OK;
+        };
+        if ((rc = stage_in(0))) return rc;
+        for (int k = 0; k < n_pass; ++k) {
+            const int f0 = k * fpp, nf = std::min(fpp, n_frames - f0);
+            if (k + 1 < n_pass && (rc = stage_in(k + 1))) return rc;
+            WN_CK(cudaStreamWaitEvent(ctx->st, ctx->ev_stage[k & 1], 0));
+            const unsigned long long before = edge_base;
+            if ((rc = run_pass(ctx, ctx->d_stage[k & 1], nf, natoms, (size_t)f0, &edge_base))) return rc;
+            if ((size_t)edge_base > ctx->h_edges_cap) {
                 /* project the whole call from the density seen so far */
                 const double per_frame = (double)edge_base / (double)(f0 + nf);
-                size_t want = (size_t)(per_frame * n_frames * 1.05) + 1024;
-                if ((rc = host_ensure(ctx, &ctx->h_edges, &ctx->h_edges_cap, std::max(want, need), true,
+                const size_t want = (size_t)(per_frame * n_frames * 1.05) + 1024;
+                if ((rc = host_ensure(ctx, &ctx->h_edges, &ctx->h_edges_cap, std::max(want, (size_t)edge_base), true,
                                       (size_t)before))) return rc;
             }
-            WN_CK(cudaEventRecord(e0, ctx->st));
+            WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 2], ctx->st_d2h));
             if (edge_base > before)
                 WN_CK(cudaMemcpyAsync(ctx->h_edges + before, ctx->d_edges + before,
-                                      (size_t)(edge_base - before) * sizeof(wn_edge), cudaMemcpyDeviceToHost, ctx->st));
-            WN_CK(cudaEventRecord(e1, ctx->st));
-            WN_CK(cudaStreamSynchronize(ctx->st));
-            cudaEventElapsedTime(&ms, e0, e1); ctx->tm.d2h_ms += ms;
+                                      (size_t)(edge_base - before) * sizeof(wn_edge), cudaMemcpyDeviceToHost, ctx->st_d2h));
+            WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 3], ctx->st_d2h));
+        }
+        WN_CK(cudaStreamSynchronize(ctx->st_d2h));
+        for (int k = 0; k < n_pass; ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev_copy[4 * k], ctx->ev_copy[4 * k + 1]); ctx->tm.h2d_ms += ms;
+            cudaEventElapsedTime(&ms, ctx->ev_copy[4 * k + 2], ctx->ev_copy[4 * k + 3]); ctx->tm.d2h_ms += ms;
+        }
+    } else {
+        for (int f0 = 0; f0 < n_frames; f0 += fpp) {
+            const int nf = std::min(fpp, n_frames - f0);
+            if ((rc = run_pass(ctx, frames + (size_t)f0 * frame_floats, nf, natoms, (size_t)f0, &edge_base))) return rc;
         }
     }
     /* small per-frame tables always come back to the host: totals and ties */
@@ -450,6 +470,9 @@ int wn_create(int device, wn_ctx** out)
     } while (0)
     WN_CKC(cudaSetDevice(device));
     WN_CKC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    WN_CKC(cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking));
+    WN_CKC(cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking));
+    for (auto& ev : ctx->ev_stage) WN_CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->ev) WN_CKC(cudaEventCreate(&ev));
     WN_CKC(cudaMallocHost((void**)&ctx->h_scalars, 64 * sizeof(unsigned long long)));
     WN_CKC(cudaMalloc((void**)&ctx->d_pair_ties, sizeof(unsigned long long)));
@@ -462,7 +485,7 @@ void wn_destroy(wn_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    cudaDeviceSynchronize();
     if (ctx->comm && ctx->nccl_lib) {
         typedef ncclResult_t (*destroy_t)(ncclComm_t);
         destroy_t fn = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
@@ -471,12 +494,16 @@ void wn_destroy(wn_ctx* ctx)
     void* dev[] = {ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, ctx->d_grid, ctx->d_cell_cnt, ctx->d_site_cell,
                    ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_cnt,
                    ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_pass_info,
-                   ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage, ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
+                   ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_copy) cudaEventDestroy(ev);
+    if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
+    if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }

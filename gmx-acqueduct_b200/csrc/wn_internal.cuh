@@ -48,13 +48,9 @@ struct WnEnergyParams {
     double a_on, a_off;    /* angle switch slots after the caller-side swap      */
 };
 
-/* row-buffer entry produced by the fused kernel, consumed by the ordered copy */
-struct __align__(16) WnTempEdge {
-    int32_t j;
-    float   length;
-    float   cosine;
-    int32_t pad;
-};
+/* Row buffers produced by the fused kernel, consumed by the ordered copy: per row
+ * row_cap entries of 4 32-bit words {j, length bits, cosine bits, unused}. */
+#define WN_ROW_WORDS 4
 
 /* ---- fused-path launch parameters ---- */
 struct WnEdgeParams {
@@ -63,7 +59,7 @@ struct WnEdgeParams {
     const double*   sdh;        /* [F][N][hs][4] sorted unit D-H vectors (x,y,z,pad) */
     const int*      cell_start; /* [F][cell_cap+1]                                */
     const WnGrid*   grid;       /* [F]                                            */
-    WnTempEdge*     rowbuf;     /* [F][N][row_cap] edges of row i, arrival order  */
+    uint32_t*       rowbuf;     /* [F][N][row_cap][4] edges of row i, arrival order */
     uint32_t*       row_cnt;    /* [F][N] edges owned by the row (zeroed before)  */
     WnFrameCounters* counters;  /* [F]                                            */
     int n_sites;
@@ -95,7 +91,7 @@ void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
 void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* frame_maxrow, int n_frames,
                         unsigned long long base, unsigned long long* frame_off,
                         unsigned long long* pass_info, cudaStream_t st);
-void wn_launch_copy(const WnTempEdge* rowbuf, int row_cap, const uint32_t* row_cnt,
+void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
                     const uint32_t* row_off, const unsigned long long* frame_off,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
                     unsigned long long edge_cap, double* block_sums, int* n_blocks_out,

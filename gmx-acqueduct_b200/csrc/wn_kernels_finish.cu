@@ -166,7 +166,7 @@ wn_k_frameoff(const unsigned long long* __restrict__ frame_total, const uint32_t
  * (row found by a shuffle binary search over the row prefix), ranks it inside its
  * row by j, evaluates the energy and stores it at span_base + row_prefix + rank. */
 __global__ void __launch_bounds__(COPY_THREADS)
-wn_k_copy(const WnTempEdge* __restrict__ rowbuf, int row_cap,
+wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
           const uint32_t* __restrict__ row_cnt, const uint32_t* __restrict__ row_off,
           const unsigned long long* __restrict__ frame_off, int n_sites, WnEnergyParams ep,
           wn_edge* __restrict__ edges, unsigned long long edge_cap, unsigned long long edge_base,
@@ -204,17 +204,21 @@ wn_k_copy(const WnTempEdge* __restrict__ rowbuf, int row_cap,
             const uint32_t rpre = __shfl_sync(FULL, pre, r);
             const uint32_t rcnt = __shfl_sync(FULL, cnt, r);
             if (e0 + lane < total) {
-                const WnTempEdge* rowp = rowbuf + ((size_t)f * n_sites + (blockIdx.x * blockDim.x + warp * 32 + r)) * row_cap;
-                const WnTempEdge t = rowp[e - rpre];
+                const int irow = blockIdx.x * blockDim.x + warp * 32 + r;
+                const uint4* rowp = reinterpret_cast<const uint4*>(rowbuf) + ((size_t)f * n_sites + irow) * (size_t)row_cap;
+                const uint4 t = rowp[e - rpre];
+                const int tj = (int)t.x;
+                const float tlen = __uint_as_float(t.y), tcos = __uint_as_float(t.z);
+                /* rank inside the row by j */
                 uint32_t rank = 0;
-                for (uint32_t k = 0; k < rcnt; ++k) rank += (rowp[k].j < t.j) ? 1u : 0u;
+                for (uint32_t k = 0; k < rcnt; ++k) rank += ((int)rowp[k].x < tj) ? 1u : 0u;
                 wn_edge out;
-                out.i = blockIdx.x * blockDim.x + warp * 32 + r;
-                out.j = t.j;
+                out.i = irow;
+                out.j = tj;
                 /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
-                out.energy = __double2float_rn(wn_compute_energy((double)t.length, (double)t.cosine, ep));
-                out.length = t.length;
-                out.cosine = t.cosine;
+                out.energy = __double2float_rn(wn_compute_energy((double)tlen, (double)tcos, ep));
+                out.length = tlen;
+                out.cosine = tcos;
                 edges[span + rpre + rank] = out;
             }
         }
@@ -272,7 +276,7 @@ void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* f
     wn_k_frameoff<<<1, 1024, 0, st>>>(frame_total, frame_maxrow, n_frames, base, frame_off, pass_info);
 }
 
-void wn_launch_copy(const WnTempEdge* rowbuf, int row_cap, const uint32_t* row_cnt,
+void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
                     const uint32_t* row_off, const unsigned long long* frame_off,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
                     unsigned long long edge_cap, double* block_sums, int* n_blocks_out,

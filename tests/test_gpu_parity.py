@@ -193,3 +193,96 @@ def test_nonfinite_coordinates_are_ignored(ctx, oracle):
     fo = res["frame_offsets"]
     for f, want in enumerate(oe):
         check_edges(res["edges"][int(fo[f]):int(fo[f + 1])], want)
+
+
+# ------------------------------------------------------------ BASELINE configurations
+def test_config2_buried_group_4000_waters(ctx, oracle):
+    """configs[1]: 4k waters + buried-water index group (the waters nearest the box
+    centre at frame 0), here as the site table of the batch."""
+    n = 4000
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 0, 3)
+    centre = box.box / 2
+    d = np.linalg.norm(frames[0][::3] - centre, axis=1)
+    group = np.sort(np.argsort(d)[:600]).astype(np.int32)
+    site_atom = 3 * group
+    h_atom = np.stack([3 * group, 3 * group + 1], axis=1).astype(np.int32)
+    ty = np.full(len(group), oracle.WATER, np.uint8)
+    ctx.set_sites(site_atom, h_atom, ty)
+    res = ctx.hbond_batch(frames)
+    compare_batch(res, *oracle_frames(oracle, frames, site_atom, h_atom, ty))
+
+
+def test_config5_asymmetric_selection_vs_solvent(ctx, oracle):
+    """configs[4]: ~500-water selection vs the full solvent set: selection placed first,
+    rows restricted to i < 500 (many short frames)."""
+    n, nsel, nf = 4000, 500, 12
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 50, nf)
+    d = np.linalg.norm(frames[0][::3] - box.box / 2, axis=1)
+    order = np.argsort(d, kind="stable")
+    waters = np.concatenate([np.sort(order[:nsel]), np.sort(order[nsel:])]).astype(np.int32)
+    site_atom = 3 * waters
+    h_atom = np.stack([3 * waters, 3 * waters + 1], axis=1).astype(np.int32)
+    ty = np.full(n, oracle.WATER, np.uint8)
+    ctx.set_sites(site_atom, h_atom, ty, first_limit=nsel)
+    res = ctx.hbond_batch(frames)
+    compare_batch(res, *oracle_frames(oracle, frames, site_atom, h_atom, ty, first_limit=nsel))
+
+
+def test_full_size_100k_atoms_properties(ctx, oracle):
+    """configs[2] at full size (33,333 waters): size-independent properties plus exact
+    parity on the first 150 rows (the oracle restricted to rows i < 150 is O(150*N))."""
+    n, nf = 33333, 3
+    d = ctx.dev_alloc(nf * 3 * n * 12)
+    ctx.synth_frames_dev(n, 1000, nf, d)
+    frames = np.empty((nf, 3 * n, 3), np.float32)
+    ctx.d2h(frames, d)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    out = ctx.hbond_batch_dev(d, nf, 3 * n)
+    e, fo, st = ctx.fetch_dev_result(out)
+    # host entry point, split in passes of 2 frames: identical bytes
+    ctx.set_batch_frames(2)
+    res = ctx.hbond_batch(frames)
+    ctx.set_batch_frames(0)
+    assert np.array_equal(res["frame_offsets"], fo) and res["edges"].tobytes() == e.tobytes()
+    assert res["stats"].tobytes() == st.tobytes()
+    for f in range(nf):
+        ef = e[int(fo[f]):int(fo[f + 1])]
+        assert np.all(ef["i"] < ef["j"]) and ef["j"].max() < n
+        key = ef["i"].astype(np.int64) * n + ef["j"]
+        assert np.all(np.diff(key) > 0)                      # lexicographic, no duplicates
+        assert np.all(ef["length"] <= np.float32(6.5)) and np.all(ef["cosine"] > 0)
+        # geometry recomputed on the host in the reference's operation order for every edge
+        a = frames[f][3 * ef["i"]].astype(np.float64); b = frames[f][3 * ef["j"]].astype(np.float64)
+        oo = a - b
+        dist = np.sqrt((oo[:, 0] * oo[:, 0] + oo[:, 1] * oo[:, 1]) + oo[:, 2] * oo[:, 2]).astype(np.float32)
+        assert np.array_equal((dist.astype(np.float64) * 10.0).astype(np.float32), ef["length"])
+        assert st["num_edges"][f] == len(ef) and st["num_sites"][f] == n
+        assert np.isclose(st["sum_energy"][f], ef["energy"].astype(np.float64).sum(), rtol=1e-9)
+    # exact parity on the first rows
+    ctx.set_water_sites(n, first_limit=150)
+    res2 = ctx.hbond_batch(frames[:2])
+    for f in range(2):
+        want, stats, _, ev = oracle.frame_hbonds(frames[f], sa, ha, ty, first_limit=150)
+        got = res2["edges"][int(res2["frame_offsets"][f]):int(res2["frame_offsets"][f + 1])]
+        check_edges(got, want)
+        full = e[int(fo[f]):int(fo[f + 1])]
+        check_edges(full[full["i"] < 150], want)
+        assert int(res2["stats"]["pair_evals"][f]) == ev
+    ctx.dev_free(d)
+
+
+def test_find_pairs_full_size_rows(ctx, oracle):
+    """CudaFindPairs at 33,333 sites: total count, order, and exact rows vs the oracle."""
+    n = 33333
+    box = oracle.synth_box(n)
+    xyz = oracle.synth_frames(box, 0, 1)[0][::3].astype(np.float64)
+    got, ties = ctx.find_pairs(xyz)
+    key = got[:, 0].astype(np.int64) * n + got[:, 1]
+    assert np.all(np.diff(key) > 0) and np.all(got[:, 0] < got[:, 1])
+    want = oracle.brute_find_pairs(xyz, first_limit=64)
+    assert np.array_equal(got[got[:, 0] < 64], want)
+    lim, _ = ctx.find_pairs(xyz, first_limit=64)
+    assert np.array_equal(lim, want)
