@@ -163,6 +163,14 @@ int host_ensure(wn_ctx* ctx, T** p, size_t* cap, size_t need, bool preserve = fa
     return WN_OK;
 }
 
+/* pow(pow(r_off,2)-pow(r_on,2),3) of switch_function_radius (src/waternetwork.cpp:20),
+ * with r_on/r_off the squared radii computeEnergy passes (:57) */
+void set_radial_denominator(WnEnergyParams& ep)
+{
+    const double d = ep.off2 * ep.off2 - ep.on2 * ep.on2;
+    ep.inv_denom_r = 1.0 / (d * d * d);
+}
+
 int default_frames_per_pass(int n_sites)
 {
     const long long target = 8ll << 20;    /* site-frames per pass */
@@ -463,6 +471,7 @@ int wn_create(int device, wn_ctx** out)
     ctx->device = device;
     ctx->ep.on2 = 5.5 * 5.5; ctx->ep.off2 = 6.5 * 6.5;
     ctx->ep.a_on = 0.0; ctx->ep.a_off = 0.25;      /* (theta_off, theta_on): caller-side swap, :59-60 */
+    set_radial_denominator(ctx->ep);
 #define WN_CKC(call)                                                            \
     do {                                                                        \
         cudaError_t e2_ = (call);                                               \
@@ -588,6 +597,7 @@ int wn_set_energy_params(wn_ctx* ctx, double r_on, double r_off, double theta_on
      * (cos*cos, theta_off, theta_on) to the angle switch (src/waternetwork.cpp:57-60) */
     ctx->ep.on2 = r_on * r_on; ctx->ep.off2 = r_off * r_off;
     ctx->ep.a_on = theta_off; ctx->ep.a_off = theta_on;
+    set_radial_denominator(ctx->ep);
     return WN_OK;
 }
 

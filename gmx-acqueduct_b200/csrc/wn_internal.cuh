@@ -46,6 +46,7 @@ struct WnFrameCounters {
 struct WnEnergyParams {
     double on2, off2;      /* r_on^2, r_off^2 (arguments of the radial switch)   */
     double a_on, a_off;    /* angle switch slots after the caller-side swap      */
+    double inv_denom_r;    /* 1 / (off2^2 - on2^2)^3 of the radial switch          */
 };
 
 /* Row buffers produced by the fused kernel, consumed by the ordered copy: per row

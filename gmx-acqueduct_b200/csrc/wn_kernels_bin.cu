@@ -82,9 +82,10 @@ wn_k_bbox(const float* __restrict__ frames, int natoms, const int* __restrict__ 
             g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
             g.ncells = g.nx * g.ny * g.nz;
             /* fp32 prefilter bound: exact acceptance needs d2 <= 0.4225*(1+2.5e-7); the
-             * dot-product form on cell-local coordinates (|a| <= sqrt(3) e, |c| <= 2 sqrt(3) e)
-             * errs by <= ~2.2e-6 e^2 + 5.5e-7 e; bound with > 2x head-room, rounded up */
-            const double tfd = 0.4225 * (1.0 + 1.0e-5) + 5.0e-6 * edge * edge + 1.5e-6 * edge;
+             * dot-product form on block-local coordinates (|a|^2 <= 1.5 e^2, |c|^2 <= 8.5 e^2,
+             * six fp32 roundings on terms <= 8.5 e^2, coordinates rounded at <= 6e-8 * 2e)
+             * errs by <= ~3.1e-6 e^2 + 5e-7 e; bound with > 2x head-room, rounded up */
+            const double tfd = 0.4225 * (1.0 + 1.0e-5) + 8.0e-6 * edge * edge + 2.0e-6 * edge;
             g.edge = (float)edge;
             g.tf = __double2float_ru(tfd);
         }

@@ -10,10 +10,11 @@
  * (src/brute-find-pairs.cpp:25), so searching the neighbouring cells of a grid
  * with edge >= 0.65 nm finds exactly the pairs that matter.
  *
- * Work decomposition: one warp per (frame, home cell), HALF SHELL: the warp pairs
- * its home sites with the sites of the 13 "forward" neighbour cells and with the
- * later sites of its own cell, so every unordered pair is examined exactly once
- * (5 contiguous runs of the cell-sorted site array).  lane = candidate, unrolled
+ * Work decomposition: one warp per (frame, home block of BX=2 x-adjacent cells),
+ * HALF SHELL: the warp pairs its home sites with the sites of the "forward"
+ * neighbour cells of the block and with the later sites of the block itself, so
+ * every unordered pair is examined exactly once (5 contiguous runs of the
+ * cell-sorted site array).  lane = candidate, unrolled
  * inner loop = home sites (broadcast from shared memory).
  *   search : fp32 prefilter in dot-product form on cell-local coordinates,
  *            a.c - (|a|^2 - T)/2 >= |c|^2/2   (3 FFMA + 1 FSETP per test),
@@ -44,8 +45,10 @@ namespace {
 #define WN_EDGES_MINBLOCKS 5   /* measured: 3 -> 4.33, 4 -> 3.71, 5 -> 3.28, 6 -> 3.57 ms / 250 frames */
 #endif
 constexpr int WARPS_PER_CTA = 8;
-constexpr int HC   = 16;                 /* home sites per chunk                      */
-constexpr int QCAP = 32 + 32 * HC;       /* queue: < 32 carried + one round of pushes */
+constexpr int BX   = 2;                  /* home block: BX cells along x (fewer, fuller rounds) */
+constexpr int HC   = 32;                 /* home sites per chunk (one hit-mask bit each)       */
+constexpr int HPUSH = 16;                /* hit-mask bits pushed per scan                       */
+constexpr int QCAP = 32 + 32 * HPUSH;    /* queue: < 32 carried + one push of <= 32*HPUSH codes */
 constexpr int MAXRUN = 5;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -176,9 +179,10 @@ wn_k_edges(const WnEdgeParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
-    const int cell = blockIdx.x * WARPS_PER_CTA + warp;
+    const int blk = blockIdx.x * WARPS_PER_CTA + warp;
     const WnGrid g = p.grid[f];
-    if (cell >= g.ncells) return;
+    const int nbx = (g.nx + BX - 1) / BX;
+    if (blk >= nbx * g.ny * g.nz) return;
 
     const size_t per_warp = sizeof(WarpShared) + (size_t)HC * p.hs * 4 * sizeof(double);
     WarpShared& ws = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)warp * per_warp);
@@ -186,20 +190,23 @@ wn_k_edges(const WnEdgeParams p)
 
     const size_t fbase = (size_t)f * p.n_sites;
     const int* cs_f = p.cell_start + (size_t)f * (p.cell_cap + 1);
-    const int h0 = __ldg(cs_f + cell), h1 = __ldg(cs_f + cell + 1);
+    /* home block: cells x0..x1 of row (cy, cz) -- contiguous in the cell-sorted array */
+    const int bx = blk % nbx, cy = (blk / nbx) % g.ny, cz = blk / (nbx * g.ny);
+    const int x0 = bx * BX, x1 = min(x0 + BX - 1, g.nx - 1);
+    const int row0 = (cz * g.ny + cy) * g.nx;
+    const int h0 = __ldg(cs_f + row0 + x0), h1 = __ldg(cs_f + row0 + x1 + 1);
     if (h0 == h1) return;
 
-    /* half shell: own cell + 13 forward neighbours as 5 runs contiguous in x
-     *   lane 0: (y  , z  ) cells x .. x+1      (own cell first)
-     *   lane 1: (y+1, z  ) cells x-1 .. x+1
-     *   lane 2..4: (y-1.., z+1) cells x-1 .. x+1                                   */
-    const int cx = cell % g.nx, cy = (cell / g.nx) % g.ny, cz = cell / (g.nx * g.ny);
+    /* half shell of the block: own cells + forward neighbours as 5 runs contiguous in x
+     *   lane 0: (y  , z  ) cells x0 .. x1+1      (own cells first)
+     *   lane 1: (y+1, z  ) cells x0-1 .. x1+1
+     *   lane 2..4: (y-1.., z+1) cells x0-1 .. x1+1                                   */
     int rs = 0, rl = 0;
     if (lane < MAXRUN) {
         const int y = (lane == 0) ? cy : (lane == 1 ? cy + 1 : cy + lane - 3);
         const int z = (lane < 2) ? cz : cz + 1;
         if (y >= 0 && y < g.ny && z < g.nz) {
-            const int xlo = (lane == 0) ? cx : max(cx - 1, 0), xhi = min(cx + 1, g.nx - 1);
+            const int xlo = (lane == 0) ? x0 : max(x0 - 1, 0), xhi = min(x1 + 1, g.nx - 1);
             const int rowc = (z * g.ny + y) * g.nx;
             rs = __ldg(cs_f + rowc + xlo);
             rl = __ldg(cs_f + rowc + xhi + 1) - rs;
@@ -217,10 +224,12 @@ wn_k_edges(const WnEdgeParams p)
     const int total = __shfl_sync(FULL, inc, MAXRUN - 1);
     if (rl > 0) { ws.run_start[slot] = rs; ws.run_pref[slot] = inc - rl; }
 
-    /* cell-local frame for the fp32 prefilter: origin = minimum corner of the home cell */
+    /* block-local frame for the fp32 prefilter: origin = centre of the home block, so
+     * |home| <= (BX/2, 1/2, 1/2) e and |candidate| <= (BX/2+1, 3/2, 3/2) e */
     const float edge = g.edge;
-    const float orx = (float)g.ox + (float)cx * edge, ory = (float)g.oy + (float)cy * edge,
-                orz = (float)g.oz + (float)cz * edge;
+    const float orx = (float)g.ox + ((float)x0 + 0.5f * (float)BX) * edge,
+                ory = (float)g.oy + ((float)cy + 0.5f) * edge,
+                orz = (float)g.oz + ((float)cz + 0.5f) * edge;
     const float half_t = 0.5f * g.tf;
 
     Counters ct = {0u, 0u, 0u, 0u};
@@ -264,9 +273,9 @@ wn_k_edges(const WnEdgeParams p)
                 cx_ = b4.x - orx; cy_ = b4.y - ory; cz_ = b4.z - orz;
                 cn = 0.5f * (cx_ * cx_ + cy_ * cy_ + cz_ * cz_);
                 code_c = (uint32_t)c;
-                /* own cell: only home rows stored before the candidate (each pair once) */
+                /* own block: only home rows stored before the candidate (each pair once) */
                 const int ahead = c - hb;
-                allow = (c >= h1) ? 0xffffffffu : (ahead >= 32 ? 0xffffffffu : (ahead <= 0 ? 0u : ((1u << ahead) - 1u)));
+                allow = (c >= h1 || ahead >= 32) ? 0xffffffffu : (ahead <= 0 ? 0u : ((1u << ahead) - 1u));
                 if (p.first_limit < p.n_sites && __float_as_int(b4.w) >= p.first_limit) allow &= low_rows;
                 if (!SIMPLE) cm = __ldg(p.smeta + fbase + c);
             }
@@ -295,29 +304,33 @@ wn_k_edges(const WnEdgeParams p)
                 }
             }
             hits &= allow;
-            /* warp scan of the hit counts -> dense queue positions */
-            const int cnt = __popc(hits);
-            int pinc = cnt;
+            /* compact the hits into the queue, HPUSH mask bits at a time (bounds the queue) */
+#pragma unroll 1
+            for (int hb0 = 0; hb0 < hc4; hb0 += HPUSH) {
+                uint32_t part = (hits >> hb0) & ((1u << HPUSH) - 1u);
+                const int cnt = __popc(part);
+                int pinc = cnt;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL, pinc, o);
-                if (lane >= o) pinc += t;
-            }
-            const int tot = __shfl_sync(FULL, pinc, 31);
-            if (tot) {
-                int pos = qlen + pinc - cnt;
-                while (hits) {
-                    const int h = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    ws.queue[pos++] = ((uint32_t)h << 27) | code_c;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, pinc, o);
+                    if (lane >= o) pinc += t;
                 }
-                qlen += tot;
-                __syncwarp();
-                while (qlen >= 32) {
-                    wn_eval_batch<SIMPLE>(p, fbase, ws, hdh, qlen - 32, 32, ct, lane);
-                    qlen -= 32;
+                const int tot = __shfl_sync(FULL, pinc, 31);
+                if (tot) {
+                    int pos = qlen + pinc - cnt;
+                    while (part) {
+                        const int h = __ffs(part) - 1 + hb0;
+                        part &= part - 1;
+                        ws.queue[pos++] = ((uint32_t)h << 27) | code_c;
+                    }
+                    qlen += tot;
+                    __syncwarp();
+                    while (qlen >= 32) {
+                        wn_eval_batch<SIMPLE>(p, fbase, ws, hdh, qlen - 32, 32, ct, lane);
+                        qlen -= 32;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
         if (qlen > 0) {

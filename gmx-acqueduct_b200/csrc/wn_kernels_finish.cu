@@ -19,7 +19,7 @@ constexpr int COPY_THREADS = 256;
 
 /* switch_function_radius (src/waternetwork.cpp:12-28); r, r_on, r_off are the
  * squared values the caller passes (:57).  pow(x,2) is restated as x*x. */
-__device__ __forceinline__ double wn_switch_radius(double r, double r_on, double r_off)
+__device__ __forceinline__ double wn_switch_radius(double r, double r_on, double r_off, double inv_denom)
 {
     double sw = 0.0;
     if (r_off > r && r > r_on) {
@@ -27,8 +27,7 @@ __device__ __forceinline__ double wn_switch_radius(double r, double r_on, double
         const double a = r2 - off2;
         sw = a * a;
         sw *= off2 + 2 * r2 - 3 * on2;
-        const double d = off2 - on2;
-        sw /= d * d * d;
+        sw *= inv_denom;          /* 1 / (r_off^2 - r_on^2)^3, precomputed in fp64 (<= 1 ulp) */
     } else if (r < r_on) {
         sw = 1.0;
     }
@@ -54,15 +53,19 @@ __device__ __forceinline__ double wn_switch_angle(double a, double a_on, double 
 }
 
 /* computeEnergy (src/waternetwork.cpp:49-66): C=3855, D=738 (static float),
- * pow(r,6), pow(r,4), pow(cosine,4) restated as products (<= a few ulp from
- * glibc pow; the contract is 1e-6 relative). */
+ * pow(r,6), pow(r,4), pow(cosine,4) restated as products, the two quotients merged
+ * into one and the constant switch denominator inverted once (all <= a few ulp from
+ * the glibc-pow evaluation; the contract is 1e-6 relative, the result is stored as
+ * float). */
 __device__ __forceinline__ double wn_compute_energy(double r, double cosine, const WnEnergyParams& ep)
 {
-    const double radius_switch = wn_switch_radius(r * r, ep.on2, ep.off2);
+    const double r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
+    const double radius_switch = wn_switch_radius(r2, ep.on2, ep.off2, ep.inv_denom_r);
     const double c2 = cosine * cosine;
     const double angle_switch = wn_switch_angle(c2, ep.a_on, ep.a_off);
-    const double r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
-    double energy = (3855.0 / r6) - (738.0 / r4);
+    /* C/r^6 - D/r^4 as one division (C - D r^2)/r^6: same value to ~2 ulp except within
+     * ~1e-9 of the zero crossing r = sqrt(C/D), which no float32 length reaches */
+    double energy = (3855.0 - 738.0 * r2) / r6;
     energy *= c2 * c2;
     energy *= radius_switch;
     energy *= angle_switch;
