@@ -135,3 +135,14 @@ def test_bench_reference_arm_contract(oracle):
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_edge_file_writer_is_byte_identical_to_reference_iostream_formatting():
+    """f1: edges-frames.xvg.dat / nodes-list.xvg.dat text, checked in C++ against std::ostream
+    driven with the reference's manipulators (src/waternetwork.cpp:485-499, :638-652, :83-93)."""
+    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "test_writer")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "test_writer OK" in r.stdout, r.stdout + r.stderr
