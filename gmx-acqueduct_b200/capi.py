@@ -24,7 +24,8 @@ assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
 
 # every symbol include/wn_b200.h declares
 SYMBOLS = [
-    "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_set_sites",
+    "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_find_pairs_pbc",
+    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_set_sites",
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
@@ -82,6 +83,9 @@ def load():
     L.wn_last_error.restype = C.c_char_p
     L.wn_version.restype = C.c_char_p
     L.wn_find_pairs.argtypes = [vp, vp, i32, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(TieReport)]
+    L.wn_find_pairs_pbc.argtypes = [vp, vp, i32, i32, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(TieReport)]
+    L.wn_hbond_batch_pbc.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
+    L.wn_hbond_batch_pbc_dev.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_set_sites.argtypes = [vp, i32, vp, vp, i32, vp, i32]
     L.wn_set_water_sites.argtypes = [vp, i32, i32]
     L.wn_set_energy_params.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -137,12 +141,17 @@ class Context:
             raise WnError(rc, self.L.wn_last_error(self.h).decode())
 
     # ---- FindPairs::find
-    def find_pairs(self, xyz, first_limit=None):
+    def find_pairs(self, xyz, first_limit=None, box=None):
         xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
         n = xyz.shape[0]
         fl = n if first_limit is None else int(first_limit)
         p, m, ties = C.c_void_p(), C.c_uint64(), TieReport()
-        self._ck(self.L.wn_find_pairs(self.h, xyz.ctypes.data, n, fl, C.byref(p), C.byref(m), C.byref(ties)))
+        if box is None:
+            self._ck(self.L.wn_find_pairs(self.h, xyz.ctypes.data, n, fl, C.byref(p), C.byref(m), C.byref(ties)))
+        else:
+            box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
+            self._ck(self.L.wn_find_pairs_pbc(self.h, xyz.ctypes.data, n, fl, box.ctypes.data, C.byref(p),
+                                              C.byref(m), C.byref(ties)))
         cnt = int(m.value)
         if cnt == 0:
             return np.zeros((0, 2), np.int32), ties.as_dict()
@@ -194,8 +203,9 @@ class Context:
         out["stats"] = st.copy() if copy else st
         return out
 
-    def hbond_batch(self, frames, copy=True):
-        """frames: host float32 [F][natoms][3] (numpy) or (ptr, n_frames, natoms)."""
+    def hbond_batch(self, frames, copy=True, boxes=None):
+        """frames: host float32 [F][natoms][3] (numpy) or (ptr, n_frames, natoms);
+        boxes: None (open boundary, the reference) or float32 [F][3] (rectangular PBC)."""
         if isinstance(frames, tuple):
             ptr, nf, natoms = frames
         else:
@@ -205,12 +215,21 @@ class Context:
             nf, natoms = frames.shape[0], frames.shape[1]
             ptr = frames.ctypes.data
         res = BatchResult()
-        self._ck(self.L.wn_hbond_batch(self.h, ptr, nf, natoms, C.byref(res)))
+        if boxes is None:
+            self._ck(self.L.wn_hbond_batch(self.h, ptr, nf, natoms, C.byref(res)))
+        else:
+            boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(nf, 3)
+            self._ck(self.L.wn_hbond_batch_pbc(self.h, ptr, boxes.ctypes.data, nf, natoms, C.byref(res)))
         return self._wrap(res, copy)
 
-    def hbond_batch_dev(self, frames_dev, n_frames, natoms):
+    def hbond_batch_dev(self, frames_dev, n_frames, natoms, boxes=None):
         res = BatchResult()
-        self._ck(self.L.wn_hbond_batch_dev(self.h, frames_dev, n_frames, natoms, C.byref(res)))
+        if boxes is None:
+            self._ck(self.L.wn_hbond_batch_dev(self.h, frames_dev, n_frames, natoms, C.byref(res)))
+        else:
+            boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(n_frames, 3)
+            self._ck(self.L.wn_hbond_batch_pbc_dev(self.h, frames_dev, boxes.ctypes.data, n_frames, natoms,
+                                                   C.byref(res)))
         return self._wrap(res)
 
     def fetch_dev_result(self, out):

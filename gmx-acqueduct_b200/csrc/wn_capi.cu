@@ -14,6 +14,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -88,6 +89,8 @@ struct wn_ctx {
     int32_t* h_pairs = nullptr;
     size_t h_pairs_cap = 0;
     unsigned long long* d_pair_ties = nullptr;
+
+    std::vector<WnGrid> h_grid;     /* periodic grids of the current pass (host-built) */
 
     /* timing */
     cudaEvent_t ev[8] = {};
@@ -238,7 +241,7 @@ static const size_t WN_ROWBUF_BUDGET = (size_t)24 << 30;
 
 /* Run the pipeline on `nf` device-resident frames; edges land in ctx->d_edges at
  * offset *edge_base (updated), frame rows at [f0, f0+nf). */
-int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
+int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int natoms, size_t f0,
              unsigned long long* edge_base)
 {
     const int N = ctx->n_sites;
@@ -247,20 +250,38 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
     /* a pass whose row buffers would not fit is split (dense inputs after row_cap grew) */
     if (nf > 1 && (size_t)nf * N * ctx->row_cap * WN_ROW_WORDS * sizeof(uint32_t) > WN_ROWBUF_BUDGET) {
         const int half = nf / 2;
-        if ((rc = run_pass(ctx, d_frames, half, natoms, f0, edge_base))) return rc;
-        return run_pass(ctx, d_frames + (size_t)half * natoms * 3, nf - half, natoms, f0 + half, edge_base);
+        if ((rc = run_pass(ctx, d_frames, boxes, half, natoms, f0, edge_base))) return rc;
+        return run_pass(ctx, d_frames + (size_t)half * natoms * 3, boxes ? boxes + 3 * (size_t)half : nullptr,
+                        nf - half, natoms, f0 + half, edge_base);
     }
     if ((rc = ensure_pass_buffers(ctx, nf))) return rc;
     const int cell_cap = ctx->cell_cap;
 
     WN_CK(cudaEventRecord(ctx->ev[0], st));
-    wn_launch_bbox(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, st);
+    bool small_box = false;      /* periodic box with < 3 cells in some dimension: all-pairs kernel */
+    int bx = 2;                  /* home block width; 1 when a periodic box has < 4 cells along x  */
+    if (boxes) {
+        ctx->h_grid.resize((size_t)nf);
+        for (int f = 0; f < nf; ++f) {
+            const float* b = boxes + 3 * (size_t)f;
+            if (!(b[0] > 0.f && b[1] > 0.f && b[2] > 0.f) || !std::isfinite(b[0]) || !std::isfinite(b[1]) || !std::isfinite(b[2]))
+                return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_pbc: box lengths must be positive and finite");
+            WnGrid& g = ctx->h_grid[f];
+            wn_host_pbc_grid(b, cell_cap, &g);
+            if (g.nx < 3 || g.ny < 3 || g.nz < 3) small_box = true;
+            if (g.nx < 4) bx = 1;
+        }
+        WN_CK(cudaMemcpyAsync(ctx->d_grid, ctx->h_grid.data(), (size_t)nf * sizeof(WnGrid), cudaMemcpyHostToDevice, st));
+        WN_CK(cudaStreamSynchronize(st));       /* h_grid is pageable and reused by the next pass */
+    } else {
+        wn_launch_bbox(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, st);
+    }
     WN_CK(cudaMemsetAsync(ctx->d_cell_cnt, 0, (size_t)nf * (cell_cap + 1) * sizeof(int), st));
     wn_launch_bin(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt,
                   ctx->d_site_cell, ctx->d_site_rank, st);
     wn_launch_cellscan(nf, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt, st);
     wn_launch_scatter(d_frames, nf, natoms, ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, N, ctx->hs,
-                      cell_cap, ctx->d_cell_cnt, ctx->d_site_cell, ctx->d_site_rank, ctx->d_spos,
+                      cell_cap, ctx->d_cell_cnt, ctx->d_site_cell, ctx->d_site_rank, ctx->d_grid, ctx->d_spos,
                       ctx->d_smeta, ctx->d_sdh, st);
     ctx->tm.launches += 4;
     WN_CK(cudaEventRecord(ctx->ev[1], st));
@@ -275,8 +296,9 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
         p.cell_start = ctx->d_cell_cnt; p.grid = ctx->d_grid;
         p.rowbuf = ctx->d_rowbuf; p.row_cnt = ctx->d_row_cnt; p.counters = ctx->d_counters;
         p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
-        p.row_cap = ctx->row_cap; p.simple = ctx->simple;
-        wn_launch_edges(p, nf, st);
+        p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? 1 : 0; p.bx = bx;
+        if (small_box) wn_launch_edges_small(p, nf, st);
+        else wn_launch_edges(p, nf, st);
         WN_CK(cudaGetLastError());
         if (attempt == 0) WN_CK(cudaEventRecord(ctx->ev[2], st));
         wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off, ctx->d_frame_total, ctx->d_frame_maxrow, st);
@@ -296,8 +318,9 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
         ctx->row_cap = nc;
         if (nf > 1 && (size_t)nf * N * nc * WN_ROW_WORDS * sizeof(uint32_t) > WN_ROWBUF_BUDGET) {
             const int half = nf / 2;
-            if ((rc = run_pass(ctx, d_frames, half, natoms, f0, edge_base))) return rc;
-            return run_pass(ctx, d_frames + (size_t)half * natoms * 3, nf - half, natoms, f0 + half, edge_base);
+            if ((rc = run_pass(ctx, d_frames, boxes, half, natoms, f0, edge_base))) return rc;
+            return run_pass(ctx, d_frames + (size_t)half * natoms * 3, boxes ? boxes + 3 * (size_t)half : nullptr,
+                            nf - half, natoms, f0 + half, edge_base);
         }
     }
 
@@ -325,7 +348,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, int nf, int natoms, size_t f0,
     return WN_OK;
 }
 
-int batch_common(wn_ctx* ctx, const float* frames, bool host_in, int n_frames, int natoms,
+int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host_in, int n_frames, int natoms,
                  wn_batch_result* out)
 {
     if (!ctx) return WN_ERR_BAD_ARG;
@@ -386,7 +409,8 @@ int batch_common(wn_ctx* ctx, const float* frames, bool host_in, int n_frames, i
             if (k + 1 < n_pass && (rc = stage_in(k + 1))) return rc;
             WN_CK(cudaStreamWaitEvent(ctx->st, ctx->ev_stage[k & 1], 0));
             const unsigned long long before = edge_base;
-            if ((rc = run_pass(ctx, ctx->d_stage[k & 1], nf, natoms, (size_t)f0, &edge_base))) return rc;
+            if ((rc = run_pass(ctx, ctx->d_stage[k & 1], boxes ? boxes + 3 * (size_t)f0 : nullptr, nf, natoms,
+                               (size_t)f0, &edge_base))) return rc;
             if ((size_t)edge_base > ctx->h_edges_cap) {
                 /* project the whole call from the density seen so far */
                 const double per_frame = (double)edge_base / (double)(f0 + nf);
@@ -409,7 +433,8 @@ int batch_common(wn_ctx* ctx, const float* frames, bool host_in, int n_frames, i
     } else {
         for (int f0 = 0; f0 < n_frames; f0 += fpp) {
             const int nf = std::min(fpp, n_frames - f0);
-            if ((rc = run_pass(ctx, frames + (size_t)f0 * frame_floats, nf, natoms, (size_t)f0, &edge_base))) return rc;
+            if ((rc = run_pass(ctx, frames + (size_t)f0 * frame_floats, boxes ? boxes + 3 * (size_t)f0 : nullptr, nf,
+                               natoms, (size_t)f0, &edge_base))) return rc;
         }
     }
     /* small per-frame tables always come back to the host: totals and ties */
@@ -612,13 +637,27 @@ int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass)
 int wn_hbond_batch(wn_ctx* ctx, const float* frames_host, int32_t n_frames, int32_t natoms,
                    wn_batch_result* out)
 {
-    return batch_common(ctx, frames_host, true, n_frames, natoms, out);
+    return batch_common(ctx, frames_host, nullptr, true, n_frames, natoms, out);
+}
+
+int wn_hbond_batch_pbc(wn_ctx* ctx, const float* frames_host, const float* boxes_host, int32_t n_frames,
+                       int32_t natoms, wn_batch_result* out)
+{
+    if (ctx && !boxes_host && n_frames > 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_pbc: boxes is NULL");
+    return batch_common(ctx, frames_host, boxes_host, true, n_frames, natoms, out);
+}
+
+int wn_hbond_batch_pbc_dev(wn_ctx* ctx, const float* frames_dev, const float* boxes_host, int32_t n_frames,
+                           int32_t natoms, wn_batch_result* out)
+{
+    if (ctx && !boxes_host && n_frames > 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_pbc_dev: boxes is NULL");
+    return batch_common(ctx, frames_dev, boxes_host, false, n_frames, natoms, out);
 }
 
 int wn_hbond_batch_dev(wn_ctx* ctx, const float* frames_dev, int32_t n_frames, int32_t natoms,
                        wn_batch_result* out)
 {
-    return batch_common(ctx, frames_dev, false, n_frames, natoms, out);
+    return batch_common(ctx, frames_dev, nullptr, false, n_frames, natoms, out);
 }
 
 int wn_get_timings(wn_ctx* ctx, wn_timings* out)
@@ -646,10 +685,37 @@ int wn_timer_stop(wn_ctx* ctx, float* elapsed_ms)
     return WN_OK;
 }
 
+static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit, const float* box3,
+                           const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
+
 int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
                   const int32_t** pairs, uint64_t* m, wn_tie_report* ties)
 {
+    return find_pairs_impl(ctx, xyz, n, first_limit, nullptr, pairs, m, ties);
+}
+
+int wn_find_pairs_pbc(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit, const float box[3],
+                      const int32_t** pairs, uint64_t* m, wn_tie_report* ties)
+{
     if (!ctx) return WN_ERR_BAD_ARG;
+    if (!box || !(box[0] > 0.f && box[1] > 0.f && box[2] > 0.f))
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_find_pairs_pbc: box lengths must be positive");
+    return find_pairs_impl(ctx, xyz, n, first_limit, box, pairs, m, ties);
+}
+
+static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit, const float* box3,
+                           const int32_t** pairs, uint64_t* m, wn_tie_report* ties)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    WnPairBox pb;
+    memset(&pb, 0, sizeof pb);
+    if (box3) {
+        pb.pbc = 1;
+        for (int c = 0; c < 3; ++c) {
+            pb.L[c] = (double)box3[c]; pb.invL[c] = 1.0 / pb.L[c];
+            pb.Lf[c] = box3[c]; pb.invLf[c] = 1.0f / box3[c];
+        }
+    }
     if (n < 0 || (n > 0 && !xyz) || !pairs || !m) return fail(ctx, WN_ERR_BAD_ARG, "wn_find_pairs: bad argument");
     WN_CK(cudaSetDevice(ctx->device));
     ctx->err.clear();
@@ -672,7 +738,7 @@ int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit
     }
     WN_CK(cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     WN_CK(cudaMemsetAsync(ctx->d_pair_ties, 0, sizeof(unsigned long long), st));
-    wn_launch_pairs_count(ctx->d_xyz, n, first_limit, ctx->d_prow_cnt, ctx->d_pair_ties, st);
+    wn_launch_pairs_count(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_cnt, ctx->d_pair_ties, st);
     wn_launch_pairs_scan(ctx->d_prow_cnt, n, ctx->d_prow_off, st);
     WN_CK(cudaGetLastError());
     WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_prow_off + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -683,7 +749,7 @@ int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit
     if ((rc = dev_ensure(ctx, &ctx->d_pairs, &ctx->d_pairs_cap, (size_t)total * 2 + 2))) return rc;
     if ((rc = host_ensure(ctx, &ctx->h_pairs, &ctx->h_pairs_cap, (size_t)total * 2 + 2))) return rc;
     if (total) {
-        wn_launch_pairs_fill(ctx->d_xyz, n, first_limit, ctx->d_prow_off, ctx->d_pairs, st);
+        wn_launch_pairs_fill(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_off, ctx->d_pairs, st);
         WN_CK(cudaGetLastError());
         WN_CK(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs, (size_t)total * 2 * sizeof(int32_t),
                               cudaMemcpyDeviceToHost, st));

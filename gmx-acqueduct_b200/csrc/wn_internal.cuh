@@ -11,15 +11,27 @@
 
 #include "wn_b200.h"
 
-/* ---- per-frame cell grid (open boundary: bounding box of the finite sites) ---- */
+/* ---- per-frame cell grid ----
+ * open boundary: bounding box of the finite sites (wn_k_bbox), cubic cells.
+ * periodic     : the box itself, n = floor(L/edge_min) cells per dimension (host-built). */
 struct WnGrid {
-    double ox, oy, oz;   /* origin (minimum corner)                   */
-    double inv;          /* 1 / cell edge                             */
+    double ox, oy, oz;   /* origin (minimum corner); 0 in periodic mode            */
+    double inv[3];       /* 1 / cell edge, per dimension                            */
+    double L[3];         /* periodic box lengths (fp64 of the float box), else 0    */
+    double invL[3];      /* 1.0 / L                                                  */
     int nx, ny, nz;
-    int ncells;          /* nx*ny*nz <= cell capacity                 */
-    float edge;          /* cell edge (fp32 copy, for cell-local frames) */
+    int ncells;          /* nx*ny*nz <= cell capacity                               */
+    float edge[3];       /* cell edge (fp32 copy, for block-local frames)           */
     float tf;            /* fp32 prefilter bound on d^2 (superset of the exact test) */
+    int pbc;             /* 1: rectangular periodic box                             */
 };
+
+/* Minimum cell edge, and the fp32 prefilter bound for a given (largest) cell edge: exact
+ * acceptance needs d2 <= 0.4225*(1+2.5e-7); the dot-product form on block-local
+ * coordinates (|a|^2 <= 1.5 e^2, |c|^2 <= 8.5 e^2, six fp32 roundings on terms <= 8.5 e^2,
+ * coordinates rounded at <= 6e-8 * 2e) errs by <= ~3.1e-6 e^2 + 5e-7 e; > 2x head-room. */
+#define WN_CELL_EDGE      (0.65 * (1.0 + 1.0e-5))
+#define WN_PREFILTER_BOUND(e) (0.4225 * (1.0 + 1.0e-5) + 8.0e-6 * (e) * (e) + 2.0e-6 * (e))
 
 /* ---- per-frame counters written by the fused kernel ---- */
 struct WnFrameCounters {
@@ -40,7 +52,6 @@ struct WnFrameCounters {
  * length in Angstrom is > 6.5.  Any accepted pair has squared distance (nm^2)
  * <= 0.4225*(1+2.5e-7); the fp32 prefilter and the cell edge carry a margin. */
 #define WN_LEN_CUT_F      6.5f
-#define WN_CELL_EDGE      (0.65 * (1.0 + 1.0e-5))
 
 /* Energy parameters in the form the kernels consume (computeEnergy, :49-66). */
 struct WnEnergyParams {
@@ -69,6 +80,8 @@ struct WnEdgeParams {
     int first_limit;
     int row_cap;
     int simple;                 /* 1: every site WATER with the list [site atom, H] */
+    int pbc;                    /* 1: grids are periodic boxes                       */
+    int bx;                     /* home block width in cells (1 or 2)               */
 };
 
 /* ---- kernel launchers (wn_kernels_*.cu).  All asynchronous on `st`. ---- */
@@ -77,14 +90,18 @@ void wn_launch_bbox(const float* frames, int n_frames, int natoms, const int* si
 void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* site_atom,
                    int n_sites, int cell_cap, const WnGrid* grid, int* cell_cnt,
                    int* site_cell, int* site_rank, cudaStream_t st);
+/* periodic grid of one frame, built on the host (uploaded with the pass) */
+void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g);
 void wn_launch_cellscan(int n_frames, int n_sites, int cell_cap, const WnGrid* grid,
                         int* cell_cnt, cudaStream_t st);
 void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,
                        const int* hv_atom, const uint32_t* meta, int n_sites, int hs,
                        int cell_cap, const int* cell_start, const int* site_cell,
-                       const int* site_rank, float4* spos, uint32_t* smeta, double* sdh,
+                       const int* site_rank, const WnGrid* grid, float4* spos, uint32_t* smeta, double* sdh,
                        cudaStream_t st);
 void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st);
+/* all-pairs variant for periodic boxes with fewer than 3 cells in some dimension */
+void wn_launch_edges_small(const WnEdgeParams& p, int n_frames, cudaStream_t st);
 void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
                        uint32_t* row_off, unsigned long long* frame_total, uint32_t* frame_maxrow,
                        cudaStream_t st);
@@ -103,11 +120,12 @@ void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long
 size_t wn_edges_smem_bytes(int hs);
 
 /* brute pair path (wn_kernels_pairs.cu) */
-void wn_launch_pairs_count(const double* xyz, int n, int first_limit, uint32_t* row_cnt,
+struct WnPairBox { int pbc; double L[3], invL[3]; float Lf[3], invLf[3]; };
+void wn_launch_pairs_count(const double* xyz, int n, int first_limit, WnPairBox box, uint32_t* row_cnt,
                            unsigned long long* ties, cudaStream_t st);
 void wn_launch_pairs_scan(const uint32_t* row_cnt, int n, unsigned long long* row_off,
                           cudaStream_t st);
-void wn_launch_pairs_fill(const double* xyz, int n, int first_limit,
+void wn_launch_pairs_fill(const double* xyz, int n, int first_limit, WnPairBox box,
                           const unsigned long long* row_off, int32_t* pairs, cudaStream_t st);
 
 /* synthetic frames (wn_synth.cu, compiled with -fmad=false) */

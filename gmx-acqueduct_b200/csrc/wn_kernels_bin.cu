@@ -63,9 +63,12 @@ wn_k_bbox(const float* __restrict__ frames, int natoms, const int* __restrict__ 
             mn[c] = (double)a; mx[c] = (double)b;
         }
         WnGrid g;
+        g.pbc = 0;
+        for (int c = 0; c < 3; ++c) { g.L[c] = 0.0; g.invL[c] = 0.0; }
         if (!(mn[0] <= mx[0])) {          /* no finite site */
-            g.ox = g.oy = g.oz = 0.0; g.inv = 1.0; g.nx = g.ny = g.nz = 1; g.ncells = 1;
-            g.edge = 1.0f; g.tf = 1.0f;
+            g.ox = g.oy = g.oz = 0.0; g.nx = g.ny = g.nz = 1; g.ncells = 1;
+            for (int c = 0; c < 3; ++c) { g.inv[c] = 1.0; g.edge[c] = 1.0f; }
+            g.tf = 1.0f;
         } else {
             double edge = WN_CELL_EDGE;
             const double ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
@@ -78,19 +81,21 @@ wn_k_bbox(const float* __restrict__ frames, int natoms, const int* __restrict__ 
                 edge *= 1.1;              /* coarser cells stay correct (edge >= cutoff) */
             }
             g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
-            g.inv = 1.0 / edge;
+            for (int c = 0; c < 3; ++c) { g.inv[c] = 1.0 / edge; g.edge[c] = (float)edge; }
             g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
             g.ncells = g.nx * g.ny * g.nz;
-            /* fp32 prefilter bound: exact acceptance needs d2 <= 0.4225*(1+2.5e-7); the
-             * dot-product form on block-local coordinates (|a|^2 <= 1.5 e^2, |c|^2 <= 8.5 e^2,
-             * six fp32 roundings on terms <= 8.5 e^2, coordinates rounded at <= 6e-8 * 2e)
-             * errs by <= ~3.1e-6 e^2 + 5e-7 e; bound with > 2x head-room, rounded up */
-            const double tfd = 0.4225 * (1.0 + 1.0e-5) + 8.0e-6 * edge * edge + 2.0e-6 * edge;
-            g.edge = (float)edge;
-            g.tf = __double2float_ru(tfd);
+            g.tf = __double2float_ru(WN_PREFILTER_BOUND(edge));
         }
         grid[f] = g;
     }
+}
+
+/* periodic mode, step 1 of the definition (oracle/wn_oracle.h): put the coordinate in the
+ * box in fp64 and round back to float; identity for 0 <= x < L */
+__device__ __forceinline__ float wn_wrap(float x, double L, double invL)
+{
+    const double xd = (double)x;
+    return __double2float_rn(__dsub_rn(xd, __dmul_rn(floor(__dmul_rn(xd, invL)), L)));
 }
 
 __device__ __forceinline__ int wn_cell_coord(double x, double o, double inv, int n)
@@ -113,9 +118,11 @@ wn_k_bin(const float* __restrict__ frames, int natoms, const int* __restrict__ s
     if (i >= n_sites) return;
     const WnGrid g = grid[f];
     const float* p = frames + ((size_t)f * natoms + (size_t)__ldg(site_atom + i)) * 3;
-    const int cx = wn_cell_coord((double)p[0], g.ox, g.inv, g.nx);
-    const int cy = wn_cell_coord((double)p[1], g.oy, g.inv, g.ny);
-    const int cz = wn_cell_coord((double)p[2], g.oz, g.inv, g.nz);
+    float x = p[0], y = p[1], z = p[2];
+    if (g.pbc) { x = wn_wrap(x, g.L[0], g.invL[0]); y = wn_wrap(y, g.L[1], g.invL[1]); z = wn_wrap(z, g.L[2], g.invL[2]); }
+    const int cx = wn_cell_coord((double)x, g.ox, g.inv[0], g.nx);
+    const int cy = wn_cell_coord((double)y, g.oy, g.inv[1], g.ny);
+    const int cz = wn_cell_coord((double)z, g.oz, g.inv[2], g.nz);
     const int cid = (cz * g.ny + cy) * g.nx + cx;
     const int rank = atomicAdd(cell_cnt + (size_t)f * (cell_cap + 1) + cid, 1);
     site_cell[(size_t)f * n_sites + i] = cid;
@@ -166,6 +173,7 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
              const int* __restrict__ hv_atom, const uint32_t* __restrict__ meta, int n_sites,
              int hs, int cell_cap, const int* __restrict__ cell_start,
              const int* __restrict__ site_cell, const int* __restrict__ site_rank,
+             const WnGrid* __restrict__ grid,
              float4* __restrict__ spos, uint32_t* __restrict__ smeta, double* __restrict__ sdh)
 {
     const int f = blockIdx.y;
@@ -173,7 +181,13 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
     if (i >= n_sites) return;
     const float* fr = frames + (size_t)f * natoms * 3;
     const float* p = fr + 3 * (size_t)__ldg(site_atom + i);
-    const float x = p[0], y = p[1], z = p[2];
+    float x = p[0], y = p[1], z = p[2];
+    const bool pbc = grid[f].pbc != 0;
+    double L[3] = {0, 0, 0}, invL[3] = {0, 0, 0};
+    if (pbc) {
+        for (int c = 0; c < 3; ++c) { L[c] = grid[f].L[c]; invL[c] = grid[f].invL[c]; }
+        x = wn_wrap(x, L[0], invL[0]); y = wn_wrap(y, L[1], invL[1]); z = wn_wrap(z, L[2], invL[2]);
+    }
     const int cid = site_cell[(size_t)f * n_sites + i];
     const int dst = cell_start[(size_t)f * (cell_cap + 1) + cid] + site_rank[(size_t)f * n_sites + i];
     const size_t o = (size_t)f * n_sites + dst;
@@ -186,9 +200,19 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
         double dx = NAN, dy = NAN, dz = NAN;
         if (at >= 0) {
             const float* h = fr + 3 * (size_t)at;
-            dx = __dsub_rn((double)h[0], sx);
-            dy = __dsub_rn((double)h[1], sy);
-            dz = __dsub_rn((double)h[2], sz);
+            if (pbc) {
+                /* wrapped hydrogen, then the minimum image of (hydrogen - site) */
+                dx = __dsub_rn((double)wn_wrap(h[0], L[0], invL[0]), sx);
+                dy = __dsub_rn((double)wn_wrap(h[1], L[1], invL[1]), sy);
+                dz = __dsub_rn((double)wn_wrap(h[2], L[2], invL[2]), sz);
+                dx = __dsub_rn(dx, __dmul_rn(rint(__dmul_rn(dx, invL[0])), L[0]));
+                dy = __dsub_rn(dy, __dmul_rn(rint(__dmul_rn(dy, invL[1])), L[1]));
+                dz = __dsub_rn(dz, __dmul_rn(rint(__dmul_rn(dz, invL[2])), L[2]));
+            } else {
+                dx = __dsub_rn((double)h[0], sx);
+                dy = __dsub_rn((double)h[1], sy);
+                dz = __dsub_rn((double)h[2], sz);
+            }
             const double l = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)),
                                                   __dmul_rn(dz, dz)));
             dx = __ddiv_rn(dx, l); dy = __ddiv_rn(dy, l); dz = __ddiv_rn(dz, l);
@@ -225,10 +249,47 @@ void wn_launch_cellscan(int n_frames, int n_sites, int cell_cap, const WnGrid* g
 void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,
                        const int* hv_atom, const uint32_t* meta, int n_sites, int hs,
                        int cell_cap, const int* cell_start, const int* site_cell,
-                       const int* site_rank, float4* spos, uint32_t* smeta, double* sdh,
+                       const int* site_rank, const WnGrid* grid, float4* spos, uint32_t* smeta, double* sdh,
                        cudaStream_t st)
 {
     dim3 g((n_sites + 255) / 256, n_frames);
     wn_k_scatter<<<g, 256, 0, st>>>(frames, natoms, site_atom, hv_atom, meta, n_sites, hs,
-                                    cell_cap, cell_start, site_cell, site_rank, spos, smeta, sdh);
+                                    cell_cap, cell_start, site_cell, site_rank, grid, spos, smeta, sdh);
+}
+
+/* Periodic grid: n = floor(L / edge_min) cells per dimension (>= 1), coarsened until the
+ * table fits; the cell edge L/n is >= edge_min in every dimension. */
+void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g)
+{
+    double L[3], emin = WN_CELL_EDGE;
+    int n[3];
+    for (int c = 0; c < 3; ++c) L[c] = (double)box[c];
+    for (;;) {
+        double tot = 1.0;
+        for (int c = 0; c < 3; ++c) {
+            double nd = floor(L[c] / emin);
+            if (!(nd >= 1.0)) nd = 1.0;
+            if (nd > 1.0e6) nd = 1.0e6;
+            n[c] = (int)nd;
+            tot *= nd;
+        }
+        if (tot <= (double)cell_cap) break;
+        emin *= 1.1;
+    }
+    double emax = 0.0;
+    g->ox = g->oy = g->oz = 0.0;
+    for (int c = 0; c < 3; ++c) {
+        const double e = L[c] / n[c];
+        g->L[c] = L[c]; g->invL[c] = 1.0 / L[c];
+        g->inv[c] = (double)n[c] / L[c];
+        g->edge[c] = (float)e;
+        if (e > emax) emax = e;
+    }
+    g->nx = n[0]; g->ny = n[1]; g->nz = n[2];
+    g->ncells = n[0] * n[1] * n[2];
+    const double tfd = WN_PREFILTER_BOUND(emax);
+    float tf = (float)tfd;
+    if ((double)tf < tfd) tf = nextafterf(tf, 3.0e38f);
+    g->tf = tf;
+    g->pbc = 1;
 }

@@ -10,7 +10,8 @@
  * (src/brute-find-pairs.cpp:25), so searching the neighbouring cells of a grid
  * with edge >= 0.65 nm finds exactly the pairs that matter.
  *
- * Work decomposition: one warp per (frame, home block of BX=2 x-adjacent cells),
+ * Work decomposition: one warp per (frame, home block of BX x-adjacent cells, BX = 2
+ * unless a periodic box has fewer than 4 cells along x),
  * HALF SHELL: the warp pairs its home sites with the sites of the "forward"
  * neighbour cells of the block and with the later sites of the block itself, so
  * every unordered pair is examined exactly once (5 contiguous runs of the
@@ -45,11 +46,10 @@ namespace {
 #define WN_EDGES_MINBLOCKS 5   /* measured: 3 -> 4.33, 4 -> 3.71, 5 -> 3.28, 6 -> 3.57 ms / 250 frames */
 #endif
 constexpr int WARPS_PER_CTA = 8;
-constexpr int BX   = 2;                  /* home block: BX cells along x (fewer, fuller rounds) */
 constexpr int HC   = 32;                 /* home sites per chunk (one hit-mask bit each)       */
 constexpr int HPUSH = 16;                /* hit-mask bits pushed per scan                       */
 constexpr int QCAP = 32 + 32 * HPUSH;    /* queue: < 32 carried + one push of <= 32*HPUSH codes */
-constexpr int MAXRUN = 5;
+constexpr int MAXRUN = 10;               /* 5 rows, each possibly split by the periodic wrap in x */
 constexpr unsigned FULL = 0xffffffffu;
 
 /* fixed part of the per-warp shared memory (followed by HC*hs unit D-H vectors) */
@@ -60,6 +60,7 @@ struct WarpShared {
     uint32_t  queue[QCAP];
     int       run_start[MAXRUN + 1];
     int       run_pref[MAXRUN + 1];
+    float4    run_org[MAXRUN];   /* periodic: origin to subtract from the run's sites (image shift folded in) */
 };
 
 struct Counters { unsigned int evals, tie_len, tie_cos, tie_pos0; };
@@ -70,18 +71,113 @@ __device__ __forceinline__ float wn_dot_f32(const double* __restrict__ d, double
     return __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(d[0], ux), __dmul_rn(d[1], uy)), __dmul_rn(d[2], uz)));
 }
 
-/* Exact geometry of make_edges for `nb` queued codes (lane < nb active). */
-template <bool SIMPLE>
+/* minimum image of a displacement component (periodic definition, oracle/wn_oracle.h):
+ * d - rint(d * (1/L)) * L, every operation rounded, round-half-even in rint */
+__device__ __forceinline__ double wn_minimg(double d, double L, double invL)
+{
+    return __dsub_rn(d, __dmul_rn(rint(__dmul_rn(d, invL)), L));
+}
+
+struct PairOut {
+    bool counted, edge, t_len, t_cos, t_pos0;
+    float len_f, cosmax;
+};
+
+/* Exact geometry of make_edges (src/waternetwork.cpp:192-259) for one pair.  a4/b4: float
+ * positions + site index bits of the two sites in ANY order (see the role symmetry in the
+ * file header); dha/dhb: their unit D-H vectors (stride 4 doubles); ma/mb: meta words. */
+template <bool SIMPLE, bool PBC>
+__device__ __forceinline__ PairOut
+wn_pair_geometry(const float4 a4, const float4 b4, const double* __restrict__ dha,
+                 const double* __restrict__ dhb, uint32_t ma, uint32_t mb, const WnGrid& g)
+{
+    PairOut r;
+    r.counted = r.edge = r.t_len = r.t_cos = r.t_pos0 = false;
+    r.cosmax = 0.f;
+    /* Vector_3 OO = sitePoints.at(first) - sitePoints.at(second)      (:194)
+     * computed here as S_a - S_b; the other role is its exact negation */
+    double ox = __dsub_rn((double)a4.x, (double)b4.x);
+    double oy = __dsub_rn((double)a4.y, (double)b4.y);
+    double oz = __dsub_rn((double)a4.z, (double)b4.z);
+    if (PBC) {
+        ox = wn_minimg(ox, g.L[0], g.invL[0]);
+        oy = wn_minimg(oy, g.L[1], g.invL[1]);
+        oz = wn_minimg(oz, g.L[2], g.invL[2]);
+    }
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ox, ox), __dmul_rn(oy, oy)), __dmul_rn(oz, oz));
+    /* float distance = CGAL::sqrt(OO*OO)                               (:195) */
+    const float dist_f = __double2float_rn(__dsqrt_rn(d2));
+    const double dd = (double)dist_f;
+    /* distance *= 10.0                                                 (:197) */
+    r.len_f = __double2float_rn(__dmul_rn(dd, 10.0));
+    /* if (distance > 6.5) isedge = false                               (:204) */
+    r.counted = r.len_f <= WN_LEN_CUT_F;
+    if (!r.counted) return r;
+    r.t_len = (r.len_f == WN_LEN_CUT_F);
+    /* OO /= distance                                                   (:196) */
+    const double ux = __ddiv_rn(ox, dd), uy = __ddiv_rn(oy, dd), uz = __ddiv_rn(oz, dd);
+    if (SIMPLE) {
+        /* every site: list [site atom itself (NaN, never wins), H] -> one cosine each;
+         * arg-max from 0 with strict '>' (:240-249) is max(c_first, c_second) when > 0 */
+        const float ca = wn_dot_f32(dha, ux, uy, uz);
+        const float cb = -wn_dot_f32(dhb, ux, uy, uz);
+        if (ca > 0.f) r.cosmax = ca;
+        r.t_cos = (ca > 0.f) && (cb == ca);
+        if (cb > r.cosmax) r.cosmax = cb;
+        r.edge = r.cosmax > 0.f;
+    } else {
+        const bool a_first = __float_as_int(a4.w) < __float_as_int(b4.w);
+        const uint32_t m_first = a_first ? ma : mb;
+        bool win = false, win0 = false;
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            const bool use_a = (s == 0) == a_first;
+            const uint32_t m = use_a ? ma : mb;
+            const int nv = (int)((m >> WN_META_NV_SHIFT) & WN_META_NV_MASK);
+            /* list index 0 is the first site's position-0 hydrogen, or the second
+             * site's when the first site has no hydrogen list at all (:251) */
+            const bool zero_here = (m & WN_META_FIRST0) && (s == 0 || !(m_first & WN_META_HASH));
+            for (int v = 0; v < nv; ++v) {
+                const float cv = use_a ? wn_dot_f32(dha + 4 * v, ux, uy, uz)        /* :219-221 */
+                                       : -wn_dot_f32(dhb + 4 * v, ux, uy, uz);      /* :231-233 */
+                if (cv > r.cosmax) {                                                /* :242-247 */
+                    r.cosmax = cv; win = true; win0 = zero_here && (v == 0);
+                } else if (r.cosmax > 0.f && cv == r.cosmax) {
+                    r.t_cos = true;
+                }
+            }
+        }
+        r.t_pos0 = win && win0;
+        r.edge = win && !win0;                                                      /* if (pos > 0) */
+    }
+    return r;
+}
+
+/* the edge belongs to row i = min(site indices): one atomic for its slot, one 16-byte store */
+__device__ __forceinline__ void
+wn_emit_edge(const WnEdgeParams& p, size_t fbase, int ia, int ib, float len_f, float cosmax)
+{
+    const int i = min(ia, ib), j = max(ia, ib);
+    const uint32_t slot = atomicAdd(p.row_cnt + fbase + i, 1u);
+    if (slot < (uint32_t)p.row_cap) {
+        /* {j, length, cosine, -} (measured: three 4-byte stores into a structure-of-arrays
+         * row cost 10 % of this kernel) */
+        reinterpret_cast<uint4*>(p.rowbuf)[(fbase + i) * (size_t)p.row_cap + slot] =
+            make_uint4((uint32_t)j, __float_as_uint(len_f), __float_as_uint(cosmax), 0u);
+    }
+}
+
+/* Exact geometry for `nb` queued codes (lane < nb active). */
+template <bool SIMPLE, bool PBC>
 __device__ __forceinline__ void
 wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const double* __restrict__ hdh,
-              int qbase, int nb, Counters& ct, int lane)
+              const WnGrid& g, int qbase, int nb, Counters& ct, int lane)
 {
-    const bool act = lane < nb;
-    bool counted = false, edge = false;
-    bool t_len = false, t_cos = false, t_pos0 = false;
-    float len_f = 0.f, cosmax = 0.f;
+    PairOut r;
+    r.counted = r.edge = r.t_len = r.t_cos = r.t_pos0 = false;
+    r.len_f = r.cosmax = 0.f;
     int ih = 0, ic = 0;
-    if (act) {
+    if (lane < nb) {
         const uint32_t code = ws.queue[qbase + lane];
         const int h = (int)(code >> 27);
         const uint32_t c = code & 0x07ffffffu;
@@ -89,90 +185,22 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
         const float4 b4 = __ldg(p.spos + fbase + c);
         ih = __float_as_int(a4.w);
         ic = __float_as_int(b4.w);
-        /* Vector_3 OO = sitePoints.at(first) - sitePoints.at(second)      (:194)
-         * computed here as S_h - S_c; the other role is its exact negation */
-        const double ox = __dsub_rn((double)a4.x, (double)b4.x);
-        const double oy = __dsub_rn((double)a4.y, (double)b4.y);
-        const double oz = __dsub_rn((double)a4.z, (double)b4.z);
-        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ox, ox), __dmul_rn(oy, oy)), __dmul_rn(oz, oz));
-        /* float distance = CGAL::sqrt(OO*OO)                               (:195) */
-        const float dist_f = __double2float_rn(__dsqrt_rn(d2));
-        const double dd = (double)dist_f;
-        /* distance *= 10.0                                                 (:197) */
-        len_f = __double2float_rn(__dmul_rn(dd, 10.0));
-        /* if (distance > 6.5) isedge = false                               (:204) */
-        counted = len_f <= WN_LEN_CUT_F;
-        if (counted) {
-            t_len = (len_f == WN_LEN_CUT_F);
-            /* OO /= distance                                               (:196) */
-            const double ux = __ddiv_rn(ox, dd), uy = __ddiv_rn(oy, dd), uz = __ddiv_rn(oz, dd);
-            const double* dh = hdh + (size_t)h * p.hs * 4;
-            const double* dc = p.sdh + (fbase + c) * (size_t)p.hs * 4;
-            if (SIMPLE) {
-                /* every site: list [site atom itself (NaN, never wins), H] -> one cosine each;
-                 * arg-max from 0 with strict '>' (:240-249) is max(c_first, c_second) when > 0 */
-                const double2 c01 = __ldg(reinterpret_cast<const double2*>(dc));
-                const double c2 = __ldg(dc + 2);
-                const double dcv[3] = {c01.x, c01.y, c2};
-                const float ch = wn_dot_f32(dh, ux, uy, uz);
-                const float cc = -wn_dot_f32(dcv, ux, uy, uz);
-                if (ch > 0.f) cosmax = ch;
-                t_cos = (ch > 0.f) && (cc == ch);
-                if (cc > cosmax) cosmax = cc;
-                edge = cosmax > 0.f;
-            } else {
-                const uint32_t mh = ws.hmeta[h];
-                const uint32_t mc = __ldg(p.smeta + fbase + c);
-                const bool h_first = ih < ic;
-                const uint32_t m_first = h_first ? mh : mc;
-                bool win = false, win0 = false;
-#pragma unroll 1
-                for (int s = 0; s < 2; ++s) {
-                    const bool use_h = (s == 0) == h_first;
-                    const uint32_t m = use_h ? mh : mc;
-                    const int nv = (int)((m >> WN_META_NV_SHIFT) & WN_META_NV_MASK);
-                    /* list index 0 is the first site's position-0 hydrogen, or the second
-                     * site's when the first site has no hydrogen list at all (:251) */
-                    const bool zero_here = (m & WN_META_FIRST0) && (s == 0 || !(m_first & WN_META_HASH));
-                    for (int v = 0; v < nv; ++v) {
-                        float cv;
-                        if (use_h) {
-                            cv = wn_dot_f32(dh + 4 * v, ux, uy, uz);               /* :219-221 */
-                        } else {
-                            const double dcv[3] = {__ldg(dc + 4 * v), __ldg(dc + 4 * v + 1), __ldg(dc + 4 * v + 2)};
-                            cv = -wn_dot_f32(dcv, ux, uy, uz);                      /* :231-233 */
-                        }
-                        if (cv > cosmax) {                                          /* :242-247 */
-                            cosmax = cv; win = true; win0 = zero_here && (v == 0);
-                        } else if (cosmax > 0.f && cv == cosmax) {
-                            t_cos = true;
-                        }
-                    }
-                }
-                t_pos0 = win && win0;
-                edge = win && !win0;                                                /* if (pos > 0) */
-            }
-        }
+        const double* dh = hdh + (size_t)h * p.hs * 4;
+        const double* dc = p.sdh + (fbase + c) * (size_t)p.hs * 4;
+        uint32_t mh = 0, mc = 0;
+        if (!SIMPLE) { mh = ws.hmeta[h]; mc = __ldg(p.smeta + fbase + c); }
+        r = wn_pair_geometry<SIMPLE, PBC>(a4, b4, dh, dc, mh, mc, g);
     }
-    ct.evals += __popc(__ballot_sync(FULL, counted));
-    if (__any_sync(FULL, t_len || t_cos || t_pos0)) {          /* rare */
-        ct.tie_len += __popc(__ballot_sync(FULL, t_len));
-        ct.tie_cos += __popc(__ballot_sync(FULL, t_cos));
-        ct.tie_pos0 += __popc(__ballot_sync(FULL, t_pos0));
+    ct.evals += __popc(__ballot_sync(FULL, r.counted));
+    if (__any_sync(FULL, r.t_len || r.t_cos || r.t_pos0)) {          /* rare */
+        ct.tie_len += __popc(__ballot_sync(FULL, r.t_len));
+        ct.tie_cos += __popc(__ballot_sync(FULL, r.t_cos));
+        ct.tie_pos0 += __popc(__ballot_sync(FULL, r.t_pos0));
     }
-    if (edge) {
-        const int i = min(ih, ic), j = max(ih, ic);
-        const uint32_t slot = atomicAdd(p.row_cnt + fbase + i, 1u);
-        if (slot < (uint32_t)p.row_cap) {
-            /* one 16-byte store per edge: {j, length, cosine, -} (measured: three 4-byte
-             * stores into a structure-of-arrays row cost 10 % of this kernel) */
-            reinterpret_cast<uint4*>(p.rowbuf)[(fbase + i) * (size_t)p.row_cap + slot] =
-                make_uint4((uint32_t)j, __float_as_uint(len_f), __float_as_uint(cosmax), 0u);
-        }
-    }
+    if (r.edge) wn_emit_edge(p, fbase, ih, ic, r.len_f, r.cosmax);
 }
 
-template <bool SIMPLE>
+template <bool SIMPLE, bool PBC, int BX>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WN_EDGES_MINBLOCKS)
 wn_k_edges(const WnEdgeParams p)
 {
@@ -180,9 +208,10 @@ wn_k_edges(const WnEdgeParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     const int blk = blockIdx.x * WARPS_PER_CTA + warp;
-    const WnGrid g = p.grid[f];
-    const int nbx = (g.nx + BX - 1) / BX;
-    if (blk >= nbx * g.ny * g.nz) return;
+    const WnGrid& g = p.grid[f];
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int nbx = (nx + BX - 1) / BX;
+    if (blk >= nbx * ny * nz) return;
 
     const size_t per_warp = sizeof(WarpShared) + (size_t)HC * p.hs * 4 * sizeof(double);
     WarpShared& ws = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)warp * per_warp);
@@ -191,25 +220,54 @@ wn_k_edges(const WnEdgeParams p)
     const size_t fbase = (size_t)f * p.n_sites;
     const int* cs_f = p.cell_start + (size_t)f * (p.cell_cap + 1);
     /* home block: cells x0..x1 of row (cy, cz) -- contiguous in the cell-sorted array */
-    const int bx = blk % nbx, cy = (blk / nbx) % g.ny, cz = blk / (nbx * g.ny);
-    const int x0 = bx * BX, x1 = min(x0 + BX - 1, g.nx - 1);
-    const int row0 = (cz * g.ny + cy) * g.nx;
+    const int bx = blk % nbx, cy = (blk / nbx) % ny, cz = blk / (nbx * ny);
+    const int x0 = bx * BX, x1 = min(x0 + BX - 1, nx - 1);
+    const int row0 = (cz * ny + cy) * nx;
     const int h0 = __ldg(cs_f + row0 + x0), h1 = __ldg(cs_f + row0 + x1 + 1);
     if (h0 == h1) return;
 
-    /* half shell of the block: own cells + forward neighbours as 5 runs contiguous in x
-     *   lane 0: (y  , z  ) cells x0 .. x1+1      (own cells first)
-     *   lane 1: (y+1, z  ) cells x0-1 .. x1+1
-     *   lane 2..4: (y-1.., z+1) cells x0-1 .. x1+1                                   */
+    /* block-local frame for the fp32 prefilter: origin = centre of the home block, so
+     * |home| <= (BX/2, 1/2, 1/2) e and |candidate| <= (BX/2+1, 3/2, 3/2) e */
+    const float orx = (float)g.ox + ((float)x0 + 0.5f * (float)BX) * g.edge[0],
+                ory = (float)g.oy + ((float)cy + 0.5f) * g.edge[1],
+                orz = (float)g.oz + ((float)cz + 0.5f) * g.edge[2];
+    const float half_t = 0.5f * g.tf;
+
+    /* half shell of the block: own cells + forward neighbours, as runs contiguous in x.
+     * rows: 0:(y,z) cells x0..x1+1 (own cells first)   1:(y+1,z) cells x0-1..x1+1
+     *       2..4:(y-1..y+1, z+1) cells x0-1..x1+1
+     * lane r < 5: the in-range part of row r; lane 5+r (periodic only): the part of row r
+     * that wraps around in x, seen through its periodic image (origin shifted by -+Lx).
+     * A row that wraps in y or z keeps its cells and shifts the origin by -+Ly / -+Lz. */
     int rs = 0, rl = 0;
+    float sox = orx, soy = ory, soz = orz;          /* origin to subtract from this run's sites */
     if (lane < MAXRUN) {
-        const int y = (lane == 0) ? cy : (lane == 1 ? cy + 1 : cy + lane - 3);
-        const int z = (lane < 2) ? cz : cz + 1;
-        if (y >= 0 && y < g.ny && z < g.nz) {
-            const int xlo = (lane == 0) ? x0 : max(x0 - 1, 0), xhi = min(x1 + 1, g.nx - 1);
-            const int rowc = (z * g.ny + y) * g.nx;
-            rs = __ldg(cs_f + rowc + xlo);
-            rl = __ldg(cs_f + rowc + xhi + 1) - rs;
+        const int row = lane % 5, part = lane / 5;
+        int y = (row == 0) ? cy : (row == 1 ? cy + 1 : cy + row - 3);
+        int z = (row < 2) ? cz : cz + 1;
+        bool ok = true;
+        if (PBC) {
+            if (y < 0) { y += ny; soy = ory + (float)g.L[1]; } else if (y >= ny) { y -= ny; soy = ory - (float)g.L[1]; }
+            if (z >= nz) { z -= nz; soz = orz - (float)g.L[2]; }
+        } else {
+            ok = (y >= 0 && y < ny && z < nz) && part == 0;
+        }
+        if (ok) {
+            int xlo = (row == 0) ? x0 : x0 - 1, xhi = x1 + 1;
+            if (part == 0) {
+                xlo = max(xlo, 0); xhi = min(xhi, nx - 1);
+            } else if (xlo < 0) {                 /* cell nx-1 acting as cell -1: image at x - Lx */
+                xlo = nx - 1; xhi = nx - 1; sox = orx + (float)g.L[0];
+            } else if (xhi >= nx) {               /* cell 0 acting as cell nx: image at x + Lx */
+                xlo = 0; xhi = 0; sox = orx - (float)g.L[0];
+            } else {
+                ok = false;
+            }
+            if (ok) {
+                const int rowc = (z * ny + y) * nx;
+                rs = __ldg(cs_f + rowc + xlo);
+                rl = __ldg(cs_f + rowc + xhi + 1) - rs;
+            }
         }
     }
     const unsigned nzm = __ballot_sync(FULL, rl > 0);
@@ -217,20 +275,15 @@ wn_k_edges(const WnEdgeParams p)
     const int slot = __popc(nzm & ((1u << lane) - 1u));
     int inc = rl;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
+    for (int o = 1; o < 16; o <<= 1) {
         const int t = __shfl_up_sync(FULL, inc, o);
         if (lane >= o) inc += t;
     }
     const int total = __shfl_sync(FULL, inc, MAXRUN - 1);
-    if (rl > 0) { ws.run_start[slot] = rs; ws.run_pref[slot] = inc - rl; }
-
-    /* block-local frame for the fp32 prefilter: origin = centre of the home block, so
-     * |home| <= (BX/2, 1/2, 1/2) e and |candidate| <= (BX/2+1, 3/2, 3/2) e */
-    const float edge = g.edge;
-    const float orx = (float)g.ox + ((float)x0 + 0.5f * (float)BX) * edge,
-                ory = (float)g.oy + ((float)cy + 0.5f) * edge,
-                orz = (float)g.oz + ((float)cz + 0.5f) * edge;
-    const float half_t = 0.5f * g.tf;
+    if (rl > 0) {
+        ws.run_start[slot] = rs; ws.run_pref[slot] = inc - rl;
+        ws.run_org[slot] = make_float4(sox, soy, soz, 0.f);
+    }
 
     Counters ct = {0u, 0u, 0u, 0u};
     for (int hb = h0; hb < h1; hb += HC) {
@@ -270,12 +323,17 @@ wn_k_edges(const WnEdgeParams p)
                 while (run + 1 < n_runs && v >= ws.run_pref[run + 1]) ++run;
                 const int c = ws.run_start[run] + (v - ws.run_pref[run]);
                 const float4 b4 = __ldg(p.spos + fbase + c);
-                cx_ = b4.x - orx; cy_ = b4.y - ory; cz_ = b4.z - orz;
+                if (PBC) {
+                    const float4 o4 = ws.run_org[run];
+                    cx_ = b4.x - o4.x; cy_ = b4.y - o4.y; cz_ = b4.z - o4.z;
+                } else {
+                    cx_ = b4.x - orx; cy_ = b4.y - ory; cz_ = b4.z - orz;
+                }
                 cn = 0.5f * (cx_ * cx_ + cy_ * cy_ + cz_ * cz_);
                 code_c = (uint32_t)c;
                 /* own block: only home rows stored before the candidate (each pair once) */
                 const int ahead = c - hb;
-                allow = (c >= h1 || ahead >= 32) ? 0xffffffffu : (ahead <= 0 ? 0u : ((1u << ahead) - 1u));
+                allow = (c < h0 || c >= h1 || ahead >= 32) ? 0xffffffffu : (ahead <= 0 ? 0u : ((1u << ahead) - 1u));
                 if (p.first_limit < p.n_sites && __float_as_int(b4.w) >= p.first_limit) allow &= low_rows;
                 if (!SIMPLE) cm = __ldg(p.smeta + fbase + c);
             }
@@ -326,7 +384,7 @@ wn_k_edges(const WnEdgeParams p)
                     qlen += tot;
                     __syncwarp();
                     while (qlen >= 32) {
-                        wn_eval_batch<SIMPLE>(p, fbase, ws, hdh, qlen - 32, 32, ct, lane);
+                        wn_eval_batch<SIMPLE, PBC>(p, fbase, ws, hdh, g, qlen - 32, 32, ct, lane);
                         qlen -= 32;
                     }
                     __syncwarp();
@@ -335,7 +393,7 @@ wn_k_edges(const WnEdgeParams p)
         }
         if (qlen > 0) {
             __syncwarp();
-            wn_eval_batch<SIMPLE>(p, fbase, ws, hdh, 0, qlen, ct, lane);
+            wn_eval_batch<SIMPLE, PBC>(p, fbase, ws, hdh, g, 0, qlen, ct, lane);
         }
     }
     if (lane == 0) {
@@ -347,6 +405,56 @@ wn_k_edges(const WnEdgeParams p)
     }
 }
 
+/* ---- all-pairs variant ----
+ * Periodic boxes with fewer than 3 cells in some dimension (e.g. the 216-water box,
+ * L = 1.86 nm): neighbour cells alias under wrap-around, so the cell sweep cannot count
+ * each pair once.  Such systems are small; one thread per cell-sorted site p pairs it with
+ * every later site q > p, exact fp64 minimum-image geometry, same output path. */
+template <bool SIMPLE, bool PBC>
+__global__ void __launch_bounds__(128)
+wn_k_edges_small(const WnEdgeParams p)
+{
+    __shared__ float4 tile[128];
+    const int f = blockIdx.y;
+    const WnGrid& g = p.grid[f];
+    const size_t fbase = (size_t)f * p.n_sites;
+    const int pa = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = pa < p.n_sites;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t ma = 0;
+    if (have) { a4 = __ldg(p.spos + fbase + pa); ma = __ldg(p.smeta + fbase + pa); }
+    const int ia = __float_as_int(a4.w);
+    const double* dha = p.sdh + (fbase + (have ? pa : 0)) * (size_t)p.hs * 4;
+    unsigned int evals = 0, tie_len = 0, tie_cos = 0, tie_pos0 = 0;
+    for (int q0 = blockIdx.x * blockDim.x; q0 < p.n_sites; q0 += 128) {
+        __syncthreads();
+        if (q0 + (int)threadIdx.x < p.n_sites) tile[threadIdx.x] = __ldg(p.spos + fbase + q0 + threadIdx.x);
+        __syncthreads();
+        if (!have) continue;
+        const int kend = min(128, p.n_sites - q0);
+        for (int k = max(0, pa + 1 - q0); k < kend; ++k) {
+            const float4 b4 = tile[k];
+            const int ib = __float_as_int(b4.w);
+            if (min(ia, ib) >= p.first_limit) continue;
+            const uint32_t mb = __ldg(p.smeta + fbase + q0 + k);
+            if (!SIMPLE) {
+                const uint32_t ta = ma & WN_META_TYPE_MASK, tb = mb & WN_META_TYPE_MASK;
+                if (!((ta != tb) || (ta == WN_WATER && tb == WN_WATER))) continue;   /* :199-203 */
+                if (!((ma | mb) & WN_META_HASH)) continue;                             /* :205-208 */
+            }
+            const PairOut r = wn_pair_geometry<SIMPLE, PBC>(a4, b4, dha, p.sdh + (fbase + q0 + k) * (size_t)p.hs * 4,
+                                                            ma, mb, g);
+            evals += r.counted; tie_len += r.t_len; tie_cos += r.t_cos; tie_pos0 += r.t_pos0;
+            if (r.edge) wn_emit_edge(p, fbase, ia, ib, r.len_f, r.cosmax);
+        }
+    }
+    WnFrameCounters* fc = p.counters + f;
+    if (evals) atomicAdd(&fc->evals, (unsigned long long)evals);
+    if (tie_len) atomicAdd(&fc->tie_len, (unsigned long long)tie_len);
+    if (tie_cos) atomicAdd(&fc->tie_cos, (unsigned long long)tie_cos);
+    if (tie_pos0) atomicAdd(&fc->tie_pos0, (unsigned long long)tie_pos0);
+}
+
 }  // namespace
 
 size_t wn_edges_smem_bytes(int hs)
@@ -354,15 +462,41 @@ size_t wn_edges_smem_bytes(int hs)
     return (size_t)WARPS_PER_CTA * (sizeof(WarpShared) + (size_t)HC * hs * 4 * sizeof(double));
 }
 
-void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st)
+namespace {
+template <bool SIMPLE, bool PBC, int BX>
+void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
     const size_t smem = wn_edges_smem_bytes(p.hs);
+    /* blocks per frame <= ceil(nx/BX)*ny*nz <= cell_cap */
     dim3 grid((p.cell_cap + WARPS_PER_CTA - 1) / WARPS_PER_CTA, n_frames);
+    cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wn_k_edges<SIMPLE, PBC, BX><<<grid, WARPS_PER_CTA * 32, smem, st>>>(p);
+}
+}  // namespace
+
+void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st)
+{
+    const int key = (p.simple ? 4 : 0) | (p.pbc ? 2 : 0) | (p.bx == 2 ? 1 : 0);
+    switch (key) {
+    case 0: launch_variant<false, false, 1>(p, n_frames, st); break;
+    case 1: launch_variant<false, false, 2>(p, n_frames, st); break;
+    case 2: launch_variant<false, true, 1>(p, n_frames, st); break;
+    case 3: launch_variant<false, true, 2>(p, n_frames, st); break;
+    case 4: launch_variant<true, false, 1>(p, n_frames, st); break;
+    case 5: launch_variant<true, false, 2>(p, n_frames, st); break;
+    case 6: launch_variant<true, true, 1>(p, n_frames, st); break;
+    default: launch_variant<true, true, 2>(p, n_frames, st); break;
+    }
+}
+
+void wn_launch_edges_small(const WnEdgeParams& p, int n_frames, cudaStream_t st)
+{
+    dim3 grid((p.n_sites + 127) / 128, n_frames);
     if (p.simple) {
-        cudaFuncSetAttribute(wn_k_edges<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        wn_k_edges<true><<<grid, WARPS_PER_CTA * 32, smem, st>>>(p);
+        if (p.pbc) wn_k_edges_small<true, true><<<grid, 128, 0, st>>>(p);
+        else wn_k_edges_small<true, false><<<grid, 128, 0, st>>>(p);
     } else {
-        cudaFuncSetAttribute(wn_k_edges<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        wn_k_edges<false><<<grid, WARPS_PER_CTA * 32, smem, st>>>(p);
+        if (p.pbc) wn_k_edges_small<false, true><<<grid, 128, 0, st>>>(p);
+        else wn_k_edges_small<false, false><<<grid, 128, 0, st>>>(p);
     }
 }

@@ -26,9 +26,9 @@ struct PairTile {
     float  fx[TILE], fy[TILE], fz[TILE];
 };
 
-template <bool FILL>
+template <bool FILL, bool PBC>
 __global__ void __launch_bounds__(ROWS)
-wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit,
+wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit, const WnPairBox box,
            uint32_t* __restrict__ row_cnt, const unsigned long long* __restrict__ row_off,
            int32_t* __restrict__ pairs, unsigned long long* __restrict__ ties)
 {
@@ -60,14 +60,28 @@ wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit,
         const int kend = min(TILE, n - j0);
         const int kbeg = max(0, i + 1 - j0);
         for (int k = kbeg; k < kend; ++k) {
-            const float dxf = fxi - t.fx[k], dyf = fyi - t.fy[k], dzf = fzi - t.fz[k];
+            float dxf = fxi - t.fx[k], dyf = fyi - t.fy[k], dzf = fzi - t.fz[k];
+            if (PBC) {
+                /* approximate minimum image; near +-L/2 either image has the same |d| */
+                dxf -= rintf(dxf * box.invLf[0]) * box.Lf[0];
+                dyf -= rintf(dyf * box.invLf[1]) * box.Lf[1];
+                dzf -= rintf(dzf * box.invLf[2]) * box.Lf[2];
+            }
             const float d2f = dxf * dxf + dyf * dyf + dzf * dzf;
             /* error of d2f vs exact: <= ~1e-6 relative from arithmetic plus
              * 2*|d|*eps*|coord| from rounding the coordinates to float */
             const float ca = fmaxf(amax, fmaxf(fmaxf(fabsf(t.fx[k]), fabsf(t.fy[k])), fabsf(t.fz[k])));
-            const float bound = 4.225f * 1.00002f + 1.0e-5f * ca * (1.0f + ca);
+            /* periodic: the fp32 image shift adds <= ~1e-6 * L per component on top */
+            const float bound = 4.225f * 1.00002f + 1.0e-5f * ca * (1.0f + ca) +
+                                (PBC ? 3.0e-5f * (box.Lf[0] + box.Lf[1] + box.Lf[2]) : 0.0f);
             if (d2f > bound) continue;
-            const double dx = __dsub_rn(xi, t.x[k]), dy = __dsub_rn(yi, t.y[k]), dz = __dsub_rn(zi, t.z[k]);
+            double dx = __dsub_rn(xi, t.x[k]), dy = __dsub_rn(yi, t.y[k]), dz = __dsub_rn(zi, t.z[k]);
+            if (PBC) {
+                /* periodic definition (oracle/wn_oracle.h): d - rint(d * (1/L)) * L */
+                dx = __dsub_rn(dx, __dmul_rn(rint(__dmul_rn(dx, box.invL[0])), box.L[0]));
+                dy = __dsub_rn(dy, __dmul_rn(rint(__dmul_rn(dy, box.invL[1])), box.L[1]));
+                dz = __dsub_rn(dz, __dmul_rn(rint(__dmul_rn(dz, box.invL[2])), box.L[2]));
+            }
             const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
             const double lhs = __dmul_rn(10.0, d2);
             if (lhs < 42.25) {
@@ -124,11 +138,13 @@ wn_k_pairs_scan(const uint32_t* __restrict__ row_cnt, int n, unsigned long long*
 
 }  // namespace
 
-void wn_launch_pairs_count(const double* xyz, int n, int first_limit, uint32_t* row_cnt,
+void wn_launch_pairs_count(const double* xyz, int n, int first_limit, WnPairBox box, uint32_t* row_cnt,
                            unsigned long long* ties, cudaStream_t st)
 {
-    wn_k_pairs<false><<<(n + ROWS - 1) / ROWS, ROWS, 0, st>>>(xyz, n, first_limit, row_cnt, nullptr,
-                                                              nullptr, ties);
+    if (box.pbc)
+        wn_k_pairs<false, true><<<(n + ROWS - 1) / ROWS, ROWS, 0, st>>>(xyz, n, first_limit, box, row_cnt, nullptr, nullptr, ties);
+    else
+        wn_k_pairs<false, false><<<(n + ROWS - 1) / ROWS, ROWS, 0, st>>>(xyz, n, first_limit, box, row_cnt, nullptr, nullptr, ties);
 }
 
 void wn_launch_pairs_scan(const uint32_t* row_cnt, int n, unsigned long long* row_off, cudaStream_t st)
@@ -136,9 +152,11 @@ void wn_launch_pairs_scan(const uint32_t* row_cnt, int n, unsigned long long* ro
     wn_k_pairs_scan<<<1, 1024, 0, st>>>(row_cnt, n, row_off);
 }
 
-void wn_launch_pairs_fill(const double* xyz, int n, int first_limit,
+void wn_launch_pairs_fill(const double* xyz, int n, int first_limit, WnPairBox box,
                           const unsigned long long* row_off, int32_t* pairs, cudaStream_t st)
 {
-    wn_k_pairs<true><<<(n + ROWS - 1) / ROWS, ROWS, 0, st>>>(xyz, n, first_limit, nullptr, row_off,
-                                                             pairs, nullptr);
+    if (box.pbc)
+        wn_k_pairs<true, true><<<(n + ROWS - 1) / ROWS, ROWS, 0, st>>>(xyz, n, first_limit, box, nullptr, row_off, pairs, nullptr);
+    else
+        wn_k_pairs<true, false><<<(n + ROWS - 1) / ROWS, ROWS, 0, st>>>(xyz, n, first_limit, box, nullptr, row_off, pairs, nullptr);
 }

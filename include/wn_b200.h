@@ -113,6 +113,13 @@ const char* wn_version(void);
 int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
                   const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
 
+/* Periodic variant (north-star extension; the reference has no PBC -- analyzeFrame
+ * receives t_pbc* and never touches it, src/waternetwork.cpp:503).  box = (Lx,Ly,Lz) of a
+ * rectangular box; displacements are minimum images, d - rint(d/L)*L in fp64 (definition
+ * frozen in oracle/wn_oracle.h).  Triclinic boxes are not supported. */
+int wn_find_pairs_pbc(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
+                      const float box[3], const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
+
 /* ---- site tables (src/waternetwork.cpp:538-577) --------------------------
  * site_atom[n_sites]: atom index (into a frame) of each site.
  * h_atom[n_sites*hmax]: atom indices of its hydrogen list in list order, -1 padded.
@@ -141,6 +148,13 @@ int wn_hbond_batch(wn_ctx* ctx, const float* frames_host, int32_t n_frames,
                    int32_t natoms, wn_batch_result* out);
 int wn_hbond_batch_dev(wn_ctx* ctx, const float* frames_dev, int32_t n_frames,
                        int32_t natoms, wn_batch_result* out);
+/* Periodic variants: boxes = host float32 [n_frames][3] = (Lx,Ly,Lz) of every frame (the
+ * diagonal of GROMACS' t_trxframe::box; rectangular boxes only).  Coordinates are first put
+ * in the box, every displacement is the fp64 minimum image (oracle/wn_oracle.h). */
+int wn_hbond_batch_pbc(wn_ctx* ctx, const float* frames_host, const float* boxes_host,
+                       int32_t n_frames, int32_t natoms, wn_batch_result* out);
+int wn_hbond_batch_pbc_dev(wn_ctx* ctx, const float* frames_dev, const float* boxes_host,
+                           int32_t n_frames, int32_t natoms, wn_batch_result* out);
 /* Frames that one wn_hbond_batch* call processes per kernel pipeline pass
  * (larger inputs are split internally).  0 restores the default heuristic. */
 int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);

@@ -275,3 +275,145 @@ size_t wno_frame_hbonds(const float* frame_xyz, int natoms,
     free(tmp); free(pairs); free(h_off); free(h_xyz); free(site_xyz);
     return ne <= cap ? ne : (size_t)-1;
 }
+
+/* ======================= periodic boundaries (defined here, see wn_oracle.h) ======================= */
+
+static inline double minimg(double d, double L, double invL)
+{
+    return d - rint(d * invL) * L;
+}
+
+void wno_wrap_frame(const float* frame_xyz, int natoms, const float box[3], float* out_xyz)
+{
+    int a, c;
+    for (a = 0; a < natoms; ++a)
+        for (c = 0; c < 3; ++c) {
+            const double L = (double)box[c], invL = 1.0 / L;
+            const double x = (double)frame_xyz[3 * (size_t)a + c];
+            out_xyz[3 * (size_t)a + c] = (float)(x - floor(x * invL) * L);
+        }
+}
+
+/* the pair test of src/brute-find-pairs.cpp:19-30 on minimum-image displacements */
+size_t wno_brute_find_pairs_pbc(const double* xyz, int n, int first_limit, const float box[3],
+                                int32_t* pairs, size_t cap, wno_ties* ties)
+{
+    float cutoff = 6.5f;
+    size_t count = 0;
+    int i, j, c;
+    double L[3], invL[3];
+    cutoff *= cutoff;
+    for (c = 0; c < 3; ++c) { L[c] = (double)box[c]; invL[c] = 1.0 / L[c]; }
+    if (first_limit > n) first_limit = n;
+    for (i = 0; i < first_limit; ++i)
+        for (j = i + 1; j < n; ++j) {
+            v3 d = v3_sub(xyz + 3 * (size_t)i, xyz + 3 * (size_t)j);
+            double lhs;
+            d.x = minimg(d.x, L[0], invL[0]); d.y = minimg(d.y, L[1], invL[1]); d.z = minimg(d.z, L[2], invL[2]);
+            lhs = 10.0 * v3_dot(d, d);
+            if (lhs < cutoff) {
+                if (pairs && count < cap) { pairs[2 * count] = i; pairs[2 * count + 1] = j; }
+                ++count;
+            } else if (ties && lhs == (double)cutoff) {
+                ties->pair_cutoff_equal++;
+            }
+        }
+    return count;
+}
+
+/* make_edges (src/waternetwork.cpp:182-263) on minimum-image displacements */
+static size_t make_edges_pbc(const int32_t* pairs, size_t m, const double* site_xyz, int n,
+                             const double* h_xyz, const int32_t* h_off, const uint8_t* site_type,
+                             const double L[3], const double invL[3],
+                             wno_edge* out, uint64_t* n_evals, wno_ties* ties)
+{
+    size_t count = 0, k;
+    uint64_t evals = 0;
+    int maxh = 0, s;
+    float *coss, *energies;
+    for (s = 0; s < n; ++s) { int nh = h_off[s + 1] - h_off[s]; if (nh > maxh) maxh = nh; }
+    coss = (float*)malloc(sizeof(float) * (size_t)(2 * maxh + 1));
+    energies = (float*)malloc(sizeof(float) * (size_t)(2 * maxh + 1));
+    for (k = 0; k < m; ++k) {
+        const int a = pairs[2 * k], b = pairs[2 * k + 1];
+        const double* pa = site_xyz + 3 * (size_t)a;
+        const double* pb = site_xyz + 3 * (size_t)b;
+        const int nha = h_off[a + 1] - h_off[a], nhb = h_off[b + 1] - h_off[b];
+        int isedge = 0;
+        v3 OO = v3_sub(pa, pb);
+        float distance;
+        OO.x = minimg(OO.x, L[0], invL[0]); OO.y = minimg(OO.y, L[1], invL[1]); OO.z = minimg(OO.z, L[2], invL[2]);
+        distance = (float)sqrt(v3_dot(OO, OO));
+        OO = v3_div(OO, (double)distance);
+        distance = (float)((double)distance * 10.0);
+        if (site_type[a] != site_type[b]) isedge = 1;
+        if (site_type[a] == WNO_WATER && site_type[b] == WNO_WATER) isedge = 1;
+        if (ties && distance == 6.5f) ties->length_equal_cut++;
+        if ((double)distance > 6.5) isedge = 0;
+        if (nha == 0 && nhb == 0) isedge = 0;
+        if (isedge) {
+            int nc = 0, h, pos = -1, i;
+            float cosmax = 0.0f;
+            ++evals;
+            for (h = 0; h < nha + nhb; ++h) {
+                const int first = h < nha;
+                const double* hp = h_xyz + 3 * (size_t)(first ? h_off[a] + h : h_off[b] + h - nha);
+                v3 DH = v3_sub(hp, first ? pa : pb);
+                float proj;
+                DH.x = minimg(DH.x, L[0], invL[0]); DH.y = minimg(DH.y, L[1], invL[1]); DH.z = minimg(DH.z, L[2], invL[2]);
+                DH = v3_div(DH, sqrt(v3_dot(DH, DH)));
+                proj = first ? (float)v3_dot(DH, OO) : (float)v3_dot(DH, v3_scale(-1.0, OO));
+                energies[nc] = (float)wno_compute_energy((double)distance, (double)proj);
+                coss[nc] = proj;
+                ++nc;
+            }
+            for (i = 0; i < nc; ++i) {
+                if (coss[i] > cosmax) { cosmax = coss[i]; pos = i; }
+                else if (ties && cosmax > 0.0f && coss[i] == cosmax) ties->cosine_argmax_equal++;
+            }
+            if (ties && pos == 0) ties->pos_zero++;
+            if (pos > 0) {
+                out[count].i = a; out[count].j = b;
+                out[count].energy = energies[pos]; out[count].length = distance; out[count].cosine = coss[pos];
+                ++count;
+            }
+        }
+    }
+    free(coss); free(energies);
+    if (n_evals) *n_evals = evals;
+    return count;
+}
+
+size_t wno_frame_hbonds_pbc(const float* frame_xyz, int natoms,
+                            const int32_t* site_atom, const int32_t* h_atom, int hmax,
+                            const uint8_t* site_type, int n, int first_limit, const float box[3],
+                            wno_edge* edges, size_t cap, double* stats,
+                            uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties)
+{
+    float* wrapped = (float*)malloc(sizeof(float) * 3 * (size_t)(natoms > 0 ? natoms : 1));
+    double* site_xyz = (double*)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
+    double* h_xyz = (double*)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1) * (size_t)(hmax > 0 ? hmax : 1));
+    int32_t* h_off = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1));
+    int32_t* pairs;
+    wno_edge* tmp;
+    size_t m, ne, k;
+    double sum_e = 0.0, L[3], invL[3];
+    int c;
+    for (c = 0; c < 3; ++c) { L[c] = (double)box[c]; invL[c] = 1.0 / L[c]; }
+    wno_wrap_frame(frame_xyz, natoms, box, wrapped);
+    wno_gather_sites(wrapped, natoms, site_atom, h_atom, hmax, n, site_xyz, h_xyz, h_off);
+    m = wno_brute_find_pairs_pbc(site_xyz, n, first_limit, box, NULL, 0, NULL);
+    pairs = (int32_t*)malloc(sizeof(int32_t) * 2 * (m ? m : 1));
+    wno_brute_find_pairs_pbc(site_xyz, n, first_limit, box, pairs, m, ties);
+    tmp = (wno_edge*)malloc(sizeof(wno_edge) * (m ? m : 1));
+    ne = make_edges_pbc(pairs, m, site_xyz, n, h_xyz, h_off, site_type, L, invL, tmp, n_evals, ties);
+    if (n_pairs) *n_pairs = m;
+    for (k = 0; k < ne; ++k) sum_e += (double)tmp[k].energy;
+    if (stats) {
+        stats[0] = (double)n; stats[1] = (double)ne;
+        stats[2] = n > 0 ? 1.0 * (double)ne / (double)n : 0.0; stats[3] = sum_e;
+    }
+    if (ne <= cap && edges) memcpy(edges, tmp, sizeof(wno_edge) * ne);
+    free(tmp); free(pairs); free(h_off); free(h_xyz); free(site_xyz); free(wrapped);
+    return ne <= cap ? ne : (size_t)-1;
+}

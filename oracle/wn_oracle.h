@@ -106,6 +106,25 @@ size_t wno_frame_hbonds(const float* frame_xyz, int natoms,
                         wno_edge* edges, size_t cap, double* stats,
                         uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties);
 
+/* ---- periodic boundaries (north-star extension; the reference has no PBC).
+ * There is no reference oracle for this mode: THIS FILE DEFINES IT (SURVEY Appendix A.4,
+ * frozen here).  Rectangular box L = (Lx,Ly,Lz), float32 as in a GROMACS frame:
+ *   1. every coordinate is first put in the box in fp64 and rounded back to float:
+ *        pw = (float)(x - floor(x * (1.0/L)) * L)          (identity for 0 <= x < L)
+ *   2. every displacement the path forms (site - site, hydrogen - site) is the minimum
+ *      image of the fp64 difference of those floats:
+ *        d = (double)pa - (double)pb;  d = d - rint(d * (1.0/L)) * L
+ *      (round-half-even: a displacement of exactly +-L/2 is kept; d(b,a) == -d(a,b))
+ *   3. everything else is Appendix A.1-A.3 unchanged on those displacements. */
+void wno_wrap_frame(const float* frame_xyz, int natoms, const float box[3], float* out_xyz);
+size_t wno_brute_find_pairs_pbc(const double* xyz, int n, int first_limit, const float box[3],
+                                int32_t* pairs, size_t cap, wno_ties* ties);
+size_t wno_frame_hbonds_pbc(const float* frame_xyz, int natoms,
+                            const int32_t* site_atom, const int32_t* h_atom, int hmax,
+                            const uint8_t* site_type, int n, int first_limit, const float box[3],
+                            wno_edge* edges, size_t cap, double* stats,
+                            uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties);
+
 #ifdef __cplusplus
 }
 #endif

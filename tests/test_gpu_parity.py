@@ -286,3 +286,109 @@ def test_find_pairs_full_size_rows(ctx, oracle):
     assert np.array_equal(got[got[:, 0] < 64], want)
     lim, _ = ctx.find_pairs(xyz, first_limit=64)
     assert np.array_equal(lim, want)
+
+
+# ------------------------------------------------------------------ periodic boxes
+def oracle_frames_pbc(oracle, frames, boxes, site_atom, h_atom, site_type, first_limit=None):
+    edges, stats, evals = [], [], 0
+    ties = oracle.Ties()
+    for f in range(frames.shape[0]):
+        e, s, _, ev = oracle.frame_hbonds_pbc(frames[f], site_atom, h_atom, site_type, boxes[f],
+                                              first_limit=first_limit, ties=ties)
+        edges.append(e); stats.append(s); evals += ev
+    return edges, np.array(stats), evals, ties.as_dict()
+
+
+@pytest.mark.parametrize("n_waters,model,nf", [(216, 1, 4),      # BASELINE configs[0] box: 2 cells/dim -> all-pairs kernel
+                                               (512, 0, 3),      # 3 cells/dim -> 1-cell home blocks
+                                               (1000, 0, 3),     # 4 cells/dim -> 2-cell home blocks, every block wraps
+                                               (4000, 0, 2)])
+def test_periodic_water_box(ctx, oracle, n_waters, model, nf):
+    box = oracle.synth_box(n_waters, model=model)
+    frames = oracle.synth_frames(box, 0, nf)
+    L = np.float32(box.box)
+    boxes = np.tile(np.array([L, L, L], np.float32), (nf, 1))
+    sa, ha, ty = oracle.water_site_table(n_waters)
+    ctx.set_water_sites(n_waters)
+    res = ctx.hbond_batch(frames, boxes=boxes)
+    compare_batch(res, *oracle_frames_pbc(oracle, frames, boxes, sa, ha, ty))
+    # more edges than with open boundaries (pairs through the box faces)
+    assert res["n_edges"] > ctx.hbond_batch(frames)["n_edges"]
+
+
+def test_periodic_anisotropic_unwrapped_mixed(ctx, oracle):
+    """Anisotropic box that changes per frame, molecules displaced by whole box vectors
+    (unwrapped trajectory), broken molecules (hydrogen on the other side of the box),
+    mixed site types, asymmetric search."""
+    rng = np.random.default_rng(8)
+    n_sites, hmax, nf = 500, 3, 3
+    natoms = 4 * n_sites
+    site_atom = np.arange(n_sites, dtype=np.int32) * 4
+    nh = rng.integers(0, 4, size=n_sites)
+    h_atom = -np.ones((n_sites, hmax), np.int32)
+    for s in range(n_sites):
+        for k in range(nh[s]):
+            h_atom[s, k] = site_atom[s] + 1 + k
+    for s in range(0, n_sites, 5):
+        h_atom[s] = [site_atom[s], site_atom[s] + 1, -1]
+    site_type = rng.integers(0, 3, size=n_sites).astype(np.uint8)
+    frames = np.zeros((nf, natoms, 3), np.float32)
+    boxes = np.zeros((nf, 3), np.float32)
+    for f in range(nf):
+        boxes[f] = [2.7 + 0.1 * f, 3.4, 2.1 + 0.2 * f]          # 4,5,3 cells ... 4,5,3
+        pos = rng.uniform(0, 1, size=(n_sites, 3)) * boxes[f]
+        frames[f, 0::4] = pos
+        for k in range(3):
+            d = rng.normal(size=(n_sites, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+            frames[f, 1 + k::4] = pos + 0.1 * d                  # some hydrogens stick out of the box
+        # unwrap: whole molecules moved by integer box vectors; single hydrogens too (broken molecules)
+        shift = rng.integers(-2, 3, size=(n_sites, 3)) * boxes[f]
+        for k in range(4):
+            frames[f, k::4] += shift
+        frames[f, 1::4][::7] += boxes[f]
+    for first_limit in (None, 60):
+        ctx.set_sites(site_atom, h_atom, site_type, first_limit=first_limit)
+        res = ctx.hbond_batch(frames, boxes=boxes)
+        compare_batch(res, *oracle_frames_pbc(oracle, frames, boxes, site_atom, h_atom, site_type, first_limit))
+    assert res["n_edges"] > 0
+
+
+def test_periodic_huge_box_equals_open_boundary(ctx, oracle):
+    n = 600
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 3, 2)
+    ctx.set_water_sites(n)
+    a = ctx.hbond_batch(frames)
+    b = ctx.hbond_batch(frames, boxes=np.full((2, 3), 50.0, np.float32))
+    assert a["edges"].tobytes() == b["edges"].tobytes() and np.array_equal(a["frame_offsets"], b["frame_offsets"])
+
+
+def test_periodic_device_batch_and_bad_boxes(ctx, oracle, capi):
+    n, nf = 1000, 5
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 0, nf)
+    boxes = np.full((nf, 3), np.float32(box.box), np.float32)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    d = ctx.dev_alloc(frames.nbytes)
+    ctx.h2d(d, frames)
+    ctx.set_batch_frames(2)
+    out = ctx.hbond_batch_dev(d, nf, 3 * n, boxes=boxes)
+    ctx.set_batch_frames(0)
+    e, fo, st = ctx.fetch_dev_result(out)
+    ctx.dev_free(d)
+    compare_batch(dict(out, edges=e, frame_offsets=fo, stats=st),
+                  *oracle_frames_pbc(oracle, frames, boxes, sa, ha, ty))
+    with pytest.raises(capi.WnError):
+        ctx.hbond_batch(frames, boxes=np.zeros((nf, 3), np.float32))
+
+
+def test_find_pairs_periodic(ctx, oracle):
+    rng = np.random.default_rng(12)
+    for n, L in ((300, (1.9, 2.2, 3.0)), (1500, (5.0, 4.3, 6.1))):
+        xyz = (rng.uniform(-1, 2, size=(n, 3)) * np.array(L)).astype(np.float32).astype(np.float64)
+        want = oracle.brute_find_pairs_pbc(xyz, L)
+        got, _ = ctx.find_pairs(xyz, box=L)
+        assert np.array_equal(got, want)
+        got, _ = ctx.find_pairs(xyz, first_limit=40, box=L)
+        assert np.array_equal(got, oracle.brute_find_pairs_pbc(xyz, L, first_limit=40))
