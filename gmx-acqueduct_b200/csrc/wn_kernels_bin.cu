@@ -90,7 +90,7 @@ wn_k_bbox(const float* __restrict__ frames, int natoms, const int* __restrict__ 
     }
 }
 
-/* periodic mode, step 1 of the definition (oracle/wn_oracle.h): put the coordinate in the
+/* periodic mode, step 1 of the definition (include/wn_b200.h, "Periodic boundaries"): put the coordinate in the
  * box in fp64 and round back to float; identity for 0 <= x < L */
 __device__ __forceinline__ float wn_wrap(float x, double L, double invL)
 {

@@ -71,7 +71,7 @@ __device__ __forceinline__ float wn_dot_f32(const double* __restrict__ d, double
     return __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(d[0], ux), __dmul_rn(d[1], uy)), __dmul_rn(d[2], uz)));
 }
 
-/* minimum image of a displacement component (periodic definition, oracle/wn_oracle.h):
+/* minimum image of a displacement component (periodic definition, include/wn_b200.h, "Periodic boundaries"):
  * d - rint(d * (1/L)) * L, every operation rounded, round-half-even in rint */
 __device__ __forceinline__ double wn_minimg(double d, double L, double invL)
 {

@@ -77,7 +77,7 @@ wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit, const WnPairB
             if (d2f > bound) continue;
             double dx = __dsub_rn(xi, t.x[k]), dy = __dsub_rn(yi, t.y[k]), dz = __dsub_rn(zi, t.z[k]);
             if (PBC) {
-                /* periodic definition (oracle/wn_oracle.h): d - rint(d * (1/L)) * L */
+                /* periodic definition (include/wn_b200.h, "Periodic boundaries"): d - rint(d * (1/L)) * L */
                 dx = __dsub_rn(dx, __dmul_rn(rint(__dmul_rn(dx, box.invL[0])), box.L[0]));
                 dy = __dsub_rn(dy, __dmul_rn(rint(__dmul_rn(dy, box.invL[1])), box.L[1]));
                 dz = __dsub_rn(dz, __dmul_rn(rint(__dmul_rn(dz, box.invL[2])), box.L[2]));

@@ -113,10 +113,19 @@ const char* wn_version(void);
 int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
                   const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
 
-/* Periodic variant (north-star extension; the reference has no PBC -- analyzeFrame
- * receives t_pbc* and never touches it, src/waternetwork.cpp:503).  box = (Lx,Ly,Lz) of a
- * rectangular box; displacements are minimum images, d - rint(d/L)*L in fp64 (definition
- * frozen in oracle/wn_oracle.h).  Triclinic boxes are not supported. */
+/* ---- Periodic boundaries (north-star extension) ---------------------------
+ * The reference has no PBC: analyzeFrame receives t_pbc* and never touches it
+ * (src/waternetwork.cpp:503), BruteFindPairs uses plain Euclidean distances
+ * (src/brute-find-pairs.cpp:25).  The periodic mode is therefore DEFINED here (and restated
+ * by the test oracle).  Rectangular box L = (Lx,Ly,Lz), float32 as in a GROMACS frame:
+ *   1. wn_hbond_batch_pbc*: every coordinate is first put in the box in fp64 and rounded
+ *      back to float, pw = (float)(x - floor(x * (1.0/L)) * L)   (identity for 0 <= x < L);
+ *      wn_find_pairs_pbc takes the caller's points as they are.
+ *   2. every displacement the path forms (site - site, hydrogen - site) is the minimum
+ *      image of the fp64 difference, d = pa - pb; d = d - rint(d * (1.0/L)) * L
+ *      (every operation rounded, rint half-to-even: +-L/2 is kept, d(b,a) == -d(a,b)).
+ *   3. everything else is unchanged.
+ * Triclinic boxes are not supported. */
 int wn_find_pairs_pbc(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
                       const float box[3], const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
 
@@ -150,7 +159,7 @@ int wn_hbond_batch_dev(wn_ctx* ctx, const float* frames_dev, int32_t n_frames,
                        int32_t natoms, wn_batch_result* out);
 /* Periodic variants: boxes = host float32 [n_frames][3] = (Lx,Ly,Lz) of every frame (the
  * diagonal of GROMACS' t_trxframe::box; rectangular boxes only).  Coordinates are first put
- * in the box, every displacement is the fp64 minimum image (oracle/wn_oracle.h). */
+ * in the box, every displacement is the fp64 minimum image ("Periodic boundaries" above). */
 int wn_hbond_batch_pbc(wn_ctx* ctx, const float* frames_host, const float* boxes_host,
                        int32_t n_frames, int32_t natoms, wn_batch_result* out);
 int wn_hbond_batch_pbc_dev(wn_ctx* ctx, const float* frames_dev, const float* boxes_host,

@@ -107,8 +107,8 @@ size_t wno_frame_hbonds(const float* frame_xyz, int natoms,
                         uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties);
 
 /* ---- periodic boundaries (north-star extension; the reference has no PBC).
- * There is no reference oracle for this mode: THIS FILE DEFINES IT (SURVEY Appendix A.4,
- * frozen here).  Rectangular box L = (Lx,Ly,Lz), float32 as in a GROMACS frame:
+ * There is no reference oracle for this mode; it is defined in include/wn_b200.h
+ * ("Periodic boundaries", after SURVEY Appendix A.4) and restated here independently.  Rectangular box L = (Lx,Ly,Lz), float32 as in a GROMACS frame:
  *   1. every coordinate is first put in the box in fp64 and rounded back to float:
  *        pw = (float)(x - floor(x * (1.0/L)) * L)          (identity for 0 <= x < L)
  *   2. every displacement the path forms (site - site, hydrogen - site) is the minimum
