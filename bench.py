@@ -37,6 +37,19 @@ SEED = 1234
 METRIC = "frames/s (H-bond pair search + energy, 100k-atom water box)"
 
 
+def synth_box_length(n_waters):
+    """Cubic box edge of the synthetic generator (include/wn_synth.h): (N / 33.4 nm^-3)^(1/3),
+    Newton iteration in the same order as wn_synth_make_box."""
+    m = 1
+    while m * m * m < n_waters:
+        m += 1
+    v = n_waters / 33.4
+    x = m * 0.32
+    for _ in range(60):
+        x = x - (x * x * x - v) / (3.0 * x * x)
+    return x
+
+
 def algorithmic_bytes_per_frame(natoms, edges_per_frame):
     """read the frame once as delivered, write compact edges + stats."""
     return 12.0 * natoms + 20.0 * edges_per_frame + 32.0
@@ -267,6 +280,24 @@ def run_own(args):
         ctx.stats_reduce(st)
         assert np.all(st["num_sites"] == n_waters)
 
+    # ---- periodic leg (north-star extension): same frames, rectangular PBC with the box of
+    # the generator; fewer steps, reported beside the headline (the reference arm is open boundary)
+    periodic = None
+    if not args.no_pbc:
+        Lbox = synth_box_length(n_waters)
+        boxes = np.tile(np.array([Lbox, Lbox, Lbox], np.float32), (F, 1))
+        kp = max(1, min(K, 5))
+        ctx.hbond_batch_dev(frames_dev, F, natoms, boxes=boxes)           # warm-up (buffers, row capacity)
+        ctx.hbond_batch_dev(frames_dev + F * frame_bytes, F, natoms, boxes=boxes)
+        barrier()
+        pe = pv = 0
+        ctx.timer_start()
+        for s in range(kp):
+            o2 = ctx.hbond_batch_dev(frames_dev + ((W + s) % (W + K)) * F * frame_bytes, F, natoms, boxes=boxes)
+            pe += o2["n_edges"]; pv += o2["n_pair_evals"]
+        pms = ctx.timer_stop()
+        periodic = {"steps": kp, "box_nm": float(Lbox), "ms": pms, "edges": pe, "evals": pv}
+
     def allmax(x):
         if dist is None:
             return x
@@ -289,6 +320,14 @@ def run_own(args):
     evals_all = allsum(float(evals_total))
     edges_all = allsum(float(edges_total))
     edges_per_frame = edges_all / frames_all
+
+    if periodic is not None:
+        pmax = allmax(periodic["ms"])
+        periodic = {"value": periodic["steps"] * F * world / (pmax * 1e-3), "unit": "frames/s",
+                    "steps": periodic["steps"], "box_nm": periodic["box_nm"],
+                    "pair_evals_per_frame": allsum(float(periodic["evals"])) / (periodic["steps"] * F * world),
+                    "edges_per_frame": allsum(float(periodic["edges"])) / (periodic["steps"] * F * world),
+                    "note": "rectangular PBC, minimum image as defined in include/wn_b200.h; no reference counterpart"}
 
     # ---- end-to-end leg: pinned host frames -> wn_hbond_batch -> pinned host results
     ring = min(4, W + K)
@@ -380,6 +419,7 @@ def run_own(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "periodic": periodic,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -398,6 +438,7 @@ def main():
     ap.add_argument("--waters", type=int, default=N_WATERS)
     ap.add_argument("--frames-per-step", type=int, default=250)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pbc", action="store_true", help="skip the periodic-boundary leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -12,7 +12,8 @@ namespace {
 }
 }  // namespace
 
-CudaFindPairs::CudaFindPairs(int device) : ctx_(nullptr), first_limit_(-1), ties_{0, 0, 0, 0}
+CudaFindPairs::CudaFindPairs(int device)
+    : ctx_(nullptr), first_limit_(-1), ties_{0, 0, 0, 0}, box_{0.f, 0.f, 0.f}, periodic_(false)
 {
     const int rc = wn_create(device, &ctx_);
     if (rc != WN_OK) raise("CudaFindPairs: wn_create", rc, nullptr);
@@ -28,7 +29,8 @@ std::vector<std::pair<int, int>> CudaFindPairs::find(std::vector<Point>& points)
     const int32_t* pairs = nullptr;
     uint64_t m = 0;
     const int32_t fl = first_limit_ < 0 ? n : first_limit_;
-    const int rc = wn_find_pairs(ctx_, xyz, n, fl, &pairs, &m, &ties_);
+    const int rc = periodic_ ? wn_find_pairs_pbc(ctx_, xyz, n, fl, box_, &pairs, &m, &ties_)
+                             : wn_find_pairs(ctx_, xyz, n, fl, &pairs, &m, &ties_);
     if (rc != WN_OK) raise("CudaFindPairs::find: wn_find_pairs", rc, ctx_);
     // std::pair<int,int> is two packed ints: one bulk copy instead of m push_backs
     static_assert(sizeof(std::pair<int, int>) == 2 * sizeof(int32_t), "pair<int,int> layout");

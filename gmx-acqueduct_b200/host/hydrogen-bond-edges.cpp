@@ -70,8 +70,14 @@ void HydrogenBondEdges::setWaterSites(int n_waters, int first_limit)
 
 HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, int n_frames, int natoms)
 {
+    return calculate(frames, nullptr, n_frames, natoms);
+}
+
+HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, const float* boxes, int n_frames, int natoms)
+{
     wn_batch_result r;
-    const int rc = wn_hbond_batch(ctx_, frames, n_frames, natoms, &r);
+    const int rc = boxes ? wn_hbond_batch_pbc(ctx_, frames, boxes, n_frames, natoms, &r)
+                         : wn_hbond_batch(ctx_, frames, n_frames, natoms, &r);
     if (rc != WN_OK) raise("HydrogenBondEdges::calculate: wn_hbond_batch", rc, ctx_);
     HydrogenBondBatch b;
     b.edges = r.edges; b.offsets = r.frame_offsets; b.stats = r.stats;
@@ -108,15 +114,29 @@ void FrameBatcher::push(int frnr, const float* xyz)
     if ((int)frnr_.size() >= batch_frames_) flush();
 }
 
+void FrameBatcher::push(int frnr, const float* xyz, const float box[3][3])
+{
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            if (a != b && box[a][b] != 0.0f)
+                throw std::invalid_argument("FrameBatcher::push: triclinic boxes are not supported");
+    if (!frnr_.empty() && boxes_.size() != 3 * frnr_.size())
+        throw std::invalid_argument("FrameBatcher::push: periodic and open frames mixed in one batch");
+    boxes_.push_back(box[0][0]); boxes_.push_back(box[1][1]); boxes_.push_back(box[2][2]);
+    push(frnr, xyz);
+}
+
 void FrameBatcher::finish() { flush(); }
 
 void FrameBatcher::flush()
 {
     if (frnr_.empty()) return;
-    const HydrogenBondBatch b = engine_.calculate(buf_.data(), (int)frnr_.size(), natoms_);
+    const HydrogenBondBatch b = engine_.calculate(buf_.data(), boxes_.empty() ? nullptr : boxes_.data(),
+                                                  (int)frnr_.size(), natoms_);
     for (int f = 0; f < b.n_frames; ++f)
         sink_(frnr_[f], b.edges + b.offsets[f], (size_t)(b.offsets[f + 1] - b.offsets[f]), b.stats[f]);
     frames_done_ += (uint64_t)b.n_frames;
     buf_.clear();
+    boxes_.clear();
     frnr_.clear();
 }

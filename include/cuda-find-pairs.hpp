@@ -32,6 +32,11 @@ public:
 
     // Asymmetric search (BASELINE config 5): only rows i < first_limit; <0 = all rows.
     void setFirstLimit(int first_limit) { first_limit_ = first_limit; }
+    // Periodic search (extension; the reference has none): rectangular box (Lx,Ly,Lz),
+    // minimum-image displacements as defined in wn_b200.h.  clearBox() restores the
+    // reference behaviour (open boundary).
+    void setBox(float lx, float ly, float lz) { box_[0] = lx; box_[1] = ly; box_[2] = lz; periodic_ = true; }
+    void clearBox() { periodic_ = false; }
     // Exact-comparison ties seen by the last find() (10*d2 == 42.25).
     const wn_tie_report& lastTies() const { return ties_; }
     wn_ctx* context() { return ctx_; }
@@ -40,6 +45,8 @@ private:
     wn_ctx* ctx_;
     int first_limit_;
     wn_tie_report ties_;
+    float box_[3];
+    bool periodic_;
 };
 
 #endif

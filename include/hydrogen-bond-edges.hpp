@@ -59,6 +59,9 @@ public:
     // frames: float32 [n_frames][natoms][3] on the host (rvec layout).  The result
     // points into library-owned pinned memory, valid until the next calculate().
     HydrogenBondBatch calculate(const float* frames, int n_frames, int natoms);
+    // Periodic variant (extension, defined in wn_b200.h): boxes = [n_frames][3] box lengths,
+    // the diagonal of each frame's t_trxframe::box.
+    HydrogenBondBatch calculate(const float* frames, const float* boxes, int n_frames, int natoms);
 
     // Convenience: one frame's result as the reference's std::vector<HydrogenBond>
     // (pair order, direction FORWARD), given the SiteInfo_ptr table of the caller.
@@ -85,6 +88,8 @@ public:
 
     FrameBatcher(HydrogenBondEdges& engine, int natoms, int batch_frames, Sink sink);
     void push(int frnr, const float* xyz /* natoms*3 */);
+    // periodic: box = GROMACS matrix fr.box; throws std::invalid_argument for a triclinic box
+    void push(int frnr, const float* xyz, const float box[3][3]);
     void finish();
     uint64_t framesDone() const { return frames_done_; }
 
@@ -94,6 +99,7 @@ private:
     int natoms_, batch_frames_;
     Sink sink_;
     std::vector<float> buf_;
+    std::vector<float> boxes_;
     std::vector<int> frnr_;
     uint64_t frames_done_;
 };

@@ -84,6 +84,32 @@ int main()
         HydrogenBondBatch again = hb.calculate(frames.data(), 1, natoms);
         std::vector<HydrogenBond> hbs = HydrogenBondEdges::toHydrogenBonds(again, 0, infos);
         CHECK(hbs.size() == ref_off[1] && hbs[0].direction == FORWARD);
+        // periodic extension through the same classes: box through the batcher == calculate()
+        {
+            const float box[3][3] = {{2.1f, 0.f, 0.f}, {0.f, 2.1f, 0.f}, {0.f, 0.f, 2.1f}};
+            std::vector<float> boxes;
+            for (int f = 0; f < n_frames; ++f) { boxes.push_back(2.1f); boxes.push_back(2.1f); boxes.push_back(2.1f); }
+            HydrogenBondBatch per = hb.calculate(frames.data(), boxes.data(), n_frames, natoms);
+            CHECK(per.n_edges > all.n_edges);                       // pairs through the faces
+            std::vector<wn_edge> pref(per.edges, per.edges + per.n_edges);
+            std::vector<wn_edge> pgot;
+            FrameBatcher pb(hb, natoms, 4, [&](int, const wn_edge* e, size_t n, const wn_frame_stats&) {
+                pgot.insert(pgot.end(), e, e + n);
+            });
+            for (int f = 0; f < n_frames; ++f) pb.push(f, &frames[(size_t)f * natoms * 3], box);
+            pb.finish();
+            CHECK(pgot.size() == pref.size());
+            for (size_t k = 0; k < pgot.size(); ++k) CHECK(pgot[k].i == pref[k].i && pgot[k].j == pref[k].j && pgot[k].cosine == pref[k].cosine);
+            const float tric[3][3] = {{2.1f, 0.f, 0.f}, {0.5f, 2.1f, 0.f}, {0.f, 0.f, 2.1f}};
+            bool thr = false;
+            try { pb.push(0, frames.data(), tric); } catch (const std::invalid_argument&) { thr = true; }
+            CHECK(thr);
+            CudaFindPairs* cf = static_cast<CudaFindPairs*>(mp_.get());
+            cf->setBox(3.0f, 3.0f, 3.0f);
+            std::vector<std::pair<int, int>> pp = mp_->find(pts);
+            cf->clearBox();
+            CHECK(pp.size() >= pairs.size());
+        }
         // error behaviour: no exception escapes the C ABI; the C++ layer throws
         bool threw = false;
         try { hb.calculate(frames.data(), 1, 10); } catch (const std::runtime_error&) { threw = true; }
