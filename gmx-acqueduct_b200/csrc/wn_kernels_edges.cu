@@ -241,7 +241,7 @@ wn_k_edges(const WnEdgeParams p)
      * A row that wraps in y or z keeps its cells and shifts the origin by -+Ly / -+Lz. */
     int rs = 0, rl = 0;
     float sox = orx, soy = ory, soz = orz;          /* origin to subtract from this run's sites */
-    if (lane < MAXRUN) {
+    if (lane < (PBC ? MAXRUN : 5)) {
         const int row = lane % 5, part = lane / 5;
         int y = (row == 0) ? cy : (row == 1 ? cy + 1 : cy + row - 3);
         int z = (row < 2) ? cz : cz + 1;
@@ -282,7 +282,7 @@ wn_k_edges(const WnEdgeParams p)
     const int total = __shfl_sync(FULL, inc, MAXRUN - 1);
     if (rl > 0) {
         ws.run_start[slot] = rs; ws.run_pref[slot] = inc - rl;
-        ws.run_org[slot] = make_float4(sox, soy, soz, 0.f);
+        if (PBC) ws.run_org[slot] = make_float4(sox, soy, soz, 0.f);
     }
 
     Counters ct = {0u, 0u, 0u, 0u};
