@@ -157,6 +157,37 @@ def cpu_reference_run(frames_host, threads):
     return dt, kind, sum(r[0] for r in results), results
 
 
+def delaunay_proxy_run(frames_host, n_frames=2):
+    """DelaunayFindPairs stand-in (the reference's CGAL finder cannot be built here: CGAL is
+    absent): scipy.spatial.Delaunay (Qhull) edge set + oracle make_edges, one thread.  It
+    reproduces python/edges.dat of the reference exactly but is NOT the
+    reference's code path; reported for context only."""
+    try:
+        from scipy.spatial import Delaunay
+    except Exception:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import wn_oracle_py as oracle
+    n = frames_host.shape[1] // 3
+    sa, ha, ty = oracle.water_site_table(n)
+    t0 = time.perf_counter()
+    edges = 0
+    for f in range(min(n_frames, frames_host.shape[0])):
+        site_xyz, h_xyz, h_off = oracle.gather_sites(frames_host[f], sa, ha, 2)
+        tri = Delaunay(site_xyz)
+        s = tri.simplices
+        pr = np.concatenate([s[:, [0, 1]], s[:, [0, 2]], s[:, [0, 3]], s[:, [1, 2]], s[:, [1, 3]], s[:, [2, 3]]])
+        pr.sort(axis=1)
+        pr = np.unique(pr, axis=0).astype(np.int32)
+        e, _ = oracle.make_edges(pr, site_xyz, h_xyz, h_off, ty)
+        edges += len(e)
+    dt = time.perf_counter() - t0
+    nf = min(n_frames, frames_host.shape[0])
+    return {"value": nf / dt, "unit": "frames/s", "cores": 1, "kind": "proxy (scipy/Qhull Delaunay + oracle make_edges)",
+            "sample": "%d frame(s), %.1f s; %.1f edges/site -- a different (sparser) edge list than the brute path"
+                      % (nf, dt, edges / nf / n)}
+
+
 def usable_threads():
     cores = os.cpu_count() or 1
     try:
@@ -391,9 +422,12 @@ def run_own(args):
         sample = np.empty((nfr, natoms, 3), np.float32)
         ctx.d2h(sample, frames_dev)
         dt, kind, _, _ = cpu_reference_run(sample, threads)
+        dt1, _, _, _ = cpu_reference_run(sample[:1], 1)
         cpu = {"value": nfr / dt, "unit": "frames/s", "cores": min(threads, nfr), "kind": kind,
                "sample": "%d frame(s) of the same 100k-atom workload, one per host thread "
-                         "(brute-find-pairs O(N^2) + make_edges), %.1f s wall" % (nfr, dt)}
+                         "(brute-find-pairs O(N^2) + make_edges), %.1f s wall" % (nfr, dt),
+               "single_thread_frames_per_s": 1.0 / dt1,
+               "delaunay_find_pairs": delaunay_proxy_run(sample)}
 
     ctx.pinned_free(host_ptr)
     ctx.dev_free(frames_dev)

@@ -29,13 +29,14 @@ SYMBOLS = [
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
-    "wn_get_timings", "wn_timer_start", "wn_timer_stop", "wn_nccl_unique_id", "wn_nccl_init", "wn_stats_reduce",
+    "wn_get_timings", "wn_selftest_div", "wn_timer_start", "wn_timer_stop", "wn_nccl_unique_id", "wn_nccl_init", "wn_stats_reduce",
 ]
 
 
 class TieReport(C.Structure):
     _fields_ = [("pair_cutoff_equal", C.c_uint64), ("length_equal_cut", C.c_uint64),
-                ("cosine_argmax_equal", C.c_uint64), ("pos_zero", C.c_uint64)]
+                ("cosine_argmax_equal", C.c_uint64), ("pos_zero", C.c_uint64),
+                ("pair_cutoff_near", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -100,6 +101,7 @@ def load():
     L.wn_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
     L.wn_synth_frames_dev.argtypes = [vp, i32, u64, i32, i64, i32, vp]
     L.wn_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.wn_selftest_div.argtypes = [vp, u64, u64, C.POINTER(u64)]
     L.wn_timer_start.argtypes = [vp]
     L.wn_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.wn_nccl_unique_id.argtypes = [vp]
@@ -249,6 +251,11 @@ class Context:
         t = Timings()
         self._ck(self.L.wn_get_timings(self.h, C.byref(t)))
         return t.as_dict()
+
+    def selftest_div(self, n_samples, seed=1):
+        bad = C.c_uint64()
+        self._ck(self.L.wn_selftest_div(self.h, int(n_samples), int(seed), C.byref(bad)))
+        return int(bad.value)
 
     def timer_start(self):
         self._ck(self.L.wn_timer_start(self.h))

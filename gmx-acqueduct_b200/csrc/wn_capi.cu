@@ -447,7 +447,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     WN_CK(cudaStreamSynchronize(ctx->st));
     if (ctx->h_frame_off[n_frames] != edge_base)
         return fail(ctx, WN_ERR_CUDA, "internal: edge totals disagree between scan and fused kernel");
-    wn_tie_report ties = {0, 0, 0, 0};
+    wn_tie_report ties = {0, 0, 0, 0, 0};
     unsigned long long evals = 0;
     for (int f = 0; f < n_frames; ++f) {
         evals += ctx->h_counters[f].evals;
@@ -509,7 +509,7 @@ int wn_create(int device, wn_ctx** out)
     for (auto& ev : ctx->ev_stage) WN_CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->ev) WN_CKC(cudaEventCreate(&ev));
     WN_CKC(cudaMallocHost((void**)&ctx->h_scalars, 64 * sizeof(unsigned long long)));
-    WN_CKC(cudaMalloc((void**)&ctx->d_pair_ties, sizeof(unsigned long long)));
+    WN_CKC(cudaMalloc((void**)&ctx->d_pair_ties, 2 * sizeof(unsigned long long)));
 #undef WN_CKC
     *out = ctx;
     return WN_OK;
@@ -720,7 +720,7 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
     WN_CK(cudaSetDevice(ctx->device));
     ctx->err.clear();
     *pairs = nullptr; *m = 0;
-    if (ties) *ties = wn_tie_report{0, 0, 0, 0};
+    if (ties) *ties = wn_tie_report{0, 0, 0, 0, 0};
     if (n < 2 || first_limit <= 0) {
         int rc;
         if ((rc = host_ensure(ctx, &ctx->h_pairs, &ctx->h_pairs_cap, (size_t)2))) return rc;
@@ -737,15 +737,15 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
         ctx->prow_cap = (size_t)n + 1;
     }
     WN_CK(cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    WN_CK(cudaMemsetAsync(ctx->d_pair_ties, 0, sizeof(unsigned long long), st));
+    WN_CK(cudaMemsetAsync(ctx->d_pair_ties, 0, 2 * sizeof(unsigned long long), st));
     wn_launch_pairs_count(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_cnt, ctx->d_pair_ties, st);
     wn_launch_pairs_scan(ctx->d_prow_cnt, n, ctx->d_prow_off, st);
     WN_CK(cudaGetLastError());
     WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_prow_off + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    WN_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_pair_ties, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_pair_ties, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     WN_CK(cudaStreamSynchronize(st));
     const unsigned long long total = ctx->h_scalars[0];
-    if (ties) ties->pair_cutoff_equal = ctx->h_scalars[1];
+    if (ties) { ties->pair_cutoff_equal = ctx->h_scalars[1]; ties->pair_cutoff_near = ctx->h_scalars[2]; }
     if ((rc = dev_ensure(ctx, &ctx->d_pairs, &ctx->d_pairs_cap, (size_t)total * 2 + 2))) return rc;
     if ((rc = host_ensure(ctx, &ctx->h_pairs, &ctx->h_pairs_cap, (size_t)total * 2 + 2))) return rc;
     if (total) {
@@ -814,6 +814,23 @@ int wn_synth_frames_dev(wn_ctx* ctx, int32_t n_waters, uint64_t seed, int32_t mo
     wn_launch_synth(n_waters, seed, model, frame0, n_frames, frames_dev, ctx->st);
     WN_CK(cudaGetLastError());
     WN_CK(cudaStreamSynchronize(ctx->st));
+    return WN_OK;
+}
+
+int wn_selftest_div(wn_ctx* ctx, uint64_t n_samples, uint64_t seed, uint64_t* mismatches)
+{
+    if (!ctx || !mismatches) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    WN_CK(cudaMemsetAsync(ctx->d_pair_ties, 0, sizeof(unsigned long long), ctx->st));
+    const int iters = 1024;
+    const unsigned long long per_block = 256ull * iters;
+    int blocks = (int)std::min<unsigned long long>((n_samples + per_block - 1) / per_block, 1u << 20);
+    if (blocks < 1) blocks = 1;
+    wn_launch_selftest_div(seed, blocks, iters, ctx->d_pair_ties, ctx->st);
+    WN_CK(cudaGetLastError());
+    WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_pair_ties, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    *mismatches = ctx->h_scalars[0];
     return WN_OK;
 }
 

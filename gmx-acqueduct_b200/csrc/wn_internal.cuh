@@ -118,6 +118,8 @@ void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long
                      const WnFrameCounters* counters, int n_frames, int n_sites,
                      wn_frame_stats* stats, cudaStream_t st);
 size_t wn_edges_smem_bytes(int hs);
+void wn_launch_selftest_div(unsigned long long seed, int blocks, int iters, unsigned long long* mismatches,
+                            cudaStream_t st);
 
 /* brute pair path (wn_kernels_pairs.cu) */
 struct WnPairBox { int pbc; double L[3], invL[3]; float Lf[3], invLf[3]; };

@@ -78,6 +78,31 @@ __device__ __forceinline__ double wn_minimg(double d, double L, double invL)
     return __dsub_rn(d, __dmul_rn(rint(__dmul_rn(d, invL)), L));
 }
 
+/* OO /= distance (src/waternetwork.cpp:196): three IEEE divisions by the same divisor.
+ * The divisor is a float widened to double (<= 24 significant bits).  With y = RN(1/b),
+ * q0 = RN(a*y), r = a - q0*b (exact in one FMA), the value q0 + r*y differs from a/b by
+ * <= 2^-105 relative, while a/b (a with <= 53, b with <= 24 significant bits) is never
+ * closer than 2^-78 relative to a rounding midpoint and never on one -- so RN(q0 + r*y)
+ * IS the correctly rounded quotient, at 3 instructions per component after one shared
+ * reciprocal (vs ~15 each for the generic IEEE division).  Outside a safe exponent range
+ * (or for non-finite input) the generic division is used.  wn_selftest_div compares the
+ * two bit for bit on the device. */
+__device__ __forceinline__ void
+wn_div3_by_float(double ox, double oy, double oz, double dd, double& ux, double& uy, double& uz)
+{
+    const double big = 1.152921504606846976e18;        /* 2^60 */
+    const bool safe = (dd >= 1.0 / big) && (dd <= big) && (fabs(ox) <= big) && (fabs(oy) <= big) && (fabs(oz) <= big);
+    if (safe) {
+        const double y = __drcp_rn(dd);
+        double q;
+        q = __dmul_rn(ox, y); ux = __fma_rn(__fma_rn(-q, dd, ox), y, q);
+        q = __dmul_rn(oy, y); uy = __fma_rn(__fma_rn(-q, dd, oy), y, q);
+        q = __dmul_rn(oz, y); uz = __fma_rn(__fma_rn(-q, dd, oz), y, q);
+    } else {
+        ux = __ddiv_rn(ox, dd); uy = __ddiv_rn(oy, dd); uz = __ddiv_rn(oz, dd);
+    }
+}
+
 struct PairOut {
     bool counted, edge, t_len, t_cos, t_pos0;
     float len_f, cosmax;
@@ -115,7 +140,8 @@ wn_pair_geometry(const float4 a4, const float4 b4, const double* __restrict__ dh
     if (!r.counted) return r;
     r.t_len = (r.len_f == WN_LEN_CUT_F);
     /* OO /= distance                                                   (:196) */
-    const double ux = __ddiv_rn(ox, dd), uy = __ddiv_rn(oy, dd), uz = __ddiv_rn(oz, dd);
+    double ux, uy, uz;
+    wn_div3_by_float(ox, oy, oz, dd, ux, uy, uz);
     if (SIMPLE) {
         /* every site: list [site atom itself (NaN, never wins), H] -> one cosine each;
          * arg-max from 0 with strict '>' (:240-249) is max(c_first, c_second) when > 0 */
@@ -455,7 +481,70 @@ wn_k_edges_small(const WnEdgeParams p)
     if (tie_pos0) atomicAdd(&fc->tie_pos0, (unsigned long long)tie_pos0);
 }
 
+/* ---- device self-test of wn_div3_by_float against the IEEE division ---- */
+__device__ __forceinline__ uint64_t wn_mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+wn_k_selftest_div(unsigned long long seed, int iters, unsigned long long* __restrict__ mismatches)
+{
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bad = 0;
+    for (int it = 0; it < iters; ++it) {
+        const uint64_t r0 = wn_mix64(seed ^ (tid * 0x9E3779B97F4A7C15ull + (uint64_t)it));
+        const uint64_t r1 = wn_mix64(r0), r2 = wn_mix64(r1), r3 = wn_mix64(r2);
+        const int mode = (int)(r3 >> 61);
+        double a[3];
+        float b;
+        if (mode < 5) {
+            /* the kernel's own distribution: differences of box coordinates, lengths < 0.7 nm */
+            for (int c = 0; c < 3; ++c) {
+                const float p = 12.0f * (float)((r0 >> (20 * c)) & 0xfffff) * (1.0f / 1048576.0f) + __uint_as_float(0x33000000u | (uint32_t)((r1 >> (8 * c)) & 0xff));
+                const float q = p + 0.7f * ((float)((r1 >> (20 * c + 2)) & 0xfffff) * (2.0f / 1048576.0f) - 1.0f);
+                a[c] = (double)p - (double)q;
+            }
+            b = 0.7f * (float)(r2 & 0xffffff) * (1.0f / 16777216.0f) + 1.0e-4f;
+        } else if (mode < 7) {
+            /* arbitrary doubles in the safe range over a float divisor with any mantissa */
+            for (int c = 0; c < 3; ++c) {
+                const uint64_t bits = wn_mix64(r0 + c);
+                const int ex = (int)(bits >> 53) % 100 - 50;
+                a[c] = ldexp(1.0 + (double)(bits & 0xfffffffffffffull) * (1.0 / 4503599627370496.0), ex) * ((bits >> 52) & 1 ? -1.0 : 1.0);
+            }
+            b = __uint_as_float((uint32_t)(0x3f800000u + ((int)((r2 >> 40) % 80) - 40) * 0x00800000) | (uint32_t)(r2 & 0x7fffff));
+        } else {
+            /* edge patterns: all-ones / sparse mantissas, exact quotients, zeros, out-of-range fallbacks */
+            const uint32_t m = (r2 & 1) ? 0x7fffffu : ((r2 & 2) ? 0x000001u : 0x400000u);
+            b = __uint_as_float(0x3e000000u | (m >> (r2 >> 8 & 7)));
+            a[0] = (double)b * (double)(int)(r0 & 0xffff); a[1] = 0.0; a[2] = ldexp((double)(r1 & 0xfffff), (int)(r1 >> 56) - 128);
+            if ((r3 & 0xff) == 0) b = 0.0f;
+            if ((r3 & 0xff) == 1) a[1] = __longlong_as_double(0x7ff8000000000000ll);
+            if ((r3 & 0xff) == 2) b = __uint_as_float(0x00000005u);
+        }
+        const double dd = (double)b;
+        double ux, uy, uz;
+        wn_div3_by_float(a[0], a[1], a[2], dd, ux, uy, uz);
+        const double rx = __ddiv_rn(a[0], dd), ry = __ddiv_rn(a[1], dd), rz = __ddiv_rn(a[2], dd);
+        const bool ok = (__double_as_longlong(ux) == __double_as_longlong(rx) || (ux != ux && rx != rx)) &&
+                        (__double_as_longlong(uy) == __double_as_longlong(ry) || (uy != uy && ry != ry)) &&
+                        (__double_as_longlong(uz) == __double_as_longlong(rz) || (uz != uz && rz != rz));
+        bad += ok ? 0 : 1;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace
+
+void wn_launch_selftest_div(unsigned long long seed, int blocks, int iters, unsigned long long* mismatches,
+                            cudaStream_t st)
+{
+    wn_k_selftest_div<<<blocks, 256, 0, st>>>(seed, iters, mismatches);
+}
 
 size_t wn_edges_smem_bytes(int hs)
 {

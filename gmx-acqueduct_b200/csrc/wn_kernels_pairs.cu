@@ -43,7 +43,7 @@ wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit, const WnPairB
      * carry an absolute error, covered by a relative + absolute margin below */
     const float amax = fmaxf(fmaxf(fabsf(fxi), fabsf(fyi)), fabsf(fzi));
     uint32_t count = 0;
-    unsigned long long tie = 0;
+    unsigned long long tie = 0, near = 0;
     unsigned long long w = FILL && own ? row_off[i] : 0ull;
 
     for (int j0 = i0 + 1; j0 < n; j0 += TILE) {
@@ -94,11 +94,14 @@ wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit, const WnPairB
             } else if (!FILL && lhs == 42.25) {
                 ++tie;
             }
+            /* near-ties: within 4 ulp(42.25) = 4 * 2^-47 of the cutoff, either side */
+            if (!FILL && fabs(lhs - 42.25) <= 2.8421709430404007e-14) ++near;
         }
     }
     if (!FILL) {
         if (i < n) row_cnt[i] = count;
         if (tie) atomicAdd(ties, tie);
+        if (near) atomicAdd(ties + 1, near);
     }
 }
 

@@ -13,7 +13,7 @@ namespace {
 }  // namespace
 
 CudaFindPairs::CudaFindPairs(int device)
-    : ctx_(nullptr), first_limit_(-1), ties_{0, 0, 0, 0}, box_{0.f, 0.f, 0.f}, periodic_(false)
+    : ctx_(nullptr), first_limit_(-1), ties_{0, 0, 0, 0, 0}, box_{0.f, 0.f, 0.f}, periodic_(false)
 {
     const int rc = wn_create(device, &ctx_);
     if (rc != WN_OK) raise("CudaFindPairs: wn_create", rc, nullptr);

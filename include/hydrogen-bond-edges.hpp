@@ -33,7 +33,7 @@ struct HydrogenBondBatch {
     int n_frames = 0;
     uint64_t n_edges = 0;
     uint64_t n_pair_evals = 0;
-    wn_tie_report ties = {0, 0, 0, 0};
+    wn_tie_report ties = {0, 0, 0, 0, 0};
 };
 
 class HydrogenBondEdges

@@ -80,6 +80,7 @@ typedef struct wn_tie_report {
     uint64_t length_equal_cut;     /* (float)dist == 6.5f in the edge test     */
     uint64_t cosine_argmax_equal;  /* equal positive cosines in the arg-max    */
     uint64_t pos_zero;             /* arg-max on list index 0 (edge dropped)   */
+    uint64_t pair_cutoff_near;     /* |10*d2 - 42.25| <= 4 ulp(42.25) (incl. ==) */
 } wn_tie_report;
 
 /* Result of one batch.  Pointers are library-owned and stay valid until the next
@@ -196,6 +197,13 @@ int wn_get_timings(wn_ctx* ctx, wn_timings* out);
  * synchronises and returns the elapsed device time between them. */
 int wn_timer_start(wn_ctx* ctx);
 int wn_timer_stop(wn_ctx* ctx, float* elapsed_ms);
+
+/* Device self-test: the fused kernel divides the O..O vector by its float-rounded length
+ * with one shared reciprocal and an FMA correction per component (exact for a divisor with
+ * <= 24 significant bits, see wn_kernels_edges.cu).  This compares that routine with the
+ * IEEE division bit for bit on n_samples triples (kernel-like, arbitrary and edge-pattern
+ * operands) and returns the number of differing triples (must be 0). */
+int wn_selftest_div(wn_ctx* ctx, uint64_t n_samples, uint64_t seed, uint64_t* mismatches);
 
 /* ---- multi-GPU: per-frame statistics reduction (NCCL) ---------------------
  * Frames are sharded across ranks with no data-path exchange; the only

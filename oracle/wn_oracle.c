@@ -111,6 +111,7 @@ size_t wno_brute_find_pairs_limited(const double* xyz, int n, int first_limit,
             } else if (ties && lhs == (double)cutoff) {
                 ties->pair_cutoff_equal++;
             }
+            if (ties && fabs(lhs - (double)cutoff) <= 2.8421709430404007e-14) ties->pair_cutoff_near++;
         }
     }
     return count;
@@ -317,6 +318,7 @@ size_t wno_brute_find_pairs_pbc(const double* xyz, int n, int first_limit, const
             } else if (ties && lhs == (double)cutoff) {
                 ties->pair_cutoff_equal++;
             }
+            if (ties && fabs(lhs - (double)cutoff) <= 2.8421709430404007e-14) ties->pair_cutoff_near++;
         }
     return count;
 }

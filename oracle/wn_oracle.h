@@ -52,6 +52,7 @@ typedef struct wno_ties {
     uint64_t length_equal_cut;    /* (float)dist == 6.5f in make_edges         */
     uint64_t cosine_argmax_equal; /* c[k] == cosmax > 0 for a later k          */
     uint64_t pos_zero;            /* arg-max landed on list index 0 (dropped)  */
+    uint64_t pair_cutoff_near;    /* |10*d2 - 42.25| <= 4 ulp(42.25), incl. == */
 } wno_ties;
 
 /* src/waternetwork.cpp:12-28 */

@@ -107,7 +107,14 @@ def test_find_pairs_edge_cases(ctx, oracle):
         xyz = np.zeros((n, 3))
         got, _ = ctx.find_pairs(xyz)
         assert np.array_equal(got, oracle.brute_find_pairs(xyz))
-    # exactly at the cutoff: 10*d2 == 42.25 is NOT a pair (strict <); d = 0.65 exactly representable? use d2 = 4.225
+    # exact and near ties at the cutoff: d2 = 4.225 -> 10*d2 == 42.25 is NOT a pair (strict <)
+    tie_xyz = np.array([[0, 0, 0], [0.5, 1.5, 1.3], [0, 0, 2.0554804791094465], [2.0554804791094470, 0, 0]])
+    to = oracle.Ties()
+    want_t = oracle.brute_find_pairs(tie_xyz, ties=to)
+    got_t, ties_t = ctx.find_pairs(tie_xyz)
+    assert np.array_equal(got_t, want_t)
+    assert ties_t["pair_cutoff_equal"] == to.pair_cutoff_equal and ties_t["pair_cutoff_near"] == to.pair_cutoff_near
+    assert ties_t["pair_cutoff_near"] >= 1
     rng = np.random.default_rng(5)
     xyz = rng.uniform(0, 3.0, size=(700, 3)).astype(np.float32).astype(np.float64)
     got, _ = ctx.find_pairs(xyz)
@@ -392,3 +399,10 @@ def test_find_pairs_periodic(ctx, oracle):
         assert np.array_equal(got, want)
         got, _ = ctx.find_pairs(xyz, first_limit=40, box=L)
         assert np.array_equal(got, oracle.brute_find_pairs_pbc(xyz, L, first_limit=40))
+
+
+def test_shared_reciprocal_division_is_ieee_exact(ctx):
+    """The three `OO /= distance` divisions share one reciprocal (3 instructions each);
+    2^33 random triples (kernel-like, arbitrary, edge patterns) against __ddiv_rn, bitwise."""
+    assert ctx.selftest_div(1 << 33, seed=20261019) == 0
+    assert ctx.selftest_div(1 << 30, seed=7) == 0

@@ -20,7 +20,8 @@ MODEL_TIP3P, MODEL_SPC = 0, 1
 
 class Ties(C.Structure):
     _fields_ = [("pair_cutoff_equal", C.c_uint64), ("length_equal_cut", C.c_uint64),
-                ("cosine_argmax_equal", C.c_uint64), ("pos_zero", C.c_uint64)]
+                ("cosine_argmax_equal", C.c_uint64), ("pos_zero", C.c_uint64),
+                ("pair_cutoff_near", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
