@@ -47,7 +47,7 @@ namespace {
 #endif
 constexpr int WARPS_PER_CTA = 8;
 constexpr int HC   = 32;                 /* home sites per chunk (one hit-mask bit each)       */
-constexpr int HPUSH = 16;                /* hit-mask bits pushed per scan                       */
+constexpr int HPUSH = 16;                /* hit-mask bits pushed per scan (20 measured slower: shared memory costs a CTA/SM) */
 constexpr int QCAP = 32 + 32 * HPUSH;    /* queue: < 32 carried + one push of <= 32*HPUSH codes */
 constexpr int MAXRUN = 10;               /* 5 rows, each possibly split by the periodic wrap in x */
 constexpr unsigned FULL = 0xffffffffu;
