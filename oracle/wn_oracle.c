@@ -157,7 +157,9 @@ size_t wno_make_edges(const int32_t* pairs, size_t m,
 
         if (site_type[a] != site_type[b]) isedge = 1;             /* :199 */
         if (site_type[a] == WNO_WATER && site_type[b] == WNO_WATER) isedge = 1;
-        if (ties && distance == 6.5f) ties->length_equal_cut++;
+        /* a tie at the cut is reported where it is consequential: the pair passes the
+         * type rule and the hydrogen rule, so the comparison below decides its fate */
+        if (ties && distance == 6.5f && isedge && !(nha == 0 && nhb == 0)) ties->length_equal_cut++;
         if ((double)distance > 6.5) isedge = 0;                   /* :204 */
         if (nha == 0 && nhb == 0) isedge = 0;                     /* :205-208 */
 
@@ -350,7 +352,7 @@ static size_t make_edges_pbc(const int32_t* pairs, size_t m, const double* site_
         distance = (float)((double)distance * 10.0);
         if (site_type[a] != site_type[b]) isedge = 1;
         if (site_type[a] == WNO_WATER && site_type[b] == WNO_WATER) isedge = 1;
-        if (ties && distance == 6.5f) ties->length_equal_cut++;
+        if (ties && distance == 6.5f && isedge && !(nha == 0 && nhb == 0)) ties->length_equal_cut++;
         if ((double)distance > 6.5) isedge = 0;
         if (nha == 0 && nhb == 0) isedge = 0;
         if (isedge) {

@@ -49,7 +49,7 @@ typedef struct wno_edge {
 /* Counters of exact comparison ties, reported next to every parity claim. */
 typedef struct wno_ties {
     uint64_t pair_cutoff_equal;   /* 10*d2 == 42.25 in the brute test          */
-    uint64_t length_equal_cut;    /* (float)dist == 6.5f in make_edges         */
+    uint64_t length_equal_cut;    /* (float)dist == 6.5f in make_edges, for pairs that pass the type and hydrogen rules */
     uint64_t cosine_argmax_equal; /* c[k] == cosmax > 0 for a later k          */
     uint64_t pos_zero;            /* arg-max landed on list index 0 (dropped)  */
     uint64_t pair_cutoff_near;    /* |10*d2 - 42.25| <= 4 ulp(42.25), incl. == */

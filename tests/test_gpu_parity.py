@@ -406,3 +406,54 @@ def test_shared_reciprocal_division_is_ieee_exact(ctx):
     2^33 random triples (kernel-like, arbitrary, edge patterns) against __ddiv_rn, bitwise."""
     assert ctx.selftest_div(1 << 33, seed=20261019) == 0
     assert ctx.selftest_div(1 << 30, seed=7) == 0
+
+
+def test_randomised_systems_open_and_periodic(ctx, oracle):
+    """40 seeded random systems: site counts 1..400, densities from dilute gas to 20x liquid,
+    random DONOR/ACCEPTOR/WATER tables with 0-3 hydrogens (some lists starting with the site
+    atom itself), random row limits, open boundary or random anisotropic periodic boxes
+    (from 1 cell per dimension upwards, coordinates not wrapped).  Bit-exact vs the oracle."""
+    rng = np.random.default_rng(20261019)
+    for trial in range(40):
+        n_sites = int(rng.integers(1, 401))
+        nf = int(rng.integers(1, 4))
+        hmax = 3
+        natoms = 4 * n_sites
+        site_atom = (np.arange(n_sites) * 4).astype(np.int32)
+        h_atom = -np.ones((n_sites, hmax), np.int32)
+        nh = rng.integers(0, 4, size=n_sites)
+        for s in range(n_sites):
+            for k in range(nh[s]):
+                h_atom[s, k] = site_atom[s] + 1 + k
+            if rng.random() < 0.25:
+                h_atom[s] = [site_atom[s], site_atom[s] + 1, -1]
+        all_water = rng.random() < 0.3
+        site_type = np.full(n_sites, oracle.WATER, np.uint8) if all_water else rng.integers(0, 3, size=n_sites).astype(np.uint8)
+        if all_water and rng.random() < 0.5:
+            h_atom[:, 0] = site_atom; h_atom[:, 1] = site_atom + 1; h_atom[:, 2] = -1     # the reference water table
+        periodic = rng.random() < 0.6
+        side = float(rng.choice([0.5, 0.9, 1.4, 2.0, 2.7, 4.1, 7.0]))
+        boxes = (np.array([side, side * rng.uniform(0.7, 1.6), side * rng.uniform(0.7, 1.6)]) *
+                 rng.uniform(0.95, 1.05, size=(nf, 3))).astype(np.float32)
+        frames = np.zeros((nf, natoms, 3), np.float32)
+        for f in range(nf):
+            pos = rng.uniform(0, 1, size=(n_sites, 3)) * boxes[f]
+            if periodic:
+                pos += rng.integers(-1, 2, size=(n_sites, 3)) * boxes[f]
+            frames[f, 0::4] = pos
+            for k in range(3):
+                d = rng.normal(size=(n_sites, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+                frames[f, 1 + k::4] = pos + 0.1 * d
+        first_limit = None if rng.random() < 0.6 else int(rng.integers(0, n_sites + 1))
+        ctx.set_sites(site_atom, h_atom, site_type, first_limit=first_limit)
+        if periodic:
+            res = ctx.hbond_batch(frames, boxes=boxes)
+            want = oracle_frames_pbc(oracle, frames, boxes, site_atom, h_atom, site_type, first_limit)
+        else:
+            res = ctx.hbond_batch(frames)
+            want = oracle_frames(oracle, frames, site_atom, h_atom, site_type, first_limit)
+        try:
+            compare_batch(res, *want)
+        except AssertionError as e:
+            raise AssertionError("trial %d (n=%d, periodic=%s, side=%.1f, first_limit=%s): %s"
+                                 % (trial, n_sites, periodic, side, first_limit, e))
