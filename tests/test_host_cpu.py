@@ -146,3 +146,13 @@ def test_edge_file_writer_is_byte_identical_to_reference_iostream_formatting():
         g.build()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "test_writer OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_make_sites_rules():
+    """f3: makeSites typing rules (src/waternetwork.cpp:95-180) restated on plain arrays."""
+    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "test_sites")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "test_sites OK" in r.stdout, r.stdout + r.stderr
