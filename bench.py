@@ -249,6 +249,14 @@ def run_reference(args):
 def run_own(args):
     import wn_pkg
     capi = wn_pkg.load_capi()
+    if not os.path.exists(capi.LIB_PATH):          # fresh checkout: compile (nvcc, in-tree); never a CPU fallback
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            import __graft_entry__ as g
+            g.build()
+        else:
+            while not os.path.exists(capi.LIB_PATH):
+                time.sleep(1.0)
+            time.sleep(2.0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -24,7 +24,11 @@ def oracle():
 @pytest.fixture(scope="session")
 def capi():
     import wn_pkg
-    return wn_pkg.load_capi()
+    mod = wn_pkg.load_capi()
+    if not os.path.exists(mod.LIB_PATH):          # fresh checkout: compile the CUDA library first
+        import __graft_entry__ as g
+        g.build()
+    return mod
 
 
 @pytest.fixture(scope="session")
