@@ -50,6 +50,7 @@ struct wn_ctx {
     unsigned long long* d_frame_total = nullptr;
     WnFrameCounters* d_counters = nullptr;
     uint32_t* d_frame_maxrow = nullptr;
+    uint32_t* d_scan_part = nullptr;     /* chunk sums / maxima of the three-phase scans, bbox keys */
     unsigned long long* d_pass_info = nullptr;
     double* d_block_sums = nullptr;
     uint32_t* d_rowbuf = nullptr;
@@ -203,6 +204,8 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
     if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_total, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_counters, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_maxrow, (size_t)cf))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_scan_part,
+                                (size_t)cf * (2 * (size_t)wn_scan_chunks_for(std::max(cn, cell_cap + 1)) + 8)))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_block_sums, (size_t)cf * ((cn + 255) / 256 + 1)))) return rc;
     if (!ctx->d_pass_info) { if ((rc = dev_realloc_plain(ctx, &ctx->d_pass_info, (size_t)2))) return rc; }
     ctx->cap_frames = cf; ctx->cap_sites = cn; ctx->cap_hs = ch; ctx->cell_cap = cell_cap;
@@ -274,16 +277,16 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         WN_CK(cudaMemcpyAsync(ctx->d_grid, ctx->h_grid.data(), (size_t)nf * sizeof(WnGrid), cudaMemcpyHostToDevice, st));
         WN_CK(cudaStreamSynchronize(st));       /* h_grid is pageable and reused by the next pass */
     } else {
-        wn_launch_bbox(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, st);
+        wn_launch_bbox(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, ctx->d_scan_part, st);
     }
     WN_CK(cudaMemsetAsync(ctx->d_cell_cnt, 0, (size_t)nf * (cell_cap + 1) * sizeof(int), st));
     wn_launch_bin(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt,
                   ctx->d_site_cell, ctx->d_site_rank, st);
-    wn_launch_cellscan(nf, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt, st);
+    wn_launch_cellscan(nf, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt, ctx->d_scan_part, st);
     wn_launch_scatter(d_frames, nf, natoms, ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, N, ctx->hs,
                       cell_cap, ctx->d_cell_cnt, ctx->d_site_cell, ctx->d_site_rank, ctx->d_grid, ctx->d_spos,
                       ctx->d_smeta, ctx->d_sdh, st);
-    ctx->tm.launches += 4;
+    ctx->tm.launches += boxes ? 5 : 7;     /* [bbox x2] bin, cell scan x3, scatter */
     WN_CK(cudaEventRecord(ctx->ev[1], st));
 
     unsigned long long end_off = 0;
@@ -301,10 +304,11 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         else wn_launch_edges(p, nf, st);
         WN_CK(cudaGetLastError());
         if (attempt == 0) WN_CK(cudaEventRecord(ctx->ev[2], st));
-        wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off, ctx->d_frame_total, ctx->d_frame_maxrow, st);
+        wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off, ctx->d_frame_total, ctx->d_frame_maxrow,
+                          ctx->d_scan_part, st);
         wn_launch_frameoff(ctx->d_frame_total, ctx->d_frame_maxrow, nf, *edge_base, ctx->d_frame_off + f0,
                            ctx->d_pass_info, st);
-        ctx->tm.launches += 3;
+        ctx->tm.launches += 5;             /* fused search, row scan x3, frame offsets */
         WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_pass_info, 2 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
         WN_CK(cudaStreamSynchronize(st));
@@ -527,7 +531,7 @@ void wn_destroy(wn_ctx* ctx)
     }
     void* dev[] = {ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, ctx->d_grid, ctx->d_cell_cnt, ctx->d_site_cell,
                    ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_cnt,
-                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_pass_info,
+                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_scan_part, ctx->d_pass_info,
                    ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce};
     for (void* p : dev) if (p) cudaFree(p);

@@ -86,14 +86,15 @@ struct WnEdgeParams {
 
 /* ---- kernel launchers (wn_kernels_*.cu).  All asynchronous on `st`. ---- */
 void wn_launch_bbox(const float* frames, int n_frames, int natoms, const int* site_atom,
-                    int n_sites, int cell_cap, WnGrid* grid, cudaStream_t st);
+                    int n_sites, int cell_cap, WnGrid* grid, uint32_t* scratch /* [F][6] */, cudaStream_t st);
+int wn_scan_chunks_for(int len);    /* chunks per frame of the three-phase scans */
 void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* site_atom,
                    int n_sites, int cell_cap, const WnGrid* grid, int* cell_cnt,
                    int* site_cell, int* site_rank, cudaStream_t st);
 /* periodic grid of one frame, built on the host (uploaded with the pass) */
 void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g);
 void wn_launch_cellscan(int n_frames, int n_sites, int cell_cap, const WnGrid* grid,
-                        int* cell_cnt, cudaStream_t st);
+                        int* cell_cnt, uint32_t* part /* [F][chunks(cell_cap)] */, cudaStream_t st);
 void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,
                        const int* hv_atom, const uint32_t* meta, int n_sites, int hs,
                        int cell_cap, const int* cell_start, const int* site_cell,
@@ -104,7 +105,7 @@ void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st);
 void wn_launch_edges_small(const WnEdgeParams& p, int n_frames, cudaStream_t st);
 void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
                        uint32_t* row_off, unsigned long long* frame_total, uint32_t* frame_maxrow,
-                       cudaStream_t st);
+                       uint32_t* part /* [2][F][chunks(n_sites)] */, cudaStream_t st);
 /* pass_info[0] = base + total edges of the pass, pass_info[1] = longest row */
 void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* frame_maxrow, int n_frames,
                         unsigned long long base, unsigned long long* frame_off,

@@ -18,78 +18,6 @@
 
 namespace {
 
-__device__ __forceinline__ bool wn_finite3(float x, float y, float z)
-{
-    return isfinite(x) && isfinite(y) && isfinite(z);
-}
-
-/* ---- bounding box + grid, one block per frame ---- */
-__global__ void __launch_bounds__(512)
-wn_k_bbox(const float* __restrict__ frames, int natoms, const int* __restrict__ site_atom,
-          int n_sites, int cell_cap, WnGrid* __restrict__ grid)
-{
-    const int f = blockIdx.x;
-    const float* fr = frames + (size_t)f * natoms * 3;
-    float lo[3] = {INFINITY, INFINITY, INFINITY};
-    float hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = threadIdx.x; i < n_sites; i += blockDim.x) {
-        const float* p = fr + 3 * (size_t)__ldg(site_atom + i);
-        const float x = p[0], y = p[1], z = p[2];
-        if (wn_finite3(x, y, z)) {
-            lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x);
-            lo[1] = fminf(lo[1], y); hi[1] = fmaxf(hi[1], y);
-            lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
-        }
-    }
-    __shared__ float s_lo[3][16], s_hi[3][16];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float a = lo[c], b = hi[c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
-            b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-        }
-        if (lane == 0) { s_lo[c][warp] = a; s_hi[c][warp] = b; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int nw = blockDim.x >> 5;
-        double mn[3], mx[3];
-        for (int c = 0; c < 3; ++c) {
-            float a = s_lo[c][0], b = s_hi[c][0];
-            for (int w = 1; w < nw; ++w) { a = fminf(a, s_lo[c][w]); b = fmaxf(b, s_hi[c][w]); }
-            mn[c] = (double)a; mx[c] = (double)b;
-        }
-        WnGrid g;
-        g.pbc = 0;
-        for (int c = 0; c < 3; ++c) { g.L[c] = 0.0; g.invL[c] = 0.0; }
-        if (!(mn[0] <= mx[0])) {          /* no finite site */
-            g.ox = g.oy = g.oz = 0.0; g.nx = g.ny = g.nz = 1; g.ncells = 1;
-            for (int c = 0; c < 3; ++c) { g.inv[c] = 1.0; g.edge[c] = 1.0f; }
-            g.tf = 1.0f;
-        } else {
-            double edge = WN_CELL_EDGE;
-            const double ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
-            double nx, ny, nz;
-            for (;;) {
-                nx = floor(ex / edge) + 1.0;
-                ny = floor(ey / edge) + 1.0;
-                nz = floor(ez / edge) + 1.0;
-                if (nx * ny * nz <= (double)cell_cap) break;
-                edge *= 1.1;              /* coarser cells stay correct (edge >= cutoff) */
-            }
-            g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
-            for (int c = 0; c < 3; ++c) { g.inv[c] = 1.0 / edge; g.edge[c] = (float)edge; }
-            g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
-            g.ncells = g.nx * g.ny * g.nz;
-            g.tf = __double2float_ru(WN_PREFILTER_BOUND(edge));
-        }
-        grid[f] = g;
-    }
-}
-
 /* periodic mode, step 1 of the definition (include/wn_b200.h, "Periodic boundaries"): put the coordinate in the
  * box in fp64 and round back to float; identity for 0 <= x < L */
 __device__ __forceinline__ float wn_wrap(float x, double L, double invL)
@@ -127,44 +55,6 @@ wn_k_bin(const float* __restrict__ frames, int natoms, const int* __restrict__ s
     const int rank = atomicAdd(cell_cnt + (size_t)f * (cell_cap + 1) + cid, 1);
     site_cell[(size_t)f * n_sites + i] = cid;
     site_rank[(size_t)f * n_sites + i] = rank;
-}
-
-/* ---- in-place exclusive scan of the cell counts, one block per frame ---- */
-__global__ void __launch_bounds__(1024)
-wn_k_cellscan(int n_sites, int cell_cap, const WnGrid* __restrict__ grid, int* __restrict__ cell_cnt)
-{
-    const int f = blockIdx.x;
-    int* cnt = cell_cnt + (size_t)f * (cell_cap + 1);
-    const int n = grid[f].ncells;
-    const int per = (n + blockDim.x - 1) / blockDim.x;
-    const int b = min(threadIdx.x * per, n), e = min(b + per, n);
-    int sum = 0;
-    for (int c = b; c < e; ++c) sum += cnt[c];
-    /* block exclusive scan of `sum` */
-    __shared__ int s_w[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int v = (lane < (int)(blockDim.x >> 5)) ? s_w[lane] : 0;
-        int iv = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= o) iv += t;
-        }
-        s_w[lane] = iv - v;
-    }
-    __syncthreads();
-    int run = s_w[warp] + inc - sum;
-    for (int c = b; c < e; ++c) { int v = cnt[c]; cnt[c] = run; run += v; }
-    if (threadIdx.x == 0) cnt[n] = n_sites;
 }
 
 /* ---- write the cell-sorted site records ---- */
@@ -225,12 +115,6 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
 
 }  // namespace
 
-void wn_launch_bbox(const float* frames, int n_frames, int natoms, const int* site_atom,
-                    int n_sites, int cell_cap, WnGrid* grid, cudaStream_t st)
-{
-    wn_k_bbox<<<n_frames, 512, 0, st>>>(frames, natoms, site_atom, n_sites, cell_cap, grid);
-}
-
 void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* site_atom,
                    int n_sites, int cell_cap, const WnGrid* grid, int* cell_cnt,
                    int* site_cell, int* site_rank, cudaStream_t st)
@@ -238,12 +122,6 @@ void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* sit
     dim3 g((n_sites + 255) / 256, n_frames);
     wn_k_bin<<<g, 256, 0, st>>>(frames, natoms, site_atom, n_sites, cell_cap, grid, cell_cnt,
                                 site_cell, site_rank);
-}
-
-void wn_launch_cellscan(int n_frames, int n_sites, int cell_cap, const WnGrid* grid,
-                        int* cell_cnt, cudaStream_t st)
-{
-    wn_k_cellscan<<<n_frames, 1024, 0, st>>>(n_sites, cell_cap, grid, cell_cnt);
 }
 
 void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,

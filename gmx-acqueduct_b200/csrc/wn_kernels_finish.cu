@@ -1,7 +1,7 @@
 /*
  * wn_kernels_finish.cu -- ordered edge list, energies and per-frame statistics.
  *
- * wn_k_rowscan / wn_k_frameoff : per-frame exclusive scan of the row lengths ->
+ * (wn_kernels_scan.cu) row scan + wn_k_frameoff : per-frame exclusive scan of the row lengths ->
  *     final position of every row, i.e. the lexicographic (i,j) order in which
  *     BruteFindPairs::find emits pairs (reference src/brute-find-pairs.cpp:21-27)
  *     and make_edges keeps them (src/waternetwork.cpp:621-633).
@@ -70,52 +70,6 @@ __device__ __forceinline__ double wn_compute_energy(double r, double cosine, con
     energy *= radius_switch;
     energy *= angle_switch;
     return energy;
-}
-
-/* ---- per-frame exclusive scan of row counts, one block per frame ---- */
-__global__ void __launch_bounds__(1024)
-wn_k_rowscan(const uint32_t* __restrict__ row_cnt, int n_sites, uint32_t* __restrict__ row_off,
-             unsigned long long* __restrict__ frame_total, uint32_t* __restrict__ frame_maxrow)
-{
-    const int f = blockIdx.x;
-    const uint32_t* cnt = row_cnt + (size_t)f * n_sites;
-    uint32_t* off = row_off + (size_t)f * n_sites;
-    const int per = (n_sites + blockDim.x - 1) / blockDim.x;
-    const int b = min(threadIdx.x * per, n_sites), e = min(b + per, n_sites);
-    unsigned long long sum = 0;
-    uint32_t mx = 0;
-    for (int i = b; i < e; ++i) { const uint32_t v = cnt[i]; sum += v; mx = max(mx, v); }
-    __shared__ unsigned long long s_w[32];
-    __shared__ uint32_t s_mx[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 31) { s_w[warp] = inc; s_mx[warp] = mx; }
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t m2 = (lane < (int)(blockDim.x >> 5)) ? s_mx[lane] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m2 = max(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-        if (lane == 0) frame_maxrow[f] = m2;
-        const unsigned long long v = (lane < (int)(blockDim.x >> 5)) ? s_w[lane] : 0ull;
-        unsigned long long iv = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= o) iv += t;
-        }
-        s_w[lane] = iv - v;
-        if (lane == 31) frame_total[f] = iv;
-    }
-    __syncthreads();
-    unsigned long long run = s_w[warp] + inc - sum;
-    for (int i = b; i < e; ++i) { const uint32_t v = cnt[i]; off[i] = (uint32_t)run; run += v; }
 }
 
 /* ---- exclusive scan of the frame totals (single block) ---- */
@@ -264,13 +218,6 @@ wn_k_stats(const double* __restrict__ block_sums, int n_blocks,
 }
 
 }  // namespace
-
-void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
-                       uint32_t* row_off, unsigned long long* frame_total, uint32_t* frame_maxrow,
-                       cudaStream_t st)
-{
-    wn_k_rowscan<<<n_frames, 1024, 0, st>>>(row_cnt, n_sites, row_off, frame_total, frame_maxrow);
-}
 
 void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* frame_maxrow, int n_frames,
                         unsigned long long base, unsigned long long* frame_off,

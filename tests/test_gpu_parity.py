@@ -457,3 +457,30 @@ def test_randomised_systems_open_and_periodic(ctx, oracle):
         except AssertionError as e:
             raise AssertionError("trial %d (n=%d, periodic=%s, side=%.1f, first_limit=%s): %s"
                                  % (trial, n_sites, periodic, side, first_limit, e))
+
+
+def test_one_million_atoms_rows_and_properties(ctx, oracle):
+    """configs[3] size (333,333 waters, ~1M atoms): exact parity on the first rows (oracle
+    restricted to rows i < 40), order/uniqueness of the full list, open and periodic."""
+    n, nf = 333333, 2
+    d = ctx.dev_alloc(nf * 3 * n * 12)
+    ctx.synth_frames_dev(n, 7, nf, d)
+    frames = np.empty((nf, 3 * n, 3), np.float32)
+    ctx.d2h(frames, d)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    L = np.float32(oracle.synth_box(n).box)
+    for boxes in (None, np.full((nf, 3), L, np.float32)):
+        out = ctx.hbond_batch_dev(d, nf, 3 * n, boxes=boxes)
+        e, fo, st = ctx.fetch_dev_result(out)
+        for f in range(nf):
+            ef = e[int(fo[f]):int(fo[f + 1])]
+            key = ef["i"].astype(np.int64) * n + ef["j"]
+            assert np.all(np.diff(key) > 0) and np.all(ef["i"] < ef["j"]) and ef["j"].max() < n
+            assert st["num_edges"][f] == len(ef)
+            if boxes is None:
+                want, _, _, _ = oracle.frame_hbonds(frames[f], sa, ha, ty, first_limit=40)
+            else:
+                want, _, _, _ = oracle.frame_hbonds_pbc(frames[f], sa, ha, ty, boxes[f], first_limit=40)
+            check_edges(ef[ef["i"] < 40], want)
+    ctx.dev_free(d)
