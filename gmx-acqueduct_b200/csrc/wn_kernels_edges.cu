@@ -54,7 +54,8 @@ constexpr unsigned FULL = 0xffffffffu;
 
 /* fixed part of the per-warp shared memory (followed by HC*hs unit D-H vectors) */
 struct WarpShared {
-    float4    hloc[HC];      /* cell-local x,y,z ; w = (|a|^2 - T)/2            (search)   */
+    float4    hloc[HC];      /* block-local coordinates for the search, two home rows per 32 bytes:
+                              * {x0,x1,y0,y1} {z0,z1,-w0,-w1},  w = (|a|^2 - T)/2  (operands of FFMA2) */
     float4    hpos[HC];      /* original float x,y,z ; w = site index bits      (geometry) */
     uint32_t  hmeta[HC];
     uint32_t  queue[QCAP];
@@ -64,6 +65,24 @@ struct WarpShared {
 };
 
 struct Counters { unsigned int evals, tie_len, tie_cos, tie_pos0; };
+
+/* Blackwell packed fp32: one FFMA2 = two independent fused multiply-adds (d = a*b + c per half) */
+__device__ __forceinline__ unsigned long long wn_pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long wn_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void wn_unpack2(unsigned long long v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 
 __device__ __forceinline__ float wn_dot_f32(const double* __restrict__ d, double ux, double uy, double uz)
 {
@@ -319,15 +338,17 @@ wn_k_edges(const WnEdgeParams p)
         __syncwarp();
         if (lane < hc4) {
             float4 a = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
-            float4 l = make_float4(0.f, 0.f, 0.f, 3.0e38f);        /* t >= |c|^2/2 never holds */
+            float lx = 0.f, ly = 0.f, lz = 0.f, nw = -3.0e38f;      /* dummy: t >= |c|^2/2 never holds */
             uint32_t m = 0;
             if (lane < hc) {
                 a = __ldg(p.spos + fbase + hb + lane);
                 m = __ldg(p.smeta + fbase + hb + lane);
-                const float lx = a.x - orx, ly = a.y - ory, lz = a.z - orz;
-                l = make_float4(lx, ly, lz, 0.5f * (lx * lx + ly * ly + lz * lz) - half_t);
+                lx = a.x - orx; ly = a.y - ory; lz = a.z - orz;
+                nw = half_t - 0.5f * (lx * lx + ly * ly + lz * lz);
             }
-            ws.hpos[lane] = a; ws.hloc[lane] = l; ws.hmeta[lane] = m;
+            ws.hpos[lane] = a; ws.hmeta[lane] = m;
+            float* hl = reinterpret_cast<float*>(ws.hloc) + (lane >> 1) * 8 + (lane & 1);
+            hl[0] = lx; hl[2] = ly; hl[4] = lz; hl[6] = nw;
         }
         for (int t = lane; t < hc * p.hs * 4; t += 32)
             hdh[t] = __ldg(p.sdh + (fbase + hb) * (size_t)p.hs * 4 + t);
@@ -363,27 +384,32 @@ wn_k_edges(const WnEdgeParams p)
                 if (p.first_limit < p.n_sites && __float_as_int(b4.w) >= p.first_limit) allow &= low_rows;
                 if (!SIMPLE) cm = __ldg(p.smeta + fbase + c);
             }
-            /* lane-private hit mask: bit h = home row h is a candidate partner */
+            /* lane-private hit mask: bit h = home row h is a candidate partner.
+             * d2 <= T  <=>  a.c - (|a|^2 - T)/2 >= |c|^2/2 ; two home rows per FFMA2 */
             uint32_t hits = 0;
+            const unsigned long long cxx = wn_pack2(cx_, cx_), cyy = wn_pack2(cy_, cy_), czz = wn_pack2(cz_, cz_);
 #pragma unroll
             for (int gq = 0; gq < HC / 4; ++gq) {
                 if (gq * 4 < hc4) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int h = gq * 4 + u;
-                        const float4 a = ws.hloc[h];
-                        /* d2 <= T  <=>  a.c - (|a|^2 - T)/2 >= |c|^2/2 */
-                        const float t = fmaf(a.z, cz_, fmaf(a.y, cy_, fmaf(a.x, cx_, -a.w)));
-                        bool pass = t >= cn;
+                    for (int u = 0; u < 2; ++u) {
+                        const int h = gq * 4 + 2 * u;
+                        const ulonglong2 xy = *reinterpret_cast<const ulonglong2*>(&ws.hloc[h]);       /* {x0,x1} {y0,y1} */
+                        const ulonglong2 zw = *reinterpret_cast<const ulonglong2*>(&ws.hloc[h + 1]);   /* {z0,z1} {-w0,-w1} */
+                        const unsigned long long t2 = wn_fma2(zw.x, czz, wn_fma2(xy.y, cyy, wn_fma2(xy.x, cxx, zw.y)));
+                        float t0, t1;
+                        wn_unpack2(t2, t0, t1);
+                        bool pass0 = t0 >= cn, pass1 = t1 >= cn;
                         if (!SIMPLE) {
                             /* type rule (:199-203) and the no-hydrogen rule (:205-208) */
-                            const uint32_t am = ws.hmeta[h];
-                            const uint32_t ta = am & WN_META_TYPE_MASK, tb = cm & WN_META_TYPE_MASK;
-                            const bool typ = (ta != tb) || (ta == WN_WATER && tb == WN_WATER);
-                            const bool anyh = ((am | cm) & WN_META_HASH) != 0;
-                            pass = pass && typ && anyh;
+                            const uint32_t tb = cm & WN_META_TYPE_MASK;
+                            const uint32_t am0 = ws.hmeta[h], am1 = ws.hmeta[h + 1];
+                            const uint32_t ta0 = am0 & WN_META_TYPE_MASK, ta1 = am1 & WN_META_TYPE_MASK;
+                            pass0 = pass0 && ((ta0 != tb) || (ta0 == WN_WATER && tb == WN_WATER)) && (((am0 | cm) & WN_META_HASH) != 0);
+                            pass1 = pass1 && ((ta1 != tb) || (ta1 == WN_WATER && tb == WN_WATER)) && (((am1 | cm) & WN_META_HASH) != 0);
                         }
-                        if (pass) hits |= (1u << h);
+                        if (pass0) hits |= (1u << h);
+                        if (pass1) hits |= (2u << h);
                     }
                 }
             }
