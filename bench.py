@@ -360,6 +360,29 @@ def run_own(args):
     edges_all = allsum(float(edges_total))
     edges_per_frame = edges_all / frames_all
 
+    # ---- standalone CudaFindPairs::find at the reference cutoff (the parity vehicle of the
+    # FindPairs boundary): host points in, host pair list out; B_find = 24 N + 8 pairs
+    find = None
+    if rank == 0 and not args.no_find:
+        one = np.empty((natoms, 3), np.float32)
+        ctx.d2h(one, frames_dev)
+        xyz = np.ascontiguousarray(one[::3], dtype=np.float64)
+        ctx.find_pairs(xyz)                                   # warm-up (allocations)
+        t_0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            pairs, _t = ctx.find_pairs(xyz)
+            tmf = ctx.timings()
+        wall = (time.perf_counter() - t_0) / reps
+        bytes_find = 24.0 * n_waters + 8.0 * len(pairs)
+        find = {"pairs": int(len(pairs)), "kernels_ms": tmf["total_ms"], "d2h_ms": tmf["d2h_ms"],
+                "wall_ms_incl_numpy_copy": wall * 1e3, "algorithmic_bytes": bytes_find,
+                "kernel_GBps": bytes_find / (tmf["total_ms"] * 1e-3) / 1e9,
+                "frac_of_hbm_peak": bytes_find / (tmf["total_ms"] * 1e-3) / 1e9 / float(
+                    json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None,
+                "note": "exact O(N^2) tile sweep (count + fill); output D2H of 8 B/pair dominates a call"}
+
     if periodic is not None:
         pmax = allmax(periodic["ms"])
         periodic = {"value": periodic["steps"] * F * world / (pmax * 1e-3), "unit": "frames/s",
@@ -462,6 +485,7 @@ def run_own(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "periodic": periodic,
+            "find_pairs": find,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -481,6 +505,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=250)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pbc", action="store_true", help="skip the periodic-boundary leg")
+    ap.add_argument("--no-find", action="store_true", help="skip the standalone CudaFindPairs::find leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -45,7 +45,8 @@ class TieReport(C.Structure):
 class BatchResult(C.Structure):
     _fields_ = [("edges", C.c_void_p), ("frame_offsets", C.c_void_p), ("stats", C.c_void_p),
                 ("n_edges", C.c_uint64), ("n_pair_evals", C.c_uint64), ("ties", TieReport),
-                ("n_frames", C.c_int32), ("on_device", C.c_int32)]
+                ("n_frames", C.c_int32), ("on_device", C.c_int32),
+                ("row_offsets", C.c_void_p), ("n_sites", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Timings(C.Structure):
@@ -188,10 +189,12 @@ class Context:
         nf, ne = res.n_frames, int(res.n_edges)
         out = {"n_edges": ne, "n_pair_evals": int(res.n_pair_evals), "ties": res.ties.as_dict(),
                "n_frames": nf}
+        out["n_sites"] = res.n_sites
         if res.on_device:
             out["edges_dev"] = res.edges
             out["frame_offsets_dev"] = res.frame_offsets
             out["stats_dev"] = res.stats
+            out["row_offsets_dev"] = res.row_offsets
             return out
         if ne:
             e = np.frombuffer((C.c_char * (ne * 20)).from_address(res.edges), dtype=EDGE_DTYPE)
@@ -203,6 +206,9 @@ class Context:
         out["edges"] = e.copy() if copy else e
         out["frame_offsets"] = fo.copy() if copy else fo
         out["stats"] = st.copy() if copy else st
+        if copy and nf and res.n_sites and res.row_offsets:
+            ro = np.frombuffer((C.c_uint32 * (nf * res.n_sites)).from_address(res.row_offsets), dtype=np.uint32)
+            out["row_offsets"] = ro.reshape(nf, res.n_sites).copy()
         return out
 
     def hbond_batch(self, frames, copy=True, boxes=None):

@@ -46,7 +46,10 @@ struct wn_ctx {
     uint32_t* d_smeta = nullptr;
     double* d_sdh = nullptr;
     uint32_t* d_row_cnt = nullptr;
-    uint32_t* d_row_off = nullptr;
+    uint32_t* d_row_off = nullptr;          /* call-wide [n_frames][n_sites] (CSR row offsets) */
+    size_t row_off_cap = 0;
+    uint32_t* h_row_off = nullptr;
+    size_t h_row_off_cap = 0;
     unsigned long long* d_frame_total = nullptr;
     WnFrameCounters* d_counters = nullptr;
     uint32_t* d_frame_maxrow = nullptr;
@@ -200,7 +203,6 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
     if ((rc = dev_realloc_plain(ctx, &ctx->d_smeta, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_sdh, fn * ch * 4))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_row_cnt, fn))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_row_off, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_total, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_counters, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_maxrow, (size_t)cf))) return rc;
@@ -214,6 +216,12 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
 
 int ensure_out_frames(wn_ctx* ctx, size_t n_frames, bool host)
 {
+    {
+        const size_t need = n_frames * (size_t)std::max(ctx->n_sites, 0) + 1;
+        int rc0;
+        if ((rc0 = dev_ensure(ctx, &ctx->d_row_off, &ctx->row_off_cap, need))) return rc0;
+        if (host && (rc0 = host_ensure(ctx, &ctx->h_row_off, &ctx->h_row_off_cap, need))) return rc0;
+    }
     if (n_frames + 1 > ctx->out_frames_cap || !ctx->d_frame_off) {
         const size_t cap = n_frames + 1;
         int rc;
@@ -304,7 +312,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         else wn_launch_edges(p, nf, st);
         WN_CK(cudaGetLastError());
         if (attempt == 0) WN_CK(cudaEventRecord(ctx->ev[2], st));
-        wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off, ctx->d_frame_total, ctx->d_frame_maxrow,
+        wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_total, ctx->d_frame_maxrow,
                           ctx->d_scan_part, st);
         wn_launch_frameoff(ctx->d_frame_total, ctx->d_frame_maxrow, nf, *edge_base, ctx->d_frame_off + f0,
                            ctx->d_pass_info, st);
@@ -331,7 +339,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
     if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, (size_t)end_off, true, (size_t)*edge_base))) return rc;
 
     int n_blocks = 0;
-    wn_launch_copy(ctx->d_rowbuf, ctx->row_cap, ctx->d_row_cnt, ctx->d_row_off, ctx->d_frame_off + f0,
+    wn_launch_copy(ctx->d_rowbuf, ctx->row_cap, ctx->d_row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0,
                    nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->d_block_sums, &n_blocks, st);
     wn_launch_stats(ctx->d_block_sums, n_blocks, ctx->d_frame_total, ctx->d_counters, nf, N,
                     ctx->d_stats + f0, st);
@@ -384,6 +392,8 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
         out->stats = host_in ? ctx->h_stats : ctx->d_stats;
         out->n_frames = n_frames;
         out->on_device = host_in ? 0 : 1;
+        out->row_offsets = host_in ? ctx->h_row_off : ctx->d_row_off;
+        out->n_sites = N;
         return WN_OK;
     }
 
@@ -448,6 +458,9 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
                           cudaMemcpyDeviceToHost, ctx->st));
     WN_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters_all, (size_t)n_frames * sizeof(WnFrameCounters),
                           cudaMemcpyDeviceToHost, ctx->st));
+    if (host_in)
+        WN_CK(cudaMemcpyAsync(ctx->h_row_off, ctx->d_row_off, (size_t)n_frames * N * sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, ctx->st));
     WN_CK(cudaStreamSynchronize(ctx->st));
     if (ctx->h_frame_off[n_frames] != edge_base)
         return fail(ctx, WN_ERR_CUDA, "internal: edge totals disagree between scan and fused kernel");
@@ -462,6 +475,8 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     out->edges = host_in ? ctx->h_edges : ctx->d_edges;
     out->frame_offsets = host_in ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
     out->stats = host_in ? ctx->h_stats : ctx->d_stats;
+    out->row_offsets = host_in ? ctx->h_row_off : ctx->d_row_off;
+    out->n_sites = N;
     out->n_edges = edge_base;
     out->n_pair_evals = evals;
     out->ties = ties;
@@ -535,7 +550,7 @@ void wn_destroy(wn_ctx* ctx)
                    ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce};
     for (void* p : dev) if (p) cudaFree(p);
-    void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs};
+    void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs, ctx->h_row_off};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
@@ -734,31 +749,48 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
     cudaStream_t st = ctx->st;
     int rc;
     if ((rc = dev_ensure(ctx, &ctx->d_xyz, &ctx->xyz_cap, (size_t)n * 3))) return rc;
-    if ((size_t)n + 1 > ctx->prow_cap) {
+    const size_t n_cnt = (size_t)n * wn_pairs_segments(n);      /* [row][column segment] */
+    if (n_cnt + 1 > ctx->prow_cap) {
         WN_CK(cudaStreamSynchronize(st));
-        if ((rc = dev_realloc_plain(ctx, &ctx->d_prow_cnt, (size_t)n + 1))) return rc;
-        if ((rc = dev_realloc_plain(ctx, &ctx->d_prow_off, (size_t)n + 1))) return rc;
-        ctx->prow_cap = (size_t)n + 1;
+        if ((rc = dev_realloc_plain(ctx, &ctx->d_prow_cnt, n_cnt + 1))) return rc;
+        if ((rc = dev_realloc_plain(ctx, &ctx->d_prow_off, n_cnt + 1))) return rc;
+        ctx->prow_cap = n_cnt + 1;
     }
+    ctx->tm = wn_timings{};
     WN_CK(cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     WN_CK(cudaMemsetAsync(ctx->d_pair_ties, 0, 2 * sizeof(unsigned long long), st));
+    WN_CK(cudaEventRecord(ctx->ev[0], st));
     wn_launch_pairs_count(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_cnt, ctx->d_pair_ties, st);
     wn_launch_pairs_scan(ctx->d_prow_cnt, n, ctx->d_prow_off, st);
     WN_CK(cudaGetLastError());
-    WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_prow_off + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaEventRecord(ctx->ev[1], st));
+    ctx->tm.launches = 2;
+    WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_prow_off + n_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     WN_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_pair_ties, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     WN_CK(cudaStreamSynchronize(st));
     const unsigned long long total = ctx->h_scalars[0];
     if (ties) { ties->pair_cutoff_equal = ctx->h_scalars[1]; ties->pair_cutoff_near = ctx->h_scalars[2]; }
     if ((rc = dev_ensure(ctx, &ctx->d_pairs, &ctx->d_pairs_cap, (size_t)total * 2 + 2))) return rc;
     if ((rc = host_ensure(ctx, &ctx->h_pairs, &ctx->h_pairs_cap, (size_t)total * 2 + 2))) return rc;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->tm.total_ms = ms;
     if (total) {
+        WN_CK(cudaEventRecord(ctx->ev[2], st));
         wn_launch_pairs_fill(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_off, ctx->d_pairs, st);
         WN_CK(cudaGetLastError());
+        WN_CK(cudaEventRecord(ctx->ev[3], st));
         WN_CK(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs, (size_t)total * 2 * sizeof(int32_t),
                               cudaMemcpyDeviceToHost, st));
+        WN_CK(cudaEventRecord(ctx->ev[4], st));
         WN_CK(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+        ctx->tm.total_ms += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+        ctx->tm.d2h_ms = ms;
+        ctx->tm.launches = 3;
     }
+    ctx->tm.passes = 1;
     *pairs = ctx->h_pairs;
     *m = total;
     return WN_OK;

@@ -128,6 +128,7 @@ void wn_launch_pairs_count(const double* xyz, int n, int first_limit, WnPairBox 
                            unsigned long long* ties, cudaStream_t st);
 void wn_launch_pairs_scan(const uint32_t* row_cnt, int n, unsigned long long* row_off,
                           cudaStream_t st);
+int wn_pairs_segments(int n);       /* column segments per row: counts/offsets are [n][segments] */
 void wn_launch_pairs_fill(const double* xyz, int n, int first_limit, WnPairBox box,
                           const unsigned long long* row_off, int32_t* pairs, cudaStream_t st);
 

@@ -32,12 +32,8 @@ std::vector<std::pair<int, int>> CudaFindPairs::find(std::vector<Point>& points)
     const int rc = periodic_ ? wn_find_pairs_pbc(ctx_, xyz, n, fl, box_, &pairs, &m, &ties_)
                              : wn_find_pairs(ctx_, xyz, n, fl, &pairs, &m, &ties_);
     if (rc != WN_OK) raise("CudaFindPairs::find: wn_find_pairs", rc, ctx_);
-    // std::pair<int,int> is two packed ints: one bulk copy instead of m push_backs
+    // std::pair<int,int> is two packed ints: one bulk range copy instead of m push_backs
     static_assert(sizeof(std::pair<int, int>) == 2 * sizeof(int32_t), "pair<int,int> layout");
-    std::vector<std::pair<int, int>> out(m);
-    for (uint64_t k = 0; k < m; ++k) {
-        out[k].first = pairs[2 * k];
-        out[k].second = pairs[2 * k + 1];
-    }
-    return out;
+    const std::pair<int, int>* first = reinterpret_cast<const std::pair<int, int>*>(pairs);
+    return std::vector<std::pair<int, int>>(first, first + m);      // one pass, no zero-fill
 }

@@ -94,6 +94,13 @@ typedef struct wn_batch_result {
     wn_tie_report         ties;           /* sum over frames                     */
     int32_t               n_frames;
     int32_t               on_device;      /* 1: edges/offsets/stats are device pointers */
+    /* CSR view of the same list (hand-off to graph analytics, e.g. connected components of
+     * the buried-water network): edges of site i in frame f are
+     * edges[frame_offsets[f] + row_offsets[f*n_sites + i] .. + row_offsets[f*n_sites + i + 1])
+     * (the last row of a frame ends at frame_offsets[f+1]); [n_frames][n_sites] uint32. */
+    const uint32_t*       row_offsets;
+    int32_t               n_sites;
+    int32_t               reserved;
 } wn_batch_result;
 
 /* ---- context ------------------------------------------------------------ */
@@ -183,7 +190,8 @@ int wn_synth_frames_dev(wn_ctx* ctx, int32_t n_waters, uint64_t seed, int32_t mo
 
 /* ---- timing of the last wn_hbond_batch* call ----------------------------- */
 typedef struct wn_timings {
-    float total_ms;        /* CUDA events around the whole call's device work   */
+    float total_ms;        /* CUDA events around the whole call's device work (wn_hbond_batch*:
+                            * sum of the stages; wn_find_pairs*: count + scan + fill kernels) */
     float bin_ms;          /* bounding box + cell binning + staging kernels     */
     float edges_ms;        /* fused search + geometry kernel                    */
     float finish_ms;       /* row scan + ordered copy/energy + stats kernels    */

@@ -35,6 +35,12 @@ def oracle_frames(oracle, frames, site_atom, h_atom, site_type, first_limit=None
 def compare_batch(res, o_edges, o_stats, o_evals, o_ties):
     fo = res["frame_offsets"]
     assert fo[0] == 0 and fo[-1] == res["n_edges"]
+    if "row_offsets" in res:                      # CSR view: row i of frame f starts at fo[f] + ro[f][i]
+        ro = res["row_offsets"]
+        for f, want in enumerate(o_edges):
+            n = ro.shape[1]
+            starts = np.searchsorted(want["i"], np.arange(n), side="left")
+            assert np.array_equal(ro[f], starts.astype(np.uint32))
     for f, want in enumerate(o_edges):
         check_edges(res["edges"][int(fo[f]):int(fo[f + 1])], want)
     st = res["stats"]
