@@ -208,7 +208,7 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
     if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_maxrow, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_scan_part,
                                 (size_t)cf * (2 * (size_t)wn_scan_chunks_for(std::max(cn, cell_cap + 1)) + 8)))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_block_sums, (size_t)cf * ((cn + 255) / 256 + 1)))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_block_sums, (size_t)cf * ((cn + 255) / 256 + 1) * 8))) return rc;
     if (!ctx->d_pass_info) { if ((rc = dev_realloc_plain(ctx, &ctx->d_pass_info, (size_t)2))) return rc; }
     ctx->cap_frames = cf; ctx->cap_sites = cn; ctx->cap_hs = ch; ctx->cell_cap = cell_cap;
     return WN_OK;

@@ -122,7 +122,10 @@ wn_k_frameoff(const unsigned long long* __restrict__ frame_total, const uint32_t
  * one contiguous span: lane e of a chunk takes the e-th temp entry of the span
  * (row found by a shuffle binary search over the row prefix), ranks it inside its
  * row by j, evaluates the energy and stores it at span_base + row_prefix + rank. */
-__global__ void __launch_bounds__(COPY_THREADS)
+#ifndef WN_COPY_MINBLOCKS
+#define WN_COPY_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(COPY_THREADS, WN_COPY_MINBLOCKS)
 wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
           const uint32_t* __restrict__ row_cnt, const uint32_t* __restrict__ row_off,
           const unsigned long long* __restrict__ frame_off, int n_sites, WnEnergyParams ep,
@@ -184,17 +187,10 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
         __syncwarp();
         for (uint32_t e = lane; e < total; e += 32) sum += (double)edges[span + e].energy;
     }
-    /* fixed-tree block reduction */
-    __shared__ double s_sum[COPY_THREADS / 32];
+    /* fixed-tree warp reduction; one partial per warp (no block barrier), summed in order by wn_k_stats */
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) sum += __shfl_down_sync(FULL, sum, s);
-    if (lane == 0) s_sum[warp] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < COPY_THREADS / 32; ++w) t += s_sum[w];
-        block_sums[(size_t)f * gridDim.x + blockIdx.x] = t;
-    }
+    if (lane == 0) block_sums[((size_t)f * gridDim.x + blockIdx.x) * (COPY_THREADS / 32) + warp] = sum;
 }
 
 /* ---- per-frame statistics row ---- */
@@ -233,7 +229,7 @@ void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt
                     cudaStream_t st)
 {
     dim3 g((n_sites + COPY_THREADS - 1) / COPY_THREADS, n_frames);
-    *n_blocks_out = (int)g.x;
+    *n_blocks_out = (int)g.x * (COPY_THREADS / 32);      /* partial sums per frame */
     wn_k_copy<<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
                                           edges, edge_cap, 0ull, block_sums);
 }
