@@ -25,7 +25,7 @@ assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
 # every symbol include/wn_b200.h declares
 SYMBOLS = [
     "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_find_pairs_pbc",
-    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_set_sites",
+    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_set_sites",
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
@@ -88,6 +88,7 @@ def load():
     L.wn_find_pairs_pbc.argtypes = [vp, vp, i32, i32, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(TieReport)]
     L.wn_hbond_batch_pbc.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_hbond_batch_pbc_dev.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
+    L.wn_hbond_batch_subset.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(BatchResult)]
     L.wn_set_sites.argtypes = [vp, i32, vp, vp, i32, vp, i32]
     L.wn_set_water_sites.argtypes = [vp, i32, i32]
     L.wn_set_energy_params.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -229,6 +230,21 @@ class Context:
             boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(nf, 3)
             self._ck(self.L.wn_hbond_batch_pbc(self.h, ptr, boxes.ctypes.data, nf, natoms, C.byref(res)))
         return self._wrap(res, copy)
+
+    def hbond_batch_subset(self, frames, subset_offsets, subset_sites, boxes=None):
+        """Per-frame site lists: frame f uses table rows subset_sites[off[f]:off[f+1]]."""
+        frames = np.ascontiguousarray(frames, dtype=np.float32)
+        nf, natoms = frames.shape[0], frames.shape[1]
+        off = np.ascontiguousarray(subset_offsets, dtype=np.int64)
+        sites = np.ascontiguousarray(subset_sites, dtype=np.int32)
+        bptr = None
+        if boxes is not None:
+            boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(nf, 3)
+            bptr = boxes.ctypes.data
+        res = BatchResult()
+        self._ck(self.L.wn_hbond_batch_subset(self.h, frames.ctypes.data, bptr, nf, natoms, off.ctypes.data,
+                                              sites.ctypes.data if len(sites) else None, C.byref(res)))
+        return self._wrap(res, True)
 
     def hbond_batch_dev(self, frames_dev, n_frames, natoms, boxes=None):
         res = BatchResult()

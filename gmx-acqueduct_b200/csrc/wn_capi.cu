@@ -95,6 +95,13 @@ struct wn_ctx {
     unsigned long long* d_pair_ties = nullptr;
 
     std::vector<WnGrid> h_grid;     /* periodic grids of the current pass (host-built) */
+    const int64_t* sub_off_host = nullptr;   /* per-frame site subsets of the current call (host) */
+    const int32_t* sub_sites_host = nullptr;
+    int* d_sub_off = nullptr;
+    size_t sub_off_cap = 0;
+    int* d_sub_sites = nullptr;
+    size_t sub_sites_cap = 0;
+    std::vector<int> h_sub_off;
 
     /* timing */
     cudaEvent_t ev[8] = {};
@@ -267,6 +274,20 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
     }
     if ((rc = ensure_pass_buffers(ctx, nf))) return rc;
     const int cell_cap = ctx->cell_cap;
+    WnSubset sub = {nullptr, nullptr};
+    if (ctx->sub_off_host) {
+        /* the pass's slice of the per-frame site lists, offsets rebased to the slice */
+        const int64_t base = ctx->sub_off_host[f0];
+        const size_t cnt = (size_t)(ctx->sub_off_host[f0 + nf] - base);
+        ctx->h_sub_off.resize((size_t)nf + 1);
+        for (int k = 0; k <= nf; ++k) ctx->h_sub_off[k] = (int)(ctx->sub_off_host[f0 + k] - base);
+        if ((rc = dev_ensure(ctx, &ctx->d_sub_off, &ctx->sub_off_cap, (size_t)nf + 1))) return rc;
+        if ((rc = dev_ensure(ctx, &ctx->d_sub_sites, &ctx->sub_sites_cap, cnt + 1))) return rc;
+        WN_CK(cudaMemcpyAsync(ctx->d_sub_off, ctx->h_sub_off.data(), ((size_t)nf + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (cnt) WN_CK(cudaMemcpyAsync(ctx->d_sub_sites, ctx->sub_sites_host + base, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
+        WN_CK(cudaStreamSynchronize(st));       /* pageable sources */
+        sub.off = ctx->d_sub_off; sub.sites = ctx->d_sub_sites;
+    }
 
     WN_CK(cudaEventRecord(ctx->ev[0], st));
     bool small_box = false;      /* periodic box with < 3 cells in some dimension: all-pairs kernel */
@@ -285,13 +306,13 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         WN_CK(cudaMemcpyAsync(ctx->d_grid, ctx->h_grid.data(), (size_t)nf * sizeof(WnGrid), cudaMemcpyHostToDevice, st));
         WN_CK(cudaStreamSynchronize(st));       /* h_grid is pageable and reused by the next pass */
     } else {
-        wn_launch_bbox(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, ctx->d_scan_part, st);
+        wn_launch_bbox(d_frames, nf, natoms, ctx->d_site_atom, N, sub, cell_cap, ctx->d_grid, ctx->d_scan_part, st);
     }
     WN_CK(cudaMemsetAsync(ctx->d_cell_cnt, 0, (size_t)nf * (cell_cap + 1) * sizeof(int), st));
-    wn_launch_bin(d_frames, nf, natoms, ctx->d_site_atom, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt,
+    wn_launch_bin(d_frames, nf, natoms, ctx->d_site_atom, N, sub, cell_cap, ctx->d_grid, ctx->d_cell_cnt,
                   ctx->d_site_cell, ctx->d_site_rank, st);
-    wn_launch_cellscan(nf, N, cell_cap, ctx->d_grid, ctx->d_cell_cnt, ctx->d_scan_part, st);
-    wn_launch_scatter(d_frames, nf, natoms, ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, N, ctx->hs,
+    wn_launch_cellscan(nf, N, sub, cell_cap, ctx->d_grid, ctx->d_cell_cnt, ctx->d_scan_part, st);
+    wn_launch_scatter(d_frames, nf, natoms, ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, N, sub, ctx->hs,
                       cell_cap, ctx->d_cell_cnt, ctx->d_site_cell, ctx->d_site_rank, ctx->d_grid, ctx->d_spos,
                       ctx->d_smeta, ctx->d_sdh, st);
     ctx->tm.launches += boxes ? 5 : 7;     /* [bbox x2] bin, cell scan x3, scatter */
@@ -307,7 +328,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         p.cell_start = ctx->d_cell_cnt; p.grid = ctx->d_grid;
         p.rowbuf = ctx->d_rowbuf; p.row_cnt = ctx->d_row_cnt; p.counters = ctx->d_counters;
         p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
-        p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? 1 : 0; p.bx = bx;
+        p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? 1 : 0; p.bx = bx; p.subset = sub;
         if (small_box) wn_launch_edges_small(p, nf, st);
         else wn_launch_edges(p, nf, st);
         WN_CK(cudaGetLastError());
@@ -341,7 +362,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
     int n_blocks = 0;
     wn_launch_copy(ctx->d_rowbuf, ctx->row_cap, ctx->d_row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0,
                    nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->d_block_sums, &n_blocks, st);
-    wn_launch_stats(ctx->d_block_sums, n_blocks, ctx->d_frame_total, ctx->d_counters, nf, N,
+    wn_launch_stats(ctx->d_block_sums, n_blocks, ctx->d_frame_total, ctx->d_counters, nf, N, sub,
                     ctx->d_stats + f0, st);
     WN_CK(cudaMemcpyAsync(ctx->d_counters_all + f0, ctx->d_counters, (size_t)nf * sizeof(WnFrameCounters),
                           cudaMemcpyDeviceToDevice, st));
@@ -546,7 +567,7 @@ void wn_destroy(wn_ctx* ctx)
     }
     void* dev[] = {ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, ctx->d_grid, ctx->d_cell_cnt, ctx->d_site_cell,
                    ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_cnt,
-                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_scan_part, ctx->d_pass_info,
+                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_scan_part, ctx->d_pass_info, ctx->d_sub_off, ctx->d_sub_sites,
                    ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce};
     for (void* p : dev) if (p) cudaFree(p);
@@ -657,6 +678,32 @@ int wn_hbond_batch(wn_ctx* ctx, const float* frames_host, int32_t n_frames, int3
                    wn_batch_result* out)
 {
     return batch_common(ctx, frames_host, nullptr, true, n_frames, natoms, out);
+}
+
+int wn_hbond_batch_subset(wn_ctx* ctx, const float* frames_host, const float* boxes_host, int32_t n_frames,
+                          int32_t natoms, const int64_t* subset_offsets, const int32_t* subset_sites,
+                          wn_batch_result* out)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (n_frames < 0 || (n_frames > 0 && !subset_offsets))
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: subset_offsets is NULL");
+    if (ctx->n_sites < 0) return fail(ctx, WN_ERR_NO_SITES, "wn_hbond_batch_subset: call wn_set_sites first");
+    for (int f = 0; f < n_frames; ++f) {
+        const int64_t a = subset_offsets[f], b = subset_offsets[f + 1];
+        if (a < 0 || b < a || b - a > (int64_t)ctx->n_sites)
+            return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: offsets must ascend, at most n_sites entries per frame");
+    }
+    const int64_t total = n_frames > 0 ? subset_offsets[n_frames] : 0;
+    if (total > 0 && !subset_sites) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: subset_sites is NULL");
+    for (int64_t k = n_frames > 0 ? subset_offsets[0] : 0; k < total; ++k)
+        if (subset_sites[k] < 0 || subset_sites[k] >= ctx->n_sites)
+            return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: site index outside the site table");
+    ctx->sub_off_host = subset_offsets;
+    ctx->sub_sites_host = subset_sites;
+    const int rc = batch_common(ctx, frames_host, boxes_host, true, n_frames, natoms, out);
+    ctx->sub_off_host = nullptr;
+    ctx->sub_sites_host = nullptr;
+    return rc;
 }
 
 int wn_hbond_batch_pbc(wn_ctx* ctx, const float* frames_host, const float* boxes_host, int32_t n_frames,

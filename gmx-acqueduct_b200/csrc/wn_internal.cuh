@@ -33,6 +33,19 @@ struct WnGrid {
 #define WN_CELL_EDGE      (0.65 * (1.0 + 1.0e-5))
 #define WN_PREFILTER_BOUND(e) (0.4225 * (1.0 + 1.0e-5) + 8.0e-6 * (e) * (e) + 2.0e-6 * (e))
 
+/* ---- per-frame site subsets (e.g. the buried waters the alpha-shape filter keeps, which
+ * change every frame: reference src/waternetwork.cpp:529-533,562-576).  Frame f uses the table
+ * rows sites[off[f] .. off[f+1]) in that order; site index i of the frame = position in that
+ * list.  off == nullptr: every frame uses the whole table. ---- */
+struct WnSubset {
+    const int* off;      /* [F+1], device */
+    const int* sites;    /* table rows, device */
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ int wn_frame_sites(const WnSubset& s, int f, int n_table) { return s.off ? s.off[f + 1] - s.off[f] : n_table; }
+__device__ __forceinline__ int wn_table_row(const WnSubset& s, int f, int i) { return s.off ? s.sites[s.off[f] + i] : i; }
+#endif
+
 /* ---- per-frame counters written by the fused kernel ---- */
 struct WnFrameCounters {
     unsigned long long evals;      /* `if (isedge)` bodies                      */
@@ -82,21 +95,22 @@ struct WnEdgeParams {
     int simple;                 /* 1: every site WATER with the list [site atom, H] */
     int pbc;                    /* 1: grids are periodic boxes                       */
     int bx;                     /* home block width in cells (1 or 2)               */
+    WnSubset subset;            /* per-frame site subsets (off == nullptr: whole table) */
 };
 
 /* ---- kernel launchers (wn_kernels_*.cu).  All asynchronous on `st`. ---- */
 void wn_launch_bbox(const float* frames, int n_frames, int natoms, const int* site_atom,
-                    int n_sites, int cell_cap, WnGrid* grid, uint32_t* scratch /* [F][6] */, cudaStream_t st);
+                    int n_sites, WnSubset sub, int cell_cap, WnGrid* grid, uint32_t* scratch /* [F][6] */, cudaStream_t st);
 int wn_scan_chunks_for(int len);    /* chunks per frame of the three-phase scans */
 void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* site_atom,
-                   int n_sites, int cell_cap, const WnGrid* grid, int* cell_cnt,
+                   int n_sites, WnSubset sub, int cell_cap, const WnGrid* grid, int* cell_cnt,
                    int* site_cell, int* site_rank, cudaStream_t st);
 /* periodic grid of one frame, built on the host (uploaded with the pass) */
 void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g);
-void wn_launch_cellscan(int n_frames, int n_sites, int cell_cap, const WnGrid* grid,
+void wn_launch_cellscan(int n_frames, int n_sites, WnSubset sub, int cell_cap, const WnGrid* grid,
                         int* cell_cnt, uint32_t* part /* [F][chunks(cell_cap)] */, cudaStream_t st);
 void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,
-                       const int* hv_atom, const uint32_t* meta, int n_sites, int hs,
+                       const int* hv_atom, const uint32_t* meta, int n_sites, WnSubset sub, int hs,
                        int cell_cap, const int* cell_start, const int* site_cell,
                        const int* site_rank, const WnGrid* grid, float4* spos, uint32_t* smeta, double* sdh,
                        cudaStream_t st);
@@ -116,7 +130,7 @@ void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt
                     unsigned long long edge_cap, double* block_sums, int* n_blocks_out,
                     cudaStream_t st);
 void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,
-                     const WnFrameCounters* counters, int n_frames, int n_sites,
+                     const WnFrameCounters* counters, int n_frames, int n_sites, WnSubset sub,
                      wn_frame_stats* stats, cudaStream_t st);
 size_t wn_edges_smem_bytes(int hs);
 void wn_launch_selftest_div(unsigned long long seed, int blocks, int iters, unsigned long long* mismatches,

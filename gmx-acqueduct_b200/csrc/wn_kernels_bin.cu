@@ -38,14 +38,14 @@ __device__ __forceinline__ int wn_cell_coord(double x, double o, double inv, int
 /* ---- cell id + arrival rank per site ---- */
 __global__ void __launch_bounds__(256)
 wn_k_bin(const float* __restrict__ frames, int natoms, const int* __restrict__ site_atom,
-         int n_sites, int cell_cap, const WnGrid* __restrict__ grid, int* __restrict__ cell_cnt,
+         int n_sites, WnSubset sub, int cell_cap, const WnGrid* __restrict__ grid, int* __restrict__ cell_cnt,
          int* __restrict__ site_cell, int* __restrict__ site_rank)
 {
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_sites) return;
+    if (i >= wn_frame_sites(sub, f, n_sites)) return;
     const WnGrid g = grid[f];
-    const float* p = frames + ((size_t)f * natoms + (size_t)__ldg(site_atom + i)) * 3;
+    const float* p = frames + ((size_t)f * natoms + (size_t)__ldg(site_atom + wn_table_row(sub, f, i))) * 3;
     float x = p[0], y = p[1], z = p[2];
     if (g.pbc) { x = wn_wrap(x, g.L[0], g.invL[0]); y = wn_wrap(y, g.L[1], g.invL[1]); z = wn_wrap(z, g.L[2], g.invL[2]); }
     const int cx = wn_cell_coord((double)x, g.ox, g.inv[0], g.nx);
@@ -60,7 +60,7 @@ wn_k_bin(const float* __restrict__ frames, int natoms, const int* __restrict__ s
 /* ---- write the cell-sorted site records ---- */
 __global__ void __launch_bounds__(256)
 wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict__ site_atom,
-             const int* __restrict__ hv_atom, const uint32_t* __restrict__ meta, int n_sites,
+             const int* __restrict__ hv_atom, const uint32_t* __restrict__ meta, int n_sites, WnSubset sub,
              int hs, int cell_cap, const int* __restrict__ cell_start,
              const int* __restrict__ site_cell, const int* __restrict__ site_rank,
              const WnGrid* __restrict__ grid,
@@ -68,9 +68,10 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
 {
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_sites) return;
+    if (i >= wn_frame_sites(sub, f, n_sites)) return;
+    const int row = wn_table_row(sub, f, i);          /* row of the site table; i = site index of this frame */
     const float* fr = frames + (size_t)f * natoms * 3;
-    const float* p = fr + 3 * (size_t)__ldg(site_atom + i);
+    const float* p = fr + 3 * (size_t)__ldg(site_atom + row);
     float x = p[0], y = p[1], z = p[2];
     const bool pbc = grid[f].pbc != 0;
     double L[3] = {0, 0, 0}, invL[3] = {0, 0, 0};
@@ -82,11 +83,11 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
     const int dst = cell_start[(size_t)f * (cell_cap + 1) + cid] + site_rank[(size_t)f * n_sites + i];
     const size_t o = (size_t)f * n_sites + dst;
     spos[o] = make_float4(x, y, z, __int_as_float(i));
-    smeta[o] = __ldg(meta + i);
+    smeta[o] = __ldg(meta + row);
     /* DH = *hydrogen - sitePoint; DH /= sqrt(DH*DH)   (src/waternetwork.cpp:219-220) */
     const double sx = (double)x, sy = (double)y, sz = (double)z;
     for (int v = 0; v < hs; ++v) {
-        const int at = __ldg(hv_atom + (size_t)i * hs + v);
+        const int at = __ldg(hv_atom + (size_t)row * hs + v);
         double dx = NAN, dy = NAN, dz = NAN;
         if (at >= 0) {
             const float* h = fr + 3 * (size_t)at;
@@ -116,22 +117,22 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
 }  // namespace
 
 void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* site_atom,
-                   int n_sites, int cell_cap, const WnGrid* grid, int* cell_cnt,
+                   int n_sites, WnSubset sub, int cell_cap, const WnGrid* grid, int* cell_cnt,
                    int* site_cell, int* site_rank, cudaStream_t st)
 {
     dim3 g((n_sites + 255) / 256, n_frames);
-    wn_k_bin<<<g, 256, 0, st>>>(frames, natoms, site_atom, n_sites, cell_cap, grid, cell_cnt,
+    wn_k_bin<<<g, 256, 0, st>>>(frames, natoms, site_atom, n_sites, sub, cell_cap, grid, cell_cnt,
                                 site_cell, site_rank);
 }
 
 void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,
-                       const int* hv_atom, const uint32_t* meta, int n_sites, int hs,
+                       const int* hv_atom, const uint32_t* meta, int n_sites, WnSubset sub, int hs,
                        int cell_cap, const int* cell_start, const int* site_cell,
                        const int* site_rank, const WnGrid* grid, float4* spos, uint32_t* smeta, double* sdh,
                        cudaStream_t st)
 {
     dim3 g((n_sites + 255) / 256, n_frames);
-    wn_k_scatter<<<g, 256, 0, st>>>(frames, natoms, site_atom, hv_atom, meta, n_sites, hs,
+    wn_k_scatter<<<g, 256, 0, st>>>(frames, natoms, site_atom, hv_atom, meta, n_sites, sub, hs,
                                     cell_cap, cell_start, site_cell, site_rank, grid, spos, smeta, sdh);
 }
 

@@ -470,20 +470,21 @@ wn_k_edges_small(const WnEdgeParams p)
     const int f = blockIdx.y;
     const WnGrid& g = p.grid[f];
     const size_t fbase = (size_t)f * p.n_sites;
+    const int n_f = wn_frame_sites(p.subset, f, p.n_sites);       /* sites of this frame */
     const int pa = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool have = pa < p.n_sites;
+    const bool have = pa < n_f;
     float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t ma = 0;
     if (have) { a4 = __ldg(p.spos + fbase + pa); ma = __ldg(p.smeta + fbase + pa); }
     const int ia = __float_as_int(a4.w);
     const double* dha = p.sdh + (fbase + (have ? pa : 0)) * (size_t)p.hs * 4;
     unsigned int evals = 0, tie_len = 0, tie_cos = 0, tie_pos0 = 0;
-    for (int q0 = blockIdx.x * blockDim.x; q0 < p.n_sites; q0 += 128) {
+    for (int q0 = blockIdx.x * blockDim.x; q0 < n_f; q0 += 128) {
         __syncthreads();
-        if (q0 + (int)threadIdx.x < p.n_sites) tile[threadIdx.x] = __ldg(p.spos + fbase + q0 + threadIdx.x);
+        if (q0 + (int)threadIdx.x < n_f) tile[threadIdx.x] = __ldg(p.spos + fbase + q0 + threadIdx.x);
         __syncthreads();
         if (!have) continue;
-        const int kend = min(128, p.n_sites - q0);
+        const int kend = min(128, n_f - q0);
         for (int k = max(0, pa + 1 - q0); k < kend; ++k) {
             const float4 b4 = tile[k];
             const int ib = __float_as_int(b4.w);

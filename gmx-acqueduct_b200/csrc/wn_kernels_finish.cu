@@ -197,11 +197,12 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
 __global__ void __launch_bounds__(128)
 wn_k_stats(const double* __restrict__ block_sums, int n_blocks,
            const unsigned long long* __restrict__ frame_total,
-           const WnFrameCounters* __restrict__ counters, int n_frames, int n_sites,
+           const WnFrameCounters* __restrict__ counters, int n_frames, int n_table, WnSubset sub,
            wn_frame_stats* __restrict__ stats)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
+    const int n_sites = wn_frame_sites(sub, f, n_table);
     double s = 0.0;
     for (int b = 0; b < n_blocks; ++b) s += block_sums[(size_t)f * n_blocks + b];
     wn_frame_stats r;
@@ -235,9 +236,9 @@ void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt
 }
 
 void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,
-                     const WnFrameCounters* counters, int n_frames, int n_sites,
+                     const WnFrameCounters* counters, int n_frames, int n_sites, WnSubset sub,
                      wn_frame_stats* stats, cudaStream_t st)
 {
     wn_k_stats<<<(n_frames + 127) / 128, 128, 0, st>>>(block_sums, n_blocks, frame_total, counters,
-                                                       n_frames, n_sites, stats);
+                                                       n_frames, n_sites, sub, stats);
 }

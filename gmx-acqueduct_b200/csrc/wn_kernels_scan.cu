@@ -90,7 +90,7 @@ wn_k_scan_chunks(uint32_t* __restrict__ part_sum, const uint32_t* __restrict__ p
 __global__ void __launch_bounds__(SCAN_THREADS)
 wn_k_scan_final(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t stride,
                 const WnGrid* __restrict__ grid, int fixed_len, int n_chunks,
-                const uint32_t* __restrict__ part_sum, int write_total, uint32_t total_value)
+                const uint32_t* __restrict__ part_sum, int write_total, uint32_t total_value, WnSubset sub)
 {
     const int f = blockIdx.y, c = blockIdx.x;
     const int n = frame_len(grid, fixed_len, f);
@@ -116,7 +116,7 @@ wn_k_scan_final(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, siz
     uint32_t run = part_sum[(size_t)f * n_chunks + c] + woff + inc - s;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) dst[base + k] = run; run += v[k]; }
-    if (write_total && c == 0 && threadIdx.x == 0) dst[n] = total_value;
+    if (write_total && c == 0 && threadIdx.x == 0) dst[n] = (uint32_t)wn_frame_sites(sub, f, (int)total_value);
 }
 
 /* ---- bounding box: ordered-integer atomics ---- */
@@ -133,9 +133,10 @@ __device__ __forceinline__ float key2f(uint32_t k)
 /* scratch[f][0..2] = min keys, [3..5] = ~max keys; identity 0xFFFFFFFF for both (memset 0xFF) */
 __global__ void __launch_bounds__(256)
 wn_k_bbox_partial(const float* __restrict__ frames, int natoms, const int* __restrict__ site_atom,
-                  int n_sites, uint32_t* __restrict__ scratch)
+                  int n_table, WnSubset sub, uint32_t* __restrict__ scratch)
 {
     const int f = blockIdx.y;
+    const int n_sites = wn_frame_sites(sub, f, n_table);
     const float* fr = frames + (size_t)f * natoms * 3;
     float lo[3] = {INFINITY, INFINITY, INFINITY};
     float hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -143,7 +144,7 @@ wn_k_bbox_partial(const float* __restrict__ frames, int natoms, const int* __res
     for (int k = threadIdx.x; k < 4096; k += 256) {
         const int i = base + k;
         if (i >= n_sites) break;
-        const float* p = fr + 3 * (size_t)__ldg(site_atom + i);
+        const float* p = fr + 3 * (size_t)__ldg(site_atom + wn_table_row(sub, f, i));
         const float x = p[0], y = p[1], z = p[2];
         if (isfinite(x) && isfinite(y) && isfinite(z)) {
             lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x);
@@ -215,16 +216,16 @@ wn_k_bbox_finalize(const uint32_t* __restrict__ scratch, int n_frames, int cell_
 int wn_scan_chunks_for(int len) { return (len + SCAN_CHUNK - 1) / SCAN_CHUNK; }
 
 void wn_launch_bbox(const float* frames, int n_frames, int natoms, const int* site_atom,
-                    int n_sites, int cell_cap, WnGrid* grid, uint32_t* scratch, cudaStream_t st)
+                    int n_sites, WnSubset sub, int cell_cap, WnGrid* grid, uint32_t* scratch, cudaStream_t st)
 {
     cudaMemsetAsync(scratch, 0xff, (size_t)n_frames * 6 * sizeof(uint32_t), st);
     dim3 g((n_sites + 4095) / 4096, n_frames);
-    wn_k_bbox_partial<<<g, 256, 0, st>>>(frames, natoms, site_atom, n_sites, scratch);
+    wn_k_bbox_partial<<<g, 256, 0, st>>>(frames, natoms, site_atom, n_sites, sub, scratch);
     wn_k_bbox_finalize<<<(n_frames + 127) / 128, 128, 0, st>>>(scratch, n_frames, cell_cap, grid);
 }
 
 /* cell counts -> cell starts, in place; start[ncells] = n_sites */
-void wn_launch_cellscan(int n_frames, int n_sites, int cell_cap, const WnGrid* grid, int* cell_cnt,
+void wn_launch_cellscan(int n_frames, int n_sites, WnSubset sub, int cell_cap, const WnGrid* grid, int* cell_cnt,
                         uint32_t* part, cudaStream_t st)
 {
     const int nch = wn_scan_chunks_for(cell_cap);
@@ -232,7 +233,7 @@ void wn_launch_cellscan(int n_frames, int n_sites, int cell_cap, const WnGrid* g
     dim3 g(nch, n_frames);
     wn_k_scan_partial<<<g, SCAN_THREADS, 0, st>>>(data, (size_t)cell_cap + 1, grid, 0, nch, part, nullptr);
     wn_k_scan_chunks<<<n_frames, 32, 0, st>>>(part, nullptr, nch, nullptr, nullptr);
-    wn_k_scan_final<<<g, SCAN_THREADS, 0, st>>>(data, data, (size_t)cell_cap + 1, grid, 0, nch, part, 1, (uint32_t)n_sites);
+    wn_k_scan_final<<<g, SCAN_THREADS, 0, st>>>(data, data, (size_t)cell_cap + 1, grid, 0, nch, part, 1, (uint32_t)n_sites, sub);
 }
 
 /* row lengths -> row offsets (+ per-frame total and longest row) */
@@ -245,5 +246,5 @@ void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites, uint3
     dim3 g(nch, n_frames);
     wn_k_scan_partial<<<g, SCAN_THREADS, 0, st>>>(row_cnt, (size_t)n_sites, nullptr, n_sites, nch, part, part_max);
     wn_k_scan_chunks<<<n_frames, 32, 0, st>>>(part, part_max, nch, frame_total, frame_maxrow);
-    wn_k_scan_final<<<g, SCAN_THREADS, 0, st>>>(row_cnt, row_off, (size_t)n_sites, nullptr, n_sites, nch, part, 0, 0u);
+    wn_k_scan_final<<<g, SCAN_THREADS, 0, st>>>(row_cnt, row_off, (size_t)n_sites, nullptr, n_sites, nch, part, 0, 0u, WnSubset{nullptr, nullptr});
 }

@@ -172,6 +172,17 @@ int wn_hbond_batch_pbc(wn_ctx* ctx, const float* frames_host, const float* boxes
                        int32_t n_frames, int32_t natoms, wn_batch_result* out);
 int wn_hbond_batch_pbc_dev(wn_ctx* ctx, const float* frames_dev, const float* boxes_host,
                            int32_t n_frames, int32_t natoms, wn_batch_result* out);
+/* Per-frame site subsets: the buried waters the reference's alpha-shape filter keeps change
+ * every frame (as_->locate, src/waternetwork.cpp:529-533; the node loop :562-576 then builds
+ * sitePoints from that frame's list).  Frame f uses the rows
+ * subset_sites[subset_offsets[f] .. subset_offsets[f+1]) of the site table, in that order; the
+ * edge indices i<j of the frame are positions in that list (= indices into the frame's
+ * sitePoints).  At most n_sites (table size) entries per frame.  boxes_host == NULL: open
+ * boundary (the reference); otherwise [n_frames][3] as in wn_hbond_batch_pbc.
+ * Result: row_offsets has stride n_sites; stats[f].num_sites is the frame's list length. */
+int wn_hbond_batch_subset(wn_ctx* ctx, const float* frames_host, const float* boxes_host,
+                          int32_t n_frames, int32_t natoms, const int64_t* subset_offsets,
+                          const int32_t* subset_sites, wn_batch_result* out);
 /* Frames that one wn_hbond_batch* call processes per kernel pipeline pass
  * (larger inputs are split internally).  0 restores the default heuristic. */
 int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);

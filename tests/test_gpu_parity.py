@@ -490,3 +490,58 @@ def test_one_million_atoms_rows_and_properties(ctx, oracle):
                 want, _, _, _ = oracle.frame_hbonds_pbc(frames[f], sa, ha, ty, boxes[f], first_limit=40)
             check_edges(ef[ef["i"] < 40], want)
     ctx.dev_free(d)
+
+
+def test_per_frame_site_subsets(ctx, oracle):
+    """The alpha-shape filter of the reference keeps a different set of buried waters every
+    frame (src/waternetwork.cpp:529-533,562-576): per-frame site lists in one batch, edge
+    indices = positions in the frame's list.  Protein-like sites first (always present), then
+    that frame's waters; open and periodic; compared with the oracle run on the gathered table."""
+    rng = np.random.default_rng(4)
+    n_w, n_p, nf = 900, 40, 6
+    box = oracle.synth_box(n_w)
+    wat = oracle.synth_frames(box, 0, nf)                       # [nf][3*n_w][3]
+    natoms = 3 * n_w + 4 * n_p
+    frames = np.zeros((nf, natoms, 3), np.float32)
+    frames[:, :3 * n_w] = wat
+    L = np.float32(box.box)
+    for f in range(nf):
+        pos = rng.uniform(0, 1, size=(n_p, 3)) * L
+        frames[f, 3 * n_w + 0::4] = pos
+        for k in range(3):
+            d = rng.normal(size=(n_p, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+            frames[f, 3 * n_w + 1 + k::4] = pos + 0.1 * d
+    # site table: protein sites (rows 0..n_p-1), then every water (rows n_p..)
+    site_atom = np.concatenate([3 * n_w + 4 * np.arange(n_p), 3 * np.arange(n_w)]).astype(np.int32)
+    h_atom = -np.ones((n_p + n_w, 3), np.int32)
+    nh = rng.integers(0, 4, size=n_p)
+    for s in range(n_p):
+        for k in range(nh[s]):
+            h_atom[s, k] = site_atom[s] + 1 + k
+    h_atom[n_p:, 0] = 3 * np.arange(n_w); h_atom[n_p:, 1] = 3 * np.arange(n_w) + 1
+    site_type = np.concatenate([rng.integers(0, 2, size=n_p), np.full(n_w, oracle.WATER)]).astype(np.uint8)
+    ctx.set_sites(site_atom, h_atom, site_type)
+    lists, off = [], [0]
+    for f in range(nf):
+        keep = np.sort(rng.choice(n_w, size=int(rng.integers(0, 400)), replace=False))
+        lst = np.concatenate([np.arange(n_p), n_p + keep]).astype(np.int32)
+        if f == 2:
+            lst = lst[:0]                                           # an empty frame
+        lists.append(lst); off.append(off[-1] + len(lst))
+    sites = np.concatenate(lists)
+    for boxes in (None, np.full((nf, 3), L, np.float32)):
+        res = ctx.hbond_batch_subset(frames, off, sites, boxes=boxes)
+        fo = res["frame_offsets"]
+        for f in range(nf):
+            lst = lists[f]
+            if boxes is None:
+                want, st, _, ev = oracle.frame_hbonds(frames[f], site_atom[lst], h_atom[lst], site_type[lst]) if len(lst) else \
+                    (np.zeros(0, oracle.EDGE_DTYPE), np.zeros(4), 0, 0)
+            else:
+                want, st, _, ev = oracle.frame_hbonds_pbc(frames[f], site_atom[lst], h_atom[lst], site_type[lst], boxes[f]) if len(lst) else \
+                    (np.zeros(0, oracle.EDGE_DTYPE), np.zeros(4), 0, 0)
+            check_edges(res["edges"][int(fo[f]):int(fo[f + 1])], want)
+            assert res["stats"]["num_sites"][f] == len(lst) and res["stats"]["num_edges"][f] == len(want)
+            assert int(res["stats"]["pair_evals"][f]) == ev
+    with pytest.raises(Exception):
+        ctx.hbond_batch_subset(frames, [0, 1, 2, 3, 4, 5, 6], np.array([0, 1, 2, 3, 4, n_p + n_w], np.int32))
