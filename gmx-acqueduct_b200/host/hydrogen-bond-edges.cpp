@@ -85,6 +85,18 @@ HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, const float*
     return b;
 }
 
+HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, const float* boxes, int n_frames, int natoms,
+                                               const int64_t* subset_offsets, const int32_t* subset_sites)
+{
+    wn_batch_result r;
+    const int rc = wn_hbond_batch_subset(ctx_, frames, boxes, n_frames, natoms, subset_offsets, subset_sites, &r);
+    if (rc != WN_OK) raise("HydrogenBondEdges::calculate: wn_hbond_batch_subset", rc, ctx_);
+    HydrogenBondBatch b;
+    b.edges = r.edges; b.offsets = r.frame_offsets; b.stats = r.stats;
+    b.n_frames = r.n_frames; b.n_edges = r.n_edges; b.n_pair_evals = r.n_pair_evals; b.ties = r.ties;
+    return b;
+}
+
 std::vector<HydrogenBond> HydrogenBondEdges::toHydrogenBonds(const HydrogenBondBatch& batch, int frame,
                                                              const std::vector<SiteInfo_ptr>& sites)
 {
@@ -126,17 +138,38 @@ void FrameBatcher::push(int frnr, const float* xyz, const float box[3][3])
     push(frnr, xyz);
 }
 
+void FrameBatcher::push(int frnr, const float* xyz, const float (*box)[3], const std::vector<int32_t>& frameSites)
+{
+    if (!frnr_.empty() && sub_off_.size() != frnr_.size() + 1)
+        throw std::invalid_argument("FrameBatcher::push: frames with and without site lists mixed in one batch");
+    if (sub_off_.empty()) sub_off_.push_back(0);
+    sub_sites_.insert(sub_sites_.end(), frameSites.begin(), frameSites.end());
+    sub_off_.push_back((int64_t)sub_sites_.size());
+    if (box) {
+        boxes_.push_back(box[0][0]); boxes_.push_back(box[1][1]); boxes_.push_back(box[2][2]);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                if (a != b && box[a][b] != 0.0f)
+                    throw std::invalid_argument("FrameBatcher::push: triclinic boxes are not supported");
+    }
+    push(frnr, xyz);
+}
+
 void FrameBatcher::finish() { flush(); }
 
 void FrameBatcher::flush()
 {
     if (frnr_.empty()) return;
-    const HydrogenBondBatch b = engine_.calculate(buf_.data(), boxes_.empty() ? nullptr : boxes_.data(),
-                                                  (int)frnr_.size(), natoms_);
+    const float* bx = boxes_.empty() ? nullptr : boxes_.data();
+    const HydrogenBondBatch b = sub_off_.empty()
+        ? engine_.calculate(buf_.data(), bx, (int)frnr_.size(), natoms_)
+        : engine_.calculate(buf_.data(), bx, (int)frnr_.size(), natoms_, sub_off_.data(), sub_sites_.data());
     for (int f = 0; f < b.n_frames; ++f)
         sink_(frnr_[f], b.edges + b.offsets[f], (size_t)(b.offsets[f + 1] - b.offsets[f]), b.stats[f]);
     frames_done_ += (uint64_t)b.n_frames;
     buf_.clear();
     boxes_.clear();
+    sub_off_.clear();
+    sub_sites_.clear();
     frnr_.clear();
 }

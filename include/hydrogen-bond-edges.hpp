@@ -63,6 +63,11 @@ public:
     // the diagonal of each frame's t_trxframe::box.
     HydrogenBondBatch calculate(const float* frames, const float* boxes, int n_frames, int natoms);
 
+    // Per-frame site lists (what as_->locate() leaves, src/waternetwork.cpp:529-533): frame f uses the
+    // table rows sites[offsets[f] .. offsets[f+1]); edge indices are positions in that list.
+    HydrogenBondBatch calculate(const float* frames, const float* boxes, int n_frames, int natoms,
+                                const int64_t* subset_offsets, const int32_t* subset_sites);
+
     // Convenience: one frame's result as the reference's std::vector<HydrogenBond>
     // (pair order, direction FORWARD), given the SiteInfo_ptr table of the caller.
     static std::vector<HydrogenBond> toHydrogenBonds(const HydrogenBondBatch& batch, int frame,
@@ -90,6 +95,9 @@ public:
     void push(int frnr, const float* xyz /* natoms*3 */);
     // periodic: box = GROMACS matrix fr.box; throws std::invalid_argument for a triclinic box
     void push(int frnr, const float* xyz, const float box[3][3]);
+    // with the frame's own site list (rows of the site table, e.g. protein sites + the buried
+    // waters of this frame); box may be nullptr.  All frames of a run must use the same variant.
+    void push(int frnr, const float* xyz, const float (*box)[3], const std::vector<int32_t>& frameSites);
     void finish();
     uint64_t framesDone() const { return frames_done_; }
 
@@ -100,6 +108,8 @@ private:
     Sink sink_;
     std::vector<float> buf_;
     std::vector<float> boxes_;
+    std::vector<int64_t> sub_off_;
+    std::vector<int32_t> sub_sites_;
     std::vector<int> frnr_;
     uint64_t frames_done_;
 };

@@ -110,6 +110,24 @@ int main()
             cf->clearBox();
             CHECK(pp.size() >= pairs.size());
         }
+        // per-frame site lists through the batcher: a frame restricted to the first 100 waters gives the
+        // edges of the full frame whose endpoints are both < 100 (indices are list positions)
+        {
+            std::vector<int32_t> first100(100);
+            for (int s = 0; s < 100; ++s) first100[s] = s;
+            std::vector<wn_edge> sub;
+            FrameBatcher sb(hb, natoms, 2, [&](int frnr, const wn_edge* e, size_t n, const wn_frame_stats& st) {
+                if (frnr == 0) { sub.assign(e, e + n); if (st.num_sites != 100) throw std::runtime_error("num_sites"); }
+            });
+            for (int f = 0; f < 3; ++f) sb.push(f, &frames[(size_t)f * natoms * 3], nullptr, first100);
+            sb.finish();
+            std::vector<wn_edge> want100;
+            for (uint64_t k = ref_off[0]; k < ref_off[1]; ++k)
+                if (ref_edges[k].i < 100 && ref_edges[k].j < 100) want100.push_back(ref_edges[k]);
+            CHECK(sub.size() == want100.size() && !sub.empty());
+            for (size_t k = 0; k < sub.size(); ++k)
+                CHECK(sub[k].i == want100[k].i && sub[k].j == want100[k].j && sub[k].energy == want100[k].energy);
+        }
         // error behaviour: no exception escapes the C ABI; the C++ layer throws
         bool threw = false;
         try { hb.calculate(frames.data(), 1, 10); } catch (const std::runtime_error&) { threw = true; }
