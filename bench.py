@@ -383,6 +383,20 @@ def run_own(args):
                 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None,
                 "note": "exact O(N^2) tile sweep (count + fill); output D2H of 8 B/pair dominates a call"}
 
+    # ---- edge-file text of a batch, formatted on the GPU (37 bytes per edge row, D2H included)
+    text = None
+    if rank == 0 and not args.no_find:
+        nft = min(F, 50)
+        ctx.hbond_batch_dev(frames_dev, nft, natoms)
+        numbers = np.arange(nft, dtype=np.int32)
+        ctx.format_edges_raw(numbers)                           # warm-up (buffers)
+        t_0 = time.perf_counter()
+        _, nbytes = ctx.format_edges_raw(numbers)
+        dtx = time.perf_counter() - t_0
+        text = {"frames": nft, "bytes": nbytes, "frames_per_s": nft / dtx, "GBps": nbytes / dtx / 1e9,
+                "note": "rows of edges-frames.xvg.dat formatted by wn_k_format_rows, D2H into pinned host memory "
+                        "included; host formatter (EdgeFileWriter): ~0.4 GB/s per core, iostream: ~0.03 GB/s"}
+
     if periodic is not None:
         pmax = allmax(periodic["ms"])
         periodic = {"value": periodic["steps"] * F * world / (pmax * 1e-3), "unit": "frames/s",
@@ -486,6 +500,7 @@ def run_own(args):
             "cpu_baseline": cpu,
             "periodic": periodic,
             "find_pairs": find,
+            "edge_file_text": text,
         }
         print(json.dumps(line))
     if dist is not None:

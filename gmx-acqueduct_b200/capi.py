@@ -25,7 +25,7 @@ assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
 # every symbol include/wn_b200.h declares
 SYMBOLS = [
     "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_find_pairs_pbc",
-    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_set_sites",
+    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_format_edges", "wn_set_sites",
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
@@ -89,6 +89,7 @@ def load():
     L.wn_hbond_batch_pbc.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_hbond_batch_pbc_dev.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_hbond_batch_subset.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(BatchResult)]
+    L.wn_format_edges.argtypes = [vp, vp, vp, i32, C.POINTER(vp), C.POINTER(u64)]
     L.wn_set_sites.argtypes = [vp, i32, vp, vp, i32, vp, i32]
     L.wn_set_water_sites.argtypes = [vp, i32, i32]
     L.wn_set_energy_params.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -268,6 +269,24 @@ class Context:
         if nf:
             self.d2h(st, out["stats_dev"])
         return e, fo, st
+
+    def format_edges(self, frame_numbers, site_ids=None):
+        """Text of the edge file for the last batch result (bytes), formatted on the GPU."""
+        fn = np.ascontiguousarray(frame_numbers, dtype=np.int32)
+        ids = None if site_ids is None else np.ascontiguousarray(site_ids, dtype=np.uint32)
+        t, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.wn_format_edges(self.h, fn.ctypes.data, None if ids is None else ids.ctypes.data,
+                                        0 if ids is None else len(ids), C.byref(t), C.byref(n)))
+        return C.string_at(t.value, int(n.value)) if n.value else b""
+
+    def format_edges_raw(self, frame_numbers, site_ids=None):
+        """As format_edges, without copying: (address of the library-owned pinned text, bytes)."""
+        fn = np.ascontiguousarray(frame_numbers, dtype=np.int32)
+        ids = None if site_ids is None else np.ascontiguousarray(site_ids, dtype=np.uint32)
+        t, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.wn_format_edges(self.h, fn.ctypes.data, None if ids is None else ids.ctypes.data,
+                                        0 if ids is None else len(ids), C.byref(t), C.byref(n)))
+        return t.value, int(n.value)
 
     def timings(self):
         t = Timings()

@@ -82,6 +82,15 @@ struct wn_ctx {
     size_t h_frames_cap = 0;
     unsigned long long* h_scalars = nullptr;   /* pinned scratch for small D2H reads */
 
+    /* text formatting of the last batch */
+    int last_frames = -1;                      /* frames of the last wn_hbond_batch* call, -1: none */
+    unsigned long long last_edges = 0;
+    char* d_text = nullptr;  size_t d_text_cap = 0;
+    char* h_text = nullptr;  size_t h_text_cap = 0;
+    unsigned long long* d_row_base = nullptr;  size_t row_base_cap = 0;
+    unsigned int* d_site_ids = nullptr;  size_t site_ids_cap = 0;
+    int* d_frame_flags = nullptr;  size_t frame_flags_cap = 0;
+
     /* pair path */
     double* d_xyz = nullptr;
     size_t xyz_cap = 0;
@@ -496,6 +505,8 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     out->edges = host_in ? ctx->h_edges : ctx->d_edges;
     out->frame_offsets = host_in ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
     out->stats = host_in ? ctx->h_stats : ctx->d_stats;
+    ctx->last_frames = n_frames;
+    ctx->last_edges = edge_base;
     out->row_offsets = host_in ? ctx->h_row_off : ctx->d_row_off;
     out->n_sites = N;
     out->n_edges = edge_base;
@@ -569,9 +580,11 @@ void wn_destroy(wn_ctx* ctx)
                    ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_cnt,
                    ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_scan_part, ctx->d_pass_info, ctx->d_sub_off, ctx->d_sub_sites,
                    ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
-                   ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce};
+                   ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce,
+                   ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags};
     for (void* p : dev) if (p) cudaFree(p);
-    void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs, ctx->h_row_off};
+    void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs, ctx->h_row_off,
+                    ctx->h_text};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
@@ -897,6 +910,59 @@ int wn_synth_frames_dev(wn_ctx* ctx, int32_t n_waters, uint64_t seed, int32_t mo
     wn_launch_synth(n_waters, seed, model, frame0, n_frames, frames_dev, ctx->st);
     WN_CK(cudaGetLastError());
     WN_CK(cudaStreamSynchronize(ctx->st));
+    return WN_OK;
+}
+
+int wn_format_edges(wn_ctx* ctx, const int32_t* frame_numbers, const uint32_t* site_ids, int32_t n_site_ids,
+                    const char** text, uint64_t* text_bytes)
+{
+    if (!ctx || !text || !text_bytes) return WN_ERR_BAD_ARG;
+    *text = nullptr; *text_bytes = 0;
+    if (ctx->last_frames < 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: no batch result to format");
+    const int F = ctx->last_frames;
+    if (F > 0 && !frame_numbers) return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: frame_numbers is NULL");
+    if (site_ids && n_site_ids < ctx->n_sites)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: site_ids shorter than the site table");
+    WN_CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    /* frame headers and row positions from the per-frame edge counts (already on the host) */
+    std::vector<std::string> hdr((size_t)F);
+    std::vector<unsigned long long> row_base((size_t)F + 1);
+    unsigned long long pos = 0, max_edges = 0;
+    for (int f = 0; f < F; ++f) {
+        hdr[f] = "#--- frame " + std::to_string(frame_numbers[f]) + " ---\n";
+        const unsigned long long cnt = ctx->h_frame_off[f + 1] - ctx->h_frame_off[f];
+        row_base[f] = pos + hdr[f].size();
+        pos = row_base[f] + 37ull * cnt;
+        max_edges = std::max(max_edges, cnt);
+    }
+    row_base[F] = pos;
+    int rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_text, &ctx->d_text_cap, (size_t)pos + 4))) return rc;
+    if ((rc = host_ensure(ctx, &ctx->h_text, &ctx->h_text_cap, (size_t)pos + 4))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_row_base, &ctx->row_base_cap, (size_t)F + 1))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_frame_flags, &ctx->frame_flags_cap, (size_t)F + 1))) return rc;
+    WN_CK(cudaMemcpyAsync(ctx->d_row_base, row_base.data(), ((size_t)F + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    WN_CK(cudaMemsetAsync(ctx->d_frame_flags, 0, ((size_t)F + 1) * sizeof(int), st));
+    const unsigned int* d_ids = nullptr;
+    if (site_ids) {
+        if ((rc = dev_ensure(ctx, &ctx->d_site_ids, &ctx->site_ids_cap, (size_t)std::max(ctx->n_sites, 1)))) return rc;
+        WN_CK(cudaMemcpyAsync(ctx->d_site_ids, site_ids, (size_t)ctx->n_sites * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+        d_ids = ctx->d_site_ids;
+    }
+    WN_CK(cudaStreamSynchronize(st));             /* pageable sources above */
+    wn_launch_format_rows(ctx->d_edges, ctx->d_frame_off, ctx->d_row_base, d_ids, F, max_edges, ctx->d_text,
+                          ctx->d_frame_flags, st);
+    WN_CK(cudaGetLastError());
+    std::vector<int> flags((size_t)F + 1, 0);
+    if (pos) WN_CK(cudaMemcpyAsync(ctx->h_text, ctx->d_text, (size_t)pos, cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaMemcpyAsync(flags.data(), ctx->d_frame_flags, ((size_t)F + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaStreamSynchronize(st));
+    for (int f = 0; f < F; ++f)
+        if (flags[f]) return fail(ctx, WN_ERR_OVERFLOW, "wn_format_edges: a field does not fit the fixed-width row; format this batch on the host");
+    for (int f = 0; f < F; ++f) memcpy(ctx->h_text + (row_base[f] - hdr[f].size()), hdr[f].data(), hdr[f].size());
+    *text = ctx->h_text;
+    *text_bytes = pos;
     return WN_OK;
 }
 

@@ -136,6 +136,11 @@ size_t wn_edges_smem_bytes(int hs);
 void wn_launch_selftest_div(unsigned long long seed, int blocks, int iters, unsigned long long* mismatches,
                             cudaStream_t st);
 
+/* text rows of the edge file (wn_kernels_format.cu) */
+void wn_launch_format_rows(const wn_edge* edges, const unsigned long long* frame_off,
+                           const unsigned long long* row_base, const unsigned int* site_ids, int n_frames,
+                           unsigned long long max_edges_per_frame, char* text, int* frame_flags, cudaStream_t st);
+
 /* brute pair path (wn_kernels_pairs.cu) */
 struct WnPairBox { int pbc; double L[3], invL[3]; float Lf[3], invLf[3]; };
 void wn_launch_pairs_count(const double* xyz, int n, int first_limit, WnPairBox box, uint32_t* row_cnt,

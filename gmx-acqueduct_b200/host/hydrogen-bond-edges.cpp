@@ -97,6 +97,16 @@ HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, const float*
     return b;
 }
 
+bool HydrogenBondEdges::formatLastBatch(const std::vector<int>& frameNumbers, const std::vector<unsigned>& ids,
+                                        const char** text, uint64_t* bytes)
+{
+    const int rc = wn_format_edges(ctx_, frameNumbers.data(), ids.empty() ? nullptr : ids.data(), (int32_t)ids.size(),
+                                   text, bytes);
+    if (rc == WN_ERR_OVERFLOW) return false;
+    if (rc != WN_OK) raise("HydrogenBondEdges::formatLastBatch: wn_format_edges", rc, ctx_);
+    return true;
+}
+
 std::vector<HydrogenBond> HydrogenBondEdges::toHydrogenBonds(const HydrogenBondBatch& batch, int frame,
                                                              const std::vector<SiteInfo_ptr>& sites)
 {

@@ -68,6 +68,13 @@ public:
     HydrogenBondBatch calculate(const float* frames, const float* boxes, int n_frames, int natoms,
                                 const int64_t* subset_offsets, const int32_t* subset_sites);
 
+    // Text of edges-frames.xvg.dat for the LAST calculate() (frame lines + 37-byte rows, the bytes
+    // the reference's iostream code writes, src/waternetwork.cpp:638-652), formatted on the GPU.
+    // ids[s] = SiteInfo::id of table row s (empty: the index).  Returns false when a field does not
+    // fit the fixed-width row (ids over 6 digits, values over 8 characters); use EdgeFileWriter then.
+    bool formatLastBatch(const std::vector<int>& frameNumbers, const std::vector<unsigned>& ids,
+                         const char** text, uint64_t* bytes);
+
     // Convenience: one frame's result as the reference's std::vector<HydrogenBond>
     // (pair order, direction FORWARD), given the SiteInfo_ptr table of the caller.
     static std::vector<HydrogenBond> toHydrogenBonds(const HydrogenBondBatch& batch, int frame,

@@ -187,6 +187,17 @@ int wn_hbond_batch_subset(wn_ctx* ctx, const float* frames_host, const float* bo
  * (larger inputs are split internally).  0 restores the default heuristic. */
 int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);
 
+/* ---- edge file text (src/waternetwork.cpp:638-652), formatted on the GPU ---------------
+ * Formats the edge list of the LAST wn_hbond_batch* call of this context as the rows of
+ * edges-frames.xvg.dat: per frame "#--- frame N ---\n" (N = frame_numbers[f]) and one 37-byte
+ * row per edge, "%6u%6u%8.4f%8.4f%8.4f\n" with id = site_ids[index] (NULL: the index itself;
+ * the reference prints SiteInfo::id).  Byte-identical to the reference's iostream output.
+ * *text: library-owned pinned host memory, valid until the next call on this context.
+ * Returns WN_ERR_OVERFLOW (nothing usable in *text) if some id needs more than 6 digits or a
+ * value more than 8 characters: format that batch with a general host formatter instead. */
+int wn_format_edges(wn_ctx* ctx, const int32_t* frame_numbers, const uint32_t* site_ids,
+                    int32_t n_site_ids, const char** text, uint64_t* text_bytes);
+
 /* ---- device buffers + synthetic frames (bench/test plumbing) ------------- */
 int wn_dev_alloc(wn_ctx* ctx, size_t bytes, void** dev_ptr);
 int wn_dev_free(wn_ctx* ctx, void* dev_ptr);

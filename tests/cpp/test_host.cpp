@@ -12,6 +12,8 @@
 
 #include "cuda-find-pairs.hpp"
 #include "hydrogen-bond-edges.hpp"
+#include "edge-file-writer.hpp"
+#include <sstream>
 
 #define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "CHECK failed: %s (%s:%d)\n", #c, __FILE__, __LINE__); return 1; } } while (0)
 
@@ -109,6 +111,45 @@ int main()
             std::vector<std::pair<int, int>> pp = mp_->find(pts);
             cf->clearBox();
             CHECK(pp.size() >= pairs.size());
+        }
+        // GPU-formatted edge file text == host EdgeFileWriter (which is checked against iostreams).
+        // Random frames may hold near-coincident sites whose energy needs more than 8 characters: then
+        // the GPU formatter must refuse (fixed-width rows) and the host writer is the fallback.
+        {
+            auto host_text = [&](const HydrogenBondBatch& b, const std::vector<unsigned>& ids, int first_frnr) {
+                std::ostringstream os;
+                EdgeFileWriter w(os, ids);
+                for (int f = 0; f < b.n_frames; ++f)
+                    w.writeFrame(first_frnr + f, b.edges + b.offsets[f], (size_t)(b.offsets[f + 1] - b.offsets[f]));
+                return os.str();
+            };
+            std::vector<unsigned> ids(n_waters);
+            for (int s = 0; s < n_waters; ++s) ids[s] = (unsigned)(s + 41);
+            HydrogenBondBatch b3 = hb.calculate(frames.data(), 3, natoms);
+            const std::string ht = host_text(b3, ids, 5);
+            bool fits = true;
+            for (size_t p = 0, q; (q = ht.find('\n', p)) != std::string::npos; p = q + 1)
+                if (ht[p] != '#' && q - p != 36) fits = false;
+            const char* txt = nullptr; uint64_t nbytes = 0;
+            const bool gpu_ok = hb.formatLastBatch({5, 6, 7}, ids, &txt, &nbytes);
+            CHECK(gpu_ok == fits);
+            if (gpu_ok) CHECK(ht == std::string(txt, (size_t)nbytes));
+            // a regular lattice of waters: every value fits, the GPU text must equal the host text
+            std::vector<float> lat((size_t)natoms * 3);
+            for (int w = 0; w < n_waters; ++w) {
+                float* p = &lat[(size_t)w * 9];
+                p[0] = 0.31f * (float)(w % 7); p[1] = 0.29f * (float)((w / 7) % 7); p[2] = 0.33f * (float)(w / 49);
+                p[3] = p[0] + 0.08f; p[4] = p[1] + 0.05f; p[5] = p[2];
+                p[6] = p[0]; p[7] = p[1] - 0.09f; p[8] = p[2] + 0.03f;
+            }
+            HydrogenBondBatch bl = hb.calculate(lat.data(), 1, natoms);
+            CHECK(bl.n_edges > 100);
+            const std::string hl = host_text(bl, ids, 42);
+            CHECK(hb.formatLastBatch({42}, ids, &txt, &nbytes));
+            CHECK(hl == std::string(txt, (size_t)nbytes));
+            std::vector<unsigned> wide(ids);
+            for (unsigned& v : wide) v += 10000000u;
+            CHECK(!hb.formatLastBatch({42}, wide, &txt, &nbytes));
         }
         // per-frame site lists through the batcher: a frame restricted to the first 100 waters gives the
         // edges of the full frame whose endpoints are both < 100 (indices are list positions)

@@ -545,3 +545,36 @@ def test_per_frame_site_subsets(ctx, oracle):
             assert int(res["stats"]["pair_evals"][f]) == ev
     with pytest.raises(Exception):
         ctx.hbond_batch_subset(frames, [0, 1, 2, 3, 4, 5, 6], np.array([0, 1, 2, 3, 4, n_p + n_w], np.int32))
+
+
+def test_gpu_text_formatter_matches_printf(ctx, oracle, capi):
+    """f1 on the GPU: the rows of edges-frames.xvg.dat (src/waternetwork.cpp:638-652) formatted by
+    wn_k_format_rows must equal "%6d%6d%8.4f%8.4f%8.4f\\n" (what std::fixed, precision 4, setw gives;
+    the host EdgeFileWriter is checked against iostreams in tests/cpp/test_writer.cpp)."""
+    n, nf = 700, 5
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 0, nf)
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames)
+    numbers = [0, 10, 20, 1000, 123456]
+    ids = (np.arange(n) + 1 + 37).astype(np.uint32)              # solvent ids offset by proteinSites.size()+1
+    text = ctx.format_edges(numbers, ids)
+    fo = res["frame_offsets"]
+    want = []
+    for f in range(nf):
+        want.append("#--- frame %d ---\n" % numbers[f])
+        for e in res["edges"][int(fo[f]):int(fo[f + 1])]:
+            want.append("%6d%6d%8.4f%8.4f%8.4f\n" % (ids[e["i"]], ids[e["j"]], e["energy"], e["length"], e["cosine"]))
+    assert text == "".join(want).encode()
+    # without an id table the indices themselves are printed
+    t2 = ctx.format_edges(numbers)
+    first = res["edges"][0]
+    assert t2.split(b"\n")[1] == ("%6d%6d%8.4f%8.4f%8.4f" % (first["i"], first["j"], first["energy"], first["length"], first["cosine"])).encode()
+    # an id with 7 digits does not fit the fixed-width row: reported, not silently truncated
+    with pytest.raises(capi.WnError) as ei:
+        ctx.format_edges(numbers, ids + 1000000)
+    assert ei.value.code == 5
+    # empty result
+    ctx.set_water_sites(3)
+    ctx.hbond_batch(np.zeros((2, 9, 3), np.float32) + np.arange(9)[None, :, None] * 5.0)
+    assert ctx.format_edges([4, 5]) == b"#--- frame 4 ---\n#--- frame 5 ---\n"
