@@ -25,7 +25,7 @@ assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
 # every symbol include/wn_b200.h declares
 SYMBOLS = [
     "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_find_pairs_pbc",
-    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_format_edges", "wn_set_sites",
+    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_hbond_batch_box9", "wn_find_pairs_box9", "wn_format_edges", "wn_set_sites",
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
@@ -89,6 +89,8 @@ def load():
     L.wn_hbond_batch_pbc.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_hbond_batch_pbc_dev.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_hbond_batch_subset.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(BatchResult)]
+    L.wn_hbond_batch_box9.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
+    L.wn_find_pairs_box9.argtypes = [vp, vp, i32, i32, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(TieReport)]
     L.wn_format_edges.argtypes = [vp, vp, vp, i32, C.POINTER(vp), C.POINTER(u64)]
     L.wn_set_sites.argtypes = [vp, i32, vp, vp, i32, vp, i32]
     L.wn_set_water_sites.argtypes = [vp, i32, i32]
@@ -153,6 +155,10 @@ class Context:
         p, m, ties = C.c_void_p(), C.c_uint64(), TieReport()
         if box is None:
             self._ck(self.L.wn_find_pairs(self.h, xyz.ctypes.data, n, fl, C.byref(p), C.byref(m), C.byref(ties)))
+        elif np.size(box) == 9:
+            box = np.ascontiguousarray(box, dtype=np.float32).reshape(9)
+            self._ck(self.L.wn_find_pairs_box9(self.h, xyz.ctypes.data, n, fl, box.ctypes.data, C.byref(p),
+                                               C.byref(m), C.byref(ties)))
         else:
             box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
             self._ck(self.L.wn_find_pairs_pbc(self.h, xyz.ctypes.data, n, fl, box.ctypes.data, C.byref(p),
@@ -227,6 +233,9 @@ class Context:
         res = BatchResult()
         if boxes is None:
             self._ck(self.L.wn_hbond_batch(self.h, ptr, nf, natoms, C.byref(res)))
+        elif np.size(boxes) == 9 * nf:
+            boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(nf, 9)
+            self._ck(self.L.wn_hbond_batch_box9(self.h, ptr, boxes.ctypes.data, nf, natoms, C.byref(res)))
         else:
             boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(nf, 3)
             self._ck(self.L.wn_hbond_batch_pbc(self.h, ptr, boxes.ctypes.data, nf, natoms, C.byref(res)))

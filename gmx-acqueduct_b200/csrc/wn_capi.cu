@@ -104,6 +104,7 @@ struct wn_ctx {
     unsigned long long* d_pair_ties = nullptr;
 
     std::vector<WnGrid> h_grid;     /* periodic grids of the current pass (host-built) */
+    int box_stride = 3;                      /* 3: (Lx,Ly,Lz) per frame; 9: triclinic matrices */
     const int64_t* sub_off_host = nullptr;   /* per-frame site subsets of the current call (host) */
     const int32_t* sub_sites_host = nullptr;
     int* d_sub_off = nullptr;
@@ -278,7 +279,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
     if (nf > 1 && (size_t)nf * N * ctx->row_cap * WN_ROW_WORDS * sizeof(uint32_t) > WN_ROWBUF_BUDGET) {
         const int half = nf / 2;
         if ((rc = run_pass(ctx, d_frames, boxes, half, natoms, f0, edge_base))) return rc;
-        return run_pass(ctx, d_frames + (size_t)half * natoms * 3, boxes ? boxes + 3 * (size_t)half : nullptr,
+        return run_pass(ctx, d_frames + (size_t)half * natoms * 3, boxes ? boxes + ctx->box_stride * (size_t)half : nullptr,
                         nf - half, natoms, f0 + half, edge_base);
     }
     if ((rc = ensure_pass_buffers(ctx, nf))) return rc;
@@ -304,10 +305,20 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
     if (boxes) {
         ctx->h_grid.resize((size_t)nf);
         for (int f = 0; f < nf; ++f) {
+            WnGrid& g = ctx->h_grid[f];
+            if (ctx->box_stride == 9) {
+                const float* b = boxes + 9 * (size_t)f;
+                for (int k = 0; k < 9; ++k)
+                    if (!std::isfinite(b[k])) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_box9: box must be finite");
+                if (!(b[0] > 0.f && b[4] > 0.f && b[8] > 0.f) || b[1] != 0.f || b[2] != 0.f || b[5] != 0.f)
+                    return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_box9: box must be lower-triangular with a positive diagonal (GROMACS convention)");
+                wn_host_tric_grid(b, &g);
+                small_box = true;             /* triclinic: all-pairs kernel */
+                continue;
+            }
             const float* b = boxes + 3 * (size_t)f;
             if (!(b[0] > 0.f && b[1] > 0.f && b[2] > 0.f) || !std::isfinite(b[0]) || !std::isfinite(b[1]) || !std::isfinite(b[2]))
                 return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_pbc: box lengths must be positive and finite");
-            WnGrid& g = ctx->h_grid[f];
             wn_host_pbc_grid(b, cell_cap, &g);
             if (g.nx < 3 || g.ny < 3 || g.nz < 3) small_box = true;
             if (g.nx < 4) bx = 1;
@@ -337,7 +348,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         p.cell_start = ctx->d_cell_cnt; p.grid = ctx->d_grid;
         p.rowbuf = ctx->d_rowbuf; p.row_cnt = ctx->d_row_cnt; p.counters = ctx->d_counters;
         p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
-        p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? 1 : 0; p.bx = bx; p.subset = sub;
+        p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? (ctx->box_stride == 9 ? 2 : 1) : 0; p.bx = bx; p.subset = sub;
         if (small_box) wn_launch_edges_small(p, nf, st);
         else wn_launch_edges(p, nf, st);
         WN_CK(cudaGetLastError());
@@ -361,7 +372,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         if (nf > 1 && (size_t)nf * N * nc * WN_ROW_WORDS * sizeof(uint32_t) > WN_ROWBUF_BUDGET) {
             const int half = nf / 2;
             if ((rc = run_pass(ctx, d_frames, boxes, half, natoms, f0, edge_base))) return rc;
-            return run_pass(ctx, d_frames + (size_t)half * natoms * 3, boxes ? boxes + 3 * (size_t)half : nullptr,
+            return run_pass(ctx, d_frames + (size_t)half * natoms * 3, boxes ? boxes + ctx->box_stride * (size_t)half : nullptr,
                             nf - half, natoms, f0 + half, edge_base);
         }
     }
@@ -453,7 +464,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
             if (k + 1 < n_pass && (rc = stage_in(k + 1))) return rc;
             WN_CK(cudaStreamWaitEvent(ctx->st, ctx->ev_stage[k & 1], 0));
             const unsigned long long before = edge_base;
-            if ((rc = run_pass(ctx, ctx->d_stage[k & 1], boxes ? boxes + 3 * (size_t)f0 : nullptr, nf, natoms,
+            if ((rc = run_pass(ctx, ctx->d_stage[k & 1], boxes ? boxes + ctx->box_stride * (size_t)f0 : nullptr, nf, natoms,
                                (size_t)f0, &edge_base))) return rc;
             if ((size_t)edge_base > ctx->h_edges_cap) {
                 /* project the whole call from the density seen so far */
@@ -477,7 +488,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     } else {
         for (int f0 = 0; f0 < n_frames; f0 += fpp) {
             const int nf = std::min(fpp, n_frames - f0);
-            if ((rc = run_pass(ctx, frames + (size_t)f0 * frame_floats, boxes ? boxes + 3 * (size_t)f0 : nullptr, nf,
+            if ((rc = run_pass(ctx, frames + (size_t)f0 * frame_floats, boxes ? boxes + ctx->box_stride * (size_t)f0 : nullptr, nf,
                                natoms, (size_t)f0, &edge_base))) return rc;
         }
     }
@@ -719,6 +730,30 @@ int wn_hbond_batch_subset(wn_ctx* ctx, const float* frames_host, const float* bo
     return rc;
 }
 
+int wn_hbond_batch_box9(wn_ctx* ctx, const float* frames_host, const float* boxes9_host, int32_t n_frames,
+                        int32_t natoms, wn_batch_result* out)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (!boxes9_host && n_frames > 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_box9: boxes is NULL");
+    bool rectangular = true;
+    for (int f = 0; f < n_frames && rectangular; ++f) {
+        const float* b = boxes9_host + 9 * (size_t)f;
+        if (b[1] != 0.f || b[2] != 0.f || b[3] != 0.f || b[5] != 0.f || b[6] != 0.f || b[7] != 0.f) rectangular = false;
+    }
+    if (rectangular) {              /* every frame rectangular: the rectangular definition and the cell sweep */
+        std::vector<float> b3((size_t)n_frames * 3);
+        for (int f = 0; f < n_frames; ++f) {
+            b3[3 * (size_t)f] = boxes9_host[9 * (size_t)f]; b3[3 * (size_t)f + 1] = boxes9_host[9 * (size_t)f + 4];
+            b3[3 * (size_t)f + 2] = boxes9_host[9 * (size_t)f + 8];
+        }
+        return batch_common(ctx, frames_host, b3.data(), true, n_frames, natoms, out);
+    }
+    ctx->box_stride = 9;
+    const int rc = batch_common(ctx, frames_host, boxes9_host, true, n_frames, natoms, out);
+    ctx->box_stride = 3;
+    return rc;
+}
+
 int wn_hbond_batch_pbc(wn_ctx* ctx, const float* frames_host, const float* boxes_host, int32_t n_frames,
                        int32_t natoms, wn_batch_result* out)
 {
@@ -782,13 +817,37 @@ int wn_find_pairs_pbc(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_l
     return find_pairs_impl(ctx, xyz, n, first_limit, box, pairs, m, ties);
 }
 
+int wn_find_pairs_box9(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit, const float box9[9],
+                       const int32_t** pairs, uint64_t* m, wn_tie_report* ties)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (!box9 || !(box9[0] > 0.f && box9[4] > 0.f && box9[8] > 0.f) || box9[1] != 0.f || box9[2] != 0.f || box9[5] != 0.f)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_find_pairs_box9: box must be lower-triangular with a positive diagonal");
+    if (box9[3] == 0.f && box9[6] == 0.f && box9[7] == 0.f) {
+        const float b3[3] = {box9[0], box9[4], box9[8]};
+        return find_pairs_impl(ctx, xyz, n, first_limit, b3, pairs, m, ties);
+    }
+    ctx->box_stride = 9;
+    const int rc = find_pairs_impl(ctx, xyz, n, first_limit, box9, pairs, m, ties);
+    ctx->box_stride = 3;
+    return rc;
+}
+
 static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit, const float* box3,
                            const int32_t** pairs, uint64_t* m, wn_tie_report* ties)
 {
     if (!ctx) return WN_ERR_BAD_ARG;
     WnPairBox pb;
     memset(&pb, 0, sizeof pb);
-    if (box3) {
+    if (box3 && ctx->box_stride == 9) {
+        const float* b = box3;
+        pb.pbc = 2;
+        const float d[3] = {b[0], b[4], b[8]}, t[3] = {b[3], b[6], b[7]};
+        for (int c = 0; c < 3; ++c) {
+            pb.L[c] = (double)d[c]; pb.invL[c] = 1.0 / pb.L[c]; pb.Lf[c] = d[c]; pb.invLf[c] = 1.0f / d[c];
+            pb.tri[c] = (double)t[c]; pb.trif[c] = t[c];
+        }
+    } else if (box3) {
         pb.pbc = 1;
         for (int c = 0; c < 3; ++c) {
             pb.L[c] = (double)box3[c]; pb.invL[c] = 1.0 / pb.L[c];

@@ -23,7 +23,8 @@ struct WnGrid {
     int ncells;          /* nx*ny*nz <= cell capacity                               */
     float edge[3];       /* cell edge (fp32 copy, for block-local frames)           */
     float tf;            /* fp32 prefilter bound on d^2 (superset of the exact test) */
-    int pbc;             /* 1: rectangular periodic box                             */
+    int pbc;             /* 0: open, 1: rectangular periodic box, 2: triclinic (L = ax,by,cz) */
+    double tri[3];       /* triclinic off-diagonals bx, cx, cy (box rows a=(ax,0,0) b=(bx,by,0) c=(cx,cy,cz)) */
 };
 
 /* Minimum cell edge, and the fp32 prefilter bound for a given (largest) cell edge: exact
@@ -42,6 +43,17 @@ struct WnSubset {
     const int* sites;    /* table rows, device */
 };
 #if defined(__CUDACC__)
+/* triclinic minimum image (include/wn_b200.h, "Periodic boundaries"): reduce along c, then b,
+ * then a; every operation rounded.  L = (ax, by, cz), tri = (bx, cx, cy). */
+__device__ __forceinline__ void wn_minimg_tric(double& x, double& y, double& z, const double* L, const double* tri)
+{
+    const double k = rint(__ddiv_rn(z, L[2]));
+    x = __dsub_rn(x, __dmul_rn(k, tri[1])); y = __dsub_rn(y, __dmul_rn(k, tri[2])); z = __dsub_rn(z, __dmul_rn(k, L[2]));
+    const double j = rint(__ddiv_rn(y, L[1]));
+    x = __dsub_rn(x, __dmul_rn(j, tri[0])); y = __dsub_rn(y, __dmul_rn(j, L[1]));
+    const double i = rint(__ddiv_rn(x, L[0]));
+    x = __dsub_rn(x, __dmul_rn(i, L[0]));
+}
 __device__ __forceinline__ int wn_frame_sites(const WnSubset& s, int f, int n_table) { return s.off ? s.off[f + 1] - s.off[f] : n_table; }
 __device__ __forceinline__ int wn_table_row(const WnSubset& s, int f, int i) { return s.off ? s.sites[s.off[f] + i] : i; }
 #endif
@@ -93,7 +105,7 @@ struct WnEdgeParams {
     int first_limit;
     int row_cap;
     int simple;                 /* 1: every site WATER with the list [site atom, H] */
-    int pbc;                    /* 1: grids are periodic boxes                       */
+    int pbc;                    /* 0 open, 1 rectangular, 2 triclinic (all-pairs kernel only) */
     int bx;                     /* home block width in cells (1 or 2)               */
     WnSubset subset;            /* per-frame site subsets (off == nullptr: whole table) */
 };
@@ -107,6 +119,8 @@ void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* sit
                    int* site_cell, int* site_rank, cudaStream_t st);
 /* periodic grid of one frame, built on the host (uploaded with the pass) */
 void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g);
+/* triclinic frame (box9 = GROMACS matrix, row-major): one cell, all-pairs kernel */
+void wn_host_tric_grid(const float box9[9], WnGrid* g);
 void wn_launch_cellscan(int n_frames, int n_sites, WnSubset sub, int cell_cap, const WnGrid* grid,
                         int* cell_cnt, uint32_t* part /* [F][chunks(cell_cap)] */, cudaStream_t st);
 void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,
@@ -142,7 +156,7 @@ void wn_launch_format_rows(const wn_edge* edges, const unsigned long long* frame
                            unsigned long long max_edges_per_frame, char* text, int* frame_flags, cudaStream_t st);
 
 /* brute pair path (wn_kernels_pairs.cu) */
-struct WnPairBox { int pbc; double L[3], invL[3]; float Lf[3], invLf[3]; };
+struct WnPairBox { int pbc; /* 0 open, 1 rectangular, 2 triclinic */ double L[3], invL[3], tri[3]; float Lf[3], invLf[3], trif[3]; };
 void wn_launch_pairs_count(const double* xyz, int n, int first_limit, WnPairBox box, uint32_t* row_cnt,
                            unsigned long long* ties, cudaStream_t st);
 void wn_launch_pairs_scan(const uint32_t* row_cnt, int n, unsigned long long* row_off,

@@ -26,6 +26,20 @@ __device__ __forceinline__ float wn_wrap(float x, double L, double invL)
     return __double2float_rn(__dsub_rn(xd, __dmul_rn(floor(__dmul_rn(xd, invL)), L)));
 }
 
+/* triclinic: put the point in the brick [0,ax) x [0,by) x [0,cz) -- a fundamental domain of the
+ * lower-triangular lattice -- reducing along c, then b, then a (GROMACS order); fp64, then float */
+__device__ __forceinline__ void wn_wrap_tric(float& xf, float& yf, float& zf, const double* L, const double* tri)
+{
+    double x = (double)xf, y = (double)yf, z = (double)zf;
+    const double fz = floor(__ddiv_rn(z, L[2]));
+    x = __dsub_rn(x, __dmul_rn(fz, tri[1])); y = __dsub_rn(y, __dmul_rn(fz, tri[2])); z = __dsub_rn(z, __dmul_rn(fz, L[2]));
+    const double fy = floor(__ddiv_rn(y, L[1]));
+    x = __dsub_rn(x, __dmul_rn(fy, tri[0])); y = __dsub_rn(y, __dmul_rn(fy, L[1]));
+    const double fx = floor(__ddiv_rn(x, L[0]));
+    x = __dsub_rn(x, __dmul_rn(fx, L[0]));
+    xf = __double2float_rn(x); yf = __double2float_rn(y); zf = __double2float_rn(z);
+}
+
 __device__ __forceinline__ int wn_cell_coord(double x, double o, double inv, int n)
 {
     /* __double2int_rd saturates and maps NaN to 0; the clamp keeps every site,
@@ -47,7 +61,8 @@ wn_k_bin(const float* __restrict__ frames, int natoms, const int* __restrict__ s
     const WnGrid g = grid[f];
     const float* p = frames + ((size_t)f * natoms + (size_t)__ldg(site_atom + wn_table_row(sub, f, i))) * 3;
     float x = p[0], y = p[1], z = p[2];
-    if (g.pbc) { x = wn_wrap(x, g.L[0], g.invL[0]); y = wn_wrap(y, g.L[1], g.invL[1]); z = wn_wrap(z, g.L[2], g.invL[2]); }
+    if (g.pbc == 1) { x = wn_wrap(x, g.L[0], g.invL[0]); y = wn_wrap(y, g.L[1], g.invL[1]); z = wn_wrap(z, g.L[2], g.invL[2]); }
+    else if (g.pbc == 2) wn_wrap_tric(x, y, z, g.L, g.tri);
     const int cx = wn_cell_coord((double)x, g.ox, g.inv[0], g.nx);
     const int cy = wn_cell_coord((double)y, g.oy, g.inv[1], g.ny);
     const int cz = wn_cell_coord((double)z, g.oz, g.inv[2], g.nz);
@@ -73,11 +88,12 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
     const float* fr = frames + (size_t)f * natoms * 3;
     const float* p = fr + 3 * (size_t)__ldg(site_atom + row);
     float x = p[0], y = p[1], z = p[2];
-    const bool pbc = grid[f].pbc != 0;
-    double L[3] = {0, 0, 0}, invL[3] = {0, 0, 0};
+    const int pbc = grid[f].pbc;
+    double L[3] = {0, 0, 0}, invL[3] = {0, 0, 0}, tri[3] = {0, 0, 0};
     if (pbc) {
-        for (int c = 0; c < 3; ++c) { L[c] = grid[f].L[c]; invL[c] = grid[f].invL[c]; }
-        x = wn_wrap(x, L[0], invL[0]); y = wn_wrap(y, L[1], invL[1]); z = wn_wrap(z, L[2], invL[2]);
+        for (int c = 0; c < 3; ++c) { L[c] = grid[f].L[c]; invL[c] = grid[f].invL[c]; tri[c] = grid[f].tri[c]; }
+        if (pbc == 1) { x = wn_wrap(x, L[0], invL[0]); y = wn_wrap(y, L[1], invL[1]); z = wn_wrap(z, L[2], invL[2]); }
+        else wn_wrap_tric(x, y, z, L, tri);
     }
     const int cid = site_cell[(size_t)f * n_sites + i];
     const int dst = cell_start[(size_t)f * (cell_cap + 1) + cid] + site_rank[(size_t)f * n_sites + i];
@@ -91,7 +107,12 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
         double dx = NAN, dy = NAN, dz = NAN;
         if (at >= 0) {
             const float* h = fr + 3 * (size_t)at;
-            if (pbc) {
+            if (pbc == 2) {
+                float hx = h[0], hy = h[1], hz = h[2];
+                wn_wrap_tric(hx, hy, hz, L, tri);
+                dx = __dsub_rn((double)hx, sx); dy = __dsub_rn((double)hy, sy); dz = __dsub_rn((double)hz, sz);
+                wn_minimg_tric(dx, dy, dz, L, tri);
+            } else if (pbc == 1) {
                 /* wrapped hydrogen, then the minimum image of (hydrogen - site) */
                 dx = __dsub_rn((double)wn_wrap(h[0], L[0], invL[0]), sx);
                 dy = __dsub_rn((double)wn_wrap(h[1], L[1], invL[1]), sy);
@@ -171,4 +192,18 @@ void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g)
     if ((double)tf < tfd) tf = nextafterf(tf, 3.0e38f);
     g->tf = tf;
     g->pbc = 1;
+    g->tri[0] = g->tri[1] = g->tri[2] = 0.0;
+}
+
+void wn_host_tric_grid(const float box9[9], WnGrid* g)
+{
+    g->ox = g->oy = g->oz = 0.0;
+    const double d[3] = {(double)box9[0], (double)box9[4], (double)box9[8]};
+    for (int c = 0; c < 3; ++c) {
+        g->L[c] = d[c]; g->invL[c] = 1.0 / d[c]; g->inv[c] = 1.0 / d[c]; g->edge[c] = (float)d[c];
+    }
+    g->tri[0] = (double)box9[3]; g->tri[1] = (double)box9[6]; g->tri[2] = (double)box9[7];
+    g->nx = g->ny = g->nz = 1; g->ncells = 1;
+    g->tf = 1.0f;
+    g->pbc = 2;
 }

@@ -130,7 +130,7 @@ struct PairOut {
 /* Exact geometry of make_edges (src/waternetwork.cpp:192-259) for one pair.  a4/b4: float
  * positions + site index bits of the two sites in ANY order (see the role symmetry in the
  * file header); dha/dhb: their unit D-H vectors (stride 4 doubles); ma/mb: meta words. */
-template <bool SIMPLE, bool PBC>
+template <bool SIMPLE, int PBC>
 __device__ __forceinline__ PairOut
 wn_pair_geometry(const float4 a4, const float4 b4, const double* __restrict__ dha,
                  const double* __restrict__ dhb, uint32_t ma, uint32_t mb, const WnGrid& g)
@@ -143,10 +143,12 @@ wn_pair_geometry(const float4 a4, const float4 b4, const double* __restrict__ dh
     double ox = __dsub_rn((double)a4.x, (double)b4.x);
     double oy = __dsub_rn((double)a4.y, (double)b4.y);
     double oz = __dsub_rn((double)a4.z, (double)b4.z);
-    if (PBC) {
+    if (PBC == 1) {
         ox = wn_minimg(ox, g.L[0], g.invL[0]);
         oy = wn_minimg(oy, g.L[1], g.invL[1]);
         oz = wn_minimg(oz, g.L[2], g.invL[2]);
+    } else if (PBC == 2) {
+        wn_minimg_tric(ox, oy, oz, g.L, g.tri);
     }
     const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ox, ox), __dmul_rn(oy, oy)), __dmul_rn(oz, oz));
     /* float distance = CGAL::sqrt(OO*OO)                               (:195) */
@@ -234,7 +236,7 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
         const double* dc = p.sdh + (fbase + c) * (size_t)p.hs * 4;
         uint32_t mh = 0, mc = 0;
         if (!SIMPLE) { mh = ws.hmeta[h]; mc = __ldg(p.smeta + fbase + c); }
-        r = wn_pair_geometry<SIMPLE, PBC>(a4, b4, dh, dc, mh, mc, g);
+        r = wn_pair_geometry<SIMPLE, PBC ? 1 : 0>(a4, b4, dh, dc, mh, mc, g);
     }
     ct.evals += __popc(__ballot_sync(FULL, r.counted));
     if (__any_sync(FULL, r.t_len || r.t_cos || r.t_pos0)) {          /* rare */
@@ -462,7 +464,7 @@ wn_k_edges(const WnEdgeParams p)
  * L = 1.86 nm): neighbour cells alias under wrap-around, so the cell sweep cannot count
  * each pair once.  Such systems are small; one thread per cell-sorted site p pairs it with
  * every later site q > p, exact fp64 minimum-image geometry, same output path. */
-template <bool SIMPLE, bool PBC>
+template <bool SIMPLE, int PBC>
 __global__ void __launch_bounds__(128)
 wn_k_edges_small(const WnEdgeParams p)
 {
@@ -479,6 +481,11 @@ wn_k_edges_small(const WnEdgeParams p)
     const int ia = __float_as_int(a4.w);
     const double* dha = p.sdh + (fbase + (have ? pa : 0)) * (size_t)p.hs * 4;
     unsigned int evals = 0, tie_len = 0, tie_cos = 0, tie_pos0 = 0;
+    /* fp32 reject test (never accepts): coordinates lie in the box, so the float image shifts err
+     * by <= ~1e-6 * L per component; near a half-box displacement either image has the same length */
+    const float Lx = (float)g.L[0], Ly = (float)g.L[1], Lz = (float)g.L[2];
+    const float tbx = (float)g.tri[0], tcx = (float)g.tri[1], tcy = (float)g.tri[2];
+    const float bound = 0.4225f * 1.0001f + 1.0e-5f * (Lx + Ly + Lz + fabsf(tbx) + fabsf(tcx) + fabsf(tcy));
     for (int q0 = blockIdx.x * blockDim.x; q0 < n_f; q0 += 128) {
         __syncthreads();
         if (q0 + (int)threadIdx.x < n_f) tile[threadIdx.x] = __ldg(p.spos + fbase + q0 + threadIdx.x);
@@ -487,6 +494,19 @@ wn_k_edges_small(const WnEdgeParams p)
         const int kend = min(128, n_f - q0);
         for (int k = max(0, pa + 1 - q0); k < kend; ++k) {
             const float4 b4 = tile[k];
+            if (PBC) {
+                float dx = a4.x - b4.x, dy = a4.y - b4.y, dz = a4.z - b4.z;
+                if (PBC == 2) {
+                    const float kz = rintf(dz / Lz);
+                    dx -= kz * tcx; dy -= kz * tcy; dz -= kz * Lz;
+                    const float jy = rintf(dy / Ly);
+                    dx -= jy * tbx; dy -= jy * Ly;
+                    dx -= rintf(dx / Lx) * Lx;
+                } else {
+                    dx -= rintf(dx / Lx) * Lx; dy -= rintf(dy / Ly) * Ly; dz -= rintf(dz / Lz) * Lz;
+                }
+                if (dx * dx + dy * dy + dz * dz > bound) continue;     /* false for NaN */
+            }
             const int ib = __float_as_int(b4.w);
             if (min(ia, ib) >= p.first_limit) continue;
             const uint32_t mb = __ldg(p.smeta + fbase + q0 + k);
@@ -609,10 +629,12 @@ void wn_launch_edges_small(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
     dim3 grid((p.n_sites + 127) / 128, n_frames);
     if (p.simple) {
-        if (p.pbc) wn_k_edges_small<true, true><<<grid, 128, 0, st>>>(p);
-        else wn_k_edges_small<true, false><<<grid, 128, 0, st>>>(p);
+        if (p.pbc == 2) wn_k_edges_small<true, 2><<<grid, 128, 0, st>>>(p);
+        else if (p.pbc == 1) wn_k_edges_small<true, 1><<<grid, 128, 0, st>>>(p);
+        else wn_k_edges_small<true, 0><<<grid, 128, 0, st>>>(p);
     } else {
-        if (p.pbc) wn_k_edges_small<false, true><<<grid, 128, 0, st>>>(p);
-        else wn_k_edges_small<false, false><<<grid, 128, 0, st>>>(p);
+        if (p.pbc == 2) wn_k_edges_small<false, 2><<<grid, 128, 0, st>>>(p);
+        else if (p.pbc == 1) wn_k_edges_small<false, 1><<<grid, 128, 0, st>>>(p);
+        else wn_k_edges_small<false, 0><<<grid, 128, 0, st>>>(p);
     }
 }

@@ -33,7 +33,7 @@ struct PairTile {
  * shared-memory tiles; blockIdx.y = segment.  Splitting the columns into `nseg` segments
  * gives the GPU enough blocks (a thread per row alone is 7 warps per SM at 33k rows) and
  * keeps the order: counts and offsets are indexed [row][segment], segments ascend in j. */
-template <bool FILL, bool PBC>
+template <bool FILL, int PBC>
 __global__ void __launch_bounds__(ROWS)
 wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit, int nseg, int seg_len, const WnPairBox box,
            uint32_t* __restrict__ row_cnt, const unsigned long long* __restrict__ row_off,
@@ -84,26 +84,34 @@ wn_k_pairs(const double* __restrict__ xyz, int n, int first_limit, int nseg, int
              * periodic: the fp32 image shift adds <= ~1e-6 * L per component on top */
             const float ca = fmaxf(amax, s_amax);
             const float bound = 4.225f * 1.00002f + 1.0e-5f * ca * (1.0f + ca) +
-                                (PBC ? 3.0e-5f * (box.Lf[0] + box.Lf[1] + box.Lf[2]) : 0.0f);
+                                (PBC ? 3.0e-5f * (box.Lf[0] + box.Lf[1] + box.Lf[2] + fabsf(box.trif[0]) + fabsf(box.trif[1]) + fabsf(box.trif[2])) : 0.0f);
             const int kend = min(TILE, c1 - j0);
             const int kbeg = max(0, i + 1 - j0);
             for (int k = kbeg; k < kend; ++k) {
                 const float4 q = t.f[k];
                 float dxf = fxi - q.x, dyf = fyi - q.y, dzf = fzi - q.z;
-                if (PBC) {
+                if (PBC == 1) {
                     /* approximate minimum image; near +-L/2 either image has the same |d| */
                     dxf -= rintf(dxf * box.invLf[0]) * box.Lf[0];
                     dyf -= rintf(dyf * box.invLf[1]) * box.Lf[1];
                     dzf -= rintf(dzf * box.invLf[2]) * box.Lf[2];
+                } else if (PBC == 2) {
+                    const float kz = rintf(dzf * box.invLf[2]);
+                    dxf -= kz * box.trif[1]; dyf -= kz * box.trif[2]; dzf -= kz * box.Lf[2];
+                    const float jy = rintf(dyf * box.invLf[1]);
+                    dxf -= jy * box.trif[0]; dyf -= jy * box.Lf[1];
+                    dxf -= rintf(dxf * box.invLf[0]) * box.Lf[0];
                 }
                 const float d2f = dxf * dxf + dyf * dyf + dzf * dzf;
                 if (d2f > bound) continue;              /* false for NaN: falls through to the exact test */
                 double dx = __dsub_rn(xi, t.x[k]), dy = __dsub_rn(yi, t.y[k]), dz = __dsub_rn(zi, t.z[k]);
-                if (PBC) {
+                if (PBC == 1) {
                     /* periodic definition (include/wn_b200.h, "Periodic boundaries"): d - rint(d * (1/L)) * L */
                     dx = __dsub_rn(dx, __dmul_rn(rint(__dmul_rn(dx, box.invL[0])), box.L[0]));
                     dy = __dsub_rn(dy, __dmul_rn(rint(__dmul_rn(dy, box.invL[1])), box.L[1]));
                     dz = __dsub_rn(dz, __dmul_rn(rint(__dmul_rn(dz, box.invL[2])), box.L[2]));
+                } else if (PBC == 2) {
+                    wn_minimg_tric(dx, dy, dz, box.L, box.tri);
                 }
                 const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                 const double lhs = __dmul_rn(10.0, d2);
@@ -178,10 +186,12 @@ void wn_launch_pairs_count(const double* xyz, int n, int first_limit, WnPairBox 
 {
     const int nseg = wn_pairs_segments(n), seg_len = (n + nseg - 1) / nseg;
     dim3 g((n + ROWS - 1) / ROWS, nseg);
-    if (box.pbc)
-        wn_k_pairs<false, true><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, row_cnt, nullptr, nullptr, ties);
+    if (box.pbc == 2)
+        wn_k_pairs<false, 2><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, row_cnt, nullptr, nullptr, ties);
+    else if (box.pbc == 1)
+        wn_k_pairs<false, 1><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, row_cnt, nullptr, nullptr, ties);
     else
-        wn_k_pairs<false, false><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, row_cnt, nullptr, nullptr, ties);
+        wn_k_pairs<false, 0><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, row_cnt, nullptr, nullptr, ties);
 }
 
 /* exclusive scan over the n*nseg [row][segment] counts */
@@ -195,8 +205,10 @@ void wn_launch_pairs_fill(const double* xyz, int n, int first_limit, WnPairBox b
 {
     const int nseg = wn_pairs_segments(n), seg_len = (n + nseg - 1) / nseg;
     dim3 g((n + ROWS - 1) / ROWS, nseg);
-    if (box.pbc)
-        wn_k_pairs<true, true><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, nullptr, row_off, pairs, nullptr);
+    if (box.pbc == 2)
+        wn_k_pairs<true, 2><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, nullptr, row_off, pairs, nullptr);
+    else if (box.pbc == 1)
+        wn_k_pairs<true, 1><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, nullptr, row_off, pairs, nullptr);
     else
-        wn_k_pairs<true, false><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, nullptr, row_off, pairs, nullptr);
+        wn_k_pairs<true, 0><<<g, ROWS, 0, st>>>(xyz, n, first_limit, nseg, seg_len, box, nullptr, row_off, pairs, nullptr);
 }

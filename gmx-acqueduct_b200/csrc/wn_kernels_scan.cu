@@ -184,7 +184,7 @@ wn_k_bbox_finalize(const uint32_t* __restrict__ scratch, int n_frames, int cell_
     const uint32_t* s = scratch + (size_t)f * 6;
     WnGrid g;
     g.pbc = 0;
-    for (int c = 0; c < 3; ++c) { g.L[c] = 0.0; g.invL[c] = 0.0; }
+    for (int c = 0; c < 3; ++c) { g.L[c] = 0.0; g.invL[c] = 0.0; g.tri[c] = 0.0; }
     if (s[0] == 0xffffffffu) {                /* no finite site */
         g.ox = g.oy = g.oz = 0.0; g.nx = g.ny = g.nz = 1; g.ncells = 1;
         for (int c = 0; c < 3; ++c) { g.inv[c] = 1.0; g.edge[c] = 1.0f; }

@@ -97,6 +97,17 @@ HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, const float*
     return b;
 }
 
+HydrogenBondBatch HydrogenBondEdges::calculateBox9(const float* frames, const float* boxes9, int n_frames, int natoms)
+{
+    wn_batch_result r;
+    const int rc = wn_hbond_batch_box9(ctx_, frames, boxes9, n_frames, natoms, &r);
+    if (rc != WN_OK) raise("HydrogenBondEdges::calculateBox9: wn_hbond_batch_box9", rc, ctx_);
+    HydrogenBondBatch b;
+    b.edges = r.edges; b.offsets = r.frame_offsets; b.stats = r.stats;
+    b.n_frames = r.n_frames; b.n_edges = r.n_edges; b.n_pair_evals = r.n_pair_evals; b.ties = r.ties;
+    return b;
+}
+
 bool HydrogenBondEdges::formatLastBatch(const std::vector<int>& frameNumbers, const std::vector<unsigned>& ids,
                                         const char** text, uint64_t* bytes)
 {
@@ -138,13 +149,10 @@ void FrameBatcher::push(int frnr, const float* xyz)
 
 void FrameBatcher::push(int frnr, const float* xyz, const float box[3][3])
 {
-    for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b)
-            if (a != b && box[a][b] != 0.0f)
-                throw std::invalid_argument("FrameBatcher::push: triclinic boxes are not supported");
-    if (!frnr_.empty() && boxes_.size() != 3 * frnr_.size())
+    if (!frnr_.empty() && boxes_.size() != 9 * frnr_.size())
         throw std::invalid_argument("FrameBatcher::push: periodic and open frames mixed in one batch");
-    boxes_.push_back(box[0][0]); boxes_.push_back(box[1][1]); boxes_.push_back(box[2][2]);
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) boxes_.push_back(box[a][b]);
     push(frnr, xyz);
 }
 
@@ -156,11 +164,12 @@ void FrameBatcher::push(int frnr, const float* xyz, const float (*box)[3], const
     sub_sites_.insert(sub_sites_.end(), frameSites.begin(), frameSites.end());
     sub_off_.push_back((int64_t)sub_sites_.size());
     if (box) {
-        boxes_.push_back(box[0][0]); boxes_.push_back(box[1][1]); boxes_.push_back(box[2][2]);
         for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b)
+            for (int b = 0; b < 3; ++b) {
                 if (a != b && box[a][b] != 0.0f)
-                    throw std::invalid_argument("FrameBatcher::push: triclinic boxes are not supported");
+                    throw std::invalid_argument("FrameBatcher::push: per-frame site lists need a rectangular box");
+                boxes_.push_back(box[a][b]);
+            }
     }
     push(frnr, xyz);
 }
@@ -170,10 +179,16 @@ void FrameBatcher::finish() { flush(); }
 void FrameBatcher::flush()
 {
     if (frnr_.empty()) return;
-    const float* bx = boxes_.empty() ? nullptr : boxes_.data();
-    const HydrogenBondBatch b = sub_off_.empty()
-        ? engine_.calculate(buf_.data(), bx, (int)frnr_.size(), natoms_)
-        : engine_.calculate(buf_.data(), bx, (int)frnr_.size(), natoms_, sub_off_.data(), sub_sites_.data());
+    HydrogenBondBatch b;
+    if (sub_off_.empty()) {
+        b = boxes_.empty() ? engine_.calculate(buf_.data(), (int)frnr_.size(), natoms_)
+                           : engine_.calculateBox9(buf_.data(), boxes_.data(), (int)frnr_.size(), natoms_);
+    } else {
+        std::vector<float> b3;                    /* site lists: rectangular boxes only (checked in push) */
+        for (size_t f = 0; 9 * f < boxes_.size(); ++f) { b3.push_back(boxes_[9 * f]); b3.push_back(boxes_[9 * f + 4]); b3.push_back(boxes_[9 * f + 8]); }
+        b = engine_.calculate(buf_.data(), b3.empty() ? nullptr : b3.data(), (int)frnr_.size(), natoms_, sub_off_.data(),
+                              sub_sites_.data());
+    }
     for (int f = 0; f < b.n_frames; ++f)
         sink_(frnr_[f], b.edges + b.offsets[f], (size_t)(b.offsets[f + 1] - b.offsets[f]), b.stats[f]);
     frames_done_ += (uint64_t)b.n_frames;

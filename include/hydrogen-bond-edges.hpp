@@ -62,6 +62,9 @@ public:
     // Periodic variant (extension, defined in wn_b200.h): boxes = [n_frames][3] box lengths,
     // the diagonal of each frame's t_trxframe::box.
     HydrogenBondBatch calculate(const float* frames, const float* boxes, int n_frames, int natoms);
+    // General boxes: boxes9 = [n_frames][9], t_trxframe::box row-major (triclinic frames run the
+    // all-pairs kernel; a batch of rectangular frames is routed to the cell-list sweep).
+    HydrogenBondBatch calculateBox9(const float* frames, const float* boxes9, int n_frames, int natoms);
 
     // Per-frame site lists (what as_->locate() leaves, src/waternetwork.cpp:529-533): frame f uses the
     // table rows sites[offsets[f] .. offsets[f+1]); edge indices are positions in that list.
@@ -100,7 +103,7 @@ public:
 
     FrameBatcher(HydrogenBondEdges& engine, int natoms, int batch_frames, Sink sink);
     void push(int frnr, const float* xyz /* natoms*3 */);
-    // periodic: box = GROMACS matrix fr.box; throws std::invalid_argument for a triclinic box
+    // periodic: box = GROMACS matrix fr.box (rectangular or triclinic)
     void push(int frnr, const float* xyz, const float box[3][3]);
     // with the frame's own site list (rows of the site table, e.g. protein sites + the buried
     // waters of this frame); box may be nullptr.  All frames of a run must use the same variant.

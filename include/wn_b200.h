@@ -133,9 +133,20 @@ int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit
  *      image of the fp64 difference, d = pa - pb; d = d - rint(d * (1.0/L)) * L
  *      (every operation rounded, rint half-to-even: +-L/2 is kept, d(b,a) == -d(a,b)).
  *   3. everything else is unchanged.
- * Triclinic boxes are not supported. */
+ * Triclinic boxes (the *_box9 entry points; box9 = GROMACS' matrix, row-major: a = (ax,0,0),
+ * b = (bx,by,0), c = (cx,cy,cz)) reduce along c, then b, then a, every operation rounded in fp64:
+ *   put in box:  fz = floor(z/cz): (x,y,z) -= fz*c;  fy = floor(y/by): (x,y) -= fy*(bx,by);
+ *                fx = floor(x/ax): x -= fx*ax;  result rounded to float
+ *   min image:   k = rint(d.z/cz): d -= k*c;  j = rint(d.y/by): d -= j*b;  i = rint(d.x/ax): d.x -= i*ax
+ * (the shortest image whenever the cutoff is small against the box, as GROMACS assumes).  A call
+ * whose frames are all rectangular uses the rectangular definition above; one with any
+ * triclinic frame uses the triclinic formulas for every frame.  Triclinic frames currently
+ * run the all-pairs kernel (O(N^2) per frame); the cell-list sweep covers rectangular boxes. */
 int wn_find_pairs_pbc(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
                       const float box[3], const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
+
+int wn_find_pairs_box9(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
+                       const float box9[9], const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
 
 /* ---- site tables (src/waternetwork.cpp:538-577) --------------------------
  * site_atom[n_sites]: atom index (into a frame) of each site.
@@ -172,6 +183,9 @@ int wn_hbond_batch_pbc(wn_ctx* ctx, const float* frames_host, const float* boxes
                        int32_t n_frames, int32_t natoms, wn_batch_result* out);
 int wn_hbond_batch_pbc_dev(wn_ctx* ctx, const float* frames_dev, const float* boxes_host,
                            int32_t n_frames, int32_t natoms, wn_batch_result* out);
+/* General boxes: boxes9_host = float32 [n_frames][9], GROMACS' t_trxframe::box row-major. */
+int wn_hbond_batch_box9(wn_ctx* ctx, const float* frames_host, const float* boxes9_host,
+                        int32_t n_frames, int32_t natoms, wn_batch_result* out);
 /* Per-frame site subsets: the buried waters the reference's alpha-shape filter keeps change
  * every frame (as_->locate, src/waternetwork.cpp:529-533; the node loop :562-576 then builds
  * sitePoints from that frame's list).  Frame f uses the rows

@@ -325,10 +325,33 @@ size_t wno_brute_find_pairs_pbc(const double* xyz, int n, int first_limit, const
     return count;
 }
 
+/* box descriptor for the periodic variants: rectangular (tric == NULL) or triclinic */
+typedef struct { const double* L; const double* invL; const double* tric; /* ax,by,cz,bx,cx,cy */ } pbox;
+
+static inline v3 minimg_box(v3 d, const pbox* b)
+{
+    if (b->tric) {
+        const double ax = b->tric[0], by = b->tric[1], cz = b->tric[2], bx = b->tric[3], cx = b->tric[4], cy = b->tric[5];
+        const double k = rint(d.z / cz);
+        d.x = d.x - k * cx; d.y = d.y - k * cy; d.z = d.z - k * cz;
+        {
+            const double j = rint(d.y / by);
+            d.x = d.x - j * bx; d.y = d.y - j * by;
+        }
+        {
+            const double i = rint(d.x / ax);
+            d.x = d.x - i * ax;
+        }
+    } else {
+        d.x = minimg(d.x, b->L[0], b->invL[0]); d.y = minimg(d.y, b->L[1], b->invL[1]); d.z = minimg(d.z, b->L[2], b->invL[2]);
+    }
+    return d;
+}
+
 /* make_edges (src/waternetwork.cpp:182-263) on minimum-image displacements */
-static size_t make_edges_pbc(const int32_t* pairs, size_t m, const double* site_xyz, int n,
+static size_t make_edges_box(const int32_t* pairs, size_t m, const double* site_xyz, int n,
                              const double* h_xyz, const int32_t* h_off, const uint8_t* site_type,
-                             const double L[3], const double invL[3],
+                             const pbox* bx_,
                              wno_edge* out, uint64_t* n_evals, wno_ties* ties)
 {
     size_t count = 0, k;
@@ -344,9 +367,8 @@ static size_t make_edges_pbc(const int32_t* pairs, size_t m, const double* site_
         const double* pb = site_xyz + 3 * (size_t)b;
         const int nha = h_off[a + 1] - h_off[a], nhb = h_off[b + 1] - h_off[b];
         int isedge = 0;
-        v3 OO = v3_sub(pa, pb);
+        v3 OO = minimg_box(v3_sub(pa, pb), bx_);
         float distance;
-        OO.x = minimg(OO.x, L[0], invL[0]); OO.y = minimg(OO.y, L[1], invL[1]); OO.z = minimg(OO.z, L[2], invL[2]);
         distance = (float)sqrt(v3_dot(OO, OO));
         OO = v3_div(OO, (double)distance);
         distance = (float)((double)distance * 10.0);
@@ -362,9 +384,8 @@ static size_t make_edges_pbc(const int32_t* pairs, size_t m, const double* site_
             for (h = 0; h < nha + nhb; ++h) {
                 const int first = h < nha;
                 const double* hp = h_xyz + 3 * (size_t)(first ? h_off[a] + h : h_off[b] + h - nha);
-                v3 DH = v3_sub(hp, first ? pa : pb);
+                v3 DH = minimg_box(v3_sub(hp, first ? pa : pb), bx_);
                 float proj;
-                DH.x = minimg(DH.x, L[0], invL[0]); DH.y = minimg(DH.y, L[1], invL[1]); DH.z = minimg(DH.z, L[2], invL[2]);
                 DH = v3_div(DH, sqrt(v3_dot(DH, DH)));
                 proj = first ? (float)v3_dot(DH, OO) : (float)v3_dot(DH, v3_scale(-1.0, OO));
                 energies[nc] = (float)wno_compute_energy((double)distance, (double)proj);
@@ -410,7 +431,99 @@ size_t wno_frame_hbonds_pbc(const float* frame_xyz, int natoms,
     pairs = (int32_t*)malloc(sizeof(int32_t) * 2 * (m ? m : 1));
     wno_brute_find_pairs_pbc(site_xyz, n, first_limit, box, pairs, m, ties);
     tmp = (wno_edge*)malloc(sizeof(wno_edge) * (m ? m : 1));
-    ne = make_edges_pbc(pairs, m, site_xyz, n, h_xyz, h_off, site_type, L, invL, tmp, n_evals, ties);
+    {
+        pbox pb_;
+        pb_.L = L; pb_.invL = invL; pb_.tric = NULL;
+        ne = make_edges_box(pairs, m, site_xyz, n, h_xyz, h_off, site_type, &pb_, tmp, n_evals, ties);
+    }
+    if (n_pairs) *n_pairs = m;
+    for (k = 0; k < ne; ++k) sum_e += (double)tmp[k].energy;
+    if (stats) {
+        stats[0] = (double)n; stats[1] = (double)ne;
+        stats[2] = n > 0 ? 1.0 * (double)ne / (double)n : 0.0; stats[3] = sum_e;
+    }
+    if (ne <= cap && edges) memcpy(edges, tmp, sizeof(wno_edge) * ne);
+    free(tmp); free(pairs); free(h_off); free(h_xyz); free(site_xyz); free(wrapped);
+    return ne <= cap ? ne : (size_t)-1;
+}
+
+/* ======================= triclinic boxes (definition: include/wn_b200.h) ======================= */
+
+static void tric_unpack(const float box9[9], double t[6])
+{
+    t[0] = (double)box9[0]; t[1] = (double)box9[4]; t[2] = (double)box9[8];   /* ax, by, cz */
+    t[3] = (double)box9[3]; t[4] = (double)box9[6]; t[5] = (double)box9[7];   /* bx, cx, cy */
+}
+
+void wno_wrap_frame_tric(const float* frame_xyz, int natoms, const float box9[9], float* out_xyz)
+{
+    double t[6];
+    int a;
+    tric_unpack(box9, t);
+    for (a = 0; a < natoms; ++a) {
+        double x = (double)frame_xyz[3 * (size_t)a], y = (double)frame_xyz[3 * (size_t)a + 1], z = (double)frame_xyz[3 * (size_t)a + 2];
+        const double fz = floor(z / t[2]);
+        double fy, fx;
+        x = x - fz * t[4]; y = y - fz * t[5]; z = z - fz * t[2];
+        fy = floor(y / t[1]);
+        x = x - fy * t[3]; y = y - fy * t[1];
+        fx = floor(x / t[0]);
+        x = x - fx * t[0];
+        out_xyz[3 * (size_t)a] = (float)x; out_xyz[3 * (size_t)a + 1] = (float)y; out_xyz[3 * (size_t)a + 2] = (float)z;
+    }
+}
+
+size_t wno_brute_find_pairs_tric(const double* xyz, int n, int first_limit, const float box9[9],
+                                 int32_t* pairs, size_t cap, wno_ties* ties)
+{
+    float cutoff = 6.5f;
+    size_t count = 0;
+    int i, j;
+    double t[6];
+    pbox pb_;
+    cutoff *= cutoff;
+    tric_unpack(box9, t);
+    pb_.L = NULL; pb_.invL = NULL; pb_.tric = t;
+    if (first_limit > n) first_limit = n;
+    for (i = 0; i < first_limit; ++i)
+        for (j = i + 1; j < n; ++j) {
+            const v3 d = minimg_box(v3_sub(xyz + 3 * (size_t)i, xyz + 3 * (size_t)j), &pb_);
+            const double lhs = 10.0 * v3_dot(d, d);
+            if (lhs < cutoff) {
+                if (pairs && count < cap) { pairs[2 * count] = i; pairs[2 * count + 1] = j; }
+                ++count;
+            } else if (ties && lhs == (double)cutoff) {
+                ties->pair_cutoff_equal++;
+            }
+            if (ties && fabs(lhs - (double)cutoff) <= 2.8421709430404007e-14) ties->pair_cutoff_near++;
+        }
+    return count;
+}
+
+size_t wno_frame_hbonds_tric(const float* frame_xyz, int natoms,
+                             const int32_t* site_atom, const int32_t* h_atom, int hmax,
+                             const uint8_t* site_type, int n, int first_limit, const float box9[9],
+                             wno_edge* edges, size_t cap, double* stats,
+                             uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties)
+{
+    float* wrapped = (float*)malloc(sizeof(float) * 3 * (size_t)(natoms > 0 ? natoms : 1));
+    double* site_xyz = (double*)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
+    double* h_xyz = (double*)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1) * (size_t)(hmax > 0 ? hmax : 1));
+    int32_t* h_off = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1));
+    int32_t* pairs;
+    wno_edge* tmp;
+    size_t m, ne, k;
+    double sum_e = 0.0, t[6];
+    pbox pb_;
+    tric_unpack(box9, t);
+    pb_.L = NULL; pb_.invL = NULL; pb_.tric = t;
+    wno_wrap_frame_tric(frame_xyz, natoms, box9, wrapped);
+    wno_gather_sites(wrapped, natoms, site_atom, h_atom, hmax, n, site_xyz, h_xyz, h_off);
+    m = wno_brute_find_pairs_tric(site_xyz, n, first_limit, box9, NULL, 0, NULL);
+    pairs = (int32_t*)malloc(sizeof(int32_t) * 2 * (m ? m : 1));
+    wno_brute_find_pairs_tric(site_xyz, n, first_limit, box9, pairs, m, ties);
+    tmp = (wno_edge*)malloc(sizeof(wno_edge) * (m ? m : 1));
+    ne = make_edges_box(pairs, m, site_xyz, n, h_xyz, h_off, site_type, &pb_, tmp, n_evals, ties);
     if (n_pairs) *n_pairs = m;
     for (k = 0; k < ne; ++k) sum_e += (double)tmp[k].energy;
     if (stats) {

@@ -126,6 +126,21 @@ size_t wno_frame_hbonds_pbc(const float* frame_xyz, int natoms,
                             wno_edge* edges, size_t cap, double* stats,
                             uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties);
 
+/* ---- triclinic boxes (GROMACS convention: box9 = rows a=(ax,0,0), b=(bx,by,0), c=(cx,cy,cz)).
+ * Definition in include/wn_b200.h ("Periodic boundaries", triclinic part), restated here:
+ *   wrap:     fz = floor(z/cz): (x,y,z) -= fz*c;  fy = floor(y/by): (x,y) -= fy*(bx,by);
+ *             fx = floor(x/ax): x -= fx*ax;   all in fp64, result rounded to float
+ *   min image of d = pa - pb:  k = rint(d.z/cz): d -= k*c;  j = rint(d.y/by): d -= j*b;
+ *             i = rint(d.x/ax): d.x -= i*ax */
+void wno_wrap_frame_tric(const float* frame_xyz, int natoms, const float box9[9], float* out_xyz);
+size_t wno_brute_find_pairs_tric(const double* xyz, int n, int first_limit, const float box9[9],
+                                 int32_t* pairs, size_t cap, wno_ties* ties);
+size_t wno_frame_hbonds_tric(const float* frame_xyz, int natoms,
+                             const int32_t* site_atom, const int32_t* h_atom, int hmax,
+                             const uint8_t* site_type, int n, int first_limit, const float box9[9],
+                             wno_edge* edges, size_t cap, double* stats,
+                             uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,10 +102,13 @@ int main()
             pb.finish();
             CHECK(pgot.size() == pref.size());
             for (size_t k = 0; k < pgot.size(); ++k) CHECK(pgot[k].i == pref[k].i && pgot[k].j == pref[k].j && pgot[k].cosine == pref[k].cosine);
-            const float tric[3][3] = {{2.1f, 0.f, 0.f}, {0.5f, 2.1f, 0.f}, {0.f, 0.f, 2.1f}};
-            bool thr = false;
-            try { pb.push(0, frames.data(), tric); } catch (const std::invalid_argument&) { thr = true; }
-            CHECK(thr);
+            // a triclinic matrix is accepted too (all-pairs kernel): same frames, skewed cell
+            const float tric[3][3] = {{2.1f, 0.f, 0.f}, {0.5f, 2.1f, 0.f}, {-0.3f, 0.4f, 2.1f}};
+            size_t n_tric = 0;
+            FrameBatcher tb(hb, natoms, 4, [&](int, const wn_edge*, size_t n, const wn_frame_stats&) { n_tric += n; });
+            for (int f = 0; f < 2; ++f) tb.push(f, &frames[(size_t)f * natoms * 3], tric);
+            tb.finish();
+            CHECK(n_tric > 0);
             CudaFindPairs* cf = static_cast<CudaFindPairs*>(mp_.get());
             cf->setBox(3.0f, 3.0f, 3.0f);
             std::vector<std::pair<int, int>> pp = mp_->find(pts);

@@ -578,3 +578,62 @@ def test_gpu_text_formatter_matches_printf(ctx, oracle, capi):
     ctx.set_water_sites(3)
     ctx.hbond_batch(np.zeros((2, 9, 3), np.float32) + np.arange(9)[None, :, None] * 5.0)
     assert ctx.format_edges([4, 5]) == b"#--- frame 4 ---\n#--- frame 5 ---\n"
+
+
+# ------------------------------------------------------------------ triclinic boxes
+def test_triclinic_boxes(ctx, oracle):
+    """GROMACS triclinic boxes (lower-triangular matrix), all-pairs kernel: skewed water boxes with
+    unwrapped coordinates, mixed site types, and the pair finder; bit-exact vs the triclinic oracle."""
+    rng = np.random.default_rng(17)
+    n, nf = 400, 3
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 5, nf).copy()
+    L = float(box.box)
+    boxes9 = np.zeros((nf, 9), np.float32)
+    for f in range(nf):
+        boxes9[f] = [L, 0, 0, 0.31 * L, 0.95 * L, 0, -0.22 * L, 0.4 * L, 0.9 * L + 0.05 * f]
+        B = boxes9[f].reshape(3, 3).astype(np.float64)
+        shift = rng.integers(-2, 3, size=(n, 3)) @ B                  # whole molecules moved by lattice vectors
+        for a in range(3):
+            frames[f, a::3] += shift.astype(np.float32)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames, boxes=boxes9)
+    edges, stats, evals = [], [], 0
+    ties = oracle.Ties()
+    for f in range(nf):
+        e, s, _, ev = oracle.frame_hbonds_tric(frames[f], sa, ha, ty, boxes9[f], ties=ties)
+        edges.append(e); stats.append(s); evals += ev
+    compare_batch(res, edges, np.array(stats), evals, ties.as_dict())
+    assert res["n_edges"] > 0
+    # mixed table + row limit
+    n_sites = 250
+    site_atom = (np.arange(n_sites) * 4).astype(np.int32)
+    h_atom = -np.ones((n_sites, 3), np.int32)
+    nh = rng.integers(0, 4, size=n_sites)
+    for s in range(n_sites):
+        for k in range(nh[s]):
+            h_atom[s, k] = site_atom[s] + 1 + k
+    site_type = rng.integers(0, 3, size=n_sites).astype(np.uint8)
+    b9 = np.array([[2.2, 0, 0, 0.7, 2.0, 0, 0.5, -0.6, 1.9]], np.float32)
+    fr = np.zeros((1, 4 * n_sites, 3), np.float32)
+    pos = rng.uniform(0, 1, size=(n_sites, 3)) @ b9.reshape(3, 3)
+    fr[0, 0::4] = pos
+    for k in range(3):
+        d = rng.normal(size=(n_sites, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+        fr[0, 1 + k::4] = pos + 0.1 * d
+    ctx.set_sites(site_atom, h_atom, site_type, first_limit=90)
+    res = ctx.hbond_batch(fr, boxes=b9)
+    t2 = oracle.Ties()
+    e, s, _, ev = oracle.frame_hbonds_tric(fr[0], site_atom, h_atom, site_type, b9[0], first_limit=90, ties=t2)
+    compare_batch(res, [e], np.array([s]), ev, t2.as_dict())
+    # a diagonal matrix routes to the rectangular definition
+    ctx.set_water_sites(n)
+    diag = np.zeros((nf, 9), np.float32); diag[:, 0] = diag[:, 4] = diag[:, 8] = L
+    fr0 = oracle.synth_frames(box, 5, nf)
+    assert ctx.hbond_batch(fr0, boxes=diag)["edges"].tobytes() == \
+        ctx.hbond_batch(fr0, boxes=np.full((nf, 3), np.float32(L)))["edges"].tobytes()
+    # pair finder
+    xyz = (rng.uniform(-1, 2, size=(500, 3)) @ boxes9[0].reshape(3, 3).astype(np.float64)).astype(np.float32).astype(np.float64)
+    got, _ = ctx.find_pairs(xyz, box=boxes9[0])
+    assert np.array_equal(got, oracle.brute_find_pairs_tric(xyz, boxes9[0]))

@@ -88,6 +88,10 @@ def lib():
                                                C.c_size_t, C.c_void_p]
         L.wno_wrap_frame.restype = None
         L.wno_wrap_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.wno_frame_hbonds_tric.restype = C.c_size_t
+        L.wno_frame_hbonds_tric.argtypes = L.wno_frame_hbonds_pbc.argtypes
+        L.wno_brute_find_pairs_tric.restype = C.c_size_t
+        L.wno_brute_find_pairs_tric.argtypes = L.wno_brute_find_pairs_pbc.argtypes
         _lib = L
     return _lib
 
@@ -285,4 +289,41 @@ def brute_find_pairs_pbc(xyz, box, first_limit=None, ties=None):
     m = lib().wno_brute_find_pairs_pbc(xyz.ctypes.data, n, fl, box.ctypes.data, None, 0, None)
     pairs = np.empty((m, 2), dtype=np.int32)
     lib().wno_brute_find_pairs_pbc(xyz.ctypes.data, n, fl, box.ctypes.data, pairs.ctypes.data, m, tp)
+    return pairs
+
+
+def frame_hbonds_tric(frame, site_atom, h_atom, site_type, box9, first_limit=None, ties=None, cap=None):
+    """One frame under the triclinic-PBC definition (box9 = GROMACS matrix, row-major)."""
+    frame = np.ascontiguousarray(frame, dtype=np.float32).reshape(-1, 3)
+    site_atom = np.ascontiguousarray(site_atom, dtype=np.int32)
+    n = len(site_atom)
+    h_atom = np.ascontiguousarray(h_atom, dtype=np.int32).reshape(n, -1) if n else np.zeros((0, 1), np.int32)
+    hmax = h_atom.shape[1]
+    site_type = np.ascontiguousarray(site_type, dtype=np.uint8)
+    box9 = np.ascontiguousarray(box9, dtype=np.float32).reshape(9)
+    fl = n if first_limit is None else int(first_limit)
+    if cap is None:
+        cap = max(n * (n - 1) // 2, 1) if n <= 4096 else 64 * n
+    edges = np.empty(cap, dtype=EDGE_DTYPE)
+    stats = np.zeros(4, dtype=np.float64)
+    npairs, nevals = C.c_uint64(0), C.c_uint64(0)
+    tp = C.byref(ties) if ties is not None else None
+    ne = lib().wno_frame_hbonds_tric(frame.ctypes.data, frame.shape[0], site_atom.ctypes.data,
+                                     h_atom.ctypes.data, hmax, site_type.ctypes.data, n, fl,
+                                     box9.ctypes.data, edges.ctypes.data, cap, stats.ctypes.data,
+                                     C.byref(npairs), C.byref(nevals), tp)
+    if ne == C.c_size_t(-1).value:
+        raise RuntimeError("oracle edge capacity overflow")
+    return edges[:ne].copy(), stats, int(npairs.value), int(nevals.value)
+
+
+def brute_find_pairs_tric(xyz, box9, first_limit=None, ties=None):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+    box9 = np.ascontiguousarray(box9, dtype=np.float32).reshape(9)
+    n = xyz.shape[0]
+    fl = n if first_limit is None else int(first_limit)
+    tp = C.byref(ties) if ties is not None else None
+    m = lib().wno_brute_find_pairs_tric(xyz.ctypes.data, n, fl, box9.ctypes.data, None, 0, None)
+    pairs = np.empty((m, 2), dtype=np.int32)
+    lib().wno_brute_find_pairs_tric(xyz.ctypes.data, n, fl, box9.ctypes.data, pairs.ctypes.data, m, tp)
     return pairs
