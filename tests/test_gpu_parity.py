@@ -637,3 +637,37 @@ def test_triclinic_boxes(ctx, oracle):
     xyz = (rng.uniform(-1, 2, size=(500, 3)) @ boxes9[0].reshape(3, 3).astype(np.float64)).astype(np.float32).astype(np.float64)
     got, _ = ctx.find_pairs(xyz, box=boxes9[0])
     assert np.array_equal(got, oracle.brute_find_pairs_tric(xyz, boxes9[0]))
+
+
+def test_energy_parameters_and_hydrogenless_tables(ctx, oracle):
+    """setRadiusShift/setAngleShift surface: non-default switch parameters, including an ordering
+    that makes the (normally unreachable) smooth branch of the angle switch live; and a
+    site table without any hydrogen list."""
+    n, nf = 500, 2
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 9, nf)
+    ctx.set_water_sites(n)
+    base = ctx.hbond_batch(frames)
+    L = oracle.lib()
+    for (r_on, r_off, t_on, t_off) in ((4.0, 6.0, 0.25, 0.0), (3.0, 6.5, 0.0, 0.25), (5.5, 6.5, 0.1, 0.6)):
+        ctx.set_energy_params(r_on, r_off, t_on, t_off)
+        res = ctx.hbond_batch(frames)
+        e = res["edges"]
+        # geometry does not depend on the energy parameters
+        for k in ("i", "j", "length", "cosine"):
+            assert np.array_equal(e[k], base["edges"][k])
+        want = np.array([L.wno_compute_energy_ex(float(a), float(b), r_on, r_off, t_on, t_off)
+                         for a, b in zip(e["length"], e["cosine"])]).astype(np.float32)
+        ge, we = e["energy"].astype(np.float64), want.astype(np.float64)
+        assert np.all(np.abs(ge - we) <= 1e-6 * np.abs(we)), np.max(np.abs(ge - we) / np.maximum(np.abs(we), 1e-300))
+        assert np.count_nonzero(we) > 0
+    ctx.set_energy_params()                                   # back to the reference defaults
+    again = ctx.hbond_batch(frames)
+    assert again["edges"].tobytes() == base["edges"].tobytes()
+    # no hydrogens anywhere: pairs exist, nothing is evaluated (src/waternetwork.cpp:205-208)
+    site_atom = (3 * np.arange(n)).astype(np.int32)
+    ctx.set_sites(site_atom, -np.ones((n, 1), np.int32), np.full(n, oracle.WATER, np.uint8))
+    r0 = ctx.hbond_batch(frames)
+    assert r0["n_edges"] == 0 and r0["n_pair_evals"] == 0
+    want, st, npairs, ev = oracle.frame_hbonds(frames[0], site_atom, -np.ones((n, 1), np.int32), np.full(n, oracle.WATER, np.uint8))
+    assert len(want) == 0 and ev == 0 and npairs > 0
