@@ -312,8 +312,10 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
                     if (!std::isfinite(b[k])) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_box9: box must be finite");
                 if (!(b[0] > 0.f && b[4] > 0.f && b[8] > 0.f) || b[1] != 0.f || b[2] != 0.f || b[5] != 0.f)
                     return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_box9: box must be lower-triangular with a positive diagonal (GROMACS convention)");
-                wn_host_tric_grid(b, &g);
-                small_box = true;             /* triclinic: all-pairs kernel */
+                wn_host_tric_grid(b, cell_cap, &g);
+                /* the shifted neighbour ranges span up to BX+3 cells in x and 4 rows in y */
+                if (g.nx < 4 || g.ny < 4 || g.nz < 3) small_box = true;
+                if (g.nx < 5) bx = 1;
                 continue;
             }
             const float* b = boxes + 3 * (size_t)f;

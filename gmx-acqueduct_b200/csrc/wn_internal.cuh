@@ -119,8 +119,8 @@ void wn_launch_bin(const float* frames, int n_frames, int natoms, const int* sit
                    int* site_cell, int* site_rank, cudaStream_t st);
 /* periodic grid of one frame, built on the host (uploaded with the pass) */
 void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g);
-/* triclinic frame (box9 = GROMACS matrix, row-major): one cell, all-pairs kernel */
-void wn_host_tric_grid(const float box9[9], WnGrid* g);
+/* triclinic frame (box9 = GROMACS matrix, row-major): cells on the brick [0,ax) x [0,by) x [0,cz) */
+void wn_host_tric_grid(const float box9[9], int cell_cap, WnGrid* g);
 void wn_launch_cellscan(int n_frames, int n_sites, WnSubset sub, int cell_cap, const WnGrid* grid,
                         int* cell_cnt, uint32_t* part /* [F][chunks(cell_cap)] */, cudaStream_t st);
 void wn_launch_scatter(const float* frames, int n_frames, int natoms, const int* site_atom,

@@ -195,15 +195,11 @@ void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g)
     g->tri[0] = g->tri[1] = g->tri[2] = 0.0;
 }
 
-void wn_host_tric_grid(const float box9[9], WnGrid* g)
+void wn_host_tric_grid(const float box9[9], int cell_cap, WnGrid* g)
 {
-    g->ox = g->oy = g->oz = 0.0;
-    const double d[3] = {(double)box9[0], (double)box9[4], (double)box9[8]};
-    for (int c = 0; c < 3; ++c) {
-        g->L[c] = d[c]; g->invL[c] = 1.0 / d[c]; g->inv[c] = 1.0 / d[c]; g->edge[c] = (float)d[c];
-    }
+    /* cells on the brick [0,ax) x [0,by) x [0,cz): same rule as the rectangular grid */
+    const float diag[3] = {box9[0], box9[4], box9[8]};
+    wn_host_pbc_grid(diag, cell_cap, g);
     g->tri[0] = (double)box9[3]; g->tri[1] = (double)box9[6]; g->tri[2] = (double)box9[7];
-    g->nx = g->ny = g->nz = 1; g->ncells = 1;
-    g->tf = 1.0f;
     g->pbc = 2;
 }

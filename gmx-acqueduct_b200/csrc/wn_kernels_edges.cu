@@ -49,7 +49,7 @@ constexpr int WARPS_PER_CTA = 8;
 constexpr int HC   = 32;                 /* home sites per chunk (one hit-mask bit each)       */
 constexpr int HPUSH = 16;                /* hit-mask bits pushed per scan (20 measured slower: shared memory costs a CTA/SM) */
 constexpr int QCAP = 32 + 32 * HPUSH;    /* queue: < 32 carried + one push of <= 32*HPUSH codes */
-constexpr int MAXRUN = 10;               /* 5 rows, each possibly split by the periodic wrap in x */
+constexpr int MAXRUN = 12;               /* 5 rows (6 on a skewed z boundary), each possibly split by the periodic wrap in x */
 constexpr unsigned FULL = 0xffffffffu;
 
 /* fixed part of the per-warp shared memory (followed by HC*hs unit D-H vectors) */
@@ -215,7 +215,7 @@ wn_emit_edge(const WnEdgeParams& p, size_t fbase, int ia, int ib, float len_f, f
 }
 
 /* Exact geometry for `nb` queued codes (lane < nb active). */
-template <bool SIMPLE, bool PBC>
+template <bool SIMPLE, int PBC>
 __device__ __forceinline__ void
 wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const double* __restrict__ hdh,
               const WnGrid& g, int qbase, int nb, Counters& ct, int lane)
@@ -236,7 +236,7 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
         const double* dc = p.sdh + (fbase + c) * (size_t)p.hs * 4;
         uint32_t mh = 0, mc = 0;
         if (!SIMPLE) { mh = ws.hmeta[h]; mc = __ldg(p.smeta + fbase + c); }
-        r = wn_pair_geometry<SIMPLE, PBC ? 1 : 0>(a4, b4, dh, dc, mh, mc, g);
+        r = wn_pair_geometry<SIMPLE, PBC>(a4, b4, dh, dc, mh, mc, g);
     }
     ct.evals += __popc(__ballot_sync(FULL, r.counted));
     if (__any_sync(FULL, r.t_len || r.t_cos || r.t_pos0)) {          /* rare */
@@ -247,7 +247,10 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
     if (r.edge) wn_emit_edge(p, fbase, ih, ic, r.len_f, r.cosmax);
 }
 
-template <bool SIMPLE, bool PBC, int BX>
+/* floor division and modulo for possibly negative cell indices */
+__device__ __forceinline__ int wn_floordiv(int a, int n) { return (a >= 0) ? a / n : -((-a + n - 1) / n); }
+
+template <bool SIMPLE, int PBC, int BX>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WN_EDGES_MINBLOCKS)
 wn_k_edges(const WnEdgeParams p)
 {
@@ -288,7 +291,57 @@ wn_k_edges(const WnEdgeParams p)
      * A row that wraps in y or z keeps its cells and shifts the origin by -+Ly / -+Lz. */
     int rs = 0, rl = 0;
     float sox = orx, soy = ory, soz = orz;          /* origin to subtract from this run's sites */
-    if (lane < (PBC ? MAXRUN : 5)) {
+    if (PBC == 2) {
+        /* Triclinic box on its brick [0,ax) x [0,by) x [0,cz) (a fundamental domain of the
+         * lower-triangular lattice).  A neighbour row reached through the y (z) boundary is the
+         * image shifted by b (c), whose x (x and y) components are not multiples of the cell
+         * edge: the candidate ranges are the cells COVERING the shifted interval.  Which block
+         * owns a pair is still decided by dz, then dy, then dx of aligned quantities (c.z = nz
+         * cells, b.y = ny cells, a.x = nx cells), so every pair is seen exactly once.
+         * lanes 0,1: own row   2,3: row y+1   4..11: up to 4 rows of plane z+1; (even, odd) =
+         * the part of the x range before / after the periodic wrap. */
+        if (lane < MAXRUN) {
+            const double rc = WN_CELL_EDGE;
+            const double ex = g.L[0] / nx, ey = g.L[1] / ny;
+            const int part = lane & 1;
+            const int grp = lane < 2 ? 0 : (lane < 4 ? 1 : 2);
+            const int k = (grp == 2 && cz + 1 >= nz) ? 1 : 0;                    /* image shifted by +k*c */
+            const int z = (grp == 2) ? cz + 1 - k * nz : cz;
+            int ru, r_hi;
+            if (grp == 0) { ru = cy; r_hi = cy; }
+            else if (grp == 1) { ru = cy + 1; r_hi = cy + 1; }
+            else {
+                const double sh = (double)k * g.tri[2];                          /* k * cy */
+                const int r_lo = __double2int_rd((cy * ey - rc - sh) / ey);
+                r_hi = __double2int_rd(((cy + 1) * ey + rc - sh) / ey);
+                ru = r_lo + ((lane - 4) >> 1);
+            }
+            if (ru <= r_hi) {
+                const int jj = wn_floordiv(ru, ny);                              /* image shifted by +jj*b */
+                const int y = ru - jj * ny;
+                int c_lo, c_hi;
+                if (grp == 0) { c_lo = x0; c_hi = x1 + 1; }
+                else {
+                    const double sh = (double)jj * g.tri[0] + (double)k * g.tri[1];   /* jj*bx + k*cx */
+                    c_lo = __double2int_rd((x0 * ex - rc - sh) / ex);
+                    c_hi = __double2int_rd(((x1 + 1) * ex + rc - sh) / ex);
+                }
+                const int ii0 = wn_floordiv(c_lo, nx);
+                const int split = (ii0 + 1) * nx;                                /* first cell of the next image */
+                int a_ = c_lo, b_ = min(c_hi, split - 1), ii = ii0;
+                if (part == 1) { a_ = split; b_ = c_hi; ii = ii0 + 1; }
+                if (a_ <= b_) {
+                    const int rowc = (z * ny + y) * nx;
+                    rs = __ldg(cs_f + rowc + (a_ - ii * nx));
+                    rl = __ldg(cs_f + rowc + (b_ - ii * nx) + 1) - rs;
+                    /* image position = site + ii*a + jj*b + k*c; fold the shift into the origin */
+                    sox = orx - (float)((double)ii * g.L[0] + (double)jj * g.tri[0] + (double)k * g.tri[1]);
+                    soy = ory - (float)((double)jj * g.L[1] + (double)k * g.tri[2]);
+                    soz = orz - (float)((double)k * g.L[2]);
+                }
+            }
+        }
+    } else if (lane < (PBC ? 10 : 5)) {
         const int row = lane % 5, part = lane / 5;
         int y = (row == 0) ? cy : (row == 1 ? cy + 1 : cy + row - 3);
         int z = (row < 2) ? cz : cz + 1;
@@ -599,7 +652,7 @@ size_t wn_edges_smem_bytes(int hs)
 }
 
 namespace {
-template <bool SIMPLE, bool PBC, int BX>
+template <bool SIMPLE, int PBC, int BX>
 void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
     const size_t smem = wn_edges_smem_bytes(p.hs);
@@ -612,16 +665,20 @@ void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 
 void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
-    const int key = (p.simple ? 4 : 0) | (p.pbc ? 2 : 0) | (p.bx == 2 ? 1 : 0);
+    const int key = (p.simple ? 6 : 0) + p.pbc * 2 + (p.bx == 2 ? 1 : 0);
     switch (key) {
-    case 0: launch_variant<false, false, 1>(p, n_frames, st); break;
-    case 1: launch_variant<false, false, 2>(p, n_frames, st); break;
-    case 2: launch_variant<false, true, 1>(p, n_frames, st); break;
-    case 3: launch_variant<false, true, 2>(p, n_frames, st); break;
-    case 4: launch_variant<true, false, 1>(p, n_frames, st); break;
-    case 5: launch_variant<true, false, 2>(p, n_frames, st); break;
-    case 6: launch_variant<true, true, 1>(p, n_frames, st); break;
-    default: launch_variant<true, true, 2>(p, n_frames, st); break;
+    case 0: launch_variant<false, 0, 1>(p, n_frames, st); break;
+    case 1: launch_variant<false, 0, 2>(p, n_frames, st); break;
+    case 2: launch_variant<false, 1, 1>(p, n_frames, st); break;
+    case 3: launch_variant<false, 1, 2>(p, n_frames, st); break;
+    case 4: launch_variant<false, 2, 1>(p, n_frames, st); break;
+    case 5: launch_variant<false, 2, 2>(p, n_frames, st); break;
+    case 6: launch_variant<true, 0, 1>(p, n_frames, st); break;
+    case 7: launch_variant<true, 0, 2>(p, n_frames, st); break;
+    case 8: launch_variant<true, 1, 1>(p, n_frames, st); break;
+    case 9: launch_variant<true, 1, 2>(p, n_frames, st); break;
+    case 10: launch_variant<true, 2, 1>(p, n_frames, st); break;
+    default: launch_variant<true, 2, 2>(p, n_frames, st); break;
     }
 }
 

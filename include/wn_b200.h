@@ -140,8 +140,8 @@ int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit
  *   min image:   k = rint(d.z/cz): d -= k*c;  j = rint(d.y/by): d -= j*b;  i = rint(d.x/ax): d.x -= i*ax
  * (the shortest image whenever the cutoff is small against the box, as GROMACS assumes).  A call
  * whose frames are all rectangular uses the rectangular definition above; one with any
- * triclinic frame uses the triclinic formulas for every frame.  Triclinic frames currently
- * run the all-pairs kernel (O(N^2) per frame); the cell-list sweep covers rectangular boxes. */
+ * triclinic frame uses the triclinic formulas for every frame.  Both run the cell-list sweep
+ * (boxes with fewer than 3-4 cells of 0.65 nm in a dimension use an all-pairs kernel). */
 int wn_find_pairs_pbc(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
                       const float box[3], const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
 

@@ -671,3 +671,32 @@ def test_energy_parameters_and_hydrogenless_tables(ctx, oracle):
     assert r0["n_edges"] == 0 and r0["n_pair_evals"] == 0
     want, st, npairs, ev = oracle.frame_hbonds(frames[0], site_atom, -np.ones((n, 1), np.int32), np.full(n, oracle.WATER, np.uint8))
     assert len(want) == 0 and ev == 0 and npairs > 0
+
+
+@pytest.mark.parametrize("n,scale,nf", [(4000, 1.0, 2),      # 7 x 7 x 6 cells: 2-cell home blocks
+                                        (1400, 0.82, 3)])    # 4 x 4 x 4 cells: 1-cell home blocks, every block wraps
+def test_triclinic_cell_sweep(ctx, oracle, n, scale, nf):
+    """Triclinic boxes large enough for the cell-list sweep (shifted neighbour rows across the y
+    and z boundaries), heavily skewed (|bx|, |cx| ~ ax/2, |cy| ~ by/2), molecules displaced by
+    lattice vectors; bit-exact vs the triclinic oracle."""
+    rng = np.random.default_rng(23 + n)
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 2, nf).copy()
+    L = float(box.box) * scale
+    boxes9 = np.zeros((nf, 9), np.float32)
+    for f in range(nf):
+        boxes9[f] = [L, 0, 0, (0.45 - 0.9 * (f % 2)) * L, 0.97 * L, 0, -0.48 * L, 0.46 * L, 0.93 * L + 0.02 * f]
+        B = boxes9[f].reshape(3, 3).astype(np.float64)
+        shift = rng.integers(-1, 2, size=(n, 3)) @ B
+        for a in range(3):
+            frames[f, a::3] += shift.astype(np.float32)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames, boxes=boxes9)
+    edges, stats, evals = [], [], 0
+    ties = oracle.Ties()
+    for f in range(nf):
+        e, s, _, ev = oracle.frame_hbonds_tric(frames[f], sa, ha, ty, boxes9[f], ties=ties)
+        edges.append(e); stats.append(s); evals += ev
+    compare_batch(res, edges, np.array(stats), evals, ties.as_dict())
+    assert res["n_edges"] > 10 * n
