@@ -700,3 +700,48 @@ def test_triclinic_cell_sweep(ctx, oracle, n, scale, nf):
         edges.append(e); stats.append(s); evals += ev
     compare_batch(res, edges, np.array(stats), evals, ties.as_dict())
     assert res["n_edges"] > 10 * n
+
+
+def test_randomised_triclinic_systems(ctx, oracle):
+    """30 seeded random triclinic systems: box sizes from one cell to ~10 cells per dimension,
+    skews up to +-0.7 of the diagonal elements (beyond what GROMACS itself allows), random tables,
+    row limits, unwrapped coordinates.  Exercises the all-pairs kernel, 1- and 2-cell home blocks."""
+    rng = np.random.default_rng(777)
+    for trial in range(30):
+        n_sites = int(rng.integers(1, 500))
+        nf = int(rng.integers(1, 3))
+        natoms = 4 * n_sites
+        site_atom = (np.arange(n_sites) * 4).astype(np.int32)
+        h_atom = -np.ones((n_sites, 3), np.int32)
+        nh = rng.integers(0, 4, size=n_sites)
+        for s in range(n_sites):
+            for k in range(nh[s]):
+                h_atom[s, k] = site_atom[s] + 1 + k
+            if rng.random() < 0.3:
+                h_atom[s] = [site_atom[s], site_atom[s] + 1, -1]
+        site_type = rng.integers(0, 3, size=n_sites).astype(np.uint8) if rng.random() < 0.7 else np.full(n_sites, oracle.WATER, np.uint8)
+        side = float(rng.choice([0.8, 1.5, 2.7, 3.4, 4.2, 6.6]))
+        boxes9 = np.zeros((nf, 9), np.float32)
+        frames = np.zeros((nf, natoms, 3), np.float32)
+        for f in range(nf):
+            ax, by, cz = side * rng.uniform(0.9, 1.3, size=3)
+            boxes9[f] = [ax, 0, 0, rng.uniform(-0.7, 0.7) * ax, by, 0, rng.uniform(-0.7, 0.7) * ax, rng.uniform(-0.7, 0.7) * by, cz]
+            B = boxes9[f].reshape(3, 3).astype(np.float64)
+            pos = rng.uniform(0, 1, size=(n_sites, 3)) @ B + rng.integers(-1, 2, size=(n_sites, 3)) @ B
+            frames[f, 0::4] = pos
+            for k in range(3):
+                d = rng.normal(size=(n_sites, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+                frames[f, 1 + k::4] = pos + 0.1 * d
+        first_limit = None if rng.random() < 0.6 else int(rng.integers(0, n_sites + 1))
+        ctx.set_sites(site_atom, h_atom, site_type, first_limit=first_limit)
+        res = ctx.hbond_batch(frames, boxes=boxes9)
+        edges, stats, evals = [], [], 0
+        ties = oracle.Ties()
+        for f in range(nf):
+            e, s, _, ev = oracle.frame_hbonds_tric(frames[f], site_atom, h_atom, site_type, boxes9[f],
+                                                   first_limit=first_limit, ties=ties)
+            edges.append(e); stats.append(s); evals += ev
+        try:
+            compare_batch(res, edges, np.array(stats), evals, ties.as_dict())
+        except AssertionError as err:
+            raise AssertionError("trial %d (n=%d, side=%.1f, box=%s): %s" % (trial, n_sites, side, boxes9[0], err))
