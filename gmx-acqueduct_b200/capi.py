@@ -25,7 +25,7 @@ assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
 # every symbol include/wn_b200.h declares
 SYMBOLS = [
     "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_find_pairs_pbc",
-    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_hbond_batch_box9", "wn_find_pairs_box9", "wn_format_edges", "wn_set_sites",
+    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_hbond_batch_ex", "wn_hbond_batch_box9", "wn_find_pairs_box9", "wn_format_edges", "wn_set_sites",
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
@@ -47,6 +47,12 @@ class BatchResult(C.Structure):
                 ("n_edges", C.c_uint64), ("n_pair_evals", C.c_uint64), ("ties", TieReport),
                 ("n_frames", C.c_int32), ("on_device", C.c_int32),
                 ("row_offsets", C.c_void_p), ("n_sites", C.c_int32), ("reserved", C.c_int32)]
+
+
+class BatchArgs(C.Structure):
+    _fields_ = [("frames", C.c_void_p), ("frames_on_device", C.c_int32), ("n_frames", C.c_int32),
+                ("natoms", C.c_int32), ("box_stride", C.c_int32), ("boxes", C.c_void_p),
+                ("subset_offsets", C.c_void_p), ("subset_sites", C.c_void_p)]
 
 
 class Timings(C.Structure):
@@ -89,6 +95,7 @@ def load():
     L.wn_hbond_batch_pbc.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_hbond_batch_pbc_dev.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_hbond_batch_subset.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(BatchResult)]
+    L.wn_hbond_batch_ex.argtypes = [vp, C.POINTER(BatchArgs), C.POINTER(BatchResult)]
     L.wn_hbond_batch_box9.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_find_pairs_box9.argtypes = [vp, vp, i32, i32, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(TieReport)]
     L.wn_format_edges.argtypes = [vp, vp, vp, i32, C.POINTER(vp), C.POINTER(u64)]
@@ -254,6 +261,28 @@ class Context:
         res = BatchResult()
         self._ck(self.L.wn_hbond_batch_subset(self.h, frames.ctypes.data, bptr, nf, natoms, off.ctypes.data,
                                               sites.ctypes.data if len(sites) else None, C.byref(res)))
+        return self._wrap(res, True)
+
+    def hbond_batch_ex(self, frames, n_frames=None, natoms=None, on_device=False, boxes=None,
+                       subset_offsets=None, subset_sites=None):
+        """General form (wn_hbond_batch_ex): host array or device pointer, open / (L) / matrix boxes,
+        optional per-frame site lists."""
+        a = BatchArgs()
+        keep = []
+        if on_device:
+            a.frames, a.n_frames, a.natoms, a.frames_on_device = frames, n_frames, natoms, 1
+        else:
+            frames = np.ascontiguousarray(frames, dtype=np.float32); keep.append(frames)
+            a.frames, a.n_frames, a.natoms, a.frames_on_device = frames.ctypes.data, frames.shape[0], frames.shape[1], 0
+        if boxes is not None:
+            boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(a.n_frames, -1); keep.append(boxes)
+            a.box_stride, a.boxes = boxes.shape[1], boxes.ctypes.data
+        if subset_offsets is not None:
+            off = np.ascontiguousarray(subset_offsets, dtype=np.int64); keep.append(off)
+            sites = np.ascontiguousarray(subset_sites, dtype=np.int32); keep.append(sites)
+            a.subset_offsets, a.subset_sites = off.ctypes.data, (sites.ctypes.data if len(sites) else None)
+        res = BatchResult()
+        self._ck(self.L.wn_hbond_batch_ex(self.h, C.byref(a), C.byref(res)))
         return self._wrap(res, True)
 
     def hbond_batch_dev(self, frames_dev, n_frames, natoms, boxes=None):

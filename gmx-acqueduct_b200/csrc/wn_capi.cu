@@ -700,80 +700,112 @@ int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass)
     return WN_OK;
 }
 
-int wn_hbond_batch(wn_ctx* ctx, const float* frames_host, int32_t n_frames, int32_t natoms,
-                   wn_batch_result* out)
-{
-    return batch_common(ctx, frames_host, nullptr, true, n_frames, natoms, out);
-}
-
-int wn_hbond_batch_subset(wn_ctx* ctx, const float* frames_host, const float* boxes_host, int32_t n_frames,
-                          int32_t natoms, const int64_t* subset_offsets, const int32_t* subset_sites,
-                          wn_batch_result* out)
+int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* a, wn_batch_result* out)
 {
     if (!ctx) return WN_ERR_BAD_ARG;
-    if (n_frames < 0 || (n_frames > 0 && !subset_offsets))
-        return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: subset_offsets is NULL");
-    if (ctx->n_sites < 0) return fail(ctx, WN_ERR_NO_SITES, "wn_hbond_batch_subset: call wn_set_sites first");
-    for (int f = 0; f < n_frames; ++f) {
-        const int64_t a = subset_offsets[f], b = subset_offsets[f + 1];
-        if (a < 0 || b < a || b - a > (int64_t)ctx->n_sites)
-            return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: offsets must ascend, at most n_sites entries per frame");
+    if (!a || !out) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: NULL argument");
+    const int nf = a->n_frames;
+    if (a->box_stride != 0 && a->box_stride != 3 && a->box_stride != 9)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: box_stride must be 0, 3 or 9");
+    if (a->box_stride != 0 && !a->boxes && nf > 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: boxes is NULL");
+    /* per-frame site lists */
+    if (a->subset_offsets) {
+        if (ctx->n_sites < 0) return fail(ctx, WN_ERR_NO_SITES, "wn_hbond_batch_ex: call wn_set_sites first");
+        for (int f = 0; f < nf; ++f) {
+            const int64_t lo = a->subset_offsets[f], hi = a->subset_offsets[f + 1];
+            if (lo < 0 || hi < lo || hi - lo > (int64_t)ctx->n_sites)
+                return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: subset offsets must ascend, at most n_sites entries per frame");
+        }
+        const int64_t total = nf > 0 ? a->subset_offsets[nf] : 0;
+        if (total > 0 && !a->subset_sites) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: subset_sites is NULL");
+        for (int64_t k = nf > 0 ? a->subset_offsets[0] : 0; k < total; ++k)
+            if (a->subset_sites[k] < 0 || a->subset_sites[k] >= ctx->n_sites)
+                return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: site index outside the site table");
     }
-    const int64_t total = n_frames > 0 ? subset_offsets[n_frames] : 0;
-    if (total > 0 && !subset_sites) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: subset_sites is NULL");
-    for (int64_t k = n_frames > 0 ? subset_offsets[0] : 0; k < total; ++k)
-        if (subset_sites[k] < 0 || subset_sites[k] >= ctx->n_sites)
-            return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: site index outside the site table");
-    ctx->sub_off_host = subset_offsets;
-    ctx->sub_sites_host = subset_sites;
-    const int rc = batch_common(ctx, frames_host, boxes_host, true, n_frames, natoms, out);
+    /* a matrix batch whose frames are all rectangular uses the rectangular definition and grid */
+    const float* boxes = a->box_stride ? a->boxes : nullptr;
+    int stride = a->box_stride == 9 ? 9 : 3;
+    std::vector<float> b3;
+    if (a->box_stride == 9) {
+        bool rectangular = true;
+        for (int f = 0; f < nf && rectangular; ++f) {
+            const float* b = a->boxes + 9 * (size_t)f;
+            if (b[1] != 0.f || b[2] != 0.f || b[3] != 0.f || b[5] != 0.f || b[6] != 0.f || b[7] != 0.f) rectangular = false;
+        }
+        if (rectangular) {
+            b3.resize((size_t)nf * 3);
+            for (int f = 0; f < nf; ++f) {
+                b3[3 * (size_t)f] = a->boxes[9 * (size_t)f]; b3[3 * (size_t)f + 1] = a->boxes[9 * (size_t)f + 4];
+                b3[3 * (size_t)f + 2] = a->boxes[9 * (size_t)f + 8];
+            }
+            boxes = b3.data();
+            stride = 3;
+        }
+    }
+    ctx->box_stride = stride;
+    ctx->sub_off_host = a->subset_offsets;
+    ctx->sub_sites_host = a->subset_offsets ? a->subset_sites : nullptr;
+    const int rc = batch_common(ctx, a->frames, boxes, a->frames_on_device == 0, nf, a->natoms, out);
+    ctx->box_stride = 3;
     ctx->sub_off_host = nullptr;
     ctx->sub_sites_host = nullptr;
     return rc;
 }
 
-int wn_hbond_batch_box9(wn_ctx* ctx, const float* frames_host, const float* boxes9_host, int32_t n_frames,
-                        int32_t natoms, wn_batch_result* out)
+static wn_batch_args make_args(const float* frames, int on_device, int32_t n_frames, int32_t natoms, int stride,
+                               const float* boxes, const int64_t* so, const int32_t* ss)
 {
-    if (!ctx) return WN_ERR_BAD_ARG;
-    if (!boxes9_host && n_frames > 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_box9: boxes is NULL");
-    bool rectangular = true;
-    for (int f = 0; f < n_frames && rectangular; ++f) {
-        const float* b = boxes9_host + 9 * (size_t)f;
-        if (b[1] != 0.f || b[2] != 0.f || b[3] != 0.f || b[5] != 0.f || b[6] != 0.f || b[7] != 0.f) rectangular = false;
-    }
-    if (rectangular) {              /* every frame rectangular: the rectangular definition and the cell sweep */
-        std::vector<float> b3((size_t)n_frames * 3);
-        for (int f = 0; f < n_frames; ++f) {
-            b3[3 * (size_t)f] = boxes9_host[9 * (size_t)f]; b3[3 * (size_t)f + 1] = boxes9_host[9 * (size_t)f + 4];
-            b3[3 * (size_t)f + 2] = boxes9_host[9 * (size_t)f + 8];
-        }
-        return batch_common(ctx, frames_host, b3.data(), true, n_frames, natoms, out);
-    }
-    ctx->box_stride = 9;
-    const int rc = batch_common(ctx, frames_host, boxes9_host, true, n_frames, natoms, out);
-    ctx->box_stride = 3;
-    return rc;
+    wn_batch_args a;
+    a.frames = frames; a.frames_on_device = on_device; a.n_frames = n_frames; a.natoms = natoms;
+    a.box_stride = stride; a.boxes = boxes; a.subset_offsets = so; a.subset_sites = ss;
+    return a;
+}
+
+int wn_hbond_batch(wn_ctx* ctx, const float* frames_host, int32_t n_frames, int32_t natoms, wn_batch_result* out)
+{
+    const wn_batch_args a = make_args(frames_host, 0, n_frames, natoms, 0, nullptr, nullptr, nullptr);
+    return wn_hbond_batch_ex(ctx, &a, out);
+}
+
+int wn_hbond_batch_dev(wn_ctx* ctx, const float* frames_dev, int32_t n_frames, int32_t natoms, wn_batch_result* out)
+{
+    const wn_batch_args a = make_args(frames_dev, 1, n_frames, natoms, 0, nullptr, nullptr, nullptr);
+    return wn_hbond_batch_ex(ctx, &a, out);
 }
 
 int wn_hbond_batch_pbc(wn_ctx* ctx, const float* frames_host, const float* boxes_host, int32_t n_frames,
                        int32_t natoms, wn_batch_result* out)
 {
     if (ctx && !boxes_host && n_frames > 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_pbc: boxes is NULL");
-    return batch_common(ctx, frames_host, boxes_host, true, n_frames, natoms, out);
+    const wn_batch_args a = make_args(frames_host, 0, n_frames, natoms, 3, boxes_host, nullptr, nullptr);
+    return wn_hbond_batch_ex(ctx, &a, out);
 }
 
 int wn_hbond_batch_pbc_dev(wn_ctx* ctx, const float* frames_dev, const float* boxes_host, int32_t n_frames,
                            int32_t natoms, wn_batch_result* out)
 {
     if (ctx && !boxes_host && n_frames > 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_pbc_dev: boxes is NULL");
-    return batch_common(ctx, frames_dev, boxes_host, false, n_frames, natoms, out);
+    const wn_batch_args a = make_args(frames_dev, 1, n_frames, natoms, 3, boxes_host, nullptr, nullptr);
+    return wn_hbond_batch_ex(ctx, &a, out);
 }
 
-int wn_hbond_batch_dev(wn_ctx* ctx, const float* frames_dev, int32_t n_frames, int32_t natoms,
-                       wn_batch_result* out)
+int wn_hbond_batch_box9(wn_ctx* ctx, const float* frames_host, const float* boxes9_host, int32_t n_frames,
+                        int32_t natoms, wn_batch_result* out)
 {
-    return batch_common(ctx, frames_dev, nullptr, false, n_frames, natoms, out);
+    if (ctx && !boxes9_host && n_frames > 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_box9: boxes is NULL");
+    const wn_batch_args a = make_args(frames_host, 0, n_frames, natoms, 9, boxes9_host, nullptr, nullptr);
+    return wn_hbond_batch_ex(ctx, &a, out);
+}
+
+int wn_hbond_batch_subset(wn_ctx* ctx, const float* frames_host, const float* boxes_host, int32_t n_frames,
+                          int32_t natoms, const int64_t* subset_offsets, const int32_t* subset_sites,
+                          wn_batch_result* out)
+{
+    if (ctx && n_frames > 0 && !subset_offsets)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_subset: subset_offsets is NULL");
+    const wn_batch_args a = make_args(frames_host, 0, n_frames, natoms, boxes_host ? 3 : 0, boxes_host, subset_offsets,
+                                      subset_sites);
+    return wn_hbond_batch_ex(ctx, &a, out);
 }
 
 int wn_get_timings(wn_ctx* ctx, wn_timings* out)

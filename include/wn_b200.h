@@ -197,6 +197,20 @@ int wn_hbond_batch_box9(wn_ctx* ctx, const float* frames_host, const float* boxe
 int wn_hbond_batch_subset(wn_ctx* ctx, const float* frames_host, const float* boxes_host,
                           int32_t n_frames, int32_t natoms, const int64_t* subset_offsets,
                           const int32_t* subset_sites, wn_batch_result* out);
+/* The general form: every combination of the options above in one call.  The other
+ * wn_hbond_batch* entry points are shorthands for it. */
+typedef struct wn_batch_args {
+    const float*   frames;          /* [n_frames][natoms][3] float32                               */
+    int32_t        frames_on_device;/* 0: host memory (results to pinned host); 1: device memory    */
+    int32_t        n_frames;
+    int32_t        natoms;
+    int32_t        box_stride;      /* 0: open boundary; 3: boxes = (Lx,Ly,Lz); 9: GROMACS matrices  */
+    const float*   boxes;           /* host, [n_frames][box_stride]; NULL iff box_stride == 0        */
+    const int64_t* subset_offsets;  /* host, [n_frames+1], or NULL: every frame uses the whole table */
+    const int32_t* subset_sites;    /* host, rows of the site table                                  */
+} wn_batch_args;
+int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* args, wn_batch_result* out);
+
 /* Frames that one wn_hbond_batch* call processes per kernel pipeline pass
  * (larger inputs are split internally).  0 restores the default heuristic. */
 int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);

@@ -745,3 +745,30 @@ def test_randomised_triclinic_systems(ctx, oracle):
             compare_batch(res, edges, np.array(stats), evals, ties.as_dict())
         except AssertionError as err:
             raise AssertionError("trial %d (n=%d, side=%.1f, box=%s): %s" % (trial, n_sites, side, boxes9[0], err))
+
+
+def test_general_entry_point_combinations(ctx, oracle):
+    """wn_hbond_batch_ex: device-resident frames + triclinic matrices + per-frame site lists in one
+    call, against the oracle on the gathered tables."""
+    rng = np.random.default_rng(5)
+    n, nf = 1500, 3
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 0, nf)
+    L = float(box.box)
+    b9 = np.tile(np.array([L, 0, 0, 0.3 * L, L, 0, -0.2 * L, 0.25 * L, L], np.float32), (nf, 1))
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    lists, off = [], [0]
+    for f in range(nf):
+        lst = np.sort(rng.choice(n, size=int(rng.integers(300, 1200)), replace=False)).astype(np.int32)
+        lists.append(lst); off.append(off[-1] + len(lst))
+    d = ctx.dev_alloc(frames.nbytes)
+    ctx.h2d(d, frames)
+    out = ctx.hbond_batch_ex(d, nf, 3 * n, on_device=True, boxes=b9, subset_offsets=off, subset_sites=np.concatenate(lists))
+    e, fo, st = ctx.fetch_dev_result(out)
+    ctx.dev_free(d)
+    for f in range(nf):
+        lst = lists[f]
+        want, s, _, ev = oracle.frame_hbonds_tric(frames[f], sa[lst], ha[lst], ty[lst], b9[f])
+        check_edges(e[int(fo[f]):int(fo[f + 1])], want)
+        assert st["num_sites"][f] == len(lst) and int(st["pair_evals"][f]) == ev
