@@ -414,16 +414,17 @@ def run_own(args):
     # D2H of pass k-1 under the kernels of pass k), so give it several passes per step
     e2e_pass = max(F // 5, 1)
     ctx.set_batch_frames(e2e_pass)
+    e2e_layout = capi.LAYOUT_CSR16          # 16 bytes per edge over PCIe (row index via the CSR offsets)
     for s in range(min(W, 2)):
-        ctx.hbond_batch((host_ptr + (s % ring) * F * frame_bytes, F, natoms), copy=False)
+        ctx.hbond_batch_ex(None, F, natoms, host_ptr=host_ptr + (s % ring) * F * frame_bytes, layout=e2e_layout, copy=False)
     barrier()
     ctx.timer_start()
     e2e_t0 = time.perf_counter()
     d2h_bytes = 0
     e2e_launches = 0
     for s in range(K):
-        res = ctx.hbond_batch((host_ptr + (s % ring) * F * frame_bytes, F, natoms), copy=False)
-        d2h_bytes += res["n_edges"] * 20 + (F + 1) * 8 + F * 40
+        res = ctx.hbond_batch_ex(None, F, natoms, host_ptr=host_ptr + (s % ring) * F * frame_bytes, layout=e2e_layout, copy=False)
+        d2h_bytes += res["n_edges"] * 16 + (F + 1) * 8 + F * 40 + F * n_waters * 4
         e2e_launches += ctx.timings()["launches"]
         # the step's result is read on the host: total edge count of the last frame
         _ = int(res["frame_offsets"][-1])
@@ -493,7 +494,8 @@ def run_own(args):
             "wall_ms_per_step": (t1 - t0) * 1e3 / K,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes,
                     "d2h_bytes_per_step": d2h_bytes / K, "host_ring_batches": ring,
-                    "frames_per_internal_pass": e2e_pass},
+                    "frames_per_internal_pass": e2e_pass,
+                    "result_layout": "WN_LAYOUT_CSR16 (16 B/edge + 4 B/site row offsets; wn_edge AoS is 20 B/edge)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,

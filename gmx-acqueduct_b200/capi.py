@@ -18,6 +18,8 @@ MODEL_TIP3P, MODEL_SPC = 0, 1
 
 EDGE_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("energy", "<f4"),
                        ("length", "<f4"), ("cosine", "<f4")])
+EDGE16_DTYPE = np.dtype([("j", "<i4"), ("energy", "<f4"), ("length", "<f4"), ("cosine", "<f4")])
+LAYOUT_EDGES, LAYOUT_CSR16 = 0, 1
 STATS_DTYPE = np.dtype([("num_sites", "<f8"), ("num_edges", "<f8"), ("ratio", "<f8"),
                         ("sum_energy", "<f8"), ("pair_evals", "<f8")])
 assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
@@ -46,13 +48,14 @@ class BatchResult(C.Structure):
     _fields_ = [("edges", C.c_void_p), ("frame_offsets", C.c_void_p), ("stats", C.c_void_p),
                 ("n_edges", C.c_uint64), ("n_pair_evals", C.c_uint64), ("ties", TieReport),
                 ("n_frames", C.c_int32), ("on_device", C.c_int32),
-                ("row_offsets", C.c_void_p), ("n_sites", C.c_int32), ("reserved", C.c_int32)]
+                ("row_offsets", C.c_void_p), ("n_sites", C.c_int32), ("layout", C.c_int32)]
 
 
 class BatchArgs(C.Structure):
     _fields_ = [("frames", C.c_void_p), ("frames_on_device", C.c_int32), ("n_frames", C.c_int32),
                 ("natoms", C.c_int32), ("box_stride", C.c_int32), ("boxes", C.c_void_p),
-                ("subset_offsets", C.c_void_p), ("subset_sites", C.c_void_p)]
+                ("subset_offsets", C.c_void_p), ("subset_sites", C.c_void_p),
+                ("result_layout", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Timings(C.Structure):
@@ -205,6 +208,8 @@ class Context:
         out = {"n_edges": ne, "n_pair_evals": int(res.n_pair_evals), "ties": res.ties.as_dict(),
                "n_frames": nf}
         out["n_sites"] = res.n_sites
+        out["layout"] = res.layout
+        edt = EDGE16_DTYPE if res.layout == LAYOUT_CSR16 else EDGE_DTYPE
         if res.on_device:
             out["edges_dev"] = res.edges
             out["frame_offsets_dev"] = res.frame_offsets
@@ -212,9 +217,9 @@ class Context:
             out["row_offsets_dev"] = res.row_offsets
             return out
         if ne:
-            e = np.frombuffer((C.c_char * (ne * 20)).from_address(res.edges), dtype=EDGE_DTYPE)
+            e = np.frombuffer((C.c_char * (ne * edt.itemsize)).from_address(res.edges), dtype=edt)
         else:
-            e = np.zeros(0, EDGE_DTYPE)
+            e = np.zeros(0, edt)
         fo = np.frombuffer((C.c_uint64 * (nf + 1)).from_address(res.frame_offsets), dtype=np.uint64)
         st = np.frombuffer((C.c_char * (nf * 40)).from_address(res.stats), dtype=STATS_DTYPE) if nf else \
             np.zeros(0, STATS_DTYPE)
@@ -264,13 +269,16 @@ class Context:
         return self._wrap(res, True)
 
     def hbond_batch_ex(self, frames, n_frames=None, natoms=None, on_device=False, boxes=None,
-                       subset_offsets=None, subset_sites=None):
+                       subset_offsets=None, subset_sites=None, layout=LAYOUT_EDGES, copy=True, host_ptr=None):
         """General form (wn_hbond_batch_ex): host array or device pointer, open / (L) / matrix boxes,
         optional per-frame site lists."""
         a = BatchArgs()
         keep = []
+        a.result_layout = layout
         if on_device:
             a.frames, a.n_frames, a.natoms, a.frames_on_device = frames, n_frames, natoms, 1
+        elif host_ptr is not None:
+            a.frames, a.n_frames, a.natoms, a.frames_on_device = host_ptr, n_frames, natoms, 0
         else:
             frames = np.ascontiguousarray(frames, dtype=np.float32); keep.append(frames)
             a.frames, a.n_frames, a.natoms, a.frames_on_device = frames.ctypes.data, frames.shape[0], frames.shape[1], 0
@@ -283,7 +291,7 @@ class Context:
             a.subset_offsets, a.subset_sites = off.ctypes.data, (sites.ctypes.data if len(sites) else None)
         res = BatchResult()
         self._ck(self.L.wn_hbond_batch_ex(self.h, C.byref(a), C.byref(res)))
-        return self._wrap(res, True)
+        return self._wrap(res, copy)
 
     def hbond_batch_dev(self, frames_dev, n_frames, natoms, boxes=None):
         res = BatchResult()
@@ -298,7 +306,7 @@ class Context:
     def fetch_dev_result(self, out):
         """Copy a device-resident batch result to numpy arrays."""
         nf, ne = out["n_frames"], out["n_edges"]
-        e = np.zeros(ne, EDGE_DTYPE)
+        e = np.zeros(ne, EDGE16_DTYPE if out.get("layout") == LAYOUT_CSR16 else EDGE_DTYPE)
         fo = np.zeros(nf + 1, np.uint64)
         st = np.zeros(nf, STATS_DTYPE)
         if ne:

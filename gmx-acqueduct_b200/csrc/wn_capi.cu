@@ -104,6 +104,7 @@ struct wn_ctx {
     unsigned long long* d_pair_ties = nullptr;
 
     std::vector<WnGrid> h_grid;     /* periodic grids of the current pass (host-built) */
+    int layout = 0;                          /* result layout of the current / last call */
     int box_stride = 3;                      /* 3: (Lx,Ly,Lz) per frame; 9: triclinic matrices */
     const int64_t* sub_off_host = nullptr;   /* per-frame site subsets of the current call (host) */
     const int32_t* sub_sites_host = nullptr;
@@ -383,7 +384,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
 
     int n_blocks = 0;
     wn_launch_copy(ctx->d_rowbuf, ctx->row_cap, ctx->d_row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0,
-                   nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->d_block_sums, &n_blocks, st);
+                   nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->layout, ctx->d_block_sums, &n_blocks, st);
     wn_launch_stats(ctx->d_block_sums, n_blocks, ctx->d_frame_total, ctx->d_counters, nf, N, sub,
                     ctx->d_stats + f0, st);
     WN_CK(cudaMemcpyAsync(ctx->d_counters_all + f0, ctx->d_counters, (size_t)nf * sizeof(WnFrameCounters),
@@ -437,6 +438,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
         out->on_device = host_in ? 0 : 1;
         out->row_offsets = host_in ? ctx->h_row_off : ctx->d_row_off;
         out->n_sites = N;
+        out->layout = ctx->layout;
         return WN_OK;
     }
 
@@ -477,8 +479,13 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
             }
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 2], ctx->st_d2h));
             if (edge_base > before)
-                WN_CK(cudaMemcpyAsync(ctx->h_edges + before, ctx->d_edges + before,
-                                      (size_t)(edge_base - before) * sizeof(wn_edge), cudaMemcpyDeviceToHost, ctx->st_d2h));
+            {
+                /* 20-byte wn_edge records, or 16-byte wn_edge16 records in the same buffers */
+                const size_t esz = ctx->layout == WN_LAYOUT_CSR16 ? sizeof(wn_edge16) : sizeof(wn_edge);
+                WN_CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_edges) + (size_t)before * esz,
+                                      reinterpret_cast<const char*>(ctx->d_edges) + (size_t)before * esz,
+                                      (size_t)(edge_base - before) * esz, cudaMemcpyDeviceToHost, ctx->st_d2h));
+            }
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 3], ctx->st_d2h));
         }
         WN_CK(cudaStreamSynchronize(ctx->st_d2h));
@@ -522,6 +529,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     ctx->last_edges = edge_base;
     out->row_offsets = host_in ? ctx->h_row_off : ctx->d_row_off;
     out->n_sites = N;
+    out->layout = ctx->layout;
     out->n_edges = edge_base;
     out->n_pair_evals = evals;
     out->ties = ties;
@@ -742,6 +750,9 @@ int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* a, wn_batch_result* out)
             stride = 3;
         }
     }
+    if (a->result_layout != WN_LAYOUT_EDGES && a->result_layout != WN_LAYOUT_CSR16)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: unknown result_layout");
+    ctx->layout = a->result_layout;
     ctx->box_stride = stride;
     ctx->sub_off_host = a->subset_offsets;
     ctx->sub_sites_host = a->subset_offsets ? a->subset_sites : nullptr;
@@ -758,6 +769,7 @@ static wn_batch_args make_args(const float* frames, int on_device, int32_t n_fra
     wn_batch_args a;
     a.frames = frames; a.frames_on_device = on_device; a.n_frames = n_frames; a.natoms = natoms;
     a.box_stride = stride; a.boxes = boxes; a.subset_offsets = so; a.subset_sites = ss;
+    a.result_layout = WN_LAYOUT_EDGES; a.reserved = 0;
     return a;
 }
 
@@ -1012,6 +1024,7 @@ int wn_format_edges(wn_ctx* ctx, const int32_t* frame_numbers, const uint32_t* s
     if (!ctx || !text || !text_bytes) return WN_ERR_BAD_ARG;
     *text = nullptr; *text_bytes = 0;
     if (ctx->last_frames < 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: no batch result to format");
+    if (ctx->layout != WN_LAYOUT_EDGES) return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: needs a WN_LAYOUT_EDGES result");
     const int F = ctx->last_frames;
     if (F > 0 && !frame_numbers) return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: frame_numbers is NULL");
     if (site_ids && n_site_ids < ctx->n_sites)

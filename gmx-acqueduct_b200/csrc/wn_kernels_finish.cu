@@ -125,6 +125,7 @@ wn_k_frameoff(const unsigned long long* __restrict__ frame_total, const uint32_t
 #ifndef WN_COPY_MINBLOCKS
 #define WN_COPY_MINBLOCKS 8
 #endif
+template <bool CSR16>
 __global__ void __launch_bounds__(COPY_THREADS, WN_COPY_MINBLOCKS)
 wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
           const uint32_t* __restrict__ row_cnt, const uint32_t* __restrict__ row_off,
@@ -172,20 +173,25 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
                 /* rank inside the row by j */
                 uint32_t rank = 0;
                 for (uint32_t k = 0; k < rcnt; ++k) rank += ((int)rowp[k].x < tj) ? 1u : 0u;
-                wn_edge out;
-                out.i = irow;
-                out.j = tj;
                 /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
-                out.energy = __double2float_rn(wn_compute_energy((double)tlen, (double)tcos, ep));
-                out.length = tlen;
-                out.cosine = tcos;
-                edges[span + rpre + rank] = out;
+                const float en = __double2float_rn(wn_compute_energy((double)tlen, (double)tcos, ep));
+                if (CSR16) {
+                    /* compact layout: {j, energy, length, cosine}, one aligned 16-byte store */
+                    reinterpret_cast<uint4*>(edges)[span + rpre + rank] =
+                        make_uint4((uint32_t)tj, __float_as_uint(en), __float_as_uint(tlen), __float_as_uint(tcos));
+                } else {
+                    wn_edge out;
+                    out.i = irow; out.j = tj; out.energy = en; out.length = tlen; out.cosine = tcos;
+                    edges[span + rpre + rank] = out;
+                }
             }
         }
         /* energies in final order (own warp's writes, ordered by the barrier):
          * the summation tree does not depend on arrival order -> deterministic */
         __syncwarp();
-        for (uint32_t e = lane; e < total; e += 32) sum += (double)edges[span + e].energy;
+        for (uint32_t e = lane; e < total; e += 32)
+            sum += CSR16 ? (double)__uint_as_float(reinterpret_cast<const uint4*>(edges)[span + e].y)
+                         : (double)edges[span + e].energy;
     }
     /* fixed-tree warp reduction; one partial per warp (no block barrier), summed in order by wn_k_stats */
 #pragma unroll
@@ -226,13 +232,17 @@ void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* f
 void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
                     const uint32_t* row_off, const unsigned long long* frame_off,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
-                    unsigned long long edge_cap, double* block_sums, int* n_blocks_out,
+                    unsigned long long edge_cap, int csr16, double* block_sums, int* n_blocks_out,
                     cudaStream_t st)
 {
     dim3 g((n_sites + COPY_THREADS - 1) / COPY_THREADS, n_frames);
     *n_blocks_out = (int)g.x * (COPY_THREADS / 32);      /* partial sums per frame */
-    wn_k_copy<<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
-                                          edges, edge_cap, 0ull, block_sums);
+    if (csr16)
+        wn_k_copy<true><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
+                                                    edges, edge_cap, 0ull, block_sums);
+    else
+        wn_k_copy<false><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
+                                                     edges, edge_cap, 0ull, block_sums);
 }
 
 void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,

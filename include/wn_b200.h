@@ -64,6 +64,15 @@ typedef struct wn_edge {
     float   cosine;   /* coss.at(pos)                */
 } wn_edge;
 
+/* Compact layout (WN_LAYOUT_CSR16): the same list without the repeated row index; i is given by
+ * row_offsets (CSR).  16 bytes per edge instead of 20: fewer bytes over PCIe, aligned stores. */
+typedef struct wn_edge16 {
+    int32_t j;
+    float   energy, length, cosine;
+} wn_edge16;
+#define WN_LAYOUT_EDGES 0   /* wn_edge[]   : {i, j, energy, length, cosine}                      */
+#define WN_LAYOUT_CSR16 1   /* wn_edge16[] : {j, energy, length, cosine}, rows via row_offsets   */
+
 /* One row per frame.  First three = columns 0..2 of hydrogen-bonds-num.xvg
  * (src/waternetwork.cpp:659-662); sum_energy and pair_evals are extras. */
 typedef struct wn_frame_stats {
@@ -86,7 +95,7 @@ typedef struct wn_tie_report {
 /* Result of one batch.  Pointers are library-owned and stay valid until the next
  * wn_hbond_batch* call on the same context or wn_destroy. */
 typedef struct wn_batch_result {
-    const wn_edge*        edges;          /* concatenated, frame by frame        */
+    const wn_edge*        edges;          /* concatenated, frame by frame; wn_edge16* when layout == WN_LAYOUT_CSR16 */
     const uint64_t*       frame_offsets;  /* n_frames+1 offsets into edges       */
     const wn_frame_stats* stats;          /* n_frames rows                       */
     uint64_t              n_edges;        /* == frame_offsets[n_frames]          */
@@ -100,7 +109,7 @@ typedef struct wn_batch_result {
      * (the last row of a frame ends at frame_offsets[f+1]); [n_frames][n_sites] uint32. */
     const uint32_t*       row_offsets;
     int32_t               n_sites;
-    int32_t               reserved;
+    int32_t               layout;         /* WN_LAYOUT_EDGES or WN_LAYOUT_CSR16 */
 } wn_batch_result;
 
 /* ---- context ------------------------------------------------------------ */
@@ -208,6 +217,8 @@ typedef struct wn_batch_args {
     const float*   boxes;           /* host, [n_frames][box_stride]; NULL iff box_stride == 0        */
     const int64_t* subset_offsets;  /* host, [n_frames+1], or NULL: every frame uses the whole table */
     const int32_t* subset_sites;    /* host, rows of the site table                                  */
+    int32_t        result_layout;   /* WN_LAYOUT_EDGES (default) or WN_LAYOUT_CSR16                  */
+    int32_t        reserved;
 } wn_batch_args;
 int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* args, wn_batch_result* out);
 

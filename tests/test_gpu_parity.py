@@ -772,3 +772,26 @@ def test_general_entry_point_combinations(ctx, oracle):
         want, s, _, ev = oracle.frame_hbonds_tric(frames[f], sa[lst], ha[lst], ty[lst], b9[f])
         check_edges(e[int(fo[f]):int(fo[f + 1])], want)
         assert st["num_sites"][f] == len(lst) and int(st["pair_evals"][f]) == ev
+
+
+def test_compact_csr16_layout(ctx, oracle, capi):
+    """WN_LAYOUT_CSR16: {j, energy, length, cosine} + row offsets carries exactly the wn_edge list."""
+    n, nf = 2000, 4
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 0, nf)
+    ctx.set_water_sites(n)
+    ctx.set_batch_frames(3)                       # two internal passes
+    full = ctx.hbond_batch_ex(frames)
+    csr = ctx.hbond_batch_ex(frames, layout=capi.LAYOUT_CSR16)
+    ctx.set_batch_frames(0)
+    assert csr["layout"] == capi.LAYOUT_CSR16 and csr["edges"].dtype == capi.EDGE16_DTYPE
+    assert np.array_equal(csr["frame_offsets"], full["frame_offsets"]) and np.array_equal(csr["row_offsets"], full["row_offsets"])
+    assert csr["stats"].tobytes() == full["stats"].tobytes()
+    for k in ("j", "energy", "length", "cosine"):
+        assert np.array_equal(csr["edges"][k].view(np.uint32), full["edges"][k].view(np.uint32))
+    # i reconstructed from the row offsets
+    fo, ro = csr["frame_offsets"], csr["row_offsets"]
+    for f in range(nf):
+        cnt = np.diff(np.append(ro[f], fo[f + 1] - fo[f]).astype(np.int64))
+        i = np.repeat(np.arange(n), cnt)
+        assert np.array_equal(i, full["edges"]["i"][int(fo[f]):int(fo[f + 1])])
