@@ -477,6 +477,15 @@ def run_own(args):
 
     ctx.pinned_free(host_ptr)
     ctx.dev_free(frames_dev)
+    # per-rank view (diagnostics: a slow rank shows here, the headline uses the max)
+    mine_rank = {"rank": rank, "ms_per_step": dev_ms / K, "wall_ms_per_step": (t1 - t0) * 1e3 / K,
+                 "edges_ms": edges_ms / K, "bin_ms": bin_ms / K, "finish_ms": finish_ms / K,
+                 "e2e_ms_per_step": e2e_ms / K, "sm_mhz": clocks.get("sm_mhz") if isinstance(clocks, dict) else None,
+                 "reasons": clocks.get("reasons") if isinstance(clocks, dict) else None}
+    per_rank = [mine_rank]
+    if dist is not None:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine_rank)
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -498,6 +507,7 @@ def run_own(args):
                     "result_layout": "WN_LAYOUT_CSR16 (16 B/edge + 4 B/site row offsets; wn_edge AoS is 20 B/edge)"},
             "gpu_launches": launches,
             "clocks": clocks,
+            "per_rank": per_rank if world > 1 else None,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "periodic": periodic,

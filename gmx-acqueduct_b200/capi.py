@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwn_b200.so")
+# WN_B200_LIB: load another build of the same library (kernel experiments); default = the in-tree build
+LIB_PATH = os.environ.get("WN_B200_LIB") or os.path.join(HERE, "libwn_b200.so")
 
 WN_OK = 0
 DONOR, ACCEPTOR, WATER = 0, 1, 2

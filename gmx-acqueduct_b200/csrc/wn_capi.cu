@@ -380,7 +380,12 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         }
     }
 
-    if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, (size_t)end_off, true, (size_t)*edge_base))) return rc;
+    /* grow with head room: edge counts of equally sized batches differ by a fraction of a percent, and a
+     * regrowth (allocation + copy + synchronisation) costs tens of milliseconds */
+    if ((size_t)end_off > ctx->edges_cap || !ctx->d_edges) {
+        const size_t want = (size_t)end_off + (size_t)end_off / 16 + 4096;
+        if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, want, true, (size_t)*edge_base))) return rc;
+    }
 
     int n_blocks = 0;
     wn_launch_copy(ctx->d_rowbuf, ctx->row_cap, ctx->d_row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0,
