@@ -53,6 +53,7 @@ struct wn_ctx {
     unsigned long long* d_frame_total = nullptr;
     WnFrameCounters* d_counters = nullptr;
     uint32_t* d_frame_maxrow = nullptr;
+    int* d_blk_prefix = nullptr;             /* [cap_frames + 2]: home-block prefix per frame, then the work counter */
     uint32_t* d_scan_part = nullptr;     /* chunk sums / maxima of the three-phase scans, bbox keys */
     unsigned long long* d_pass_info = nullptr;
     double* d_block_sums = nullptr;
@@ -224,6 +225,7 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
     if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_total, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_counters, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_maxrow, (size_t)cf))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_blk_prefix, (size_t)cf + 2))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_scan_part,
                                 (size_t)cf * (2 * (size_t)wn_scan_chunks_for(std::max(cn, cell_cap + 1)) + 8)))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_block_sums, (size_t)cf * ((cn + 255) / 256 + 1) * 8))) return rc;
@@ -352,6 +354,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         p.rowbuf = ctx->d_rowbuf; p.row_cnt = ctx->d_row_cnt; p.counters = ctx->d_counters;
         p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
         p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? (ctx->box_stride == 9 ? 2 : 1) : 0; p.bx = bx; p.subset = sub;
+        p.blk_prefix = ctx->d_blk_prefix; p.work_next = reinterpret_cast<unsigned int*>(ctx->d_blk_prefix + nf + 1); p.n_frames = nf;
         if (small_box) wn_launch_edges_small(p, nf, st);
         else wn_launch_edges(p, nf, st);
         WN_CK(cudaGetLastError());
@@ -360,7 +363,7 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
                           ctx->d_scan_part, st);
         wn_launch_frameoff(ctx->d_frame_total, ctx->d_frame_maxrow, nf, *edge_base, ctx->d_frame_off + f0,
                            ctx->d_pass_info, st);
-        ctx->tm.launches += 5;             /* fused search, row scan x3, frame offsets */
+        ctx->tm.launches += small_box ? 5 : 6;   /* [home-block prefix] fused search, row scan x3, frame offsets */
         WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_pass_info, 2 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
         WN_CK(cudaStreamSynchronize(st));
@@ -604,7 +607,7 @@ void wn_destroy(wn_ctx* ctx)
     }
     void* dev[] = {ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, ctx->d_grid, ctx->d_cell_cnt, ctx->d_site_cell,
                    ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_cnt,
-                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_scan_part, ctx->d_pass_info, ctx->d_sub_off, ctx->d_sub_sites,
+                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_blk_prefix, ctx->d_scan_part, ctx->d_pass_info, ctx->d_sub_off, ctx->d_sub_sites,
                    ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce,
                    ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags};

@@ -108,6 +108,9 @@ struct WnEdgeParams {
     int pbc;                    /* 0 open, 1 rectangular, 2 triclinic (all-pairs kernel only) */
     int bx;                     /* home block width in cells (1 or 2)               */
     WnSubset subset;            /* per-frame site subsets (off == nullptr: whole table) */
+    int*            blk_prefix; /* [F+1] exclusive prefix of the home blocks per frame (written by the launcher's kernel) */
+    unsigned int*   work_next;  /* next unclaimed home block of the pass (dynamic scheduling)  */
+    int n_frames;
 };
 
 /* ---- kernel launchers (wn_kernels_*.cu).  All asynchronous on `st`. ---- */

@@ -39,6 +39,7 @@
  * (first site's list, then second site's, :215-249) depends on the roles.
  */
 #include "wn_internal.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -250,22 +251,74 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
 /* floor division and modulo for possibly negative cell indices */
 __device__ __forceinline__ int wn_floordiv(int a, int n) { return (a >= 0) ? a / n : -((-a + n - 1) / n); }
 
+/* home blocks per frame -> exclusive prefix over the frames of the pass; resets the work counter */
+template <int BX>
+__global__ void __launch_bounds__(1024)
+wn_k_block_prefix(const WnGrid* __restrict__ grid, int n_frames, int* __restrict__ prefix, unsigned int* __restrict__ work_next)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_carry = 0; *work_next = 0u; }
+    __syncthreads();
+    for (int base = 0; base < n_frames; base += blockDim.x) {
+        const int f = base + threadIdx.x;
+        int nb = 0;
+        if (f < n_frames) nb = ((grid[f].nx + BX - 1) / BX) * grid[f].ny * grid[f].nz;
+        int inc = nb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_w[lane];
+            int iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, iv, o);
+                if (lane >= o) iv += t;
+            }
+            s_w[lane] = iv - v;
+        }
+        __syncthreads();
+        const int excl = s_carry + s_w[warp] + inc - nb;
+        if (f < n_frames) prefix[f] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + nb;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[n_frames] = s_carry;
+}
+
+/* Persistent warps: every warp claims home blocks (frame, block) from one counter until the pass is
+ * exhausted -- blocks differ in cost (10..30 home sites, boundary blocks with few neighbours), and a
+ * static block-per-warp grid left ~20 % of the resident warp slots idle behind the slowest warp of a CTA. */
 template <bool SIMPLE, int PBC, int BX>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WN_EDGES_MINBLOCKS)
 wn_k_edges(const WnEdgeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.y;
-    const int blk = blockIdx.x * WARPS_PER_CTA + warp;
-    const WnGrid& g = p.grid[f];
-    const int nx = g.nx, ny = g.ny, nz = g.nz;
-    const int nbx = (nx + BX - 1) / BX;
-    if (blk >= nbx * ny * nz) return;
-
     const size_t per_warp = sizeof(WarpShared) + (size_t)HC * p.hs * 4 * sizeof(double);
     WarpShared& ws = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)warp * per_warp);
     double* hdh = reinterpret_cast<double*>(smem_raw + (size_t)warp * per_warp + sizeof(WarpShared));
+    const int n_items = __ldg(p.blk_prefix + p.n_frames);
+    int f = 0;
+    for (;;) {
+    /* (claiming the next block ahead of time was measured slower: the extra live register spills) */
+    unsigned int item = 0;
+    if (lane == 0) item = atomicAdd(p.work_next, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= (unsigned int)n_items) break;
+    /* frame of the item: items are claimed in increasing order, so the search starts at the last frame */
+    while (__ldg(p.blk_prefix + f + 1) <= (int)item) ++f;
+    const int blk = (int)item - __ldg(p.blk_prefix + f);
+    const WnGrid& g = p.grid[f];
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int nbx = (nx + BX - 1) / BX;
 
     const size_t fbase = (size_t)f * p.n_sites;
     const int* cs_f = p.cell_start + (size_t)f * (p.cell_cap + 1);
@@ -274,7 +327,7 @@ wn_k_edges(const WnEdgeParams p)
     const int x0 = bx * BX, x1 = min(x0 + BX - 1, nx - 1);
     const int row0 = (cz * ny + cy) * nx;
     const int h0 = __ldg(cs_f + row0 + x0), h1 = __ldg(cs_f + row0 + x1 + 1);
-    if (h0 == h1) return;
+    if (h0 == h1) continue;
 
     /* block-local frame for the fp32 prefilter: origin = centre of the home block, so
      * |home| <= (BX/2, 1/2, 1/2) e and |candidate| <= (BX/2+1, 3/2, 3/2) e */
@@ -510,6 +563,8 @@ wn_k_edges(const WnEdgeParams p)
         if (ct.tie_cos) atomicAdd(&fc->tie_cos, (unsigned long long)ct.tie_cos);
         if (ct.tie_pos0) atomicAdd(&fc->tie_pos0, (unsigned long long)ct.tie_pos0);
     }
+    __syncwarp();        /* the per-warp shared memory is rewritten by the next block */
+    }
 }
 
 /* ---- all-pairs variant ----
@@ -656,10 +711,18 @@ template <bool SIMPLE, int PBC, int BX>
 void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
     const size_t smem = wn_edges_smem_bytes(p.hs);
-    /* blocks per frame <= ceil(nx/BX)*ny*nz <= cell_cap */
-    dim3 grid((p.cell_cap + WARPS_PER_CTA - 1) / WARPS_PER_CTA, n_frames);
+    static int ctas = 0;                      /* resident CTAs of the whole device (same for every variant: smem-bound) */
     cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    wn_k_edges<SIMPLE, PBC, BX><<<grid, WARPS_PER_CTA * 32, smem, st>>>(p);
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wn_k_edges<SIMPLE, PBC, BX>, WARPS_PER_CTA * 32, smem);
+    ctas = std::max(1, per_sm) * std::max(1, sms);
+    wn_k_block_prefix<BX><<<1, 1024, 0, st>>>(p.grid, n_frames, p.blk_prefix, p.work_next);
+    /* no more CTAs than there is work for (blocks per frame <= cell_cap) */
+    const long long max_items = (long long)n_frames * p.cell_cap;
+    const int grid = (int)std::min<long long>(ctas, (max_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    wn_k_edges<SIMPLE, PBC, BX><<<std::max(grid, 1), WARPS_PER_CTA * 32, smem, st>>>(p);
 }
 }  // namespace
 
