@@ -233,8 +233,9 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
         const float4 b4 = __ldg(p.spos + fbase + c);
         ih = __float_as_int(a4.w);
         ic = __float_as_int(b4.w);
-        const double* dh = hdh + (size_t)h * p.hs * 4;
-        const double* dc = p.sdh + (fbase + c) * (size_t)p.hs * 4;
+        const int hs = SIMPLE ? 1 : p.hs;
+        const double* dh = hdh + (size_t)h * hs * 4;
+        const double* dc = p.sdh + (fbase + c) * (size_t)hs * 4;
         uint32_t mh = 0, mc = 0;
         if (!SIMPLE) { mh = ws.hmeta[h]; mc = __ldg(p.smeta + fbase + c); }
         r = wn_pair_geometry<SIMPLE, PBC>(a4, b4, dh, dc, mh, mc, g);
@@ -246,6 +247,29 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
         ct.tie_pos0 += __popc(__ballot_sync(FULL, r.t_pos0));
     }
     if (r.edge) wn_emit_edge(p, fbase, ih, ic, r.len_f, r.cosmax);
+}
+
+/* inclusive warp scan of a small count; returns the warp total, `excl` = sum over the lower lanes */
+__device__ __forceinline__ int wn_scan_counts(int cnt, int lane, int& excl)
+{
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    excl = inc - cnt;
+    return __shfl_sync(FULL, inc, 31);
+}
+
+/* one queue code per set bit of `part` (bit b = home row hb0 + b), from position `pos` on */
+__device__ __forceinline__ void wn_store_codes(WarpShared& ws, uint32_t part, int hb0, uint32_t code_c, int pos)
+{
+    while (part) {
+        const int h = __ffs(part) - 1 + hb0;
+        part &= part - 1;
+        ws.queue[pos++] = ((uint32_t)h << 27) | code_c;
+    }
 }
 
 /* floor division and modulo for possibly negative cell indices */
@@ -302,7 +326,9 @@ wn_k_edges(const WnEdgeParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = sizeof(WarpShared) + (size_t)HC * p.hs * 4 * sizeof(double);
+    /* SIMPLE: exactly one valid hydrogen per site -> compile-time strides */
+    const int hs = SIMPLE ? 1 : p.hs;
+    const size_t per_warp = sizeof(WarpShared) + (size_t)HC * hs * 4 * sizeof(double);
     WarpShared& ws = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)warp * per_warp);
     double* hdh = reinterpret_cast<double*>(smem_raw + (size_t)warp * per_warp + sizeof(WarpShared));
     const int n_items = __ldg(p.blk_prefix + p.n_frames);
@@ -458,8 +484,8 @@ wn_k_edges(const WnEdgeParams p)
             float* hl = reinterpret_cast<float*>(ws.hloc) + (lane >> 1) * 8 + (lane & 1);
             hl[0] = lx; hl[2] = ly; hl[4] = lz; hl[6] = nw;
         }
-        for (int t = lane; t < hc * p.hs * 4; t += 32)
-            hdh[t] = __ldg(p.sdh + (fbase + hb) * (size_t)p.hs * 4 + t);
+        for (int t = lane; t < hc * hs * 4; t += 32)
+            hdh[t] = __ldg(p.sdh + (fbase + hb) * (size_t)hs * 4 + t);
         __syncwarp();
         /* rows >= first_limit own nothing: a pair needs min(index) < first_limit */
         uint32_t low_rows = 0;
@@ -522,32 +548,37 @@ wn_k_edges(const WnEdgeParams p)
                 }
             }
             hits &= allow;
-            /* compact the hits into the queue, HPUSH mask bits at a time (bounds the queue) */
-#pragma unroll 1
-            for (int hb0 = 0; hb0 < hc4; hb0 += HPUSH) {
-                uint32_t part = (hits >> hb0) & ((1u << HPUSH) - 1u);
-                const int cnt = __popc(part);
-                int pinc = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(FULL, pinc, o);
-                    if (lane >= o) pinc += t;
-                }
-                const int tot = __shfl_sync(FULL, pinc, 31);
-                if (tot) {
-                    int pos = qlen + pinc - cnt;
-                    while (part) {
-                        const int h = __ffs(part) - 1 + hb0;
-                        part &= part - 1;
-                        ws.queue[pos++] = ((uint32_t)h << 27) | code_c;
-                    }
-                    qlen += tot;
+            /* compact the hits into the queue: one warp scan of the per-lane hit counts, each lane then
+             * stores its (home, candidate) codes behind those of the lower lanes.  A round with more
+             * hits than the queue holds (dense clusters) is pushed HPUSH mask bits at a time. */
+            int excl;
+            const int tot_all = wn_scan_counts(__popc(hits), lane, excl);
+            if (tot_all) {
+                if (qlen + tot_all <= QCAP) {
+                    wn_store_codes(ws, hits, 0, code_c, qlen + excl);
+                    qlen += tot_all;
                     __syncwarp();
                     while (qlen >= 32) {
                         wn_eval_batch<SIMPLE, PBC>(p, fbase, ws, hdh, g, qlen - 32, 32, ct, lane);
                         qlen -= 32;
                     }
                     __syncwarp();
+                } else {
+#pragma unroll 1
+                    for (int hb0 = 0; hb0 < hc4; hb0 += HPUSH) {
+                        const uint32_t part = (hits >> hb0) & ((1u << HPUSH) - 1u);
+                        const int tot = wn_scan_counts(__popc(part), lane, excl);
+                        if (tot) {
+                            wn_store_codes(ws, part, hb0, code_c, qlen + excl);
+                            qlen += tot;
+                            __syncwarp();
+                            while (qlen >= 32) {
+                                wn_eval_batch<SIMPLE, PBC>(p, fbase, ws, hdh, g, qlen - 32, 32, ct, lane);
+                                qlen -= 32;
+                            }
+                            __syncwarp();
+                        }
+                    }
                 }
             }
         }
