@@ -412,7 +412,7 @@ def run_own(args):
         ctx.d2h(host_arr[r], frames_dev + r * F * frame_bytes)
     # one call per step; inside the call the library pipelines sub-passes (H2D of pass k+1 and
     # D2H of pass k-1 under the kernels of pass k), so give it several passes per step
-    e2e_pass = max(F // 5, 1)
+    e2e_pass = max(F // 5, 1) if args.e2e_pass < 0 else args.e2e_pass      # 0 = the library's own schedule
     ctx.set_batch_frames(e2e_pass)
     e2e_layout = capi.LAYOUT_CSR16          # 16 bytes per edge over PCIe (row index via the CSR offsets)
     for s in range(min(W, 2)):
@@ -530,6 +530,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--waters", type=int, default=N_WATERS)
     ap.add_argument("--frames-per-step", type=int, default=250)
+    ap.add_argument("--e2e-pass", type=int, default=0, help="frames per internal pass of the e2e leg (0: library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pbc", action="store_true", help="skip the periodic-boundary leg")
     ap.add_argument("--no-find", action="store_true", help="skip the standalone CudaFindPairs::find leg")

@@ -452,17 +452,29 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
 
     const int fpp = ctx->user_frames_per_pass > 0 ? ctx->user_frames_per_pass : default_frames_per_pass(N);
     const size_t frame_floats = (size_t)natoms * 3;
-    const int n_pass = (n_frames + fpp - 1) / fpp;
     if (host_in) {
         /* Host variant, pipelined: the H2D copy of pass k+1 (st_h2d) and the D2H copy of the
-         * edges of pass k-1 (st_d2h) run under the kernels of pass k (st). */
+         * results of pass k-1 (st_d2h) run under the kernels of pass k (st).  The result copy is the
+         * longest stage (PCIe), so the first passes are short: the D2H engine starts early and the
+         * later, full-size passes keep it busy. */
+        std::vector<std::pair<int, int> > plan;        /* (first frame, frames) */
+        {
+            int f0 = 0, nf = ctx->user_frames_per_pass > 0 ? std::max(1, fpp / 8) : std::max(1, fpp / 32);
+            while (f0 < n_frames) {
+                const int take = std::min(std::min(nf, fpp), n_frames - f0);
+                plan.push_back(std::make_pair(f0, take));
+                f0 += take;
+                nf *= 2;
+            }
+        }
+        const int n_pass = (int)plan.size();
         while (ctx->ev_copy.size() < (size_t)4 * n_pass) {
             cudaEvent_t e; WN_CK(cudaEventCreate(&e)); ctx->ev_copy.push_back(e);
         }
         auto stage_in = [&](int k) -> int {
-            const int f0 = k * fpp, nf = std::min(fpp, n_frames - f0), b = k & 1;
+            const int f0 = plan[k].first, nf = plan[k].second, b = k & 1;
             int rc2;
-            if ((rc2 = dev_ensure(ctx, &ctx->d_stage[b], &ctx->stage_cap[b], (size_t)nf * frame_floats))) return rc2;
+            if ((rc2 = dev_ensure(ctx, &ctx->d_stage[b], &ctx->stage_cap[b], (size_t)std::max(nf, std::min(fpp, n_frames)) * frame_floats))) return rc2;
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k], ctx->st_h2d));
             WN_CK(cudaMemcpyAsync(ctx->d_stage[b], frames + (size_t)f0 * frame_floats,
                                   (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->st_h2d));
@@ -470,9 +482,9 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
             WN_CK(cudaEventRecord(ctx->ev_stage[b], ctx->st_h2d));
             return WN_OK;
         };
-        if ((rc = stage_in(0))) return rc;
+        if (n_pass > 0 && (rc = stage_in(0))) return rc;
         for (int k = 0; k < n_pass; ++k) {
-            const int f0 = k * fpp, nf = std::min(fpp, n_frames - f0);
+            const int f0 = plan[k].first, nf = plan[k].second;
             if (k + 1 < n_pass && (rc = stage_in(k + 1))) return rc;
             WN_CK(cudaStreamWaitEvent(ctx->st, ctx->ev_stage[k & 1], 0));
             const unsigned long long before = edge_base;
@@ -494,6 +506,10 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
                                       reinterpret_cast<const char*>(ctx->d_edges) + (size_t)before * esz,
                                       (size_t)(edge_base - before) * esz, cudaMemcpyDeviceToHost, ctx->st_d2h));
             }
+            /* the row offsets of the pass travel with its edges */
+            if (N > 0)
+                WN_CK(cudaMemcpyAsync(ctx->h_row_off + (size_t)f0 * N, ctx->d_row_off + (size_t)f0 * N,
+                                      (size_t)nf * N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 3], ctx->st_d2h));
         }
         WN_CK(cudaStreamSynchronize(ctx->st_d2h));
@@ -516,9 +532,6 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
                           cudaMemcpyDeviceToHost, ctx->st));
     WN_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters_all, (size_t)n_frames * sizeof(WnFrameCounters),
                           cudaMemcpyDeviceToHost, ctx->st));
-    if (host_in)
-        WN_CK(cudaMemcpyAsync(ctx->h_row_off, ctx->d_row_off, (size_t)n_frames * N * sizeof(uint32_t),
-                              cudaMemcpyDeviceToHost, ctx->st));
     WN_CK(cudaStreamSynchronize(ctx->st));
     if (ctx->h_frame_off[n_frames] != edge_base)
         return fail(ctx, WN_ERR_CUDA, "internal: edge totals disagree between scan and fused kernel");
