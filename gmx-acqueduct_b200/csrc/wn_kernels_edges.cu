@@ -48,7 +48,12 @@ namespace {
 #endif
 constexpr int WARPS_PER_CTA = 8;
 constexpr int HC   = 32;                 /* home sites per chunk (one hit-mask bit each)       */
-constexpr int HPUSH = 16;                /* hit-mask bits pushed per scan (20 measured slower: shared memory costs a CTA/SM) */
+#ifndef WN_EDGES_HPUSH
+#define WN_EDGES_HPUSH 8
+#endif
+constexpr int HPUSH = WN_EDGES_HPUSH;    /* hit-mask bits per push on the dense-round path; sizes the queue, and the shared
+                                          * memory of the resident CTAs decides how much of the SM's 256 KB stays L1
+                                          * (measured: a 228 KB carve-out instead of 196 KB cost 25 % of this kernel) */
 constexpr int QCAP = 32 + 32 * HPUSH;    /* queue: < 32 carried + one push of <= 32*HPUSH codes */
 constexpr int MAXRUN = 12;               /* 5 rows (6 on a skewed z boundary), each possibly split by the periodic wrap in x */
 constexpr unsigned FULL = 0xffffffffu;
@@ -742,13 +747,23 @@ template <bool SIMPLE, int PBC, int BX>
 void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
     const size_t smem = wn_edges_smem_bytes(p.hs);
-    static int ctas = 0;                      /* resident CTAs of the whole device (same for every variant: smem-bound) */
-    cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0, dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wn_k_edges<SIMPLE, PBC, BX>, WARPS_PER_CTA * 32, smem);
-    ctas = std::max(1, per_sm) * std::max(1, sms);
+    /* launch geometry of this variant: one CTA per resident slot of the device (persistent warps) */
+    static int s_ctas = 0;
+    static size_t s_smem = 0;
+    if (s_ctas == 0 || s_smem != smem) {
+        cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wn_k_edges<SIMPLE, PBC, BX>, WARPS_PER_CTA * 32, smem);
+        per_sm = std::max(1, per_sm);
+        /* ask for exactly the shared memory the resident CTAs use (1 KB per CTA is reserved); the rest stays L1 */
+        const int carve = (int)std::min<size_t>(100, ((size_t)per_sm * (smem + 1024) * 100 + 233471) / 233472);
+        cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        s_ctas = per_sm * std::max(1, sms);
+        s_smem = smem;
+    }
+    const int ctas = s_ctas;
     wn_k_block_prefix<BX><<<1, 1024, 0, st>>>(p.grid, n_frames, p.blk_prefix, p.work_next);
     /* no more CTAs than there is work for (blocks per frame <= cell_cap) */
     const long long max_items = (long long)n_frames * p.cell_cap;
