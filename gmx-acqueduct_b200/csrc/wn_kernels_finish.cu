@@ -199,18 +199,23 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
     if (lane == 0) block_sums[((size_t)f * gridDim.x + blockIdx.x) * (COPY_THREADS / 32) + warp] = sum;
 }
 
-/* ---- per-frame statistics row ---- */
+/* ---- per-frame statistics row: one warp per frame ----
+ * The partial sums are added in a fixed order (lane-strided, then a shuffle tree), so the energy sum
+ * does not depend on scheduling. */
 __global__ void __launch_bounds__(128)
 wn_k_stats(const double* __restrict__ block_sums, int n_blocks,
            const unsigned long long* __restrict__ frame_total,
            const WnFrameCounters* __restrict__ counters, int n_frames, int n_table, WnSubset sub,
            wn_frame_stats* __restrict__ stats)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (f >= n_frames) return;
-    const int n_sites = wn_frame_sites(sub, f, n_table);
     double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += block_sums[(size_t)f * n_blocks + b];
+    for (int b = lane; b < n_blocks; b += 32) s += block_sums[(size_t)f * n_blocks + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane) return;
+    const int n_sites = wn_frame_sites(sub, f, n_table);
     wn_frame_stats r;
     r.num_sites = (double)n_sites;                              /* :659 */
     r.num_edges = (double)frame_total[f];                       /* :660 */
@@ -249,6 +254,6 @@ void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long
                      const WnFrameCounters* counters, int n_frames, int n_sites, WnSubset sub,
                      wn_frame_stats* stats, cudaStream_t st)
 {
-    wn_k_stats<<<(n_frames + 127) / 128, 128, 0, st>>>(block_sums, n_blocks, frame_total, counters,
+    wn_k_stats<<<(n_frames + 3) / 4, 128, 0, st>>>(block_sums, n_blocks, frame_total, counters,
                                                        n_frames, n_sites, sub, stats);
 }
