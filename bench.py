@@ -397,6 +397,33 @@ def run_own(args):
                 "note": "rows of edges-frames.xvg.dat formatted by wn_k_format_rows, D2H into pinned host memory "
                         "included; host formatter (EdgeFileWriter): ~0.4 GB/s per core, iostream: ~0.03 GB/s"}
 
+    # ---- connected components of the networks of a device-resident batch (the first step of the
+    # reference's downstream script, python/network-analysis.py): union-find on the edge list in HBM
+    comps = None
+    if rank == 0 and not args.no_find:
+        outc = ctx.hbond_batch_dev(frames_dev, F, natoms)
+        import ctypes
+        lab, stc = ctypes.c_void_p(), ctypes.c_void_p()
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peak_gbs = float(json.load(fh).get("hbm_gbs", 6650.0))
+        except Exception:
+            peak_gbs = 6650.0
+        ctx._ck(ctx.L.wn_components(ctx.h, 0.0, ctypes.byref(lab), ctypes.byref(stc)))      # warm-up (buffers)
+        ctx.timer_start()
+        reps = 5
+        for _ in range(reps):
+            ctx._ck(ctx.L.wn_components(ctx.h, 0.0, ctypes.byref(lab), ctypes.byref(stc)))
+        cms = ctx.timer_stop() / reps
+        st_c = np.zeros(F, capi.COMPONENT_DTYPE)
+        ctx.d2h(st_c, stc.value)
+        cc_bytes = outc["n_edges"] * 12 + F * n_waters * 4      # i, j, energy of every edge + one label per site
+        comps = {"frames": F, "ms": cms, "frames_per_s": F / (cms * 1e-3), "edges_per_s": outc["n_edges"] / (cms * 1e-3),
+                 "algorithmic_bytes": cc_bytes, "GBps": cc_bytes / (cms * 1e-3) / 1e9,
+                 "frac_of_hbm_peak": cc_bytes / (cms * 1e-3) / 1e9 / peak_gbs,
+                 "components_frame0": int(st_c["n_components"][0]), "largest_frame0": int(st_c["largest"][0]),
+                 "note": "wn_components at threshold 0.0 on the HBM-resident edge list (iota + hook + flatten + stats kernels)"}
+
     if periodic is not None:
         pmax = allmax(periodic["ms"])
         periodic = {"value": periodic["steps"] * F * world / (pmax * 1e-3), "unit": "frames/s",
@@ -513,6 +540,7 @@ def run_own(args):
             "periodic": periodic,
             "find_pairs": find,
             "edge_file_text": text,
+            "components": comps,
         }
         print(json.dumps(line))
     if dist is not None:

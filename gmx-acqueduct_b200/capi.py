@@ -20,6 +20,7 @@ MODEL_TIP3P, MODEL_SPC = 0, 1
 EDGE_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("energy", "<f4"),
                        ("length", "<f4"), ("cosine", "<f4")])
 EDGE16_DTYPE = np.dtype([("j", "<i4"), ("energy", "<f4"), ("length", "<f4"), ("cosine", "<f4")])
+COMPONENT_DTYPE = np.dtype([("n_components", "<i4"), ("largest", "<i4"), ("n_nodes", "<i4"), ("n_edges", "<i4")])
 LAYOUT_EDGES, LAYOUT_CSR16 = 0, 1
 STATS_DTYPE = np.dtype([("num_sites", "<f8"), ("num_edges", "<f8"), ("ratio", "<f8"),
                         ("sum_energy", "<f8"), ("pair_evals", "<f8")])
@@ -28,7 +29,7 @@ assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
 # every symbol include/wn_b200.h declares
 SYMBOLS = [
     "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_find_pairs_pbc",
-    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_hbond_batch_ex", "wn_hbond_batch_box9", "wn_find_pairs_box9", "wn_format_edges", "wn_set_sites",
+    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_hbond_batch_ex", "wn_hbond_batch_box9", "wn_find_pairs_box9", "wn_format_edges", "wn_components", "wn_set_sites",
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
@@ -118,6 +119,7 @@ def load():
     L.wn_synth_frames_dev.argtypes = [vp, i32, u64, i32, i64, i32, vp]
     L.wn_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.wn_selftest_div.argtypes = [vp, u64, u64, C.POINTER(u64)]
+    L.wn_components.argtypes = [vp, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.wn_timer_start.argtypes = [vp]
     L.wn_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.wn_nccl_unique_id.argtypes = [vp]
@@ -210,6 +212,7 @@ class Context:
                "n_frames": nf}
         out["n_sites"] = res.n_sites
         out["layout"] = res.layout
+        self._last_frames, self._last_on_device = nf, bool(res.on_device)
         edt = EDGE16_DTYPE if res.layout == LAYOUT_CSR16 else EDGE_DTYPE
         if res.on_device:
             out["edges_dev"] = res.edges
@@ -316,6 +319,26 @@ class Context:
         if nf:
             self.d2h(st, out["stats_dev"])
         return e, fo, st
+
+    def components(self, threshold=0.0, n_frames=None):
+        """Connected components of the last batch (wn_components): (labels [F][N] int32, stats [F] structured).
+        For a device-resident batch the arrays are fetched to the host here."""
+        lab, st = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.wn_components(self.h, C.c_float(threshold), C.byref(lab), C.byref(st)))
+        F, N = self._last_frames if n_frames is None else n_frames, self.n_sites
+        labels = np.zeros((F, N), np.int32)
+        stats = np.zeros(F, COMPONENT_DTYPE)
+        if self._last_on_device:
+            if labels.size:
+                self.d2h(labels, lab.value)
+            if F:
+                self.d2h(stats, st.value)
+        else:
+            if labels.size:
+                labels[...] = np.frombuffer((C.c_char * (labels.size * 4)).from_address(lab.value), dtype=np.int32).reshape(F, N)
+            if F:
+                stats[...] = np.frombuffer((C.c_char * (F * 16)).from_address(st.value), dtype=COMPONENT_DTYPE)
+        return labels, stats
 
     def format_edges(self, frame_numbers, site_ids=None):
         """Text of the edge file for the last batch result (bytes), formatted on the GPU."""

@@ -85,6 +85,14 @@ struct wn_ctx {
 
     /* text formatting of the last batch */
     int last_frames = -1;                      /* frames of the last wn_hbond_batch* call, -1: none */
+    int last_on_device = 0;                    /* that call's results live on the device (*_dev) */
+    /* connected components of the last batch */
+    int* d_cc_labels = nullptr; int* d_cc_work = nullptr; int* d_cc_count = nullptr; int* d_cc_minidx = nullptr;
+    unsigned int* d_cc_kept = nullptr;
+    wn_component_stats* d_cc_stats = nullptr;
+    size_t cc_labels_cap = 0, cc_work_cap = 0, cc_count_cap = 0, cc_minidx_cap = 0, cc_kept_cap = 0, cc_stats_cap = 0;
+    int* h_cc_labels = nullptr; wn_component_stats* h_cc_stats = nullptr;
+    size_t h_cc_labels_cap = 0, h_cc_stats_cap = 0;
     unsigned long long last_edges = 0;
     char* d_text = nullptr;  size_t d_text_cap = 0;
     char* h_text = nullptr;  size_t h_text_cap = 0;
@@ -548,6 +556,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     out->stats = host_in ? ctx->h_stats : ctx->d_stats;
     ctx->last_frames = n_frames;
     ctx->last_edges = edge_base;
+    ctx->last_on_device = host_in ? 0 : 1;
     out->row_offsets = host_in ? ctx->h_row_off : ctx->d_row_off;
     out->n_sites = N;
     out->layout = ctx->layout;
@@ -623,10 +632,11 @@ void wn_destroy(wn_ctx* ctx)
                    ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_blk_prefix, ctx->d_scan_part, ctx->d_pass_info, ctx->d_sub_off, ctx->d_sub_sites,
                    ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce,
-                   ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags};
+                   ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags,
+                   ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx, ctx->d_cc_kept, ctx->d_cc_stats};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs, ctx->h_row_off,
-                    ctx->h_text};
+                    ctx->h_text, ctx->h_cc_labels, ctx->h_cc_stats};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
@@ -1090,6 +1100,41 @@ int wn_format_edges(wn_ctx* ctx, const int32_t* frame_numbers, const uint32_t* s
     for (int f = 0; f < F; ++f) memcpy(ctx->h_text + (row_base[f] - hdr[f].size()), hdr[f].data(), hdr[f].size());
     *text = ctx->h_text;
     *text_bytes = pos;
+    return WN_OK;
+}
+
+int wn_components(wn_ctx* ctx, float weight_threshold, const int32_t** labels, const wn_component_stats** stats)
+{
+    if (!ctx || !labels || !stats) return WN_ERR_BAD_ARG;
+    *labels = nullptr; *stats = nullptr;
+    if (ctx->last_frames < 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_components: no batch result to analyse");
+    WN_CK(cudaSetDevice(ctx->device));
+    const int F = ctx->last_frames, N = std::max(ctx->n_sites, 0);
+    const size_t n = (size_t)F * N;
+    int rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_cc_labels, &ctx->cc_labels_cap, n + 1))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_cc_work, &ctx->cc_work_cap, n + 1))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_cc_count, &ctx->cc_count_cap, n + 1))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_cc_minidx, &ctx->cc_minidx_cap, n + 1))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_cc_kept, &ctx->cc_kept_cap, (size_t)F + 1))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_cc_stats, &ctx->cc_stats_cap, (size_t)F + 1))) return rc;
+    unsigned long long max_edges = 0;
+    for (int f = 0; f < F; ++f) max_edges = std::max<unsigned long long>(max_edges, ctx->h_frame_off[f + 1] - ctx->h_frame_off[f]);
+    wn_launch_components(ctx->d_edges, ctx->layout == WN_LAYOUT_CSR16 ? 1 : 0, ctx->d_frame_off, ctx->d_row_off, F, N,
+                         max_edges, weight_threshold, ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx,
+                         ctx->d_cc_kept, ctx->d_cc_stats, ctx->st);
+    WN_CK(cudaGetLastError());
+    if (ctx->last_on_device) {
+        WN_CK(cudaStreamSynchronize(ctx->st));
+        *labels = ctx->d_cc_labels; *stats = ctx->d_cc_stats;
+        return WN_OK;
+    }
+    if ((rc = host_ensure(ctx, &ctx->h_cc_labels, &ctx->h_cc_labels_cap, n + 1))) return rc;
+    if ((rc = host_ensure(ctx, &ctx->h_cc_stats, &ctx->h_cc_stats_cap, (size_t)F + 1))) return rc;
+    if (n) WN_CK(cudaMemcpyAsync(ctx->h_cc_labels, ctx->d_cc_labels, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    if (F) WN_CK(cudaMemcpyAsync(ctx->h_cc_stats, ctx->d_cc_stats, (size_t)F * sizeof(wn_component_stats), cudaMemcpyDeviceToHost, ctx->st));
+    WN_CK(cudaStreamSynchronize(ctx->st));
+    *labels = ctx->h_cc_labels; *stats = ctx->h_cc_stats;
     return WN_OK;
 }
 

@@ -154,6 +154,10 @@ void wn_launch_selftest_div(unsigned long long seed, int blocks, int iters, unsi
                             cudaStream_t st);
 
 /* text rows of the edge file (wn_kernels_format.cu) */
+void wn_launch_components(const void* edges, int csr16, const unsigned long long* frame_off, const uint32_t* row_off,
+                          int n_frames, int n_sites, unsigned long long max_edges, float threshold,
+                          int* labels, int* work, int* count, int* minidx, unsigned int* kept,
+                          wn_component_stats* stats, cudaStream_t st);
 void wn_launch_format_rows(const wn_edge* edges, const unsigned long long* frame_off,
                            const unsigned long long* row_base, const unsigned int* site_ids, int n_frames,
                            unsigned long long max_edges_per_frame, char* text, int* frame_flags, cudaStream_t st);

@@ -1,0 +1,279 @@
+/*
+ * wn_kernels_graph.cu -- connected components of the per-frame hydrogen-bond networks (sm_100a).
+ *
+ * The first thing the reference's downstream analysis does with edges-frames.xvg.dat
+ * (python/network-analysis.py:141-171) is, per frame: build a graph from the edge rows with
+ * weight = |energy| (:169-171), drop the edges with weight <= threshold (filter_edge_by_weight,
+ * :16-24), drop the nodes left without edges (remove_node_degree, :26-35) and take the connected
+ * component of chosen nodes (nx.node_connected_component, :155).  Here the components of ALL frames
+ * of a batch are labelled on the device, straight from the edge list the pipeline left in HBM
+ * (lock-free union-find; an edge is kept unless |energy| <= threshold, so a NaN energy is kept, as
+ * the Python comparison keeps it):
+ *   wn_k_cc_iota      parent[v] = v
+ *   wn_k_cc_sample    round k = 0, 1: every site joins the k-th kept edge of its own row, then
+ *   wn_k_cc_compress  parent[v] = root(v)                      (neighbour sampling, as in Afforest)
+ *   wn_k_cc_hook      one thread per edge: union of the two ends (nearly always already joined)
+ *   wn_k_cc_flatten   parent[v] = root(v), or -1 for a site without a kept edge
+ *   wn_k_cc_collect   smallest member of every component (atomicMin per warp-level group)
+ *   wn_k_cc_relabel   label[v] = smallest member of v's component; component sizes
+ *   wn_k_cc_stats     per frame: components, largest component, sites in components, kept edges
+ * Trees are linked by a hashed priority of the root (larger hash under smaller hash): linking by the
+ * site index itself builds chains as long as the index order of the input (a lattice-ordered box
+ * gave 4.6 ms for one sampling round), while random priorities keep the expected depth logarithmic.
+ * The labels are made canonical afterwards (smallest member), so the comparison with a CPU
+ * union-find is exact.  Integer work on L2-resident arrays (132 KB of parents per 100k-atom
+ * frame); 12 of the 20 (16) bytes of every edge are read three times (two sampling rounds, one hook).
+ */
+#include "wn_internal.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int CC_THREADS = 256;
+constexpr int CC_SAMPLE_ROUNDS = 2;       /* measured at 250 x 33,333 sites, all edges kept: 0 -> 21.3 ms, 1 -> 7.8, 2 -> 4.1, 3 -> 4.5, 4 -> 4.7 */
+constexpr unsigned FULL = 0xffffffffu;
+
+/* bijective hash of a site index: the linking priority of a root */
+__device__ __forceinline__ uint32_t wn_cc_prio(int v) { return (uint32_t)v * 0x9E3779B1u; }
+
+/* root of v with path halving; concurrent halving writes store a valid ancestor */
+__device__ __forceinline__ int wn_cc_find(volatile int* parent, int v)
+{
+    int p = parent[v];
+    while (p != v) {
+        const int gp = parent[p];
+        if (gp != p) parent[v] = gp;
+        v = p;
+        p = gp;
+    }
+    return v;
+}
+
+/* lock-free union: the root with the larger priority value goes under the other one */
+__device__ __forceinline__ void wn_cc_union(volatile int* parent, int a, int b)
+{
+    int ra = wn_cc_find(parent, a), rb = wn_cc_find(parent, b);
+    while (ra != rb) {
+        const bool a_low = wn_cc_prio(ra) < wn_cc_prio(rb);
+        const int child = a_low ? rb : ra, top = a_low ? ra : rb;
+        const int old = atomicCAS(const_cast<int*>(parent) + child, child, top);
+        if (old == child) break;
+        ra = wn_cc_find(parent, child);                    /* somebody else moved it: follow and retry */
+        rb = wn_cc_find(parent, top);
+    }
+}
+
+__device__ __forceinline__ void wn_cc_edge(const void* __restrict__ edges, bool csr16, unsigned long long e, int& j, float& en)
+{
+    if (csr16) {
+        const uint4 r = reinterpret_cast<const uint4*>(edges)[e];
+        j = (int)r.x; en = __uint_as_float(r.y);
+    } else {
+        const wn_edge* r = reinterpret_cast<const wn_edge*>(edges) + e;
+        j = r->j; en = r->energy;
+    }
+}
+
+__global__ void __launch_bounds__(CC_THREADS)
+wn_k_cc_iota(int* __restrict__ parent, int* __restrict__ minidx, int n_sites)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n_sites) {
+        parent[(size_t)blockIdx.y * n_sites + v] = v;
+        minidx[(size_t)blockIdx.y * n_sites + v] = 0x7fffffff;
+    }
+}
+
+/* Neighbour sampling: every site first joins the K-th kept edge of its own row.  With one union per site
+ * few threads meet at the same root; after two rounds nearly all of a liquid's network is one tree, and the
+ * pass over ALL edges finds both ends under the same root with two reads per edge.  (Hooking all ~12 edges
+ * per site at once was measured 5x slower: every thread of the frame ends up at the giant component's root.) */
+template <bool CSR16>
+__global__ void __launch_bounds__(CC_THREADS)
+wn_k_cc_sample(const void* __restrict__ edges, const unsigned long long* __restrict__ frame_off,
+               const uint32_t* __restrict__ row_off, int n_sites, float threshold, int K, int* __restrict__ parent_all)
+{
+    const int f = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_sites) return;
+    const unsigned long long b = frame_off[f], n = frame_off[f + 1] - b;
+    const uint32_t* ro = row_off + (size_t)f * n_sites;
+    const unsigned long long r0 = ro[v], r1 = (v + 1 < n_sites) ? (unsigned long long)ro[v + 1] : n;
+    int seen = 0;
+    for (unsigned long long e = r0; e < r1; ++e) {
+        int j; float en;
+        wn_cc_edge(edges, CSR16, b + e, j, en);
+        if (fabsf(en) <= threshold) continue;              /* filter_edge_by_weight: removed iff weight <= threshold */
+        if (seen++ == K) { wn_cc_union(parent_all + (size_t)f * n_sites, v, j); break; }
+    }
+}
+
+/* parent[v] = root(v).  In place: no union runs concurrently, so roots are final, and a walk that passes
+ * through v reads either v's old parent or v's root -- both ancestors of v on the way to the same root. */
+__global__ void __launch_bounds__(CC_THREADS)
+wn_k_cc_compress(int* __restrict__ parent_all, int n_sites)
+{
+    const int f = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_sites) return;
+    volatile int* parent = parent_all + (size_t)f * n_sites;
+    int r = v, p = parent[r];
+    while (p != r) { r = p; p = parent[r]; }
+    parent[v] = r;
+}
+
+template <bool CSR16>
+__global__ void __launch_bounds__(CC_THREADS)
+wn_k_cc_hook(const void* __restrict__ edges, const unsigned long long* __restrict__ frame_off,
+             const uint32_t* __restrict__ row_off, int n_sites, float threshold,
+             int* __restrict__ parent_all, int* __restrict__ has_all, unsigned int* __restrict__ kept)
+{
+    const int f = blockIdx.y;
+    const unsigned long long b = frame_off[f], n = frame_off[f + 1] - b;
+    volatile int* parent = parent_all + (size_t)f * n_sites;
+    int* has = has_all + (size_t)f * n_sites;             /* site has a kept edge (remove_node_degree keeps it) */
+    unsigned int mine = 0;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        int i, j;
+        float en;
+        wn_cc_edge(edges, CSR16, b + e, j, en);
+        if (fabsf(en) <= threshold) continue;
+        if (CSR16) {
+            /* row of edge e: largest i with row_off[i] <= e */
+            const uint32_t* ro = row_off + (size_t)f * n_sites;
+            int lo = 0, hi = n_sites - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if ((unsigned long long)__ldg(ro + mid) <= e) lo = mid; else hi = mid - 1;
+            }
+            i = lo;
+        } else {
+            i = (reinterpret_cast<const wn_edge*>(edges) + (b + e))->i;
+        }
+        ++mine;
+        has[i] = 1; has[j] = 1;
+        wn_cc_union(parent, i, j);
+    }
+    /* kept-edge count of the frame */
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(FULL, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kept + f, mine);
+}
+
+/* parent[v] = root(v), or -1 for a site without a kept edge (never visited by a walk) */
+__global__ void __launch_bounds__(CC_THREADS)
+wn_k_cc_flatten(int* __restrict__ parent_all, const int* __restrict__ has_all, int n_sites)
+{
+    const int f = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_sites) return;
+    volatile int* parent = parent_all + (size_t)f * n_sites;
+    int r = -1;
+    if (has_all[(size_t)f * n_sites + v]) {
+        r = v;
+        int p = parent[r];
+        while (p != r) { r = p; p = parent[r]; }
+    }
+    parent[v] = r;
+}
+
+/* smallest member of every component; lanes of a warp under the same root issue one atomic */
+__global__ void __launch_bounds__(CC_THREADS)
+wn_k_cc_collect(const int* __restrict__ root_all, int* __restrict__ minidx_all, int n_sites)
+{
+    const int f = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = v < n_sites ? root_all[(size_t)f * n_sites + v] : -1;
+    const unsigned grp = __match_any_sync(FULL, r);
+    if (r < 0) return;
+    const int lowest = __reduce_min_sync(grp, v);
+    if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicMin(minidx_all + (size_t)f * n_sites + r, lowest);
+}
+
+/* label[v] = smallest member of the component (in place over the roots); sizes collected at the label */
+__global__ void __launch_bounds__(CC_THREADS)
+wn_k_cc_relabel(int* __restrict__ label_all, const int* __restrict__ minidx_all, int* __restrict__ count_all, int n_sites)
+{
+    const int f = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    int l = -1;
+    if (v < n_sites) {
+        const int r = label_all[(size_t)f * n_sites + v];
+        if (r >= 0) l = minidx_all[(size_t)f * n_sites + r];
+    }
+    const unsigned grp = __match_any_sync(FULL, l);
+    if (l < 0) return;
+    /* nobody reads label_all[v] as a root any more: every thread read its own slot above, and the
+     * minidx lookups go to a different array */
+    label_all[(size_t)f * n_sites + v] = l;
+    if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(count_all + (size_t)f * n_sites + l, __popc(grp));
+}
+
+__global__ void __launch_bounds__(CC_THREADS)
+wn_k_cc_stats(const int* __restrict__ labels_all, const int* __restrict__ count_all, const unsigned int* __restrict__ kept,
+              int n_sites, wn_component_stats* __restrict__ stats)
+{
+    const int f = blockIdx.x;
+    const int* labels = labels_all + (size_t)f * n_sites;
+    const int* count = count_all + (size_t)f * n_sites;
+    int comps = 0, largest = 0, nodes = 0;
+    for (int v = threadIdx.x; v < n_sites; v += blockDim.x) {
+        const int l = labels[v];
+        if (l >= 0) ++nodes;
+        if (l == v) { ++comps; largest = max(largest, count[v]); }
+    }
+    __shared__ int s_c[CC_THREADS / 32], s_l[CC_THREADS / 32], s_n[CC_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        comps += __shfl_down_sync(FULL, comps, o);
+        nodes += __shfl_down_sync(FULL, nodes, o);
+        largest = max(largest, __shfl_down_sync(FULL, largest, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = comps; s_l[threadIdx.x >> 5] = largest; s_n[threadIdx.x >> 5] = nodes; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int c = 0, l = 0, nn = 0;
+        for (int w = 0; w < CC_THREADS / 32; ++w) { c += s_c[w]; l = max(l, s_l[w]); nn += s_n[w]; }
+        wn_component_stats r;
+        r.n_components = c; r.largest = l; r.n_nodes = nn; r.n_edges = (int32_t)kept[f];
+        stats[f] = r;
+    }
+}
+
+}  // namespace
+
+/* labels: [F][N] (the union-find parent array while the kernels run); work, count, minidx: [F][N] ints; kept: [F] */
+void wn_launch_components(const void* edges, int csr16, const unsigned long long* frame_off, const uint32_t* row_off,
+                          int n_frames, int n_sites, unsigned long long max_edges, float threshold,
+                          int* labels, int* work, int* count, int* minidx, unsigned int* kept,
+                          wn_component_stats* stats, cudaStream_t st)
+{
+    if (n_frames <= 0) return;
+    const size_t n = (size_t)n_frames * (size_t)n_sites;
+    cudaMemsetAsync(work, 0, n * sizeof(int), st);
+    cudaMemsetAsync(count, 0, n * sizeof(int), st);
+    cudaMemsetAsync(kept, 0, (size_t)n_frames * sizeof(unsigned int), st);
+    if (n_sites > 0) {
+        dim3 gv((n_sites + CC_THREADS - 1) / CC_THREADS, n_frames);
+        wn_k_cc_iota<<<gv, CC_THREADS, 0, st>>>(labels, minidx, n_sites);
+        if (max_edges > 0) {
+            for (int k = 0; k < CC_SAMPLE_ROUNDS; ++k) {
+                if (csr16) wn_k_cc_sample<true><<<gv, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, k, labels);
+                else wn_k_cc_sample<false><<<gv, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, k, labels);
+                wn_k_cc_compress<<<gv, CC_THREADS, 0, st>>>(labels, n_sites);
+            }
+            /* a few edges per thread: enough CTAs to fill the device, bounded grid for huge frames */
+            const unsigned long long want = (max_edges + CC_THREADS * 4 - 1) / (CC_THREADS * 4);
+            dim3 ge((unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(want, 1), 65535), n_frames);
+            if (csr16)
+                wn_k_cc_hook<true><<<ge, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, labels, work, kept);
+            else
+                wn_k_cc_hook<false><<<ge, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, labels, work, kept);
+        }
+        wn_k_cc_flatten<<<gv, CC_THREADS, 0, st>>>(labels, work, n_sites);
+        wn_k_cc_collect<<<gv, CC_THREADS, 0, st>>>(labels, minidx, n_sites);
+        wn_k_cc_relabel<<<gv, CC_THREADS, 0, st>>>(labels, minidx, count, n_sites);
+    }
+    wn_k_cc_stats<<<n_frames, CC_THREADS, 0, st>>>(labels, count, kept, n_sites, stats);
+}

@@ -118,6 +118,12 @@ bool HydrogenBondEdges::formatLastBatch(const std::vector<int>& frameNumbers, co
     return true;
 }
 
+void HydrogenBondEdges::componentsOfLastBatch(float weightThreshold, const int32_t** labels, const wn_component_stats** stats)
+{
+    const int rc = wn_components(ctx_, weightThreshold, labels, stats);
+    if (rc != WN_OK) raise("HydrogenBondEdges::componentsOfLastBatch: wn_components", rc, ctx_);
+}
+
 std::vector<HydrogenBond> HydrogenBondEdges::toHydrogenBonds(const HydrogenBondBatch& batch, int frame,
                                                              const std::vector<SiteInfo_ptr>& sites)
 {

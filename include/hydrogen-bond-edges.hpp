@@ -78,6 +78,12 @@ public:
     bool formatLastBatch(const std::vector<int>& frameNumbers, const std::vector<unsigned>& ids,
                          const char** text, uint64_t* bytes);
 
+    // Connected components of the networks of the LAST calculate() (python/network-analysis.py:141-171:
+    // edges with |energy| <= weightThreshold dropped, then sites without an edge dropped).
+    // labels[f * nSites + s] = smallest site of s's component in frame f, -1 without a kept edge;
+    // library-owned pinned memory, valid until the next call.
+    void componentsOfLastBatch(float weightThreshold, const int32_t** labels, const wn_component_stats** stats);
+
     // Convenience: one frame's result as the reference's std::vector<HydrogenBond>
     // (pair order, direction FORWARD), given the SiteInfo_ptr table of the caller.
     static std::vector<HydrogenBond> toHydrogenBonds(const HydrogenBondBatch& batch, int frame,

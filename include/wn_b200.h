@@ -234,6 +234,25 @@ int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);
  * *text: library-owned pinned host memory, valid until the next call on this context.
  * Returns WN_ERR_OVERFLOW (nothing usable in *text) if some id needs more than 6 digits or a
  * value more than 8 characters: format that batch with a general host formatter instead. */
+/* ---- connected components of the per-frame networks (python/network-analysis.py:141-171) ----
+ * Works on the edge list of the LAST wn_hbond_batch* call of this context (either layout), on the
+ * device.  Per frame, as the reference's downstream script does with the edge file: an edge is
+ * dropped iff |energy| <= weight_threshold (filter_edge_by_weight, :16-24; the script uses 0.0 on
+ * the 4-decimal text, i.e. 5e-5 on the binary value), sites left without an edge are dropped
+ * (remove_node_degree, :26-35), the rest is split into connected components
+ * (nx.node_connected_component, :155).
+ * labels[f * n_sites + s]: smallest site index of the component of site s in frame f, or -1 if s has
+ * no kept edge.  stats[f]: see wn_component_stats.  Both are library-owned and valid until the next
+ * call on this context: pinned host memory when the batch came from host frames, device memory when
+ * it was a *_dev batch (like the batch result itself). */
+typedef struct wn_component_stats {
+    int32_t n_components;   /* components with at least one edge                 */
+    int32_t largest;        /* sites in the largest component                    */
+    int32_t n_nodes;        /* sites with at least one kept edge                 */
+    int32_t n_edges;        /* kept edges                                        */
+} wn_component_stats;
+int wn_components(wn_ctx* ctx, float weight_threshold, const int32_t** labels, const wn_component_stats** stats);
+
 int wn_format_edges(wn_ctx* ctx, const int32_t* frame_numbers, const uint32_t* site_ids,
                     int32_t n_site_ids, const char** text, uint64_t* text_bytes);
 

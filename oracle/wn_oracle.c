@@ -534,3 +534,41 @@ size_t wno_frame_hbonds_tric(const float* frame_xyz, int natoms,
     free(tmp); free(pairs); free(h_off); free(h_xyz); free(site_xyz); free(wrapped);
     return ne <= cap ? ne : (size_t)-1;
 }
+
+
+/* ---- connected components (python/network-analysis.py:16-35, 141-171) ---- */
+static int cc_root(int32_t* parent, int v)
+{
+    int r = v;
+    while (parent[r] != r) r = parent[r];
+    while (parent[v] != r) { const int nx = parent[v]; parent[v] = r; v = nx; }
+    return r;
+}
+
+void wno_components(const wno_edge* edges, size_t n_edges, int n_sites, float threshold,
+                    int32_t* labels, int32_t stats[4])
+{
+    int32_t* parent = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_sites > 0 ? n_sites : 1));
+    int32_t* count = (int32_t*)calloc((size_t)(n_sites > 0 ? n_sites : 1), sizeof(int32_t));
+    unsigned char* has = (unsigned char*)calloc((size_t)(n_sites > 0 ? n_sites : 1), 1);
+    int32_t kept = 0, comps = 0, largest = 0, nodes = 0;
+    for (int v = 0; v < n_sites; ++v) parent[v] = v;
+    for (size_t e = 0; e < n_edges; ++e) {
+        const float w = fabsf(edges[e].energy);            /* weight=abs(float(line[2]))  :169 */
+        if (w <= threshold) continue;                      /* removed iff weight <= threshold  :22 */
+        ++kept;
+        has[edges[e].i] = has[edges[e].j] = 1;
+        const int a = cc_root(parent, edges[e].i), b = cc_root(parent, edges[e].j);
+        if (a < b) parent[b] = a; else if (b < a) parent[a] = b;   /* root = smallest member */
+    }
+    for (int v = 0; v < n_sites; ++v) {
+        if (!has[v]) { labels[v] = -1; continue; }         /* remove_node_degree  :31-34 */
+        labels[v] = cc_root(parent, v);
+        ++count[labels[v]];
+        ++nodes;
+    }
+    for (int v = 0; v < n_sites; ++v)
+        if (labels[v] == v) { ++comps; if (count[v] > largest) largest = count[v]; }
+    stats[0] = comps; stats[1] = largest; stats[2] = nodes; stats[3] = kept;
+    free(parent); free(count); free(has);
+}

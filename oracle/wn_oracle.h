@@ -141,6 +141,16 @@ size_t wno_frame_hbonds_tric(const float* frame_xyz, int natoms,
                              wno_edge* edges, size_t cap, double* stats,
                              uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties);
 
+/* ---- connected components of one frame's network -----------------------------------------
+ * Restates what python/network-analysis.py does with the edge rows of a frame before any graph
+ * metric: weight = |energy| (:169-171); filter_edge_by_weight removes an edge iff weight <= threshold
+ * (:16-24; NaN compares false and stays); remove_node_degree removes the sites without an edge
+ * (:26-35); nx.node_connected_component / connected_components split the rest (:155).
+ * labels[s] = smallest site index of the component of s, -1 if s kept no edge.
+ * stats = {components, largest component (sites), sites in components, kept edges}. */
+void wno_components(const wno_edge* edges, size_t n_edges, int n_sites, float threshold,
+                    int32_t* labels, int32_t stats[4]);
+
 #ifdef __cplusplus
 }
 #endif

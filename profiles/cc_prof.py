@@ -1,0 +1,19 @@
+#!/usr/bin/env python
+"""wn_components alone on a device-resident batch (kernel experiments): python profiles/cc_prof.py [frames]"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, wn_pkg
+capi = wn_pkg.load_capi()
+n, F = 33333, int(sys.argv[1]) if len(sys.argv) > 1 else 250
+ctx = capi.Context(0); ctx.set_water_sites(n); ctx.set_batch_frames(F)
+dev = ctx.dev_alloc(F * 3 * n * 12)
+ctx.synth_frames_dev(n, 0, F, dev, seed=1234)
+for layout in (capi.LAYOUT_EDGES, capi.LAYOUT_CSR16):
+    ctx.hbond_batch_ex(dev, F, 3 * n, on_device=True, layout=layout)
+    lab, st = ctypes.c_void_p(), ctypes.c_void_p()
+    for thr in (0.0, 0.0, 1.0, 3.0):
+        ctx.timer_start()
+        ctx._ck(ctx.L.wn_components(ctx.h, thr, ctypes.byref(lab), ctypes.byref(st)))
+        ms = ctx.timer_stop()
+        s = np.zeros(F, capi.COMPONENT_DTYPE); ctx.d2h(s, st.value)
+        print("layout", layout, "thr", thr, "ms %.3f" % ms, s[0])

@@ -153,6 +153,30 @@ int main()
             std::vector<unsigned> wide(ids);
             for (unsigned& v : wide) v += 10000000u;
             CHECK(!hb.formatLastBatch({42}, wide, &txt, &nbytes));
+            // connected components of that frame against a plain union-find on the host
+            {
+                const int32_t* labels = nullptr; const wn_component_stats* cs = nullptr;
+                const float thr = 0.5f;
+                hb.componentsOfLastBatch(thr, &labels, &cs);
+                std::vector<int> par((size_t)n_waters), has((size_t)n_waters, 0);
+                for (int s = 0; s < n_waters; ++s) par[s] = s;
+                auto root = [&](int v) { while (par[v] != v) v = par[v] = par[par[v]]; return v; };
+                int kept = 0;
+                for (uint64_t k = bl.offsets[0]; k < bl.offsets[1]; ++k) {
+                    const wn_edge& e = bl.edges[k];
+                    if (std::fabs(e.energy) <= thr) continue;
+                    ++kept; has[e.i] = has[e.j] = 1;
+                    const int a = root(e.i), b = root(e.j);
+                    if (a < b) par[b] = a; else if (b < a) par[a] = b;
+                }
+                int comps = 0, nodes = 0;
+                for (int s = 0; s < n_waters; ++s) {
+                    const int want = has[s] ? root(s) : -1;
+                    CHECK(labels[s] == want);
+                    nodes += has[s]; comps += (want == s);
+                }
+                CHECK(cs[0].n_edges == kept && cs[0].n_nodes == nodes && cs[0].n_components == comps);
+            }
         }
         // per-frame site lists through the batcher: a frame restricted to the first 100 waters gives the
         // edges of the full frame whose endpoints are both < 100 (indices are list positions)

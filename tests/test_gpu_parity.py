@@ -795,3 +795,63 @@ def test_compact_csr16_layout(ctx, oracle, capi):
         cnt = np.diff(np.append(ro[f], fo[f + 1] - fo[f]).astype(np.int64))
         i = np.repeat(np.arange(n), cnt)
         assert np.array_equal(i, full["edges"]["i"][int(fo[f]):int(fo[f + 1])])
+
+
+def test_connected_components_match_oracle(ctx, oracle, capi):
+    """wn_components (union-find on the device-resident edge list) against the CPU restatement of the
+    reference script's filter + connected components: canonical labels and per-frame counts, exact."""
+    n, nf = 4000, 3
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 0, nf)
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames)
+    fo = res["frame_offsets"]
+
+    def check(thr, labels, stats):
+        for f in range(nf):
+            e = res["edges"][int(fo[f]):int(fo[f + 1])]
+            lab, st = oracle.components(e, n, thr)
+            assert np.array_equal(labels[f], lab), (thr, f)
+            assert [stats[f][k] for k in ("n_components", "largest", "n_nodes", "n_edges")] == list(st), (thr, f)
+
+    for thr in (0.0, 5e-5, 1.0, 3.0, 1e9):
+        labels, stats = ctx.components(thr)
+        check(thr, labels, stats)
+    # giant component at threshold 0, fragments at a high threshold
+    _, s0 = ctx.components(0.0)
+    _, s3 = ctx.components(3.0)
+    assert s0["largest"][0] > n // 2 and s3["n_components"][0] > s0["n_components"][0]
+    # compact layout (row index from the CSR offsets) and a device-resident multi-pass batch
+    ctx.set_batch_frames(2)
+    ctx.hbond_batch_ex(frames, layout=capi.LAYOUT_CSR16)
+    labels, stats = ctx.components(1.0)
+    check(1.0, labels, stats)
+    dev = ctx.dev_alloc(frames.nbytes)
+    ctx.h2d(dev, frames)
+    ctx.hbond_batch_dev(dev, nf, 3 * n)
+    labels, stats = ctx.components(1.0)
+    check(1.0, labels, stats)
+    ctx.dev_free(dev)
+    ctx.set_batch_frames(0)
+
+
+def test_connected_components_small_and_degenerate(ctx, oracle):
+    """Mixed site tables, empty frames, coincident sites (NaN energies are kept, as in the script)."""
+    rng = np.random.default_rng(3)
+    n = 300
+    o = rng.uniform(0, 1.2, size=(n, 3))
+    o[10] = o[11]                                  # coincident pair: NaN cosine/energy paths
+    h1 = o + rng.normal(size=(n, 3)) * 0.06
+    h2 = o + rng.normal(size=(n, 3)) * 0.06
+    frames = np.stack([o, h1, h2], axis=1).reshape(1, 3 * n, 3).astype(np.float32)
+    frames = np.concatenate([frames, frames * 100.0])          # second frame: nothing within reach
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames)
+    fo = res["frame_offsets"]
+    for thr in (0.0, 0.7):
+        labels, stats = ctx.components(thr)
+        for f in range(2):
+            lab, st = oracle.components(res["edges"][int(fo[f]):int(fo[f + 1])], n, thr)
+            assert np.array_equal(labels[f], lab)
+            assert [stats[f][k] for k in ("n_components", "largest", "n_nodes", "n_edges")] == list(st)
+    assert stats["n_edges"][1] == 0 and np.all(labels[1] == -1)

@@ -201,6 +201,18 @@ def frame_hbonds(frame, site_atom, h_atom, site_type, first_limit=None, ties=Non
     return edges[:ne].copy(), stats, int(npairs.value), int(nevals.value)
 
 
+def components(edges, n_sites, threshold=0.0):
+    """Connected components of one frame's edge list: (labels[n_sites], stats[4])."""
+    edges = np.ascontiguousarray(edges, dtype=EDGE_DTYPE)
+    labels = np.empty(max(n_sites, 1), dtype=np.int32)
+    stats = np.zeros(4, dtype=np.int32)
+    fn = lib().wno_components
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    fn(edges.ctypes.data, len(edges), n_sites, threshold, labels.ctypes.data, stats.ctypes.data)
+    return labels[:n_sites].copy(), stats
+
+
 # ------------------------------------------------------------- synthetic input
 def synth_box(n_waters, seed=1234, model=MODEL_TIP3P):
     b = SynthBox()
