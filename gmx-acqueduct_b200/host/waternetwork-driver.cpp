@@ -1,0 +1,300 @@
+// waternetwork-driver.cpp -- the waternetwork analysis as a standalone program, without GROMACS.
+//
+// Walks a multi-frame .gro trajectory through the flow of the reference's trajectory-analysis module
+// (reference src/waternetwork.cpp): initAnalysis (:392-500: makeSites for the protein and the solvent
+// selection, solvent ids offset, nodes file, edges file header), analyzeFrame (:503-667: site list =
+// protein sites then waters, pair search, make_edges, edge rows, the two statistics rows) and
+// finishAnalysis (:670-676), with the search/geometry/energy stage on the GPU through
+// CudaFindPairs' sibling HydrogenBondEdges + FrameBatcher.  It exists because the real
+// gmx::TrajectoryAnalysisModule glue cannot be built where GROMACS is absent; the files it writes
+// are the ones python/network-analysis.py reads (nodes-list.xvg.dat, edges-frames.xvg.dat).
+//
+// What it does not do (out of scope here): GROMACS selections (the solvent is chosen by residue
+// name, the protein is everything else), the alpha-shape filter of buried waters (as_->locate, :533 --
+// a per-frame list of water indices can be supplied instead with -buried), trajectory formats other
+// than .gro, the xvg legend headers of AnalysisDataPlotModule (data rows only, " %11.3f" time and
+// " %8.3f" values, the plot module's default formats).
+//
+//   wn_waternetwork -f traj.gro [-edges edges-frames.xvg] [-nodes nodes-list.xvg]
+//                   [-ohb hydrogen-bonds-num.xvg] [-obw buried-waters-num.xvg]
+//                   [-solvent SOL,WAT,HOH,TIP3] [-buried lists.txt] [-pbc] [-batch 256] [-device 0]
+//                   [-don 5.5] [-doff 6.5] [-aon 0.25] [-aoff 0.0] [-bug-compat 0|1]
+// File name options take the reference's base names: ".dat" is appended to -edges/-nodes (:461,:485).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "edge-file-writer.hpp"
+#include "hydrogen-bond-edges.hpp"
+#include "make-sites.hpp"
+
+namespace {
+
+struct GroFrame {
+    std::vector<float> xyz;          // natoms * 3, nm
+    float box[3][3];                 // GROMACS matrix (rows = box vectors)
+    double time;
+    bool has_time;
+};
+
+std::string trim(const std::string& s)
+{
+    size_t a = 0, b = s.size();
+    while (a < b && (s[a] == ' ' || s[a] == '\t' || s[a] == '\r')) ++a;
+    while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\t' || s[b - 1] == '\r' || s[b - 1] == '\n')) --b;
+    return s.substr(a, b - a);
+}
+
+// One frame of a .gro file.  Fixed columns: resnr 0-5, resname 5-10, atom name 10-15, atom nr 15-20,
+// then the coordinates in equal-width fields (8.3 by default; the width is taken from the distance
+// between the decimal points, as GROMACS does).  names/resnr are filled from the first frame only.
+bool readGroFrame(std::istream& in, GroFrame& fr, std::vector<std::string>* atomName, std::vector<std::string>* resName,
+                  std::vector<int>* resNr)
+{
+    std::string title, line;
+    if (!std::getline(in, title)) return false;
+    if (trim(title).empty() && in.peek() == EOF) return false;
+    if (!std::getline(in, line)) return false;
+    const long natoms = std::strtol(line.c_str(), nullptr, 10);
+    if (natoms < 0) throw std::runtime_error(".gro: bad atom count line: " + line);
+    fr.has_time = false; fr.time = 0.0;
+    const size_t tp = title.rfind("t=");
+    if (tp != std::string::npos) { fr.time = std::strtod(title.c_str() + tp + 2, nullptr); fr.has_time = true; }
+    fr.xyz.assign((size_t)natoms * 3, 0.f);
+    if (atomName) { atomName->clear(); resName->clear(); resNr->clear(); }
+    for (long a = 0; a < natoms; ++a) {
+        if (!std::getline(in, line)) throw std::runtime_error(".gro: file ends inside a frame");
+        if (line.size() < 44) throw std::runtime_error(".gro: short atom line: " + line);
+        if (atomName) {
+            resNr->push_back((int)std::strtol(line.substr(0, 5).c_str(), nullptr, 10));
+            resName->push_back(trim(line.substr(5, 5)));
+            atomName->push_back(trim(line.substr(10, 5)));
+        }
+        const size_t p1 = line.find('.', 20), p2 = p1 == std::string::npos ? p1 : line.find('.', p1 + 1);
+        const size_t w = (p1 != std::string::npos && p2 != std::string::npos) ? p2 - p1 : 8;
+        for (int c = 0; c < 3; ++c)
+            fr.xyz[(size_t)a * 3 + c] = (float)std::strtod(line.substr(20 + (size_t)c * w, w).c_str(), nullptr);
+    }
+    if (!std::getline(in, line)) throw std::runtime_error(".gro: missing box line");
+    double b[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::istringstream bs(line);
+    for (int k = 0; k < 9 && (bs >> b[k]); ++k) {}
+    // v1(x) v2(y) v3(z) v1(y) v1(z) v2(x) v2(z) v3(x) v3(y)
+    fr.box[0][0] = (float)b[0]; fr.box[1][1] = (float)b[1]; fr.box[2][2] = (float)b[2];
+    fr.box[0][1] = (float)b[3]; fr.box[0][2] = (float)b[4];
+    fr.box[1][0] = (float)b[5]; fr.box[1][2] = (float)b[6];
+    fr.box[2][0] = (float)b[7]; fr.box[2][1] = (float)b[8];
+    return true;
+}
+
+// element string of an atom from its name (a .gro file carries no elements): leading digits skipped,
+// then the first letter -- "HW1", "1HH1" -> "H", "OW" -> "O".
+std::string elementOf(const std::string& name)
+{
+    for (char ch : name)
+        if (!(ch >= '0' && ch <= '9')) return std::string(1, ch);
+    return std::string();
+}
+
+struct Options {
+    std::string traj, edges = "edges-frames.xvg", nodes = "nodes-list.xvg", ohb = "hydrogen-bonds-num.xvg",
+                obw = "buried-waters-num.xvg", buried;
+    std::set<std::string> solvent{"SOL", "WAT", "HOH", "TIP3", "SPC"};
+    bool pbc = false, bugCompat = true;
+    int batch = 256, device = 0;
+    double don = 5.5, doff = 6.5, aon = 0.25, aoff = 0.0;
+};
+
+Options parse(int argc, char** argv)
+{
+    Options o;
+    for (int k = 1; k < argc; ++k) {
+        const std::string a = argv[k];
+        auto val = [&]() -> std::string {
+            if (k + 1 >= argc) throw std::runtime_error("missing value after " + a);
+            return argv[++k];
+        };
+        if (a == "-f") o.traj = val();
+        else if (a == "-edges") o.edges = val();
+        else if (a == "-nodes") o.nodes = val();
+        else if (a == "-ohb") o.ohb = val();
+        else if (a == "-obw") o.obw = val();
+        else if (a == "-buried") o.buried = val();
+        else if (a == "-pbc") o.pbc = true;
+        else if (a == "-batch") o.batch = std::atoi(val().c_str());
+        else if (a == "-device") o.device = std::atoi(val().c_str());
+        else if (a == "-don") o.don = std::atof(val().c_str());
+        else if (a == "-doff") o.doff = std::atof(val().c_str());
+        else if (a == "-aon") o.aon = std::atof(val().c_str());
+        else if (a == "-aoff") o.aoff = std::atof(val().c_str());
+        else if (a == "-bug-compat") o.bugCompat = std::atoi(val().c_str()) != 0;
+        else if (a == "-solvent") {
+            o.solvent.clear();
+            std::istringstream ss(val());
+            for (std::string t; std::getline(ss, t, ',');) if (!t.empty()) o.solvent.insert(t);
+        } else throw std::runtime_error("unknown option " + a);
+    }
+    if (o.traj.empty()) throw std::runtime_error("usage: wn_waternetwork -f traj.gro [options] (see the file header)");
+    if (o.batch < 1) o.batch = 1;
+    return o;
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    try {
+        const Options opt = parse(argc, argv);
+        std::ifstream in(opt.traj);
+        if (!in) throw std::runtime_error("cannot open " + opt.traj);
+
+        // ---- topology from the first frame (initAnalysis, :392-425)
+        GroFrame fr;
+        std::vector<std::string> atomName, resNameAtom;
+        std::vector<int> resNr;
+        if (!readGroFrame(in, fr, &atomName, &resNameAtom, &resNr)) throw std::runtime_error("empty trajectory");
+        const int natoms = (int)atomName.size();
+        TopologyView top;
+        top.atomName = atomName;
+        top.element.resize((size_t)natoms);
+        top.resIndex.resize((size_t)natoms);
+        for (int a = 0; a < natoms; ++a) {
+            top.element[a] = elementOf(atomName[a]);
+            if (a == 0 || resNr[a] != resNr[a - 1] || resNameAtom[a] != resNameAtom[a - 1]) top.resName.push_back(resNameAtom[a]);
+            top.resIndex[a] = (int)top.resName.size() - 1;
+        }
+        std::vector<int> proteinSel, solventSel;
+        for (int a = 0; a < natoms; ++a) (opt.solvent.count(resNameAtom[a]) ? solventSel : proteinSel).push_back(a);
+        if (solventSel.size() % 3) throw std::runtime_error("solvent selection is not a whole number of 3-site waters");
+
+        std::vector<SiteInfo> proteinSites, solventSites;
+        makeSites(proteinSel, top, proteinSites);
+        std::clog << "Protein has : " << proteinSites.size() << " Sites of out " << proteinSel.size() << " atoms." << std::endl;
+        // The reference's makeSites walks TOPOLOGY indices (:150-166) but analyzeFrame reads the water w at
+        // SELECTION position 3w (:564-575): the solvent sites are the oxygens of the selection in order.
+        {
+            std::vector<SiteInfo> all;
+            makeSites(solventSel, top, all);
+            solventSites = all;
+        }
+        std::clog << "Solvent has : " << solventSites.size() << " Sites of out " << solventSel.size() << " atoms." << std::endl;
+        if (solventSites.size() * 3 != solventSel.size())
+            throw std::runtime_error("solvent: expected one site (OW/O) per 3-atom water");
+        offsetSolventIds(solventSites, proteinSites.size());
+        std::clog << "Total number of sites : " << proteinSites.size() + solventSites.size() << std::endl;
+
+        // ---- site table: protein sites, then every water (:547-576); atom indices into the frame as read
+        const size_t nP = proteinSites.size(), nW = solventSites.size();
+        std::vector<SiteInfo> table;
+        std::vector<std::vector<int> > hydrogens;
+        for (const SiteInfo& s : proteinSites) {
+            SiteInfo t = s;
+            std::vector<int> h;
+            for (int hi : proteinHydrogenAtoms(s, opt.bugCompat)) {          // positions in the protein selection (:554)
+                if (hi < 0 || (size_t)hi >= proteinSel.size()) throw std::out_of_range("protein hydrogen index (proteinPoints.at)");
+                h.push_back(proteinSel[(size_t)hi]);
+            }
+            if ((size_t)s.atmIndex >= proteinSel.size()) throw std::out_of_range("protein site index (proteinPoints.at)");
+            t.atmIndex = (unsigned)proteinSel[(size_t)s.atmIndex];             // proteinPoints.at(info.atmIndex) (:559)
+            table.push_back(t);
+            hydrogens.push_back(h);
+        }
+        for (size_t w = 0; w < nW; ++w) {
+            SiteInfo t = solventSites[w];
+            std::vector<int> h;
+            for (int hi : waterHydrogenAtoms((int)w, solventSites[w])) h.push_back(solventSel[(size_t)hi]);   // :569
+            t.atmIndex = (unsigned)solventSel[3 * w];                                                        // :575
+            table.push_back(t);
+            hydrogens.push_back(h);
+        }
+        std::vector<unsigned> ids;
+        for (const SiteInfo& s : table) ids.push_back(s.id);
+
+        // ---- nodes file (:461-482) and edges header (:485-499)
+        if (!opt.nodes.empty()) {
+            std::ofstream nf(opt.nodes + ".dat");
+            EdgeFileWriter::writeNodesHeader(nf);
+            for (const SiteInfo& s : proteinSites) EdgeFileWriter::writeNode(nf, s);
+            for (const SiteInfo& s : solventSites) EdgeFileWriter::writeNode(nf, s);
+        }
+        std::ofstream ef;
+        EdgeFileWriter* writer = nullptr;
+        if (!opt.edges.empty()) {
+            ef.open(opt.edges + ".dat");
+            writer = new EdgeFileWriter(ef, ids);
+            writer->writeHeader();
+        }
+        std::ofstream ohb, obw;
+        if (!opt.ohb.empty()) ohb.open(opt.ohb);
+        if (!opt.obw.empty()) obw.open(opt.obw);
+
+        // ---- optional per-frame water lists (what as_->locate leaves in filteredPoints, :533)
+        std::ifstream buried;
+        if (!opt.buried.empty()) { buried.open(opt.buried); if (!buried) throw std::runtime_error("cannot open " + opt.buried); }
+
+        HydrogenBondEdges hb(opt.device);
+        hb.setRadiusShift((float)opt.don, (float)opt.doff);
+        hb.setAngleShift((float)opt.aon, (float)opt.aoff);
+        hb.setSites(table, hydrogens);
+
+        std::vector<double> times;
+        std::vector<size_t> filtered;
+        char row[256];
+        uint64_t total_edges = 0;
+        FrameBatcher batcher(hb, natoms, opt.batch,
+            [&](int frnr, const wn_edge* e, size_t n, const wn_frame_stats& st) {
+                if (writer) writer->writeFrame(frnr, e, n);                         // :638-652
+                total_edges += n;
+                const double t = times[(size_t)frnr];
+                if (obw.is_open()) {                                                 // :654-657
+                    std::snprintf(row, sizeof row, " %11.3f %8.3f %8.3f\n", t, (double)filtered[(size_t)frnr], 0.0);
+                    obw << row;
+                }
+                if (ohb.is_open()) {                                                 // :659-666
+                    std::snprintf(row, sizeof row, " %11.3f %8.3f %8.3f %8.3f %8.3f %8.3f %8.3f\n", t, st.num_sites,
+                                  st.num_edges, st.ratio, 0.0, 0.0, 0.0);
+                    ohb << row;
+                }
+            });
+
+        int frnr = 0;
+        do {
+            if ((int)(fr.xyz.size() / 3) != natoms) throw std::runtime_error(".gro: atom count changes between frames");
+            times.push_back(fr.has_time ? fr.time : (double)frnr);
+            const float (*box)[3] = opt.pbc ? fr.box : nullptr;
+            if (buried.is_open()) {
+                std::string line;
+                if (!std::getline(buried, line)) throw std::runtime_error("-buried: fewer lines than frames");
+                std::vector<int32_t> rows;
+                for (size_t s = 0; s < nP; ++s) rows.push_back((int32_t)s);
+                std::istringstream ls(line);
+                size_t cnt = 0;
+                for (long w; ls >> w; ++cnt) {
+                    if (w < 0 || (size_t)w >= nW) throw std::out_of_range("-buried: water index (solventSites_.at)");
+                    rows.push_back((int32_t)(nP + (size_t)w));
+                }
+                filtered.push_back(cnt);
+                batcher.push(frnr, fr.xyz.data(), box, rows);
+            } else {
+                filtered.push_back(nW);
+                if (box) batcher.push(frnr, fr.xyz.data(), box); else batcher.push(frnr, fr.xyz.data());
+            }
+            ++frnr;
+        } while (readGroFrame(in, fr, nullptr, nullptr, nullptr));
+        batcher.finish();                                                            // finishAnalysis (:670)
+        delete writer;
+        std::clog << frnr << " frames, " << total_edges << " hydrogen bonds" << std::endl;
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "wn_waternetwork: " << e.what() << std::endl;
+        return 1;
+    }
+}

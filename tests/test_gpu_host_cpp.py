@@ -28,3 +28,96 @@ def test_cpp_host_mirror_fails_loudly_without_gpu():
         g.build()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def _write_gro(path, frames, box, with_time=True):
+    """Multi-frame .gro of a pure water box (OW, HW1, HW2 per SOL residue), 8.3 coordinate fields."""
+    nf, natoms, _ = frames.shape
+    with open(path, "w") as fh:
+        for f in range(nf):
+            fh.write("synthetic water box%s\n" % (" t= %9.5f" % (2.0 * f) if with_time else ""))
+            fh.write("%5d\n" % natoms)
+            for a in range(natoms):
+                w = a // 3
+                fh.write("%5d%-5s%5s%5d%8.3f%8.3f%8.3f\n" % ((w + 1) % 100000, "SOL", ("OW", "HW1", "HW2")[a % 3],
+                                                           (a + 1) % 100000, *frames[f, a]))
+            fh.write("%10.5f%10.5f%10.5f\n" % (box, box, box))
+
+
+def _parse_back(frames):
+    """What the driver reads: every coordinate through its 8.3 text field and (float)strtod."""
+    import numpy as np
+    txt = np.char.mod("%8.3f", frames.astype(np.float64))
+    return txt.astype(np.float64).astype(np.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pbc", [False, True])
+def test_standalone_driver_writes_the_reference_files(tmp_path, pbc):
+    """wn_waternetwork on a synthetic .gro trajectory: edges file, nodes file and statistics rows equal
+    what the oracle (open boundary) / the periodic oracle gives for the same parsed coordinates."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import wn_oracle_py as o
+    n, nf = 216, 3
+    sb = o.synth_box(n, model=o.MODEL_SPC)
+    frames = o.synth_frames(sb, 0, nf)
+    box = float(sb.box)
+    gro = str(tmp_path / "traj.gro")
+    _write_gro(gro, frames, box)
+    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
+    assert os.path.exists(exe), "build first: __graft_entry__.build()"
+    args = [exe, "-f", gro, "-edges", str(tmp_path / "edges"), "-nodes", str(tmp_path / "nodes"),
+            "-ohb", str(tmp_path / "ohb.xvg"), "-obw", str(tmp_path / "obw.xvg"), "-batch", "2"]
+    if pbc:
+        args.append("-pbc")
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Solvent has : 216 Sites of out 648 atoms." in r.stderr
+
+    parsed = _parse_back(frames)
+    sa, ha, ty = o.water_site_table(n)
+    boxf = np.float32(np.float64("%10.5f" % box))
+    want = "%6s%8s%6s%6s%8s%6s%8s%8s%8s" % ("#Id", "AtmId", "ResId", "Id", "AtmId", "ResId", "Energy", "Length", "Cos\n")
+    ohb = ""
+    for f in range(nf):
+        if pbc:
+            e, st, _, _ = o.frame_hbonds_pbc(parsed[f], sa, ha, ty, np.array([boxf] * 3, np.float32))
+        else:
+            e, st, _, _ = o.frame_hbonds(parsed[f], sa, ha, ty)
+        want += "#--- frame %d ---\n" % f
+        # ids: solvent site w has id (w + 1) + nProtein + 1 = w + 2  (src/waternetwork.cpp:420-423)
+        want += "".join("%6d%6d%8.4f%8.4f%8.4f\n" % (a + 2, b + 2, en, ln, cs)
+                        for a, b, en, ln, cs in zip(e["i"], e["j"], e["energy"].astype(np.float64),
+                                                    e["length"].astype(np.float64), e["cosine"].astype(np.float64)))
+        ohb += " %11.3f %8.3f %8.3f %8.3f %8.3f %8.3f %8.3f\n" % (2.0 * f, n, len(e), len(e) / n, 0, 0, 0)
+    got = open(str(tmp_path / "edges.dat")).read()
+    assert got == want
+    assert open(str(tmp_path / "ohb.xvg")).read() == ohb
+    assert open(str(tmp_path / "obw.xvg")).read() == "".join(" %11.3f %8.3f %8.3f\n" % (2.0 * f, n, 0) for f in range(nf))
+    nodes = open(str(tmp_path / "nodes.dat")).read().splitlines()
+    assert len(nodes) == 1 + n and nodes[0].split() == ["#Id", "AtmId", "Name", "ResId", "Res", "Type", "Hyd"]
+    assert nodes[1].split()[:3] == ["2", "0", "OW"]
+
+
+def test_standalone_driver_fails_loudly_without_gpu(tmp_path):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    gro = tmp_path / "t.gro"
+    gro.write_text("w\n    3\n    1SOL     OW    1   0.100   0.100   0.100\n    1SOL    HW1    2   0.190   0.100   0.100\n"
+                   "    1SOL    HW2    3   0.070   0.190   0.100\n   1.00000   1.00000   1.00000\n")
+    r = subprocess.run([exe, "-f", str(gro), "-edges", str(tmp_path / "e"), "-nodes", str(tmp_path / "n"),
+                        "-ohb", "", "-obw", ""], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+    # the topology part runs before the device is touched: nodes file of the one water
+    rows = (tmp_path / "n.dat").read_text().splitlines()
+    assert rows[1].split() == ["2", "0", "OW", "0", "SOL", "2", "2"]
