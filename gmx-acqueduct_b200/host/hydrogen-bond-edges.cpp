@@ -195,6 +195,7 @@ void FrameBatcher::flush()
         b = engine_.calculate(buf_.data(), b3.empty() ? nullptr : b3.data(), (int)frnr_.size(), natoms_, sub_off_.data(),
                               sub_sites_.data());
     }
+    if (batch_hook_) batch_hook_(frnr_, b);
     for (int f = 0; f < b.n_frames; ++f)
         sink_(frnr_[f], b.edges + b.offsets[f], (size_t)(b.offsets[f + 1] - b.offsets[f]), b.stats[f]);
     frames_done_ += (uint64_t)b.n_frames;

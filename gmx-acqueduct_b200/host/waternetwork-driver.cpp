@@ -18,7 +18,7 @@
 //   wn_waternetwork -f traj.gro [-edges edges-frames.xvg] [-nodes nodes-list.xvg]
 //                   [-ohb hydrogen-bonds-num.xvg] [-obw buried-waters-num.xvg]
 //                   [-solvent SOL,WAT,HOH,TIP3] [-buried lists.txt] [-pbc] [-batch 256] [-device 0]
-//                   [-don 5.5] [-doff 6.5] [-aon 0.25] [-aoff 0.0] [-bug-compat 0|1]
+//                   [-don 5.5] [-doff 6.5] [-aon 0.25] [-aoff 0.0] [-bug-compat 0|1] [-gpu-text 1|0]
 // File name options take the reference's base names: ".dat" is appended to -edges/-nodes (:461,:485).
 #include <cmath>
 #include <cstdio>
@@ -108,7 +108,7 @@ struct Options {
     std::string traj, edges = "edges-frames.xvg", nodes = "nodes-list.xvg", ohb = "hydrogen-bonds-num.xvg",
                 obw = "buried-waters-num.xvg", buried;
     std::set<std::string> solvent{"SOL", "WAT", "HOH", "TIP3", "SPC"};
-    bool pbc = false, bugCompat = true;
+    bool pbc = false, bugCompat = true, gpuText = true;
     int batch = 256, device = 0;
     double don = 5.5, doff = 6.5, aon = 0.25, aoff = 0.0;
 };
@@ -136,6 +136,7 @@ Options parse(int argc, char** argv)
         else if (a == "-aon") o.aon = std::atof(val().c_str());
         else if (a == "-aoff") o.aoff = std::atof(val().c_str());
         else if (a == "-bug-compat") o.bugCompat = std::atoi(val().c_str()) != 0;
+        else if (a == "-gpu-text") o.gpuText = std::atoi(val().c_str()) != 0;
         else if (a == "-solvent") {
             o.solvent.clear();
             std::istringstream ss(val());
@@ -247,11 +248,24 @@ int main(int argc, char** argv)
 
         std::vector<double> times;
         std::vector<size_t> filtered;
+        std::vector<std::vector<int32_t> > frameRows;      // -buried: the site list of every pending frame
         char row[256];
         uint64_t total_edges = 0;
+        bool batch_text_done = false;      // the batch's rows were formatted on the GPU and written in one piece
         FrameBatcher batcher(hb, natoms, opt.batch,
             [&](int frnr, const wn_edge* e, size_t n, const wn_frame_stats& st) {
-                if (writer) writer->writeFrame(frnr, e, n);                         // :638-652
+                if (writer && !batch_text_done) {                                   // :638-652 (host formatter)
+                    if (buried.is_open()) {
+                        /* edge indices are positions in this frame's site list: back to table rows for the ids */
+                        const std::vector<int32_t>& rows = frameRows[(size_t)frnr];
+                        std::vector<wn_edge> mapped(e, e + n);
+                        for (wn_edge& m : mapped) { m.i = rows[(size_t)m.i]; m.j = rows[(size_t)m.j]; }
+                        writer->writeFrame(frnr, mapped.data(), n);
+                        std::vector<int32_t>().swap(frameRows[(size_t)frnr]);
+                    } else {
+                        writer->writeFrame(frnr, e, n);
+                    }
+                }
                 total_edges += n;
                 const double t = times[(size_t)frnr];
                 if (obw.is_open()) {                                                 // :654-657
@@ -264,6 +278,19 @@ int main(int argc, char** argv)
                     ohb << row;
                 }
             });
+
+        // edge rows of a whole batch from the GPU formatter (same bytes); a batch with a field wider than its
+        // column (ids over 6 digits, values over 8 characters) goes through the host writer instead
+        batcher.setBatchHook([&](const std::vector<int>& frameNumbers, const HydrogenBondBatch&) {
+            batch_text_done = false;
+            if (!writer || !opt.gpuText || buried.is_open()) return;     // site lists: ids differ per frame, host path
+            const char* text = nullptr; uint64_t bytes = 0;
+            if (hb.formatLastBatch(frameNumbers, ids, &text, &bytes)) {
+                ef.write(text, (std::streamsize)bytes);
+                ef.flush();
+                batch_text_done = true;
+            }
+        });
 
         int frnr = 0;
         do {
@@ -282,6 +309,8 @@ int main(int argc, char** argv)
                     rows.push_back((int32_t)(nP + (size_t)w));
                 }
                 filtered.push_back(cnt);
+                frameRows.resize((size_t)frnr + 1);
+                frameRows[(size_t)frnr] = rows;
                 batcher.push(frnr, fr.xyz.data(), box, rows);
             } else {
                 filtered.push_back(nW);

@@ -116,12 +116,17 @@ public:
     void push(int frnr, const float* xyz, const float (*box)[3], const std::vector<int32_t>& frameSites);
     void finish();
     uint64_t framesDone() const { return frames_done_; }
+    // Optional: called once per processed batch, before the per-frame sink calls, while the batch is
+    // still the engine's "last batch" (so formatLastBatch / componentsOfLastBatch apply to it).
+    typedef std::function<void(const std::vector<int>& frameNumbers, const HydrogenBondBatch& batch)> BatchHook;
+    void setBatchHook(BatchHook hook) { batch_hook_ = hook; }
 
 private:
     void flush();
     HydrogenBondEdges& engine_;
     int natoms_, batch_frames_;
     Sink sink_;
+    BatchHook batch_hook_;
     std::vector<float> buf_;
     std::vector<float> boxes_;
     std::vector<int64_t> sub_off_;

@@ -52,8 +52,8 @@ def _parse_back(frames):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("pbc", [False, True])
-def test_standalone_driver_writes_the_reference_files(tmp_path, pbc):
+@pytest.mark.parametrize("pbc,gpu_text", [(False, 1), (True, 1), (False, 0)])
+def test_standalone_driver_writes_the_reference_files(tmp_path, pbc, gpu_text):
     """wn_waternetwork on a synthetic .gro trajectory: edges file, nodes file and statistics rows equal
     what the oracle (open boundary) / the periodic oracle gives for the same parsed coordinates."""
     import numpy as np
@@ -69,7 +69,7 @@ def test_standalone_driver_writes_the_reference_files(tmp_path, pbc):
     exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
     assert os.path.exists(exe), "build first: __graft_entry__.build()"
     args = [exe, "-f", gro, "-edges", str(tmp_path / "edges"), "-nodes", str(tmp_path / "nodes"),
-            "-ohb", str(tmp_path / "ohb.xvg"), "-obw", str(tmp_path / "obw.xvg"), "-batch", "2"]
+            "-ohb", str(tmp_path / "ohb.xvg"), "-obw", str(tmp_path / "obw.xvg"), "-batch", "2", "-gpu-text", str(gpu_text)]
     if pbc:
         args.append("-pbc")
     r = subprocess.run(args, capture_output=True, text=True, timeout=300)
@@ -121,3 +121,41 @@ def test_standalone_driver_fails_loudly_without_gpu(tmp_path):
     # the topology part runs before the device is touched: nodes file of the one water
     rows = (tmp_path / "n.dat").read_text().splitlines()
     assert rows[1].split() == ["2", "0", "OW", "0", "SOL", "2", "2"]
+
+
+@pytest.mark.gpu
+def test_standalone_driver_buried_lists(tmp_path):
+    """-buried: a different water list per frame; ids in the edge file are those of the listed waters."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import wn_oracle_py as o
+    n, nf = 216, 3
+    sb = o.synth_box(n, model=o.MODEL_SPC)
+    frames = o.synth_frames(sb, 0, nf)
+    gro = str(tmp_path / "traj.gro")
+    _write_gro(gro, frames, float(sb.box), with_time=False)
+    rng = np.random.default_rng(2)
+    lists = [np.sort(rng.choice(n, size=k, replace=False)) for k in (150, 0, 216)]
+    (tmp_path / "buried.txt").write_text("".join(" ".join(str(int(w)) for w in l) + "\n" for l in lists))
+    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
+    r = subprocess.run([exe, "-f", gro, "-edges", str(tmp_path / "edges"), "-nodes", "", "-ohb", str(tmp_path / "ohb.xvg"),
+                        "-obw", str(tmp_path / "obw.xvg"), "-buried", str(tmp_path / "buried.txt"), "-batch", "4"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    parsed = _parse_back(frames)
+    want = "%6s%8s%6s%6s%8s%6s%8s%8s%8s" % ("#Id", "AtmId", "ResId", "Id", "AtmId", "ResId", "Energy", "Length", "Cos\n")
+    obw = ""
+    for f in range(nf):
+        l = lists[f]
+        sa = (3 * l).astype(np.int32)
+        ha = np.stack([3 * l, 3 * l + 1], axis=1).astype(np.int32)
+        ty = np.full(len(l), o.WATER, np.uint8)
+        e, st, _, _ = o.frame_hbonds(parsed[f], sa, ha, ty)
+        want += "#--- frame %d ---\n" % f
+        want += "".join("%6d%6d%8.4f%8.4f%8.4f\n" % (l[a] + 2, l[b] + 2, en, ln, cs)
+                        for a, b, en, ln, cs in zip(e["i"], e["j"], e["energy"].astype(np.float64),
+                                                    e["length"].astype(np.float64), e["cosine"].astype(np.float64)))
+        obw += " %11.3f %8.3f %8.3f\n" % (f, len(l), 0)
+    assert open(str(tmp_path / "edges.dat")).read() == want
+    assert open(str(tmp_path / "obw.xvg")).read() == obw
