@@ -259,18 +259,17 @@ int ensure_out_frames(wn_ctx* ctx, size_t n_frames, bool host)
         if ((rc = dev_realloc_plain(ctx, &ctx->d_counters_all, cap))) return rc;
         ctx->out_frames_cap = cap;
     }
-    if (host || true) {
-        if (n_frames + 1 > ctx->h_frames_cap || !ctx->h_frame_off) {
-            const size_t cap = n_frames + 1;
-            if (ctx->h_frame_off) WN_CK(cudaFreeHost(ctx->h_frame_off));
-            if (ctx->h_stats) WN_CK(cudaFreeHost(ctx->h_stats));
-            if (ctx->h_counters) WN_CK(cudaFreeHost(ctx->h_counters));
-            ctx->h_frame_off = nullptr; ctx->h_stats = nullptr; ctx->h_counters = nullptr;
-            WN_CK(cudaMallocHost((void**)&ctx->h_frame_off, cap * sizeof(uint64_t)));
-            WN_CK(cudaMallocHost((void**)&ctx->h_stats, cap * sizeof(wn_frame_stats)));
-            WN_CK(cudaMallocHost((void**)&ctx->h_counters, cap * sizeof(WnFrameCounters)));
-            ctx->h_frames_cap = cap;
-        }
+    /* the small per-frame tables (offsets, statistics, counters) come back to the host for every batch */
+    if (n_frames + 1 > ctx->h_frames_cap || !ctx->h_frame_off) {
+        const size_t cap = n_frames + 1;
+        if (ctx->h_frame_off) WN_CK(cudaFreeHost(ctx->h_frame_off));
+        if (ctx->h_stats) WN_CK(cudaFreeHost(ctx->h_stats));
+        if (ctx->h_counters) WN_CK(cudaFreeHost(ctx->h_counters));
+        ctx->h_frame_off = nullptr; ctx->h_stats = nullptr; ctx->h_counters = nullptr;
+        WN_CK(cudaMallocHost((void**)&ctx->h_frame_off, cap * sizeof(uint64_t)));
+        WN_CK(cudaMallocHost((void**)&ctx->h_stats, cap * sizeof(wn_frame_stats)));
+        WN_CK(cudaMallocHost((void**)&ctx->h_counters, cap * sizeof(WnFrameCounters)));
+        ctx->h_frames_cap = cap;
     }
     return WN_OK;
 }

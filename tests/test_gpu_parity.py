@@ -855,3 +855,24 @@ def test_connected_components_small_and_degenerate(ctx, oracle):
             assert np.array_equal(labels[f], lab)
             assert [stats[f][k] for k in ("n_components", "largest", "n_nodes", "n_edges")] == list(st)
     assert stats["n_edges"][1] == 0 and np.all(labels[1] == -1)
+
+
+def test_results_are_reproducible_run_to_run(ctx, oracle, capi):
+    """Row slots are claimed with atomics and home blocks by a work counter, so arrival order differs from
+    run to run; the ordered copy and the fixed-order sums must hide that: edges, offsets, statistics
+    (including the fp64 energy sum) and component labels are byte-identical across runs, pass sizes and layouts."""
+    n, nf = 4000, 6
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 100, nf)
+    ctx.set_water_sites(n)
+    ref = None
+    for rep, pass_frames in enumerate((0, 0, 1, 4, 6)):
+        ctx.set_batch_frames(pass_frames)
+        res = ctx.hbond_batch(frames)
+        labels, cst = ctx.components(0.5)
+        cur = (res["edges"].tobytes(), res["frame_offsets"].tobytes(), res["stats"].tobytes(),
+               res["row_offsets"].tobytes(), labels.tobytes(), cst.tobytes())
+        if ref is None:
+            ref = cur
+        assert cur == ref, (rep, pass_frames)
+    ctx.set_batch_frames(0)
