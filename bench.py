@@ -460,6 +460,37 @@ def run_own(args):
     e2e_ms_max = allmax(max(e2e_ms, e2e_wall * 1e3))
     e2e_fps = frames_all / (e2e_ms_max * 1e-3)
 
+    # ---- host frames in -> component labels out: the edge list never crosses PCIe (results_on_device),
+    # only 4 bytes per site and 16 per frame come back.  A different result than the headline e2e (labels and
+    # component statistics instead of the edge list), reported beside it.
+    e2e_cc = None
+    if rank == 0 and not args.no_find:
+        import ctypes
+        lab_h, lab_hp = ctx.pinned_array((F, n_waters), np.int32)
+        st_h, st_hp = ctx.pinned_array((F,), capi.COMPONENT_DTYPE)
+        lab, stc = ctypes.c_void_p(), ctypes.c_void_p()
+
+        def one(s):
+            ctx.hbond_batch_ex(None, F, natoms, host_ptr=host_ptr + (s % ring) * F * frame_bytes, results_on_device=True, copy=False)
+            ctx._ck(ctx.L.wn_components(ctx.h, 0.0, ctypes.byref(lab), ctypes.byref(stc)))
+            ctx._ck(ctx.L.wn_memcpy_d2h(ctx.h, lab_hp, lab, F * n_waters * 4))
+            ctx._ck(ctx.L.wn_memcpy_d2h(ctx.h, st_hp, stc, F * 16))
+            return int(st_h["n_components"][-1])
+
+        one(0)
+        kc = max(1, min(K, 5))
+        ctx.timer_start()
+        t_0 = time.perf_counter()
+        for s in range(kc):
+            one(s + 1)
+        cc_ms = max(ctx.timer_stop(), (time.perf_counter() - t_0) * 1e3)
+        e2e_cc = {"value": kc * F / (cc_ms * 1e-3), "unit": "frames/s", "steps": kc,
+                  "h2d_bytes_per_step": F * frame_bytes, "d2h_bytes_per_step": F * n_waters * 4 + F * 16 + (F + 1) * 8 + F * 40,
+                  "note": "pinned host frames -> wn_hbond_batch_ex(results_on_device) -> wn_components(0.0) -> labels + "
+                          "component statistics in pinned host memory; the edge list stays in HBM"}
+        ctx.pinned_free(lab_hp); ctx.pinned_free(st_hp)
+
+
     # ---- roofline of the dominant kernel (wn_k_edges), this rank
     peaks = {}
     try:
@@ -541,6 +572,7 @@ def run_own(args):
             "find_pairs": find,
             "edge_file_text": text,
             "components": comps,
+            "e2e_components": e2e_cc,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -57,7 +57,7 @@ class BatchArgs(C.Structure):
     _fields_ = [("frames", C.c_void_p), ("frames_on_device", C.c_int32), ("n_frames", C.c_int32),
                 ("natoms", C.c_int32), ("box_stride", C.c_int32), ("boxes", C.c_void_p),
                 ("subset_offsets", C.c_void_p), ("subset_sites", C.c_void_p),
-                ("result_layout", C.c_int32), ("reserved", C.c_int32)]
+                ("result_layout", C.c_int32), ("results_on_device", C.c_int32)]
 
 
 class Timings(C.Structure):
@@ -273,12 +273,14 @@ class Context:
         return self._wrap(res, True)
 
     def hbond_batch_ex(self, frames, n_frames=None, natoms=None, on_device=False, boxes=None,
-                       subset_offsets=None, subset_sites=None, layout=LAYOUT_EDGES, copy=True, host_ptr=None):
+                       subset_offsets=None, subset_sites=None, layout=LAYOUT_EDGES, copy=True, host_ptr=None,
+                       results_on_device=False):
         """General form (wn_hbond_batch_ex): host array or device pointer, open / (L) / matrix boxes,
         optional per-frame site lists."""
         a = BatchArgs()
         keep = []
         a.result_layout = layout
+        a.results_on_device = 1 if results_on_device else 0
         if on_device:
             a.frames, a.n_frames, a.natoms, a.frames_on_device = frames, n_frames, natoms, 1
         elif host_ptr is not None:

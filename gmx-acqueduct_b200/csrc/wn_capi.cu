@@ -114,6 +114,7 @@ struct wn_ctx {
 
     std::vector<WnGrid> h_grid;     /* periodic grids of the current pass (host-built) */
     int layout = 0;                          /* result layout of the current / last call */
+    bool keep_dev = false;                   /* current call: host frames in, results stay on the device */
     int box_stride = 3;                      /* 3: (Lx,Ly,Lz) per frame; 9: triclinic matrices */
     const int64_t* sub_off_host = nullptr;   /* per-frame site subsets of the current call (host) */
     const int32_t* sub_sites_host = nullptr;
@@ -433,7 +434,9 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     ctx->tm = wn_timings{};
     memset(out, 0, sizeof *out);
     int rc;
-    if ((rc = ensure_out_frames(ctx, (size_t)n_frames, host_in))) return rc;
+    /* results go where the frames came from, unless the caller keeps them on the device (results_on_device) */
+    const bool host_out = host_in && !ctx->keep_dev;
+    if ((rc = ensure_out_frames(ctx, (size_t)n_frames, host_out))) return rc;
 
     const int N = ctx->n_sites;
     unsigned long long edge_base = 0;
@@ -441,17 +444,17 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
         /* nothing to search: empty edge lists, zero rows */
         for (int f = 0; f <= n_frames; ++f) ctx->h_frame_off[f] = 0;
         for (int f = 0; f < n_frames; ++f) ctx->h_stats[f] = wn_frame_stats{0, 0, 0, 0, 0};
-        if (!host_in && n_frames > 0) {
+        if (!host_out && n_frames > 0) {
             WN_CK(cudaMemsetAsync(ctx->d_frame_off, 0, (size_t)(n_frames + 1) * sizeof(unsigned long long), ctx->st));
             WN_CK(cudaMemsetAsync(ctx->d_stats, 0, (size_t)n_frames * sizeof(wn_frame_stats), ctx->st));
             WN_CK(cudaStreamSynchronize(ctx->st));
         }
-        out->edges = host_in ? ctx->h_edges : ctx->d_edges;
-        out->frame_offsets = host_in ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
-        out->stats = host_in ? ctx->h_stats : ctx->d_stats;
+        out->edges = host_out ? ctx->h_edges : ctx->d_edges;
+        out->frame_offsets = host_out ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
+        out->stats = host_out ? ctx->h_stats : ctx->d_stats;
         out->n_frames = n_frames;
-        out->on_device = host_in ? 0 : 1;
-        out->row_offsets = host_in ? ctx->h_row_off : ctx->d_row_off;
+        out->on_device = host_out ? 0 : 1;
+        out->row_offsets = host_out ? ctx->h_row_off : ctx->d_row_off;
         out->n_sites = N;
         out->layout = ctx->layout;
         return WN_OK;
@@ -497,7 +500,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
             const unsigned long long before = edge_base;
             if ((rc = run_pass(ctx, ctx->d_stage[k & 1], boxes ? boxes + ctx->box_stride * (size_t)f0 : nullptr, nf, natoms,
                                (size_t)f0, &edge_base))) return rc;
-            if ((size_t)edge_base > ctx->h_edges_cap) {
+            if (host_out && (size_t)edge_base > ctx->h_edges_cap) {
                 /* project the whole call from the density seen so far */
                 const double per_frame = (double)edge_base / (double)(f0 + nf);
                 const size_t want = (size_t)(per_frame * n_frames * 1.05) + 1024;
@@ -505,7 +508,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
                                       (size_t)before))) return rc;
             }
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 2], ctx->st_d2h));
-            if (edge_base > before)
+            if (host_out && edge_base > before)
             {
                 /* 20-byte wn_edge records, or 16-byte wn_edge16 records in the same buffers */
                 const size_t esz = ctx->layout == WN_LAYOUT_CSR16 ? sizeof(wn_edge16) : sizeof(wn_edge);
@@ -514,7 +517,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
                                       (size_t)(edge_base - before) * esz, cudaMemcpyDeviceToHost, ctx->st_d2h));
             }
             /* the row offsets of the pass travel with its edges */
-            if (N > 0)
+            if (host_out && N > 0)
                 WN_CK(cudaMemcpyAsync(ctx->h_row_off + (size_t)f0 * N, ctx->d_row_off + (size_t)f0 * N,
                                       (size_t)nf * N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 3], ctx->st_d2h));
@@ -550,20 +553,20 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
         ties.cosine_argmax_equal += ctx->h_counters[f].tie_cos;
         ties.pos_zero += ctx->h_counters[f].tie_pos0;
     }
-    out->edges = host_in ? ctx->h_edges : ctx->d_edges;
-    out->frame_offsets = host_in ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
-    out->stats = host_in ? ctx->h_stats : ctx->d_stats;
+    out->edges = host_out ? ctx->h_edges : ctx->d_edges;
+    out->frame_offsets = host_out ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
+    out->stats = host_out ? ctx->h_stats : ctx->d_stats;
     ctx->last_frames = n_frames;
     ctx->last_edges = edge_base;
-    ctx->last_on_device = host_in ? 0 : 1;
-    out->row_offsets = host_in ? ctx->h_row_off : ctx->d_row_off;
+    ctx->last_on_device = host_out ? 0 : 1;
+    out->row_offsets = host_out ? ctx->h_row_off : ctx->d_row_off;
     out->n_sites = N;
     out->layout = ctx->layout;
     out->n_edges = edge_base;
     out->n_pair_evals = evals;
     out->ties = ties;
     out->n_frames = n_frames;
-    out->on_device = host_in ? 0 : 1;
+    out->on_device = host_out ? 0 : 1;
     return WN_OK;
 }
 
@@ -783,11 +786,13 @@ int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* a, wn_batch_result* out)
     if (a->result_layout != WN_LAYOUT_EDGES && a->result_layout != WN_LAYOUT_CSR16)
         return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: unknown result_layout");
     ctx->layout = a->result_layout;
+    ctx->keep_dev = a->results_on_device != 0;
     ctx->box_stride = stride;
     ctx->sub_off_host = a->subset_offsets;
     ctx->sub_sites_host = a->subset_offsets ? a->subset_sites : nullptr;
     const int rc = batch_common(ctx, a->frames, boxes, a->frames_on_device == 0, nf, a->natoms, out);
     ctx->box_stride = 3;
+    ctx->keep_dev = false;
     ctx->sub_off_host = nullptr;
     ctx->sub_sites_host = nullptr;
     return rc;
@@ -799,7 +804,7 @@ static wn_batch_args make_args(const float* frames, int on_device, int32_t n_fra
     wn_batch_args a;
     a.frames = frames; a.frames_on_device = on_device; a.n_frames = n_frames; a.natoms = natoms;
     a.box_stride = stride; a.boxes = boxes; a.subset_offsets = so; a.subset_sites = ss;
-    a.result_layout = WN_LAYOUT_EDGES; a.reserved = 0;
+    a.result_layout = WN_LAYOUT_EDGES; a.results_on_device = 0;
     return a;
 }
 

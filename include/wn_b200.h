@@ -218,7 +218,9 @@ typedef struct wn_batch_args {
     const int64_t* subset_offsets;  /* host, [n_frames+1], or NULL: every frame uses the whole table */
     const int32_t* subset_sites;    /* host, rows of the site table                                  */
     int32_t        result_layout;   /* WN_LAYOUT_EDGES (default) or WN_LAYOUT_CSR16                  */
-    int32_t        reserved;
+    int32_t        results_on_device; /* 1: host frames in, but edges and row offsets stay in device memory (as for a
+                                     * *_dev batch) for consumers that continue on the GPU: wn_components,
+                                     * wn_format_edges; only the small per-frame tables come back.  0: default */
 } wn_batch_args;
 int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* args, wn_batch_result* out);
 

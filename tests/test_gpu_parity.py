@@ -876,3 +876,26 @@ def test_results_are_reproducible_run_to_run(ctx, oracle, capi):
             ref = cur
         assert cur == ref, (rep, pass_frames)
     ctx.set_batch_frames(0)
+
+
+def test_host_frames_results_kept_on_device(ctx, oracle, capi):
+    """results_on_device: host frames in, edge list left in HBM (for wn_components / wn_format_edges);
+    fetched explicitly it equals the host result, and the components computed from it are the same."""
+    n, nf = 1000, 5
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 7, nf)
+    ctx.set_water_sites(n)
+    ctx.set_batch_frames(2)
+    host = ctx.hbond_batch_ex(frames)
+    lab_h, st_h = ctx.components(0.5)
+    dev = ctx.hbond_batch_ex(frames, results_on_device=True)
+    assert "edges_dev" in dev and dev["n_edges"] == host["n_edges"]
+    e, fo, st = ctx.fetch_dev_result(dev)
+    assert e.tobytes() == host["edges"].tobytes() and np.array_equal(fo, host["frame_offsets"])
+    assert st.tobytes() == host["stats"].tobytes()
+    lab_d, st_d = ctx.components(0.5)
+    assert np.array_equal(lab_d, lab_h) and st_d.tobytes() == st_h.tobytes()
+    text_d = ctx.format_edges(np.arange(nf))
+    ctx.hbond_batch_ex(frames)
+    assert ctx.format_edges(np.arange(nf)) == text_d
+    ctx.set_batch_frames(0)
