@@ -422,7 +422,7 @@ def run_own(args):
                  "algorithmic_bytes": cc_bytes, "GBps": cc_bytes / (cms * 1e-3) / 1e9,
                  "frac_of_hbm_peak": cc_bytes / (cms * 1e-3) / 1e9 / peak_gbs,
                  "components_frame0": int(st_c["n_components"][0]), "largest_frame0": int(st_c["largest"][0]),
-                 "note": "wn_components at threshold 0.0 on the HBM-resident edge list (iota + hook + flatten + stats kernels)"}
+                 "note": "wn_components at threshold 0.0 on the HBM-resident edge list (one CTA per frame, union-find in shared memory)"}
 
     if periodic is not None:
         pmax = allmax(periodic["ms"])

@@ -8,7 +8,9 @@
  * component of chosen nodes (nx.node_connected_component, :155).  Here the components of ALL frames
  * of a batch are labelled on the device, straight from the edge list the pipeline left in HBM
  * (lock-free union-find; an edge is kept unless |energy| <= threshold, so a NaN energy is kept, as
- * the Python comparison keeps it):
+ * the Python comparison keeps it).  Frames whose parent array fits one SM's shared memory (up to ~56 k
+ * sites) run in ONE CTA each, entirely on chip (wn_k_cc_smem, below); larger frames take the
+ * multi-kernel global-memory path:
  *   wn_k_cc_iota      parent[v] = v
  *   wn_k_cc_sample    round k = 0, 1: every site joins the k-th kept edge of its own row, then
  *   wn_k_cc_compress  parent[v] = root(v)                      (neighbour sampling, as in Afforest)
@@ -241,6 +243,211 @@ wn_k_cc_stats(const int* __restrict__ labels_all, const int* __restrict__ count_
     }
 }
 
+/* ---- one CTA per frame, union-find in shared memory ----
+ * The parent array of a frame (4 bytes per site: 133 KB for the 100k-atom box) fits the 227 KB of one SM,
+ * so the whole labelling of a frame runs in ONE CTA on shared memory: a hop of a find costs ~30 cycles
+ * instead of an L2 round trip (the global version spends 98 % of its cycles waiting on those: issue
+ * utilisation 2.4 %).  Same algorithm (hashed root priority, path halving, CAS hooking), then the smallest
+ * member of every component is collected IN PLACE: roots switch their own slot to (member | FLAG) and the
+ * members atomicMin into it, so no second array is needed.  Sizes go through the global count array. */
+constexpr int CCS_THREADS = 1024;
+constexpr int CC_FLAG = 1 << 30;
+#ifndef WN_CCS_PHASES
+#define WN_CCS_PHASES 8
+#endif
+constexpr int CCS_PHASES = WN_CCS_PHASES;
+
+__device__ __forceinline__ int wn_ccs_find(volatile int* parent, int v)
+{
+    int p = parent[v];
+    while (p != v) {
+        const int gp = parent[p];
+        if (gp != p) parent[v] = gp;
+        v = p;
+        p = gp;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void wn_ccs_union(int* parent, int a, int b)
+{
+    int ra = wn_ccs_find(parent, a), rb = wn_ccs_find(parent, b);
+    while (ra != rb) {
+        const bool a_low = wn_cc_prio(ra) < wn_cc_prio(rb);
+        const int child = a_low ? rb : ra, top = a_low ? ra : rb;
+        const int old = atomicCAS(parent + child, child, top);
+        if (old == child) break;
+        ra = wn_ccs_find(parent, child);
+        rb = wn_ccs_find(parent, top);
+    }
+}
+
+template <bool CSR16>
+__global__ void __launch_bounds__(CCS_THREADS, 1)
+wn_k_cc_smem(const void* __restrict__ edges, const unsigned long long* __restrict__ frame_off,
+             const uint32_t* __restrict__ row_off, int n_sites, float threshold,
+             int* __restrict__ labels_all, int* __restrict__ count_all, wn_component_stats* __restrict__ stats)
+{
+    extern __shared__ int s_cc[];
+    int* parent = s_cc;                                      /* [n_sites] */
+    unsigned int* has = reinterpret_cast<unsigned int*>(s_cc + n_sites);   /* bit per site: has a kept edge */
+    __shared__ int s_red[3][CCS_THREADS / 32];
+    __shared__ unsigned int s_kept;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long b = frame_off[f], n = frame_off[f + 1] - b;
+    const int n_words = (n_sites + 31) >> 5;
+    for (int v = tid; v < n_sites; v += CCS_THREADS) parent[v] = v;
+    for (int w = tid; w < n_words; w += CCS_THREADS) has[w] = 0u;
+    if (tid == 0) s_kept = 0u;
+    __syncthreads();
+
+    unsigned int mine = 0;
+    /* The edge list streams from HBM in CCS_PHASES slices; after every slice all sites are re-pointed at their
+     * roots, so the finds of the next slice take one or two hops (random shared-memory reads with bank
+     * conflicts are what this kernel is bound by: ~10 hops per find, 3.4 ms per 250 frames, without the
+     * intermediate flattening; 1.5 ms with it). */
+    auto flatten_all = [&]() {
+        __syncthreads();
+        for (int v = tid; v < n_sites; v += CCS_THREADS) {
+            volatile int* vp = parent;
+            int r = v, p = vp[r];
+            while (p != r) { r = p; p = vp[r]; }
+            vp[v] = r;
+        }
+        __syncthreads();
+    };
+    if (CSR16) {
+        /* a warp takes 32 consecutive rows = one contiguous span of 16-byte records: lane per edge (coalesced),
+         * the row index comes from a shuffle binary search over the 32 row offsets held by the lanes */
+        const uint32_t* ro = row_off + (size_t)f * n_sites;
+        const int lane = tid & 31, warp = tid >> 5, n_warps = CCS_THREADS / 32;
+        const int n_blocks = (n_sites + 31) >> 5;
+        const int slice = (n_blocks + CCS_PHASES - 1) / CCS_PHASES;
+        for (int ph = 0; ph < CCS_PHASES; ++ph) {
+            const int b1 = min(n_blocks, (ph + 1) * slice);
+            for (int blk = ph * slice + warp; blk < b1; blk += n_warps) {
+                const int v0 = blk << 5;
+                const unsigned long long my = (v0 + lane < n_sites) ? (unsigned long long)ro[v0 + lane] : n;
+                const unsigned long long first = __shfl_sync(FULL, my, 0);
+                const unsigned long long last = (v0 + 32 < n_sites) ? (unsigned long long)ro[v0 + 32] : n;
+                for (unsigned long long e0 = first; e0 < last; e0 += 64) {
+                    uint4 rec[2];
+                    unsigned long long ee[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        ee[u] = e0 + 32 * u + lane;
+                        rec[u] = make_uint4(0u, 0u, 0u, 0u);
+                        if (ee[u] < last) rec[u] = reinterpret_cast<const uint4*>(edges)[b + ee[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        /* largest r with ro[v0 + r] <= e (offsets are non-decreasing over the lanes) */
+                        int r = 0;
+#pragma unroll
+                        for (int s = 16; s > 0; s >>= 1) {
+                            const unsigned long long t = __shfl_sync(FULL, my, r + s);
+                            if (t <= ee[u]) r += s;
+                        }
+                        if (ee[u] >= last || fabsf(__uint_as_float(rec[u].y)) <= threshold) continue;
+                        const int i = v0 + r, j = (int)rec[u].x;
+                        ++mine;
+                        atomicOr(has + (i >> 5), 1u << (i & 31));
+                        atomicOr(has + (j >> 5), 1u << (j & 31));
+                        wn_ccs_union(parent, i, j);
+                    }
+                }
+            }
+            if (ph + 1 < CCS_PHASES) flatten_all();
+        }
+    } else {
+        /* four edges per thread in flight hide the HBM latency with one CTA per SM */
+        const wn_edge* ed = reinterpret_cast<const wn_edge*>(edges) + b;
+        const unsigned long long slice = (n + CCS_PHASES - 1) / CCS_PHASES;
+        for (int ph = 0; ph < CCS_PHASES; ++ph) {
+            const unsigned long long s0 = (unsigned long long)ph * slice, s1 = min(n, s0 + slice);
+            for (unsigned long long e0 = s0 + (unsigned long long)tid; e0 < s1; e0 += 4ull * CCS_THREADS) {
+                int ei[4], ej[4];
+                float en[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long e = e0 + (unsigned long long)u * CCS_THREADS;
+                    ei[u] = -1; ej[u] = 0; en[u] = 0.f;
+                    if (e < s1) { ei[u] = ed[e].i; ej[u] = ed[e].j; en[u] = ed[e].energy; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ei[u] < 0 || fabsf(en[u]) <= threshold) continue;    /* filter_edge_by_weight: removed iff weight <= threshold */
+                    ++mine;
+                    atomicOr(has + (ei[u] >> 5), 1u << (ei[u] & 31));
+                    atomicOr(has + (ej[u] >> 5), 1u << (ej[u] & 31));
+                    wn_ccs_union(parent, ei[u], ej[u]);
+                }
+            }
+            if (ph + 1 < CCS_PHASES) flatten_all();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(FULL, mine, o);
+    if ((tid & 31) == 0 && mine) atomicAdd(&s_kept, mine);
+    /* every member points at its root (in-place argument as in wn_k_cc_compress) */
+    flatten_all();
+    /* roots: own slot becomes (smallest member so far | FLAG); sites without an edge: -1 */
+    for (int v = tid; v < n_sites; v += CCS_THREADS) {
+        const bool member = (has[v >> 5] >> (v & 31)) & 1u;
+        if (!member) parent[v] = -1;
+        else if (parent[v] == v) parent[v] = v | CC_FLAG;
+    }
+    __syncthreads();
+    for (int v = tid; v < n_sites; v += CCS_THREADS) {
+        const int p = parent[v];
+        if (p >= 0 && !(p & CC_FLAG)) atomicMin(parent + p, v | CC_FLAG);     /* p is a root slot: flagged values only */
+    }
+    __syncthreads();
+    /* labels out, component sizes at the label's slot of the global count array (zeroed by the launcher) */
+    int* labels = labels_all + (size_t)f * n_sites;
+    int* count = count_all + (size_t)f * n_sites;
+    int nodes = 0;
+    for (int v0 = 0; v0 < n_sites; v0 += CCS_THREADS) {
+        const int v = v0 + tid;
+        int l = -1;
+        if (v < n_sites) {
+            const int p = parent[v];
+            if (p >= 0) l = ((p & CC_FLAG) ? p : parent[p]) & ~CC_FLAG;
+            labels[v] = l;
+        }
+        const unsigned grp = __match_any_sync(FULL, l);
+        if (l >= 0) {
+            ++nodes;
+            if ((tid & 31) == __ffs(grp) - 1) atomicAdd(count + l, __popc(grp));
+        }
+    }
+    __syncthreads();
+    int comps = 0, largest = 0;
+    for (int v = tid; v < n_sites; v += CCS_THREADS) {
+        const int p = parent[v];
+        /* the smallest member of a component is the site whose label is itself */
+        if (p >= 0) {
+            const int l = ((p & CC_FLAG) ? p : parent[p]) & ~CC_FLAG;
+            if (l == v) { ++comps; largest = max(largest, (int)*reinterpret_cast<volatile int*>(count + v)); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        comps += __shfl_down_sync(FULL, comps, o);
+        nodes += __shfl_down_sync(FULL, nodes, o);
+        largest = max(largest, __shfl_down_sync(FULL, largest, o));
+    }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = comps; s_red[1][tid >> 5] = largest; s_red[2][tid >> 5] = nodes; }
+    __syncthreads();
+    if (tid == 0) {
+        int c = 0, l = 0, nn = 0;
+        for (int w = 0; w < CCS_THREADS / 32; ++w) { c += s_red[0][w]; l = max(l, s_red[1][w]); nn += s_red[2][w]; }
+        wn_component_stats r;
+        r.n_components = c; r.largest = l; r.n_nodes = nn; r.n_edges = (int32_t)s_kept;
+        stats[f] = r;
+    }
+}
+
 }  // namespace
 
 /* labels: [F][N] (the union-find parent array while the kernels run); work, count, minidx: [F][N] ints; kept: [F] */
@@ -251,8 +458,20 @@ void wn_launch_components(const void* edges, int csr16, const unsigned long long
 {
     if (n_frames <= 0) return;
     const size_t n = (size_t)n_frames * (size_t)n_sites;
-    cudaMemsetAsync(work, 0, n * sizeof(int), st);
     cudaMemsetAsync(count, 0, n * sizeof(int), st);
+    /* frames whose parent array fits one SM's shared memory: one CTA per frame, everything on chip */
+    const size_t smem = (size_t)n_sites * sizeof(int) + (size_t)((n_sites + 31) / 32) * sizeof(unsigned int);
+    if (n_sites > 0 && smem <= 220u * 1024u) {
+        if (csr16) {
+            cudaFuncSetAttribute(wn_k_cc_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            wn_k_cc_smem<true><<<n_frames, CCS_THREADS, smem, st>>>(edges, frame_off, row_off, n_sites, threshold, labels, count, stats);
+        } else {
+            cudaFuncSetAttribute(wn_k_cc_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            wn_k_cc_smem<false><<<n_frames, CCS_THREADS, smem, st>>>(edges, frame_off, row_off, n_sites, threshold, labels, count, stats);
+        }
+        return;
+    }
+    cudaMemsetAsync(work, 0, n * sizeof(int), st);
     cudaMemsetAsync(kept, 0, (size_t)n_frames * sizeof(unsigned int), st);
     if (n_sites > 0) {
         dim3 gv((n_sites + CC_THREADS - 1) / CC_THREADS, n_frames);

@@ -899,3 +899,17 @@ def test_host_frames_results_kept_on_device(ctx, oracle, capi):
     ctx.hbond_batch_ex(frames)
     assert ctx.format_edges(np.arange(nf)) == text_d
     ctx.set_batch_frames(0)
+
+
+def test_connected_components_large_frame_global_path(ctx, oracle):
+    """More sites than one SM's shared memory holds (> ~56 k): the multi-kernel global-memory union-find."""
+    n = 60000
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 0, 1)
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames)
+    for thr in (0.0, 1.5):
+        labels, stats = ctx.components(thr)
+        lab, st = oracle.components(res["edges"], n, thr)
+        assert np.array_equal(labels[0], lab)
+        assert [stats[0][k] for k in ("n_components", "largest", "n_nodes", "n_edges")] == list(st)
