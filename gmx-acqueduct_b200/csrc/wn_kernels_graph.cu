@@ -32,6 +32,10 @@
 namespace {
 
 constexpr int CC_THREADS = 256;
+#ifndef WN_CC_HOOK_SLICES
+#define WN_CC_HOOK_SLICES 4
+#endif
+constexpr int CC_HOOK_SLICES = WN_CC_HOOK_SLICES;
 constexpr int CC_SAMPLE_ROUNDS = 2;       /* measured at 250 x 33,333 sites, all edges kept: 0 -> 21.3 ms, 1 -> 7.8, 2 -> 4.1, 3 -> 4.5, 4 -> 4.7 */
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -127,15 +131,18 @@ wn_k_cc_compress(int* __restrict__ parent_all, int n_sites)
 template <bool CSR16>
 __global__ void __launch_bounds__(CC_THREADS)
 wn_k_cc_hook(const void* __restrict__ edges, const unsigned long long* __restrict__ frame_off,
-             const uint32_t* __restrict__ row_off, int n_sites, float threshold,
+             const uint32_t* __restrict__ row_off, int n_sites, float threshold, int slice, int n_slices,
              int* __restrict__ parent_all, int* __restrict__ has_all, unsigned int* __restrict__ kept)
 {
     const int f = blockIdx.y;
-    const unsigned long long b = frame_off[f], n = frame_off[f + 1] - b;
+    const unsigned long long b = frame_off[f], n_all = frame_off[f + 1] - b;
+    /* this launch handles the slice-th part of the frame's edges (the trees are flattened between slices) */
+    const unsigned long long per = (n_all + n_slices - 1) / n_slices;
+    const unsigned long long e_lo = (unsigned long long)slice * per, n = min(n_all, e_lo + per);
     volatile int* parent = parent_all + (size_t)f * n_sites;
     int* has = has_all + (size_t)f * n_sites;             /* site has a kept edge (remove_node_degree keeps it) */
     unsigned int mine = 0;
-    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+    for (unsigned long long e = e_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
          e += (unsigned long long)gridDim.x * blockDim.x) {
         int i, j;
         float en;
@@ -482,13 +489,18 @@ void wn_launch_components(const void* edges, int csr16, const unsigned long long
                 else wn_k_cc_sample<false><<<gv, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, k, labels);
                 wn_k_cc_compress<<<gv, CC_THREADS, 0, st>>>(labels, n_sites);
             }
-            /* a few edges per thread: enough CTAs to fill the device, bounded grid for huge frames */
-            const unsigned long long want = (max_edges + CC_THREADS * 4 - 1) / (CC_THREADS * 4);
+            /* all edges in CC_HOOK_SLICES launches with a compression in between (shorter finds); a few edges per
+             * thread: enough CTAs to fill the device, bounded grid for huge frames */
+            const unsigned long long per = (max_edges + CC_HOOK_SLICES - 1) / CC_HOOK_SLICES;
+            const unsigned long long want = (per + CC_THREADS * 4 - 1) / (CC_THREADS * 4);
             dim3 ge((unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(want, 1), 65535), n_frames);
-            if (csr16)
-                wn_k_cc_hook<true><<<ge, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, labels, work, kept);
-            else
-                wn_k_cc_hook<false><<<ge, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, labels, work, kept);
+            for (int s = 0; s < CC_HOOK_SLICES; ++s) {
+                if (csr16)
+                    wn_k_cc_hook<true><<<ge, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, s, CC_HOOK_SLICES, labels, work, kept);
+                else
+                    wn_k_cc_hook<false><<<ge, CC_THREADS, 0, st>>>(edges, frame_off, row_off, n_sites, threshold, s, CC_HOOK_SLICES, labels, work, kept);
+                if (s + 1 < CC_HOOK_SLICES) wn_k_cc_compress<<<gv, CC_THREADS, 0, st>>>(labels, n_sites);
+            }
         }
         wn_k_cc_flatten<<<gv, CC_THREADS, 0, st>>>(labels, work, n_sites);
         wn_k_cc_collect<<<gv, CC_THREADS, 0, st>>>(labels, minidx, n_sites);
