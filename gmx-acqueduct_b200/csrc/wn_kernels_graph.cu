@@ -28,6 +28,8 @@
  */
 #include "wn_internal.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -466,9 +468,12 @@ void wn_launch_components(const void* edges, int csr16, const unsigned long long
     if (n_frames <= 0) return;
     const size_t n = (size_t)n_frames * (size_t)n_sites;
     cudaMemsetAsync(count, 0, n * sizeof(int), st);
+    /* WN_COMPONENTS_PATH=global forces the multi-kernel path for frames that would fit shared memory (tests) */
+    const char* force = getenv("WN_COMPONENTS_PATH");
+    const bool allow_smem = !force || strcmp(force, "global") != 0;
     /* frames whose parent array fits one SM's shared memory: one CTA per frame, everything on chip */
     const size_t smem = (size_t)n_sites * sizeof(int) + (size_t)((n_sites + 31) / 32) * sizeof(unsigned int);
-    if (n_sites > 0 && smem <= 220u * 1024u) {
+    if (allow_smem && n_sites > 0 && smem <= 220u * 1024u) {
         if (csr16) {
             cudaFuncSetAttribute(wn_k_cc_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             wn_k_cc_smem<true><<<n_frames, CCS_THREADS, smem, st>>>(edges, frame_off, row_off, n_sites, threshold, labels, count, stats);

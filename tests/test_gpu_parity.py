@@ -901,15 +901,31 @@ def test_host_frames_results_kept_on_device(ctx, oracle, capi):
     ctx.set_batch_frames(0)
 
 
-def test_connected_components_large_frame_global_path(ctx, oracle):
-    """More sites than one SM's shared memory holds (> ~56 k): the multi-kernel global-memory union-find."""
-    n = 60000
-    box = oracle.synth_box(n)
-    frames = oracle.synth_frames(box, 0, 1)
-    ctx.set_water_sites(n)
-    res = ctx.hbond_batch(frames)
-    for thr in (0.0, 1.5):
-        labels, stats = ctx.components(thr)
-        lab, st = oracle.components(res["edges"], n, thr)
-        assert np.array_equal(labels[0], lab)
-        assert [stats[0][k] for k in ("n_components", "largest", "n_nodes", "n_edges")] == list(st)
+def test_connected_components_every_path(ctx, oracle, capi):
+    """The two implementations behind wn_components -- one CTA per frame in shared memory, multi-kernel
+    global memory (frames over ~56 k sites, or forced) -- on the same batches, both layouts, against the oracle."""
+    import os
+    cases = [(60000, 1, (0.0, 1.5), (None,)), (3000, 3, (0.0, 0.8), (None, "global"))]
+    try:
+        for n, nf, thrs, paths in cases:
+            box = oracle.synth_box(n)
+            frames = oracle.synth_frames(box, 0, nf)
+            ctx.set_water_sites(n)
+            res = ctx.hbond_batch(frames)
+            fo = res["frame_offsets"]
+            want = {thr: [oracle.components(res["edges"][int(fo[f]):int(fo[f + 1])], n, thr) for f in range(nf)] for thr in thrs}
+            for layout in (capi.LAYOUT_EDGES, capi.LAYOUT_CSR16):
+                ctx.hbond_batch_ex(frames, layout=layout)
+                for path in paths:
+                    if path is None:
+                        os.environ.pop("WN_COMPONENTS_PATH", None)
+                    else:
+                        os.environ["WN_COMPONENTS_PATH"] = path
+                    for thr in thrs:
+                        labels, stats = ctx.components(thr)
+                        for f in range(nf):
+                            lab, st = want[thr][f]
+                            assert np.array_equal(labels[f], lab), (n, layout, path, thr, f)
+                            assert [stats[f][k] for k in ("n_components", "largest", "n_nodes", "n_edges")] == list(st), (n, layout, path, thr, f)
+    finally:
+        os.environ.pop("WN_COMPONENTS_PATH", None)
