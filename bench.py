@@ -295,14 +295,14 @@ def run_own(args):
     sampler.start()
     time.sleep(0.25)
     barrier()
-    edges_total = evals_total = launches = passes = 0
+    edges_total = evals_total = tests_total = launches = passes = 0
     edges_ms = bin_ms = finish_ms = 0.0
     stats_rows = []
     t0 = time.perf_counter()
     ctx.timer_start()
     for s in range(W, W + K):
         out = ctx.hbond_batch_dev(frames_dev + s * F * frame_bytes, F, natoms)
-        edges_total += out["n_edges"]; evals_total += out["n_pair_evals"]
+        edges_total += out["n_edges"]; evals_total += out["n_pair_evals"]; tests_total += out["n_candidate_tests"]
         tm = ctx.timings()
         launches += tm["launches"]; passes += tm["passes"]
         edges_ms += tm["edges_ms"]; bin_ms += tm["bin_ms"]; finish_ms += tm["finish_ms"]
@@ -357,6 +357,7 @@ def run_own(args):
     frames_all = K * F * world
     fps = frames_all / (dev_ms_max * 1e-3)
     evals_all = allsum(float(evals_total))
+    tests_all = allsum(float(tests_total))
     edges_all = allsum(float(edges_total))
     edges_per_frame = edges_all / frames_all
 
@@ -556,6 +557,8 @@ def run_own(args):
                        "l2_policy": "inputs larger than L2: every step reads %d distinct frames (%.0f MB)" % (F, F * frame_bytes / 1e6),
                        "parallelism": "frame-sharded x%d" % world},
             "pair_evals_per_s": evals_all / (dev_ms_max * 1e-3),
+            "candidate_tests_per_s": tests_all / (dev_ms_max * 1e-3),
+            "candidate_tests_per_frame": tests_all / frames_all,
             "edges_per_s": edges_all / (dev_ms_max * 1e-3),
             "pair_evals_per_frame": evals_all / frames_all, "edges_per_frame": edges_per_frame,
             "wall_ms_per_step": (t1 - t0) * 1e3 / K,

@@ -50,7 +50,8 @@ class BatchResult(C.Structure):
     _fields_ = [("edges", C.c_void_p), ("frame_offsets", C.c_void_p), ("stats", C.c_void_p),
                 ("n_edges", C.c_uint64), ("n_pair_evals", C.c_uint64), ("ties", TieReport),
                 ("n_frames", C.c_int32), ("on_device", C.c_int32),
-                ("row_offsets", C.c_void_p), ("n_sites", C.c_int32), ("layout", C.c_int32)]
+                ("row_offsets", C.c_void_p), ("n_sites", C.c_int32), ("layout", C.c_int32),
+                ("n_candidate_tests", C.c_uint64)]
 
 
 class BatchArgs(C.Structure):
@@ -208,7 +209,8 @@ class Context:
     # ---- batches
     def _wrap(self, res, copy=True):
         nf, ne = res.n_frames, int(res.n_edges)
-        out = {"n_edges": ne, "n_pair_evals": int(res.n_pair_evals), "ties": res.ties.as_dict(),
+        out = {"n_edges": ne, "n_pair_evals": int(res.n_pair_evals), "n_candidate_tests": int(res.n_candidate_tests),
+               "ties": res.ties.as_dict(),
                "n_frames": nf}
         out["n_sites"] = res.n_sites
         out["layout"] = res.layout

@@ -546,9 +546,10 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     if (ctx->h_frame_off[n_frames] != edge_base)
         return fail(ctx, WN_ERR_CUDA, "internal: edge totals disagree between scan and fused kernel");
     wn_tie_report ties = {0, 0, 0, 0, 0};
-    unsigned long long evals = 0;
+    unsigned long long evals = 0, tests = 0;
     for (int f = 0; f < n_frames; ++f) {
         evals += ctx->h_counters[f].evals;
+        tests += ctx->h_counters[f].tests;
         ties.length_equal_cut += ctx->h_counters[f].tie_len;
         ties.cosine_argmax_equal += ctx->h_counters[f].tie_cos;
         ties.pos_zero += ctx->h_counters[f].tie_pos0;
@@ -564,6 +565,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     out->layout = ctx->layout;
     out->n_edges = edge_base;
     out->n_pair_evals = evals;
+    out->n_candidate_tests = tests;
     out->ties = ties;
     out->n_frames = n_frames;
     out->on_device = host_out ? 0 : 1;

@@ -64,6 +64,7 @@ struct WnFrameCounters {
     unsigned long long tie_len;    /* (float)dist == 6.5f                       */
     unsigned long long tie_cos;    /* equal positive cosines in the arg-max     */
     unsigned long long tie_pos0;   /* arg-max on list index 0                   */
+    unsigned long long tests;      /* (home site, candidate) pairs the fp32 prefilter looked at (implementation-dependent) */
 };
 
 /* ---- site meta word (one per site) ---- */

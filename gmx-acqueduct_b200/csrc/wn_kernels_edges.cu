@@ -499,6 +499,9 @@ wn_k_edges(const WnEdgeParams p)
             low_rows = __ballot_sync(FULL, low);
         }
 
+        /* candidate tests of this chunk (statistic only: one fire-and-forget reduction per chunk) */
+        if (lane == 0) atomicAdd(&(p.counters + f)->tests, (unsigned long long)hc * (unsigned long long)total);
+
         int qlen = 0, run = 0;
         const int rounds = (total + 31) >> 5;
         for (int r = 0; r < rounds; ++r) {
@@ -667,6 +670,7 @@ wn_k_edges_small(const WnEdgeParams p)
     }
     WnFrameCounters* fc = p.counters + f;
     if (evals) atomicAdd(&fc->evals, (unsigned long long)evals);
+    if (have && n_f - 1 - pa > 0) atomicAdd(&fc->tests, (unsigned long long)(n_f - 1 - pa));
     if (tie_len) atomicAdd(&fc->tie_len, (unsigned long long)tie_len);
     if (tie_cos) atomicAdd(&fc->tie_cos, (unsigned long long)tie_cos);
     if (tie_pos0) atomicAdd(&fc->tie_pos0, (unsigned long long)tie_pos0);

@@ -110,6 +110,8 @@ typedef struct wn_batch_result {
     const uint32_t*       row_offsets;
     int32_t               n_sites;
     int32_t               layout;         /* WN_LAYOUT_EDGES or WN_LAYOUT_CSR16 */
+    uint64_t              n_candidate_tests; /* (site, candidate) pairs the search examined, sum over frames:
+                                              * implementation-dependent, reported next to n_pair_evals */
 } wn_batch_result;
 
 /* ---- context ------------------------------------------------------------ */

@@ -890,6 +890,10 @@ def test_host_frames_results_kept_on_device(ctx, oracle, capi):
     lab_h, st_h = ctx.components(0.5)
     dev = ctx.hbond_batch_ex(frames, results_on_device=True)
     assert "edges_dev" in dev and dev["n_edges"] == host["n_edges"]
+    # every counted pair evaluation was first a candidate test; the half-shell sweep looks at a few hundred
+    # candidates per site at liquid density
+    assert host["n_pair_evals"] <= host["n_candidate_tests"] == dev["n_candidate_tests"]
+    assert 50 * n * nf < host["n_candidate_tests"] < 400 * n * nf
     e, fo, st = ctx.fetch_dev_result(dev)
     assert e.tobytes() == host["edges"].tobytes() and np.array_equal(fo, host["frame_offsets"])
     assert st.tobytes() == host["stats"].tobytes()

@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol(capi):
 
 def test_struct_layouts_match_header(capi):
     assert ctypes.sizeof(capi.TieReport) == 40
-    assert ctypes.sizeof(capi.BatchResult) == 8 * 3 + 8 * 2 + 40 + 8 + 8 + 8
+    assert ctypes.sizeof(capi.BatchResult) == 8 * 3 + 8 * 2 + 40 + 8 + 8 + 8 + 8
     assert capi.EDGE_DTYPE.itemsize == 20 and capi.STATS_DTYPE.itemsize == 40 and capi.EDGE16_DTYPE.itemsize == 16
     assert ctypes.sizeof(capi.BatchArgs) == 8 + 4 * 4 + 8 * 3 + 8
     assert ctypes.sizeof(capi.Timings) == 32
