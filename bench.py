@@ -296,6 +296,7 @@ def run_own(args):
     time.sleep(0.25)
     barrier()
     edges_total = evals_total = tests_total = launches = passes = 0
+    ties_total = {}
     edges_ms = bin_ms = finish_ms = 0.0
     stats_rows = []
     t0 = time.perf_counter()
@@ -303,6 +304,8 @@ def run_own(args):
     for s in range(W, W + K):
         out = ctx.hbond_batch_dev(frames_dev + s * F * frame_bytes, F, natoms)
         edges_total += out["n_edges"]; evals_total += out["n_pair_evals"]; tests_total += out["n_candidate_tests"]
+        for k, v in out["ties"].items():
+            ties_total[k] = ties_total.get(k, 0) + v
         tm = ctx.timings()
         launches += tm["launches"]; passes += tm["passes"]
         edges_ms += tm["edges_ms"]; bin_ms += tm["bin_ms"]; finish_ms += tm["finish_ms"]
@@ -376,7 +379,8 @@ def run_own(args):
             tmf = ctx.timings()
         wall = (time.perf_counter() - t_0) / reps
         bytes_find = 24.0 * n_waters + 8.0 * len(pairs)
-        find = {"pairs": int(len(pairs)), "kernels_ms": tmf["total_ms"], "d2h_ms": tmf["d2h_ms"],
+        find = {"pairs": int(len(pairs)), "ties": _t if isinstance(_t, dict) else None,
+                "kernels_ms": tmf["total_ms"], "d2h_ms": tmf["d2h_ms"],
                 "wall_ms_incl_numpy_copy": wall * 1e3, "algorithmic_bytes": bytes_find,
                 "kernel_GBps": bytes_find / (tmf["total_ms"] * 1e-3) / 1e9,
                 "frac_of_hbm_peak": bytes_find / (tmf["total_ms"] * 1e-3) / 1e9 / float(
@@ -559,6 +563,7 @@ def run_own(args):
             "pair_evals_per_s": evals_all / (dev_ms_max * 1e-3),
             "candidate_tests_per_s": tests_all / (dev_ms_max * 1e-3),
             "candidate_tests_per_frame": tests_all / frames_all,
+            "ties_rank0": ties_total,      # exact-comparison ties met in the timed frames (SURVEY 8d evidence)
             "edges_per_s": edges_all / (dev_ms_max * 1e-3),
             "pair_evals_per_frame": evals_all / frames_all, "edges_per_frame": edges_per_frame,
             "wall_ms_per_step": (t1 - t0) * 1e3 / K,
