@@ -518,6 +518,7 @@ def run_own(args):
         pass
     roofline = {"bound": "hbm", "kernel": "wn_k_edges", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac_of_nominal_8000": achieved / 8000.0,
                 "bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": k_ms,
                 "frames_per_launch": K * F / max(passes, 1),
                 "pipeline_frac": (algorithmic_bytes_per_frame(natoms, edges_per_frame) * fps / world / 1e9) / peak,
