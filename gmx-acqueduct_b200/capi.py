@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WN_B200_LIB") or os.path.join(HERE, "libwn_b200.so")
 
 WN_OK = 0
+# status codes of include/wn_b200.h
+WN_ERR_CUDA, WN_ERR_OOM, WN_ERR_BAD_ARG, WN_ERR_NO_SITES, WN_ERR_OVERFLOW, WN_ERR_NCCL, WN_ERR_NO_DEVICE = 1, 2, 3, 4, 5, 6, 7
 DONOR, ACCEPTOR, WATER = 0, 1, 2
 MODEL_TIP3P, MODEL_SPC = 0, 1
 

@@ -933,3 +933,25 @@ def test_connected_components_every_path(ctx, oracle, capi):
                             assert [stats[f][k] for k in ("n_components", "largest", "n_nodes", "n_edges")] == list(st), (n, layout, path, thr, f)
     finally:
         os.environ.pop("WN_COMPONENTS_PATH", None)
+
+
+def test_new_entry_points_reject_misuse(oracle, capi):
+    """Error behaviour of the later additions: no batch yet, unknown layout, text of a CSR16 result."""
+    c = capi.Context(0)
+    try:
+        c.set_water_sites(10)
+        with pytest.raises(capi.WnError) as ei:
+            c.components(0.0, n_frames=1)
+        assert ei.value.code == capi.WN_ERR_BAD_ARG and "no batch result" in str(ei.value)
+        frames = oracle.synth_frames(oracle.synth_box(10), 0, 2)
+        with pytest.raises(capi.WnError) as ei:
+            c.hbond_batch_ex(frames, layout=7)
+        assert ei.value.code == capi.WN_ERR_BAD_ARG and "result_layout" in str(ei.value)
+        c.hbond_batch_ex(frames, layout=capi.LAYOUT_CSR16)
+        with pytest.raises(capi.WnError) as ei:
+            c.format_edges(np.arange(2))
+        assert "WN_LAYOUT_EDGES" in str(ei.value)
+        labels, stats = c.components(0.0)              # a CSR16 result is fine for the components
+        assert labels.shape == (2, 10)
+    finally:
+        c.close()

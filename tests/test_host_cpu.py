@@ -157,3 +157,15 @@ def test_make_sites_rules():
         g.build()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "test_sites OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_python_status_codes_match_the_header():
+    """status codes match the header (capi.py mirrors include/wn_b200.h)."""
+    import re
+    import wn_pkg
+    capi = wn_pkg.load_capi()
+    hdr = open(os.path.join(ROOT, "include", "wn_b200.h")).read()
+    codes = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"#define (WN_(?:OK|ERR_[A-Z_]+))\s+(\d+)", hdr))
+    assert len(codes) >= 8
+    for name, value in codes.items():
+        assert getattr(capi, name) == value, name
