@@ -14,8 +14,9 @@
 //   analyzeFrame    the frame's coordinates (protein selection, then solvent selection) are pushed into a
 //                   FrameBatcher; with an alpha-shape filter the frame's site list is protein sites followed
 //                   by the waters the filter keeps (:533, :562-576) -- the filter itself (CGAL alpha shapes) is
-//                   outside this path, so every solvent water is used unless -buried-index supplies the lists
-//   finishAnalysis  flushes the last batch (:670)
+//                   outside this path, so this module uses every solvent water (FrameBatcher::push with a
+//                   frameSites list is the hook for a filter)
+//   ModuleData::finish / finishAnalysis  flush the last batch and its data-set rows, close the edges file (:670)
 // Edge rows come from the GPU formatter once per batch (wn_format_edges), with the host writer as fallback.
 #ifdef WN_WITH_GROMACS
 
@@ -34,7 +35,11 @@
 class WaterNetworkB200 : public gmx::TrajectoryAnalysisModule
 {
 public:
-    WaterNetworkB200() : lengthOn_(5.5), lengthOff_(6.5), angleOn_(0.25), angleOff_(0.0), batchFrames_(256), usePbc_(false) {}
+    WaterNetworkB200() : lengthOn_(5.5), lengthOff_(6.5), angleOn_(0.25), angleOff_(0.0), batchFrames_(256), usePbc_(false)
+    {
+        registerAnalysisDataset(&buriedData_, "buried");
+        registerAnalysisDataset(&hydroBondData_, "hbond");
+    }
 
     void initOptions(gmx::IOptionsContainer* options, gmx::TrajectoryAnalysisSettings* settings) override
     {
@@ -114,8 +119,6 @@ public:
 
         buriedData_.setColumnCount(0, 2);
         hydroBondData_.setColumnCount(0, 6);
-        registerAnalysisDataset(&buriedData_, "buried");
-        registerAnalysisDataset(&hydroBondData_, "hbond");
         addPlot(settings, buriedData_, fnBuried_, "Filter Statistics");
         addPlot(settings, hydroBondData_, fnHydroBond_, "Graph Statistics");
 
