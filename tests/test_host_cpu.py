@@ -169,3 +169,16 @@ def test_python_status_codes_match_the_header():
     assert len(codes) >= 8
     for name, value in codes.items():
         assert getattr(capi, name) == value, name
+
+
+def test_gromacs_module_passes_the_front_end_against_the_api_shim():
+    """GROMACS is absent: the compile-gated module is at least run through g++ -fsyntax-only against
+    tests/shim/gromacs (declarations restated from the public API) and, ungated, compiles to nothing."""
+    import subprocess
+    src = os.path.join(ROOT, "gmx-acqueduct_b200", "host", "gromacs", "waternetwork-b200.cpp")
+    inc = ["-I" + os.path.join(ROOT, "include")]
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-DWN_WITH_GROMACS",
+                        "-I" + os.path.join(ROOT, "tests", "shim")] + inc + [src], capture_output=True, text=True)
+    assert r.returncode == 0 and "error" not in r.stderr, r.stderr
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only"] + inc + [src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
