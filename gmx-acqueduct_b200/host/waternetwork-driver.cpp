@@ -19,6 +19,10 @@
 //                   [-ohb hydrogen-bonds-num.xvg] [-obw buried-waters-num.xvg]
 //                   [-solvent SOL,WAT,HOH,TIP3] [-buried lists.txt] [-pbc] [-batch 256] [-device 0]
 //                   [-don 5.5] [-doff 6.5] [-aon 0.25] [-aoff 0.0] [-bug-compat 0|1] [-gpu-text 1|0]
+//                   [-components threshold [-ocomp components-num.xvg]]
+// -components: per frame, the connected components of the network after dropping the edges with
+// |energy| <= threshold (the first step of python/network-analysis.py, computed on the GPU): one row
+// "time components largest sites edges" per frame.
 // File name options take the reference's base names: ".dat" is appended to -edges/-nodes (:461,:485).
 #include <cmath>
 #include <cstdio>
@@ -106,11 +110,13 @@ std::string elementOf(const std::string& name)
 
 struct Options {
     std::string traj, edges = "edges-frames.xvg", nodes = "nodes-list.xvg", ohb = "hydrogen-bonds-num.xvg",
-                obw = "buried-waters-num.xvg", buried;
+                obw = "buried-waters-num.xvg", buried, ocomp = "components-num.xvg";
     std::set<std::string> solvent{"SOL", "WAT", "HOH", "TIP3", "SPC"};
     bool pbc = false, bugCompat = true, gpuText = true;
     int batch = 256, device = 0;
     double don = 5.5, doff = 6.5, aon = 0.25, aoff = 0.0;
+    bool components = false;
+    double compThreshold = 0.0;
 };
 
 Options parse(int argc, char** argv)
@@ -137,6 +143,8 @@ Options parse(int argc, char** argv)
         else if (a == "-aoff") o.aoff = std::atof(val().c_str());
         else if (a == "-bug-compat") o.bugCompat = std::atoi(val().c_str()) != 0;
         else if (a == "-gpu-text") o.gpuText = std::atoi(val().c_str()) != 0;
+        else if (a == "-components") { o.components = true; o.compThreshold = std::atof(val().c_str()); }
+        else if (a == "-ocomp") o.ocomp = val();
         else if (a == "-solvent") {
             o.solvent.clear();
             std::istringstream ss(val());
@@ -281,7 +289,18 @@ int main(int argc, char** argv)
 
         // edge rows of a whole batch from the GPU formatter (same bytes); a batch with a field wider than its
         // column (ids over 6 digits, values over 8 characters) goes through the host writer instead
+        std::ofstream ocomp;
+        if (opt.components && !opt.ocomp.empty()) ocomp.open(opt.ocomp);
         batcher.setBatchHook([&](const std::vector<int>& frameNumbers, const HydrogenBondBatch&) {
+            if (ocomp.is_open()) {
+                const int32_t* labels = nullptr; const wn_component_stats* cs = nullptr;
+                hb.componentsOfLastBatch((float)opt.compThreshold, &labels, &cs);
+                for (size_t k = 0; k < frameNumbers.size(); ++k) {
+                    std::snprintf(row, sizeof row, " %11.3f %8d %8d %8d %8d\n", times[(size_t)frameNumbers[k]], cs[k].n_components,
+                                  cs[k].largest, cs[k].n_nodes, cs[k].n_edges);
+                    ocomp << row;
+                }
+            }
             batch_text_done = false;
             if (!writer || !opt.gpuText || buried.is_open()) return;     // site lists: ids differ per frame, host path
             const char* text = nullptr; uint64_t bytes = 0;

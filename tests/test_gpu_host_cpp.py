@@ -69,7 +69,8 @@ def test_standalone_driver_writes_the_reference_files(tmp_path, pbc, gpu_text):
     exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
     assert os.path.exists(exe), "build first: __graft_entry__.build()"
     args = [exe, "-f", gro, "-edges", str(tmp_path / "edges"), "-nodes", str(tmp_path / "nodes"),
-            "-ohb", str(tmp_path / "ohb.xvg"), "-obw", str(tmp_path / "obw.xvg"), "-batch", "2", "-gpu-text", str(gpu_text)]
+            "-ohb", str(tmp_path / "ohb.xvg"), "-obw", str(tmp_path / "obw.xvg"), "-batch", "2", "-gpu-text", str(gpu_text),
+            "-components", "0.5", "-ocomp", str(tmp_path / "comp.xvg")]
     if pbc:
         args.append("-pbc")
     r = subprocess.run(args, capture_output=True, text=True, timeout=300)
@@ -81,6 +82,7 @@ def test_standalone_driver_writes_the_reference_files(tmp_path, pbc, gpu_text):
     boxf = np.float32(np.float64("%10.5f" % box))
     want = "%6s%8s%6s%6s%8s%6s%8s%8s%8s" % ("#Id", "AtmId", "ResId", "Id", "AtmId", "ResId", "Energy", "Length", "Cos\n")
     ohb = ""
+    comp = ""
     for f in range(nf):
         if pbc:
             e, st, _, _ = o.frame_hbonds_pbc(parsed[f], sa, ha, ty, np.array([boxf] * 3, np.float32))
@@ -92,8 +94,11 @@ def test_standalone_driver_writes_the_reference_files(tmp_path, pbc, gpu_text):
                         for a, b, en, ln, cs in zip(e["i"], e["j"], e["energy"].astype(np.float64),
                                                     e["length"].astype(np.float64), e["cosine"].astype(np.float64)))
         ohb += " %11.3f %8.3f %8.3f %8.3f %8.3f %8.3f %8.3f\n" % (2.0 * f, n, len(e), len(e) / n, 0, 0, 0)
+        _, cst = o.components(e, n, 0.5)
+        comp += " %11.3f %8d %8d %8d %8d\n" % (2.0 * f, cst[0], cst[1], cst[2], cst[3])
     got = open(str(tmp_path / "edges.dat")).read()
     assert got == want
+    assert open(str(tmp_path / "comp.xvg")).read() == comp
     assert open(str(tmp_path / "ohb.xvg")).read() == ohb
     assert open(str(tmp_path / "obw.xvg")).read() == "".join(" %11.3f %8.3f %8.3f\n" % (2.0 * f, n, 0) for f in range(nf))
     nodes = open(str(tmp_path / "nodes.dat")).read().splitlines()
