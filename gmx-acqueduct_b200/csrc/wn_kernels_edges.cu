@@ -325,7 +325,8 @@ wn_k_block_prefix(const WnGrid* __restrict__ grid, int n_frames, int* __restrict
 /* Persistent warps: every warp claims home blocks (frame, block) from one counter until the pass is
  * exhausted -- blocks differ in cost (10..30 home sites, boundary blocks with few neighbours), and a
  * static block-per-warp grid left ~20 % of the resident warp slots idle behind the slowest warp of a CTA. */
-template <bool SIMPLE, int PBC, int BX>
+/* LIMITED: only pairs with min(index) < first_limit are wanted (BASELINE config 5); compiled out otherwise */
+template <bool SIMPLE, int PBC, int BX, bool LIMITED>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WN_EDGES_MINBLOCKS)
 wn_k_edges(const WnEdgeParams p)
 {
@@ -494,7 +495,7 @@ wn_k_edges(const WnEdgeParams p)
         __syncwarp();
         /* rows >= first_limit own nothing: a pair needs min(index) < first_limit */
         uint32_t low_rows = 0;
-        if (p.first_limit < p.n_sites) {
+        if (LIMITED) {
             const bool low = lane < hc && __float_as_int(ws.hpos[lane].w) < p.first_limit;
             low_rows = __ballot_sync(FULL, low);
         }
@@ -523,7 +524,7 @@ wn_k_edges(const WnEdgeParams p)
                 /* own block: only home rows stored before the candidate (each pair once) */
                 const int ahead = c - hb;
                 allow = (c < h0 || c >= h1 || ahead >= 32) ? 0xffffffffu : (ahead <= 0 ? 0u : ((1u << ahead) - 1u));
-                if (p.first_limit < p.n_sites && __float_as_int(b4.w) >= p.first_limit) allow &= low_rows;
+                if (LIMITED && __float_as_int(b4.w) >= p.first_limit) allow &= low_rows;
                 if (!SIMPLE) cm = __ldg(p.smeta + fbase + c);
             }
             /* lane-private hit mask: bit h = home row h is a candidate partner.
@@ -747,7 +748,7 @@ size_t wn_edges_smem_bytes(int hs)
 }
 
 namespace {
-template <bool SIMPLE, int PBC, int BX>
+template <bool SIMPLE, int PBC, int BX, bool LIMITED>
 void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
     const size_t smem = wn_edges_smem_bytes(p.hs);
@@ -755,15 +756,15 @@ void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
     static int s_ctas = 0;
     static size_t s_smem = 0;
     if (s_ctas == 0 || s_smem != smem) {
-        cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX, LIMITED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0, dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wn_k_edges<SIMPLE, PBC, BX>, WARPS_PER_CTA * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wn_k_edges<SIMPLE, PBC, BX, LIMITED>, WARPS_PER_CTA * 32, smem);
         per_sm = std::max(1, per_sm);
         /* ask for exactly the shared memory the resident CTAs use (1 KB per CTA is reserved); the rest stays L1 */
         const int carve = (int)std::min<size_t>(100, ((size_t)per_sm * (smem + 1024) * 100 + 233471) / 233472);
-        cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(wn_k_edges<SIMPLE, PBC, BX, LIMITED>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         s_ctas = per_sm * std::max(1, sms);
         s_smem = smem;
     }
@@ -772,7 +773,16 @@ void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
     /* no more CTAs than there is work for (blocks per frame <= cell_cap) */
     const long long max_items = (long long)n_frames * p.cell_cap;
     const int grid = (int)std::min<long long>(ctas, (max_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    wn_k_edges<SIMPLE, PBC, BX><<<std::max(grid, 1), WARPS_PER_CTA * 32, smem, st>>>(p);
+    wn_k_edges<SIMPLE, PBC, BX, LIMITED><<<std::max(grid, 1), WARPS_PER_CTA * 32, smem, st>>>(p);
+}
+}  // namespace
+
+namespace {
+template <bool SIMPLE, int PBC, int BX>
+void launch_limited(const WnEdgeParams& p, int n_frames, cudaStream_t st)
+{
+    if (p.first_limit < p.n_sites) launch_variant<SIMPLE, PBC, BX, true>(p, n_frames, st);
+    else launch_variant<SIMPLE, PBC, BX, false>(p, n_frames, st);
 }
 }  // namespace
 
@@ -780,18 +790,18 @@ void wn_launch_edges(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 {
     const int key = (p.simple ? 6 : 0) + p.pbc * 2 + (p.bx == 2 ? 1 : 0);
     switch (key) {
-    case 0: launch_variant<false, 0, 1>(p, n_frames, st); break;
-    case 1: launch_variant<false, 0, 2>(p, n_frames, st); break;
-    case 2: launch_variant<false, 1, 1>(p, n_frames, st); break;
-    case 3: launch_variant<false, 1, 2>(p, n_frames, st); break;
-    case 4: launch_variant<false, 2, 1>(p, n_frames, st); break;
-    case 5: launch_variant<false, 2, 2>(p, n_frames, st); break;
-    case 6: launch_variant<true, 0, 1>(p, n_frames, st); break;
-    case 7: launch_variant<true, 0, 2>(p, n_frames, st); break;
-    case 8: launch_variant<true, 1, 1>(p, n_frames, st); break;
-    case 9: launch_variant<true, 1, 2>(p, n_frames, st); break;
-    case 10: launch_variant<true, 2, 1>(p, n_frames, st); break;
-    default: launch_variant<true, 2, 2>(p, n_frames, st); break;
+    case 0: launch_limited<false, 0, 1>(p, n_frames, st); break;
+    case 1: launch_limited<false, 0, 2>(p, n_frames, st); break;
+    case 2: launch_limited<false, 1, 1>(p, n_frames, st); break;
+    case 3: launch_limited<false, 1, 2>(p, n_frames, st); break;
+    case 4: launch_limited<false, 2, 1>(p, n_frames, st); break;
+    case 5: launch_limited<false, 2, 2>(p, n_frames, st); break;
+    case 6: launch_limited<true, 0, 1>(p, n_frames, st); break;
+    case 7: launch_limited<true, 0, 2>(p, n_frames, st); break;
+    case 8: launch_limited<true, 1, 1>(p, n_frames, st); break;
+    case 9: launch_limited<true, 1, 2>(p, n_frames, st); break;
+    case 10: launch_limited<true, 2, 1>(p, n_frames, st); break;
+    default: launch_limited<true, 2, 2>(p, n_frames, st); break;
     }
 }
 
