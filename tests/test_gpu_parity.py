@@ -955,3 +955,26 @@ def test_new_entry_points_reject_misuse(oracle, capi):
         assert labels.shape == (2, 10)
     finally:
         c.close()
+
+
+def test_soak_many_frames_against_oracle(ctx, oracle):
+    """200 frames of the 4,000-water box in one device batch (persistent warps over ~50 k home blocks, several
+    internal passes): every frame's edge list equals the oracle's, bit for bit."""
+    n, nf = 4000, 200
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 1000, nf)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    ctx.set_batch_frames(64)
+    res = ctx.hbond_batch(frames)
+    ctx.set_batch_frames(0)
+    fo = res["frame_offsets"]
+    for f in range(nf):
+        want, stats, _, nevals = oracle.frame_hbonds(frames[f], sa, ha, ty)
+        got = res["edges"][int(fo[f]):int(fo[f + 1])]
+        assert len(got) == len(want), f
+        assert np.array_equal(got["i"], want["i"]) and np.array_equal(got["j"], want["j"]), f
+        assert np.array_equal(got["length"].view(np.uint32), want["length"].view(np.uint32)), f
+        assert np.array_equal(got["cosine"].view(np.uint32), want["cosine"].view(np.uint32)), f
+        assert np.allclose(got["energy"], want["energy"], rtol=1e-6, atol=0), f
+        assert res["stats"]["pair_evals"][f] == nevals
