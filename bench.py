@@ -50,6 +50,14 @@ def synth_box_length(n_waters):
     return x
 
 
+def workload_config(n_waters):
+    """The workload both arms run (identical keys and values in the own and the reference line)."""
+    return {"workload": "configs[2]: 100k-atom (33,333 TIP3P waters) box, open boundary (reference BruteFindPairs has no PBC)"
+            if n_waters == N_WATERS else "custom: %d waters" % n_waters,
+            "n_waters": n_waters, "natoms": 3 * n_waters, "seed": SEED,
+            "generator": "include/wn_synth.h jittered-lattice water, 33.4 nm^-3, frames 0.. of seed 1234"}
+
+
 def algorithmic_bytes_per_frame(natoms, edges_per_frame):
     """read the frame once as delivered, write compact edges + stats."""
     return 12.0 * natoms + 20.0 * edges_per_frame + 32.0
@@ -113,7 +121,16 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------- reference (CPU) arm
-def cpu_reference_run(frames_host, threads):
+def edge_digest(e):
+    """Order-sensitive digest of the bit-exact part of an edge list: (i, j, length, cosine) bytes."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for k in ("i", "j", "length", "cosine"):
+        h.update(np.ascontiguousarray(e[k]).tobytes())
+    return h.hexdigest()
+
+
+def cpu_reference_run(frames_host, threads, keep_energy=False):
     """Reference path on the host: brute-find-pairs + make_edges per frame, frames
     fanned out over `threads` host threads (ctypes releases the GIL).  Uses the
     reference's own sources (oracle/_ref) when that build is present, else the
@@ -131,10 +148,10 @@ def cpu_reference_run(frames_host, threads):
     def work(f):
         if ref is not None:
             e, npairs = oracle.ref_frame_hbonds_water(frames_host[f])
-            results[f] = (len(e), None)
+            results[f] = (len(e), None, edge_digest(e), e["energy"].copy() if keep_energy else None)
         else:
             e, st, npairs, ev = oracle.frame_hbonds(frames_host[f], sa, ha, ty)
-            results[f] = (len(e), ev)
+            results[f] = (len(e), ev, edge_digest(e), e["energy"].copy() if keep_energy else None)
 
     t0 = time.perf_counter()
     pending = list(range(nf))
@@ -233,10 +250,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2]: 100k-atom (33,333 TIP3P waters) box, open boundary (reference BruteFindPairs has no PBC)"
-                   if args.waters == N_WATERS else "custom: %d waters" % args.waters,
-                   "n_waters": args.waters, "natoms": 3 * args.waters, "frames_per_step": per_step,
-                   "seed": SEED},
+        "config": workload_config(args.waters),
+        "run": {"frames_per_step": per_step, "frames_total": args.steps * per_step,
+                "parallelism": "%d host threads, one frame each" % threads},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -526,17 +542,48 @@ def run_own(args):
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same frames
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = usable_threads()
         nfr = max(1, min(threads, 64))
         sample = np.empty((nfr, natoms, 3), np.float32)
         ctx.d2h(sample, frames_dev)
-        dt, kind, _, _ = cpu_reference_run(sample, threads)
+        dt, kind, _, cres = cpu_reference_run(sample, threads, keep_energy=True)
         dt1, _, _, _ = cpu_reference_run(sample[:1], 1)
+        # the frames the CPU arm just processed, through the GPU path: same edge lists?
+        outp = ctx.hbond_batch_dev(frames_dev, nfr, natoms)
+        ge, gfo, _gst = ctx.fetch_dev_result(outp)
+        bad = []
+        for f in range(nfr):
+            gf = ge[int(gfo[f]):int(gfo[f + 1])]
+            ok = len(gf) == cres[f][0] and edge_digest(gf) == cres[f][2]
+            if ok and len(gf):
+                we = cres[f][3].astype(np.float64)
+                ok = bool(np.all(np.abs(gf["energy"].astype(np.float64) - we) <= 1e-6 * np.abs(we)))
+            if not ok:
+                bad.append(f)
+        parity = {"frames": nfr, "edges": int(sum(r[0] for r in cres)), "ok": not bad,
+                  "checked": "edge count and the bytes of (i, j, length, cosine) per frame vs the %s CPU result "
+                             "of the same frames; energy <= 1e-6 relative" % kind}
+        if bad:
+            parity["bad_frames"] = bad
+        chunked = None
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import wn_oracle_py as oracle
+        if oracle.ref() is not None and hasattr(oracle.ref(), "wnref_frame_hbonds_water_chunked"):
+            t_c = time.perf_counter()
+            ec, _npairs, secs = oracle.ref_frame_hbonds_water_chunked(sample[0], threads)
+            t_c = time.perf_counter() - t_c
+            chunked = {"value": 1.0 / t_c, "unit": "frames/s", "cores": threads,
+                       "find_s": secs[0], "make_edges_s": secs[1],
+                       "same_edges_as_frame_per_thread": bool(len(ec) == cres[0][0] and edge_digest(ec) == cres[0][2]),
+                       "note": "the reference's own per-frame schedule (src/waternetwork.cpp:583-633): single-threaded "
+                               "brute find, then hardware_concurrency() std::async chunks of make_edges joined in order"}
         cpu = {"value": nfr / dt, "unit": "frames/s", "cores": min(threads, nfr), "kind": kind,
                "sample": "%d frame(s) of the same 100k-atom workload, one per host thread "
                          "(brute-find-pairs O(N^2) + make_edges), %.1f s wall" % (nfr, dt),
                "single_thread_frames_per_s": 1.0 / dt1,
+               "intra_frame_chunked": chunked,
                "delaunay_find_pairs": delaunay_proxy_run(sample)}
 
     ctx.pinned_free(host_ptr)
@@ -555,12 +602,10 @@ def run_own(args):
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[2]: 100k-atom (33,333 TIP3P waters) box, open boundary (reference BruteFindPairs has no PBC)"
-                       if n_waters == N_WATERS else "custom: %d waters" % n_waters,
-                       "n_waters": n_waters, "natoms": natoms, "frames_per_step": F,
-                       "frames_total": frames_all, "seed": SEED,
-                       "l2_policy": "inputs larger than L2: every step reads %d distinct frames (%.0f MB)" % (F, F * frame_bytes / 1e6),
-                       "parallelism": "frame-sharded x%d" % world},
+            "config": workload_config(n_waters),
+            "run": {"frames_per_step": F, "frames_total": frames_all,
+                    "l2_policy": "inputs larger than L2: every step reads %d distinct frames (%.0f MB)" % (F, F * frame_bytes / 1e6),
+                    "parallelism": "frame-sharded x%d" % world},
             "pair_evals_per_s": evals_all / (dev_ms_max * 1e-3),
             "candidate_tests_per_s": tests_all / (dev_ms_max * 1e-3),
             "candidate_tests_per_frame": tests_all / frames_all,
@@ -577,6 +622,7 @@ def run_own(args):
             "per_rank": per_rank if world > 1 else None,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity_in_bench": parity,
             "periodic": periodic,
             "find_pairs": find,
             "edge_file_text": text,
@@ -588,6 +634,9 @@ def run_own(args):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+    if parity is not None and not parity["ok"]:
+        print("bench.py: GPU edge lists differ from the CPU reference on frames %s" % parity.get("bad_frames"), file=sys.stderr)
+        return 3
     return 0
 
 

@@ -86,6 +86,7 @@ struct wn_ctx {
     /* text formatting of the last batch */
     int last_frames = -1;                      /* frames of the last wn_hbond_batch* call, -1: none */
     int last_on_device = 0;                    /* that call's results live on the device (*_dev) */
+    int last_subset = 0;                       /* that call used per-frame site lists: edge indices are list positions */
     /* connected components of the last batch */
     int* d_cc_labels = nullptr; int* d_cc_work = nullptr; int* d_cc_count = nullptr; int* d_cc_minidx = nullptr;
     unsigned int* d_cc_kept = nullptr;
@@ -560,6 +561,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     ctx->last_frames = n_frames;
     ctx->last_edges = edge_base;
     ctx->last_on_device = host_out ? 0 : 1;
+    ctx->last_subset = ctx->sub_off_host ? 1 : 0;
     out->row_offsets = host_out ? ctx->h_row_off : ctx->d_row_off;
     out->n_sites = N;
     out->layout = ctx->layout;
@@ -709,7 +711,7 @@ int wn_set_sites(wn_ctx* ctx, int32_t n_sites, const int32_t* site_atom, const i
         WN_CK(cudaMemcpy(ctx->d_meta, meta.data(), meta.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     ctx->n_sites = n_sites; ctx->hs = hs; ctx->simple = simple ? 1 : 0; ctx->max_atom = max_atom;
-    ctx->first_limit = first_limit < 0 ? 0 : first_limit;
+    ctx->first_limit = first_limit < 0 ? n_sites : first_limit;     /* negative: every row, as the C++ wrappers say */
     ctx->row_cap = 32;      /* a new table is a new system: forget a grown row capacity */
     return WN_OK;
 }
@@ -1062,6 +1064,11 @@ int wn_format_edges(wn_ctx* ctx, const int32_t* frame_numbers, const uint32_t* s
     *text = nullptr; *text_bytes = 0;
     if (ctx->last_frames < 0) return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: no batch result to format");
     if (ctx->layout != WN_LAYOUT_EDGES) return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: needs a WN_LAYOUT_EDGES result");
+    /* per-frame site lists: edge indices are positions in each frame's list, not table rows, so a table of
+     * ids cannot be applied on the device; map the indices on the host (EdgeFileWriter) instead */
+    if (ctx->last_subset && site_ids)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: the last batch used per-frame site lists (edge indices are list "
+                    "positions); pass site_ids = NULL or format on the host");
     const int F = ctx->last_frames;
     if (F > 0 && !frame_numbers) return fail(ctx, WN_ERR_BAD_ARG, "wn_format_edges: frame_numbers is NULL");
     if (site_ids && n_site_ids < ctx->n_sites)

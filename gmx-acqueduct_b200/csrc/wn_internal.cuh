@@ -30,7 +30,9 @@ struct WnGrid {
 /* Minimum cell edge, and the fp32 prefilter bound for a given (largest) cell edge: exact
  * acceptance needs d2 <= 0.4225*(1+2.5e-7); the dot-product form on block-local
  * coordinates (|a|^2 <= 1.5 e^2, |c|^2 <= 8.5 e^2, six fp32 roundings on terms <= 8.5 e^2,
- * coordinates rounded at <= 6e-8 * 2e) errs by <= ~3.1e-6 e^2 + 5e-7 e; > 2x head-room. */
+ * coordinates rounded at <= 6e-8 * 2e) errs by <= ~3.1e-6 e^2 + 5e-7 e; > 2x head-room.
+ * Periodic grids add a term for the float image shift folded into the run origin
+ * (wn_host_pbc_grid: 8 ulp of twice the longest box vector). */
 #define WN_CELL_EDGE      (0.65 * (1.0 + 1.0e-5))
 #define WN_PREFILTER_BOUND(e) (0.4225 * (1.0 + 1.0e-5) + 8.0e-6 * (e) * (e) + 2.0e-6 * (e))
 

@@ -187,7 +187,13 @@ void wn_host_pbc_grid(const float box[3], int cell_cap, WnGrid* g)
     }
     g->nx = n[0]; g->ny = n[1]; g->nz = n[2];
     g->ncells = n[0] * n[1] * n[2];
-    const double tfd = WN_PREFILTER_BOUND(emax);
+    /* the periodic image shift is folded into a float run origin (orx -+ L, or ii*ax + jj*bx + k*cx):
+     * each component is rounded at up to ulp(|shift|)/2 + ulp(|origin|)/2, and a d^2 of ~0.42 with
+     * |d| <= 1.2 nm moves by <= 2*1.2*3*ulp -- negligible for everyday boxes, decisive from ~30 nm on */
+    double lmax = 0.0;
+    for (int c = 0; c < 3; ++c) lmax = fmax(lmax, 2.0 * L[c]);      /* triclinic: |ii*ax + jj*bx + k*cx| < 2 max L */
+    const double ulp_shift = (double)(nextafterf((float)lmax, 3.0e38f) - (float)lmax);
+    const double tfd = WN_PREFILTER_BOUND(emax) + 8.0 * ulp_shift;
     float tf = (float)tfd;
     if ((double)tf < tfd) tf = nextafterf(tf, 3.0e38f);
     g->tf = tf;

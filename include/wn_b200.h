@@ -237,7 +237,9 @@ int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);
  * the reference prints SiteInfo::id).  Byte-identical to the reference's iostream output.
  * *text: library-owned pinned host memory, valid until the next call on this context.
  * Returns WN_ERR_OVERFLOW (nothing usable in *text) if some id needs more than 6 digits or a
- * value more than 8 characters: format that batch with a general host formatter instead. */
+ * value more than 8 characters: format that batch with a general host formatter instead.
+ * After a batch with per-frame site lists the edge indices are list positions, which a table of
+ * ids cannot translate on the device: site_ids must be NULL then (WN_ERR_BAD_ARG otherwise). */
 /* ---- connected components of the per-frame networks (python/network-analysis.py:141-171) ----
  * Works on the edge list of the LAST wn_hbond_batch* call of this context (either layout), on the
  * device.  Per frame, as the reference's downstream script does with the edge file: an edge is
@@ -246,7 +248,8 @@ int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);
  * (remove_node_degree, :26-35), the rest is split into connected components
  * (nx.node_connected_component, :155).
  * labels[f * n_sites + s]: smallest site index of the component of site s in frame f, or -1 if s has
- * no kept edge.  stats[f]: see wn_component_stats.  Both are library-owned and valid until the next
+ * no kept edge.  After a batch with per-frame site lists (wn_hbond_batch_subset) s and the labels are
+ * positions in that frame's list, as the edge indices are; entries past the list's length are -1.  stats[f]: see wn_component_stats.  Both are library-owned and valid until the next
  * call on this context: pinned host memory when the batch came from host frames, device memory when
  * it was a *_dev batch (like the batch result itself). */
 typedef struct wn_component_stats {

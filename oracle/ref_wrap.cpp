@@ -17,7 +17,10 @@
 
 #include <cmath>
 #include <cstdint>
+#include <chrono>
 #include <cstring>
+#include <functional>
+#include <future>
 #include <iomanip>
 #include <iostream>
 #include <string>
@@ -129,6 +132,76 @@ size_t wnref_frame_hbonds_water(const float* frame, int n_waters, wnref_edge* ou
         out[k].cosine = (float)hb[k].angle;
     }
     return hb.size();
+}
+
+/* The same frame the way analyzeFrame itself schedules it (src/waternetwork.cpp:583-633): the pair search
+ * on the calling thread, then the pair list cut into `n_chunks` contiguous ranges (the reference uses
+ * std::thread::hardware_concurrency()), one std::async(std::launch::async, make_edges, ...) per range on the
+ * shared read-only site arrays (:608-618), futures joined in order and concatenated (:621-633).  The range
+ * arithmetic is restated (even split, remainder spread over the first ranges); the reference's own has
+ * undefined behaviour for lists shorter than the thread count and the same result
+ * otherwise.  seconds[0] = find, seconds[1] = make_edges fan-out + join.  This is the reference's
+ * INTRA-frame parallel variant: one frame at a time on all cores. */
+size_t wnref_frame_hbonds_water_chunked(const float* frame, int n_waters, int n_chunks, wnref_edge* out, size_t cap,
+                                        uint64_t* n_pairs, double* seconds)
+{
+    std::vector<Point> solventPoints;
+    solventPoints.reserve(3 * (size_t)n_waters);
+    for (int i = 0; i < 3 * n_waters; ++i)
+        solventPoints.push_back(Point(frame[3 * i], frame[3 * i + 1], frame[3 * i + 2]));
+    std::vector<Point> sitePoints;
+    std::vector<std::vector<Point_ptr>> hydrogenPoints;
+    std::vector<SiteInfo_ptr> siteInfos;
+    for (int index = 0; index < n_waters; ++index) {
+        std::vector<Point_ptr> hydrogens(2);
+        for (unsigned int i = 0; i < 2; i++)
+            hydrogens.at(i) = std::make_shared<Point>(solventPoints.at(3 * index + i));
+        hydrogenPoints.push_back(hydrogens);
+        SiteInfo info;
+        info.type = WATER;
+        info.id = (unsigned)index;
+        info.atmIndex = (unsigned)(3 * index);
+        info.resIndex = (unsigned)index;
+        info.nbHydrogen = 2;
+        siteInfos.push_back(std::make_shared<SiteInfo>(info));
+        sitePoints.push_back(solventPoints.at(3 * index));
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    BruteFindPairs finder;
+    std::vector<std::pair<int, int>> pairs = finder.find(sitePoints);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (n_pairs) *n_pairs = pairs.size();
+    if (n_chunks < 1) n_chunks = 1;
+    typedef std::vector<std::pair<int, int>>::iterator It;
+    std::vector<std::future<std::vector<HydrogenBond>>> futures;
+    const size_t m = pairs.size(), base = m / (size_t)n_chunks, extra = m % (size_t)n_chunks;
+    size_t start = 0;
+    for (int k = 0; k < n_chunks; ++k) {
+        const size_t len = base + ((size_t)k < extra ? 1 : 0);
+        It b = pairs.begin() + (std::ptrdiff_t)start, e = pairs.begin() + (std::ptrdiff_t)(start + len);
+        futures.push_back(std::async(std::launch::async, [&, b, e]() mutable {
+            return make_edges(b, e, sitePoints, hydrogenPoints, siteInfos);
+        }));
+        start += len;
+    }
+    size_t count = 0;
+    for (auto& fut : futures) {
+        std::vector<HydrogenBond> hb = fut.get();
+        for (size_t k = 0; k < hb.size(); ++k, ++count) {
+            if (count >= cap) continue;
+            out[count].i = (int32_t)hb[k].sites.first->id;
+            out[count].j = (int32_t)hb[k].sites.second->id;
+            out[count].energy = (float)hb[k].energy;
+            out[count].length = (float)hb[k].length;
+            out[count].cosine = (float)hb[k].angle;
+        }
+    }
+    const auto t2 = std::chrono::steady_clock::now();
+    if (seconds) {
+        seconds[0] = std::chrono::duration<double>(t1 - t0).count();
+        seconds[1] = std::chrono::duration<double>(t2 - t1).count();
+    }
+    return count;
 }
 
 } /* extern "C" */

@@ -447,6 +447,62 @@ size_t wno_frame_hbonds_pbc(const float* frame_xyz, int natoms,
     return ne <= cap ? ne : (size_t)-1;
 }
 
+/* ---- scattered rows of one frame (test infrastructure for the large configurations) ----
+ * The pairs (i, j > i) of the listed rows only, in the order of the list (ascending rows give the
+ * reference's lexicographic order restricted to those rows), through the same pair test
+ * (src/brute-find-pairs.cpp:19-30) and the same make_edges (src/waternetwork.cpp:182-263).
+ * box == NULL: open boundary; else the rectangular periodic definition above. */
+size_t wno_frame_hbonds_rows(const float* frame_xyz, int natoms,
+                             const int32_t* site_atom, const int32_t* h_atom, int hmax,
+                             const uint8_t* site_type, int n, const int32_t* rows, int n_rows,
+                             const float* box, wno_edge* edges, size_t cap, uint64_t* n_evals)
+{
+    float* wrapped = NULL;
+    double* site_xyz = (double*)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
+    double* h_xyz = (double*)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1) * (size_t)(hmax > 0 ? hmax : 1));
+    int32_t* h_off = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1));
+    int32_t* pairs = NULL;
+    wno_edge* tmp;
+    size_t m = 0, pcap = 0, ne;
+    double L[3] = {0, 0, 0}, invL[3] = {0, 0, 0};
+    float cutoff = 6.5f;
+    int r, j, c;
+    cutoff *= cutoff;
+    if (box) {
+        for (c = 0; c < 3; ++c) { L[c] = (double)box[c]; invL[c] = 1.0 / L[c]; }
+        wrapped = (float*)malloc(sizeof(float) * 3 * (size_t)(natoms > 0 ? natoms : 1));
+        wno_wrap_frame(frame_xyz, natoms, box, wrapped);
+        frame_xyz = wrapped;
+    }
+    wno_gather_sites(frame_xyz, natoms, site_atom, h_atom, hmax, n, site_xyz, h_xyz, h_off);
+    for (r = 0; r < n_rows; ++r) {
+        const int i = rows[r];
+        if (i < 0 || i >= n) continue;
+        for (j = i + 1; j < n; ++j) {
+            v3 d = v3_sub(site_xyz + 3 * (size_t)i, site_xyz + 3 * (size_t)j);
+            if (box) { d.x = minimg(d.x, L[0], invL[0]); d.y = minimg(d.y, L[1], invL[1]); d.z = minimg(d.z, L[2], invL[2]); }
+            if (10.0 * v3_dot(d, d) < cutoff) {
+                if (m == pcap) {
+                    pcap = pcap ? 2 * pcap : 4096;
+                    pairs = (int32_t*)realloc(pairs, sizeof(int32_t) * 2 * pcap);
+                }
+                pairs[2 * m] = i; pairs[2 * m + 1] = j; ++m;
+            }
+        }
+    }
+    tmp = (wno_edge*)malloc(sizeof(wno_edge) * (m ? m : 1));
+    if (box) {
+        pbox pb_;
+        pb_.L = L; pb_.invL = invL; pb_.tric = NULL;
+        ne = make_edges_box(pairs, m, site_xyz, n, h_xyz, h_off, site_type, &pb_, tmp, n_evals, NULL);
+    } else {
+        ne = wno_make_edges(pairs, m, site_xyz, n, h_xyz, h_off, site_type, tmp, n_evals, NULL);
+    }
+    if (ne <= cap && edges) memcpy(edges, tmp, sizeof(wno_edge) * ne);
+    free(tmp); free(pairs); free(h_off); free(h_xyz); free(site_xyz); free(wrapped);
+    return ne <= cap ? ne : (size_t)-1;
+}
+
 /* ======================= triclinic boxes (definition: include/wn_b200.h) ======================= */
 
 static void tric_unpack(const float box9[9], double t[6])

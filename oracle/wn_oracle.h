@@ -126,6 +126,14 @@ size_t wno_frame_hbonds_pbc(const float* frame_xyz, int natoms,
                             wno_edge* edges, size_t cap, double* stats,
                             uint64_t* n_pairs, uint64_t* n_evals, wno_ties* ties);
 
+/* Scattered rows of one frame: the edges (i, j > i) of the listed rows only, in list order
+ * (test infrastructure for the 100k- and 1M-atom configurations, where a whole frame costs the
+ * oracle seconds to minutes).  box == NULL: open boundary (the reference); else rectangular PBC. */
+size_t wno_frame_hbonds_rows(const float* frame_xyz, int natoms,
+                             const int32_t* site_atom, const int32_t* h_atom, int hmax,
+                             const uint8_t* site_type, int n, const int32_t* rows, int n_rows,
+                             const float* box, wno_edge* edges, size_t cap, uint64_t* n_evals);
+
 /* ---- triclinic boxes (GROMACS convention: box9 = rows a=(ax,0,0), b=(bx,by,0), c=(cx,cy,cz)).
  * Definition in include/wn_b200.h ("Periodic boundaries", triclinic part), restated here:
  *   wrap:     fz = floor(z/cz): (x,y,z) -= fz*c;  fy = floor(y/by): (x,y) -= fy*(bx,by);

@@ -287,6 +287,110 @@ def test_full_size_100k_atoms_properties(ctx, oracle):
     ctx.dev_free(d)
 
 
+def test_full_size_100k_atoms_whole_frames_vs_oracle(ctx, oracle):
+    """configs[2] at full size, the configuration the bench numbers are quoted on: EVERY edge of whole
+    frames against the oracle (reference src/brute-find-pairs.cpp:19-30 + src/waternetwork.cpp:182-263),
+    open boundary and rectangular PBC -- bit-exact (i, j, length, cosine), energy <= 1e-6 relative, the
+    statistics row and the pair-evaluation count.  The oracle needs ~3 s (open) / ~7 s (periodic) per frame."""
+    n, nf = 33333, 2
+    d = ctx.dev_alloc(nf * 3 * n * 12)
+    ctx.synth_frames_dev(n, 4242, nf, d)
+    frames = np.empty((nf, 3 * n, 3), np.float32)
+    ctx.d2h(frames, d)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    L = np.float32(oracle.synth_box(n).box)
+    # open boundary: two whole frames (device-resident batch, as the bench's timed leg runs it)
+    out = ctx.hbond_batch_dev(d, nf, 3 * n)
+    e, fo, st = ctx.fetch_dev_result(out)
+    evals = 0
+    for f in range(nf):
+        want, stats, npairs, ev = oracle.frame_hbonds(frames[f], sa, ha, ty)
+        assert len(want) > 390000 and npairs > 15000000
+        check_edges(e[int(fo[f]):int(fo[f + 1])], want)
+        assert st["num_sites"][f] == stats[0] and st["num_edges"][f] == stats[1] and st["ratio"][f] == stats[2]
+        assert np.isclose(st["sum_energy"][f], stats[3], rtol=ENERGY_RTOL, atol=0)
+        assert int(st["pair_evals"][f]) == ev
+        evals += ev
+    assert out["n_pair_evals"] == evals
+    # rectangular PBC: one whole frame through the host entry point in the compact layout
+    boxes = np.full((1, 3), L, np.float32)
+    res = ctx.hbond_batch_ex(frames[:1], boxes=boxes, layout=1)
+    want, stats, _, ev = oracle.frame_hbonds_pbc(frames[0], sa, ha, ty, boxes[0])
+    assert len(want) > 420000
+    got = np.zeros(res["n_edges"], want.dtype)
+    ro = res["row_offsets"][0].astype(np.int64)
+    cnt = np.diff(np.append(ro, res["n_edges"]))
+    got["i"] = np.repeat(np.arange(n, dtype=np.int32), cnt)
+    for k in ("j", "energy", "length", "cosine"):
+        got[k] = res["edges"][k]
+    check_edges(got, want)
+    assert int(res["stats"]["pair_evals"][0]) == ev and res["stats"]["num_edges"][0] == stats[1]
+    ctx.dev_free(d)
+
+
+def test_energy_known_answers_through_the_batch(ctx, oracle):
+    """Known-answer test of computeEnergy (reference src/waternetwork.cpp:49-66) on the GPU: two-water frames
+    whose edge has exactly the (r, cos) of a grid point of tests/golden/energy_kat.npz (values from the
+    reference's own sources) go through wn_hbond_batch; the returned energy must be the golden one
+    (float-rounded as make_edges stores it, :222) within 1e-6 relative, with the sign of zero."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "energy_kat.npz"))
+    sa, ha, ty = oracle.water_site_table(2)
+
+    def frame_for(x, hx, hy):
+        fr = np.zeros((6, 3), np.float32)
+        fr[1] = (hx, hy, 0.0)                      # H1 of water A (site A at the origin)
+        fr[2] = (0.0, 0.0, 0.08)
+        fr[3] = (x, 0.0, 0.0)                      # water B on the x axis
+        fr[4] = (np.float32(x) - np.float32(0.1), 0.0, 0.0)     # its H1 points at A: cosine -1, never selected
+        fr[5] = (x, 0.0, 0.08)
+        return fr
+
+    def ulps(v, k):
+        return np.float32(v).view(np.int32).__add__(k).view(np.float32) if k else np.float32(v)
+
+    frames, wants = [], []
+    for a, r in enumerate(g["r"]):
+        rf = np.float32(r)
+        if float(rf) != float(r) or rf > np.float32(6.5):
+            continue
+        for b, c in enumerate(g["cos"]):
+            cf = np.float32(c)
+            if not (c > 0) or float(cf) != float(c):
+                continue
+            hit = None
+            for kx in range(-3, 4):
+                x = ulps(np.float32(float(rf) / 10.0), kx)
+                if np.float32(np.float64(x) * 10.0) != rf:
+                    continue
+                hx = np.float32(-float(cf) * 0.1)
+                hy0 = np.float32(np.sqrt(max(0.01 - float(hx) ** 2, 0.0)))
+                for ky in range(-40, 41):
+                    hy = ulps(hy0, ky) if hy0 > 0 else np.float32(0.0)
+                    fr = frame_for(x, hx, hy)
+                    e, _, _, _ = oracle.frame_hbonds(fr, sa, ha, ty)
+                    if len(e) == 1 and e["length"][0] == rf and e["cosine"][0] == cf:
+                        hit = (fr, e[0])
+                        break
+                if hit:
+                    break
+            if hit:
+                golden = np.float32(g["energy"][a, b])
+                assert hit[1]["energy"].view(np.uint32) == golden.view(np.uint32)     # oracle == reference value
+                frames.append(hit[0]); wants.append((rf, cf, golden))
+    assert len(frames) >= 40, len(frames)            # 13 radii x 4 cosines are float-representable
+    ctx.set_water_sites(2)
+    res = ctx.hbond_batch(np.stack(frames))
+    assert res["n_edges"] == len(frames) and np.all(np.diff(res["frame_offsets"]) == 1)
+    for k, (rf, cf, golden) in enumerate(wants):
+        ed = res["edges"][k]
+        assert ed["i"] == 0 and ed["j"] == 1 and ed["length"] == rf and ed["cosine"] == cf
+        assert abs(float(ed["energy"]) - float(golden)) <= ENERGY_RTOL * abs(float(golden)), (rf, cf, ed["energy"], golden)
+        if golden == 0:
+            assert np.signbit(ed["energy"]) == np.signbit(golden)
+
+
 def test_find_pairs_full_size_rows(ctx, oracle):
     """CudaFindPairs at 33,333 sites: total count, order, and exact rows vs the oracle."""
     n = 33333
@@ -489,6 +593,13 @@ def test_one_million_atoms_rows_and_properties(ctx, oracle):
             else:
                 want, _, _, _ = oracle.frame_hbonds_pbc(frames[f], sa, ha, ty, boxes[f], first_limit=40)
             check_edges(ef[ef["i"] < 40], want)
+            # 2,000+ rows scattered over the whole box (every region of the 33^3-cell grid, not one corner),
+            # plus the last rows: every edge of those rows, bit-exact, none missing, none extra
+            rows = np.unique(np.concatenate([np.random.default_rng(100 + f).integers(0, n, 2200),
+                                             np.arange(n - 30, n)])).astype(np.int32)
+            want_r, _ = oracle.frame_hbonds_rows(frames[f], sa, ha, ty, rows, box=None if boxes is None else boxes[f])
+            assert len(want_r) > 20000
+            check_edges(ef[np.isin(ef["i"], rows)], want_r)
     ctx.dev_free(d)
 
 
@@ -543,8 +654,26 @@ def test_per_frame_site_subsets(ctx, oracle):
             check_edges(res["edges"][int(fo[f]):int(fo[f + 1])], want)
             assert res["stats"]["num_sites"][f] == len(lst) and res["stats"]["num_edges"][f] == len(want)
             assert int(res["stats"]["pair_evals"][f]) == ev
+    # consumers of the last batch after per-frame site lists: indices are list positions.  The device formatter
+    # refuses an id table (it would print the ids of the wrong rows); components are labelled by list position.
+    res = ctx.hbond_batch_subset(frames, off, sites)
+    import wn_pkg
+    with pytest.raises(wn_pkg.load_capi().WnError) as ei:
+        ctx.format_edges(list(range(nf)), (np.arange(n_p + n_w) + 1).astype(np.uint32))
+    assert ei.value.code == 3
+    text = ctx.format_edges(list(range(nf)))                      # no id table: the list positions themselves
+    assert text.count(b"\n") == nf + res["n_edges"]
+    labels, cst = ctx.components(0.0)
+    fo = res["frame_offsets"]
+    for f in range(nf):
+        lab, stc = oracle.components(res["edges"][int(fo[f]):int(fo[f + 1])], len(lists[f]), 0.0)
+        assert np.array_equal(labels[f][:len(lists[f])], lab) and np.all(labels[f][len(lists[f]):] == -1)
+        assert int(cst["n_components"][f]) == int(stc[0])
     with pytest.raises(Exception):
         ctx.hbond_batch_subset(frames, [0, 1, 2, 3, 4, 5, 6], np.array([0, 1, 2, 3, 4, n_p + n_w], np.int32))
+    # a negative first_limit means "every row", as in the C++ wrappers
+    ctx.set_sites(site_atom, h_atom, site_type, first_limit=-1)
+    assert ctx.hbond_batch(frames[:1])["n_edges"] > 0
 
 
 def test_gpu_text_formatter_matches_printf(ctx, oracle, capi):

@@ -117,6 +117,10 @@ def ref():
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         R.wnref_frame_hbonds_water.restype = C.c_size_t
         R.wnref_frame_hbonds_water.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        if hasattr(R, "wnref_frame_hbonds_water_chunked"):
+            R.wnref_frame_hbonds_water_chunked.restype = C.c_size_t
+            R.wnref_frame_hbonds_water_chunked.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                                           C.c_void_p, C.c_void_p]
         _ref = R
     return _ref
 
@@ -201,6 +205,35 @@ def frame_hbonds(frame, site_atom, h_atom, site_type, first_limit=None, ties=Non
     return edges[:ne].copy(), stats, int(npairs.value), int(nevals.value)
 
 
+def frame_hbonds_rows(frame, site_atom, h_atom, site_type, rows, box=None, cap=None):
+    """Edges (i, j > i) of the listed rows of one frame, in list order; box=None: open boundary,
+    else rectangular PBC (Lx, Ly, Lz).  Returns (edges, n_pair_evals)."""
+    frame = np.ascontiguousarray(frame, dtype=np.float32).reshape(-1, 3)
+    site_atom = np.ascontiguousarray(site_atom, dtype=np.int32)
+    n = len(site_atom)
+    h_atom = np.ascontiguousarray(h_atom, dtype=np.int32).reshape(n, -1) if n else np.zeros((0, 1), np.int32)
+    hmax = h_atom.shape[1]
+    site_type = np.ascontiguousarray(site_type, dtype=np.uint8)
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    bptr = None
+    if box is not None:
+        box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
+        bptr = box.ctypes.data
+    if cap is None:
+        cap = 256 * max(len(rows), 1) + 1024
+    edges = np.empty(cap, dtype=EDGE_DTYPE)
+    nevals = C.c_uint64(0)
+    fn = lib().wno_frame_hbonds_rows
+    fn.restype = C.c_size_t
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                   C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    ne = fn(frame.ctypes.data, frame.shape[0], site_atom.ctypes.data, h_atom.ctypes.data, hmax,
+            site_type.ctypes.data, n, rows.ctypes.data, len(rows), bptr, edges.ctypes.data, cap, C.byref(nevals))
+    if ne == C.c_size_t(-1).value:
+        raise RuntimeError("oracle edge capacity overflow")
+    return edges[:ne].copy(), int(nevals.value)
+
+
 def components(edges, n_sites, threshold=0.0):
     """Connected components of one frame's edge list: (labels[n_sites], stats[4])."""
     edges = np.ascontiguousarray(edges, dtype=EDGE_DTYPE)
@@ -264,6 +297,24 @@ def ref_frame_hbonds_water(frame, cap=None):
     if ne > cap:
         raise RuntimeError("reference edge capacity overflow")
     return out[:ne].copy(), int(npairs.value)
+
+
+def ref_frame_hbonds_water_chunked(frame, n_chunks, cap=None):
+    """The reference's intra-frame schedule (src/waternetwork.cpp:583-633): single-threaded find, then
+    n_chunks std::async(make_edges) ranges joined in order.  Returns (edges, n_pairs, (find_s, edges_s))."""
+    R = ref()
+    frame = np.ascontiguousarray(frame, dtype=np.float32).reshape(-1, 3)
+    n = frame.shape[0] // 3
+    if cap is None:
+        cap = 64 * max(n, 1)
+    out = np.empty(cap, dtype=EDGE_DTYPE)
+    npairs = C.c_uint64(0)
+    secs = (C.c_double * 2)()
+    ne = R.wnref_frame_hbonds_water_chunked(frame.ctypes.data, n, int(n_chunks), out.ctypes.data, cap,
+                                            C.byref(npairs), secs)
+    if ne > cap:
+        raise RuntimeError("reference edge capacity overflow")
+    return out[:ne].copy(), int(npairs.value), (secs[0], secs[1])
 
 
 # ------------------------------------------------------------------ periodic mode
