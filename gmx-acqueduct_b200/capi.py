@@ -22,8 +22,9 @@ MODEL_TIP3P, MODEL_SPC = 0, 1
 EDGE_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("energy", "<f4"),
                        ("length", "<f4"), ("cosine", "<f4")])
 EDGE16_DTYPE = np.dtype([("j", "<i4"), ("energy", "<f4"), ("length", "<f4"), ("cosine", "<f4")])
+EDGE12_DTYPE = np.dtype([("j", "<i4"), ("length", "<f4"), ("cosine", "<f4")])
 COMPONENT_DTYPE = np.dtype([("n_components", "<i4"), ("largest", "<i4"), ("n_nodes", "<i4"), ("n_edges", "<i4")])
-LAYOUT_EDGES, LAYOUT_CSR16 = 0, 1
+LAYOUT_EDGES, LAYOUT_CSR16, LAYOUT_CSR12 = 0, 1, 2
 STATS_DTYPE = np.dtype([("num_sites", "<f8"), ("num_edges", "<f8"), ("ratio", "<f8"),
                         ("sum_energy", "<f8"), ("pair_evals", "<f8")])
 assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
@@ -35,6 +36,7 @@ SYMBOLS = [
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
+    "wn_device_count", "wn_set_result_sets", "wn_bind_thread_to_device", "wn_pcie_probe",
     "wn_get_timings", "wn_selftest_div", "wn_timer_start", "wn_timer_stop", "wn_nccl_unique_id", "wn_nccl_init", "wn_stats_reduce",
 ]
 
@@ -113,6 +115,10 @@ def load():
     L.wn_hbond_batch.argtypes = [vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_hbond_batch_dev.argtypes = [vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_set_batch_frames.argtypes = [vp, i32]
+    L.wn_device_count.argtypes = []
+    L.wn_set_result_sets.argtypes = [vp, i32]
+    L.wn_bind_thread_to_device.argtypes = [vp, C.POINTER(i32)]
+    L.wn_pcie_probe.argtypes = [vp, C.c_size_t, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.wn_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.wn_dev_free.argtypes = [vp, vp]
     L.wn_host_alloc_pinned.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -208,6 +214,20 @@ class Context:
     def set_batch_frames(self, n):
         self._ck(self.L.wn_set_batch_frames(self.h, int(n)))
 
+    def set_result_sets(self, n):
+        self._ck(self.L.wn_set_result_sets(self.h, int(n)))
+
+    def bind_thread_to_device(self):
+        n = C.c_int32()
+        self._ck(self.L.wn_bind_thread_to_device(self.h, C.byref(n)))
+        return int(n.value)
+
+    def pcie_probe(self, nbytes=256 << 20, repeats=4):
+        """(h2d GB/s, d2h GB/s) of plain pinned copies on this context's GPU."""
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.wn_pcie_probe(self.h, int(nbytes), int(repeats), C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     # ---- batches
     def _wrap(self, res, copy=True):
         nf, ne = res.n_frames, int(res.n_edges)
@@ -217,7 +237,7 @@ class Context:
         out["n_sites"] = res.n_sites
         out["layout"] = res.layout
         self._last_frames, self._last_on_device = nf, bool(res.on_device)
-        edt = EDGE16_DTYPE if res.layout == LAYOUT_CSR16 else EDGE_DTYPE
+        edt = EDGE16_DTYPE if res.layout == LAYOUT_CSR16 else EDGE12_DTYPE if res.layout == LAYOUT_CSR12 else EDGE_DTYPE
         if res.on_device:
             out["edges_dev"] = res.edges
             out["frame_offsets_dev"] = res.frame_offsets
@@ -316,7 +336,8 @@ class Context:
     def fetch_dev_result(self, out):
         """Copy a device-resident batch result to numpy arrays."""
         nf, ne = out["n_frames"], out["n_edges"]
-        e = np.zeros(ne, EDGE16_DTYPE if out.get("layout") == LAYOUT_CSR16 else EDGE_DTYPE)
+        e = np.zeros(ne, EDGE16_DTYPE if out.get("layout") == LAYOUT_CSR16 else
+                     EDGE12_DTYPE if out.get("layout") == LAYOUT_CSR12 else EDGE_DTYPE)
         fo = np.zeros(nf + 1, np.uint64)
         st = np.zeros(nf, STATS_DTYPE)
         if ne:

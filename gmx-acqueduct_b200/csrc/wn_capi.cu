@@ -12,6 +12,8 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sched.h>
+#include <ctype.h>
 
 #include <algorithm>
 #include <cmath>
@@ -48,8 +50,6 @@ struct wn_ctx {
     uint32_t* d_row_cnt = nullptr;
     uint32_t* d_row_off = nullptr;          /* call-wide [n_frames][n_sites] (CSR row offsets) */
     size_t row_off_cap = 0;
-    uint32_t* h_row_off = nullptr;
-    size_t h_row_off_cap = 0;
     unsigned long long* d_frame_total = nullptr;
     WnFrameCounters* d_counters = nullptr;
     uint32_t* d_frame_maxrow = nullptr;
@@ -74,13 +74,22 @@ struct wn_ctx {
     WnFrameCounters* d_counters_all = nullptr;
     size_t out_frames_cap = 0;
 
-    /* call-wide outputs (pinned host) */
-    wn_edge* h_edges = nullptr;
-    size_t h_edges_cap = 0;
-    uint64_t* h_frame_off = nullptr;
-    wn_frame_stats* h_stats = nullptr;
-    WnFrameCounters* h_counters = nullptr;
-    size_t h_frames_cap = 0;
+    /* call-wide outputs (pinned host).  Two sets: with wn_set_result_sets(ctx, 2) consecutive batch calls
+     * alternate between them, so the result of call k stays valid while call k+1 runs (a caller can hand
+     * batch k to its sink while the GPU works on batch k+1: FrameBatcher does). */
+    struct HostSet {
+        wn_edge* edges = nullptr;
+        size_t edges_cap = 0;
+        uint64_t* frame_off = nullptr;
+        wn_frame_stats* stats = nullptr;
+        WnFrameCounters* counters = nullptr;
+        size_t frames_cap = 0;
+        uint32_t* row_off = nullptr;
+        size_t row_off_cap = 0;
+    } hset[2];
+    int n_sets = 1, cur = 0;
+    float* d_eside = nullptr;                  /* WN_LAYOUT_CSR12: energies of the pass in final order (for the sum) */
+    size_t eside_cap = 0;
     unsigned long long* h_scalars = nullptr;   /* pinned scratch for small D2H reads */
 
     /* text formatting of the last batch */
@@ -250,7 +259,7 @@ int ensure_out_frames(wn_ctx* ctx, size_t n_frames, bool host)
         const size_t need = n_frames * (size_t)std::max(ctx->n_sites, 0) + 1;
         int rc0;
         if ((rc0 = dev_ensure(ctx, &ctx->d_row_off, &ctx->row_off_cap, need))) return rc0;
-        if (host && (rc0 = host_ensure(ctx, &ctx->h_row_off, &ctx->h_row_off_cap, need))) return rc0;
+        if (host && (rc0 = host_ensure(ctx, &ctx->hset[ctx->cur].row_off, &ctx->hset[ctx->cur].row_off_cap, need))) return rc0;
     }
     if (n_frames + 1 > ctx->out_frames_cap || !ctx->d_frame_off) {
         const size_t cap = n_frames + 1;
@@ -262,16 +271,16 @@ int ensure_out_frames(wn_ctx* ctx, size_t n_frames, bool host)
         ctx->out_frames_cap = cap;
     }
     /* the small per-frame tables (offsets, statistics, counters) come back to the host for every batch */
-    if (n_frames + 1 > ctx->h_frames_cap || !ctx->h_frame_off) {
+    if (n_frames + 1 > ctx->hset[ctx->cur].frames_cap || !ctx->hset[ctx->cur].frame_off) {
         const size_t cap = n_frames + 1;
-        if (ctx->h_frame_off) WN_CK(cudaFreeHost(ctx->h_frame_off));
-        if (ctx->h_stats) WN_CK(cudaFreeHost(ctx->h_stats));
-        if (ctx->h_counters) WN_CK(cudaFreeHost(ctx->h_counters));
-        ctx->h_frame_off = nullptr; ctx->h_stats = nullptr; ctx->h_counters = nullptr;
-        WN_CK(cudaMallocHost((void**)&ctx->h_frame_off, cap * sizeof(uint64_t)));
-        WN_CK(cudaMallocHost((void**)&ctx->h_stats, cap * sizeof(wn_frame_stats)));
-        WN_CK(cudaMallocHost((void**)&ctx->h_counters, cap * sizeof(WnFrameCounters)));
-        ctx->h_frames_cap = cap;
+        if (ctx->hset[ctx->cur].frame_off) WN_CK(cudaFreeHost(ctx->hset[ctx->cur].frame_off));
+        if (ctx->hset[ctx->cur].stats) WN_CK(cudaFreeHost(ctx->hset[ctx->cur].stats));
+        if (ctx->hset[ctx->cur].counters) WN_CK(cudaFreeHost(ctx->hset[ctx->cur].counters));
+        ctx->hset[ctx->cur].frame_off = nullptr; ctx->hset[ctx->cur].stats = nullptr; ctx->hset[ctx->cur].counters = nullptr;
+        WN_CK(cudaMallocHost((void**)&ctx->hset[ctx->cur].frame_off, cap * sizeof(uint64_t)));
+        WN_CK(cudaMallocHost((void**)&ctx->hset[ctx->cur].stats, cap * sizeof(wn_frame_stats)));
+        WN_CK(cudaMallocHost((void**)&ctx->hset[ctx->cur].counters, cap * sizeof(WnFrameCounters)));
+        ctx->hset[ctx->cur].frames_cap = cap;
     }
     return WN_OK;
 }
@@ -399,9 +408,12 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, want, true, (size_t)*edge_base))) return rc;
     }
 
+    if (ctx->layout == WN_LAYOUT_CSR12) {
+        if ((rc = dev_ensure(ctx, &ctx->d_eside, &ctx->eside_cap, ctx->edges_cap))) return rc;
+    }
     int n_blocks = 0;
     wn_launch_copy(ctx->d_rowbuf, ctx->row_cap, ctx->d_row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0,
-                   nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->layout, ctx->d_block_sums, &n_blocks, st);
+                   nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->layout, ctx->d_eside, ctx->d_block_sums, &n_blocks, st);
     wn_launch_stats(ctx->d_block_sums, n_blocks, ctx->d_frame_total, ctx->d_counters, nf, N, sub,
                     ctx->d_stats + f0, st);
     WN_CK(cudaMemcpyAsync(ctx->d_counters_all + f0, ctx->d_counters, (size_t)nf * sizeof(WnFrameCounters),
@@ -434,6 +446,7 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     ctx->err.clear();
     ctx->tm = wn_timings{};
     memset(out, 0, sizeof *out);
+    if (ctx->n_sets == 2) ctx->cur ^= 1;          /* the previous call's host results stay untouched */
     int rc;
     /* results go where the frames came from, unless the caller keeps them on the device (results_on_device) */
     const bool host_out = host_in && !ctx->keep_dev;
@@ -443,19 +456,19 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     unsigned long long edge_base = 0;
     if (N == 0 || n_frames == 0) {
         /* nothing to search: empty edge lists, zero rows */
-        for (int f = 0; f <= n_frames; ++f) ctx->h_frame_off[f] = 0;
-        for (int f = 0; f < n_frames; ++f) ctx->h_stats[f] = wn_frame_stats{0, 0, 0, 0, 0};
+        for (int f = 0; f <= n_frames; ++f) ctx->hset[ctx->cur].frame_off[f] = 0;
+        for (int f = 0; f < n_frames; ++f) ctx->hset[ctx->cur].stats[f] = wn_frame_stats{0, 0, 0, 0, 0};
         if (!host_out && n_frames > 0) {
             WN_CK(cudaMemsetAsync(ctx->d_frame_off, 0, (size_t)(n_frames + 1) * sizeof(unsigned long long), ctx->st));
             WN_CK(cudaMemsetAsync(ctx->d_stats, 0, (size_t)n_frames * sizeof(wn_frame_stats), ctx->st));
             WN_CK(cudaStreamSynchronize(ctx->st));
         }
-        out->edges = host_out ? ctx->h_edges : ctx->d_edges;
-        out->frame_offsets = host_out ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
-        out->stats = host_out ? ctx->h_stats : ctx->d_stats;
+        out->edges = host_out ? ctx->hset[ctx->cur].edges : ctx->d_edges;
+        out->frame_offsets = host_out ? ctx->hset[ctx->cur].frame_off : (const uint64_t*)ctx->d_frame_off;
+        out->stats = host_out ? ctx->hset[ctx->cur].stats : ctx->d_stats;
         out->n_frames = n_frames;
         out->on_device = host_out ? 0 : 1;
-        out->row_offsets = host_out ? ctx->h_row_off : ctx->d_row_off;
+        out->row_offsets = host_out ? ctx->hset[ctx->cur].row_off : ctx->d_row_off;
         out->n_sites = N;
         out->layout = ctx->layout;
         return WN_OK;
@@ -501,25 +514,26 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
             const unsigned long long before = edge_base;
             if ((rc = run_pass(ctx, ctx->d_stage[k & 1], boxes ? boxes + ctx->box_stride * (size_t)f0 : nullptr, nf, natoms,
                                (size_t)f0, &edge_base))) return rc;
-            if (host_out && (size_t)edge_base > ctx->h_edges_cap) {
+            if (host_out && (size_t)edge_base > ctx->hset[ctx->cur].edges_cap) {
                 /* project the whole call from the density seen so far */
                 const double per_frame = (double)edge_base / (double)(f0 + nf);
                 const size_t want = (size_t)(per_frame * n_frames * 1.05) + 1024;
-                if ((rc = host_ensure(ctx, &ctx->h_edges, &ctx->h_edges_cap, std::max(want, (size_t)edge_base), true,
+                if ((rc = host_ensure(ctx, &ctx->hset[ctx->cur].edges, &ctx->hset[ctx->cur].edges_cap, std::max(want, (size_t)edge_base), true,
                                       (size_t)before))) return rc;
             }
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 2], ctx->st_d2h));
             if (host_out && edge_base > before)
             {
                 /* 20-byte wn_edge records, or 16-byte wn_edge16 records in the same buffers */
-                const size_t esz = ctx->layout == WN_LAYOUT_CSR16 ? sizeof(wn_edge16) : sizeof(wn_edge);
-                WN_CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_edges) + (size_t)before * esz,
+                const size_t esz = ctx->layout == WN_LAYOUT_CSR16 ? sizeof(wn_edge16)
+                                 : ctx->layout == WN_LAYOUT_CSR12 ? sizeof(wn_edge12) : sizeof(wn_edge);
+                WN_CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->hset[ctx->cur].edges) + (size_t)before * esz,
                                       reinterpret_cast<const char*>(ctx->d_edges) + (size_t)before * esz,
                                       (size_t)(edge_base - before) * esz, cudaMemcpyDeviceToHost, ctx->st_d2h));
             }
             /* the row offsets of the pass travel with its edges */
             if (host_out && N > 0)
-                WN_CK(cudaMemcpyAsync(ctx->h_row_off + (size_t)f0 * N, ctx->d_row_off + (size_t)f0 * N,
+                WN_CK(cudaMemcpyAsync(ctx->hset[ctx->cur].row_off + (size_t)f0 * N, ctx->d_row_off + (size_t)f0 * N,
                                       (size_t)nf * N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 3], ctx->st_d2h));
         }
@@ -537,32 +551,32 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
         }
     }
     /* small per-frame tables always come back to the host: totals and ties */
-    WN_CK(cudaMemcpyAsync(ctx->h_frame_off, ctx->d_frame_off, (size_t)(n_frames + 1) * sizeof(uint64_t),
+    WN_CK(cudaMemcpyAsync(ctx->hset[ctx->cur].frame_off, ctx->d_frame_off, (size_t)(n_frames + 1) * sizeof(uint64_t),
                           cudaMemcpyDeviceToHost, ctx->st));
-    WN_CK(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, (size_t)n_frames * sizeof(wn_frame_stats),
+    WN_CK(cudaMemcpyAsync(ctx->hset[ctx->cur].stats, ctx->d_stats, (size_t)n_frames * sizeof(wn_frame_stats),
                           cudaMemcpyDeviceToHost, ctx->st));
-    WN_CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters_all, (size_t)n_frames * sizeof(WnFrameCounters),
+    WN_CK(cudaMemcpyAsync(ctx->hset[ctx->cur].counters, ctx->d_counters_all, (size_t)n_frames * sizeof(WnFrameCounters),
                           cudaMemcpyDeviceToHost, ctx->st));
     WN_CK(cudaStreamSynchronize(ctx->st));
-    if (ctx->h_frame_off[n_frames] != edge_base)
+    if (ctx->hset[ctx->cur].frame_off[n_frames] != edge_base)
         return fail(ctx, WN_ERR_CUDA, "internal: edge totals disagree between scan and fused kernel");
     wn_tie_report ties = {0, 0, 0, 0, 0};
     unsigned long long evals = 0, tests = 0;
     for (int f = 0; f < n_frames; ++f) {
-        evals += ctx->h_counters[f].evals;
-        tests += ctx->h_counters[f].tests;
-        ties.length_equal_cut += ctx->h_counters[f].tie_len;
-        ties.cosine_argmax_equal += ctx->h_counters[f].tie_cos;
-        ties.pos_zero += ctx->h_counters[f].tie_pos0;
+        evals += ctx->hset[ctx->cur].counters[f].evals;
+        tests += ctx->hset[ctx->cur].counters[f].tests;
+        ties.length_equal_cut += ctx->hset[ctx->cur].counters[f].tie_len;
+        ties.cosine_argmax_equal += ctx->hset[ctx->cur].counters[f].tie_cos;
+        ties.pos_zero += ctx->hset[ctx->cur].counters[f].tie_pos0;
     }
-    out->edges = host_out ? ctx->h_edges : ctx->d_edges;
-    out->frame_offsets = host_out ? ctx->h_frame_off : (const uint64_t*)ctx->d_frame_off;
-    out->stats = host_out ? ctx->h_stats : ctx->d_stats;
+    out->edges = host_out ? ctx->hset[ctx->cur].edges : ctx->d_edges;
+    out->frame_offsets = host_out ? ctx->hset[ctx->cur].frame_off : (const uint64_t*)ctx->d_frame_off;
+    out->stats = host_out ? ctx->hset[ctx->cur].stats : ctx->d_stats;
     ctx->last_frames = n_frames;
     ctx->last_edges = edge_base;
     ctx->last_on_device = host_out ? 0 : 1;
     ctx->last_subset = ctx->sub_off_host ? 1 : 0;
-    out->row_offsets = host_out ? ctx->h_row_off : ctx->d_row_off;
+    out->row_offsets = host_out ? ctx->hset[ctx->cur].row_off : ctx->d_row_off;
     out->n_sites = N;
     out->layout = ctx->layout;
     out->n_edges = edge_base;
@@ -578,7 +592,14 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
 
 extern "C" {
 
-const char* wn_version(void) { return "wn_b200 0.1 sm_100a"; }
+const char* wn_version(void) { return "wn_b200 0.2 sm_100a"; }
+
+int wn_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
 
 int wn_create(int device, wn_ctx** out)
 {
@@ -639,10 +660,11 @@ void wn_destroy(wn_ctx* ctx)
                    ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce,
                    ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags,
-                   ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx, ctx->d_cc_kept, ctx->d_cc_stats};
+                   ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx, ctx->d_cc_kept, ctx->d_cc_stats, ctx->d_eside};
     for (void* p : dev) if (p) cudaFree(p);
-    void* host[] = {ctx->h_edges, ctx->h_frame_off, ctx->h_stats, ctx->h_counters, ctx->h_scalars, ctx->h_pairs, ctx->h_row_off,
-                    ctx->h_text, ctx->h_cc_labels, ctx->h_cc_stats};
+    void* host[] = {ctx->hset[0].edges, ctx->hset[0].frame_off, ctx->hset[0].stats, ctx->hset[0].counters, ctx->hset[0].row_off,
+                    ctx->hset[1].edges, ctx->hset[1].frame_off, ctx->hset[1].stats, ctx->hset[1].counters, ctx->hset[1].row_off,
+                    ctx->h_scalars, ctx->h_pairs, ctx->h_text, ctx->h_cc_labels, ctx->h_cc_stats};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
@@ -745,6 +767,86 @@ int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass)
     return WN_OK;
 }
 
+int wn_set_result_sets(wn_ctx* ctx, int32_t n_sets)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (n_sets != 1 && n_sets != 2) return fail(ctx, WN_ERR_BAD_ARG, "wn_set_result_sets: 1 or 2");
+    ctx->n_sets = n_sets;
+    if (n_sets == 1) ctx->cur = 0;
+    return WN_OK;
+}
+
+/* CPUs next to the device, from sysfs (the PCI device's local_cpulist); empty when the platform does not say */
+static int local_cpus_of_device(int device, cpu_set_t* set)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (char* c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* fh = fopen(path.c_str(), "r");
+    if (!fh) return 0;
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof line, fh) != nullptr;
+    fclose(fh);
+    if (!got) return 0;
+    CPU_ZERO(set);
+    int n = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k < 1) continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, set); ++n; }
+    }
+    return n;
+}
+
+int wn_bind_thread_to_device(wn_ctx* ctx, int32_t* n_cpus)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (n_cpus) *n_cpus = 0;
+    cpu_set_t want, have, both;
+    const int n = local_cpus_of_device(ctx->device, &want);
+    if (n <= 0) return WN_OK;                              /* the platform does not expose the locality: nothing to do */
+    if (sched_getaffinity(0, sizeof have, &have) != 0) return WN_OK;
+    CPU_AND(&both, &want, &have);
+    const int k = CPU_COUNT(&both);
+    if (k <= 0 || k == CPU_COUNT(&have)) { if (n_cpus) *n_cpus = k == CPU_COUNT(&have) ? k : 0; return WN_OK; }
+    if (sched_setaffinity(0, sizeof both, &both) != 0) return WN_OK;
+    if (n_cpus) *n_cpus = k;
+    return WN_OK;
+}
+
+int wn_pcie_probe(wn_ctx* ctx, size_t bytes, int32_t repeats, double* h2d_gbs, double* d2h_gbs)
+{
+    if (!ctx || bytes == 0 || repeats < 1) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    void *h = nullptr, *d = nullptr;
+    WN_CK(cudaMallocHost(&h, bytes));
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) { cudaFreeHost(h); return cuda_fail(ctx, e, "cudaMalloc (wn_pcie_probe)"); }
+    memset(h, 1, bytes);
+    float ms_in = 0.f, ms_out = 0.f;
+    cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->st_h2d);           /* warm-up */
+    cudaStreamSynchronize(ctx->st_h2d);
+    cudaEventRecord(ctx->ev[4], ctx->st_h2d);
+    for (int r = 0; r < repeats; ++r) cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->st_h2d);
+    cudaEventRecord(ctx->ev[5], ctx->st_h2d);
+    cudaEventSynchronize(ctx->ev[5]);
+    cudaEventElapsedTime(&ms_in, ctx->ev[4], ctx->ev[5]);
+    cudaEventRecord(ctx->ev[4], ctx->st_d2h);
+    for (int r = 0; r < repeats; ++r) cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->st_d2h);
+    cudaEventRecord(ctx->ev[5], ctx->st_d2h);
+    cudaEventSynchronize(ctx->ev[5]);
+    cudaEventElapsedTime(&ms_out, ctx->ev[4], ctx->ev[5]);
+    e = cudaGetLastError();
+    cudaFree(d); cudaFreeHost(h);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "wn_pcie_probe");
+    if (h2d_gbs) *h2d_gbs = (double)bytes * repeats / (ms_in * 1e-3) / 1e9;
+    if (d2h_gbs) *d2h_gbs = (double)bytes * repeats / (ms_out * 1e-3) / 1e9;
+    return WN_OK;
+}
+
 int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* a, wn_batch_result* out)
 {
     if (!ctx) return WN_ERR_BAD_ARG;
@@ -787,7 +889,7 @@ int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* a, wn_batch_result* out)
             stride = 3;
         }
     }
-    if (a->result_layout != WN_LAYOUT_EDGES && a->result_layout != WN_LAYOUT_CSR16)
+    if (a->result_layout != WN_LAYOUT_EDGES && a->result_layout != WN_LAYOUT_CSR16 && a->result_layout != WN_LAYOUT_CSR12)
         return fail(ctx, WN_ERR_BAD_ARG, "wn_hbond_batch_ex: unknown result_layout");
     ctx->layout = a->result_layout;
     ctx->keep_dev = a->results_on_device != 0;
@@ -1081,7 +1183,7 @@ int wn_format_edges(wn_ctx* ctx, const int32_t* frame_numbers, const uint32_t* s
     unsigned long long pos = 0, max_edges = 0;
     for (int f = 0; f < F; ++f) {
         hdr[f] = "#--- frame " + std::to_string(frame_numbers[f]) + " ---\n";
-        const unsigned long long cnt = ctx->h_frame_off[f + 1] - ctx->h_frame_off[f];
+        const unsigned long long cnt = ctx->hset[ctx->cur].frame_off[f + 1] - ctx->hset[ctx->cur].frame_off[f];
         row_base[f] = pos + hdr[f].size();
         pos = row_base[f] + 37ull * cnt;
         max_edges = std::max(max_edges, cnt);
@@ -1132,7 +1234,9 @@ int wn_components(wn_ctx* ctx, float weight_threshold, const int32_t** labels, c
     if ((rc = dev_ensure(ctx, &ctx->d_cc_kept, &ctx->cc_kept_cap, (size_t)F + 1))) return rc;
     if ((rc = dev_ensure(ctx, &ctx->d_cc_stats, &ctx->cc_stats_cap, (size_t)F + 1))) return rc;
     unsigned long long max_edges = 0;
-    for (int f = 0; f < F; ++f) max_edges = std::max<unsigned long long>(max_edges, ctx->h_frame_off[f + 1] - ctx->h_frame_off[f]);
+    for (int f = 0; f < F; ++f) max_edges = std::max<unsigned long long>(max_edges, ctx->hset[ctx->cur].frame_off[f + 1] - ctx->hset[ctx->cur].frame_off[f]);
+    if (ctx->layout == WN_LAYOUT_CSR12)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_components: a WN_LAYOUT_CSR12 result carries no energies; use WN_LAYOUT_EDGES or WN_LAYOUT_CSR16");
     wn_launch_components(ctx->d_edges, ctx->layout == WN_LAYOUT_CSR16 ? 1 : 0, ctx->d_frame_off, ctx->d_row_off, F, N,
                          max_edges, weight_threshold, ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx,
                          ctx->d_cc_kept, ctx->d_cc_stats, ctx->st);

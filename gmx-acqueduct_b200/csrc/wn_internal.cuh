@@ -147,7 +147,7 @@ void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* f
 void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
                     const uint32_t* row_off, const unsigned long long* frame_off,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
-                    unsigned long long edge_cap, int csr16, double* block_sums, int* n_blocks_out,
+                    unsigned long long edge_cap, int layout, float* energy_side, double* block_sums, int* n_blocks_out,
                     cudaStream_t st);
 void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,
                      const WnFrameCounters* counters, int n_frames, int n_sites, WnSubset sub,

@@ -125,13 +125,13 @@ wn_k_frameoff(const unsigned long long* __restrict__ frame_total, const uint32_t
 #ifndef WN_COPY_MINBLOCKS
 #define WN_COPY_MINBLOCKS 8
 #endif
-template <bool CSR16>
+template <int LAYOUT>      /* WN_LAYOUT_EDGES / _CSR16 / _CSR12 */
 __global__ void __launch_bounds__(COPY_THREADS, WN_COPY_MINBLOCKS)
 wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
           const uint32_t* __restrict__ row_cnt, const uint32_t* __restrict__ row_off,
           const unsigned long long* __restrict__ frame_off, int n_sites, WnEnergyParams ep,
           wn_edge* __restrict__ edges, unsigned long long edge_cap, unsigned long long edge_base,
-          double* __restrict__ block_sums)
+          float* __restrict__ energy_side, double* __restrict__ block_sums)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int f = blockIdx.y;
@@ -175,10 +175,16 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
                 for (uint32_t k = 0; k < rcnt; ++k) rank += ((int)rowp[k].x < tj) ? 1u : 0u;
                 /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
                 const float en = __double2float_rn(wn_compute_energy((double)tlen, (double)tcos, ep));
-                if (CSR16) {
+                if (LAYOUT == WN_LAYOUT_CSR16) {
                     /* compact layout: {j, energy, length, cosine}, one aligned 16-byte store */
                     reinterpret_cast<uint4*>(edges)[span + rpre + rank] =
                         make_uint4((uint32_t)tj, __float_as_uint(en), __float_as_uint(tlen), __float_as_uint(tcos));
+                } else if (LAYOUT == WN_LAYOUT_CSR12) {
+                    /* {j, length, cosine}: the energy is a function of the last two and stays on the device
+                     * (side array in final order, for the statistics row only) */
+                    uint32_t* o = reinterpret_cast<uint32_t*>(edges) + (span + rpre + rank) * 3;
+                    o[0] = (uint32_t)tj; o[1] = __float_as_uint(tlen); o[2] = __float_as_uint(tcos);
+                    energy_side[span + rpre + rank] = en;
                 } else {
                     wn_edge out;
                     out.i = irow; out.j = tj; out.energy = en; out.length = tlen; out.cosine = tcos;
@@ -190,8 +196,9 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
          * the summation tree does not depend on arrival order -> deterministic */
         __syncwarp();
         for (uint32_t e = lane; e < total; e += 32)
-            sum += CSR16 ? (double)__uint_as_float(reinterpret_cast<const uint4*>(edges)[span + e].y)
-                         : (double)edges[span + e].energy;
+            sum += LAYOUT == WN_LAYOUT_CSR16 ? (double)__uint_as_float(reinterpret_cast<const uint4*>(edges)[span + e].y)
+                 : LAYOUT == WN_LAYOUT_CSR12 ? (double)energy_side[span + e]
+                                             : (double)edges[span + e].energy;
     }
     /* fixed-tree warp reduction; one partial per warp (no block barrier), summed in order by wn_k_stats */
 #pragma unroll
@@ -237,17 +244,21 @@ void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* f
 void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
                     const uint32_t* row_off, const unsigned long long* frame_off,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
-                    unsigned long long edge_cap, int csr16, double* block_sums, int* n_blocks_out,
+                    unsigned long long edge_cap, int layout, float* energy_side, double* block_sums, int* n_blocks_out,
                     cudaStream_t st)
 {
     dim3 g((n_sites + COPY_THREADS - 1) / COPY_THREADS, n_frames);
     *n_blocks_out = (int)g.x * (COPY_THREADS / 32);      /* partial sums per frame */
-    if (csr16)
-        wn_k_copy<true><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
-                                                    edges, edge_cap, 0ull, block_sums);
+    /* edge_cap counts 20-byte records; the compact layouts use the same buffer */
+    if (layout == WN_LAYOUT_CSR16)
+        wn_k_copy<WN_LAYOUT_CSR16><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
+                                                               edges, edge_cap, 0ull, energy_side, block_sums);
+    else if (layout == WN_LAYOUT_CSR12)
+        wn_k_copy<WN_LAYOUT_CSR12><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
+                                                               edges, edge_cap, 0ull, energy_side, block_sums);
     else
-        wn_k_copy<false><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
-                                                     edges, edge_cap, 0ull, block_sums);
+        wn_k_copy<WN_LAYOUT_EDGES><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
+                                                               edges, edge_cap, 0ull, energy_side, block_sums);
 }
 
 void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,

@@ -4,8 +4,10 @@
 
 #include <algorithm>
 #include <cstring>
+#include <exception>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 namespace {
 [[noreturn]] void raise(const char* what, int rc, const wn_ctx* ctx)
@@ -13,10 +15,19 @@ namespace {
     throw std::runtime_error(std::string(what) + " failed (status " + std::to_string(rc) + "): " +
                              wn_last_error(ctx));
 }
+
+HydrogenBondBatch wrap(const wn_batch_result& r)
+{
+    HydrogenBondBatch b;
+    b.edges = r.edges; b.offsets = r.frame_offsets; b.stats = r.stats;
+    b.n_frames = r.n_frames; b.n_edges = r.n_edges; b.n_pair_evals = r.n_pair_evals; b.ties = r.ties;
+    b.row_offsets = r.row_offsets; b.n_sites = r.n_sites; b.layout = r.layout;
+    return b;
+}
 }  // namespace
 
 HydrogenBondEdges::HydrogenBondEdges(int device)
-    : ctx_(nullptr), r_on_(5.5), r_off_(6.5), a_on_(0.25), a_off_(0.0)
+    : ctx_(nullptr), device_(device), r_on_(5.5), r_off_(6.5), a_on_(0.25), a_off_(0.0)
 {
     const int rc = wn_create(device, &ctx_);
     if (rc != WN_OK) raise("HydrogenBondEdges: wn_create", rc, nullptr);
@@ -79,10 +90,7 @@ HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, const float*
     const int rc = boxes ? wn_hbond_batch_pbc(ctx_, frames, boxes, n_frames, natoms, &r)
                          : wn_hbond_batch(ctx_, frames, n_frames, natoms, &r);
     if (rc != WN_OK) raise("HydrogenBondEdges::calculate: wn_hbond_batch", rc, ctx_);
-    HydrogenBondBatch b;
-    b.edges = r.edges; b.offsets = r.frame_offsets; b.stats = r.stats;
-    b.n_frames = r.n_frames; b.n_edges = r.n_edges; b.n_pair_evals = r.n_pair_evals; b.ties = r.ties;
-    return b;
+    return wrap(r);
 }
 
 HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, const float* boxes, int n_frames, int natoms,
@@ -91,10 +99,7 @@ HydrogenBondBatch HydrogenBondEdges::calculate(const float* frames, const float*
     wn_batch_result r;
     const int rc = wn_hbond_batch_subset(ctx_, frames, boxes, n_frames, natoms, subset_offsets, subset_sites, &r);
     if (rc != WN_OK) raise("HydrogenBondEdges::calculate: wn_hbond_batch_subset", rc, ctx_);
-    HydrogenBondBatch b;
-    b.edges = r.edges; b.offsets = r.frame_offsets; b.stats = r.stats;
-    b.n_frames = r.n_frames; b.n_edges = r.n_edges; b.n_pair_evals = r.n_pair_evals; b.ties = r.ties;
-    return b;
+    return wrap(r);
 }
 
 HydrogenBondBatch HydrogenBondEdges::calculateBox9(const float* frames, const float* boxes9, int n_frames, int natoms)
@@ -102,10 +107,51 @@ HydrogenBondBatch HydrogenBondEdges::calculateBox9(const float* frames, const fl
     wn_batch_result r;
     const int rc = wn_hbond_batch_box9(ctx_, frames, boxes9, n_frames, natoms, &r);
     if (rc != WN_OK) raise("HydrogenBondEdges::calculateBox9: wn_hbond_batch_box9", rc, ctx_);
-    HydrogenBondBatch b;
-    b.edges = r.edges; b.offsets = r.frame_offsets; b.stats = r.stats;
-    b.n_frames = r.n_frames; b.n_edges = r.n_edges; b.n_pair_evals = r.n_pair_evals; b.ties = r.ties;
-    return b;
+    return wrap(r);
+}
+
+HydrogenBondBatch HydrogenBondEdges::calculateEx(const wn_batch_args& args)
+{
+    wn_batch_result r;
+    const int rc = wn_hbond_batch_ex(ctx_, &args, &r);
+    if (rc != WN_OK) raise("HydrogenBondEdges::calculateEx: wn_hbond_batch_ex", rc, ctx_);
+    return wrap(r);
+}
+
+void HydrogenBondEdges::setResultSets(int n)
+{
+    const int rc = wn_set_result_sets(ctx_, n);
+    if (rc != WN_OK) raise("HydrogenBondEdges::setResultSets", rc, ctx_);
+}
+
+int HydrogenBondEdges::bindThreadToDevice()
+{
+    int32_t n = 0;
+    const int rc = wn_bind_thread_to_device(ctx_, &n);
+    if (rc != WN_OK) raise("HydrogenBondEdges::bindThreadToDevice", rc, ctx_);
+    return n;
+}
+
+float* HydrogenBondEdges::allocPinnedFloats(size_t count)
+{
+    void* p = nullptr;
+    const int rc = wn_host_alloc_pinned(ctx_, count * sizeof(float), &p);
+    if (rc != WN_OK) raise("HydrogenBondEdges::allocPinnedFloats: wn_host_alloc_pinned", rc, ctx_);
+    return static_cast<float*>(p);
+}
+
+void HydrogenBondEdges::freePinned(void* p) { if (p) wn_host_free_pinned(ctx_, p); }
+
+void HydrogenBondEdges::ncclInit(const void* id128, int rank, int nranks)
+{
+    const int rc = wn_nccl_init(ctx_, id128, rank, nranks);
+    if (rc != WN_OK) raise("HydrogenBondEdges::ncclInit: wn_nccl_init", rc, ctx_);
+}
+
+void HydrogenBondEdges::statsReduce(wn_frame_stats* table, int64_t n_frames_total)
+{
+    const int rc = wn_stats_reduce(ctx_, table, n_frames_total);
+    if (rc != WN_OK) raise("HydrogenBondEdges::statsReduce: wn_stats_reduce", rc, ctx_);
 }
 
 bool HydrogenBondEdges::formatLastBatch(const std::vector<int>& frameNumbers, const std::vector<unsigned>& ids,
@@ -139,69 +185,247 @@ std::vector<HydrogenBond> HydrogenBondEdges::toHydrogenBonds(const HydrogenBondB
 }
 
 // ---------------------------------------------------------------- FrameBatcher
-FrameBatcher::FrameBatcher(HydrogenBondEdges& engine, int natoms, int batch_frames, Sink sink)
-    : engine_(engine), natoms_(natoms), batch_frames_(std::max(batch_frames, 1)), sink_(sink),
-      frames_done_(0)
+struct FrameBatcher::Lane {
+    HydrogenBondEdges* eng = nullptr;
+    float* stage[2] = {nullptr, nullptr};      // pinned staging buffers: one fills while the other is on the GPU
+    int fill = 0;
+    std::vector<int> frnr[2];
+    std::vector<uint64_t> seq[2];              // push sequence number of every frame = its row of the statistics table
+    std::vector<float> boxes[2];
+    std::vector<int64_t> sub_off[2];
+    std::vector<int32_t> sub_sites[2];
+    std::vector<float> b3;                     // rectangular box lengths of a site-list batch
+    std::future<HydrogenBondBatch> fut;
+    int flying = -1;                           // staging buffer of the batch in flight, -1: none
+    bool have_ready = false;                   // a finished batch waits for delivery
+    HydrogenBondBatch ready;
+    int ready_buf = 0;
+    std::vector<wn_frame_stats> table;         // this GPU's rows of the run's statistics table (zero elsewhere)
+};
+
+void FrameBatcher::init(int natoms, int batch_frames, int layout)
 {
-    buf_.reserve((size_t)batch_frames_ * natoms_ * 3);
+    natoms_ = natoms; batch_frames_ = std::max(batch_frames, 1); layout_ = layout;
+    cur_ = 0; frames_done_ = 0; frames_pushed_ = 0; pipelined_ = true;
+    const size_t count = (size_t)batch_frames_ * (size_t)natoms_ * 3;
+    for (Lane* l : lanes_) {
+        // allocate from a thread pinned next to the GPU: pinned pages are touched (placed) by the allocating thread
+        std::exception_ptr err;
+        std::thread t([&]() {
+            try {
+                l->eng->bindThreadToDevice();
+                l->stage[0] = l->eng->allocPinnedFloats(std::max<size_t>(count, 1));
+                l->stage[1] = l->eng->allocPinnedFloats(std::max<size_t>(count, 1));
+                l->eng->setResultSets(2);
+            } catch (...) { err = std::current_exception(); }
+        });
+        t.join();
+        if (err) std::rethrow_exception(err);
+    }
+    if (lanes_.size() > 1) {
+        // one NCCL communicator over the GPUs of this process (statistics table only)
+        unsigned char id[128];
+        if (wn_nccl_unique_id(id) != WN_OK)
+            throw std::runtime_error(std::string("FrameBatcher: wn_nccl_unique_id failed: ") + wn_last_error(nullptr));
+        std::vector<std::thread> ts;
+        std::vector<std::exception_ptr> errs(lanes_.size());
+        for (size_t g = 0; g < lanes_.size(); ++g)
+            ts.emplace_back([&, g]() {
+                try { lanes_[g]->eng->ncclInit(id, (int)g, (int)lanes_.size()); } catch (...) { errs[g] = std::current_exception(); }
+            });
+        for (auto& t : ts) t.join();
+        for (auto& e : errs) if (e) std::rethrow_exception(e);
+    }
+}
+
+FrameBatcher::FrameBatcher(HydrogenBondEdges& engine, int natoms, int batch_frames, Sink sink)
+    : sink_(sink)
+{
+    Lane* l = new Lane();
+    l->eng = &engine;
+    lanes_.push_back(l);
+    init(natoms, batch_frames, WN_LAYOUT_EDGES);
+}
+
+FrameBatcher::FrameBatcher(const std::vector<HydrogenBondEdges*>& engines, int natoms, int batch_frames, FrameSink sink,
+                           int layout)
+    : frame_sink_(sink)
+{
+    if (engines.empty()) throw std::invalid_argument("FrameBatcher: no engine");
+    for (HydrogenBondEdges* e : engines) {
+        Lane* l = new Lane();
+        l->eng = e;
+        lanes_.push_back(l);
+    }
+    init(natoms, batch_frames, layout);
+}
+
+FrameBatcher::~FrameBatcher()
+{
+    for (Lane* l : lanes_) {
+        if (l->fut.valid()) { try { l->fut.get(); } catch (...) {} }
+        l->eng->freePinned(l->stage[0]);
+        l->eng->freePinned(l->stage[1]);
+        try { l->eng->setResultSets(1); } catch (...) {}
+        delete l;
+    }
+}
+
+float* FrameBatcher::stage()
+{
+    Lane& l = *lanes_[cur_];
+    return l.stage[l.fill] + l.frnr[l.fill].size() * (size_t)natoms_ * 3;
+}
+
+void FrameBatcher::commit(int frnr)
+{
+    Lane& l = *lanes_[cur_];
+    l.frnr[l.fill].push_back(frnr);
+    l.seq[l.fill].push_back(frames_pushed_++);
+    if ((int)l.frnr[l.fill].size() >= batch_frames_) submit();
 }
 
 void FrameBatcher::push(int frnr, const float* xyz)
 {
-    buf_.insert(buf_.end(), xyz, xyz + (size_t)natoms_ * 3);
-    frnr_.push_back(frnr);
-    if ((int)frnr_.size() >= batch_frames_) flush();
+    std::memcpy(stage(), xyz, (size_t)natoms_ * 3 * sizeof(float));
+    commit(frnr);
 }
 
 void FrameBatcher::push(int frnr, const float* xyz, const float box[3][3])
 {
-    if (!frnr_.empty() && boxes_.size() != 9 * frnr_.size())
+    Lane& l = *lanes_[cur_];
+    if (!l.frnr[l.fill].empty() && l.boxes[l.fill].size() != 9 * l.frnr[l.fill].size())
         throw std::invalid_argument("FrameBatcher::push: periodic and open frames mixed in one batch");
     for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) boxes_.push_back(box[a][b]);
+        for (int b = 0; b < 3; ++b) l.boxes[l.fill].push_back(box[a][b]);
     push(frnr, xyz);
 }
 
 void FrameBatcher::push(int frnr, const float* xyz, const float (*box)[3], const std::vector<int32_t>& frameSites)
 {
-    if (!frnr_.empty() && sub_off_.size() != frnr_.size() + 1)
+    Lane& l = *lanes_[cur_];
+    const int b = l.fill;
+    if (!l.frnr[b].empty() && l.sub_off[b].size() != l.frnr[b].size() + 1)
         throw std::invalid_argument("FrameBatcher::push: frames with and without site lists mixed in one batch");
-    if (sub_off_.empty()) sub_off_.push_back(0);
-    sub_sites_.insert(sub_sites_.end(), frameSites.begin(), frameSites.end());
-    sub_off_.push_back((int64_t)sub_sites_.size());
+    if (l.sub_off[b].empty()) l.sub_off[b].push_back(0);
+    l.sub_sites[b].insert(l.sub_sites[b].end(), frameSites.begin(), frameSites.end());
+    l.sub_off[b].push_back((int64_t)l.sub_sites[b].size());
     if (box) {
         for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) {
-                if (a != b && box[a][b] != 0.0f)
+            for (int c = 0; c < 3; ++c) {
+                if (a != c && box[a][c] != 0.0f)
                     throw std::invalid_argument("FrameBatcher::push: per-frame site lists need a rectangular box");
-                boxes_.push_back(box[a][b]);
+                l.boxes[b].push_back(box[a][c]);
             }
     }
     push(frnr, xyz);
 }
 
-void FrameBatcher::finish() { flush(); }
-
-void FrameBatcher::flush()
+void FrameBatcher::deliverOldest()
 {
-    if (frnr_.empty()) return;
-    HydrogenBondBatch b;
-    if (sub_off_.empty()) {
-        b = boxes_.empty() ? engine_.calculate(buf_.data(), (int)frnr_.size(), natoms_)
-                           : engine_.calculateBox9(buf_.data(), boxes_.data(), (int)frnr_.size(), natoms_);
-    } else {
-        std::vector<float> b3;                    /* site lists: rectangular boxes only (checked in push) */
-        for (size_t f = 0; 9 * f < boxes_.size(); ++f) { b3.push_back(boxes_[9 * f]); b3.push_back(boxes_[9 * f + 4]); b3.push_back(boxes_[9 * f + 8]); }
-        b = engine_.calculate(buf_.data(), b3.empty() ? nullptr : b3.data(), (int)frnr_.size(), natoms_, sub_off_.data(),
-                              sub_sites_.data());
+    if (pending_.empty()) return;
+    Lane& l = *lanes_[pending_.front()];
+    pending_.erase(pending_.begin());
+    if (!l.have_ready) {                        // still in flight: wait for it
+        l.ready = l.fut.get();
+        l.ready_buf = l.flying;
+        l.flying = -1;
     }
-    if (batch_hook_) batch_hook_(frnr_, b);
-    for (int f = 0; f < b.n_frames; ++f)
-        sink_(frnr_[f], b.edges + b.offsets[f], (size_t)(b.offsets[f + 1] - b.offsets[f]), b.stats[f]);
+    l.have_ready = false;
+    const HydrogenBondBatch& b = l.ready;
+    const int buf = l.ready_buf;
+    const size_t esz = b.layout == WN_LAYOUT_CSR16 ? sizeof(wn_edge16) : b.layout == WN_LAYOUT_CSR12 ? sizeof(wn_edge12)
+                                                                                                    : sizeof(wn_edge);
+    for (int f = 0; f < b.n_frames; ++f) {
+        const uint64_t seq = l.seq[buf][f];
+        if (l.table.size() <= seq) l.table.resize(seq + 1, wn_frame_stats{0, 0, 0, 0, 0});
+        l.table[seq] = b.stats[f];
+        const size_t n = (size_t)(b.offsets[f + 1] - b.offsets[f]);
+        if (frame_sink_) {
+            FrameResult r;
+            r.frnr = l.frnr[buf][f]; r.layout = b.layout;
+            r.edges = reinterpret_cast<const char*>(b.edges) + (size_t)b.offsets[f] * esz;
+            r.n_edges = n;
+            r.row_offsets = b.row_offsets ? b.row_offsets + (size_t)f * b.n_sites : nullptr;
+            r.n_sites = b.n_sites; r.stats = b.stats[f]; r.device = l.eng->device();
+            frame_sink_(r);
+        } else if (sink_) {
+            sink_(l.frnr[buf][f], b.edges + b.offsets[f], n, b.stats[f]);
+        }
+    }
     frames_done_ += (uint64_t)b.n_frames;
-    buf_.clear();
-    boxes_.clear();
-    sub_off_.clear();
-    sub_sites_.clear();
-    frnr_.clear();
+    l.frnr[buf].clear(); l.seq[buf].clear(); l.boxes[buf].clear(); l.sub_off[buf].clear(); l.sub_sites[buf].clear();
+}
+
+void FrameBatcher::submit()
+{
+    Lane& l = *lanes_[cur_];
+    const int buf = l.fill;
+    if (l.frnr[buf].empty()) return;
+    // one call at a time per context: the lane's previous batch must have left the GPU (its result stays
+    // valid in the other host result set and is handed to the sink below, while the new batch runs)
+    if (l.flying >= 0) {
+        l.ready = l.fut.get();
+        l.ready_buf = l.flying;
+        l.flying = -1;
+        l.have_ready = true;
+    }
+    wn_batch_args a;
+    a.frames = l.stage[buf]; a.frames_on_device = 0; a.n_frames = (int32_t)l.frnr[buf].size(); a.natoms = natoms_;
+    a.box_stride = 0; a.boxes = nullptr; a.subset_offsets = nullptr; a.subset_sites = nullptr;
+    a.result_layout = layout_; a.results_on_device = 0;
+    if (!l.sub_off[buf].empty()) {
+        a.subset_offsets = l.sub_off[buf].data(); a.subset_sites = l.sub_sites[buf].data();
+        if (!l.boxes[buf].empty()) {              /* site lists: rectangular boxes only (checked in push) */
+            l.b3.clear();
+            for (size_t f = 0; 9 * f < l.boxes[buf].size(); ++f) {
+                l.b3.push_back(l.boxes[buf][9 * f]); l.b3.push_back(l.boxes[buf][9 * f + 4]); l.b3.push_back(l.boxes[buf][9 * f + 8]);
+            }
+            a.box_stride = 3; a.boxes = l.b3.data();
+        }
+    } else if (!l.boxes[buf].empty()) {
+        a.box_stride = 9; a.boxes = l.boxes[buf].data();
+    }
+    HydrogenBondEdges* eng = l.eng;
+    const bool async = pipelined_ && !batch_hook_;
+    if (async) {
+        l.fut = std::async(std::launch::async, [eng, a]() {
+            eng->bindThreadToDevice();
+            return eng->calculateEx(a);
+        });
+        l.flying = buf;
+        pending_.push_back(cur_);
+        l.fill = 1 - buf;
+        // everything older than the batch just submitted goes to the sink now, in frame order
+        while (pending_.size() > lanes_.size() || (!pending_.empty() && lanes_[pending_.front()]->have_ready)) deliverOldest();
+    } else {
+        while (!pending_.empty()) deliverOldest();
+        l.ready = eng->calculateEx(a);
+        l.ready_buf = buf;
+        l.have_ready = true;
+        if (batch_hook_) batch_hook_(l.frnr[buf], l.ready);
+        pending_.push_back(cur_);
+        deliverOldest();
+    }
+    cur_ = (cur_ + 1) % (int)lanes_.size();
+}
+
+void FrameBatcher::finish()
+{
+    submit();                                   // the partial tail batch, if any
+    while (!pending_.empty()) deliverOldest();
+    // statistics rows of the whole run: per GPU a zero-padded table, summed with NCCL when there are several
+    const size_t F = (size_t)frames_pushed_;
+    for (Lane* l : lanes_) l->table.resize(F, wn_frame_stats{0, 0, 0, 0, 0});
+    if (lanes_.size() > 1 && F > 0) {
+        std::vector<std::thread> ts;
+        std::vector<std::exception_ptr> errs(lanes_.size());
+        for (size_t g = 0; g < lanes_.size(); ++g)
+            ts.emplace_back([&, g]() {
+                try { lanes_[g]->eng->statsReduce(lanes_[g]->table.data(), (int64_t)F); } catch (...) { errs[g] = std::current_exception(); }
+            });
+        for (auto& t : ts) t.join();
+        for (auto& e : errs) if (e) std::rethrow_exception(e);
+    }
+    reduced_ = lanes_[0]->table;
 }

@@ -17,12 +17,17 @@
 //
 //   wn_waternetwork -f traj.gro [-edges edges-frames.xvg] [-nodes nodes-list.xvg]
 //                   [-ohb hydrogen-bonds-num.xvg] [-obw buried-waters-num.xvg]
-//                   [-solvent SOL,WAT,HOH,TIP3] [-buried lists.txt] [-pbc] [-batch 256] [-device 0]
+//                   [-solvent SOL,WAT,HOH,TIP3] [-buried lists.txt] [-pbc] [-batch 256] [-device 0] [-gpus N]
 //                   [-don 5.5] [-doff 6.5] [-aon 0.25] [-aoff 0.0] [-bug-compat 0|1] [-gpu-text 1|0]
 //                   [-components threshold [-ocomp components-num.xvg]]
 // -components: per frame, the connected components of the network after dropping the edges with
 // |energy| <= threshold (the first step of python/network-analysis.py, computed on the GPU): one row
 // "time components largest sites edges" per frame.
+// -gpus N (N > 1): the trajectory is sharded frame-wise over GPUs 0..N-1 of this box -- consecutive blocks of
+// -batch frames go round-robin to the GPUs (one context, one staging pipeline and one worker thread per GPU),
+// the edge rows are written in frame order from the per-GPU results, and the rows of hydrogen-bonds-num.xvg
+// come from the NCCL sum of the per-GPU statistics tables (the only exchange between the GPUs).  The files are
+// byte-identical to a one-GPU run.  -components and the GPU text formatter are one-GPU features.
 // File name options take the reference's base names: ".dat" is appended to -edges/-nodes (:461,:485).
 #include <cmath>
 #include <cstdio>
@@ -30,6 +35,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <set>
 #include <sstream>
 #include <stdexcept>
@@ -113,7 +119,7 @@ struct Options {
                 obw = "buried-waters-num.xvg", buried, ocomp = "components-num.xvg";
     std::set<std::string> solvent{"SOL", "WAT", "HOH", "TIP3", "SPC"};
     bool pbc = false, bugCompat = true, gpuText = true;
-    int batch = 256, device = 0;
+    int batch = 256, device = 0, gpus = 1;
     double don = 5.5, doff = 6.5, aon = 0.25, aoff = 0.0;
     bool components = false;
     double compThreshold = 0.0;
@@ -137,6 +143,7 @@ Options parse(int argc, char** argv)
         else if (a == "-pbc") o.pbc = true;
         else if (a == "-batch") o.batch = std::atoi(val().c_str());
         else if (a == "-device") o.device = std::atoi(val().c_str());
+        else if (a == "-gpus") o.gpus = std::atoi(val().c_str());
         else if (a == "-don") o.don = std::atof(val().c_str());
         else if (a == "-doff") o.doff = std::atof(val().c_str());
         else if (a == "-aon") o.aon = std::atof(val().c_str());
@@ -153,6 +160,8 @@ Options parse(int argc, char** argv)
     }
     if (o.traj.empty()) throw std::runtime_error("usage: wn_waternetwork -f traj.gro [options] (see the file header)");
     if (o.batch < 1) o.batch = 1;
+    if (o.gpus < 1) o.gpus = 1;
+    if (o.gpus > 1 && o.components) throw std::runtime_error("-components needs -gpus 1 (it works on one context's last batch)");
     return o;
 }
 
@@ -249,10 +258,15 @@ int main(int argc, char** argv)
         std::ifstream buried;
         if (!opt.buried.empty()) { buried.open(opt.buried); if (!buried) throw std::runtime_error("cannot open " + opt.buried); }
 
-        HydrogenBondEdges hb(opt.device);
-        hb.setRadiusShift((float)opt.don, (float)opt.doff);
-        hb.setAngleShift((float)opt.aon, (float)opt.aoff);
-        hb.setSites(table, hydrogens);
+        // one engine (context) per GPU; the site table and the energy parameters are replicated
+        std::vector<std::unique_ptr<HydrogenBondEdges> > engines;
+        for (int g = 0; g < opt.gpus; ++g) {
+            engines.emplace_back(new HydrogenBondEdges(opt.gpus > 1 ? g : opt.device));
+            engines.back()->setRadiusShift((float)opt.don, (float)opt.doff);
+            engines.back()->setAngleShift((float)opt.aon, (float)opt.aoff);
+            engines.back()->setSites(table, hydrogens);
+        }
+        HydrogenBondEdges& hb = *engines[0];
 
         std::vector<double> times;
         std::vector<size_t> filtered;
@@ -260,8 +274,8 @@ int main(int argc, char** argv)
         char row[256];
         uint64_t total_edges = 0;
         bool batch_text_done = false;      // the batch's rows were formatted on the GPU and written in one piece
-        FrameBatcher batcher(hb, natoms, opt.batch,
-            [&](int frnr, const wn_edge* e, size_t n, const wn_frame_stats& st) {
+        const bool sharded = opt.gpus > 1;
+        auto frameSink = [&](int frnr, const wn_edge* e, size_t n, const wn_frame_stats& st) {
                 if (writer && !batch_text_done) {                                   // :638-652 (host formatter)
                     if (buried.is_open()) {
                         /* edge indices are positions in this frame's site list: back to table rows for the ids */
@@ -280,18 +294,29 @@ int main(int argc, char** argv)
                     std::snprintf(row, sizeof row, " %11.3f %8.3f %8.3f\n", t, (double)filtered[(size_t)frnr], 0.0);
                     obw << row;
                 }
-                if (ohb.is_open()) {                                                 // :659-666
+                if (ohb.is_open() && !sharded) {                                     // :659-666
                     std::snprintf(row, sizeof row, " %11.3f %8.3f %8.3f %8.3f %8.3f %8.3f %8.3f\n", t, st.num_sites,
                                   st.num_edges, st.ratio, 0.0, 0.0, 0.0);
                     ohb << row;
                 }
-            });
+            };
+        std::unique_ptr<FrameBatcher> batcherPtr;
+        if (!sharded) {
+            batcherPtr.reset(new FrameBatcher(hb, natoms, opt.batch, frameSink));
+        } else {
+            std::vector<HydrogenBondEdges*> eng;
+            for (auto& e : engines) eng.push_back(e.get());
+            batcherPtr.reset(new FrameBatcher(eng, natoms, opt.batch, [&](const FrameResult& r) {
+                frameSink(r.frnr, static_cast<const wn_edge*>(r.edges), r.n_edges, r.stats);
+            }, WN_LAYOUT_EDGES));
+        }
+        FrameBatcher& batcher = *batcherPtr;
 
         // edge rows of a whole batch from the GPU formatter (same bytes); a batch with a field wider than its
         // column (ids over 6 digits, values over 8 characters) goes through the host writer instead
         std::ofstream ocomp;
         if (opt.components && !opt.ocomp.empty()) ocomp.open(opt.ocomp);
-        batcher.setBatchHook([&](const std::vector<int>& frameNumbers, const HydrogenBondBatch&) {
+        if (!sharded) batcher.setBatchHook([&](const std::vector<int>& frameNumbers, const HydrogenBondBatch&) {
             if (ocomp.is_open()) {
                 const int32_t* labels = nullptr; const wn_component_stats* cs = nullptr;
                 hb.componentsOfLastBatch((float)opt.compThreshold, &labels, &cs);
@@ -338,6 +363,15 @@ int main(int argc, char** argv)
             ++frnr;
         } while (readGroFrame(in, fr, nullptr, nullptr, nullptr));
         batcher.finish();                                                            // finishAnalysis (:670)
+        if (sharded && ohb.is_open()) {
+            // rows of every frame from the NCCL-summed statistics table (each row was filled by exactly one GPU)
+            const std::vector<wn_frame_stats>& all = batcher.reducedStats();
+            for (size_t f = 0; f < all.size(); ++f) {
+                std::snprintf(row, sizeof row, " %11.3f %8.3f %8.3f %8.3f %8.3f %8.3f %8.3f\n", times[f], all[f].num_sites,
+                              all[f].num_edges, all[f].ratio, 0.0, 0.0, 0.0);
+                ohb << row;
+            }
+        }
         delete writer;
         std::clog << frnr << " frames, " << total_edges << " hydrogen bonds" << std::endl;
         return 0;

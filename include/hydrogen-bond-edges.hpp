@@ -20,12 +20,16 @@
 #include <cstddef>
 #include <cstdint>
 #include <functional>
+#include <future>
 #include <vector>
 
 #include "wn_b200.h"
 #include "wn_types.hpp"
 
 // One processed batch, host side.  edges of frame f: [offsets[f], offsets[f+1]).
+// layout WN_LAYOUT_EDGES: `edges` are wn_edge records.  Compact layouts (WN_LAYOUT_CSR16 / _CSR12): the same
+// memory holds wn_edge16 / wn_edge12 records (use edges16() / edges12()) and the row index i comes from
+// row_offsets: edges of site i in frame f = [offsets[f] + row_offsets[f*n_sites + i], ... next row).
 struct HydrogenBondBatch {
     const wn_edge* edges = nullptr;
     const uint64_t* offsets = nullptr;
@@ -34,6 +38,23 @@ struct HydrogenBondBatch {
     uint64_t n_edges = 0;
     uint64_t n_pair_evals = 0;
     wn_tie_report ties = {0, 0, 0, 0, 0};
+    const uint32_t* row_offsets = nullptr;
+    int n_sites = 0;
+    int layout = WN_LAYOUT_EDGES;
+    const wn_edge16* edges16() const { return reinterpret_cast<const wn_edge16*>(edges); }
+    const wn_edge12* edges12() const { return reinterpret_cast<const wn_edge12*>(edges); }
+};
+
+// One frame of a batch as the compact sink sees it (any layout).
+struct FrameResult {
+    int frnr = 0;
+    int layout = WN_LAYOUT_EDGES;
+    const void* edges = nullptr;           // wn_edge / wn_edge16 / wn_edge12 records of this frame
+    size_t n_edges = 0;
+    const uint32_t* row_offsets = nullptr; // [n_sites] offsets of the rows inside this frame's records
+    int n_sites = 0;
+    wn_frame_stats stats = {0, 0, 0, 0, 0};
+    int device = 0;                        // GPU that processed the frame
 };
 
 class HydrogenBondEdges
@@ -89,50 +110,94 @@ public:
     static std::vector<HydrogenBond> toHydrogenBonds(const HydrogenBondBatch& batch, int frame,
                                                      const std::vector<SiteInfo_ptr>& sites);
 
+    // The general form (wn_hbond_batch_ex): any combination of boxes, site lists, result layout.
+    HydrogenBondBatch calculateEx(const wn_batch_args& args);
+    // 2: consecutive calculate() results alternate between two host buffer sets (a result stays valid
+    // while the next batch runs); FrameBatcher switches this on for pipelined batching.
+    void setResultSets(int n);
+    // Pin the calling thread next to this engine's GPU (see wn_bind_thread_to_device); returns the CPUs in the set.
+    int bindThreadToDevice();
+    // Pinned host memory (for staging frames): faster H2D, required for asynchronous overlap.
+    float* allocPinnedFloats(size_t count);
+    void freePinned(void* p);
+    // Several GPUs: per-frame statistics rows are summed over the shards with NCCL (the only collective).
+    void ncclInit(const void* id128, int rank, int nranks);
+    void statsReduce(wn_frame_stats* table, int64_t n_frames_total);
+    int device() const { return device_; }
+
     wn_ctx* context() { return ctx_; }
 
 private:
     void pushParams();
     wn_ctx* ctx_;
+    int device_;
     double r_on_, r_off_, a_on_, a_off_;
 };
 
-// Frame batching for WaterNetwork::analyzeFrame (src/waternetwork.cpp:503): buffer
-// frames on the host, run one batch per `batch_frames`, deliver results per frame in
-// frame order through the sink (which writes the edge rows :638-652 and the data-set
-// points :654-666).  finish() flushes the tail (call from finishAnalysis, :670).
+// Frame batching for WaterNetwork::analyzeFrame (src/waternetwork.cpp:503): frames are staged in PINNED host
+// memory, one batch per `batch_frames`, results delivered per frame in frame order through the sink (which
+// writes the edge rows :638-652 and the data-set points :654-666).  finish() flushes the tail (call from
+// finishAnalysis, :670).
+//
+// Pipelined: while batch k is on the GPU (a worker thread inside the C ABI call), the caller keeps pushing
+// batch k+1 into the second staging buffer; batch k is handed to the sink -- on the CALLER's thread, in frame
+// order -- when batch k+1 is submitted, i.e. while the GPU already works on k+1 (two host result sets).
+// Several engines (one per GPU): batches go round-robin to the GPUs, i.e. every GPU owns contiguous blocks of
+// batch_frames frames; delivery stays in frame order; the only cross-GPU exchange is the NCCL sum
+// of the statistics table at finish() (reducedStats()), which serves the .xvg rows.
 class FrameBatcher
 {
 public:
     typedef std::function<void(int frnr, const wn_edge* edges, size_t n_edges,
                                const wn_frame_stats& stats)> Sink;
+    typedef std::function<void(const FrameResult&)> FrameSink;
 
+    // classic form: 20-byte wn_edge records ({i, j, energy, length, cosine})
     FrameBatcher(HydrogenBondEdges& engine, int natoms, int batch_frames, Sink sink);
+    // compact form (default layout WN_LAYOUT_CSR16: 16 bytes per edge over PCIe), one or several GPUs
+    FrameBatcher(const std::vector<HydrogenBondEdges*>& engines, int natoms, int batch_frames, FrameSink sink,
+                 int layout = WN_LAYOUT_CSR16);
+    ~FrameBatcher();
+    FrameBatcher(const FrameBatcher&) = delete;
+    FrameBatcher& operator=(const FrameBatcher&) = delete;
+
     void push(int frnr, const float* xyz /* natoms*3 */);
     // periodic: box = GROMACS matrix fr.box (rectangular or triclinic)
     void push(int frnr, const float* xyz, const float box[3][3]);
     // with the frame's own site list (rows of the site table, e.g. protein sites + the buried
     // waters of this frame); box may be nullptr.  All frames of a run must use the same variant.
     void push(int frnr, const float* xyz, const float (*box)[3], const std::vector<int32_t>& frameSites);
+    // zero-copy producers: where the next frame's natoms*3 floats go (pinned memory); then commit(frnr)
+    float* stage();
+    void commit(int frnr);
     void finish();
     uint64_t framesDone() const { return frames_done_; }
     // Optional: called once per processed batch, before the per-frame sink calls, while the batch is
-    // still the engine's "last batch" (so formatLastBatch / componentsOfLastBatch apply to it).
+    // still the engine's "last batch" (so formatLastBatch / componentsOfLastBatch apply to it).  A hook
+    // switches the pipelining off (batch k is fully delivered before batch k+1 is submitted).
     typedef std::function<void(const std::vector<int>& frameNumbers, const HydrogenBondBatch& batch)> BatchHook;
     void setBatchHook(BatchHook hook) { batch_hook_ = hook; }
+    void setPipelined(bool on) { pipelined_ = on; }
+    // After finish(): one row per pushed frame, in push order.  With several GPUs this is the NCCL sum of
+    // the per-GPU zero-padded tables (wn_stats_reduce), with one GPU the rows as delivered.
+    const std::vector<wn_frame_stats>& reducedStats() const { return reduced_; }
+    int gpus() const { return (int)lanes_.size(); }
 
 private:
-    void flush();
-    HydrogenBondEdges& engine_;
-    int natoms_, batch_frames_;
+    struct Lane;
+    void init(int natoms, int batch_frames, int layout);
+    void submit();                      // current lane's filling buffer -> GPU
+    void deliverOldest();               // wait for the oldest in-flight batch, hand it to the sink
+    std::vector<Lane*> lanes_;
+    std::vector<int> pending_;          // lanes with a batch in flight, oldest first
+    int cur_;                           // lane being filled
+    int natoms_, batch_frames_, layout_;
     Sink sink_;
+    FrameSink frame_sink_;
     BatchHook batch_hook_;
-    std::vector<float> buf_;
-    std::vector<float> boxes_;
-    std::vector<int64_t> sub_off_;
-    std::vector<int32_t> sub_sites_;
-    std::vector<int> frnr_;
-    uint64_t frames_done_;
+    bool pipelined_;
+    uint64_t frames_done_, frames_pushed_;
+    std::vector<wn_frame_stats> reduced_;
 };
 
 #endif

@@ -70,8 +70,17 @@ typedef struct wn_edge16 {
     int32_t j;
     float   energy, length, cosine;
 } wn_edge16;
+/* Smallest layout (WN_LAYOUT_CSR12): {j, length, cosine}, rows via row_offsets.  The energy of an edge is a
+ * pure function of its (length, cosine) -- computeEnergy(distance, proj), src/waternetwork.cpp:49-66,222 -- so a
+ * host that needs it recomputes it on demand (include/wn_energy.h: wn_edge_energy, the reference's own
+ * formula); 12 instead of 16/20 bytes per edge cross PCIe.  stats[f].sum_energy is still filled on the device. */
+typedef struct wn_edge12 {
+    int32_t j;
+    float   length, cosine;
+} wn_edge12;
 #define WN_LAYOUT_EDGES 0   /* wn_edge[]   : {i, j, energy, length, cosine}                      */
 #define WN_LAYOUT_CSR16 1   /* wn_edge16[] : {j, energy, length, cosine}, rows via row_offsets   */
+#define WN_LAYOUT_CSR12 2   /* wn_edge12[] : {j, length, cosine}, rows via row_offsets           */
 
 /* One row per frame.  First three = columns 0..2 of hydrogen-bonds-num.xvg
  * (src/waternetwork.cpp:659-662); sum_energy and pair_evals are extras. */
@@ -95,7 +104,7 @@ typedef struct wn_tie_report {
 /* Result of one batch.  Pointers are library-owned and stay valid until the next
  * wn_hbond_batch* call on the same context or wn_destroy. */
 typedef struct wn_batch_result {
-    const wn_edge*        edges;          /* concatenated, frame by frame; wn_edge16* when layout == WN_LAYOUT_CSR16 */
+    const wn_edge*        edges;          /* concatenated, frame by frame; wn_edge16* / wn_edge12* for the compact layouts */
     const uint64_t*       frame_offsets;  /* n_frames+1 offsets into edges       */
     const wn_frame_stats* stats;          /* n_frames rows                       */
     uint64_t              n_edges;        /* == frame_offsets[n_frames]          */
@@ -122,6 +131,8 @@ void wn_destroy(wn_ctx* ctx);
 const char* wn_last_error(const wn_ctx* ctx);
 /* Library identification: "wn_b200 <version> sm_100a". */
 const char* wn_version(void);
+/* Number of CUDA devices visible to the process (0 when there is none or the driver is unusable). */
+int wn_device_count(void);
 
 /* ---- FindPairs::find (include/find-pairs.hpp:11) -------------------------
  * Semantics of BruteFindPairs::find (src/brute-find-pairs.cpp:19-30): all i<j
@@ -219,7 +230,7 @@ typedef struct wn_batch_args {
     const float*   boxes;           /* host, [n_frames][box_stride]; NULL iff box_stride == 0        */
     const int64_t* subset_offsets;  /* host, [n_frames+1], or NULL: every frame uses the whole table */
     const int32_t* subset_sites;    /* host, rows of the site table                                  */
-    int32_t        result_layout;   /* WN_LAYOUT_EDGES (default) or WN_LAYOUT_CSR16                  */
+    int32_t        result_layout;   /* WN_LAYOUT_EDGES (default), WN_LAYOUT_CSR16 or WN_LAYOUT_CSR12  */
     int32_t        results_on_device; /* 1: host frames in, but edges and row offsets stay in device memory (as for a
                                      * *_dev batch) for consumers that continue on the GPU: wn_components,
                                      * wn_format_edges; only the small per-frame tables come back.  0: default */
@@ -229,6 +240,21 @@ int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* args, wn_batch_result* o
 /* Frames that one wn_hbond_batch* call processes per kernel pipeline pass
  * (larger inputs are split internally).  0 restores the default heuristic. */
 int wn_set_batch_frames(wn_ctx* ctx, int32_t frames_per_pass);
+
+/* Host result buffers of a context: 1 (default) -- the pointers of a batch result stay valid until the next
+ * wn_hbond_batch* call; 2 -- consecutive calls alternate between two sets, so a result stays valid until the
+ * call AFTER the next one (the caller can consume batch k on one thread while batch k+1 runs on another;
+ * FrameBatcher does exactly that).  wn_format_edges / wn_components always refer to the latest call. */
+int wn_set_result_sets(wn_ctx* ctx, int32_t n_sets);
+
+/* Pin the CALLING thread to the CPUs next to the context's GPU (sysfs local_cpulist of the PCI device), so that
+ * pinned buffers allocated afterwards (first touch) and the copies' host side sit on the GPU's NUMA node.
+ * *n_cpus (may be NULL): CPUs in the resulting set, 0 when the platform exposes no locality (nothing changed). */
+int wn_bind_thread_to_device(wn_ctx* ctx, int32_t* n_cpus);
+
+/* Plain pinned-memory copy bandwidth of this context's GPU (GB/s, `repeats` back-to-back copies of `bytes`):
+ * the ceiling of the host-buffer entry points; run it on all ranks at once to see what shared uplinks leave. */
+int wn_pcie_probe(wn_ctx* ctx, size_t bytes, int32_t repeats, double* h2d_gbs, double* d2h_gbs);
 
 /* ---- edge file text (src/waternetwork.cpp:638-652), formatted on the GPU ---------------
  * Formats the edge list of the LAST wn_hbond_batch* call of this context as the rows of

@@ -13,6 +13,9 @@
 #include "cuda-find-pairs.hpp"
 #include "hydrogen-bond-edges.hpp"
 #include "edge-file-writer.hpp"
+#include "wn_energy.h"
+#include <algorithm>
+#include <cstring>
 #include <sstream>
 
 #define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "CHECK failed: %s (%s:%d)\n", #c, __FILE__, __LINE__); return 1; } } while (0)
@@ -195,6 +198,86 @@ int main()
             CHECK(sub.size() == want100.size() && !sub.empty());
             for (size_t k = 0; k < sub.size(); ++k)
                 CHECK(sub[k].i == want100[k].i && sub[k].j == want100[k].j && sub[k].energy == want100[k].energy);
+        }
+        // compact layouts + pipelined batching (+ several GPUs when the box has them): the same edges as the
+        // single calculate() above, delivered in frame order; the NCCL-summed statistics table has every row
+        {
+            auto run_compact = [&](const std::vector<HydrogenBondEdges*>& engs, int layout, int per_batch, bool staged,
+                                   std::vector<wn_edge>& out, std::vector<wn_frame_stats>& rows) -> bool {
+                out.clear();
+                std::vector<int> seen;
+                const wn_energy_params ep = wn_energy_defaults();
+                FrameBatcher cb(engs, natoms, per_batch, [&](const FrameResult& r) {
+                    seen.push_back(r.frnr);
+                    if (r.n_sites != n_waters || r.layout != layout) throw std::runtime_error("frame result header");
+                    for (int i = 0; i < n_waters; ++i) {
+                        const size_t b = r.row_offsets[i], e = i + 1 < n_waters ? r.row_offsets[i + 1] : r.n_edges;
+                        for (size_t k = b; k < e; ++k) {
+                            wn_edge w; w.i = i;
+                            if (layout == WN_LAYOUT_CSR16) {
+                                const wn_edge16& c = static_cast<const wn_edge16*>(r.edges)[k];
+                                w.j = c.j; w.energy = c.energy; w.length = c.length; w.cosine = c.cosine;
+                            } else if (layout == WN_LAYOUT_CSR12) {
+                                const wn_edge12& c = static_cast<const wn_edge12*>(r.edges)[k];
+                                w.j = c.j; w.length = c.length; w.cosine = c.cosine;
+                                w.energy = wn_edge_energy(c.length, c.cosine, &ep);        // on demand, on the host
+                            } else {
+                                w = static_cast<const wn_edge*>(r.edges)[k];
+                            }
+                            out.push_back(w);
+                        }
+                    }
+                }, layout);
+                for (int f = 0; f < n_frames; ++f) {
+                    if (staged) { std::memcpy(cb.stage(), &frames[(size_t)f * natoms * 3], (size_t)natoms * 3 * sizeof(float)); cb.commit(100 + f); }
+                    else cb.push(100 + f, &frames[(size_t)f * natoms * 3]);
+                }
+                cb.finish();
+                rows = cb.reducedStats();
+                if (seen.size() != (size_t)n_frames) return false;
+                for (int f = 0; f < n_frames; ++f) if (seen[f] != 100 + f) return false;
+                return true;
+            };
+            auto same = [&](const std::vector<wn_edge>& a, bool exact_energy) {
+                if (a.size() != ref_edges.size()) return false;
+                for (size_t k = 0; k < a.size(); ++k) {
+                    if (a[k].i != ref_edges[k].i || a[k].j != ref_edges[k].j || a[k].length != ref_edges[k].length ||
+                        a[k].cosine != ref_edges[k].cosine) return false;
+                    const double d = std::fabs((double)a[k].energy - (double)ref_edges[k].energy);
+                    if (exact_energy ? d != 0.0 : d > 1e-6 * std::fabs((double)ref_edges[k].energy)) return false;
+                }
+                return true;
+            };
+            std::vector<wn_frame_stats> ref_stats(all.stats, all.stats + n_frames);
+            HydrogenBondBatch again0 = hb.calculate(frames.data(), n_frames, natoms);       // `all` was overwritten long ago
+            ref_stats.assign(again0.stats, again0.stats + n_frames);
+            std::vector<wn_edge> got2;
+            std::vector<wn_frame_stats> rows;
+            std::vector<HydrogenBondEdges*> one{&hb};
+            CHECK(run_compact(one, WN_LAYOUT_CSR16, 2, false, got2, rows) && same(got2, true));
+            CHECK(rows.size() == (size_t)n_frames);
+            for (int f = 0; f < n_frames; ++f)
+                CHECK(rows[f].num_edges == ref_stats[f].num_edges && rows[f].sum_energy == ref_stats[f].sum_energy);
+            CHECK(run_compact(one, WN_LAYOUT_CSR12, 3, true, got2, rows) && same(got2, false));
+            for (int f = 0; f < n_frames; ++f) CHECK(rows[f].sum_energy == ref_stats[f].sum_energy);
+            CHECK(run_compact(one, WN_LAYOUT_EDGES, 1, false, got2, rows) && same(got2, true));
+            const int ndev = wn_device_count();
+            if (ndev >= 2) {
+                std::vector<std::unique_ptr<HydrogenBondEdges> > more;
+                std::vector<HydrogenBondEdges*> engs{&hb};
+                for (int g = 1; g < std::min(ndev, 4); ++g) {
+                    more.emplace_back(new HydrogenBondEdges(g));
+                    more.back()->setWaterSites(n_waters);
+                    engs.push_back(more.back().get());
+                }
+                CHECK(run_compact(engs, WN_LAYOUT_CSR16, 2, false, got2, rows) && same(got2, true));
+                CHECK(rows.size() == (size_t)n_frames);
+                for (int f = 0; f < n_frames; ++f)      // NCCL sum of zero-padded per-GPU tables == the rows themselves
+                    CHECK(rows[f].num_sites == n_waters && rows[f].num_edges == ref_stats[f].num_edges &&
+                          rows[f].ratio == ref_stats[f].ratio && rows[f].sum_energy == ref_stats[f].sum_energy &&
+                          rows[f].pair_evals == ref_stats[f].pair_evals);
+                std::printf("multi-GPU batcher OK on %zu GPUs\n", engs.size());
+            }
         }
         // error behaviour: no exception escapes the C ABI; the C++ layer throws
         bool threw = false;

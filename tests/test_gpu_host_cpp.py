@@ -164,3 +164,58 @@ def test_standalone_driver_buried_lists(tmp_path):
         obw += " %11.3f %8.3f %8.3f\n" % (f, len(l), 0)
     assert open(str(tmp_path / "edges.dat")).read() == want
     assert open(str(tmp_path / "obw.xvg")).read() == obw
+
+
+def _device_count():
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "gmx-acqueduct_b200", "libwn_b200.so"))
+    return int(lib.wn_device_count())
+
+
+@pytest.mark.gpu
+def test_standalone_driver_frame_sharding_over_gpus(tmp_path):
+    """wn_waternetwork -gpus N (frame blocks round-robin over the GPUs, one context + worker thread each,
+    NCCL sum of the statistics tables for the .xvg rows): every file byte-identical to the one-GPU run.
+    Needs two GPUs in the box (gpurun --gpus 2); the one-GPU pipelined path is compared as well."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import wn_oracle_py as o
+    n, nf = 216, 11
+    sb = o.synth_box(n, model=o.MODEL_SPC)
+    frames = o.synth_frames(sb, 0, nf)
+    gro = str(tmp_path / "traj.gro")
+    _write_gro(gro, frames, float(sb.box))
+    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
+
+    def run(tag, extra):
+        d = tmp_path / tag
+        d.mkdir()
+        r = subprocess.run([exe, "-f", gro, "-edges", str(d / "edges"), "-nodes", str(d / "nodes"), "-ohb", str(d / "ohb.xvg"),
+                            "-obw", str(d / "obw.xvg"), "-batch", "2"] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return {k: open(str(d / k)).read() for k in ("edges.dat", "nodes.dat", "ohb.xvg", "obw.xvg")}
+
+    base = run("one", ["-gpu-text", "0"])
+    assert base["edges.dat"].count("#--- frame") == nf
+    assert run("one_gputext", ["-gpu-text", "1"]) == base
+    ndev = _device_count()
+    if ndev < 2:
+        pytest.skip("one GPU in this box: sharded run not exercised (run under gpurun --gpus 2)")
+    for g in sorted({2, min(ndev, 4), min(ndev, 8)}):
+        assert run("g%d" % g, ["-gpus", str(g)]) == base
+        assert run("g%d_pbc" % g, ["-gpus", str(g), "-pbc"]) == run("one_pbc_%d" % g, ["-pbc"])
+
+
+@pytest.mark.gpu
+def test_cpp_bench_binary_small():
+    """wn_bench (the C++ end-to-end bench of FrameBatcher + CudaFindPairs) runs and delivers frames in order."""
+    import json
+    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_bench")
+    assert os.path.exists(exe), "build first: __graft_entry__.build()"
+    for layout, mode in (("16", "push"), ("12", "stage"), ("20", "push")):
+        r = subprocess.run([exe, "-waters", "2000", "-batch", "8", "-batches", "3", "-warmup", "2", "-ring", "16",
+                            "-layout", layout, "-mode", mode], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["in_frame_order"] and d["timed_frames"] == 24 and d["e2e_cpp"] > 0 and d["find_pairs"] > 0
+        assert d["stats_rows_reduced"] == 40 and d["layout_bytes_per_edge"] == int(layout)

@@ -182,3 +182,17 @@ def test_gromacs_module_passes_the_front_end_against_the_api_shim():
     assert r.returncode == 0 and "error" not in r.stderr, r.stderr
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only"] + inc + [src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_host_energy_header_matches_the_oracle_bit_for_bit(tmp_path, oracle):
+    """include/wn_energy.h (energy on demand for the 12-byte layout) == the oracle's computeEnergy restatement,
+    float-rounded, on a 16k-point (r, cos) grid: both follow the reference's pow() arithmetic
+    (src/waternetwork.cpp:12-66).  The oracle is linked here as the checker only."""
+    import subprocess
+    exe = str(tmp_path / "t_energy")
+    src = os.path.join(ROOT, "tests", "c", "test_energy_header.c")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L" + os.path.join(ROOT, "oracle"), "-lwn_oracle", "-lm",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("0 of "), r.stdout + r.stderr
