@@ -379,11 +379,12 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         if (attempt == 0) WN_CK(cudaEventRecord(ctx->ev[2], st));
         wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_total, ctx->d_frame_maxrow,
                           ctx->d_scan_part, st);
+        /* the two pass scalars (edge total, longest row) are written by the kernel straight into pinned host
+         * memory (UVA: the pointer is valid on the device): a cudaMemcpyAsync here would queue on the D2H copy
+         * engine behind the previous pass's result copy and stall this stream until that copy ends */
         wn_launch_frameoff(ctx->d_frame_total, ctx->d_frame_maxrow, nf, *edge_base, ctx->d_frame_off + f0,
-                           ctx->d_pass_info, st);
+                           ctx->h_scalars, st);
         ctx->tm.launches += small_box ? 5 : 6;   /* [home-block prefix] fused search, row scan x3, frame offsets */
-        WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_pass_info, 2 * sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, st));
         WN_CK(cudaStreamSynchronize(st));
         end_off = ctx->h_scalars[0];
         const unsigned long long max_row = ctx->h_scalars[1];

@@ -3,6 +3,7 @@
 #include "hydrogen-bond-edges.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <stdexcept>
@@ -196,6 +197,7 @@ struct FrameBatcher::Lane {
     std::vector<int32_t> sub_sites[2];
     std::vector<float> b3;                     // rectangular box lengths of a site-list batch
     std::future<HydrogenBondBatch> fut;
+    double seconds[2] = {0.0, 0.0};            // wall time of the batch of each staging buffer inside the C ABI
     int flying = -1;                           // staging buffer of the batch in flight, -1: none
     bool have_ready = false;                   // a finished batch waits for delivery
     HydrogenBondBatch ready;
@@ -334,6 +336,7 @@ void FrameBatcher::deliverOldest()
     l.have_ready = false;
     const HydrogenBondBatch& b = l.ready;
     const int buf = l.ready_buf;
+    batch_seconds_.push_back(l.seconds[buf]);
     const size_t esz = b.layout == WN_LAYOUT_CSR16 ? sizeof(wn_edge16) : b.layout == WN_LAYOUT_CSR12 ? sizeof(wn_edge12)
                                                                                                     : sizeof(wn_edge);
     for (int f = 0; f < b.n_frames; ++f) {
@@ -389,9 +392,13 @@ void FrameBatcher::submit()
     HydrogenBondEdges* eng = l.eng;
     const bool async = pipelined_ && !batch_hook_;
     if (async) {
-        l.fut = std::async(std::launch::async, [eng, a]() {
+        double* secs = &l.seconds[buf];
+        l.fut = std::async(std::launch::async, [eng, a, secs]() {
             eng->bindThreadToDevice();
-            return eng->calculateEx(a);
+            const auto t0 = std::chrono::steady_clock::now();
+            HydrogenBondBatch r = eng->calculateEx(a);
+            *secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            return r;
         });
         l.flying = buf;
         pending_.push_back(cur_);
@@ -400,7 +407,9 @@ void FrameBatcher::submit()
         while (pending_.size() > lanes_.size() || (!pending_.empty() && lanes_[pending_.front()]->have_ready)) deliverOldest();
     } else {
         while (!pending_.empty()) deliverOldest();
+        const auto t0 = std::chrono::steady_clock::now();
         l.ready = eng->calculateEx(a);
+        l.seconds[buf] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         l.ready_buf = buf;
         l.have_ready = true;
         if (batch_hook_) batch_hook_(l.frnr[buf], l.ready);
@@ -410,22 +419,35 @@ void FrameBatcher::submit()
     cur_ = (cur_ + 1) % (int)lanes_.size();
 }
 
-void FrameBatcher::finish()
+void FrameBatcher::flush()
 {
     submit();                                   // the partial tail batch, if any
     while (!pending_.empty()) deliverOldest();
-    // statistics rows of the whole run: per GPU a zero-padded table, summed with NCCL when there are several
+}
+
+void FrameBatcher::finish()
+{
+    flush();
+    // statistics rows of the whole run: per GPU a zero-padded table (its own rows only), summed with NCCL
+    // when there are several GPUs -- every row is owned by exactly one GPU, so the sum is exact
     const size_t F = (size_t)frames_pushed_;
-    for (Lane* l : lanes_) l->table.resize(F, wn_frame_stats{0, 0, 0, 0, 0});
     if (lanes_.size() > 1 && F > 0) {
+        std::vector<std::vector<wn_frame_stats> > tmp(lanes_.size());
+        for (size_t g = 0; g < lanes_.size(); ++g) {
+            tmp[g] = lanes_[g]->table;
+            tmp[g].resize(F, wn_frame_stats{0, 0, 0, 0, 0});
+        }
         std::vector<std::thread> ts;
         std::vector<std::exception_ptr> errs(lanes_.size());
         for (size_t g = 0; g < lanes_.size(); ++g)
             ts.emplace_back([&, g]() {
-                try { lanes_[g]->eng->statsReduce(lanes_[g]->table.data(), (int64_t)F); } catch (...) { errs[g] = std::current_exception(); }
+                try { lanes_[g]->eng->statsReduce(tmp[g].data(), (int64_t)F); } catch (...) { errs[g] = std::current_exception(); }
             });
         for (auto& t : ts) t.join();
         for (auto& e : errs) if (e) std::rethrow_exception(e);
+        reduced_.swap(tmp[0]);
+    } else {
+        reduced_ = lanes_[0]->table;
+        reduced_.resize(F, wn_frame_stats{0, 0, 0, 0, 0});
     }
-    reduced_ = lanes_[0]->table;
 }

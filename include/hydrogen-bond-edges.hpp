@@ -170,6 +170,8 @@ public:
     // zero-copy producers: where the next frame's natoms*3 floats go (pinned memory); then commit(frnr)
     float* stage();
     void commit(int frnr);
+    // submit the partial batch and deliver everything in flight (the pipeline is empty afterwards)
+    void flush();
     void finish();
     uint64_t framesDone() const { return frames_done_; }
     // Optional: called once per processed batch, before the per-frame sink calls, while the batch is
@@ -182,6 +184,8 @@ public:
     // the per-GPU zero-padded tables (wn_stats_reduce), with one GPU the rows as delivered.
     const std::vector<wn_frame_stats>& reducedStats() const { return reduced_; }
     int gpus() const { return (int)lanes_.size(); }
+    // wall-clock seconds every batch spent inside the C ABI call (H2D + kernels + D2H), in delivery order
+    const std::vector<double>& batchSeconds() const { return batch_seconds_; }
 
 private:
     struct Lane;
@@ -198,6 +202,7 @@ private:
     bool pipelined_;
     uint64_t frames_done_, frames_pushed_;
     std::vector<wn_frame_stats> reduced_;
+    std::vector<double> batch_seconds_;
 };
 
 #endif
