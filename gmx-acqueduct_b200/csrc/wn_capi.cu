@@ -121,6 +121,12 @@ struct wn_ctx {
     int32_t* h_pairs = nullptr;
     size_t h_pairs_cap = 0;
     unsigned long long* d_pair_ties = nullptr;
+    /* cell-list pair path */
+    int find_mode = 0;                       /* WN_FIND_AUTO / WN_FIND_ALLPAIRS / WN_FIND_CELLS */
+    int last_find_cells = 0;                 /* the last wn_find_pairs* call ran the cell-list sweep */
+    int* d_cp_cell = nullptr;    size_t cp_cell_cap = 0;
+    int* d_cp_site_cell = nullptr; int* d_cp_site_rank = nullptr; double4* d_cp_srec = nullptr;
+    size_t cp_site_cap = 0;
 
     std::vector<WnGrid> h_grid;     /* periodic grids of the current pass (host-built) */
     int layout = 0;                          /* result layout of the current / last call */
@@ -661,7 +667,8 @@ void wn_destroy(wn_ctx* ctx)
                    ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce,
                    ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags,
-                   ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx, ctx->d_cc_kept, ctx->d_cc_stats, ctx->d_eside};
+                   ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx, ctx->d_cc_kept, ctx->d_cc_stats, ctx->d_eside,
+                   ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_cp_site_rank, ctx->d_cp_srec};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ctx->hset[0].edges, ctx->hset[0].frame_off, ctx->hset[0].stats, ctx->hset[0].counters, ctx->hset[0].row_off,
                     ctx->hset[1].edges, ctx->hset[1].frame_off, ctx->hset[1].stats, ctx->hset[1].counters, ctx->hset[1].row_off,
@@ -1021,6 +1028,57 @@ int wn_find_pairs_box9(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_
     return rc;
 }
 
+/* Grid of the cell-list pair search.  The pair test 10*d2 < 42.25 accepts distances below 2.0555 nm (the unit
+ * slip of src/brute-find-pairs.cpp:19-20); cells of at least half that, so partners sit within two cells.
+ * Open boundary: cubic cells over the bounding box of the finite points.  Periodic: the box divided into
+ * floor(L/edge) cells per dimension, at least 5 (otherwise the 5 neighbour cells alias: all-pairs kernel). */
+static bool cellpair_grid(const double* xyz, int n, const WnPairBox& pb, WnCellPairGrid* g)
+{
+    const double edge_min = 0.5 * std::sqrt(4.225) * (1.0 + 1.0e-9);
+    const double cell_budget = std::max(4096.0, 2.0 * (double)n);
+    memset(g, 0, sizeof *g);
+    g->pbc = pb.pbc;
+    if (pb.pbc == 1) {
+        double e = edge_min;
+        for (;;) {
+            double cells = 1.0;
+            for (int c = 0; c < 3; ++c) {
+                const double q = std::floor(pb.L[c] / e);
+                if (!(q >= 5.0)) return false;
+                g->n[c] = (int)std::min(q, 1.0e6);
+                cells *= (double)g->n[c];
+            }
+            if (cells <= cell_budget) break;
+            e *= 1.26;
+        }
+        for (int c = 0; c < 3; ++c) {
+            g->o[c] = 0.0; g->L[c] = pb.L[c]; g->invL[c] = pb.invL[c];
+            g->inv[c] = (double)g->n[c] / pb.L[c];
+        }
+    } else {
+        double lo[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL}, hi[3] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
+        for (size_t k = 0; k < (size_t)n; ++k)
+            for (int c = 0; c < 3; ++c) {
+                const double v = xyz[3 * k + c];
+                if (std::isfinite(v)) { lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v); }
+            }
+        double e = edge_min;
+        for (;;) {
+            double cells = 1.0;
+            for (int c = 0; c < 3; ++c) {
+                const double ext = hi[c] >= lo[c] ? hi[c] - lo[c] : 0.0;
+                g->n[c] = (int)std::min(std::floor(ext / e) + 1.0, 1.0e6);
+                cells *= (double)g->n[c];
+            }
+            if (cells <= cell_budget) break;
+            e *= 1.26;
+        }
+        for (int c = 0; c < 3; ++c) { g->o[c] = hi[c] >= lo[c] ? lo[c] : 0.0; g->inv[c] = 1.0 / e; }
+    }
+    g->ncells = g->n[0] * g->n[1] * g->n[2];
+    return true;
+}
+
 static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit, const float* box3,
                            const int32_t** pairs, uint64_t* m, wn_tie_report* ties)
 {
@@ -1063,16 +1121,42 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
         if ((rc = dev_realloc_plain(ctx, &ctx->d_prow_off, n_cnt + 1))) return rc;
         ctx->prow_cap = n_cnt + 1;
     }
+    /* cell-list sweep (O(N)) or the exact all-pairs tile kernel (tiny inputs, triclinic boxes, periodic boxes
+     * under 5 cells of half the cutoff in a dimension) */
+    WnCellPairGrid cg;
+    bool cells = ctx->find_mode != WN_FIND_ALLPAIRS && pb.pbc != 2 && wn_cellpairs_supported(n) &&
+                 (ctx->find_mode == WN_FIND_CELLS || n >= 1024);
+    if (cells) cells = cellpair_grid(xyz, n, pb, &cg);
+    ctx->last_find_cells = cells ? 1 : 0;
+    if (cells) {
+        if ((rc = dev_ensure(ctx, &ctx->d_cp_cell, &ctx->cp_cell_cap, (size_t)cg.ncells + 1))) return rc;
+        if ((size_t)n > ctx->cp_site_cap) {
+            WN_CK(cudaStreamSynchronize(st));
+            if ((rc = dev_realloc_plain(ctx, &ctx->d_cp_site_cell, (size_t)n))) return rc;
+            if ((rc = dev_realloc_plain(ctx, &ctx->d_cp_site_rank, (size_t)n))) return rc;
+            if ((rc = dev_realloc_plain(ctx, &ctx->d_cp_srec, (size_t)n))) return rc;
+            ctx->cp_site_cap = (size_t)n;
+        }
+    }
+    const size_t n_tot = cells ? (size_t)n : n_cnt;             /* where the scan leaves the pair total */
     ctx->tm = wn_timings{};
     WN_CK(cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     WN_CK(cudaMemsetAsync(ctx->d_pair_ties, 0, 2 * sizeof(unsigned long long), st));
     WN_CK(cudaEventRecord(ctx->ev[0], st));
-    wn_launch_pairs_count(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_cnt, ctx->d_pair_ties, st);
-    wn_launch_pairs_scan(ctx->d_prow_cnt, n, ctx->d_prow_off, st);
+    if (cells) {
+        wn_launch_cellpairs_bin(ctx->d_xyz, n, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_cp_site_rank, ctx->d_cp_srec, st);
+        wn_launch_cellpairs_count(ctx->d_cp_srec, n, first_limit, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_prow_cnt,
+                                  ctx->d_pair_ties, st);
+        wn_launch_scan64(ctx->d_prow_cnt, n, ctx->d_prow_off, st);
+        ctx->tm.launches = 5;
+    } else {
+        wn_launch_pairs_count(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_cnt, ctx->d_pair_ties, st);
+        wn_launch_pairs_scan(ctx->d_prow_cnt, n, ctx->d_prow_off, st);
+        ctx->tm.launches = 2;
+    }
     WN_CK(cudaGetLastError());
     WN_CK(cudaEventRecord(ctx->ev[1], st));
-    ctx->tm.launches = 2;
-    WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_prow_off + n_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_prow_off + n_tot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     WN_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_pair_ties, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     WN_CK(cudaStreamSynchronize(st));
     const unsigned long long total = ctx->h_scalars[0];
@@ -1084,7 +1168,11 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
     ctx->tm.total_ms = ms;
     if (total) {
         WN_CK(cudaEventRecord(ctx->ev[2], st));
-        wn_launch_pairs_fill(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_off, ctx->d_pairs, st);
+        if (cells)
+            wn_launch_cellpairs_fill(ctx->d_cp_srec, n, first_limit, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_prow_off,
+                                     ctx->d_pairs, st);
+        else
+            wn_launch_pairs_fill(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_off, ctx->d_pairs, st);
         WN_CK(cudaGetLastError());
         WN_CK(cudaEventRecord(ctx->ev[3], st));
         WN_CK(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs, (size_t)total * 2 * sizeof(int32_t),
@@ -1095,13 +1183,24 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
         ctx->tm.total_ms += ms;
         cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
         ctx->tm.d2h_ms = ms;
-        ctx->tm.launches = 3;
+        ctx->tm.launches += 1;
     }
     ctx->tm.passes = 1;
     *pairs = ctx->h_pairs;
     *m = total;
     return WN_OK;
 }
+
+int wn_set_find_mode(wn_ctx* ctx, int32_t mode)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (mode != WN_FIND_AUTO && mode != WN_FIND_ALLPAIRS && mode != WN_FIND_CELLS)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_set_find_mode: unknown mode");
+    ctx->find_mode = mode;
+    return WN_OK;
+}
+
+int wn_last_find_used_cells(const wn_ctx* ctx) { return ctx ? ctx->last_find_cells : 0; }
 
 /* ---- plumbing ---- */
 int wn_dev_alloc(wn_ctx* ctx, size_t bytes, void** dev_ptr)

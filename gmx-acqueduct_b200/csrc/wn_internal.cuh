@@ -175,6 +175,25 @@ int wn_pairs_segments(int n);       /* column segments per row: counts/offsets a
 void wn_launch_pairs_fill(const double* xyz, int n, int first_limit, WnPairBox box,
                           const unsigned long long* row_off, int32_t* pairs, cudaStream_t st);
 
+/* cell-list pair path (wn_kernels_cellpairs.cu): CudaFindPairs::find in O(N) */
+struct WnCellPairGrid {
+    double o[3];         /* grid origin (open: minimum corner of the finite sites; periodic: 0) */
+    double inv[3];       /* 1 / cell edge                                                        */
+    double L[3], invL[3];/* periodic box                                                         */
+    int n[3];            /* cells per dimension                                                  */
+    int ncells;
+    int pbc;             /* 0 open, 1 rectangular periodic                                       */
+};
+int wn_cellpairs_supported(int n);     /* the per-warp bitmap over j fits in shared memory */
+void wn_launch_cellpairs_bin(const double* xyz, int n, const WnCellPairGrid& g, int* cell_cnt, int* site_cell,
+                             int* site_rank, double4* srec, cudaStream_t st);
+void wn_launch_cellpairs_count(const double4* srec, int n, int first_limit, const WnCellPairGrid& g, const int* cell_start,
+                               const int* site_cell, uint32_t* row_cnt, unsigned long long* ties, cudaStream_t st);
+void wn_launch_cellpairs_fill(const double4* srec, int n, int first_limit, const WnCellPairGrid& g, const int* cell_start,
+                              const int* site_cell, const unsigned long long* row_off, int32_t* pairs, cudaStream_t st);
+/* exclusive 64-bit scan of `len` 32-bit counts (+ total at [len]) */
+void wn_launch_scan64(const uint32_t* cnt, int len, unsigned long long* off, cudaStream_t st);
+
 /* synthetic frames (wn_synth.cu, compiled with -fmad=false) */
 void wn_launch_synth(int n_waters, uint64_t seed, int model, int64_t frame0, int n_frames,
                      float* frames, cudaStream_t st);

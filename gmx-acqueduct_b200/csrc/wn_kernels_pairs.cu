@@ -200,6 +200,11 @@ void wn_launch_pairs_scan(const uint32_t* row_cnt, int n, unsigned long long* ro
     wn_k_pairs_scan<<<1, 1024, 0, st>>>(row_cnt, n * wn_pairs_segments(n), row_off);
 }
 
+void wn_launch_scan64(const uint32_t* cnt, int len, unsigned long long* off, cudaStream_t st)
+{
+    wn_k_pairs_scan<<<1, 1024, 0, st>>>(cnt, len, off);
+}
+
 void wn_launch_pairs_fill(const double* xyz, int n, int first_limit, WnPairBox box,
                           const unsigned long long* row_off, int32_t* pairs, cudaStream_t st)
 {

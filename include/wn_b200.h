@@ -170,6 +170,17 @@ int wn_find_pairs_pbc(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_l
 int wn_find_pairs_box9(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
                        const float box9[9], const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
 
+/* How wn_find_pairs* searches.  WN_FIND_AUTO (default): the cell-list sweep (cells of half the 2.0555 nm
+ * cutoff, 5x5x5 neighbourhood, exact fp64 test on every candidate, O(N)) for n >= 1024 points on open and
+ * rectangular periodic boxes of at least 5 cells per dimension; the exact all-pairs tile kernel otherwise
+ * (triclinic boxes, small periodic boxes, tiny inputs).  Both give the same pair list bit for bit; the other two
+ * modes force one of them where it applies (tests).  wn_last_find_used_cells: which one the last call ran. */
+#define WN_FIND_AUTO     0
+#define WN_FIND_ALLPAIRS 1
+#define WN_FIND_CELLS    2
+int wn_set_find_mode(wn_ctx* ctx, int32_t mode);
+int wn_last_find_used_cells(const wn_ctx* ctx);
+
 /* ---- site tables (src/waternetwork.cpp:538-577) --------------------------
  * site_atom[n_sites]: atom index (into a frame) of each site.
  * h_atom[n_sites*hmax]: atom indices of its hydrogen list in list order, -1 padded.

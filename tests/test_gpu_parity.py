@@ -405,6 +405,90 @@ def test_find_pairs_full_size_rows(ctx, oracle):
     assert np.array_equal(lim, want)
 
 
+def test_cell_list_find_pairs_matches_brute_and_all_pairs_kernel(ctx, oracle):
+    """CudaFindPairs' cell-list sweep (cells of half the 2.0555 nm cutoff) == BruteFindPairs::find
+    (src/brute-find-pairs.cpp:19-30) == the all-pairs tile kernel, bit for bit, open and periodic."""
+    rng = np.random.default_rng(77)
+    try:
+        # forced on small inputs: one cell, a few cells, sparse points over a large extent, non-finite points
+        cases = [np.zeros((5, 3)), rng.uniform(0, 1.0, size=(40, 3)), rng.uniform(-3, 9.0, size=(900, 3)),
+                 rng.uniform(0, 400.0, size=(600, 3)), rng.normal(0, 2.0, size=(1200, 3))]
+        bad = rng.uniform(0, 6.0, size=(500, 3))
+        bad[7] = np.nan; bad[30, 1] = np.inf; bad[31, 2] = -np.inf
+        cases.append(bad)
+        for xyz in cases:
+            xyz = xyz.astype(np.float32).astype(np.float64)
+            to = oracle.Ties()
+            want = oracle.brute_find_pairs(xyz, ties=to)
+            ctx.set_find_mode(2)
+            got, ties = ctx.find_pairs(xyz)
+            assert ctx.last_find_used_cells()
+            assert np.array_equal(got, want)
+            assert ties["pair_cutoff_equal"] == to.pair_cutoff_equal and ties["pair_cutoff_near"] == to.pair_cutoff_near
+            lim, _ = ctx.find_pairs(xyz, first_limit=17)
+            assert np.array_equal(lim, oracle.brute_find_pairs(xyz, first_limit=17))
+            ctx.set_find_mode(1)
+            ap, _ = ctx.find_pairs(xyz)
+            assert not ctx.last_find_used_cells() and np.array_equal(ap, want)
+        # cutoff ties: 10*d2 == 42.25 is not a pair (strict <), and the tie report counts it
+        tie_xyz = np.array([[0, 0, 0], [0.5, 1.5, 1.3], [0, 0, 2.0554804791094465], [2.0554804791094470, 0, 0]])
+        to = oracle.Ties()
+        want_t = oracle.brute_find_pairs(tie_xyz, ties=to)
+        ctx.set_find_mode(2)
+        got_t, ties_t = ctx.find_pairs(tie_xyz)
+        assert np.array_equal(got_t, want_t)
+        assert ties_t["pair_cutoff_equal"] == to.pair_cutoff_equal and ties_t["pair_cutoff_near"] == to.pair_cutoff_near
+        # periodic: boxes of >= 5 cells take the sweep, smaller ones fall back; unwrapped coordinates
+        for n, L in ((1500, (5.3, 5.2, 6.1)), (2500, (7.0, 5.2, 11.0)), (300, (1.9, 2.2, 3.0))):
+            xyz = (rng.uniform(-1, 2, size=(n, 3)) * np.array(L)).astype(np.float32).astype(np.float64)
+            want = oracle.brute_find_pairs_pbc(xyz, L)
+            ctx.set_find_mode(2)
+            got, _ = ctx.find_pairs(xyz, box=L)
+            assert ctx.last_find_used_cells() == (min(L) > 5.14)
+            assert np.array_equal(got, want)
+            lim, _ = ctx.find_pairs(xyz, first_limit=40, box=L)
+            assert np.array_equal(lim, oracle.brute_find_pairs_pbc(xyz, L, first_limit=40))
+        # the 100k-atom box: automatic mode takes the sweep; whole list equal to the all-pairs kernel's
+        n = 33333
+        xyz = oracle.synth_frames(oracle.synth_box(n), 0, 1)[0][::3].astype(np.float64)
+        ctx.set_find_mode(0)
+        got, _ = ctx.find_pairs(xyz)
+        assert ctx.last_find_used_cells()
+        ctx.set_find_mode(1)
+        ap, _ = ctx.find_pairs(xyz)
+        assert np.array_equal(got, ap)
+        L = (10.0, 10.0, 10.0)
+        ctx.set_find_mode(0)
+        got, _ = ctx.find_pairs(xyz, box=L)
+        assert ctx.last_find_used_cells()
+        ctx.set_find_mode(1)
+        ap, _ = ctx.find_pairs(xyz, box=L)
+        assert np.array_equal(got, ap)
+    finally:
+        ctx.set_find_mode(0)
+
+
+def test_cell_list_find_pairs_one_million_atoms(ctx, oracle):
+    """333,333 sites (BASELINE configs[3]): the sweep is O(N); order + scattered rows against the oracle."""
+    n = 333333
+    xyz = oracle.synth_frames(oracle.synth_box(n), 0, 1)[0][::3].astype(np.float64)
+    rows = np.unique(np.random.default_rng(3).integers(0, n, size=24))
+    got, _ = ctx.find_pairs(xyz)
+    assert ctx.last_find_used_cells()
+    key = got[:, 0].astype(np.int64) * n + got[:, 1]
+    assert np.all(np.diff(key) > 0) and np.all(got[:, 0] < got[:, 1])
+    # brute rows of the oracle: row i = pairs (i, j > i); the oracle's loop with first_limit is a prefix, so
+    # evaluate the scattered rows by permuting each one to the front
+    for i in rows:
+        d = xyz - xyz[i]
+        lhs = 10.0 * ((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])
+        want_j = np.nonzero((lhs < 42.25) & (np.arange(n) > i))[0]
+        a, b = np.searchsorted(got[:, 0], [i, i + 1])
+        assert np.array_equal(got[a:b, 1], want_j)
+    want = oracle.brute_find_pairs(xyz, first_limit=8)
+    assert np.array_equal(got[got[:, 0] < 8], want)
+
+
 # ------------------------------------------------------------------ periodic boxes
 def oracle_frames_pbc(oracle, frames, boxes, site_atom, h_atom, site_type, first_limit=None):
     edges, stats, evals = [], [], 0
