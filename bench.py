@@ -285,7 +285,7 @@ def run_own(args):
     n_waters, natoms = args.waters, 3 * args.waters
     F, K, W = args.frames_per_step, args.steps, args.warmup
     ctx.set_water_sites(n_waters)
-    ctx.set_batch_frames(F)
+    ctx.set_batch_frames(args.pass_frames)      # 0: the library's own pass schedule inside a step
 
     if world > 1:
         ids = [ctx.nccl_unique_id() if rank == 0 else None]
@@ -325,18 +325,63 @@ def run_own(args):
         tm = ctx.timings()
         launches += tm["launches"]; passes += tm["passes"]
         edges_ms += tm["edges_ms"]; bin_ms += tm["bin_ms"]; finish_ms += tm["finish_ms"]
-    dev_ms = ctx.timer_stop()
-    t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1)
-    barrier()
-    # per-frame statistics of the last step -> NCCL sum over ranks (the only collective)
+    # per-frame statistics of the last step -> NCCL sum over ranks: the path's only collective, INSIDE the timed
+    # region (once per run, as in a trajectory job: the .xvg tables are written at the end)
+    stats_reduce = None
     if world > 1:
+        t_r0 = time.perf_counter()
         st = np.zeros(world * F, capi.STATS_DTYPE)
         mine = np.zeros(F, capi.STATS_DTYPE)
         ctx.d2h(mine, out["stats_dev"])
         st[rank * F:(rank + 1) * F] = mine
         ctx.stats_reduce(st)
-        assert np.all(st["num_sites"] == n_waters)
+        t_r1 = time.perf_counter()
+    dev_ms = ctx.timer_stop()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    barrier()
+    if world > 1:
+        # every row is owned by exactly one rank, so the sum must return each rank's rows bit for bit
+        own = st[rank * F:(rank + 1) * F]
+        for name in capi.STATS_DTYPE.names:
+            if not np.array_equal(own[name].view(np.uint64), mine[name].view(np.uint64)):
+                raise SystemExit("bench: wn_stats_reduce changed this rank's own rows (%s)" % name)
+        if not (np.all(st["num_sites"] == n_waters) and np.all(st["num_edges"] > 0) and np.all(st["sum_energy"] < 0)):
+            raise SystemExit("bench: reduced statistics table has empty rows")
+        # cross-rank check: all ranks hold the same table
+        digest = [float(st["num_edges"].sum()), float(st["sum_energy"].sum())]
+        alld = [None] * world
+        dist.all_gather_object(alld, digest)
+        if any(d != alld[0] for d in alld):
+            raise SystemExit("bench: ranks disagree on the reduced statistics table")
+        stats_reduce = {"rows": int(world * F), "bytes": int(st.nbytes), "ms_incl_d2h": (t_r1 - t_r0) * 1e3,
+                        "inside_timed_region": True, "own_rows_bit_exact": True, "ranks_agree": True}
+
+    # ---- sustained leg: the same step repeated for >= 1 s (>= 250 steps cycling over the resident frames: every
+    # step still reads 300 MB of distinct input), with its own clock samples
+    sustained = None
+    if not args.no_sustained:
+        K2 = max(250, int(1.2e3 / max(dev_ms / K, 1e-3)))
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+        time.sleep(0.25)
+        barrier()
+        ts0 = time.perf_counter()
+        ctx.timer_start()
+        for s in range(K2):
+            ctx.hbond_batch_dev(frames_dev + (s % (W + K)) * F * frame_bytes, F, natoms)
+        sus_ms = ctx.timer_stop()
+        ts1 = time.perf_counter()
+        clocks2 = sampler2.stop(ts0, ts1)
+        barrier()
+        sus_ms_max = sus_ms
+        if dist is not None:
+            import torch
+            tt = torch.tensor([sus_ms_max], dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sus_ms_max = float(tt[0])
+        sustained = {"value": K2 * F * world / (sus_ms_max * 1e-3), "unit": "frames/s", "steps": K2,
+                     "seconds": sus_ms_max * 1e-3, "ms_per_step": sus_ms_max / K2, "clocks": clocks2}
 
     # ---- periodic leg (north-star extension): same frames, rectangular PBC with the box of
     # the generator; fewer steps, reported beside the headline (the reference arm is open boundary)
@@ -492,6 +537,36 @@ def run_own(args):
     e2e_ms_max = allmax(max(e2e_ms, e2e_wall * 1e3))
     e2e_fps = frames_all / (e2e_ms_max * 1e-3)
 
+    # ---- PCIe ceiling: plain pinned copies on every rank AT THE SAME TIME (shared uplinks show here), and what
+    # the e2e leg's D2H volume would take at that rate
+    barrier()
+    h2d_gbs, d2h_gbs = ctx.pcie_probe(256 << 20, 4)
+    barrier()
+    d2h_all = allsum(d2h_gbs)
+    d2h_min = -allmax(-d2h_gbs)
+    pcie = {"h2d_gbs_this_rank": h2d_gbs, "d2h_gbs_this_rank": d2h_gbs, "pcie_d2h_ceiling_gbs": d2h_all,
+            "d2h_gbs_slowest_rank": d2h_min,
+            "e2e_ceiling_frames_per_s": world * F / ((d2h_bytes / K) / (d2h_min * 1e9)) if d2h_min > 0 else None,
+            "e2e_frac_of_ceiling": (e2e_fps / (world * F / ((d2h_bytes / K) / (d2h_min * 1e9)))) if d2h_min > 0 else None,
+            "note": "ceiling = every rank moving its D2H bytes per step at the slowest rank's concurrent pinned-copy rate"}
+
+    # ---- the C++ drop-in itself: FrameBatcher (include/hydrogen-bond-edges.hpp) fed frame by frame, its sink called
+    # per frame -- the binary a maintainer's analyzeFrame patch would behave like (host/wn-bench.cpp)
+    e2e_cpp = None
+    if rank == 0 and world == 1 and not args.no_cpp:
+        exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_bench")
+        if os.path.exists(exe):
+            ctx.set_batch_frames(0)
+            try:
+                pr = subprocess.run([exe, "-waters", str(n_waters), "-batch", str(F), "-batches", "12", "-warmup", "2",
+                                     "-layout", "16", "-find", "0"], capture_output=True, text=True, timeout=600)
+                if pr.returncode == 0 and pr.stdout.strip():
+                    e2e_cpp = json.loads(pr.stdout.strip().splitlines()[-1])
+                else:
+                    e2e_cpp = {"error": (pr.stderr or "no output")[-300:]}
+            except Exception as exc:        # noqa: BLE001 -- the leg is informative, not the headline
+                e2e_cpp = {"error": str(exc)[-300:]}
+
     # ---- host frames in -> component labels out: the edge list never crosses PCIe (results_on_device),
     # only 4 bytes per site and 16 per frame come back.  A different result than the headline e2e (labels and
     # component statistics instead of the edge list), reported beside it.
@@ -629,6 +704,10 @@ def run_own(args):
                     "frames_per_internal_pass": e2e_pass,
                     "result_layout": "WN_LAYOUT_CSR16 (16 B/edge + 4 B/site row offsets; wn_edge AoS is 20 B/edge)"},
             "gpu_launches": launches,
+            "sustained": sustained,
+            "stats_reduce": stats_reduce,
+            "pcie": pcie,
+            "e2e_cpp": e2e_cpp,
             "clocks": clocks,
             "per_rank": per_rank if world > 1 else None,
             "roofline": roofline,
@@ -660,6 +739,10 @@ def main():
     ap.add_argument("--waters", type=int, default=N_WATERS)
     ap.add_argument("--frames-per-step", type=int, default=250)
     ap.add_argument("--e2e-pass", type=int, default=0, help="frames per internal pass of the e2e leg (0: library default)")
+    ap.add_argument("--pass-frames", type=int, default=0,
+                    help="frames per internal pass of the device-resident leg (0: library default, a quarter of ~8M site-frames)")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 1 s sustained leg")
+    ap.add_argument("--no-cpp", action="store_true", help="skip the C++ drop-in leg (wn_bench)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pbc", action="store_true", help="skip the periodic-boundary leg")
     ap.add_argument("--no-find", action="store_true", help="skip the standalone CudaFindPairs::find leg")

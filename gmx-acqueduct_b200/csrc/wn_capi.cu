@@ -12,6 +12,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>      /* header-only: ranges cost nothing unless a profiler injects a collector */
 #include <sched.h>
 #include <ctype.h>
 
@@ -47,18 +48,31 @@ struct wn_ctx {
     float4* d_spos = nullptr;
     uint32_t* d_smeta = nullptr;
     double* d_sdh = nullptr;
-    uint32_t* d_row_cnt = nullptr;
     uint32_t* d_row_off = nullptr;          /* call-wide [n_frames][n_sites] (CSR row offsets) */
     size_t row_off_cap = 0;
-    unsigned long long* d_frame_total = nullptr;
-    WnFrameCounters* d_counters = nullptr;
-    uint32_t* d_frame_maxrow = nullptr;
     int* d_blk_prefix = nullptr;             /* [cap_frames + 2]: home-block prefix per frame, then the work counter */
     uint32_t* d_scan_part = nullptr;     /* chunk sums / maxima of the three-phase scans, bbox keys */
-    unsigned long long* d_pass_info = nullptr;
-    double* d_block_sums = nullptr;
-    uint32_t* d_rowbuf = nullptr;
-    size_t rowbuf_cap = 0;          /* 32-bit words */
+    /* Buffers a pass's front (staging + fused search + row scan, stream st) hands to its back (ordered copy +
+     * statistics, stream st_fin).  Two sets: the back of pass k runs under the front of pass k+1. */
+    struct PassSet {
+        uint32_t* row_cnt = nullptr;
+        unsigned long long* frame_total = nullptr;
+        WnFrameCounters* counters = nullptr;
+        uint32_t* frame_maxrow = nullptr;
+        double* block_sums = nullptr;
+        uint32_t* rowbuf = nullptr;
+        size_t rowbuf_cap = 0;          /* 32-bit words */
+        int* sub_off = nullptr;  size_t sub_off_cap = 0;        /* per-frame site lists of the pass (device) */
+        int* sub_sites = nullptr;  size_t sub_sites_cap = 0;
+        WnGrid* h_grid = nullptr;  size_t h_grid_cap = 0;        /* pinned: host-built periodic grids of the pass */
+        cudaEvent_t back_done = nullptr;                         /* the back that last read this set has finished */
+        bool used = false;
+    } pset[2];
+    cudaStream_t st_fin = nullptr;
+    unsigned long long* d_chain = nullptr;    /* [1] edges of the call so far (advanced by wn_k_frameoff) */
+    unsigned long long* h_pass = nullptr;     /* pinned [2 * passes]: {edge total after the pass, longest row} */
+    size_t h_pass_cap = 0;
+    std::vector<cudaEvent_t> ev_pass;         /* 6 timing events per pass */
     int row_cap = 32;               /* slots per row; grows (sticky) when a row overflows */
     float* d_stage[2] = {nullptr, nullptr};   /* host variant: frames of one pass, ping-pong */
     size_t stage_cap[2] = {0, 0};
@@ -128,16 +142,11 @@ struct wn_ctx {
     int* d_cp_site_cell = nullptr; int* d_cp_site_rank = nullptr; double4* d_cp_srec = nullptr;
     size_t cp_site_cap = 0;
 
-    std::vector<WnGrid> h_grid;     /* periodic grids of the current pass (host-built) */
     int layout = 0;                          /* result layout of the current / last call */
     bool keep_dev = false;                   /* current call: host frames in, results stay on the device */
     int box_stride = 3;                      /* 3: (Lx,Ly,Lz) per frame; 9: triclinic matrices */
     const int64_t* sub_off_host = nullptr;   /* per-frame site subsets of the current call (host) */
     const int32_t* sub_sites_host = nullptr;
-    int* d_sub_off = nullptr;
-    size_t sub_off_cap = 0;
-    int* d_sub_sites = nullptr;
-    size_t sub_sites_cap = 0;
     std::vector<int> h_sub_off;
 
     /* timing */
@@ -153,6 +162,12 @@ struct wn_ctx {
 };
 
 namespace {
+
+/* NVTX range over a scope (stage markers for nsys / ncu --nvtx) */
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(wn_ctx* c, int code, const std::string& msg)
 {
@@ -182,9 +197,10 @@ int dev_ensure(wn_ctx* ctx, T** p, size_t* cap, size_t need, bool preserve = fal
     if (ncap == 0) ncap = 1;
     T* np = nullptr;
     WN_CK(cudaMalloc((void**)&np, ncap * sizeof(T)));
+    if (*p) WN_CK(cudaDeviceSynchronize());                             /* rare: kernels and copies of other streams may be in flight */
     if (preserve && *p && used)
         WN_CK(cudaMemcpyAsync(np, *p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->st));
-    if (*p) { WN_CK(cudaDeviceSynchronize()); WN_CK(cudaFree(*p)); }   /* rare: copies may be in flight */
+    if (*p) { WN_CK(cudaStreamSynchronize(ctx->st)); WN_CK(cudaFree(*p)); }
     *p = np;
     *cap = ncap;
     return WN_OK;
@@ -234,7 +250,7 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
 {
     const int N = ctx->n_sites;
     if (F <= ctx->cap_frames && N <= ctx->cap_sites && ctx->hs <= ctx->cap_hs && ctx->d_grid) return WN_OK;
-    WN_CK(cudaStreamSynchronize(ctx->st));
+    WN_CK(cudaDeviceSynchronize());
     const int cf = std::max(F, ctx->cap_frames), cn = std::max(N, ctx->cap_sites), ch = std::max(ctx->hs, ctx->cap_hs);
     const int cell_cap = cn / 4 + 27;
     const size_t fn = (size_t)cf * cn;
@@ -246,15 +262,16 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
     if ((rc = dev_realloc_plain(ctx, &ctx->d_spos, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_smeta, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_sdh, fn * ch * 4))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_row_cnt, fn))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_total, (size_t)cf))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_counters, (size_t)cf))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_frame_maxrow, (size_t)cf))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_blk_prefix, (size_t)cf + 2))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_scan_part,
                                 (size_t)cf * (2 * (size_t)wn_scan_chunks_for(std::max(cn, cell_cap + 1)) + 8)))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_block_sums, (size_t)cf * ((cn + 255) / 256 + 1) * 8))) return rc;
-    if (!ctx->d_pass_info) { if ((rc = dev_realloc_plain(ctx, &ctx->d_pass_info, (size_t)2))) return rc; }
+    for (wn_ctx::PassSet& S : ctx->pset) {
+        if ((rc = dev_realloc_plain(ctx, &S.row_cnt, fn))) return rc;
+        if ((rc = dev_realloc_plain(ctx, &S.frame_total, (size_t)cf))) return rc;
+        if ((rc = dev_realloc_plain(ctx, &S.counters, (size_t)cf))) return rc;
+        if ((rc = dev_realloc_plain(ctx, &S.frame_maxrow, (size_t)cf))) return rc;
+        if ((rc = dev_realloc_plain(ctx, &S.block_sums, (size_t)cf * ((cn + 255) / 256 + 1) * 8))) return rc;
+    }
     ctx->cap_frames = cf; ctx->cap_sites = cn; ctx->cap_hs = ch; ctx->cell_cap = cell_cap;
     return WN_OK;
 }
@@ -291,26 +308,57 @@ int ensure_out_frames(wn_ctx* ctx, size_t n_frames, bool host)
     return WN_OK;
 }
 
-/* Device memory the row buffers of one pass may take (bytes). */
+/* Fronts queued ahead of the pass whose back is next.  Measured on the 100k-atom box (profiles/r02/overlap_sweep/):
+ * with one front ahead the ordered copy of pass k shares the SMs with the search of pass k+1, and every split of a
+ * 250-frame step into 2-10 overlapped passes was SLOWER than one pass (4.26-5.11 ms against 4.10 ms per step, for
+ * any stream priority and with the search limited to 4 CTAs per SM): the persistent search kernel owns the register
+ * file, the copy only gets the gaps, and both stages pay their launch tails once per pass.  So passes run back to
+ * back; what the two streams still buy is that the D2H copy of a pass (host variant) starts the moment its back ends. */
+#ifndef WN_PASS_LOOKAHEAD
+#define WN_PASS_LOOKAHEAD 0
+#endif
+
+/* Device memory the row buffers of the two pass sets may take together (bytes). */
 static const size_t WN_ROWBUF_BUDGET = (size_t)24 << 30;
 
-/* Run the pipeline on `nf` device-resident frames; edges land in ctx->d_edges at
- * offset *edge_base (updated), frame rows at [f0, f0+nf). */
-int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int natoms, size_t f0,
-             unsigned long long* edge_base)
+struct PassPlan { int f0, nf; };
+
+/* frames of [f, n_frames) -> passes of at most `unit` frames (and `nf_cap`, the row-buffer budget); `ramp`: the
+ * first passes are short (unit/8, doubling) so that the first results reach the D2H engine early */
+void build_plan(int f, int n_frames, int unit, int nf_cap, bool ramp, std::vector<PassPlan>& plan)
+{
+    unit = std::max(1, std::min(unit, nf_cap));
+    if (ramp) {
+        for (int nf = std::max(1, unit / 8); f < n_frames && nf < unit; nf *= 2) {
+            const int take = std::min(nf, n_frames - f);
+            plan.push_back(PassPlan{f, take});
+            f += take;
+        }
+    }
+    const int rest = n_frames - f;
+    if (rest <= 0) return;
+    const int np = (rest + unit - 1) / unit, each = rest / np, extra = rest % np;      /* equal passes: no short tail */
+    for (int q = 0; q < np; ++q) {
+        const int take = each + (q < extra ? 1 : 0);
+        plan.push_back(PassPlan{f, take});
+        f += take;
+    }
+}
+
+/* FRONT of a pass, on ctx->st: staging (bbox, bin, cell scan, scatter), the fused search + geometry kernel, the
+ * row scan and the frame offsets (chained on the device) for `nf` device-resident frames -> row buffers of set S.
+ * ev[0..3]: start / staged / searched / front done. */
+int pass_front(wn_ctx* ctx, wn_ctx::PassSet& S, const float* d_frames, const float* boxes, int nf, int natoms, size_t f0,
+               unsigned long long* pass_info, cudaEvent_t* ev)
 {
     const int N = ctx->n_sites;
     cudaStream_t st = ctx->st;
     int rc;
-    /* a pass whose row buffers would not fit is split (dense inputs after row_cap grew) */
-    if (nf > 1 && (size_t)nf * N * ctx->row_cap * WN_ROW_WORDS * sizeof(uint32_t) > WN_ROWBUF_BUDGET) {
-        const int half = nf / 2;
-        if ((rc = run_pass(ctx, d_frames, boxes, half, natoms, f0, edge_base))) return rc;
-        return run_pass(ctx, d_frames + (size_t)half * natoms * 3, boxes ? boxes + ctx->box_stride * (size_t)half : nullptr,
-                        nf - half, natoms, f0 + half, edge_base);
-    }
-    if ((rc = ensure_pass_buffers(ctx, nf))) return rc;
     const int cell_cap = ctx->cell_cap;
+    /* the back of the pass that used this set two passes ago must have read everything */
+    if (S.used) WN_CK(cudaStreamWaitEvent(st, S.back_done, 0));
+    S.used = true;
+    if ((rc = dev_ensure(ctx, &S.rowbuf, &S.rowbuf_cap, (size_t)nf * N * ctx->row_cap * WN_ROW_WORDS))) return rc;
     WnSubset sub = {nullptr, nullptr};
     if (ctx->sub_off_host) {
         /* the pass's slice of the per-frame site lists, offsets rebased to the slice */
@@ -318,21 +366,28 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
         const size_t cnt = (size_t)(ctx->sub_off_host[f0 + nf] - base);
         ctx->h_sub_off.resize((size_t)nf + 1);
         for (int k = 0; k <= nf; ++k) ctx->h_sub_off[k] = (int)(ctx->sub_off_host[f0 + k] - base);
-        if ((rc = dev_ensure(ctx, &ctx->d_sub_off, &ctx->sub_off_cap, (size_t)nf + 1))) return rc;
-        if ((rc = dev_ensure(ctx, &ctx->d_sub_sites, &ctx->sub_sites_cap, cnt + 1))) return rc;
-        WN_CK(cudaMemcpyAsync(ctx->d_sub_off, ctx->h_sub_off.data(), ((size_t)nf + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-        if (cnt) WN_CK(cudaMemcpyAsync(ctx->d_sub_sites, ctx->sub_sites_host + base, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
-        WN_CK(cudaStreamSynchronize(st));       /* pageable sources */
-        sub.off = ctx->d_sub_off; sub.sites = ctx->d_sub_sites;
+        if ((rc = dev_ensure(ctx, &S.sub_off, &S.sub_off_cap, (size_t)nf + 1))) return rc;
+        if ((rc = dev_ensure(ctx, &S.sub_sites, &S.sub_sites_cap, cnt + 1))) return rc;
+        /* pageable sources: the calls return once the driver has staged them */
+        WN_CK(cudaMemcpyAsync(S.sub_off, ctx->h_sub_off.data(), ((size_t)nf + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (cnt) WN_CK(cudaMemcpyAsync(S.sub_sites, ctx->sub_sites_host + base, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
+        WN_CK(cudaStreamSynchronize(st));
+        sub.off = S.sub_off; sub.sites = S.sub_sites;
     }
 
-    WN_CK(cudaEventRecord(ctx->ev[0], st));
+    WN_CK(cudaEventRecord(ev[0], st));
+    nvtxRangePushA("wn:bin (bbox, cells, sort)");
+    struct PopOnExit { int n; ~PopOnExit() { while (n-- > 0) nvtxRangePop(); } } nvtx_guard{1};
     bool small_box = false;      /* periodic box with < 3 cells in some dimension: all-pairs kernel */
     int bx = 2;                  /* home block width; 1 when a periodic box has < 4 cells along x  */
     if (boxes) {
-        ctx->h_grid.resize((size_t)nf);
+        if ((size_t)nf > S.h_grid_cap) {
+            if (S.h_grid) { WN_CK(cudaDeviceSynchronize()); WN_CK(cudaFreeHost(S.h_grid)); S.h_grid = nullptr; }
+            S.h_grid_cap = (size_t)nf + (size_t)nf / 2;
+            WN_CK(cudaMallocHost((void**)&S.h_grid, S.h_grid_cap * sizeof(WnGrid)));
+        }
         for (int f = 0; f < nf; ++f) {
-            WnGrid& g = ctx->h_grid[f];
+            WnGrid& g = S.h_grid[f];
             if (ctx->box_stride == 9) {
                 const float* b = boxes + 9 * (size_t)f;
                 for (int k = 0; k < 9; ++k)
@@ -352,8 +407,8 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
             if (g.nx < 3 || g.ny < 3 || g.nz < 3) small_box = true;
             if (g.nx < 4) bx = 1;
         }
-        WN_CK(cudaMemcpyAsync(ctx->d_grid, ctx->h_grid.data(), (size_t)nf * sizeof(WnGrid), cudaMemcpyHostToDevice, st));
-        WN_CK(cudaStreamSynchronize(st));       /* h_grid is pageable and reused by the next pass */
+        /* pinned and owned by the set: the copy is asynchronous, the set is not reused before its back has finished */
+        WN_CK(cudaMemcpyAsync(ctx->d_grid, S.h_grid, (size_t)nf * sizeof(WnGrid), cudaMemcpyHostToDevice, st));
     } else {
         wn_launch_bbox(d_frames, nf, natoms, ctx->d_site_atom, N, sub, cell_cap, ctx->d_grid, ctx->d_scan_part, st);
     }
@@ -365,78 +420,55 @@ int run_pass(wn_ctx* ctx, const float* d_frames, const float* boxes, int nf, int
                       cell_cap, ctx->d_cell_cnt, ctx->d_site_cell, ctx->d_site_rank, ctx->d_grid, ctx->d_spos,
                       ctx->d_smeta, ctx->d_sdh, st);
     ctx->tm.launches += boxes ? 5 : 7;     /* [bbox x2] bin, cell scan x3, scatter */
-    WN_CK(cudaEventRecord(ctx->ev[1], st));
+    WN_CK(cudaEventRecord(ev[1], st));
+    nvtxRangePop(); nvtxRangePushA("wn:edges (fused search + geometry)");
 
-    unsigned long long end_off = 0;
-    for (int attempt = 0;; ++attempt) {
-        if ((rc = dev_ensure(ctx, &ctx->d_rowbuf, &ctx->rowbuf_cap, (size_t)nf * N * ctx->row_cap * WN_ROW_WORDS))) return rc;
-        WN_CK(cudaMemsetAsync(ctx->d_row_cnt, 0, (size_t)nf * N * sizeof(uint32_t), st));
-        WN_CK(cudaMemsetAsync(ctx->d_counters, 0, (size_t)nf * sizeof(WnFrameCounters), st));
-        WnEdgeParams p;
-        p.spos = ctx->d_spos; p.smeta = ctx->d_smeta; p.sdh = ctx->d_sdh;
-        p.cell_start = ctx->d_cell_cnt; p.grid = ctx->d_grid;
-        p.rowbuf = ctx->d_rowbuf; p.row_cnt = ctx->d_row_cnt; p.counters = ctx->d_counters;
-        p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
-        p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? (ctx->box_stride == 9 ? 2 : 1) : 0; p.bx = bx; p.subset = sub;
-        p.blk_prefix = ctx->d_blk_prefix; p.work_next = reinterpret_cast<unsigned int*>(ctx->d_blk_prefix + nf + 1); p.n_frames = nf;
-        if (small_box) wn_launch_edges_small(p, nf, st);
-        else wn_launch_edges(p, nf, st);
-        WN_CK(cudaGetLastError());
-        if (attempt == 0) WN_CK(cudaEventRecord(ctx->ev[2], st));
-        wn_launch_rowscan(ctx->d_row_cnt, nf, N, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_total, ctx->d_frame_maxrow,
-                          ctx->d_scan_part, st);
-        /* the two pass scalars (edge total, longest row) are written by the kernel straight into pinned host
-         * memory (UVA: the pointer is valid on the device): a cudaMemcpyAsync here would queue on the D2H copy
-         * engine behind the previous pass's result copy and stall this stream until that copy ends */
-        wn_launch_frameoff(ctx->d_frame_total, ctx->d_frame_maxrow, nf, *edge_base, ctx->d_frame_off + f0,
-                           ctx->h_scalars, st);
-        ctx->tm.launches += small_box ? 5 : 6;   /* [home-block prefix] fused search, row scan x3, frame offsets */
-        WN_CK(cudaStreamSynchronize(st));
-        end_off = ctx->h_scalars[0];
-        const unsigned long long max_row = ctx->h_scalars[1];
-        if (max_row <= (unsigned long long)ctx->row_cap) break;
-        /* a row overflowed its slots: grow the (sticky) row capacity and repeat the search */
-        if (attempt > 0) return fail(ctx, WN_ERR_CUDA, "internal: row capacity still too small after growing");
-        int nc = ctx->row_cap;
-        while ((unsigned long long)nc < max_row) nc *= 2;
-        ctx->row_cap = nc;
-        if (nf > 1 && (size_t)nf * N * nc * WN_ROW_WORDS * sizeof(uint32_t) > WN_ROWBUF_BUDGET) {
-            const int half = nf / 2;
-            if ((rc = run_pass(ctx, d_frames, boxes, half, natoms, f0, edge_base))) return rc;
-            return run_pass(ctx, d_frames + (size_t)half * natoms * 3, boxes ? boxes + ctx->box_stride * (size_t)half : nullptr,
-                            nf - half, natoms, f0 + half, edge_base);
-        }
-    }
+    WN_CK(cudaMemsetAsync(S.row_cnt, 0, (size_t)nf * N * sizeof(uint32_t), st));
+    WN_CK(cudaMemsetAsync(S.counters, 0, (size_t)nf * sizeof(WnFrameCounters), st));
+    WnEdgeParams p;
+    p.spos = ctx->d_spos; p.smeta = ctx->d_smeta; p.sdh = ctx->d_sdh;
+    p.cell_start = ctx->d_cell_cnt; p.grid = ctx->d_grid;
+    p.rowbuf = S.rowbuf; p.row_cnt = S.row_cnt; p.counters = S.counters;
+    p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
+    p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? (ctx->box_stride == 9 ? 2 : 1) : 0; p.bx = bx; p.subset = sub;
+    p.blk_prefix = ctx->d_blk_prefix; p.work_next = reinterpret_cast<unsigned int*>(ctx->d_blk_prefix + nf + 1); p.n_frames = nf;
+    if (small_box) wn_launch_edges_small(p, nf, st);
+    else wn_launch_edges(p, nf, st);
+    WN_CK(cudaGetLastError());
+    WN_CK(cudaEventRecord(ev[2], st));
+    nvtxRangePop(); nvtxRangePushA("wn:finish (row scan, frame offsets)");
+    wn_launch_rowscan(S.row_cnt, nf, N, ctx->d_row_off + f0 * (size_t)N, S.frame_total, S.frame_maxrow, ctx->d_scan_part, st);
+    /* the pass scalars (edge total of the call so far, longest row) are written by the kernel straight into pinned
+     * host memory (UVA: the pointer is valid on the device): a cudaMemcpyAsync here would queue on the D2H copy
+     * engine behind an earlier pass's result copy */
+    wn_launch_frameoff(S.frame_total, S.frame_maxrow, nf, ctx->d_chain, ctx->d_frame_off + f0, pass_info, st);
+    ctx->tm.launches += small_box ? 5 : 6;   /* [home-block prefix] fused search, row scan x3, frame offsets */
+    WN_CK(cudaGetLastError());
+    WN_CK(cudaEventRecord(ev[3], st));
+    return WN_OK;
+}
 
-    /* grow with head room: edge counts of equally sized batches differ by a fraction of a percent, and a
-     * regrowth (allocation + copy + synchronisation) costs tens of milliseconds */
-    if ((size_t)end_off > ctx->edges_cap || !ctx->d_edges) {
-        const size_t want = (size_t)end_off + (size_t)end_off / 16 + 4096;
-        if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, want, true, (size_t)*edge_base))) return rc;
-    }
-
-    if (ctx->layout == WN_LAYOUT_CSR12) {
-        if ((rc = dev_ensure(ctx, &ctx->d_eside, &ctx->eside_cap, ctx->edges_cap))) return rc;
-    }
+/* BACK of a pass, on ctx->st_fin: rows ordered by j at their lexicographic offset + energies (wn_k_copy), the
+ * statistics rows, the pass's counters.  ev[3]: front done (waited for); ev[4], ev[5]: back start / done. */
+int pass_back(wn_ctx* ctx, wn_ctx::PassSet& S, int nf, size_t f0, cudaEvent_t* ev)
+{
+    const int N = ctx->n_sites;
+    cudaStream_t st = ctx->st_fin;
+    WnSubset sub = {nullptr, nullptr};
+    if (ctx->sub_off_host) { sub.off = S.sub_off; sub.sites = S.sub_sites; }
+    WN_CK(cudaStreamWaitEvent(st, ev[3], 0));
+    WN_CK(cudaEventRecord(ev[4], st));
+    NvtxRange nvtx_back("wn:finish (ordered copy, energies, statistics)");
     int n_blocks = 0;
-    wn_launch_copy(ctx->d_rowbuf, ctx->row_cap, ctx->d_row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0,
-                   nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->layout, ctx->d_eside, ctx->d_block_sums, &n_blocks, st);
-    wn_launch_stats(ctx->d_block_sums, n_blocks, ctx->d_frame_total, ctx->d_counters, nf, N, sub,
-                    ctx->d_stats + f0, st);
-    WN_CK(cudaMemcpyAsync(ctx->d_counters_all + f0, ctx->d_counters, (size_t)nf * sizeof(WnFrameCounters),
+    wn_launch_copy(S.rowbuf, ctx->row_cap, S.row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0,
+                   nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->layout, ctx->d_eside, S.block_sums, &n_blocks, st);
+    wn_launch_stats(S.block_sums, n_blocks, S.frame_total, S.counters, nf, N, sub, ctx->d_stats + f0, st);
+    WN_CK(cudaMemcpyAsync(ctx->d_counters_all + f0, S.counters, (size_t)nf * sizeof(WnFrameCounters),
                           cudaMemcpyDeviceToDevice, st));
     ctx->tm.launches += 2;
-    WN_CK(cudaEventRecord(ctx->ev[3], st));
     WN_CK(cudaGetLastError());
-    WN_CK(cudaStreamSynchronize(st));
-    float a = 0, b = 0, c2 = 0;
-    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&c2, ctx->ev[2], ctx->ev[3]);
-    ctx->tm.bin_ms += a; ctx->tm.edges_ms += b; ctx->tm.finish_ms += c2;
-    ctx->tm.total_ms += a + b + c2;
-    ctx->tm.passes += 1;
-    *edge_base = end_off;
+    WN_CK(cudaEventRecord(ev[5], st));
+    WN_CK(cudaEventRecord(S.back_done, st));
     return WN_OK;
 }
 
@@ -481,62 +513,116 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
         return WN_OK;
     }
 
+    /* ---- the call as a pipeline of passes ----
+     * st     : front of pass k   (staging, fused search, row scan)          -> row buffers of set k & 1
+     * st_fin : back of pass k-1  (ordered copy + energies, statistics)      <- row buffers of set (k-1) & 1
+     * st_h2d : frames of pass k+1 (host variant)      st_d2h : results of pass k-2 (host variant)
+     * The host learns a pass's edge total and longest row from pinned memory after its front (one event wait, with
+     * the next front already queued), sizes the edge array exactly, and queues the back.  A row longer than its
+     * slots (dense input) drains the pipeline, doubles the (sticky) row capacity and repeats from that pass. */
     const int fpp = ctx->user_frames_per_pass > 0 ? ctx->user_frames_per_pass : default_frames_per_pass(N);
+    const int unit = fpp;
     const size_t frame_floats = (size_t)natoms * 3;
-    if (host_in) {
-        /* Host variant, pipelined: the H2D copy of pass k+1 (st_h2d) and the D2H copy of the
-         * results of pass k-1 (st_d2h) run under the kernels of pass k (st).  The result copy is the
-         * longest stage (PCIe), so the first passes are short: the D2H engine starts early and the
-         * later, full-size passes keep it busy. */
-        std::vector<std::pair<int, int> > plan;        /* (first frame, frames) */
-        {
-            int f0 = 0, nf = ctx->user_frames_per_pass > 0 ? std::max(1, fpp / 8) : std::max(1, fpp / 32);
-            while (f0 < n_frames) {
-                const int take = std::min(std::min(nf, fpp), n_frames - f0);
-                plan.push_back(std::make_pair(f0, take));
-                f0 += take;
-                nf *= 2;
-            }
-        }
+    auto nf_cap_now = [&]() -> int {
+        const size_t per_frame = (size_t)std::max(N, 1) * ctx->row_cap * WN_ROW_WORDS * sizeof(uint32_t);
+        return (int)std::max<size_t>(1, std::min<size_t>((WN_ROWBUF_BUDGET / 2) / per_frame, (size_t)1 << 20));
+    };
+    std::vector<PassPlan> plan;
+    build_plan(0, n_frames, unit, nf_cap_now(), host_in, plan);
+    auto prepare = [&]() -> int {
+        int rc2, max_nf = 0;
+        for (const PassPlan& pp : plan) max_nf = std::max(max_nf, pp.nf);
+        if ((rc2 = ensure_pass_buffers(ctx, max_nf))) return rc2;
+        while (ctx->ev_pass.size() < 6 * plan.size()) { cudaEvent_t e; WN_CK(cudaEventCreate(&e)); ctx->ev_pass.push_back(e); }
+        while (ctx->ev_copy.size() < 4 * plan.size()) { cudaEvent_t e; WN_CK(cudaEventCreate(&e)); ctx->ev_copy.push_back(e); }
+        if ((rc2 = host_ensure(ctx, &ctx->h_pass, &ctx->h_pass_cap, 2 * plan.size()))) return rc2;
+        if (host_in)
+            for (int b = 0; b < 2; ++b)
+                if ((rc2 = dev_ensure(ctx, &ctx->d_stage[b], &ctx->stage_cap[b], (size_t)max_nf * frame_floats))) return rc2;
+        return WN_OK;
+    };
+    if ((rc = prepare())) return rc;
+    WN_CK(cudaMemsetAsync(ctx->d_chain, 0, sizeof(unsigned long long), ctx->st));
+    for (wn_ctx::PassSet& S : ctx->pset) S.used = false;      /* every earlier call ended drained */
+
+    auto stage_in = [&](int k) -> int {
+        const int f0 = plan[k].f0, nf = plan[k].nf, b = k & 1;
+        NvtxRange nvtx_h2d("wn:h2d (frames of a pass)");
+        /* the staging buffer was read by the front of pass k-2 */
+        if (k >= 2) WN_CK(cudaStreamWaitEvent(ctx->st_h2d, ctx->ev_pass[6 * (k - 2) + 3], 0));
+        WN_CK(cudaEventRecord(ctx->ev_copy[4 * k], ctx->st_h2d));
+        WN_CK(cudaMemcpyAsync(ctx->d_stage[b], frames + (size_t)f0 * frame_floats,
+                              (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->st_h2d));
+        WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 1], ctx->st_h2d));
+        WN_CK(cudaEventRecord(ctx->ev_stage[b], ctx->st_h2d));
+        return WN_OK;
+    };
+    int enq = 0, staged = -1, k = 0, grown_at = -1;
+    while (k < (int)plan.size()) {
         const int n_pass = (int)plan.size();
-        while (ctx->ev_copy.size() < (size_t)4 * n_pass) {
-            cudaEvent_t e; WN_CK(cudaEventCreate(&e)); ctx->ev_copy.push_back(e);
+        while (enq < n_pass && enq <= k + WN_PASS_LOOKAHEAD) {
+            const int f0 = plan[enq].f0, nf = plan[enq].nf;
+            const float* src = frames + (size_t)f0 * frame_floats;
+            if (host_in) {
+                if (staged < enq) { if ((rc = stage_in(enq))) return rc; staged = enq; }
+                WN_CK(cudaStreamWaitEvent(ctx->st, ctx->ev_stage[enq & 1], 0));
+                src = ctx->d_stage[enq & 1];
+            }
+            if ((rc = pass_front(ctx, ctx->pset[enq & 1], src, boxes ? boxes + ctx->box_stride * (size_t)f0 : nullptr, nf, natoms,
+                                 (size_t)f0, ctx->h_pass + 2 * (size_t)enq, &ctx->ev_pass[6 * (size_t)enq]))) return rc;
+            ++enq;
+            if (host_in && enq < n_pass && staged < enq) { if ((rc = stage_in(enq))) return rc; staged = enq; }
         }
-        auto stage_in = [&](int k) -> int {
-            const int f0 = plan[k].first, nf = plan[k].second, b = k & 1;
-            int rc2;
-            if ((rc2 = dev_ensure(ctx, &ctx->d_stage[b], &ctx->stage_cap[b], (size_t)std::max(nf, std::min(fpp, n_frames)) * frame_floats))) return rc2;
-            WN_CK(cudaEventRecord(ctx->ev_copy[4 * k], ctx->st_h2d));
-            WN_CK(cudaMemcpyAsync(ctx->d_stage[b], frames + (size_t)f0 * frame_floats,
-                                  (size_t)nf * frame_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->st_h2d));
-            WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 1], ctx->st_h2d));
-            WN_CK(cudaEventRecord(ctx->ev_stage[b], ctx->st_h2d));
-            return WN_OK;
-        };
-        if (n_pass > 0 && (rc = stage_in(0))) return rc;
-        for (int k = 0; k < n_pass; ++k) {
-            const int f0 = plan[k].first, nf = plan[k].second;
-            if (k + 1 < n_pass && (rc = stage_in(k + 1))) return rc;
-            WN_CK(cudaStreamWaitEvent(ctx->st, ctx->ev_stage[k & 1], 0));
+        const int f0 = plan[k].f0, nf = plan[k].nf;
+        WN_CK(cudaEventSynchronize(ctx->ev_pass[6 * (size_t)k + 3]));
+        const unsigned long long end_off = ctx->h_pass[2 * (size_t)k], max_row = ctx->h_pass[2 * (size_t)k + 1];
+        if (max_row > (unsigned long long)ctx->row_cap) {
+            /* a row overflowed its slots: drain, grow the (sticky) row capacity, repeat from this pass */
+            if (grown_at == f0) return fail(ctx, WN_ERR_CUDA, "internal: row capacity still too small after growing");
+            grown_at = f0;
+            WN_CK(cudaDeviceSynchronize());
+            int nc = ctx->row_cap;
+            while ((unsigned long long)nc < max_row) nc *= 2;
+            ctx->row_cap = nc;
+            plan.resize((size_t)k);
+            build_plan(f0, n_frames, unit, nf_cap_now(), false, plan);
+            if ((rc = prepare())) return rc;
+            ctx->h_scalars[8] = edge_base;
+            WN_CK(cudaMemcpyAsync(ctx->d_chain, ctx->h_scalars + 8, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->st));
+            for (wn_ctx::PassSet& S : ctx->pset) S.used = false;
+            enq = k; staged = k - 1;
+            continue;
+        }
+        /* grow with head room: edge counts of equally sized batches differ by a fraction of a percent, and a
+         * regrowth (allocation + copy + synchronisation) costs tens of milliseconds */
+        if ((size_t)end_off > ctx->edges_cap || !ctx->d_edges) {
+            const double per_frame = (double)end_off / (double)(f0 + nf);
+            const size_t want = std::max((size_t)end_off + (size_t)end_off / 16, (size_t)(per_frame * n_frames * 1.02)) + 4096;
+            if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, want, true, (size_t)edge_base))) return rc;
+        }
+        if (ctx->layout == WN_LAYOUT_CSR12) {
+            if ((rc = dev_ensure(ctx, &ctx->d_eside, &ctx->eside_cap, ctx->edges_cap))) return rc;
+        }
+        if ((rc = pass_back(ctx, ctx->pset[k & 1], nf, (size_t)f0, &ctx->ev_pass[6 * (size_t)k]))) return rc;
+        if (host_in) {
             const unsigned long long before = edge_base;
-            if ((rc = run_pass(ctx, ctx->d_stage[k & 1], boxes ? boxes + ctx->box_stride * (size_t)f0 : nullptr, nf, natoms,
-                               (size_t)f0, &edge_base))) return rc;
-            if (host_out && (size_t)edge_base > ctx->hset[ctx->cur].edges_cap) {
+            if (host_out && (size_t)end_off > ctx->hset[ctx->cur].edges_cap) {
                 /* project the whole call from the density seen so far */
-                const double per_frame = (double)edge_base / (double)(f0 + nf);
+                const double per_frame = (double)end_off / (double)(f0 + nf);
                 const size_t want = (size_t)(per_frame * n_frames * 1.05) + 1024;
-                if ((rc = host_ensure(ctx, &ctx->hset[ctx->cur].edges, &ctx->hset[ctx->cur].edges_cap, std::max(want, (size_t)edge_base), true,
+                if ((rc = host_ensure(ctx, &ctx->hset[ctx->cur].edges, &ctx->hset[ctx->cur].edges_cap, std::max(want, (size_t)end_off), true,
                                       (size_t)before))) return rc;
             }
+            NvtxRange nvtx_d2h("wn:d2h (edges + row offsets of a pass)");
+            WN_CK(cudaStreamWaitEvent(ctx->st_d2h, ctx->ev_pass[6 * (size_t)k + 5], 0));
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 2], ctx->st_d2h));
-            if (host_out && edge_base > before)
-            {
+            if (host_out && end_off > before) {
                 /* 20-byte wn_edge records, or 16-byte wn_edge16 records in the same buffers */
                 const size_t esz = ctx->layout == WN_LAYOUT_CSR16 ? sizeof(wn_edge16)
                                  : ctx->layout == WN_LAYOUT_CSR12 ? sizeof(wn_edge12) : sizeof(wn_edge);
                 WN_CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->hset[ctx->cur].edges) + (size_t)before * esz,
                                       reinterpret_cast<const char*>(ctx->d_edges) + (size_t)before * esz,
-                                      (size_t)(edge_base - before) * esz, cudaMemcpyDeviceToHost, ctx->st_d2h));
+                                      (size_t)(end_off - before) * esz, cudaMemcpyDeviceToHost, ctx->st_d2h));
             }
             /* the row offsets of the pass travel with its edges */
             if (host_out && N > 0)
@@ -544,19 +630,12 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
                                       (size_t)nf * N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
             WN_CK(cudaEventRecord(ctx->ev_copy[4 * k + 3], ctx->st_d2h));
         }
-        WN_CK(cudaStreamSynchronize(ctx->st_d2h));
-        for (int k = 0; k < n_pass; ++k) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ctx->ev_copy[4 * k], ctx->ev_copy[4 * k + 1]); ctx->tm.h2d_ms += ms;
-            cudaEventElapsedTime(&ms, ctx->ev_copy[4 * k + 2], ctx->ev_copy[4 * k + 3]); ctx->tm.d2h_ms += ms;
-        }
-    } else {
-        for (int f0 = 0; f0 < n_frames; f0 += fpp) {
-            const int nf = std::min(fpp, n_frames - f0);
-            if ((rc = run_pass(ctx, frames + (size_t)f0 * frame_floats, boxes ? boxes + ctx->box_stride * (size_t)f0 : nullptr, nf,
-                               natoms, (size_t)f0, &edge_base))) return rc;
-        }
+        edge_base = end_off;
+        ++k;
     }
+    /* everything the backs wrote is visible to st before the small tables are read */
+    for (wn_ctx::PassSet& S : ctx->pset)
+        if (S.used) WN_CK(cudaStreamWaitEvent(ctx->st, S.back_done, 0));
     /* small per-frame tables always come back to the host: totals and ties */
     WN_CK(cudaMemcpyAsync(ctx->hset[ctx->cur].frame_off, ctx->d_frame_off, (size_t)(n_frames + 1) * sizeof(uint64_t),
                           cudaMemcpyDeviceToHost, ctx->st));
@@ -565,6 +644,28 @@ int batch_common(wn_ctx* ctx, const float* frames, const float* boxes, bool host
     WN_CK(cudaMemcpyAsync(ctx->hset[ctx->cur].counters, ctx->d_counters_all, (size_t)n_frames * sizeof(WnFrameCounters),
                           cudaMemcpyDeviceToHost, ctx->st));
     WN_CK(cudaStreamSynchronize(ctx->st));
+    if (host_in) WN_CK(cudaStreamSynchronize(ctx->st_d2h));
+    {
+        /* stage times: sums over the passes (fronts and backs of neighbouring passes overlap);
+         * total: first front start -> last front/back end */
+        const int n_pass = (int)plan.size();
+        float ms = 0, span = 0;
+        for (int q = 0; q < n_pass; ++q) {
+            cudaEvent_t* e = &ctx->ev_pass[6 * (size_t)q];
+            cudaEventElapsedTime(&ms, e[0], e[1]); ctx->tm.bin_ms += ms;
+            cudaEventElapsedTime(&ms, e[1], e[2]); ctx->tm.edges_ms += ms;
+            cudaEventElapsedTime(&ms, e[2], e[3]); ctx->tm.finish_ms += ms;
+            cudaEventElapsedTime(&ms, e[4], e[5]); ctx->tm.finish_ms += ms;
+            cudaEventElapsedTime(&ms, ctx->ev_pass[0], e[3]); span = std::max(span, ms);
+            cudaEventElapsedTime(&ms, ctx->ev_pass[0], e[5]); span = std::max(span, ms);
+            if (host_in) {
+                cudaEventElapsedTime(&ms, ctx->ev_copy[4 * q], ctx->ev_copy[4 * q + 1]); ctx->tm.h2d_ms += ms;
+                cudaEventElapsedTime(&ms, ctx->ev_copy[4 * q + 2], ctx->ev_copy[4 * q + 3]); ctx->tm.d2h_ms += ms;
+            }
+        }
+        ctx->tm.total_ms = span;
+        ctx->tm.passes = n_pass;
+    }
     if (ctx->hset[ctx->cur].frame_off[n_frames] != edge_base)
         return fail(ctx, WN_ERR_CUDA, "internal: edge totals disagree between scan and fused kernel");
     wn_tie_report ties = {0, 0, 0, 0, 0};
@@ -639,7 +740,15 @@ int wn_create(int device, wn_ctx** out)
         if (e2_ != cudaSuccess) { int rc_ = cuda_fail(nullptr, e2_, #call); delete ctx; return rc_; } \
     } while (0)
     WN_CKC(cudaSetDevice(device));
-    WN_CKC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    {
+        /* the back of a pass (ordered copy) goes first: its result is what the D2H engine waits for */
+        int prio_lo = 0, prio_hi = 0;
+        WN_CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        WN_CKC(cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking, prio_lo));
+        WN_CKC(cudaStreamCreateWithPriority(&ctx->st_fin, cudaStreamNonBlocking, prio_hi));
+    }
+    for (wn_ctx::PassSet& S : ctx->pset) WN_CKC(cudaEventCreateWithFlags(&S.back_done, cudaEventDisableTiming));
+    WN_CKC(cudaMalloc((void**)&ctx->d_chain, sizeof(unsigned long long)));
     WN_CKC(cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking));
     WN_CKC(cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev_stage) WN_CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -662,9 +771,12 @@ void wn_destroy(wn_ctx* ctx)
         if (fn) fn(ctx->comm);
     }
     void* dev[] = {ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, ctx->d_grid, ctx->d_cell_cnt, ctx->d_site_cell,
-                   ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_cnt,
-                   ctx->d_row_off, ctx->d_frame_total, ctx->d_counters, ctx->d_frame_maxrow, ctx->d_blk_prefix, ctx->d_scan_part, ctx->d_pass_info, ctx->d_sub_off, ctx->d_sub_sites,
-                   ctx->d_block_sums, ctx->d_rowbuf, ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
+                   ctx->d_site_rank, ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->d_row_off, ctx->d_blk_prefix, ctx->d_scan_part, ctx->d_chain,
+                   ctx->pset[0].row_cnt, ctx->pset[0].frame_total, ctx->pset[0].counters, ctx->pset[0].frame_maxrow, ctx->pset[0].block_sums,
+                   ctx->pset[0].rowbuf, ctx->pset[0].sub_off, ctx->pset[0].sub_sites,
+                   ctx->pset[1].row_cnt, ctx->pset[1].frame_total, ctx->pset[1].counters, ctx->pset[1].frame_maxrow, ctx->pset[1].block_sums,
+                   ctx->pset[1].rowbuf, ctx->pset[1].sub_off, ctx->pset[1].sub_sites,
+                   ctx->d_stage[0], ctx->d_stage[1], ctx->d_edges, ctx->d_frame_off, ctx->d_stats, ctx->d_counters_all,
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce,
                    ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags,
                    ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx, ctx->d_cc_kept, ctx->d_cc_stats, ctx->d_eside,
@@ -672,11 +784,14 @@ void wn_destroy(wn_ctx* ctx)
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ctx->hset[0].edges, ctx->hset[0].frame_off, ctx->hset[0].stats, ctx->hset[0].counters, ctx->hset[0].row_off,
                     ctx->hset[1].edges, ctx->hset[1].frame_off, ctx->hset[1].stats, ctx->hset[1].counters, ctx->hset[1].row_off,
-                    ctx->h_scalars, ctx->h_pairs, ctx->h_text, ctx->h_cc_labels, ctx->h_cc_stats};
+                    ctx->h_scalars, ctx->h_pass, ctx->pset[0].h_grid, ctx->pset[1].h_grid, ctx->h_pairs, ctx->h_text, ctx->h_cc_labels, ctx->h_cc_stats};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_copy) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_pass) cudaEventDestroy(ev);
+    for (wn_ctx::PassSet& S : ctx->pset) if (S.back_done) cudaEventDestroy(S.back_done);
+    if (ctx->st_fin) cudaStreamDestroy(ctx->st_fin);
     if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
     if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
     if (ctx->st) cudaStreamDestroy(ctx->st);

@@ -140,9 +140,10 @@ void wn_launch_edges_small(const WnEdgeParams& p, int n_frames, cudaStream_t st)
 void wn_launch_rowscan(const uint32_t* row_cnt, int n_frames, int n_sites,
                        uint32_t* row_off, unsigned long long* frame_total, uint32_t* frame_maxrow,
                        uint32_t* part /* [2][F][chunks(n_sites)] */, cudaStream_t st);
-/* pass_info[0] = base + total edges of the pass, pass_info[1] = longest row */
+/* chain[0] (device): edges of the call before this pass, advanced by the pass's total;
+ * pass_info[0] = the new chain[0], pass_info[1] = longest row of the pass */
 void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* frame_maxrow, int n_frames,
-                        unsigned long long base, unsigned long long* frame_off,
+                        unsigned long long* chain, unsigned long long* frame_off,
                         unsigned long long* pass_info, cudaStream_t st);
 void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
                     const uint32_t* row_off, const unsigned long long* frame_off,

@@ -75,10 +75,12 @@ __device__ __forceinline__ double wn_compute_energy(double r, double cosine, con
 /* ---- exclusive scan of the frame totals (single block) ---- */
 __global__ void __launch_bounds__(1024)
 wn_k_frameoff(const unsigned long long* __restrict__ frame_total, const uint32_t* __restrict__ frame_maxrow,
-              int n_frames, unsigned long long base, unsigned long long* __restrict__ frame_off,
+              int n_frames, unsigned long long* __restrict__ chain, unsigned long long* __restrict__ frame_off,
               unsigned long long* __restrict__ pass_info)
 {
     __shared__ uint32_t s_max;
+    /* the call's running edge total lives on the device: passes chain without a host round trip */
+    const unsigned long long base = chain[0];
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
     {
@@ -109,7 +111,7 @@ wn_k_frameoff(const unsigned long long* __restrict__ frame_total, const uint32_t
             if (lane >= o) iv += t;
         }
         s_w[lane] = iv - v;
-        if (lane == 31) { frame_off[n_frames] = base + iv; pass_info[0] = base + iv; }
+        if (lane == 31) { frame_off[n_frames] = base + iv; pass_info[0] = base + iv; chain[0] = base + iv; }
     }
     __syncthreads();
     if (threadIdx.x == 0) pass_info[1] = s_max;
@@ -235,10 +237,10 @@ wn_k_stats(const double* __restrict__ block_sums, int n_blocks,
 }  // namespace
 
 void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* frame_maxrow, int n_frames,
-                        unsigned long long base, unsigned long long* frame_off,
+                        unsigned long long* chain, unsigned long long* frame_off,
                         unsigned long long* pass_info, cudaStream_t st)
 {
-    wn_k_frameoff<<<1, 1024, 0, st>>>(frame_total, frame_maxrow, n_frames, base, frame_off, pass_info);
+    wn_k_frameoff<<<1, 1024, 0, st>>>(frame_total, frame_maxrow, n_frames, chain, frame_off, pass_info);
 }
 
 void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
