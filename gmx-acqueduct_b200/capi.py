@@ -32,7 +32,7 @@ assert EDGE_DTYPE.itemsize == 20 and STATS_DTYPE.itemsize == 40
 # every symbol include/wn_b200.h declares
 SYMBOLS = [
     "wn_create", "wn_destroy", "wn_last_error", "wn_version", "wn_find_pairs", "wn_find_pairs_pbc",
-    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_hbond_batch_ex", "wn_hbond_batch_box9", "wn_find_pairs_box9", "wn_set_find_mode", "wn_last_find_used_cells", "wn_format_edges", "wn_components", "wn_set_sites",
+    "wn_hbond_batch_pbc", "wn_hbond_batch_pbc_dev", "wn_hbond_batch_subset", "wn_hbond_batch_ex", "wn_hbond_batch_box9", "wn_find_pairs_box9", "wn_set_find_mode", "wn_last_find_used_cells", "wn_make_edges", "wn_format_edges", "wn_components", "wn_set_sites",
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
@@ -108,6 +108,7 @@ def load():
     L.wn_hbond_batch_ex.argtypes = [vp, C.POINTER(BatchArgs), C.POINTER(BatchResult)]
     L.wn_hbond_batch_box9.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_find_pairs_box9.argtypes = [vp, vp, i32, i32, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(TieReport)]
+    L.wn_make_edges.argtypes = [vp, vp, i32, vp, vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(TieReport)]
     L.wn_set_find_mode.argtypes = [vp, i32]
     L.wn_last_find_used_cells.argtypes = [vp]
     L.wn_format_edges.argtypes = [vp, vp, vp, i32, C.POINTER(vp), C.POINTER(u64)]
@@ -192,6 +193,22 @@ class Context:
             return np.zeros((0, 2), np.int32), ties.as_dict()
         buf = (C.c_int32 * (2 * cnt)).from_address(p.value)
         return np.frombuffer(buf, dtype=np.int32).reshape(cnt, 2).copy(), ties.as_dict()
+
+    def make_edges(self, frame, pairs, box9=None):
+        """make_edges of the reference on a caller-supplied pair list, in the given order and orientation:
+        (edges, n_pair_evals, ties)."""
+        frame = np.ascontiguousarray(frame, dtype=np.float32).reshape(-1, 3)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        b = None if box9 is None else np.ascontiguousarray(box9, dtype=np.float32).reshape(9)
+        e, n, ev, ties = C.c_void_p(), C.c_uint64(), C.c_uint64(), TieReport()
+        self._ck(self.L.wn_make_edges(self.h, frame.ctypes.data, frame.shape[0], None if b is None else b.ctypes.data,
+                                      pairs.ctypes.data if len(pairs) else None, len(pairs), C.byref(e), C.byref(n),
+                                      C.byref(ev), C.byref(ties)))
+        cnt = int(n.value)
+        if cnt == 0:
+            return np.zeros(0, EDGE_DTYPE), int(ev.value), ties.as_dict()
+        buf = (C.c_char * (cnt * EDGE_DTYPE.itemsize)).from_address(e.value)
+        return np.frombuffer(buf, dtype=EDGE_DTYPE).copy(), int(ev.value), ties.as_dict()
 
     def set_find_mode(self, mode):
         """0: automatic, 1: all-pairs tile kernel, 2: cell-list sweep (wn_b200.h WN_FIND_*)."""

@@ -135,6 +135,12 @@ struct wn_ctx {
     int32_t* h_pairs = nullptr;
     size_t h_pairs_cap = 0;
     unsigned long long* d_pair_ties = nullptr;
+    /* make_edges over a caller-supplied pair list */
+    int2* d_pl_pairs = nullptr;  size_t pl_pairs_cap = 0;
+    float2* d_pl_tmp = nullptr;  size_t pl_tmp_cap = 0;
+    uint32_t* d_pl_blk = nullptr;  size_t pl_blk_cap = 0;
+    unsigned long long* d_pl_off = nullptr;  size_t pl_off_cap = 0;
+    WnFrameCounters* d_pl_counters = nullptr;   /* [1] counters, then one word: bad index flag */
     /* cell-list pair path */
     int find_mode = 0;                       /* WN_FIND_AUTO / WN_FIND_ALLPAIRS / WN_FIND_CELLS */
     int last_find_cells = 0;                 /* the last wn_find_pairs* call ran the cell-list sweep */
@@ -780,6 +786,7 @@ void wn_destroy(wn_ctx* ctx)
                    ctx->d_xyz, ctx->d_prow_cnt, ctx->d_prow_off, ctx->d_pairs, ctx->d_pair_ties, ctx->d_reduce,
                    ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags,
                    ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx, ctx->d_cc_kept, ctx->d_cc_stats, ctx->d_eside,
+                   ctx->d_pl_pairs, ctx->d_pl_tmp, ctx->d_pl_blk, ctx->d_pl_off, ctx->d_pl_counters,
                    ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_cp_site_rank, ctx->d_cp_srec};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ctx->hset[0].edges, ctx->hset[0].frame_off, ctx->hset[0].stats, ctx->hset[0].counters, ctx->hset[0].row_off,
@@ -1303,6 +1310,107 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
     ctx->tm.passes = 1;
     *pairs = ctx->h_pairs;
     *m = total;
+    return WN_OK;
+}
+
+/* ---- make_edges over a caller-supplied pair list (src/waternetwork.cpp:182-263) ---- */
+int wn_make_edges(wn_ctx* ctx, const float* frame, int32_t natoms, const float* box9, const int32_t* pairs, uint64_t m,
+                  const wn_edge** edges, uint64_t* n_edges, uint64_t* n_pair_evals, wn_tie_report* ties)
+{
+    if (!ctx) return WN_ERR_BAD_ARG;
+    if (!edges || !n_edges || natoms < 0 || (!frame && natoms > 0) || (!pairs && m > 0))
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_make_edges: bad argument");
+    if (ctx->n_sites < 0) return fail(ctx, WN_ERR_NO_SITES, "wn_make_edges: call wn_set_sites first");
+    if (ctx->max_atom >= natoms && ctx->n_sites > 0)
+        return fail(ctx, WN_ERR_BAD_ARG, "wn_make_edges: site table refers to atoms beyond natoms");
+    if (m >= ((uint64_t)1 << 40)) return fail(ctx, WN_ERR_OVERFLOW, "wn_make_edges: pair list too long");
+    WN_CK(cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    ctx->tm = wn_timings{};
+    *edges = nullptr; *n_edges = 0;
+    if (n_pair_evals) *n_pair_evals = 0;
+    if (ties) *ties = wn_tie_report{0, 0, 0, 0, 0};
+    const int N = ctx->n_sites;
+    int pbc = 0;
+    WnGrid g;
+    memset(&g, 0, sizeof g);
+    int rc;
+    if ((rc = ensure_pass_buffers(ctx, 1))) return rc;
+    if (box9) {
+        for (int k = 0; k < 9; ++k)
+            if (!std::isfinite(box9[k])) return fail(ctx, WN_ERR_BAD_ARG, "wn_make_edges: box must be finite");
+        if (!(box9[0] > 0.f && box9[4] > 0.f && box9[8] > 0.f) || box9[1] != 0.f || box9[2] != 0.f || box9[5] != 0.f)
+            return fail(ctx, WN_ERR_BAD_ARG, "wn_make_edges: box must be lower-triangular with a positive diagonal (GROMACS convention)");
+        if (box9[3] == 0.f && box9[6] == 0.f && box9[7] == 0.f) {
+            const float b3[3] = {box9[0], box9[4], box9[8]};
+            wn_host_pbc_grid(b3, ctx->cell_cap, &g);
+            pbc = 1;
+        } else {
+            wn_host_tric_grid(box9, ctx->cell_cap, &g);
+            pbc = 2;
+        }
+    }
+    if (N == 0 || m == 0) {
+        if ((rc = host_ensure(ctx, &ctx->hset[ctx->cur].edges, &ctx->hset[ctx->cur].edges_cap, (size_t)1))) return rc;
+        *edges = ctx->hset[ctx->cur].edges;
+        return WN_OK;
+    }
+    cudaStream_t st = ctx->st;
+    ctx->last_frames = -1;                       /* the call reuses the batch buffers: no "last batch" afterwards */
+    const int nb = wn_pl_blocks(m);
+    if ((rc = dev_ensure(ctx, &ctx->d_stage[0], &ctx->stage_cap[0], (size_t)natoms * 3))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_pl_pairs, &ctx->pl_pairs_cap, (size_t)m))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_pl_tmp, &ctx->pl_tmp_cap, (size_t)m))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_pl_blk, &ctx->pl_blk_cap, (size_t)nb + 1))) return rc;
+    if ((rc = dev_ensure(ctx, &ctx->d_pl_off, &ctx->pl_off_cap, (size_t)nb + 1))) return rc;
+    if (!ctx->d_pl_counters) WN_CK(cudaMalloc((void**)&ctx->d_pl_counters, sizeof(WnFrameCounters) + 8));
+    unsigned int* d_bad = reinterpret_cast<unsigned int*>(ctx->d_pl_counters + 1);
+    /* pageable sources: each call returns once the driver has staged the data */
+    WN_CK(cudaMemcpyAsync(ctx->d_stage[0], frame, (size_t)natoms * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    WN_CK(cudaMemcpyAsync(ctx->d_pl_pairs, pairs, (size_t)m * sizeof(int2), cudaMemcpyHostToDevice, st));
+    WN_CK(cudaMemcpyAsync(ctx->d_grid, &g, sizeof g, cudaMemcpyHostToDevice, st));
+    WN_CK(cudaMemsetAsync(ctx->d_pl_counters, 0, sizeof(WnFrameCounters) + 8, st));
+    WN_CK(cudaEventRecord(ctx->ev[0], st));
+    /* site records in table order: the batched path's staging kernel with the identity permutation
+     * (one cell holding every site, rank = table row) */
+    WN_CK(cudaMemsetAsync(ctx->d_cell_cnt, 0, 2 * sizeof(int), st));
+    WN_CK(cudaMemsetAsync(ctx->d_site_cell, 0, (size_t)N * sizeof(int), st));
+    wn_launch_pl_iota(ctx->d_site_rank, N, st);
+    const WnSubset nosub = {nullptr, nullptr};
+    wn_launch_scatter(ctx->d_stage[0], 1, natoms, ctx->d_site_atom, ctx->d_hv_atom, ctx->d_meta, N, nosub, ctx->hs,
+                      ctx->cell_cap, ctx->d_cell_cnt, ctx->d_site_cell, ctx->d_site_rank, ctx->d_grid, ctx->d_spos,
+                      ctx->d_smeta, ctx->d_sdh, st);
+    wn_launch_pl_eval(ctx->d_spos, ctx->d_smeta, ctx->d_sdh, ctx->hs, ctx->simple, pbc, ctx->d_grid, ctx->d_pl_pairs, m, N,
+                      ctx->d_pl_tmp, ctx->d_pl_blk, ctx->d_pl_counters, d_bad, st);
+    wn_launch_scan64(ctx->d_pl_blk, nb, ctx->d_pl_off, st);
+    WN_CK(cudaGetLastError());
+    WN_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_pl_off + nb, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_pl_counters, sizeof(WnFrameCounters) + 8, cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaStreamSynchronize(st));
+    const unsigned long long total = ctx->h_scalars[0];
+    WnFrameCounters fc;
+    memcpy(&fc, ctx->h_scalars + 1, sizeof fc);
+    unsigned int bad = 0;
+    memcpy(&bad, reinterpret_cast<const char*>(ctx->h_scalars + 1) + sizeof fc, sizeof bad);
+    if (bad) return fail(ctx, WN_ERR_BAD_ARG, "wn_make_edges: a pair refers to a site outside the table");
+    if ((size_t)total > ctx->edges_cap || !ctx->d_edges)
+        if ((rc = dev_ensure(ctx, &ctx->d_edges, &ctx->edges_cap, (size_t)total + (size_t)total / 16 + 4096))) return rc;
+    if ((rc = host_ensure(ctx, &ctx->hset[ctx->cur].edges, &ctx->hset[ctx->cur].edges_cap, (size_t)total + 1))) return rc;
+    wn_launch_pl_write(ctx->d_pl_pairs, ctx->d_pl_tmp, m, ctx->d_pl_off, ctx->ep, ctx->d_edges, ctx->edges_cap, st);
+    WN_CK(cudaGetLastError());
+    WN_CK(cudaEventRecord(ctx->ev[1], st));
+    if (total)
+        WN_CK(cudaMemcpyAsync(ctx->hset[ctx->cur].edges, ctx->d_edges, (size_t)total * sizeof(wn_edge), cudaMemcpyDeviceToHost, st));
+    WN_CK(cudaEventRecord(ctx->ev[2], st));
+    WN_CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->tm.total_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->tm.d2h_ms = ms;
+    ctx->tm.launches = 5; ctx->tm.passes = 1;
+    *edges = ctx->hset[ctx->cur].edges;
+    *n_edges = total;
+    if (n_pair_evals) *n_pair_evals = fc.evals;
+    if (ties) { ties->length_equal_cut = fc.tie_len; ties->cosine_argmax_equal = fc.tie_cos; ties->pos_zero = fc.tie_pos0; }
     return WN_OK;
 }
 

@@ -195,6 +195,15 @@ void wn_launch_cellpairs_fill(const double4* srec, int n, int first_limit, const
 /* exclusive 64-bit scan of `len` 32-bit counts (+ total at [len]) */
 void wn_launch_scan64(const uint32_t* cnt, int len, unsigned long long* off, cudaStream_t st);
 
+/* make_edges over a caller-supplied pair list (wn_kernels_pairlist.cu) */
+void wn_launch_pl_iota(int* rank, int n, cudaStream_t st);
+int wn_pl_blocks(unsigned long long m);
+void wn_launch_pl_eval(const float4* spos, const uint32_t* smeta, const double* sdh, int hs, int simple, int pbc,
+                       const WnGrid* grid, const int2* pairs, unsigned long long m, int n_sites, float2* tmp,
+                       uint32_t* blk_cnt, WnFrameCounters* counters, unsigned int* bad_index, cudaStream_t st);
+void wn_launch_pl_write(const int2* pairs, const float2* tmp, unsigned long long m, const unsigned long long* blk_off,
+                        WnEnergyParams ep, wn_edge* edges, unsigned long long edge_cap, cudaStream_t st);
+
 /* synthetic frames (wn_synth.cu, compiled with -fmad=false) */
 void wn_launch_synth(int n_waters, uint64_t seed, int model, int64_t frame0, int n_frames,
                      float* frames, cudaStream_t st);

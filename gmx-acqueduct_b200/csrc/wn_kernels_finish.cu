@@ -12,65 +12,11 @@
  *     fp64 energy sum and the pair-evaluation count.
  */
 #include "wn_internal.cuh"
+#include "wn_geometry.cuh"
 
 namespace {
 
 constexpr int COPY_THREADS = 256;
-
-/* switch_function_radius (src/waternetwork.cpp:12-28); r, r_on, r_off are the
- * squared values the caller passes (:57).  pow(x,2) is restated as x*x. */
-__device__ __forceinline__ double wn_switch_radius(double r, double r_on, double r_off, double inv_denom)
-{
-    double sw = 0.0;
-    if (r_off > r && r > r_on) {
-        const double r2 = r * r, off2 = r_off * r_off, on2 = r_on * r_on;
-        const double a = r2 - off2;
-        sw = a * a;
-        sw *= off2 + 2 * r2 - 3 * on2;
-        sw *= inv_denom;          /* 1 / (r_off^2 - r_on^2)^3, precomputed in fp64 (<= 1 ulp) */
-    } else if (r < r_on) {
-        sw = 1.0;
-    }
-    return sw;
-}
-
-/* switch_function_angle (src/waternetwork.cpp:30-47) */
-__device__ __forceinline__ double wn_switch_angle(double a, double a_on, double a_off)
-{
-    double sw = 0.0;
-    if (a_off < a && a < a_on) {
-        const double a2 = a * a, off2 = a_off * a_off, on2 = a_on * a_on;
-        const double t = a2 - off2;
-        sw = t * t;
-        sw *= off2 + 2 * a2 - 3 * on2;
-        const double d = off2 - on2;
-        sw /= d * d * d;
-        sw *= -1.0;
-    } else if (a > a_on) {
-        sw = 1.0;
-    }
-    return sw;
-}
-
-/* computeEnergy (src/waternetwork.cpp:49-66): C=3855, D=738 (static float),
- * pow(r,6), pow(r,4), pow(cosine,4) restated as products, the two quotients merged
- * into one and the constant switch denominator inverted once (all <= a few ulp from
- * the glibc-pow evaluation; the contract is 1e-6 relative, the result is stored as
- * float). */
-__device__ __forceinline__ double wn_compute_energy(double r, double cosine, const WnEnergyParams& ep)
-{
-    const double r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
-    const double radius_switch = wn_switch_radius(r2, ep.on2, ep.off2, ep.inv_denom_r);
-    const double c2 = cosine * cosine;
-    const double angle_switch = wn_switch_angle(c2, ep.a_on, ep.a_off);
-    /* C/r^6 - D/r^4 as one division (C - D r^2)/r^6: same value to ~2 ulp except within
-     * ~1e-9 of the zero crossing r = sqrt(C/D), which no float32 length reaches */
-    double energy = (3855.0 - 738.0 * r2) / r6;
-    energy *= c2 * c2;
-    energy *= radius_switch;
-    energy *= angle_switch;
-    return energy;
-}
 
 /* ---- exclusive scan of the frame totals (single block) ---- */
 __global__ void __launch_bounds__(1024)

@@ -171,6 +171,44 @@ void HydrogenBondEdges::componentsOfLastBatch(float weightThreshold, const int32
     if (rc != WN_OK) raise("HydrogenBondEdges::componentsOfLastBatch: wn_components", rc, ctx_);
 }
 
+const wn_edge* HydrogenBondEdges::makeEdgesRaw(const float* frame, int natoms, const std::pair<int, int>* pairs,
+                                              size_t n_pairs, size_t* n_edges, const float (*box)[3])
+{
+    static_assert(sizeof(std::pair<int, int>) == 2 * sizeof(int32_t), "pair<int,int> layout");
+    pushParams();
+    float b9[9];
+    if (box)
+        for (int a = 0; a < 3; ++a)
+            for (int c = 0; c < 3; ++c) b9[3 * a + c] = box[a][c];
+    const wn_edge* e = nullptr;
+    uint64_t n = 0;
+    const int rc = wn_make_edges(ctx_, frame, natoms, box ? b9 : nullptr, reinterpret_cast<const int32_t*>(pairs),
+                                 (uint64_t)n_pairs, &e, &n, nullptr, nullptr);
+    if (rc != WN_OK) {
+        // an index outside the site table is what the reference's .at() reports as std::out_of_range
+        const std::string msg = std::string("HydrogenBondEdges::makeEdges: wn_make_edges failed (status ") + std::to_string(rc) +
+                                "): " + wn_last_error(ctx_);
+        if (rc == WN_ERR_BAD_ARG && msg.find("outside the table") != std::string::npos) throw std::out_of_range(msg);
+        throw std::runtime_error(msg);
+    }
+    if (n_edges) *n_edges = (size_t)n;
+    return e;
+}
+
+std::vector<HydrogenBond> HydrogenBondEdges::makeEdges(const float* frame, int natoms,
+                                                       const std::vector<std::pair<int, int>>& pairs,
+                                                       const std::vector<SiteInfo_ptr>& sites, const float (*box)[3])
+{
+    size_t n = 0;
+    const wn_edge* e = makeEdgesRaw(frame, natoms, pairs.data(), pairs.size(), &n, box);
+    std::vector<HydrogenBond> out;
+    out.reserve(n);
+    for (size_t k = 0; k < n; ++k)
+        out.push_back(HydrogenBond{SiteInfoPair(sites.at(e[k].i), sites.at(e[k].j)), FORWARD,
+                                   (double)e[k].length, (double)e[k].cosine, (double)e[k].energy});
+    return out;
+}
+
 std::vector<HydrogenBond> HydrogenBondEdges::toHydrogenBonds(const HydrogenBondBatch& batch, int frame,
                                                              const std::vector<SiteInfo_ptr>& sites)
 {

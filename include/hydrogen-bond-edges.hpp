@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <functional>
 #include <future>
+#include <utility>
 #include <vector>
 
 #include "wn_b200.h"
@@ -104,6 +105,17 @@ public:
     // labels[f * nSites + s] = smallest site of s's component in frame f, -1 without a kept edge;
     // library-owned pinned memory, valid until the next call.
     void componentsOfLastBatch(float weightThreshold, const int32_t** labels, const wn_component_stats** stats);
+
+    // make_edges of the reference (src/waternetwork.cpp:182-263) on ONE frame and a caller-supplied pair list, in
+    // the list's own order and (first, second) orientation -- what the live module does with the list of its
+    // DelaunayFindPairs (:399,:583,:590-633).  Keep the host finder, hand its pairs over, get the same
+    // std::vector<HydrogenBond> the reference's chunked std::async fan-out joins (:621-633).
+    // frame: float32 [natoms][3]; box: NULL (reference behaviour) or the GROMACS box matrix (periodic extension).
+    std::vector<HydrogenBond> makeEdges(const float* frame, int natoms, const std::vector<std::pair<int, int>>& pairs,
+                                        const std::vector<SiteInfo_ptr>& sites, const float (*box)[3] = nullptr);
+    // the same, raw: library-owned wn_edge records (i = first, j = second), valid until the next call
+    const wn_edge* makeEdgesRaw(const float* frame, int natoms, const std::pair<int, int>* pairs, size_t n_pairs,
+                                size_t* n_edges, const float (*box)[3] = nullptr);
 
     // Convenience: one frame's result as the reference's std::vector<HydrogenBond>
     // (pair order, direction FORWARD), given the SiteInfo_ptr table of the caller.

@@ -181,6 +181,23 @@ int wn_find_pairs_box9(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_
 int wn_set_find_mode(wn_ctx* ctx, int32_t mode);
 int wn_last_find_used_cells(const wn_ctx* ctx);
 
+/* ---- make_edges on a caller-supplied pair list (src/waternetwork.cpp:182-263) --------------
+ * The reference calls make_edges on whatever list its pair finder returned.  The live module's finder is
+ * DelaunayFindPairs (src/waternetwork.cpp:399): Delaunay edges in finite_edges order whose (first, second)
+ * orientation is not i < j.  The orientation decides the sign of OO (:194), which site's hydrogen list is
+ * scanned first in the arg-max (:215-249), the `pos > 0` rule (:251) and which site is printed first -- so the
+ * batched path above (all i < j pairs within 0.65 nm, lexicographic) equals Brute + make_edges, not the live
+ * Delaunay output.  This entry point closes that gap: the host keeps its own finder (Delaunay stays on the host,
+ * out of scope here) and hands the list over; every pair is evaluated in the GIVEN order and orientation, and
+ * the pairs that become edges come back in that order with i = first, j = second.
+ * frame: host float[natoms][3]; box9: NULL (reference behaviour: plain Euclidean) or a GROMACS box matrix
+ * (periodic extension as defined above); pairs: host int32[m][2] indexing the site table of wn_set_sites
+ * (an index outside the table -> WN_ERR_BAD_ARG, where the reference's .at() throws).  first_limit is ignored.
+ * *edges: library-owned pinned wn_edge[*n_edges], valid until the next call; afterwards the context holds no
+ * "last batch" (wn_format_edges / wn_components need a wn_hbond_batch* call first). */
+int wn_make_edges(wn_ctx* ctx, const float* frame, int32_t natoms, const float* box9, const int32_t* pairs, uint64_t m,
+                  const wn_edge** edges, uint64_t* n_edges, uint64_t* n_pair_evals, wn_tie_report* ties);
+
 /* ---- site tables (src/waternetwork.cpp:538-577) --------------------------
  * site_atom[n_sites]: atom index (into a frame) of each site.
  * h_atom[n_sites*hmax]: atom indices of its hydrogen list in list order, -1 padded.

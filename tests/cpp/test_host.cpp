@@ -89,6 +89,34 @@ int main()
         HydrogenBondBatch again = hb.calculate(frames.data(), 1, natoms);
         std::vector<HydrogenBond> hbs = HydrogenBondEdges::toHydrogenBonds(again, 0, infos);
         CHECK(hbs.size() == ref_off[1] && hbs[0].direction == FORWARD);
+        // ---- make_edges on the finder's own pair list (what analyzeFrame does, :583-633): the oxygens of frame 0
+        // through FindPairs::find, the list handed to makeEdges in order -> the batched path's frame 0;
+        // the same list reversed and flipped -> the same number of edges, every one with first/second swapped
+        {
+            std::vector<Point> oxy;
+            for (int w = 0; w < n_waters; ++w) {
+                const float* p = &frames[(size_t)(3 * w) * 3];
+                oxy.push_back(Point((double)p[0], (double)p[1], (double)p[2]));
+            }
+            std::vector<std::pair<int, int>> pl = mp_->find(oxy);
+            std::vector<HydrogenBond> me = hb.makeEdges(frames.data(), natoms, pl, infos);
+            CHECK(me.size() == hbs.size());
+            for (size_t k = 0; k < me.size(); ++k)
+                CHECK(me[k].sites.first->id == hbs[k].sites.first->id && me[k].sites.second->id == hbs[k].sites.second->id &&
+                      me[k].length == hbs[k].length && me[k].angle == hbs[k].angle && me[k].energy == hbs[k].energy);
+            std::vector<std::pair<int, int>> rev;
+            for (size_t k = pl.size(); k-- > 0;) rev.push_back(std::make_pair(pl[k].second, pl[k].first));
+            std::vector<HydrogenBond> mr = hb.makeEdges(frames.data(), natoms, rev, infos);
+            CHECK(mr.size() == me.size());                     // water-water, one real hydrogen each: symmetric decision
+            for (size_t k = 0; k < mr.size(); ++k) {
+                const HydrogenBond& a = mr[k];
+                const HydrogenBond& b = me[me.size() - 1 - k];
+                CHECK(a.sites.first->id == b.sites.second->id && a.sites.second->id == b.sites.first->id && a.length == b.length);
+            }
+            bool threw_oor = false;
+            try { hb.makeEdges(frames.data(), natoms, {std::make_pair(0, n_waters)}, infos); } catch (const std::out_of_range&) { threw_oor = true; }
+            CHECK(threw_oor);                                  // the reference's .at() throws the same
+        }
         // periodic extension through the same classes: box through the batcher == calculate()
         {
             const float box[3][3] = {{2.1f, 0.f, 0.f}, {0.f, 2.1f, 0.f}, {0.f, 0.f, 2.1f}};

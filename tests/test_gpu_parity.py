@@ -489,6 +489,86 @@ def test_cell_list_find_pairs_one_million_atoms(ctx, oracle):
     assert np.array_equal(got[got[:, 0] < 8], want)
 
 
+def test_make_edges_on_a_caller_supplied_pair_list(ctx, oracle, capi):
+    """wn_make_edges = the reference's make_edges (src/waternetwork.cpp:182-263) on whatever pair list the host
+    finder produced -- e.g. DelaunayFindPairs' list, whose order is not lexicographic and whose (first, second)
+    orientation is not i < j (:399).  Random orientation and order, duplicates and self pairs, mixed site types with
+    0..3 hydrogens (the `pos > 0` rule depends on the orientation), against the oracle's make_edges bit for bit."""
+    rng = np.random.default_rng(21)
+    # (a) water box: every i<j pair within the brute cutoff, shuffled and randomly flipped
+    n = 1000
+    frame = oracle.synth_frames(oracle.synth_box(n), 7, 1)[0]
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    site_xyz, h_xyz, h_off = oracle.gather_sites(frame, sa, ha, 2)
+    pairs = oracle.brute_find_pairs(site_xyz)
+    # in order and i<j: equals the batched path
+    got, ev, _ = ctx.make_edges(frame, pairs)
+    batch = ctx.hbond_batch(frame[None])
+    check_edges(got, batch["edges"])
+    assert ev == batch["n_pair_evals"]
+    perm = rng.permutation(len(pairs))[:60000]
+    pl = pairs[perm].copy()
+    flip = rng.random(len(pl)) < 0.5
+    pl[flip] = pl[flip][:, ::-1]
+    pl = np.concatenate([pl, pl[:100], np.stack([np.arange(50), np.arange(50)], axis=1).astype(np.int32)])
+    to = oracle.Ties()
+    want, want_ev = oracle.make_edges(pl, site_xyz, h_xyz, h_off, ty, ties=to)
+    got, ev, ties = ctx.make_edges(frame, pl)
+    assert len(got) == len(want) and ev == want_ev
+    assert np.array_equal(got["i"], want["i"]) and np.array_equal(got["j"], want["j"])      # given orientation kept
+    check_edges(got, want)
+    assert ties["length_equal_cut"] == to.length_equal_cut and ties["cosine_argmax_equal"] == to.cosine_argmax_equal
+    # (b) mixed DONOR/ACCEPTOR/WATER table, 0..3 hydrogens, lists that start with the site atom (F8, F9)
+    n_sites, hmax = 300, 3
+    natoms = n_sites * 4
+    site_atom = np.arange(n_sites, dtype=np.int32) * 4
+    nh = rng.integers(0, 4, size=n_sites)
+    h_atom = -np.ones((n_sites, hmax), np.int32)
+    for s_ in range(n_sites):
+        for k in range(nh[s_]):
+            h_atom[s_, k] = site_atom[s_] + 1 + k
+    for s_ in range(0, n_sites, 7):
+        h_atom[s_, 0] = site_atom[s_]; h_atom[s_, 1] = site_atom[s_] + 1; h_atom[s_, 2] = -1
+    site_type = rng.integers(0, 3, size=n_sites).astype(np.uint8)
+    fr = np.zeros((natoms, 3), np.float32)
+    pos = rng.uniform(0, 2.0, size=(n_sites, 3))
+    fr[0::4] = pos
+    for k in range(3):
+        d = rng.normal(size=(n_sites, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+        fr[1 + k::4] = pos + 0.1 * d
+    ctx.set_sites(site_atom, h_atom, site_type)
+    site_xyz, h_xyz, h_off = oracle.gather_sites(fr, site_atom, h_atom, hmax)
+    pl = rng.integers(0, n_sites, size=(40000, 2)).astype(np.int32)
+    to = oracle.Ties()
+    want, want_ev = oracle.make_edges(pl, site_xyz, h_xyz, h_off, site_type, ties=to)
+    got, ev, ties = ctx.make_edges(fr, pl)
+    assert len(want) > 100 and len(got) == len(want) and ev == want_ev
+    assert np.array_equal(got["i"], want["i"]) and np.array_equal(got["j"], want["j"])
+    check_edges(got, want)
+    assert ties["pos_zero"] == to.pos_zero and to.pos_zero > 0
+    # the two orientations of a pair are different questions (the reason this entry point exists)
+    rev, _, _ = ctx.make_edges(fr, pl[:, ::-1])
+    assert len(rev) != len(got) or not np.array_equal(rev["cosine"], got["cosine"])
+    # (c) periodic: the brute periodic pair list of a water box, in order -> the periodic batch result
+    n = 512
+    box = oracle.synth_box(n)
+    frame = oracle.synth_frames(box, 3, 1)[0]
+    ctx.set_water_sites(n)
+    L = np.float32(box.box)
+    b9 = np.diag([L, L, L]).astype(np.float32).reshape(9)
+    pairs = oracle.brute_find_pairs_pbc(frame[::3].astype(np.float64), (L, L, L))
+    got, ev, _ = ctx.make_edges(frame, pairs, box9=b9)
+    pb = ctx.hbond_batch(frame[None], boxes=np.array([[L, L, L]], np.float32))
+    check_edges(got, pb["edges"])
+    # (d) errors and empty input
+    e0, _, _ = ctx.make_edges(frame, np.zeros((0, 2), np.int32))
+    assert len(e0) == 0
+    with pytest.raises(capi.WnError) as ei:
+        ctx.make_edges(frame, np.array([[0, n]], np.int32))
+    assert ei.value.code == capi.WN_ERR_BAD_ARG and "outside the table" in str(ei.value)
+
+
 # ------------------------------------------------------------------ periodic boxes
 def oracle_frames_pbc(oracle, frames, boxes, site_atom, h_atom, site_type, first_limit=None):
     edges, stats, evals = [], [], 0
