@@ -163,7 +163,20 @@ int wn_find_pairs(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit
  * (the shortest image whenever the cutoff is small against the box, as GROMACS assumes).  A call
  * whose frames are all rectangular uses the rectangular definition above; one with any
  * triclinic frame uses the triclinic formulas for every frame.  Both run the cell-list sweep
- * (boxes with fewer than 3-4 cells of 0.65 nm in a dimension use an all-pairs kernel). */
+ * (boxes with fewer than 3-4 cells of 0.65 nm in a dimension use an all-pairs kernel).
+ *
+ * How this relates to GROMACS' own rectangular rule (pbc_dx_aiuc: `dx = xi - xj` in FLOAT,
+ * `while (dx > L/2) dx -= L; while (dx <= -L/2) dx += L`).  The two are the same geometry, not the
+ * same bits -- deliberately:
+ *   - here the difference of two float coordinates is formed in fp64 (exact) and only the image shift rounds, so a
+ *     pair that does not cross the box is evaluated with EXACTLY the reference's open-boundary arithmetic (a box much
+ *     larger than the system reproduces the non-periodic edge list bit for bit; tested).  The float rule rounds every
+ *     difference to 24 bits first: d^2 of a good part of the pairs moves by ~1e-7 relative, lengths and cosines by a
+ *     few float ulps, and a pair within ~1e-5 A of the 6.5 A cut (or a cosine within ~1e-6 of 0) may change sides;
+ *   - exactly at +-L/2 (only reachable when a box edge is under twice the cut, 1.3 nm) this definition keeps the
+ *     sign, d(b,a) == -d(a,b), so a pair is the same question in both orientations; the float rule maps both to +L/2;
+ *   - boxes so small that a pair is within the cut through two images: both rules keep one image, one edge.
+ * tests/test_oracle_cpu.py::test_pbc_contract_against_the_gromacs_float_minimum_image measures all three. */
 int wn_find_pairs_pbc(wn_ctx* ctx, const double* xyz, int32_t n, int32_t first_limit,
                       const float box[3], const int32_t** pairs, uint64_t* m, wn_tie_report* ties);
 
