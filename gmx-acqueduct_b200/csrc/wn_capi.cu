@@ -50,7 +50,7 @@ struct wn_ctx {
     double* d_sdh = nullptr;
     uint32_t* d_row_off = nullptr;          /* call-wide [n_frames][n_sites] (CSR row offsets) */
     size_t row_off_cap = 0;
-    int* d_blk_prefix = nullptr;             /* [cap_frames + 2]: home-block prefix per frame, then the work counter */
+    int* d_blk_prefix = nullptr;             /* home-block prefix per frame [F+1], the work counter, division constants [F][2] */
     uint32_t* d_scan_part = nullptr;     /* chunk sums / maxima of the three-phase scans, bbox keys */
     /* Buffers a pass's front (staging + fused search + row scan, stream st) hands to its back (ordered copy +
      * statistics, stream st_fin).  Two sets: the back of pass k runs under the front of pass k+1. */
@@ -268,7 +268,7 @@ int ensure_pass_buffers(wn_ctx* ctx, int F)
     if ((rc = dev_realloc_plain(ctx, &ctx->d_spos, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_smeta, fn))) return rc;
     if ((rc = dev_realloc_plain(ctx, &ctx->d_sdh, fn * ch * 4))) return rc;
-    if ((rc = dev_realloc_plain(ctx, &ctx->d_blk_prefix, (size_t)cf + 2))) return rc;
+    if ((rc = dev_realloc_plain(ctx, &ctx->d_blk_prefix, 3 * (size_t)cf + 4))) return rc;     /* prefix[cf+1], counter, magic[cf] */
     if ((rc = dev_realloc_plain(ctx, &ctx->d_scan_part,
                                 (size_t)cf * (2 * (size_t)wn_scan_chunks_for(std::max(cn, cell_cap + 1)) + 8)))) return rc;
     for (wn_ctx::PassSet& S : ctx->pset) {
@@ -438,6 +438,7 @@ int pass_front(wn_ctx* ctx, wn_ctx::PassSet& S, const float* d_frames, const flo
     p.n_sites = N; p.cell_cap = cell_cap; p.hs = ctx->hs; p.first_limit = ctx->first_limit;
     p.row_cap = ctx->row_cap; p.simple = ctx->simple; p.pbc = boxes ? (ctx->box_stride == 9 ? 2 : 1) : 0; p.bx = bx; p.subset = sub;
     p.blk_prefix = ctx->d_blk_prefix; p.work_next = reinterpret_cast<unsigned int*>(ctx->d_blk_prefix + nf + 1); p.n_frames = nf;
+    p.blk_magic = reinterpret_cast<uint2*>(ctx->d_blk_prefix + ((nf + 2 + 1) & ~1));
     if (small_box) wn_launch_edges_small(p, nf, st);
     else wn_launch_edges(p, nf, st);
     WN_CK(cudaGetLastError());

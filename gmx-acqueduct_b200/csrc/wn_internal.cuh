@@ -113,6 +113,7 @@ struct WnEdgeParams {
     WnSubset subset;            /* per-frame site subsets (off == nullptr: whole table) */
     int*            blk_prefix; /* [F+1] exclusive prefix of the home blocks per frame (written by the launcher's kernel) */
     unsigned int*   work_next;  /* next unclaimed home block of the pass (dynamic scheduling)  */
+    uint2*          blk_magic;  /* [F] ceil(2^32 / nbx), ceil(2^32 / ny): block index -> (bx, cy, cz) without divisions */
     int n_frames;
 };
 

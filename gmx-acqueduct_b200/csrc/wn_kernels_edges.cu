@@ -162,13 +162,24 @@ __device__ __forceinline__ void wn_store_codes(WarpShared& ws, uint32_t part, in
     }
 }
 
+/* x / d and x % d for 0 <= x < 2^31, d >= 1, with m = ceil(2^32 / d) precomputed: umulhi gives the quotient or
+ * one more (one less for d = 1, m = 2^32 - 1); one correction either way (~6 instructions instead of ~30) */
+__device__ __forceinline__ void wn_divmod(int x, int d, unsigned int m, int& q, int& r)
+{
+    q = (int)__umulhi((unsigned int)x, m);
+    r = x - q * d;
+    if (r < 0) { --q; r += d; }
+    else if (r >= d) { ++q; r -= d; }
+}
+
 /* floor division and modulo for possibly negative cell indices */
 __device__ __forceinline__ int wn_floordiv(int a, int n) { return (a >= 0) ? a / n : -((-a + n - 1) / n); }
 
 /* home blocks per frame -> exclusive prefix over the frames of the pass; resets the work counter */
 template <int BX>
 __global__ void __launch_bounds__(1024)
-wn_k_block_prefix(const WnGrid* __restrict__ grid, int n_frames, int* __restrict__ prefix, unsigned int* __restrict__ work_next)
+wn_k_block_prefix(const WnGrid* __restrict__ grid, int n_frames, int* __restrict__ prefix, unsigned int* __restrict__ work_next,
+                  uint2* __restrict__ magic)
 {
     __shared__ int s_w[32];
     __shared__ int s_carry;
@@ -178,7 +189,13 @@ wn_k_block_prefix(const WnGrid* __restrict__ grid, int n_frames, int* __restrict
     for (int base = 0; base < n_frames; base += blockDim.x) {
         const int f = base + threadIdx.x;
         int nb = 0;
-        if (f < n_frames) nb = ((grid[f].nx + BX - 1) / BX) * grid[f].ny * grid[f].nz;
+        if (f < n_frames) {
+            const int nbx = (grid[f].nx + BX - 1) / BX;
+            nb = nbx * grid[f].ny * grid[f].nz;
+            /* ceil(2^32 / d) (d = 1: 2^32 - 1); wn_divmod corrects the quotient by at most one */
+            magic[f] = make_uint2(nbx > 1 ? (unsigned int)((0x100000000ull + (unsigned)nbx - 1) / (unsigned)nbx) : 0xffffffffu,
+                                  grid[f].ny > 1 ? (unsigned int)((0x100000000ull + (unsigned)grid[f].ny - 1) / (unsigned)grid[f].ny) : 0xffffffffu);
+        }
         int inc = nb;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -240,7 +257,12 @@ wn_k_edges(const WnEdgeParams p)
     const size_t fbase = (size_t)f * p.n_sites;
     const int* cs_f = p.cell_start + (size_t)f * (p.cell_cap + 1);
     /* home block: cells x0..x1 of row (cy, cz) -- contiguous in the cell-sorted array */
-    const int bx = blk % nbx, cy = (blk / nbx) % ny, cz = blk / (nbx * ny);
+    int bx, cy, cz, t_;
+    {
+        const uint2 mg = __ldg(p.blk_magic + f);
+        wn_divmod(blk, nbx, mg.x, t_, bx);
+        wn_divmod(t_, ny, mg.y, cz, cy);
+    }
     const int x0 = bx * BX, x1 = min(x0 + BX - 1, nx - 1);
     const int row0 = (cz * ny + cy) * nx;
     const int h0 = __ldg(cs_f + row0 + x0), h1 = __ldg(cs_f + row0 + x1 + 1);
@@ -654,7 +676,7 @@ void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
         s_smem = smem;
     }
     const int ctas = s_ctas;
-    wn_k_block_prefix<BX><<<1, 1024, 0, st>>>(p.grid, n_frames, p.blk_prefix, p.work_next);
+    wn_k_block_prefix<BX><<<1, 1024, 0, st>>>(p.grid, n_frames, p.blk_prefix, p.work_next, p.blk_magic);
     /* no more CTAs than there is work for (blocks per frame <= cell_cap) */
     const long long max_items = (long long)n_frames * p.cell_cap;
     const int grid = (int)std::min<long long>(ctas, (max_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
