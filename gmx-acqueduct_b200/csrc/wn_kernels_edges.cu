@@ -676,11 +676,11 @@ void launch_variant(const WnEdgeParams& p, int n_frames, cudaStream_t st)
         s_smem = smem;
     }
     const int ctas = s_ctas;
-    wn_k_block_prefix<BX><<<1, 1024, 0, st>>>(p.grid, n_frames, p.blk_prefix, p.work_next, p.blk_magic);
     /* no more CTAs than there is work for (blocks per frame <= cell_cap) */
     const long long max_items = (long long)n_frames * p.cell_cap;
-    const int grid = (int)std::min<long long>(ctas, (max_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    wn_k_edges<SIMPLE, PBC, BX, LIMITED><<<std::max(grid, 1), WARPS_PER_CTA * 32, smem, st>>>(p);
+    const int grid = std::max(1, (int)std::min<long long>(ctas, (max_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
+    wn_k_block_prefix<BX><<<1, 1024, 0, st>>>(p.grid, n_frames, p.blk_prefix, p.work_next, p.blk_magic);
+    wn_k_edges<SIMPLE, PBC, BX, LIMITED><<<grid, WARPS_PER_CTA * 32, smem, st>>>(p);
 }
 }  // namespace
 
