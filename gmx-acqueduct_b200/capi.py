@@ -36,7 +36,7 @@ SYMBOLS = [
     "wn_set_water_sites", "wn_set_energy_params", "wn_hbond_batch", "wn_hbond_batch_dev",
     "wn_set_batch_frames", "wn_dev_alloc", "wn_dev_free", "wn_host_alloc_pinned",
     "wn_host_free_pinned", "wn_memcpy_d2h", "wn_memcpy_h2d", "wn_synth_frames_dev",
-    "wn_device_count", "wn_set_result_sets", "wn_bind_thread_to_device", "wn_pcie_probe",
+    "wn_device_count", "wn_set_result_sets", "wn_bind_thread_to_device", "wn_pcie_probe", "wn_pcie_probe_mix",
     "wn_get_timings", "wn_selftest_div", "wn_timer_start", "wn_timer_stop", "wn_nccl_unique_id", "wn_nccl_init", "wn_stats_reduce",
 ]
 
@@ -108,6 +108,7 @@ def load():
     L.wn_hbond_batch_ex.argtypes = [vp, C.POINTER(BatchArgs), C.POINTER(BatchResult)]
     L.wn_hbond_batch_box9.argtypes = [vp, vp, vp, i32, i32, C.POINTER(BatchResult)]
     L.wn_find_pairs_box9.argtypes = [vp, vp, i32, i32, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(TieReport)]
+    L.wn_pcie_probe_mix.argtypes = [vp, C.c_size_t, C.c_size_t, i32, C.POINTER(C.c_double)]
     L.wn_make_edges.argtypes = [vp, vp, i32, vp, vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(TieReport)]
     L.wn_set_find_mode.argtypes = [vp, i32]
     L.wn_last_find_used_cells.argtypes = [vp]
@@ -253,6 +254,12 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.wn_pcie_probe(self.h, int(nbytes), int(repeats), C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
+
+    def pcie_probe_mix(self, d2h_bytes, h2d_bytes, repeats=4):
+        """Seconds per repeat of d2h_bytes out and h2d_bytes in, concurrently (pinned memory)."""
+        sec = C.c_double()
+        self._ck(self.L.wn_pcie_probe_mix(self.h, int(d2h_bytes), int(h2d_bytes), int(repeats), C.byref(sec)))
+        return float(sec.value)
 
     # ---- batches
     def _wrap(self, res, copy=True):

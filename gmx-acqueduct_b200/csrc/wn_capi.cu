@@ -145,7 +145,7 @@ struct wn_ctx {
     int find_mode = 0;                       /* WN_FIND_AUTO / WN_FIND_ALLPAIRS / WN_FIND_CELLS */
     int last_find_cells = 0;                 /* the last wn_find_pairs* call ran the cell-list sweep */
     int* d_cp_cell = nullptr;    size_t cp_cell_cap = 0;
-    int* d_cp_site_cell = nullptr; int* d_cp_site_rank = nullptr; double4* d_cp_srec = nullptr;
+    int* d_cp_site_cell = nullptr; int* d_cp_site_rank = nullptr; double4* d_cp_srec = nullptr; float4* d_cp_srecf = nullptr;
     size_t cp_site_cap = 0;
 
     int layout = 0;                          /* result layout of the current / last call */
@@ -788,7 +788,7 @@ void wn_destroy(wn_ctx* ctx)
                    ctx->d_text, ctx->d_row_base, ctx->d_site_ids, ctx->d_frame_flags,
                    ctx->d_cc_labels, ctx->d_cc_work, ctx->d_cc_count, ctx->d_cc_minidx, ctx->d_cc_kept, ctx->d_cc_stats, ctx->d_eside,
                    ctx->d_pl_pairs, ctx->d_pl_tmp, ctx->d_pl_blk, ctx->d_pl_off, ctx->d_pl_counters,
-                   ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_cp_site_rank, ctx->d_cp_srec};
+                   ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_cp_site_rank, ctx->d_cp_srec, ctx->d_cp_srecf};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ctx->hset[0].edges, ctx->hset[0].frame_off, ctx->hset[0].stats, ctx->hset[0].counters, ctx->hset[0].row_off,
                     ctx->hset[1].edges, ctx->hset[1].frame_off, ctx->hset[1].stats, ctx->hset[1].counters, ctx->hset[1].row_off,
@@ -978,6 +978,41 @@ int wn_pcie_probe(wn_ctx* ctx, size_t bytes, int32_t repeats, double* h2d_gbs, d
     return WN_OK;
 }
 
+int wn_pcie_probe_mix(wn_ctx* ctx, size_t d2h_bytes, size_t h2d_bytes, int32_t repeats, double* seconds)
+{
+    if (!ctx || !seconds || repeats < 1 || (d2h_bytes == 0 && h2d_bytes == 0)) return WN_ERR_BAD_ARG;
+    WN_CK(cudaSetDevice(ctx->device));
+    void *ho = nullptr, *hi = nullptr, *d_o = nullptr, *di = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (d2h_bytes) { e = cudaMallocHost(&ho, d2h_bytes); if (e == cudaSuccess) e = cudaMalloc(&d_o, d2h_bytes); }
+    if (e == cudaSuccess && h2d_bytes) { e = cudaMallocHost(&hi, h2d_bytes); if (e == cudaSuccess) e = cudaMalloc(&di, h2d_bytes); }
+    if (e == cudaSuccess) {
+        if (ho) memset(ho, 1, d2h_bytes);                      /* touch: first-touch placement, no page faults in the timed part */
+        if (hi) memset(hi, 1, h2d_bytes);
+        cudaDeviceSynchronize();
+        cudaEventRecord(ctx->ev[4], ctx->st_d2h);
+        cudaStreamWaitEvent(ctx->st_h2d, ctx->ev[4], 0);
+        for (int r = 0; r < repeats; ++r) {
+            if (d2h_bytes) cudaMemcpyAsync(ho, d_o, d2h_bytes, cudaMemcpyDeviceToHost, ctx->st_d2h);
+            if (h2d_bytes) cudaMemcpyAsync(di, hi, h2d_bytes, cudaMemcpyHostToDevice, ctx->st_h2d);
+        }
+        cudaEventRecord(ctx->ev[5], ctx->st_h2d);
+        cudaStreamWaitEvent(ctx->st_d2h, ctx->ev[5], 0);
+        cudaEventRecord(ctx->ev[5], ctx->st_d2h);                /* both directions done */
+        cudaEventSynchronize(ctx->ev[5]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+        *seconds = (double)ms * 1e-3 / repeats;
+        e = cudaGetLastError();
+    }
+    if (d_o) cudaFree(d_o);
+    if (di) cudaFree(di);
+    if (ho) cudaFreeHost(ho);
+    if (hi) cudaFreeHost(hi);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "wn_pcie_probe_mix");
+    return WN_OK;
+}
+
 int wn_hbond_batch_ex(wn_ctx* ctx, const wn_batch_args* a, wn_batch_result* out)
 {
     if (!ctx) return WN_ERR_BAD_ARG;
@@ -1161,6 +1196,12 @@ static bool cellpair_grid(const double* xyz, int n, const WnPairBox& pb, WnCellP
     const double cell_budget = std::max(4096.0, 2.0 * (double)n);
     memset(g, 0, sizeof *g);
     g->pbc = pb.pbc;
+    double lo_all[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL}, hi_all[3] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
+    for (size_t k = 0; k < (size_t)n; ++k)
+        for (int c = 0; c < 3; ++c) {
+            const double v = xyz[3 * k + c];
+            if (std::isfinite(v)) { lo_all[c] = std::min(lo_all[c], v); hi_all[c] = std::max(hi_all[c], v); }
+        }
     if (pb.pbc == 1) {
         double e = edge_min;
         for (;;) {
@@ -1179,12 +1220,8 @@ static bool cellpair_grid(const double* xyz, int n, const WnPairBox& pb, WnCellP
             g->inv[c] = (double)g->n[c] / pb.L[c];
         }
     } else {
-        double lo[3] = {HUGE_VAL, HUGE_VAL, HUGE_VAL}, hi[3] = {-HUGE_VAL, -HUGE_VAL, -HUGE_VAL};
-        for (size_t k = 0; k < (size_t)n; ++k)
-            for (int c = 0; c < 3; ++c) {
-                const double v = xyz[3 * k + c];
-                if (std::isfinite(v)) { lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v); }
-            }
+        const double* lo = lo_all;
+        const double* hi = hi_all;
         double e = edge_min;
         for (;;) {
             double cells = 1.0;
@@ -1199,6 +1236,23 @@ static bool cellpair_grid(const double* xyz, int n, const WnPairBox& pb, WnCellP
         for (int c = 0; c < 3; ++c) { g->o[c] = hi[c] >= lo[c] ? lo[c] : 0.0; g->inv[c] = 1.0 / e; }
     }
     g->ncells = g->n[0] * g->n[1] * g->n[2];
+    /* fp32 reject bound on the squared distance.  The kernel tests origin-relative float copies: each component of a
+     * displacement is off by <= e = 2^-20 * (largest |coordinate - origin| + largest box edge + cutoff) (roundings of the
+     * two copies, of their difference and of the float image shift, with head-room), so an exact d2 <= 4.225 shows up
+     * as d2_f32 <= (4.225 + 2*sqrt(3*4.225)*e + 3*e^2) * (1 + 2^-21): a strict superset, false positives ~1e-5. */
+    double amax = 0.0, lmax = 0.0;
+    for (int c = 0; c < 3; ++c) {
+        if (hi_all[c] >= lo_all[c]) amax = std::max(amax, std::max(std::fabs(hi_all[c] - g->o[c]), std::fabs(lo_all[c] - g->o[c])));
+        lmax = std::max(lmax, g->L[c]);
+        g->Lf[c] = (float)g->L[c];
+        g->invLf[c] = g->pbc ? 1.0f / (float)g->L[c] : 0.0f;
+    }
+    if (!(amax < 1.0e30)) return false;              /* float copies would overflow: exact all-pairs kernel */
+    const double e = std::ldexp(amax + lmax + 2.1, -20);
+    const double bd = (4.225 + 2.0 * std::sqrt(3.0 * 4.225) * e + 3.0 * e * e) * (1.0 + std::ldexp(1.0, -21));
+    float bf = (float)bd;
+    if ((double)bf < bd) bf = std::nextafterf(bf, INFINITY);
+    g->bound_f = bf;
     return true;
 }
 
@@ -1258,6 +1312,7 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
             if ((rc = dev_realloc_plain(ctx, &ctx->d_cp_site_cell, (size_t)n))) return rc;
             if ((rc = dev_realloc_plain(ctx, &ctx->d_cp_site_rank, (size_t)n))) return rc;
             if ((rc = dev_realloc_plain(ctx, &ctx->d_cp_srec, (size_t)n))) return rc;
+            if ((rc = dev_realloc_plain(ctx, &ctx->d_cp_srecf, (size_t)n))) return rc;
             ctx->cp_site_cap = (size_t)n;
         }
     }
@@ -1267,8 +1322,9 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
     WN_CK(cudaMemsetAsync(ctx->d_pair_ties, 0, 2 * sizeof(unsigned long long), st));
     WN_CK(cudaEventRecord(ctx->ev[0], st));
     if (cells) {
-        wn_launch_cellpairs_bin(ctx->d_xyz, n, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_cp_site_rank, ctx->d_cp_srec, st);
-        wn_launch_cellpairs_count(ctx->d_cp_srec, n, first_limit, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_prow_cnt,
+        wn_launch_cellpairs_bin(ctx->d_xyz, n, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_cp_site_rank, ctx->d_cp_srec,
+                                ctx->d_cp_srecf, st);
+        wn_launch_cellpairs_count(ctx->d_cp_srec, ctx->d_cp_srecf, n, first_limit, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_prow_cnt,
                                   ctx->d_pair_ties, st);
         wn_launch_scan64(ctx->d_prow_cnt, n, ctx->d_prow_off, st);
         ctx->tm.launches = 5;
@@ -1292,7 +1348,7 @@ static int find_pairs_impl(wn_ctx* ctx, const double* xyz, int32_t n, int32_t fi
     if (total) {
         WN_CK(cudaEventRecord(ctx->ev[2], st));
         if (cells)
-            wn_launch_cellpairs_fill(ctx->d_cp_srec, n, first_limit, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_prow_off,
+            wn_launch_cellpairs_fill(ctx->d_cp_srec, ctx->d_cp_srecf, n, first_limit, cg, ctx->d_cp_cell, ctx->d_cp_site_cell, ctx->d_prow_off,
                                      ctx->d_pairs, st);
         else
             wn_launch_pairs_fill(ctx->d_xyz, n, first_limit, pb, ctx->d_prow_off, ctx->d_pairs, st);

@@ -185,14 +185,18 @@ struct WnCellPairGrid {
     int n[3];            /* cells per dimension                                                  */
     int ncells;
     int pbc;             /* 0 open, 1 rectangular periodic                                       */
+    float Lf[3], invLf[3];  /* fp32 copies for the reject test                                   */
+    float bound_f;       /* reject when the fp32 squared distance exceeds this (superset of 10*d2 < 42.25) */
 };
 int wn_cellpairs_supported(int n);     /* the per-warp bitmap over j fits in shared memory */
 void wn_launch_cellpairs_bin(const double* xyz, int n, const WnCellPairGrid& g, int* cell_cnt, int* site_cell,
-                             int* site_rank, double4* srec, cudaStream_t st);
-void wn_launch_cellpairs_count(const double4* srec, int n, int first_limit, const WnCellPairGrid& g, const int* cell_start,
-                               const int* site_cell, uint32_t* row_cnt, unsigned long long* ties, cudaStream_t st);
-void wn_launch_cellpairs_fill(const double4* srec, int n, int first_limit, const WnCellPairGrid& g, const int* cell_start,
-                              const int* site_cell, const unsigned long long* row_off, int32_t* pairs, cudaStream_t st);
+                             int* site_rank, double4* srec, float4* srecf, cudaStream_t st);
+void wn_launch_cellpairs_count(const double4* srec, const float4* srecf, int n, int first_limit, const WnCellPairGrid& g,
+                               const int* cell_start, const int* site_cell, uint32_t* row_cnt, unsigned long long* ties,
+                               cudaStream_t st);
+void wn_launch_cellpairs_fill(const double4* srec, const float4* srecf, int n, int first_limit, const WnCellPairGrid& g,
+                              const int* cell_start, const int* site_cell, const unsigned long long* row_off, int32_t* pairs,
+                              cudaStream_t st);
 /* exclusive 64-bit scan of `len` 32-bit counts (+ total at [len]) */
 void wn_launch_scan64(const uint32_t* cnt, int len, unsigned long long* off, cudaStream_t st);
 

@@ -296,6 +296,10 @@ int wn_bind_thread_to_device(wn_ctx* ctx, int32_t* n_cpus);
 /* Plain pinned-memory copy bandwidth of this context's GPU (GB/s, `repeats` back-to-back copies of `bytes`):
  * the ceiling of the host-buffer entry points; run it on all ranks at once to see what shared uplinks leave. */
 int wn_pcie_probe(wn_ctx* ctx, size_t bytes, int32_t repeats, double* h2d_gbs, double* d2h_gbs);
+/* The same with the traffic mix of a batch call: per repeat `d2h_bytes` device-to-host and `h2d_bytes` host-to-device
+ * AT THE SAME TIME (two copy streams), *seconds = time per repeat until both directions are done.  Called on all ranks
+ * at once with a step's volumes, it is the time no host-buffer batch call can beat on this machine. */
+int wn_pcie_probe_mix(wn_ctx* ctx, size_t d2h_bytes, size_t h2d_bytes, int32_t repeats, double* seconds);
 
 /* ---- edge file text (src/waternetwork.cpp:638-652), formatted on the GPU ---------------
  * Formats the edge list of the LAST wn_hbond_batch* call of this context as the rows of
