@@ -11,6 +11,24 @@
 
 #include "wn_b200.h"
 
+/* ---- checked build (make -C gmx-acqueduct_b200 checked -> libwn_b200_checked.so, -DWN_CHECKS) ----
+ * compute-sanitizer is not available on every pool; this build carries its own bounds checks on every shared-memory
+ * queue, bitmap and row-slot index and on every computed global index, and traps (the call then fails with
+ * cudaErrorAssert / an illegal-instruction error) where the release build would read or write out of bounds. */
+#if defined(WN_CHECKS) && defined(__CUDACC__)
+#include <cstdio>
+#define WN_CHECK(cond)                                                                                  \
+    do {                                                                                                \
+        if (!(cond)) {                                                                                  \
+            printf("WN_CHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__,     \
+                   (int)blockIdx.x, (int)threadIdx.x);                                                  \
+            __trap();                                                                                   \
+        }                                                                                               \
+    } while (0)
+#else
+#define WN_CHECK(cond) ((void)0)
+#endif
+
 /* ---- per-frame cell grid ----
  * open boundary: bounding box of the finite sites (wn_k_bbox), cubic cells.
  * periodic     : the box itself, n = floor(L/edge_min) cells per dimension (host-built). */

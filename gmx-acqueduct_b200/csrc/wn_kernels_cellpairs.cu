@@ -131,6 +131,7 @@ cp_exact_batch(const double4* __restrict__ srec, const double4& me, int i, const
     if (lane < nq) {
         const double4 c = srec[queue[lane]];
         const int j = (int)__double_as_longlong(c.w);
+        WN_CHECK(j > i);
         /* squared_distance(points.at(i), points.at(j)) (:25): p_i - p_j component-wise */
         double dx = __dsub_rn(me.x, c.x), dy = __dsub_rn(me.y, c.y), dz = __dsub_rn(me.z, c.z);
         if (PBC) {
@@ -142,6 +143,7 @@ cp_exact_batch(const double4* __restrict__ srec, const double4& me, int i, const
         const double lhs = __dmul_rn(10.0, d2);
         if (lhs < 42.25) {
             if (FILL) {
+                WN_CHECK((j >> 5) < (int)(sm - bm));
                 const uint32_t old = atomicOr(bm + (j >> 5), 1u << (j & 31));
                 if (old == 0u) atomicOr(sm + (j >> 10), 1u << ((j >> 5) & 31));
             } else {
@@ -263,6 +265,7 @@ wn_k_cp_sweep(const double4* __restrict__ srec, const float4* __restrict__ srecf
                 const unsigned m0 = __ballot_sync(FULL, p0), m1 = __ballot_sync(FULL, p1);
                 if (m0 | m1) {
                     const unsigned lt = (1u << lane) - 1u;
+                    WN_CHECK(qlen >= 0 && qlen + __popc(m0) + __popc(m1) <= CP_QCAP && (!p0 || q < n) && (!p1 || q + 32 < n));
                     if (p0) queue[qlen + __popc(m0 & lt)] = q;
                     if (p1) queue[qlen + __popc(m0) + __popc(m1 & lt)] = q + 32;
                     qlen += __popc(m0) + __popc(m1);
@@ -304,7 +307,7 @@ wn_k_cp_sweep(const double4* __restrict__ srec, const float4* __restrict__ srecf
                 if (n_list == 0) continue;
                 {
                     int at = (int)(inc - __popc(sw));
-                    for (uint32_t t = sw; t; t &= t - 1) wl[at++] = (unsigned short)(lane * 32 + __ffs(t) - 1);
+                    for (uint32_t t = sw; t; t &= t - 1) { WN_CHECK(at < 1024); wl[at++] = (unsigned short)(lane * 32 + __ffs(t) - 1); }
                     if (s < swords) sm[s] = 0u;
                 }
                 __syncwarp();
@@ -325,8 +328,10 @@ wn_k_cp_sweep(const double4* __restrict__ srec, const float4* __restrict__ srecf
                         if (lane >= o) pinc += t;
                     }
                     unsigned long long pos = w + (pinc - mine);
-                    for (; bits; bits &= bits - 1)
+                    for (; bits; bits &= bits - 1) {
+                        WN_CHECK(wi < words && pos < row_off[i + 1]);
                         reinterpret_cast<int2*>(pairs)[pos++] = make_int2(i, wi * 32 + __ffs(bits) - 1);
+                    }
                     w += __shfl_sync(FULL, pinc, 31);
                 }
                 __syncwarp();

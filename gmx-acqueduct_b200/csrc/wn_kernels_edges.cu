@@ -96,6 +96,7 @@ __device__ __forceinline__ void
 wn_emit_edge(const WnEdgeParams& p, size_t fbase, int ia, int ib, float len_f, float cosmax)
 {
     const int i = min(ia, ib), j = max(ia, ib);
+    WN_CHECK(i >= 0 && j < p.n_sites && i != j);
     const uint32_t slot = atomicAdd(p.row_cnt + fbase + i, 1u);
     if (slot < (uint32_t)p.row_cap) {
         /* {j, length, cosine, -} (measured: three 4-byte stores into a structure-of-arrays
@@ -116,9 +117,11 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
     r.len_f = r.cosmax = 0.f;
     int ih = 0, ic = 0;
     if (lane < nb) {
+        WN_CHECK(qbase >= 0 && qbase + lane < QCAP);
         const uint32_t code = ws.queue[qbase + lane];
         const int h = (int)(code >> 27);
         const uint32_t c = code & 0x07ffffffu;
+        WN_CHECK(h < HC && c < (uint32_t)p.n_sites);
         const float4 a4 = ws.hpos[h];
         const float4 b4 = __ldg(p.spos + fbase + c);
         ih = __float_as_int(a4.w);
@@ -158,6 +161,7 @@ __device__ __forceinline__ void wn_store_codes(WarpShared& ws, uint32_t part, in
     while (part) {
         const int h = __ffs(part) - 1 + hb0;
         part &= part - 1;
+        WN_CHECK(pos >= 0 && pos < QCAP && h < HC);
         ws.queue[pos++] = ((uint32_t)h << 27) | code_c;
     }
 }
@@ -372,6 +376,7 @@ wn_k_edges(const WnEdgeParams p)
         if (lane >= o) inc += t;
     }
     const int total = __shfl_sync(FULL, inc, MAXRUN - 1);
+    WN_CHECK(n_runs <= MAXRUN && total >= 0 && total <= p.n_sites && h0 >= 0 && h1 <= p.n_sites);
     if (rl > 0) {
         ws.run_start[slot] = rs; ws.run_pref[slot] = inc - rl;
         if (PBC) ws.run_org[slot] = make_float4(sox, soy, soz, 0.f);
@@ -419,6 +424,7 @@ wn_k_edges(const WnEdgeParams p)
             if (v < total) {
                 while (run + 1 < n_runs && v >= ws.run_pref[run + 1]) ++run;
                 const int c = ws.run_start[run] + (v - ws.run_pref[run]);
+                WN_CHECK(run < n_runs && c >= 0 && c < p.n_sites);
                 const float4 b4 = __ldg(p.spos + fbase + c);
                 if (PBC) {
                     const float4 o4 = ws.run_org[run];

@@ -115,12 +115,15 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
             if (e0 + lane < total) {
                 const int irow = blockIdx.x * blockDim.x + warp * 32 + r;
                 const uint4* rowp = reinterpret_cast<const uint4*>(rowbuf) + ((size_t)f * n_sites + irow) * (size_t)row_cap;
+                WN_CHECK(e >= rpre && e - rpre < rcnt && rcnt <= (uint32_t)row_cap && irow < n_sites);
                 const uint4 t = rowp[e - rpre];
                 const int tj = (int)t.x;
+                WN_CHECK(tj > irow && tj < n_sites);
                 const float tlen = __uint_as_float(t.y), tcos = __uint_as_float(t.z);
                 /* rank inside the row by j */
                 uint32_t rank = 0;
                 for (uint32_t k = 0; k < rcnt; ++k) rank += ((int)rowp[k].x < tj) ? 1u : 0u;
+                WN_CHECK(rank < rcnt && span + rpre + rank < edge_cap);
                 /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
                 const float en = __double2float_rn(wn_compute_energy((double)tlen, (double)tcos, ep));
                 if (LAYOUT == WN_LAYOUT_CSR16) {

@@ -94,6 +94,7 @@ wn_k_pl_write(const int2* __restrict__ pairs, const float2* __restrict__ tmp, un
     for (int w = 0; w < warp; ++w) before += s_w[w];
     if (edge) {
         const unsigned long long pos = blk_off[blockIdx.x] + (unsigned long long)before + __popc(b & ((1u << lane) - 1u));
+        WN_CHECK(pos < edge_cap);
         if (pos < edge_cap) {
             const int2 pr = pairs[p];
             wn_edge out;
