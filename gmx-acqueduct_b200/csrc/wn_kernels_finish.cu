@@ -121,8 +121,19 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
                 WN_CHECK(tj > irow && tj < n_sites);
                 const float tlen = __uint_as_float(t.y), tcos = __uint_as_float(t.z);
                 /* rank inside the row by j */
+#ifndef WN_COPY_PLAIN_RANK
+                /* entries with j' >= j counted through the carry of j' - j (0 <= j < 2^27: the unsigned borrow is the
+                 * comparison): two instructions per entry instead of compare + add + select */
+                uint32_t ge = 0;
+                for (uint32_t k = 0; k < rcnt; ++k) {
+                    uint32_t tmp;
+                    asm("sub.cc.u32 %1, %2, %3;\n\taddc.u32 %0, %0, 0;" : "+r"(ge), "=r"(tmp) : "r"(rowp[k].x), "r"((uint32_t)tj));
+                }
+                const uint32_t rank = rcnt - ge;
+#else
                 uint32_t rank = 0;
                 for (uint32_t k = 0; k < rcnt; ++k) rank += ((int)rowp[k].x < tj) ? 1u : 0u;
+#endif
                 WN_CHECK(rank < rcnt && span + rpre + rank < edge_cap);
                 /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
                 const float en = __double2float_rn(wn_compute_energy((double)tlen, (double)tcos, ep));
