@@ -467,9 +467,10 @@ int pass_back(wn_ctx* ctx, wn_ctx::PassSet& S, int nf, size_t f0, cudaEvent_t* e
     WN_CK(cudaEventRecord(ev[4], st));
     NvtxRange nvtx_back("wn:finish (ordered copy, energies, statistics)");
     int n_blocks = 0;
-    wn_launch_copy(S.rowbuf, ctx->row_cap, S.row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0,
+    wn_launch_copy(S.rowbuf, ctx->row_cap, S.row_cnt, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0, S.counters,
                    nf, N, ctx->ep, ctx->d_edges, ctx->edges_cap, ctx->layout, ctx->d_eside, S.block_sums, &n_blocks, st);
-    wn_launch_stats(S.block_sums, n_blocks, S.frame_total, S.counters, nf, N, sub, ctx->d_stats + f0, st);
+    wn_launch_stats(S.block_sums, n_blocks, S.frame_total, S.counters, nf, N, sub, ctx->d_stats + f0, ctx->d_edges, ctx->layout,
+                    ctx->d_eside, ctx->d_row_off + f0 * (size_t)N, ctx->d_frame_off + f0, st);
     WN_CK(cudaMemcpyAsync(ctx->d_counters_all + f0, S.counters, (size_t)nf * sizeof(WnFrameCounters),
                           cudaMemcpyDeviceToDevice, st));
     ctx->tm.launches += 2;

@@ -85,7 +85,11 @@ struct WnFrameCounters {
     unsigned long long tie_cos;    /* equal positive cosines in the arg-max     */
     unsigned long long tie_pos0;   /* arg-max on list index 0                   */
     unsigned long long tests;      /* (home site, candidate) pairs the fp32 prefilter looked at (implementation-dependent) */
+    unsigned long long short_edges;/* edges shorter than WN_SHORT_EDGE_A: their energy may leave the fixed-point range of
+                                    * the ordered copy's energy sum (wn_k_copy), which then sums this frame in final order */
 };
+/* |E| <= 3855/r^6 (cos^4 <= 1, switches <= 1): below 0.56 A an edge's energy can reach 2^17 */
+#define WN_SHORT_EDGE_A 0.56f
 
 /* ---- site meta word (one per site) ---- */
 #define WN_META_TYPE_MASK 3u
@@ -165,13 +169,15 @@ void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* f
                         unsigned long long* chain, unsigned long long* frame_off,
                         unsigned long long* pass_info, cudaStream_t st);
 void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
-                    const uint32_t* row_off, const unsigned long long* frame_off,
+                    const uint32_t* row_off, const unsigned long long* frame_off, const WnFrameCounters* counters,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
                     unsigned long long edge_cap, int layout, float* energy_side, double* block_sums, int* n_blocks_out,
                     cudaStream_t st);
 void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,
                      const WnFrameCounters* counters, int n_frames, int n_sites, WnSubset sub,
-                     wn_frame_stats* stats, cudaStream_t st);
+                     wn_frame_stats* stats, const wn_edge* edges, int layout, const float* energy_side,
+                     const uint32_t* row_off /* of the pass */, const unsigned long long* frame_off /* of the pass */,
+                     cudaStream_t st);
 size_t wn_edges_smem_bytes(int hs);
 void wn_launch_selftest_div(unsigned long long seed, int blocks, int iters, unsigned long long* mismatches,
                             cudaStream_t st);

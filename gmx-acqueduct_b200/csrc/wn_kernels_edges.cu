@@ -134,10 +134,12 @@ wn_eval_batch(const WnEdgeParams& p, size_t fbase, const WarpShared& ws, const d
         r = wn_pair_geometry<SIMPLE, PBC>(a4, b4, dh, dc, mh, mc, g);
     }
     ct.evals += __popc(__ballot_sync(FULL, r.counted));
-    if (__any_sync(FULL, r.t_len || r.t_cos || r.t_pos0)) {          /* rare */
+    const bool short_edge = r.edge && r.len_f < WN_SHORT_EDGE_A;        /* unphysical: the energy sum leaves its fast path */
+    if (__any_sync(FULL, r.t_len || r.t_cos || r.t_pos0 || short_edge)) {          /* rare */
         ct.tie_len += __popc(__ballot_sync(FULL, r.t_len));
         ct.tie_cos += __popc(__ballot_sync(FULL, r.t_cos));
         ct.tie_pos0 += __popc(__ballot_sync(FULL, r.t_pos0));
+        if (__any_sync(FULL, short_edge)) ct.tie_pos0 |= 0x80000000u;       /* remembered in the spare top bit, reported per block */
     }
     if (r.edge) wn_emit_edge(p, fbase, ih, ic, r.len_f, r.cosmax);
 }
@@ -514,7 +516,8 @@ wn_k_edges(const WnEdgeParams p)
         if (ct.evals) atomicAdd(&fc->evals, (unsigned long long)ct.evals);
         if (ct.tie_len) atomicAdd(&fc->tie_len, (unsigned long long)ct.tie_len);
         if (ct.tie_cos) atomicAdd(&fc->tie_cos, (unsigned long long)ct.tie_cos);
-        if (ct.tie_pos0) atomicAdd(&fc->tie_pos0, (unsigned long long)ct.tie_pos0);
+        if (ct.tie_pos0 & 0x80000000u) atomicAdd(&fc->short_edges, 1ull);
+        if (ct.tie_pos0 & 0x7fffffffu) atomicAdd(&fc->tie_pos0, (unsigned long long)(ct.tie_pos0 & 0x7fffffffu));
     }
     __syncwarp();        /* the per-warp shared memory is rewritten by the next block */
     }
@@ -579,6 +582,7 @@ wn_k_edges_small(const WnEdgeParams p)
             const PairOut r = wn_pair_geometry<SIMPLE, PBC>(a4, b4, dha, p.sdh + (fbase + q0 + k) * (size_t)p.hs * 4,
                                                             ma, mb, g);
             evals += r.counted; tie_len += r.t_len; tie_cos += r.t_cos; tie_pos0 += r.t_pos0;
+            if (r.edge && r.len_f < WN_SHORT_EDGE_A) atomicAdd(&(p.counters + f)->short_edges, 1ull);
             if (r.edge) wn_emit_edge(p, fbase, ia, ib, r.len_f, r.cosmax);
         }
     }

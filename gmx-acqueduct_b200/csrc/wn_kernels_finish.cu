@@ -77,8 +77,8 @@ template <int LAYOUT>      /* WN_LAYOUT_EDGES / _CSR16 / _CSR12 */
 __global__ void __launch_bounds__(COPY_THREADS, WN_COPY_MINBLOCKS)
 wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
           const uint32_t* __restrict__ row_cnt, const uint32_t* __restrict__ row_off,
-          const unsigned long long* __restrict__ frame_off, int n_sites, WnEnergyParams ep,
-          wn_edge* __restrict__ edges, unsigned long long edge_cap, unsigned long long edge_base,
+          const unsigned long long* __restrict__ frame_off, const WnFrameCounters* __restrict__ counters, int n_sites,
+          WnEnergyParams ep, wn_edge* __restrict__ edges, unsigned long long edge_cap, unsigned long long edge_base,
           float* __restrict__ energy_side, double* __restrict__ block_sums)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -99,7 +99,14 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
     const uint32_t total = __shfl_sync(FULL, inc, 31);
     /* frame_off carries the offset of this pass inside the call's edge array */
     const unsigned long long span = frame_off[f] - edge_base + __shfl_sync(FULL, off, 0);
-    double sum = 0.0;
+    /* The warp's energy sum must not depend on the arrival order of the row entries.  Each (float) energy is added
+     * as an integer multiple of 2^-36 -- integer addition is associative, so no second pass over the records just
+     * written is needed (that re-read missed L2 often enough to cost 0.9 GB of DRAM reads per 250 frames).  1,024
+     * edges of |E| < 2^17 stay inside 63 bits; 1.5e-11 absolute per edge against frame sums of 1e4..1e6 and a 1e-6
+     * relative contract.  A frame with an edge shorter than WN_SHORT_EDGE_A (the fused kernel counts them: only there can
+     * |E| reach 2^17) is summed by wn_k_stats from the written records in final order instead; which path runs depends
+     * on the data only, so the sum stays run-to-run deterministic either way. */
+    long long fix = 0;
     if (total && span + total <= edge_cap) {
         for (uint32_t e0 = 0; e0 < total; e0 += 32) {
             const uint32_t e = min(e0 + lane, total - 1);
@@ -137,6 +144,7 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
                 WN_CHECK(rank < rcnt && span + rpre + rank < edge_cap);
                 /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
                 const float en = __double2float_rn(wn_compute_energy((double)tlen, (double)tcos, ep));
+                fix += __double2ll_rn((double)en * 68719476736.0);
                 if (LAYOUT == WN_LAYOUT_CSR16) {
                     /* compact layout: {j, energy, length, cosine}, one aligned 16-byte store */
                     reinterpret_cast<uint4*>(edges)[span + rpre + rank] =
@@ -154,18 +162,14 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
                 }
             }
         }
-        /* energies in final order (own warp's writes, ordered by the barrier):
-         * the summation tree does not depend on arrival order -> deterministic */
-        __syncwarp();
-        for (uint32_t e = lane; e < total; e += 32)
-            sum += LAYOUT == WN_LAYOUT_CSR16 ? (double)__uint_as_float(reinterpret_cast<const uint4*>(edges)[span + e].y)
-                 : LAYOUT == WN_LAYOUT_CSR12 ? (double)energy_side[span + e]
-                                             : (double)edges[span + e].energy;
     }
-    /* fixed-tree warp reduction; one partial per warp (no block barrier), summed in order by wn_k_stats */
+    /* one partial per warp (no block barrier), summed in a fixed order by wn_k_stats; NaN = "this frame has energies the
+     * fixed-point sum may not hold": wn_k_stats then sums the warp's records in final order */
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) sum += __shfl_down_sync(FULL, sum, s);
-    if (lane == 0) block_sums[((size_t)f * gridDim.x + blockIdx.x) * (COPY_THREADS / 32) + warp] = sum;
+    for (int s = 16; s > 0; s >>= 1) fix += __shfl_down_sync(FULL, fix, s);
+    if (lane == 0)
+        block_sums[((size_t)f * gridDim.x + blockIdx.x) * (COPY_THREADS / 32) + warp] =
+            counters[f].short_edges ? __longlong_as_double(0x7ff8000000000000ll) : (double)fix * 1.4551915228366852e-11;   /* 2^-36 */
 }
 
 /* ---- per-frame statistics row: one warp per frame ----
@@ -175,14 +179,43 @@ __global__ void __launch_bounds__(128)
 wn_k_stats(const double* __restrict__ block_sums, int n_blocks,
            const unsigned long long* __restrict__ frame_total,
            const WnFrameCounters* __restrict__ counters, int n_frames, int n_table, WnSubset sub,
-           wn_frame_stats* __restrict__ stats)
+           wn_frame_stats* __restrict__ stats,
+           const wn_edge* __restrict__ edges, int layout, const float* __restrict__ energy_side,
+           const uint32_t* __restrict__ row_off, const unsigned long long* __restrict__ frame_off)
 {
+    constexpr unsigned FULL = 0xffffffffu;
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (f >= n_frames) return;
     double s = 0.0;
-    for (int b = lane; b < n_blocks; b += 32) s += block_sums[(size_t)f * n_blocks + b];
+    for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+        const int b = b0 + lane;
+        double v = b < n_blocks ? block_sums[(size_t)f * n_blocks + b] : 0.0;
+        /* partials flagged by wn_k_copy (energies beyond the fixed-point range): the 32 rows of that warp, summed by
+         * this warp in final order with a fixed tree */
+        unsigned flagged = __ballot_sync(FULL, v != v);
+        while (flagged) {
+            const int src = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            const int row0 = (b0 + src) * 32;                                  /* first row of the flagged warp */
+            unsigned long long lo = 0, hi = 0;                                 /* warps past the last row own nothing */
+            if (row0 < n_table) {
+                lo = frame_off[f] + row_off[(size_t)f * n_table + row0];
+                hi = row0 + 32 < n_table ? frame_off[f] + row_off[(size_t)f * n_table + row0 + 32] : frame_off[f + 1];
+            }
+            double t = 0.0;
+            for (unsigned long long e = lo + lane; e < hi; e += 32)
+                t += layout == WN_LAYOUT_CSR16 ? (double)__uint_as_float(reinterpret_cast<const uint4*>(edges)[e].y)
+                   : layout == WN_LAYOUT_CSR12 ? (double)energy_side[e]
+                                               : (double)edges[e].energy;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(FULL, t, o);
+            t = __shfl_sync(FULL, t, 0);
+            if (lane == src) v = t;
+        }
+        s += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(FULL, s, o);
     if (lane) return;
     const int n_sites = wn_frame_sites(sub, f, n_table);
     wn_frame_stats r;
@@ -204,7 +237,7 @@ void wn_launch_frameoff(const unsigned long long* frame_total, const uint32_t* f
 }
 
 void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt,
-                    const uint32_t* row_off, const unsigned long long* frame_off,
+                    const uint32_t* row_off, const unsigned long long* frame_off, const WnFrameCounters* counters,
                     int n_frames, int n_sites, WnEnergyParams ep, wn_edge* edges,
                     unsigned long long edge_cap, int layout, float* energy_side, double* block_sums, int* n_blocks_out,
                     cudaStream_t st)
@@ -213,20 +246,21 @@ void wn_launch_copy(const uint32_t* rowbuf, int row_cap, const uint32_t* row_cnt
     *n_blocks_out = (int)g.x * (COPY_THREADS / 32);      /* partial sums per frame */
     /* edge_cap counts 20-byte records; the compact layouts use the same buffer */
     if (layout == WN_LAYOUT_CSR16)
-        wn_k_copy<WN_LAYOUT_CSR16><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
+        wn_k_copy<WN_LAYOUT_CSR16><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, counters, n_sites, ep,
                                                                edges, edge_cap, 0ull, energy_side, block_sums);
     else if (layout == WN_LAYOUT_CSR12)
-        wn_k_copy<WN_LAYOUT_CSR12><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
+        wn_k_copy<WN_LAYOUT_CSR12><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, counters, n_sites, ep,
                                                                edges, edge_cap, 0ull, energy_side, block_sums);
     else
-        wn_k_copy<WN_LAYOUT_EDGES><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, n_sites, ep,
+        wn_k_copy<WN_LAYOUT_EDGES><<<g, COPY_THREADS, 0, st>>>(rowbuf, row_cap, row_cnt, row_off, frame_off, counters, n_sites, ep,
                                                                edges, edge_cap, 0ull, energy_side, block_sums);
 }
 
 void wn_launch_stats(const double* block_sums, int n_blocks, const unsigned long long* frame_total,
                      const WnFrameCounters* counters, int n_frames, int n_sites, WnSubset sub,
-                     wn_frame_stats* stats, cudaStream_t st)
+                     wn_frame_stats* stats, const wn_edge* edges, int layout, const float* energy_side,
+                     const uint32_t* row_off, const unsigned long long* frame_off, cudaStream_t st)
 {
     wn_k_stats<<<(n_frames + 3) / 4, 128, 0, st>>>(block_sums, n_blocks, frame_total, counters,
-                                                       n_frames, n_sites, sub, stats);
+                                                       n_frames, n_sites, sub, stats, edges, layout, energy_side, row_off, frame_off);
 }

@@ -569,6 +569,33 @@ def test_make_edges_on_a_caller_supplied_pair_list(ctx, oracle, capi):
     assert ei.value.code == capi.WN_ERR_BAD_ARG and "outside the table" in str(ei.value)
 
 
+def test_energy_sum_fast_and_ordered_paths(ctx, oracle):
+    """sum_energy of a frame: an exact fixed-point sum inside wn_k_copy (order-free), or -- when the fused kernel saw an
+    edge under 0.56 A, whose energy may leave the fixed-point range -- the written records summed in final order by
+    wn_k_stats.  Both within 1e-6 of the oracle, bit-identical run to run and independent of how frames are batched."""
+    n = 1000
+    box = oracle.synth_box(n)
+    frames = oracle.synth_frames(box, 11, 4).copy()
+    # frame 1: water 7 moved onto water 400 (O-O distance 0.02 nm): a huge, perfectly legal energy
+    frames[1, 3 * 7:3 * 7 + 3] += frames[1, 3 * 400] - frames[1, 3 * 7] - np.float32(0.02)
+    # frame 3: a second short pair, in the last rows (the copy's last, partly empty, warps)
+    frames[3, 3 * 998:3 * 998 + 3] += frames[3, 3 * 999] - frames[3, 3 * 998] + np.float32(0.015)
+    sa, ha, ty = oracle.water_site_table(n)
+    ctx.set_water_sites(n)
+    res = ctx.hbond_batch(frames)
+    oe, ost, oev, oties = oracle_frames(oracle, frames, sa, ha, ty)
+    compare_batch(res, oe, ost, oev, oties)
+    for f in (1, 3):                                       # the two frames really carry an edge under 0.56 A, and it dominates
+        assert (oe[f]["length"] < 0.56).sum() >= 1 and abs(ost[f, 3]) > 100 * abs(ost[0, 3])
+    for f in (0, 2):
+        assert (oe[f]["length"] < 0.56).sum() == 0
+    again = ctx.hbond_batch(frames)
+    assert np.array_equal(again["stats"]["sum_energy"].view(np.uint64), res["stats"]["sum_energy"].view(np.uint64))
+    for f in range(4):                                     # batch composition does not matter
+        one = ctx.hbond_batch(frames[f:f + 1])
+        assert one["stats"]["sum_energy"].view(np.uint64)[0] == res["stats"]["sum_energy"].view(np.uint64)[f]
+
+
 # ------------------------------------------------------------------ periodic boxes
 def oracle_frames_pbc(oracle, frames, boxes, site_atom, h_atom, site_type, first_limit=None):
     edges, stats, evals = [], [], 0
