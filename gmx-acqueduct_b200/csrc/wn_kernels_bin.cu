@@ -49,8 +49,15 @@ __device__ __forceinline__ int wn_cell_coord(double x, double o, double inv, int
     return min(max(c, 0), n - 1);
 }
 
+/* The staging kernels wait on gathers and (wn_k_bin) on returning atomics: resident warps matter more than registers
+ * (at the compiler's own 58-64 registers only half of the warp slots were filled: issue utilisation 16-20 %; measured
+ * 8 / 6 / 5 / 4 blocks per SM: 0.503 / 0.482 / 0.482 / 0.484 ms for the staging of 250 frames). */
+#ifndef WN_STAGE_MINBLOCKS
+#define WN_STAGE_MINBLOCKS 6
+#endif
+
 /* ---- cell id + arrival rank per site ---- */
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WN_STAGE_MINBLOCKS)
 wn_k_bin(const float* __restrict__ frames, int natoms, const int* __restrict__ site_atom,
          int n_sites, WnSubset sub, int cell_cap, const WnGrid* __restrict__ grid, int* __restrict__ cell_cnt,
          int* __restrict__ site_cell, int* __restrict__ site_rank)
@@ -58,7 +65,7 @@ wn_k_bin(const float* __restrict__ frames, int natoms, const int* __restrict__ s
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= wn_frame_sites(sub, f, n_sites)) return;
-    const WnGrid g = grid[f];
+    const WnGrid& g = grid[f];           /* fields are read where they are needed (a by-value copy held 40 registers) */
     const float* p = frames + ((size_t)f * natoms + (size_t)__ldg(site_atom + wn_table_row(sub, f, i))) * 3;
     float x = p[0], y = p[1], z = p[2];
     if (g.pbc == 1) { x = wn_wrap(x, g.L[0], g.invL[0]); y = wn_wrap(y, g.L[1], g.invL[1]); z = wn_wrap(z, g.L[2], g.invL[2]); }
@@ -73,7 +80,7 @@ wn_k_bin(const float* __restrict__ frames, int natoms, const int* __restrict__ s
 }
 
 /* ---- write the cell-sorted site records ---- */
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WN_STAGE_MINBLOCKS)
 wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict__ site_atom,
              const int* __restrict__ hv_atom, const uint32_t* __restrict__ meta, int n_sites, WnSubset sub,
              int hs, int cell_cap, const int* __restrict__ cell_start,
@@ -88,10 +95,12 @@ wn_k_scatter(const float* __restrict__ frames, int natoms, const int* __restrict
     const float* fr = frames + (size_t)f * natoms * 3;
     const float* p = fr + 3 * (size_t)__ldg(site_atom + row);
     float x = p[0], y = p[1], z = p[2];
-    const int pbc = grid[f].pbc;
-    double L[3] = {0, 0, 0}, invL[3] = {0, 0, 0}, tri[3] = {0, 0, 0};
+    const WnGrid& g = grid[f];           /* box fields are read inside the periodic branches only (registers) */
+    const int pbc = g.pbc;
+    const double* L = g.L;
+    const double* invL = g.invL;
+    const double* tri = g.tri;
     if (pbc) {
-        for (int c = 0; c < 3; ++c) { L[c] = grid[f].L[c]; invL[c] = grid[f].invL[c]; tri[c] = grid[f].tri[c]; }
         if (pbc == 1) { x = wn_wrap(x, L[0], invL[0]); y = wn_wrap(y, L[1], invL[1]); z = wn_wrap(z, L[2], invL[2]); }
         else wn_wrap_tric(x, y, z, L, tri);
     }
