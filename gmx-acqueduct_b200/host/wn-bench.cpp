@@ -88,7 +88,9 @@ int main(int argc, char** argv)
         int last_frnr = -1, first_timed = 1 << 30;
         bool in_order = true;
         const wn_energy_params ep = wn_energy_defaults();
+        std::vector<uint64_t> per_gpu((size_t)gpus, 0);
         auto sink = [&](const FrameResult& r) {
+            if (r.frnr >= first_timed && r.device >= 0 && r.device < gpus) ++per_gpu[(size_t)r.device];
             in_order = in_order && r.frnr == last_frnr + 1;
             last_frnr = r.frnr;
             if (r.frnr >= first_timed) { edges_seen += r.n_edges; ++frames_seen; }
@@ -164,19 +166,21 @@ int main(int argc, char** argv)
             find_ms = (now() - t0) / reps * 1e3;
         }
         const size_t esz = layout == WN_LAYOUT_CSR12 ? 12 : layout == WN_LAYOUT_CSR16 ? 16 : 20;
+        std::string pg;
+        for (int g = 0; g < gpus; ++g) pg += (g ? ", " : "") + std::to_string(per_gpu[(size_t)g]);
         std::string bs;
         for (size_t k = 0; k < batch_s.size(); ++k) { char t[32]; std::snprintf(t, sizeof t, "%s%.1f", k ? ", " : "", batch_s[k] * 1e3); bs += t; }
         std::printf("{\"bench\": \"wn_bench (C++ drop-in: FrameBatcher over the C ABI)\", \"e2e_cpp\": %.1f, \"unit\": \"frames/s\", "
                     "\"gpus\": %d, \"mode\": \"%s\", \"layout_bytes_per_edge\": %zu, \"n_waters\": %d, \"batch_frames\": %d, "
                     "\"timed_frames\": %llu, \"timed_s\": %.4f, \"edges_per_frame\": %.1f, \"in_frame_order\": %s, "
                     "\"h2d_bytes_per_frame\": %zu, \"d2h_bytes_per_frame\": %.0f, \"warmup_s\": %.3f, \"stats_rows_reduced\": %zu, "
-                    "\"find_wall_ms\": %.3f, \"find_pairs\": %zu, \"checksum\": %.6g, \"batch_call_ms\": [%s], "
+                    "\"find_wall_ms\": %.3f, \"find_pairs\": %zu, \"checksum\": %.6g, \"frames_per_gpu\": [%s], \"batch_call_ms\": [%s], "
                     "\"last_call\": {\"h2d_ms\": %.2f, \"kernels_ms\": %.2f, \"d2h_ms\": %.2f, \"passes\": %d}}\n",
                     (double)timed_frames / t_run, gpus, mode.c_str(), esz, waters, batch, (unsigned long long)timed_frames, t_run,
                     timed_frames ? (double)timed_edges / (double)timed_frames : 0.0, in_order ? "true" : "false",
                     frame_floats * sizeof(float),
                     timed_frames ? (double)timed_edges * (double)esz / (double)timed_frames + 4.0 * waters + 48.0 : 0.0,
-                    t_first, reduced_rows, find_ms, n_pairs, checksum, bs.c_str(), last_tm.h2d_ms, last_tm.total_ms, last_tm.d2h_ms,
+                    t_first, reduced_rows, find_ms, n_pairs, checksum, pg.c_str(), bs.c_str(), last_tm.h2d_ms, last_tm.total_ms, last_tm.d2h_ms,
                     last_tm.passes);
         return in_order ? 0 : 1;
     } catch (const std::exception& e) {

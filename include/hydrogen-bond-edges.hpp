@@ -201,6 +201,7 @@ public:
 
 private:
     struct Lane;
+    int chooseLane() const;        // GPU expected to be free first (not used by submit() yet, see there)
     void init(int natoms, int batch_frames, int layout);
     void submit();                      // current lane's filling buffer -> GPU
     void deliverOldest();               // wait for the oldest in-flight batch, hand it to the sink
