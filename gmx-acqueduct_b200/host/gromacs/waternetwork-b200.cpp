@@ -8,7 +8,13 @@
 //
 // It is the module of the reference (src/waternetwork.cpp: class WaterNetwork, include/waternetwork.hpp)
 // with the per-frame body of analyzeFrame (:538-652) replaced by frame batching:
-//   initOptions     same option names and defaults (:343-379); -don/-doff/-aon/-aoff now reach the energy (F6)
+//   initOptions     same option names and defaults (:343-379).  -don/-doff/-aon/-aoff are parsed and IGNORED, as in
+//                   the reference (computeEnergy is always called with its defaults 5.5/6.5/0.25/0.0),
+//                   unless the new switch -switchopts is given -- then they reach the energy
+//   differences from the reference binary a user must know: (1) the pair list is Brute's, not Delaunay's (twice the
+//                   edges, lexicographic order: INTEGRATION.md section 0); (2) there is no alpha-shape filter, so
+//                   every solvent water is a site and the "buried" data set holds the solvent count, not num_filtered;
+//                   (3) EXPERIMENTAL until built and run against GROMACS 2019.x
 //   initAnalysis    makeSites for both selections through the GROMACS-free restatement (include/make-sites.hpp),
 //                   solvent ids offset (:420-423), nodes file and edges header (:461-499), site table upload
 //   analyzeFrame    the frame's coordinates (protein selection, then solvent selection) are pushed into a
@@ -64,6 +70,8 @@ public:
         options->addOption(gmx::DoubleOption("doff").store(&lengthOff_).description("Radial switch ends here (Angstrom)"));
         options->addOption(gmx::DoubleOption("aon").store(&angleOn_).description("Angle switch bound (cosine squared)"));
         options->addOption(gmx::DoubleOption("aoff").store(&angleOff_).description("Angle switch bound (cosine squared)"));
+        options->addOption(gmx::BooleanOption("switchopts").store(&useSwitchOptions_)
+                               .description("Apply -don/-doff/-aon/-aoff to the energy (the reference parses and ignores them)"));
         options->addOption(gmx::IntegerOption("batch").store(&batchFrames_).description("Frames per GPU batch"));
         options->addOption(gmx::BooleanOption("usepbc").store(&usePbc_).description("Minimum-image search in the frame's box"));
     }
@@ -113,8 +121,10 @@ public:
 
         finder_ = std::make_shared<CudaFindPairs>(0);        // the FindPairs drop-in (mp_); the batch path below fuses it
         engine_.reset(new HydrogenBondEdges(0));
-        engine_->setRadiusShift((float)lengthOn_, (float)lengthOff_);
-        engine_->setAngleShift((float)angleOn_, (float)angleOff_);
+        if (useSwitchOptions_) {                              // default: the reference's fixed 5.5 / 6.5 / 0.25 / 0.0
+            engine_->setRadiusShift((float)lengthOn_, (float)lengthOff_);
+            engine_->setAngleShift((float)angleOn_, (float)angleOff_);
+        }
         engine_->setSites(table, hydrogens);
 
         buriedData_.setColumnCount(0, 2);
@@ -235,6 +245,7 @@ private:
     double lengthOn_, lengthOff_, angleOn_, angleOff_;
     int batchFrames_;
     bool usePbc_;
+    bool useSwitchOptions_ = false;
     gmx::Selection solventSel_, proteinSel_;
     gmx::AnalysisData buriedData_, hydroBondData_;
     std::shared_ptr<FindPairs> finder_;                   // was std::shared_ptr<DelaunayFindPairs> mp_ (include/waternetwork.hpp:94)
