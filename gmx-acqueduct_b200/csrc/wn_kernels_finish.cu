@@ -100,12 +100,13 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
     /* frame_off carries the offset of this pass inside the call's edge array */
     const unsigned long long span = frame_off[f] - edge_base + __shfl_sync(FULL, off, 0);
     /* The warp's energy sum must not depend on the arrival order of the row entries.  Each (float) energy is added
-     * as an integer multiple of 2^-36 -- integer addition is associative, so no second pass over the records just
-     * written is needed (that re-read missed L2 often enough to cost 0.9 GB of DRAM reads per 250 frames).  1,024
-     * edges of |E| < 2^17 stay inside 63 bits; 1.5e-11 absolute per edge against frame sums of 1e4..1e6 and a 1e-6
-     * relative contract.  A frame with an edge shorter than WN_SHORT_EDGE_A (the fused kernel counts them: only there can
-     * |E| reach 2^17) is summed by wn_k_stats from the written records in final order instead; which path runs depends
-     * on the data only, so the sum stays run-to-run deterministic either way. */
+     * as an integer multiple of 2^-32 -- integer addition is associative, so no second pass over the records just
+     * written is needed (that re-read missed L2 often enough to cost 0.9 GB of DRAM reads per 250 frames).
+     * Range: |E| <= 3855/r^6 < 2^17 for every edge of at least WN_SHORT_EDGE_A = 0.56 A (cos^4 and both switches are
+     * <= 1), so a warp's 32 rows of up to 512 slots stay inside 63 bits; resolution 2.3e-10 per edge, i.e. <= 1e-9
+     * relative on frame sums of 1e3..1e6 against a 1e-6 contract.  A frame with a shorter edge (the fused kernel
+     * counts them) or a row capacity beyond 512 is summed by wn_k_stats from the written records in final order
+     * instead; which path runs depends on the data only, so the sum stays run-to-run deterministic either way. */
     long long fix = 0;
     if (total && span + total <= edge_cap) {
         for (uint32_t e0 = 0; e0 < total; e0 += 32) {
@@ -144,7 +145,7 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
                 WN_CHECK(rank < rcnt && span + rpre + rank < edge_cap);
                 /* energies.push_back(computeEnergy(distance, proj)): float  (:222,:234) */
                 const float en = __double2float_rn(wn_compute_energy((double)tlen, (double)tcos, ep));
-                fix += __double2ll_rn((double)en * 68719476736.0);
+                fix += __double2ll_rn((double)en * 4294967296.0);
                 if (LAYOUT == WN_LAYOUT_CSR16) {
                     /* compact layout: {j, energy, length, cosine}, one aligned 16-byte store */
                     reinterpret_cast<uint4*>(edges)[span + rpre + rank] =
@@ -169,7 +170,8 @@ wn_k_copy(const uint32_t* __restrict__ rowbuf, int row_cap,
     for (int s = 16; s > 0; s >>= 1) fix += __shfl_down_sync(FULL, fix, s);
     if (lane == 0)
         block_sums[((size_t)f * gridDim.x + blockIdx.x) * (COPY_THREADS / 32) + warp] =
-            counters[f].short_edges ? __longlong_as_double(0x7ff8000000000000ll) : (double)fix * 1.4551915228366852e-11;   /* 2^-36 */
+            (counters[f].short_edges || row_cap > 512) ? __longlong_as_double(0x7ff8000000000000ll)
+                                                       : (double)fix * 2.3283064365386963e-10;   /* 2^-32 */
 }
 
 /* ---- per-frame statistics row: one warp per frame ----

@@ -196,3 +196,81 @@ def test_host_energy_header_matches_the_oracle_bit_for_bit(tmp_path, oracle):
                            "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("0 of "), r.stdout + r.stderr
+
+
+# ---------------------------------------------------------------- device arithmetic restated on the CPU
+def test_cell_list_reject_bound_is_a_superset_of_the_exact_pair_test():
+    """wn_k_cp_sweep rejects candidates with an fp32 test on origin-relative float copies (csrc/wn_kernels_cellpairs.cu);
+    the bound comes from cellpair_grid (csrc/wn_capi.cu): e = 2^-20 (amax + lmax + 2.1),
+    bound = (4.225 + 2 sqrt(3 * 4.225) e + 3 e^2)(1 + 2^-21), rounded up to float.  Restated in numpy (float32 ops round
+    like the device's; both a fused and an unfused accumulation are tried): no pair the reference's fp64 test accepts
+    (10 * d2 < 42.25) may be rejected, for systems from 1 nm to 100 um across and pairs hugging the cutoff."""
+    rng = np.random.default_rng(5)
+    for amax in (1.0, 10.0, 100.0, 1.0e3, 1.0e4, 1.0e5):
+        for lmax, pbc in ((0.0, False), (amax, True)):
+            e = np.ldexp(amax + lmax + 2.1, -20)
+            bd = (4.225 + 2.0 * np.sqrt(3.0 * 4.225) * e + 3.0 * e * e) * (1.0 + np.ldexp(1.0, -21))
+            bf = np.float32(bd)
+            if float(bf) < bd:
+                bf = np.nextafter(bf, np.float32(np.inf))
+            n = 20000
+            a = rng.uniform(0.0, amax, size=(n, 3))
+            u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+            # distances hugging the cutoff from below, plus a spread of smaller ones
+            r = np.where(rng.random(n) < 0.7, np.sqrt(4.225) * (1.0 - rng.uniform(0, 1e-7, n)), rng.uniform(0, np.sqrt(4.225), n))
+            b = a + u * r[:, None]
+            d = a - b
+            d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+            accepted = 10.0 * d2 < 42.25
+            assert accepted.sum() > n // 2
+            af, bf32 = a.astype(np.float32), b.astype(np.float32)          # origin 0: the copies the kernel stores
+            df = (af - bf32).astype(np.float32)
+            if pbc:
+                L = np.float32(lmax)
+                df = (df - np.rint(df * (np.float32(1.0) / L)).astype(np.float32) * L).astype(np.float32)
+            unfused = ((df[:, 0] * df[:, 0] + df[:, 1] * df[:, 1]).astype(np.float32) + df[:, 2] * df[:, 2]).astype(np.float32)
+            d64 = df.astype(np.float64)
+            fused = ((d64[:, 0] * d64[:, 0] + d64[:, 1] * d64[:, 1]) + d64[:, 2] * d64[:, 2]).astype(np.float32)   # one rounding
+            for d2f in (unfused, fused):
+                assert np.all(d2f[accepted] <= bf), (amax, pbc, float((d2f[accepted] - bf).max()))
+            # and the bound stays tight where coordinates are small: few false positives
+            if amax <= 100.0 and not pbc:
+                far = 10.0 * d2 >= 42.25 * (1.0 + 1e-3)
+                assert not np.any(unfused[far] <= bf)
+
+
+def test_block_decode_reciprocals_give_exact_quotients():
+    """wn_divmod (csrc/wn_kernels_edges.cu): q = umulhi(x, ceil(2^32 / d)) corrected by at most one, for the block
+    index -> (bx, cy, cz) decode; exact for every divisor and every block index a pass can have."""
+    rng = np.random.default_rng(9)
+    ds = np.concatenate([np.arange(1, 600), rng.integers(600, 1 << 20, size=400)]).astype(np.uint64)
+    for d in ds:
+        m = np.uint64(0xffffffff) if d == 1 else np.uint64(((1 << 32) + int(d) - 1) // int(d))
+        x = np.concatenate([np.arange(0, 2000), rng.integers(0, 1 << 31, size=3000),
+                            np.array([int(d) - 1, int(d), int(d) + 1, (1 << 31) - 1])]).astype(np.uint64)
+        q = ((x * m) >> np.uint64(32)).astype(np.int64)
+        r = x.astype(np.int64) - q * int(d)
+        q = np.where(r < 0, q - 1, np.where(r >= int(d), q + 1, q))
+        r = x.astype(np.int64) - q * int(d)
+        assert np.array_equal(q, x.astype(np.int64) // int(d)) and np.all((r >= 0) & (r < int(d)))
+
+
+def test_fixed_point_energy_sum_range_and_accuracy():
+    """wn_k_copy adds every float energy as a multiple of 2^-32 (csrc/wn_kernels_finish.cu).  With the oracle's
+    computeEnergy: (1) no edge of at least 0.56 A (WN_SHORT_EDGE_A; shorter ones send the frame to the ordered path)
+    reaches 2^17, so 32 rows x 512 slots stay inside 63 bits; (2) the fixed-point sum of a frame's energies equals the
+    fp64 sum to ~1e-9 relative; (3) it does not depend on the order."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import wn_oracle_py as oracle
+    r = np.concatenate([np.float32(0.56) + np.arange(0, 4000, dtype=np.float32) * np.float32(1e-4), np.linspace(0.96, 6.5, 3000).astype(np.float32)])
+    worst = max(abs(oracle.compute_energy(float(x), 1.0)) for x in r)
+    assert worst < 2.0 ** 17 and worst * 32 * 512 * 2.0 ** 32 < 2.0 ** 63
+    n = 1000
+    frame = oracle.synth_frames(oracle.synth_box(n), 0, 1)[0]
+    e = oracle.frame_hbonds(frame, *oracle.water_site_table(n))[0]["energy"]
+    fix = np.rint(e.astype(np.float64) * 2.0 ** 32).astype(np.int64)
+    total = float(fix.sum()) * 2.0 ** -32
+    ref = float(np.sum(e.astype(np.float64)))
+    assert abs(total - ref) <= 1e-9 * abs(ref)
+    perm = np.random.default_rng(1).permutation(len(fix))
+    assert int(fix[perm].sum()) == int(fix.sum())
