@@ -1,6 +1,7 @@
 // hydrogen-bond-edges.cpp -- HydrogenBondEdges and FrameBatcher over the C ABI
 // (see include/hydrogen-bond-edges.hpp).
 #include "hydrogen-bond-edges.hpp"
+#include "frame-copy-pool.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -397,9 +398,16 @@ void FrameBatcher::commit(int frnr)
     if ((int)l.frnr[l.fill].size() >= batch_frames_) submit();
 }
 
+void FrameBatcher::setCopyThreads(int n)
+{
+    copy_pool_.reset(n > 1 ? new FrameCopyPool(n - 1) : nullptr);
+}
+
 void FrameBatcher::push(int frnr, const float* xyz)
 {
-    std::memcpy(stage(), xyz, (size_t)natoms_ * 3 * sizeof(float));
+    const size_t bytes = (size_t)natoms_ * 3 * sizeof(float);
+    if (copy_pool_) copy_pool_->copy(stage(), xyz, bytes);
+    else std::memcpy(stage(), xyz, bytes);
     commit(frnr);
 }
 

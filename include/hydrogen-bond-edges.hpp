@@ -20,6 +20,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <functional>
+#include <memory>
 #include <future>
 #include <utility>
 #include <vector>
@@ -191,6 +192,9 @@ public:
     // switches the pipelining off (batch k is fully delivered before batch k+1 is submitted).
     typedef std::function<void(const std::vector<int>& frameNumbers, const HydrogenBondBatch& batch)> BatchHook;
     void setBatchHook(BatchHook hook) { batch_hook_ = hook; }
+    // push() copies every frame into pinned staging memory; one host thread moves ~7 GB/s (~6 k frames/s of the
+    // 100k-atom box).  n > 1: n - 1 helper threads share each copy (include/frame-copy-pool.hpp).  Default 1.
+    void setCopyThreads(int n);
     void setPipelined(bool on) { pipelined_ = on; }
     // After finish(): one row per pushed frame, in push order.  With several GPUs this is the NCCL sum of
     // the per-GPU zero-padded tables (wn_stats_reduce), with one GPU the rows as delivered.
@@ -216,6 +220,7 @@ private:
     uint64_t frames_done_, frames_pushed_;
     std::vector<wn_frame_stats> reduced_;
     std::vector<double> batch_seconds_;
+    std::unique_ptr<class FrameCopyPool> copy_pool_;
 };
 
 #endif

@@ -149,6 +149,17 @@ def test_edge_file_writer_is_byte_identical_to_reference_iostream_formatting():
     assert r.returncode == 0 and "test_writer OK" in r.stdout, r.stdout + r.stderr
 
 
+def test_frame_copy_pool_is_byte_exact():
+    """include/frame-copy-pool.hpp (the helper threads FrameBatcher::push can share a frame copy with): odd sizes and
+    offsets, back-to-back and spaced copies, 0-3 helpers, byte for byte; clean shutdown."""
+    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "test_copy_pool")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "test_copy_pool OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_make_sites_rules():
     """f3: makeSites typing rules (src/waternetwork.cpp:95-180) restated on plain arrays."""
     exe = os.path.join(ROOT, "gmx-acqueduct_b200", "test_sites")
