@@ -389,6 +389,10 @@ def test_energy_known_answers_through_the_batch(ctx, oracle):
         assert abs(float(ed["energy"]) - float(golden)) <= ENERGY_RTOL * abs(float(golden)), (rf, cf, ed["energy"], golden)
         if golden == 0:
             assert np.signbit(ed["energy"]) == np.signbit(golden)
+        # a one-edge frame: the statistics row's sum is that edge's float energy, however small (energies down to
+        # 1e-8 sit below the 2^-33 resolution of the fixed-point partials; wn_k_stats then sums the written records)
+        se = float(res["stats"]["sum_energy"][k])
+        assert abs(se - float(ed["energy"])) <= 1.2e-7 * abs(float(ed["energy"])), (rf, cf, se, ed["energy"])
 
 
 def test_find_pairs_full_size_rows(ctx, oracle):

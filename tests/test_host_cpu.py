@@ -285,3 +285,19 @@ def test_fixed_point_energy_sum_range_and_accuracy():
     assert abs(total - ref) <= 1e-9 * abs(ref)
     perm = np.random.default_rng(1).permutation(len(fix))
     assert int(fix[perm].sum()) == int(fix.sum())
+    # (4) wn_k_stats keeps the fixed-point sum only where |sum| * 1e-7 >= n_edges * 2^-33 and sums the float records
+    # otherwise: with that rule every subset of a frame's edges -- down to single edges of 1e-8 at the cutoff -- stays
+    # inside 1.2e-7 relative of the fp64 sum of its float energies (contract: 1e-6)
+    rng = np.random.default_rng(2)
+    order = np.argsort(np.abs(e))
+    subsets = [order[:k] for k in (1, 2, 3, 5, 10, 40, 200)] + [np.array([k]) for k in order[:60]] + \
+              [rng.choice(len(e), size=int(k), replace=False) for k in rng.integers(1, 30, size=200)]
+    fallbacks = 0
+    for idx in subsets:
+        ee = e[idx].astype(np.float64)
+        s_fix = float(np.rint(ee * 2.0 ** 32).sum()) * 2.0 ** -32
+        keep = abs(s_fix) * 1e-7 >= len(ee) * 2.0 ** -33
+        fallbacks += not keep
+        got = s_fix if keep else float(ee.sum())
+        assert abs(got - float(ee.sum())) <= 1.2e-7 * abs(float(ee.sum()))
+    assert fallbacks > 0
