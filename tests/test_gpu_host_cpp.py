@@ -30,80 +30,15 @@ def test_cpp_host_mirror_fails_loudly_without_gpu():
     assert r.returncode == 2 and "no CPU fallback" in r.stderr
 
 
-def _write_gro(path, frames, box, with_time=True):
-    """Multi-frame .gro of a pure water box (OW, HW1, HW2 per SOL residue), 8.3 coordinate fields."""
-    nf, natoms, _ = frames.shape
-    with open(path, "w") as fh:
-        for f in range(nf):
-            fh.write("synthetic water box%s\n" % (" t= %9.5f" % (2.0 * f) if with_time else ""))
-            fh.write("%5d\n" % natoms)
-            for a in range(natoms):
-                w = a // 3
-                fh.write("%5d%-5s%5s%5d%8.3f%8.3f%8.3f\n" % ((w + 1) % 100000, "SOL", ("OW", "HW1", "HW2")[a % 3],
-                                                           (a + 1) % 100000, *frames[f, a]))
-            fh.write("%10.5f%10.5f%10.5f\n" % (box, box, box))
-
-
-def _parse_back(frames):
-    """What the driver reads: every coordinate through its 8.3 text field and (float)strtod."""
-    import numpy as np
-    txt = np.char.mod("%8.3f", frames.astype(np.float64))
-    return txt.astype(np.float64).astype(np.float32)
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("pbc,gpu_text", [(False, 1), (True, 1), (False, 0)])
 def test_standalone_driver_writes_the_reference_files(tmp_path, pbc, gpu_text):
     """wn_waternetwork on a synthetic .gro trajectory: edges file, nodes file and statistics rows equal
     what the oracle (open boundary) / the periodic oracle gives for the same parsed coordinates."""
-    import numpy as np
-    import sys
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import wn_oracle_py as o
-    n, nf = 216, 3
-    sb = o.synth_box(n, model=o.MODEL_SPC)
-    frames = o.synth_frames(sb, 0, nf)
-    box = float(sb.box)
-    gro = str(tmp_path / "traj.gro")
-    _write_gro(gro, frames, box)
+    import driver_cases
     exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
     assert os.path.exists(exe), "build first: __graft_entry__.build()"
-    args = [exe, "-f", gro, "-edges", str(tmp_path / "edges"), "-nodes", str(tmp_path / "nodes"),
-            "-ohb", str(tmp_path / "ohb.xvg"), "-obw", str(tmp_path / "obw.xvg"), "-batch", "2", "-gpu-text", str(gpu_text),
-            "-components", "0.5", "-ocomp", str(tmp_path / "comp.xvg")]
-    if pbc:
-        args.append("-pbc")
-    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "Solvent has : 216 Sites of out 648 atoms." in r.stderr
-
-    parsed = _parse_back(frames)
-    sa, ha, ty = o.water_site_table(n)
-    boxf = np.float32(np.float64("%10.5f" % box))
-    want = "%6s%8s%6s%6s%8s%6s%8s%8s%8s" % ("#Id", "AtmId", "ResId", "Id", "AtmId", "ResId", "Energy", "Length", "Cos\n")
-    ohb = ""
-    comp = ""
-    for f in range(nf):
-        if pbc:
-            e, st, _, _ = o.frame_hbonds_pbc(parsed[f], sa, ha, ty, np.array([boxf] * 3, np.float32))
-        else:
-            e, st, _, _ = o.frame_hbonds(parsed[f], sa, ha, ty)
-        want += "#--- frame %d ---\n" % f
-        # ids: solvent site w has id (w + 1) + nProtein + 1 = w + 2  (src/waternetwork.cpp:420-423)
-        want += "".join("%6d%6d%8.4f%8.4f%8.4f\n" % (a + 2, b + 2, en, ln, cs)
-                        for a, b, en, ln, cs in zip(e["i"], e["j"], e["energy"].astype(np.float64),
-                                                    e["length"].astype(np.float64), e["cosine"].astype(np.float64)))
-        ohb += " %11.3f %8.3f %8.3f %8.3f %8.3f %8.3f %8.3f\n" % (2.0 * f, n, len(e), len(e) / n, 0, 0, 0)
-        _, cst = o.components(e, n, 0.5)
-        comp += " %11.3f %8d %8d %8d %8d\n" % (2.0 * f, cst[0], cst[1], cst[2], cst[3])
-    got = open(str(tmp_path / "edges.dat")).read()
-    assert got == want
-    assert open(str(tmp_path / "comp.xvg")).read() == comp
-    assert open(str(tmp_path / "ohb.xvg")).read() == ohb
-    assert open(str(tmp_path / "obw.xvg")).read() == "".join(" %11.3f %8.3f %8.3f\n" % (2.0 * f, n, 0) for f in range(nf))
-    nodes = open(str(tmp_path / "nodes.dat")).read().splitlines()
-    assert len(nodes) == 1 + n and nodes[0].split() == ["#Id", "AtmId", "Name", "ResId", "Res", "Type", "Hyd"]
-    assert nodes[1].split()[:3] == ["2", "0", "OW"]
+    driver_cases.check_reference_files(exe, tmp_path, pbc, gpu_text)
 
 
 def test_standalone_driver_fails_loudly_without_gpu(tmp_path):
@@ -131,39 +66,8 @@ def test_standalone_driver_fails_loudly_without_gpu(tmp_path):
 @pytest.mark.gpu
 def test_standalone_driver_buried_lists(tmp_path):
     """-buried: a different water list per frame; ids in the edge file are those of the listed waters."""
-    import numpy as np
-    import sys
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import wn_oracle_py as o
-    n, nf = 216, 3
-    sb = o.synth_box(n, model=o.MODEL_SPC)
-    frames = o.synth_frames(sb, 0, nf)
-    gro = str(tmp_path / "traj.gro")
-    _write_gro(gro, frames, float(sb.box), with_time=False)
-    rng = np.random.default_rng(2)
-    lists = [np.sort(rng.choice(n, size=k, replace=False)) for k in (150, 0, 216)]
-    (tmp_path / "buried.txt").write_text("".join(" ".join(str(int(w)) for w in l) + "\n" for l in lists))
-    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
-    r = subprocess.run([exe, "-f", gro, "-edges", str(tmp_path / "edges"), "-nodes", "", "-ohb", str(tmp_path / "ohb.xvg"),
-                        "-obw", str(tmp_path / "obw.xvg"), "-buried", str(tmp_path / "buried.txt"), "-batch", "4"],
-                       capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout + r.stderr
-    parsed = _parse_back(frames)
-    want = "%6s%8s%6s%6s%8s%6s%8s%8s%8s" % ("#Id", "AtmId", "ResId", "Id", "AtmId", "ResId", "Energy", "Length", "Cos\n")
-    obw = ""
-    for f in range(nf):
-        l = lists[f]
-        sa = (3 * l).astype(np.int32)
-        ha = np.stack([3 * l, 3 * l + 1], axis=1).astype(np.int32)
-        ty = np.full(len(l), o.WATER, np.uint8)
-        e, st, _, _ = o.frame_hbonds(parsed[f], sa, ha, ty)
-        want += "#--- frame %d ---\n" % f
-        want += "".join("%6d%6d%8.4f%8.4f%8.4f\n" % (l[a] + 2, l[b] + 2, en, ln, cs)
-                        for a, b, en, ln, cs in zip(e["i"], e["j"], e["energy"].astype(np.float64),
-                                                    e["length"].astype(np.float64), e["cosine"].astype(np.float64)))
-        obw += " %11.3f %8.3f %8.3f\n" % (f, len(l), 0)
-    assert open(str(tmp_path / "edges.dat")).read() == want
-    assert open(str(tmp_path / "obw.xvg")).read() == obw
+    import driver_cases
+    driver_cases.check_buried_lists(os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork"), tmp_path)
 
 
 def _device_count():
@@ -176,34 +80,12 @@ def _device_count():
 def test_standalone_driver_frame_sharding_over_gpus(tmp_path):
     """wn_waternetwork -gpus N (frame blocks round-robin over the GPUs, one context + worker thread each,
     NCCL sum of the statistics tables for the .xvg rows): every file byte-identical to the one-GPU run.
-    Needs two GPUs in the box (gpurun --gpus 2); the one-GPU pipelined path is compared as well."""
-    import sys
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import wn_oracle_py as o
-    n, nf = 216, 11
-    sb = o.synth_box(n, model=o.MODEL_SPC)
-    frames = o.synth_frames(sb, 0, nf)
-    gro = str(tmp_path / "traj.gro")
-    _write_gro(gro, frames, float(sb.box))
-    exe = os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork")
-
-    def run(tag, extra):
-        d = tmp_path / tag
-        d.mkdir()
-        r = subprocess.run([exe, "-f", gro, "-edges", str(d / "edges"), "-nodes", str(d / "nodes"), "-ohb", str(d / "ohb.xvg"),
-                            "-obw", str(d / "obw.xvg"), "-batch", "2"] + extra, capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, r.stdout + r.stderr
-        return {k: open(str(d / k)).read() for k in ("edges.dat", "nodes.dat", "ohb.xvg", "obw.xvg")}
-
-    base = run("one", ["-gpu-text", "0"])
-    assert base["edges.dat"].count("#--- frame") == nf
-    assert run("one_gputext", ["-gpu-text", "1"]) == base
-    ndev = _device_count()
-    if ndev < 2:
+    Needs two GPUs in the box (gpurun --gpus 2); the one-GPU pipelined path is compared as well.  The same check
+    runs on the CPU box against the stand-in C ABI with 8 "GPUs" (tests/test_host_mock_cpu.py)."""
+    import driver_cases
+    done = driver_cases.check_frame_sharding(os.path.join(ROOT, "gmx-acqueduct_b200", "wn_waternetwork"), tmp_path, _device_count())
+    if not done:
         pytest.skip("one GPU in this box: sharded run not exercised (run under gpurun --gpus 2)")
-    for g in sorted({2, min(ndev, 4), min(ndev, 8)}):
-        assert run("g%d" % g, ["-gpus", str(g)]) == base
-        assert run("g%d_pbc" % g, ["-gpus", str(g), "-pbc"]) == run("one_pbc_%d" % g, ["-pbc"])
 
 
 @pytest.mark.gpu

@@ -1,0 +1,120 @@
+"""The C++ host mirror (CudaFindPairs, HydrogenBondEdges, FrameBatcher, the standalone driver) on a CPU box.
+
+The product has no CPU path: libwn_b200.so fails loudly without a device.  These tests link the SAME host sources
+against tests/mock/wn_mock_abi.cpp -- a stand-in for the C ABI with the test oracle behind it, test infrastructure
+only -- so that the host logic around the C ABI is exercised here: batching, pipelining, frame order, frame blocks
+round-robin over several "GPUs" (the N>1 path of SURVEY 8e in the C++ product), the summed statistics table, the
+files the driver writes.  The GPU suite runs the same checks (tests/driver_cases.py, tests/cpp/test_host.cpp) against
+the shipped binaries on a B200."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK = os.path.join(ROOT, "tests", "mock")
+BUILD = os.path.join(MOCK, "build")
+
+
+@pytest.fixture(scope="module")
+def mock_build():
+    subprocess.check_call(["make", "-s", "-j4", "-C", MOCK, "all"])
+    return BUILD
+
+
+def _run(exe, timeout=300, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([exe], capture_output=True, text=True, timeout=timeout, env=e)
+
+
+def test_cpp_host_mirror_on_the_stand_in(mock_build):
+    """tests/cpp/test_host.cpp, unchanged: FindPairs drop-in, batched == unbatched, makeEdges on a pair list, periodic
+    and triclinic boxes, GPU-text == host writer, components, site lists, compact layouts, several GPUs."""
+    r = _run(os.path.join(mock_build, "test_host_mock"))
+    assert r.returncode == 0 and "test_host OK" in r.stdout and "multi-GPU batcher OK on 4 GPUs" in r.stdout, r.stdout + r.stderr
+    # one "GPU" in the box: the several-GPU branch is skipped, everything else still holds
+    r = _run(os.path.join(mock_build, "test_host_mock"), env={"WN_MOCK_DEVICES": "1"})
+    assert r.returncode == 0 and "test_host OK" in r.stdout and "multi-GPU" not in r.stdout, r.stdout + r.stderr
+
+
+def test_frame_batcher_state_machine_several_gpus(mock_build):
+    """FrameBatcher over 1-8 "GPUs" of uneven speed: 25 run shapes (batch size, layout, push/stage, pipelined or not,
+    helper copy threads, a flush in the middle), frame order, delivery on the caller's thread, block-to-GPU assignment,
+    the summed statistics table, overlap of the GPUs in time, boxes and site lists, batch hook, failing batch calls."""
+    r = _run(os.path.join(mock_build, "test_batcher_mock"))
+    assert r.returncode == 0 and "test_batcher_mock OK" in r.stdout, r.stdout + r.stderr
+
+
+def _sanitizer_links(flag):
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not cxx:
+        return False
+    p = subprocess.run([cxx, flag, "-x", "c++", "-", "-o", "/dev/null"], input="int main(){return 0;}", capture_output=True, text=True)
+    return p.returncode == 0
+
+
+def test_frame_batcher_under_thread_sanitizer(mock_build):
+    """The worker threads, the helper copy threads and the caller share staging buffers, result sets and the lane
+    state: the stress test under ThreadSanitizer reports no data race."""
+    if not _sanitizer_links("-fsanitize=thread"):
+        pytest.skip("no ThreadSanitizer runtime with this compiler")
+    subprocess.check_call(["make", "-s", "-C", MOCK, "tsan"])
+    r = _run(os.path.join(mock_build, "test_batcher_tsan"), env={"TSAN_OPTIONS": "halt_on_error=1 exitcode=66"})
+    assert r.returncode == 0 and "test_batcher_mock OK" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stdout + r.stderr[-3000:]
+
+
+def test_host_mirror_under_address_sanitizer(mock_build):
+    """Result pointers are only valid until the next call (or the one after it with two result sets): the stand-in
+    re-assigns its buffers exactly then, so a host that reads an expired result trips AddressSanitizer."""
+    if not _sanitizer_links("-fsanitize=address"):
+        pytest.skip("no AddressSanitizer runtime with this compiler")
+    subprocess.check_call(["make", "-s", "-j2", "-C", MOCK, "asan"])
+    for exe, ok in (("test_batcher_asan", "test_batcher_mock OK"), ("test_host_asan", "test_host OK")):
+        r = _run(os.path.join(mock_build, exe), env={"ASAN_OPTIONS": "detect_leaks=1"})
+        assert r.returncode == 0 and ok in r.stdout, exe + ": " + r.stdout + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("pbc,gpu_text", [(False, 1), (True, 1), (False, 0)])
+def test_standalone_driver_writes_the_reference_files(mock_build, tmp_path, pbc, gpu_text):
+    import driver_cases
+    driver_cases.check_reference_files(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, pbc, gpu_text)
+
+
+def test_standalone_driver_buried_lists(mock_build, tmp_path):
+    import driver_cases
+    driver_cases.check_buried_lists(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path)
+
+
+def test_standalone_driver_frame_sharding_over_8_gpus(mock_build, tmp_path):
+    """-gpus 2, 4 and 8: edge, node and statistics files byte-identical to the one-GPU run (open and periodic)."""
+    import driver_cases
+    assert driver_cases.check_frame_sharding(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, 8) == [2, 4, 8]
+
+
+def test_standalone_driver_buried_lists_sharded(mock_build, tmp_path):
+    """Per-frame site lists through the sharded path: the ids of the listed waters, frames in order."""
+    import driver_cases
+    driver_cases.check_buried_lists(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, extra=["-gpus", "3", "-batch", "1"])
+
+
+def test_the_stand_in_is_not_part_of_the_product():
+    """Nothing that ships includes, links or names the stand-in; it is built only by tests/mock/Makefile."""
+    hits = []
+    for base in ("gmx-acqueduct_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".so", ".o", ".a")) or "checked_obj" in dp:
+                    continue
+                p = os.path.join(dp, fn)
+                try:
+                    txt = open(p, errors="ignore").read()
+                except OSError:
+                    continue
+                if "wn_mock" in txt or "tests/mock" in txt:
+                    hits.append(p)
+    for fn in ("bench.py", "__graft_entry__.py", "wn_pkg.py"):
+        if "wn_mock" in open(os.path.join(ROOT, fn)).read():
+            hits.append(fn)
+    assert not hits, hits
