@@ -498,7 +498,7 @@ int FrameBatcher::chooseLane() const
         double t;
         if (l.flying < 0) t = l.have_ready ? 1.0 : 0.0;
         else if (l.worker && l.worker->finished()) t = l.have_ready ? 1.0 : 0.5;      // done, result not collected yet
-        else t = l.t_start + l.typical;
+        else t = l.typical > 0.0 ? l.t_start + l.typical : 1.0e299;      // no batch of this GPU timed yet: rotation order
         if (t < best_t) { best_t = t; best = c; }
     }
     return best;
@@ -546,8 +546,20 @@ void FrameBatcher::submit()
         l.flying = buf;
         pending_.push_back(cur_);
         l.fill = 1 - buf;
-        // everything older than the batch just submitted goes to the sink now, in frame order
-        while (pending_.size() > lanes_.size() || (!pending_.empty() && lanes_[pending_.front()]->have_ready)) deliverOldest();
+        // everything older than the batch just submitted goes to the sink now, in frame order.  Round-robin: at most one
+        // batch per GPU stays in flight behind it.  Dynamic choice: only what has already left its GPU is delivered here
+        // (waiting for the oldest batch would idle the fast GPUs behind a slow one); a GPU's own older result is
+        // delivered before that GPU is handed its next batch (top of submit / after the choice below), which bounds
+        // what is in flight to the two staging buffers and two result sets per GPU.
+        if (dynamic_) {
+            while (!pending_.empty()) {
+                const Lane& o = *lanes_[pending_.front()];
+                if (!(o.have_ready || (o.flying >= 0 && o.worker && o.worker->finished()))) break;
+                deliverOldest();
+            }
+        } else {
+            while (pending_.size() > lanes_.size() || (!pending_.empty() && lanes_[pending_.front()]->have_ready)) deliverOldest();
+        }
     } else {
         while (!pending_.empty()) deliverOldest();
         const auto t0 = std::chrono::steady_clock::now();
@@ -559,11 +571,12 @@ void FrameBatcher::submit()
         pending_.push_back(cur_);
         deliverOldest();
     }
-    // Round-robin over the GPUs.  Handing the next batch to the GPU expected to be free first (chooseLane) was
-    // tried because GPUs behind a shared PCIe uplink are ~1.5x slower end to end: fine on 2 GPUs, but the one 8-GPU
-    // run of it showed a single batch call stalling for 88 s inside the C ABI (not understood, no GPU time left to
-    // chase it), so the measured-good static order stays; chooseLane() is kept for that follow-up.
-    cur_ = (cur_ + 1) % (int)lanes_.size();
+    // Round-robin over the GPUs by default.  Handing the next batch to the GPU expected to be free first (chooseLane,
+    // setDynamicGpuChoice) exists because GPUs behind a shared PCIe uplink are ~1.5x slower end to end: fine on 2 GPUs
+    // and on the CPU stand-in with uneven speeds (tests/cpp/test_batcher_mock.cpp), but the one 8-GPU run of it showed
+    // a single batch call taking 88 s INSIDE the C ABI (below this logic; not understood, no GPU time left to chase
+    // it), so the measured-good static order stays the default.
+    cur_ = dynamic_ && async ? chooseLane() : (cur_ + 1) % (int)lanes_.size();
     while (lanes_[cur_]->have_ready && !pending_.empty()) deliverOldest();
 }
 

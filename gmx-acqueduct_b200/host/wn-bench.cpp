@@ -8,7 +8,8 @@
 // Also times CudaFindPairs::find behind the FindPairs interface (include/find-pairs.hpp:11).
 //
 //   wn_bench [-waters 33333] [-batch 250] [-batches 12] [-warmup 2] [-gpus 1] [-layout 16|12|20]
-//            [-mode push|stage] [-ring 250] [-find 0|1] [-threads T] [-pipelined 1|0] [-copy-threads 4]
+//            [-mode push|stage] [-ring 250] [-find 0|1] [-threads T] [-pipelined 1|0] [-copy-threads 4] [-dynamic 0|1]
+// -dynamic 1: FrameBatcher::setDynamicGpuChoice (next batch to the GPU expected to be free first; default round-robin).
 // Prints ONE JSON line.  Frames: the synthetic water box of include/wn_synth.h (seed 1234), a ring of
 // -ring distinct frames generated before the clock starts.
 #include <atomic>
@@ -36,7 +37,7 @@ double now()
 
 int main(int argc, char** argv)
 {
-    int waters = 33333, batch = 250, batches = 12, warmup = 2, gpus = 1, layout_b = 16, ring = 250, do_find = 1, pipelined = 1, copy_threads = 4;
+    int waters = 33333, batch = 250, batches = 12, warmup = 2, gpus = 1, layout_b = 16, ring = 250, do_find = 1, pipelined = 1, copy_threads = 4, dynamic = 0;
     unsigned threads = std::max(1u, std::thread::hardware_concurrency());
     std::string mode = "push";
     for (int k = 1; k + 1 < argc; k += 2) {
@@ -53,6 +54,7 @@ int main(int argc, char** argv)
         else if (a == "-find") do_find = std::atoi(v);
         else if (a == "-pipelined") pipelined = std::atoi(v);
         else if (a == "-copy-threads") copy_threads = std::atoi(v);
+        else if (a == "-dynamic") dynamic = std::atoi(v);
         else if (a == "-threads") threads = (unsigned)std::atoi(v);
         else { std::fprintf(stderr, "wn_bench: unknown option %s\n", a.c_str()); return 2; }
     }
@@ -142,6 +144,7 @@ int main(int argc, char** argv)
             }
             // empty the pipeline, then start the clock: the timed frames are pushed, processed and delivered inside it
             fb.flush();
+            fb.setDynamicGpuChoice(dynamic != 0);          // after the warm-up: round-robin filled both staging buffers of every GPU
             first_timed = frnr;
             const double t0 = now();
             feed(batches * gpus);
@@ -173,12 +176,12 @@ int main(int argc, char** argv)
         std::string bs;
         for (size_t k = 0; k < batch_s.size(); ++k) { char t[32]; std::snprintf(t, sizeof t, "%s%.1f", k ? ", " : "", batch_s[k] * 1e3); bs += t; }
         std::printf("{\"bench\": \"wn_bench (C++ drop-in: FrameBatcher over the C ABI)\", \"e2e_cpp\": %.1f, \"unit\": \"frames/s\", "
-                    "\"gpus\": %d, \"mode\": \"%s\", \"copy_threads\": %d, \"layout_bytes_per_edge\": %zu, \"n_waters\": %d, \"batch_frames\": %d, "
+                    "\"gpus\": %d, \"mode\": \"%s\", \"copy_threads\": %d, \"dynamic_gpu_choice\": %d, \"layout_bytes_per_edge\": %zu, \"n_waters\": %d, \"batch_frames\": %d, "
                     "\"timed_frames\": %llu, \"timed_s\": %.4f, \"edges_per_frame\": %.1f, \"in_frame_order\": %s, "
                     "\"h2d_bytes_per_frame\": %zu, \"d2h_bytes_per_frame\": %.0f, \"warmup_s\": %.3f, \"stats_rows_reduced\": %zu, "
                     "\"find_wall_ms\": %.3f, \"find_pairs\": %zu, \"checksum\": %.6g, \"frames_per_gpu\": [%s], \"batch_call_ms\": [%s], "
                     "\"last_call\": {\"h2d_ms\": %.2f, \"kernels_ms\": %.2f, \"d2h_ms\": %.2f, \"passes\": %d}}\n",
-                    (double)timed_frames / t_run, gpus, mode.c_str(), copy_threads, esz, waters, batch, (unsigned long long)timed_frames, t_run,
+                    (double)timed_frames / t_run, gpus, mode.c_str(), copy_threads, dynamic, esz, waters, batch, (unsigned long long)timed_frames, t_run,
                     timed_frames ? (double)timed_edges / (double)timed_frames : 0.0, in_order ? "true" : "false",
                     frame_floats * sizeof(float),
                     timed_frames ? (double)timed_edges * (double)esz / (double)timed_frames + 4.0 * waters + 48.0 : 0.0,

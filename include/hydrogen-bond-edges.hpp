@@ -196,6 +196,10 @@ public:
     // 100k-atom box).  n > 1: n - 1 helper threads share each copy (include/frame-copy-pool.hpp).  Default 1.
     void setCopyThreads(int n);
     void setPipelined(bool on) { pipelined_ = on; }
+    // Several GPUs: false (default) -- batches go round-robin; true -- the next batch is staged for the GPU expected to
+    // be free first (GPUs behind a shared PCIe uplink are slower end to end, round-robin waits for the slowest).
+    // Results are delivered in frame order either way.  Opt-in: measured on 2 GPUs only.
+    void setDynamicGpuChoice(bool on) { dynamic_ = on; }
     // After finish(): one row per pushed frame, in push order.  With several GPUs this is the NCCL sum of
     // the per-GPU zero-padded tables (wn_stats_reduce), with one GPU the rows as delivered.
     const std::vector<wn_frame_stats>& reducedStats() const { return reduced_; }
@@ -205,7 +209,7 @@ public:
 
 private:
     struct Lane;
-    int chooseLane() const;        // GPU expected to be free first (not used by submit() yet, see there)
+    int chooseLane() const;        // GPU expected to be free first (setDynamicGpuChoice)
     void init(int natoms, int batch_frames, int layout);
     void submit();                      // current lane's filling buffer -> GPU
     void deliverOldest();               // wait for the oldest in-flight batch, hand it to the sink
@@ -217,6 +221,7 @@ private:
     FrameSink frame_sink_;
     BatchHook batch_hook_;
     bool pipelined_;
+    bool dynamic_ = false;
     uint64_t frames_done_, frames_pushed_;
     std::vector<wn_frame_stats> reduced_;
     std::vector<double> batch_seconds_;

@@ -76,6 +76,7 @@ struct Run {
     bool staged, pipelined;
     int copy_threads;
     int flush_at;      // flush() after this many frames (-1: never)
+    bool dynamic;      // setDynamicGpuChoice
 };
 
 }  // namespace
@@ -122,6 +123,7 @@ int main()
                 Run r;
                 r.gpus = g; r.per_batch = b; r.layout = variant % 3; r.staged = (variant / 3) % 2 == 1; r.pipelined = variant % 5 != 4;
                 r.copy_threads = variant % 4 == 1 ? 3 : 1; r.flush_at = variant % 3 == 2 ? 5 + variant % 7 : -1;
+                r.dynamic = variant % 2 == 1 && g > 1;
                 runs.push_back(r);
                 ++variant;
             }
@@ -143,6 +145,7 @@ int main()
             CHECK(fb.gpus() == r.gpus);
             fb.setPipelined(r.pipelined);
             fb.setCopyThreads(r.copy_threads);
+            fb.setDynamicGpuChoice(r.dynamic);
             for (int f = 0; f < F; ++f) {
                 const float* src = &frames[(size_t)f * kAtoms * 3];
                 if (r.staged) { std::memcpy(fb.stage(), src, (size_t)kAtoms * 3 * sizeof(float)); fb.commit(1000 + f); }
@@ -163,7 +166,7 @@ int main()
             CHECK(rows.size() == (size_t)F);
             for (int f = 0; f < F; ++f) CHECK(same_stats(rows[(size_t)f], ref.stats[(size_t)f]));
             // contiguous blocks of per_batch frames go round-robin to the GPUs (a flush ends a block early)
-            {
+            if (!r.dynamic) {
                 int lane = 0, in_block = 0;
                 for (int f = 0; f < F; ++f) {
                     CHECK(dev[(size_t)f] == lane);
@@ -201,6 +204,35 @@ int main()
             const double d1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
             CHECK(d1 < 0.85 * (8 * 0.012 + 4 * 0.030));
             for (int g = 0; g < 4; ++g) wn_mock_set_delay_us(g, 0);
+        }
+
+        // ---- opt-in dynamic GPU choice (setDynamicGpuChoice): with one GPU three times slower than the other two the
+        // next batch goes to whichever GPU is expected to be free first; same frames, same order, same table, less time
+        {
+            std::vector<HydrogenBondEdges*> engs{engines[0].get(), engines[1].get(), engines[2].get()};
+            double secs[2] = {0, 0};
+            for (int dyn = 0; dyn < 2; ++dyn) {
+                wn_mock_set_delay_us(0, 15000); wn_mock_set_delay_us(1, 5000); wn_mock_set_delay_us(2, 5000);
+                std::vector<int> dev;
+                bool ok = true; int n_seen = 0;
+                FrameBatcher fb(engs, kAtoms, 2, [&](const FrameResult& fr) {
+                    if (fr.frnr != n_seen || !same_edges(decode(fr), ref.edges[(size_t)(fr.frnr % F)], true)) ok = false;
+                    dev.push_back(fr.device); ++n_seen;
+                }, WN_LAYOUT_CSR16);
+                fb.setDynamicGpuChoice(dyn == 1);
+                const auto t0 = std::chrono::steady_clock::now();
+                for (int f = 0; f < 48; ++f) fb.push(f, &frames[(size_t)(f % F) * kAtoms * 3]);
+                fb.finish();
+                secs[dyn] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                CHECK(ok && n_seen == 48 && fb.reducedStats().size() == 48);
+                for (int f = 0; f < 48; ++f) CHECK(same_stats(fb.reducedStats()[(size_t)f], ref.stats[(size_t)(f % F)]));
+                int on_slow = 0;
+                for (int d : dev) on_slow += d == 0;
+                if (dyn == 0) CHECK(on_slow == 16);                 // round-robin: a third of the frames on the slow GPU
+                else CHECK(on_slow < 16 && on_slow > 0);
+            }
+            CHECK(secs[1] < 0.85 * secs[0]);
+            for (int g = 0; g < 3; ++g) wn_mock_set_delay_us(g, 0);
         }
 
         // ---- periodic and triclinic boxes, and per-frame site lists, over three GPUs == one GPU unbatched

@@ -118,3 +118,23 @@ def test_the_stand_in_is_not_part_of_the_product():
         if "wn_mock" in open(os.path.join(ROOT, fn)).read():
             hits.append(fn)
     assert not hits, hits
+
+
+def test_cpp_bench_binary_on_the_stand_in(mock_build):
+    """wn_bench (host/wn-bench.cpp) linked against the stand-in: every option combination the GPU test and bench.py use
+    runs to completion, delivers the frames in order and prints one JSON line (the numbers mean nothing here)."""
+    import json
+    exe = os.path.join(mock_build, "wn_bench_mock")
+    for extra in (["-layout", "16", "-mode", "push"], ["-layout", "12", "-mode", "stage"], ["-layout", "20", "-mode", "push", "-copy-threads", "1"],
+                  ["-layout", "16", "-mode", "push", "-gpus", "3"], ["-layout", "12", "-mode", "stage", "-gpus", "4", "-dynamic", "1"],
+                  ["-layout", "16", "-mode", "push", "-gpus", "2", "-pipelined", "0"]):
+        r = subprocess.run([exe, "-waters", "300", "-batch", "4", "-batches", "3", "-warmup", "2", "-ring", "8"] + extra,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, " ".join(extra) + ": " + r.stdout + r.stderr
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        g = d["gpus"]
+        assert d["in_frame_order"] and d["timed_frames"] == 12 * g and d["e2e_cpp"] > 0 and d["find_pairs"] > 0
+        assert d["stats_rows_reduced"] == 20 * g and sum(d["frames_per_gpu"]) == 12 * g
+        assert d["layout_bytes_per_edge"] == int(extra[1])
+        if "-dynamic" not in extra:
+            assert d["frames_per_gpu"] == [12] * g            # round-robin: equal shares
