@@ -157,7 +157,7 @@ int main(int argc, char** argv)
             wn_get_timings(eng[0]->context(), &last_tm);
         }
         // ---- FindPairs drop-in: CudaFindPairs::find on the oxygens of frame 0 (std::vector<Point> in, vector of pairs out)
-        double find_ms = 0.0;
+        double find_ms = 0.0, find_into_ms = 0.0;
         size_t n_pairs = 0;
         if (do_find) {
             std::shared_ptr<FindPairs> mp = std::make_shared<CudaFindPairs>(0);
@@ -169,6 +169,14 @@ int main(int argc, char** argv)
             const double t0 = now();
             for (int r = 0; r < reps; ++r) n_pairs = mp->find(pts).size();
             find_ms = (now() - t0) / reps * 1e3;
+            // the same list into a vector the caller keeps (no fresh 127 MB allocation per frame)
+            CudaFindPairs* cf = static_cast<CudaFindPairs*>(mp.get());
+            std::vector<std::pair<int, int> > kept;
+            cf->findInto(pts, kept);
+            const double t1 = now();
+            for (int r = 0; r < reps; ++r) cf->findInto(pts, kept);
+            find_into_ms = (now() - t1) / reps * 1e3;
+            if (kept.size() != n_pairs) throw std::runtime_error("findInto and find disagree");
         }
         const size_t esz = layout == WN_LAYOUT_CSR12 ? 12 : layout == WN_LAYOUT_CSR16 ? 16 : 20;
         std::string pg;
@@ -179,13 +187,13 @@ int main(int argc, char** argv)
                     "\"gpus\": %d, \"mode\": \"%s\", \"copy_threads\": %d, \"dynamic_gpu_choice\": %d, \"layout_bytes_per_edge\": %zu, \"n_waters\": %d, \"batch_frames\": %d, "
                     "\"timed_frames\": %llu, \"timed_s\": %.4f, \"edges_per_frame\": %.1f, \"in_frame_order\": %s, "
                     "\"h2d_bytes_per_frame\": %zu, \"d2h_bytes_per_frame\": %.0f, \"warmup_s\": %.3f, \"stats_rows_reduced\": %zu, "
-                    "\"find_wall_ms\": %.3f, \"find_pairs\": %zu, \"checksum\": %.6g, \"frames_per_gpu\": [%s], \"batch_call_ms\": [%s], "
+                    "\"find_wall_ms\": %.3f, \"find_into_wall_ms\": %.3f, \"find_pairs\": %zu, \"checksum\": %.6g, \"frames_per_gpu\": [%s], \"batch_call_ms\": [%s], "
                     "\"last_call\": {\"h2d_ms\": %.2f, \"kernels_ms\": %.2f, \"d2h_ms\": %.2f, \"passes\": %d}}\n",
                     (double)timed_frames / t_run, gpus, mode.c_str(), copy_threads, dynamic, esz, waters, batch, (unsigned long long)timed_frames, t_run,
                     timed_frames ? (double)timed_edges / (double)timed_frames : 0.0, in_order ? "true" : "false",
                     frame_floats * sizeof(float),
                     timed_frames ? (double)timed_edges * (double)esz / (double)timed_frames + 4.0 * waters + 48.0 : 0.0,
-                    t_first, reduced_rows, find_ms, n_pairs, checksum, pg.c_str(), bs.c_str(), last_tm.h2d_ms, last_tm.total_ms, last_tm.d2h_ms,
+                    t_first, reduced_rows, find_ms, find_into_ms, n_pairs, checksum, pg.c_str(), bs.c_str(), last_tm.h2d_ms, last_tm.total_ms, last_tm.d2h_ms,
                     last_tm.passes);
         return in_order ? 0 : 1;
     } catch (const std::exception& e) {

@@ -16,6 +16,8 @@
 #define WN_CUDAFINDPAIRS_HPP
 
 #include <cstdint>
+#include <utility>
+#include <vector>
 
 #include "find-pairs.hpp"
 #include "wn_b200.h"
@@ -29,6 +31,12 @@ public:
     CudaFindPairs& operator=(const CudaFindPairs&) = delete;
 
     std::vector<std::pair<int, int>> find(std::vector<Point>& points) override;
+    // The same list into a vector the caller keeps from frame to frame: its storage stays mapped, so the 127 MB of
+    // the 100k-atom box cost one shared copy instead of a fresh allocation's page faults (not in the reference's
+    // interface; find() above is).
+    void findInto(std::vector<Point>& points, std::vector<std::pair<int, int>>& pairs);
+    // ... and without any copy: the library-owned pinned list itself, valid until the next call on this finder.
+    const std::pair<int, int>* findRaw(std::vector<Point>& points, uint64_t* n_pairs);
 
     // Asymmetric search (BASELINE config 5): only rows i < first_limit; <0 = all rows.
     void setFirstLimit(int first_limit) { first_limit_ = first_limit; }

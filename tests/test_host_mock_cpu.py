@@ -138,3 +138,17 @@ def test_cpp_bench_binary_on_the_stand_in(mock_build):
         assert d["layout_bytes_per_edge"] == int(extra[1])
         if "-dynamic" not in extra:
             assert d["frames_per_gpu"] == [12] * g            # round-robin: equal shares
+
+
+def test_find_pairs_result_hand_over_large_lists(mock_build):
+    """CudaFindPairs::find (by value), findInto (a vector the caller keeps) and findRaw on lists above the size where
+    the hand-over goes parallel (huge-page hint + first touch from several threads, shared copy), growing, shrinking
+    and empty -- identical to a brute loop; also under AddressSanitizer/UBSan (test_host_mirror_under_address_sanitizer
+    builds the binary)."""
+    r = _run(os.path.join(mock_build, "test_findpairs_mock"))
+    assert r.returncode == 0 and "test_findpairs_mock OK" in r.stdout, r.stdout + r.stderr
+    asan = os.path.join(mock_build, "test_findpairs_asan")
+    if _sanitizer_links("-fsanitize=address"):
+        subprocess.check_call(["make", "-s", "-C", MOCK, "build/test_findpairs_asan"])
+        r = _run(asan)
+        assert r.returncode == 0 and "test_findpairs_mock OK" in r.stdout, r.stdout + r.stderr[-3000:]
