@@ -146,3 +146,136 @@ def check_frame_sharding(exe, tmp_path, ndev):
         assert run("g%d_pbc" % g, ["-gpus", str(g), "-pbc"]) == run("one_pbc_%d" % g, ["-pbc"])
         done.append(g)
     return done
+
+
+# ---- protein + water: the site rules of makeSites and the site order of analyzeFrame, restated from the reference text
+_SITE_NAMES = {"OW", "O", "N", "SG", "NE2", "OE1", "OD1", "ND2", "OG", "OG1", "OH", "NE1", "NZ", "NH1", "NH2", "ND1"}   # :99-118
+_DONOR, _ACCEPTOR, _WATER = 0, 1, 2
+_SITE_TYPE = {"NE": _DONOR, "NH1": _DONOR, "NH2": _DONOR, "ND1": _DONOR, "ND2": _DONOR, "OD1": _DONOR, "OD2": _DONOR,
+              "NE1": _DONOR, "NE2": _DONOR, "OE1": _ACCEPTOR, "OE2": _ACCEPTOR, "NZ": _DONOR, "OG": _DONOR, "OH": _DONOR,
+              "O": _ACCEPTOR, "N": _DONOR, "SG": _DONOR, "OW": _WATER, "OCD": _ACCEPTOR}                               # :120-139
+
+
+def _make_sites(selection, names, resnames_of_atom, resindex_of_atom):
+    """makeSites (src/waternetwork.cpp:141-179) on plain lists: [(id, atmIndex, name, resIndex, resName, type, nbH)]."""
+    out, count = [], 0
+    for index in selection:
+        name = names[index]
+        if name not in _SITE_NAMES:
+            continue
+        count += 1
+        nhb = 0
+        while True:
+            if index + nhb + 1 > len(selection):                # :157, topology index against selection size, as written
+                break
+            if index + nhb + 1 >= len(names):                   # (the reference would read past the topology)
+                break
+            probe = names[index + nhb + 1].lstrip("0123456789")[:1]      # element of a .gro atom: first letter of its name
+            if "H" not in probe:
+                break
+            nhb += 1
+        typ = _SITE_TYPE.get(name, _DONOR)                      # operator[] default-constructs DONOR (:168)
+        if resnames_of_atom[index] == "WAT":                    # :170-173
+            typ = _WATER
+        out.append((count, index, name, resindex_of_atom[index], resnames_of_atom[index], typ, nhb))
+    return out
+
+
+def check_protein_and_water(exe, tmp_path, bug_compat, extra=()):
+    """A small 'protein' (SER, LYS, THR, GLN with explicit hydrogens) in front of a water box: nodes file, edges file
+    and statistics rows against the oracle run on the site table that the reference's makeSites (:95-180) and
+    analyzeFrame (:547-576) would build -- protein sites first (hydrogens at proteinPoints[id + i + 1] with
+    -bug-compat 1, :554; at atmIndex + i + 1 otherwise), then every water with hydrogen list {3w, 3w+1, ...}."""
+    import numpy as np
+    import wn_oracle_py as o
+    n_w, nf = 125, 3
+    sb = o.synth_box(n_w, model=o.MODEL_SPC)
+    wframes = o.synth_frames(sb, 0, nf)
+    residues = [("SER", ["N", "H", "CA", "HA", "CB", "HB1", "HB2", "OG", "HG", "C", "O"]),
+                ("LYS", ["N", "H", "CA", "HA", "CB", "HB1", "CG", "CD", "CE", "NZ", "HZ1", "HZ2", "HZ3", "C", "O"]),
+                ("THR", ["N", "H", "CA", "HA", "CB", "HB", "OG1", "HG1", "CG2", "1HG2", "C", "O"]),
+                ("GLN", ["N", "H", "CA", "CB", "CG", "CD", "OE1", "NE2", "1HE2", "2HE2", "C", "O"])]
+    names, resn, resi = [], [], []
+    for r, (rn, atoms) in enumerate(residues):
+        for a in atoms:
+            names.append(a); resn.append(rn); resi.append(r)
+    n_p = len(names)
+    for w in range(n_w):
+        for a in ("OW", "HW1", "HW2"):
+            names.append(a); resn.append("SOL"); resi.append(len(residues) + w)
+    natoms = len(names)
+    rng = np.random.default_rng(17)
+    frames = np.zeros((nf, natoms, 3), np.float32)
+    box = float(sb.box)
+    for f in range(nf):
+        # heavy atoms on a loose random walk inside the box, hydrogens 0.1 nm from the atom before them
+        pos = np.zeros((n_p, 3))
+        cur = rng.uniform(0.3 * box, 0.7 * box, size=3)
+        for a in range(n_p):
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            if names[a].lstrip("0123456789").startswith("H"):
+                pos[a] = pos[a - 1] + 0.1 * d
+            else:
+                cur = cur + 0.15 * d
+                pos[a] = cur
+        frames[f, :n_p] = pos
+        frames[f, n_p:] = wframes[f]
+    gro = str(tmp_path / "traj.gro")
+    with open(gro, "w") as fh:
+        for f in range(nf):
+            fh.write("protein in water t= %9.5f\n" % (0.5 * f))
+            fh.write("%5d\n" % natoms)
+            for a in range(natoms):
+                fh.write("%5d%-5s%5s%5d%8.3f%8.3f%8.3f\n" % (resi[a] + 1, resn[a], names[a], a + 1, *frames[f, a]))
+            fh.write("%10.5f%10.5f%10.5f\n" % (box, box, box))
+    r = subprocess.run([exe, "-f", gro, "-edges", str(tmp_path / "edges"), "-nodes", str(tmp_path / "nodes"),
+                        "-ohb", str(tmp_path / "ohb.xvg"), "-obw", str(tmp_path / "obw.xvg"), "-batch", "2",
+                        "-bug-compat", str(int(bug_compat))] + list(extra), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+    protein_sel = list(range(n_p))
+    solvent_sel = list(range(n_p, natoms))
+    psites = _make_sites(protein_sel, names, resn, resi)
+    ssites = _make_sites(solvent_sel, names, resn, resi)
+    assert len(psites) >= 9 and len(ssites) == n_w
+    assert "Protein has : %d Sites of out %d atoms." % (len(psites), n_p) in r.stderr
+    n_ps = len(psites)
+    ssites = [(sid + n_ps + 1,) + tuple(rest) for (sid, *rest) in ssites]              # :420-423
+    # nodes file (:461-482, operator<< of SiteInfo: seven setw(7) fields)
+    want_nodes = "%7s%7s%7s%7s%7s%7s%7s" % ("#Id", "AtmId", "Name", "ResId", "Res", "Type", "Hyd\n")
+    for (sid, idx, nm, ri, rn, ty, nh) in psites + ssites:
+        want_nodes += "%7d%7d%7s%7d%7s%7d%7d\n" % (sid, idx, nm, ri, rn, ty, nh)
+    assert open(str(tmp_path / "nodes.dat")).read() == want_nodes
+    # the site table analyzeFrame builds (:547-576): atom indices into the frame
+    hmax = max(1, max(s[6] for s in psites + ssites))
+    site_atom, h_atom, types, ids = [], [], [], []
+    for (sid, idx, nm, ri, rn, ty, nh) in psites:
+        base = sid if bug_compat else idx
+        hs = [protein_sel[base + i + 1] for i in range(nh)]                      # proteinPoints.at(id + i + 1) (:554)
+        site_atom.append(protein_sel[idx]); h_atom.append(hs + [-1] * (hmax - nh)); types.append(ty); ids.append(sid)
+    for w, (sid, idx, nm, ri, rn, ty, nh) in enumerate(ssites):
+        hs = [solvent_sel[3 * w + i] for i in range(nh)]                         # solventPoints.at(3*idx + i) (:569)
+        site_atom.append(solvent_sel[3 * w]); h_atom.append(hs + [-1] * (hmax - nh)); types.append(ty); ids.append(sid)
+    # the quirk of :157 shows: the last waters of a solvent selection that does not start at atom 0 lose hydrogens
+    assert ssites[0][6] == 2 and ssites[-1][6] < 2
+    sa = np.array(site_atom, np.int32); ha = np.array(h_atom, np.int32).reshape(len(sa), hmax); ty = np.array(types, np.uint8)
+    parsed = parse_back(frames)
+    want = EDGE_HEADER
+    ohb = ""
+    n_mixed = 0
+    boxf = np.float32(np.float64("%10.5f" % box))
+    for f in range(nf):
+        if "-pbc" in extra:
+            e, st, _, _ = o.frame_hbonds_pbc(parsed[f], sa, ha, ty, np.array([boxf] * 3, np.float32))
+        else:
+            e, st, _, _ = o.frame_hbonds(parsed[f], sa, ha, ty)
+        n_mixed += int(np.sum((e["i"] < n_ps) != (e["j"] < n_ps)))
+        want += "#--- frame %d ---\n" % f
+        want += "".join("%6d%6d%8.4f%8.4f%8.4f\n" % (ids[a], ids[b], en, ln, cs)
+                        for a, b, en, ln, cs in zip(e["i"], e["j"], e["energy"].astype(np.float64),
+                                                    e["length"].astype(np.float64), e["cosine"].astype(np.float64)))
+        ohb += " %11.3f %8.3f %8.3f %8.3f %8.3f %8.3f %8.3f\n" % (0.5 * f, len(sa), len(e), len(e) / len(sa), 0, 0, 0)
+    assert n_mixed > 0                                                           # protein-water bonds really occur
+    assert open(str(tmp_path / "edges.dat")).read() == want
+    assert open(str(tmp_path / "ohb.xvg")).read() == ohb
+    assert open(str(tmp_path / "obw.xvg")).read() == "".join(" %11.3f %8.3f %8.3f\n" % (0.5 * f, n_w, 0) for f in range(nf))

@@ -152,3 +152,11 @@ def test_find_pairs_result_hand_over_large_lists(mock_build):
         subprocess.check_call(["make", "-s", "-C", MOCK, "build/test_findpairs_asan"])
         r = _run(asan)
         assert r.returncode == 0 and "test_findpairs_mock OK" in r.stdout, r.stdout + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("bug_compat,extra", [(True, []), (False, []), (True, ["-gpus", "2"]), (True, ["-pbc", "-gpu-text", "0"])])
+def test_standalone_driver_protein_and_water(mock_build, tmp_path, bug_compat, extra):
+    """makeSites typing + protein sites end to end: nodes, edges and statistics files of a small
+    protein in water against the oracle on the site table restated from the reference's text."""
+    import driver_cases
+    driver_cases.check_protein_and_water(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, bug_compat, extra)
