@@ -2,9 +2,12 @@
 //
 // COMPILE-GATED: built only with -DWN_WITH_GROMACS against a GROMACS 2019.x installation
 // (`make -C gmx-acqueduct_b200 gromacs-module GMX_PREFIX=/path/to/gromacs`).  GROMACS is not present in
-// the container this repository is developed in, so THIS FILE HAS NOT BEEN COMPILED; the same flow is
-// exercised end to end without GROMACS by host/waternetwork-driver.cpp (wn_waternetwork), whose output
-// files are byte-compared with the oracle in tests/test_gpu_host_cpp.py.
+// the container this repository is developed in, so THIS FILE HAS NOT BEEN COMPILED AGAINST GROMACS.  What the test
+// suite does instead: it compiles, links and RUNS this source against a small working miniature of the API calls it
+// makes (tests/shim/gromacs_run, written from the public API documentation) and the CPU stand-in of the C ABI, on a
+// protein-in-water .gro trajectory, and compares its nodes / edges files and data-set rows with those of
+// host/waternetwork-driver.cpp (wn_waternetwork) -- the same flow without GROMACS, whose output files are
+// byte-compared with the oracle (tests/test_host_mock_cpu.py, tests/test_gpu_host_cpp.py).
 //
 // It is the module of the reference (src/waternetwork.cpp: class WaterNetwork, include/waternetwork.hpp)
 // with the per-frame body of analyzeFrame (:538-652) replaced by frame batching:

@@ -279,3 +279,29 @@ def check_protein_and_water(exe, tmp_path, bug_compat, extra=()):
     assert open(str(tmp_path / "edges.dat")).read() == want
     assert open(str(tmp_path / "ohb.xvg")).read() == ohb
     assert open(str(tmp_path / "obw.xvg")).read() == "".join(" %11.3f %8.3f %8.3f\n" % (0.5 * f, n_w, 0) for f in range(nf))
+
+
+def check_gromacs_module_equals_driver(module_exe, driver_exe, tmp_path, pbc=False, batch=2):
+    """The compile-gated GROMACS module (host/gromacs/waternetwork-b200.cpp, run on the working API miniature of
+    tests/shim/gromacs_run) writes the same nodes, edges and statistics as the standalone driver -- which
+    check_protein_and_water pins to the oracle -- for the same protein-in-water trajectory."""
+    extra = ["-pbc", "-gpu-text", "0"] if pbc else []
+    check_protein_and_water(driver_exe, tmp_path, True, extra)
+    m = tmp_path / "module"
+    m.mkdir()
+    args = [module_exe, "-f", str(tmp_path / "traj.gro"), "-edges", str(m / "edges"), "-nodes", str(m / "nodes"),
+            "-ohb", str(m / "ohb"), "-obw", str(m / "obw"), "-batch", str(batch)]
+    if pbc:
+        args.append("-usepbc")
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # GROMACS completes plot-type file names with .xvg; the module appends .dat for nodes and edges (:461,:485)
+    assert open(str(m / "edges.xvg.dat")).read() == open(str(tmp_path / "edges.dat")).read()
+    assert open(str(m / "nodes.xvg.dat")).read() == open(str(tmp_path / "nodes.dat")).read()
+
+    def rows(path):
+        return [l for l in open(path).read().splitlines() if l and l[0] not in "#@"]
+
+    assert rows(str(m / "ohb.xvg")) == rows(str(tmp_path / "ohb.xvg"))
+    assert rows(str(m / "obw.xvg")) == rows(str(tmp_path / "obw.xvg"))
+    assert len(rows(str(m / "ohb.xvg"))) == 3

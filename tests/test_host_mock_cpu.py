@@ -160,3 +160,14 @@ def test_standalone_driver_protein_and_water(mock_build, tmp_path, bug_compat, e
     protein in water against the oracle on the site table restated from the reference's text."""
     import driver_cases
     driver_cases.check_protein_and_water(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, bug_compat, extra)
+
+
+@pytest.mark.parametrize("pbc,batch", [(False, 2), (True, 2), (False, 1), (False, 64)])
+def test_gromacs_module_runs_and_equals_the_driver(mock_build, tmp_path, pbc, batch):
+    """SURVEY 8 f2: the gated gmx::TrajectoryAnalysisModule source compiled, linked and RUN (GROMACS is absent: against
+    a working miniature of the API calls it makes, tests/shim/gromacs_run, and the stand-in C ABI) on a protein-in-water
+    trajectory: same nodes/edges files and data-set rows as the standalone driver, whose output is pinned to the oracle.
+    Batch sizes below, equal to and above the frame count exercise the late data-set rows (ModuleData::finish)."""
+    import driver_cases
+    driver_cases.check_gromacs_module_equals_driver(os.path.join(mock_build, "wn_gmx_module_mock"),
+                                                    os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, pbc, batch)
