@@ -76,6 +76,8 @@ struct Run {
     bool staged, pipelined;
     int copy_threads;
     int flush_at;      // flush() after this many frames (-1: never)
+    int flush2_at;     // a second flush (-1: never)
+    int n_frames;      // frames pushed (<= the 23 prepared)
     bool dynamic;      // setDynamicGpuChoice
 };
 
@@ -124,11 +126,27 @@ int main()
                 r.gpus = g; r.per_batch = b; r.layout = variant % 3; r.staged = (variant / 3) % 2 == 1; r.pipelined = variant % 5 != 4;
                 r.copy_threads = variant % 4 == 1 ? 3 : 1; r.flush_at = variant % 3 == 2 ? 5 + variant % 7 : -1;
                 r.dynamic = variant % 2 == 1 && g > 1;
+                r.flush2_at = -1; r.n_frames = F;
                 runs.push_back(r);
                 ++variant;
             }
+        // ... and a seeded random sweep over the same dimensions, with shorter runs, empty runs and two flushes
+        {
+            std::mt19937 fz(2024);
+            auto pick = [&](int lo, int hi) { return std::uniform_int_distribution<int>(lo, hi)(fz); };
+            for (int k = 0; k < 150; ++k) {
+                Run r;
+                r.gpus = pick(1, 8); r.per_batch = pick(1, 9); r.layout = pick(0, 2); r.staged = pick(0, 1) == 1; r.pipelined = pick(0, 4) != 0;
+                r.copy_threads = pick(1, 3); r.dynamic = pick(0, 1) == 1 && r.gpus > 1;
+                r.n_frames = pick(0, F);
+                r.flush_at = pick(0, 2) == 0 && r.n_frames > 0 ? pick(1, r.n_frames) : -1;
+                r.flush2_at = r.flush_at > 0 && pick(0, 1) == 1 && r.flush_at < r.n_frames ? pick(r.flush_at + 1, r.n_frames) : -1;
+                runs.push_back(r);
+            }
+        }
         std::uniform_int_distribution<int> delay(0, 400);
         for (const Run& r : runs) {
+            const int F = r.n_frames;
             for (int g = 0; g < 8; ++g) wn_mock_set_delay_us(g, delay(rng));       // GPUs of a host are not equally fast
             std::vector<HydrogenBondEdges*> engs;
             for (int g = 0; g < r.gpus; ++g) engs.push_back(engines[(size_t)g].get());
@@ -150,7 +168,7 @@ int main()
                 const float* src = &frames[(size_t)f * kAtoms * 3];
                 if (r.staged) { std::memcpy(fb.stage(), src, (size_t)kAtoms * 3 * sizeof(float)); fb.commit(1000 + f); }
                 else fb.push(1000 + f, src);
-                if (f + 1 == r.flush_at) {
+                if (f + 1 == r.flush_at || f + 1 == r.flush2_at) {
                     fb.flush();
                     CHECK(fb.framesDone() == (uint64_t)(f + 1) && (int)seen.size() == f + 1);       // nothing left in flight
                 }
@@ -171,7 +189,7 @@ int main()
                 for (int f = 0; f < F; ++f) {
                     CHECK(dev[(size_t)f] == lane);
                     ++in_block;
-                    if (in_block == r.per_batch || f + 1 == r.flush_at) { in_block = 0; lane = (lane + 1) % r.gpus; }
+                    if (in_block == r.per_batch || f + 1 == r.flush_at || f + 1 == r.flush2_at) { in_block = 0; lane = (lane + 1) % r.gpus; }
                 }
             }
             CHECK(fb.batchSeconds().size() >= (size_t)((F + r.per_batch - 1) / r.per_batch));
@@ -355,7 +373,7 @@ int main()
             HydrogenBondBatch again = engines[1]->calculate(frames.data(), 2, kAtoms);
             CHECK(again.n_frames == 2 && same_edges(std::vector<wn_edge>(again.edges + again.offsets[1], again.edges + again.offsets[2]), ref.edges[1], true));
         }
-        std::printf("test_batcher_mock OK: %zu run shapes, %d frames each\n", runs.size(), F);
+        std::printf("test_batcher_mock OK: %zu run shapes, up to %d frames each\n", runs.size(), F);
         return 0;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
