@@ -356,7 +356,7 @@ FrameBatcher::FrameBatcher(HydrogenBondEdges& engine, int natoms, int batch_fram
     Lane* l = new Lane();
     l->eng = &engine;
     lanes_.push_back(l);
-    init(natoms, batch_frames, WN_LAYOUT_EDGES);
+    try { init(natoms, batch_frames, WN_LAYOUT_EDGES); } catch (...) { destroy(); throw; }
 }
 
 FrameBatcher::FrameBatcher(const std::vector<HydrogenBondEdges*>& engines, int natoms, int batch_frames, FrameSink sink,
@@ -369,10 +369,12 @@ FrameBatcher::FrameBatcher(const std::vector<HydrogenBondEdges*>& engines, int n
         l->eng = e;
         lanes_.push_back(l);
     }
-    init(natoms, batch_frames, layout);
+    try { init(natoms, batch_frames, layout); } catch (...) { destroy(); throw; }      // a constructor that throws runs no destructor
 }
 
-FrameBatcher::~FrameBatcher()
+FrameBatcher::~FrameBatcher() { destroy(); }
+
+void FrameBatcher::destroy()
 {
     for (Lane* l : lanes_) {
         if (l->flying >= 0 && l->worker) { try { l->worker->get(); } catch (...) {} }
@@ -382,6 +384,7 @@ FrameBatcher::~FrameBatcher()
         try { l->eng->setResultSets(1); } catch (...) {}
         delete l;
     }
+    lanes_.clear();
 }
 
 float* FrameBatcher::stage()

@@ -211,6 +211,7 @@ private:
     struct Lane;
     int chooseLane() const;        // GPU expected to be free first (setDynamicGpuChoice)
     void init(int natoms, int batch_frames, int layout);
+    void destroy();                     // workers joined, staging freed (destructor, and a constructor that fails half way)
     void submit();                      // current lane's filling buffer -> GPU
     void deliverOldest();               // wait for the oldest in-flight batch, hand it to the sink
     std::vector<Lane*> lanes_;

@@ -373,6 +373,21 @@ int main()
             HydrogenBondBatch again = engines[1]->calculate(frames.data(), 2, kAtoms);
             CHECK(again.n_frames == 2 && same_edges(std::vector<wn_edge>(again.edges + again.offsets[1], again.edges + again.offsets[2]), ref.edges[1], true));
         }
+        // ---- a constructor that fails half way (pinned staging of the second GPU cannot be allocated) throws and
+        // leaves nothing behind (the AddressSanitizer build checks the leak); the engines stay usable
+        {
+            std::vector<HydrogenBondEdges*> engs{engines[0].get(), engines[1].get(), engines[2].get()};
+            wn_mock_fail_pinned_alloc(1, 1);                // GPU 1: its second staging buffer
+            bool threw = false;
+            try { FrameBatcher fb(engs, kAtoms, 2, [&](const FrameResult&) {}, WN_LAYOUT_CSR16); } catch (const std::runtime_error&) { threw = true; }
+            wn_mock_fail_pinned_alloc(-1, 0);
+            CHECK(threw);
+            int n_seen = 0;
+            FrameBatcher fb(engs, kAtoms, 2, [&](const FrameResult&) { ++n_seen; }, WN_LAYOUT_CSR16);
+            for (int f = 0; f < 5; ++f) fb.push(f, &frames[(size_t)f * kAtoms * 3]);
+            fb.finish();
+            CHECK(n_seen == 5);
+        }
         std::printf("test_batcher_mock OK: %zu run shapes, up to %d frames each\n", runs.size(), F);
         return 0;
     } catch (const std::exception& e) {

@@ -10,6 +10,8 @@ void wn_mock_set_delay_us(int device, long us_per_frame);
 long wn_mock_batch_calls(int device);
 /* batch calls on `device` fail with WN_ERR_CUDA after `after_calls` more successful ones (device < 0: never) */
 void wn_mock_fail_batches(int device, long after_calls);
+/* pinned allocations on `device` fail with WN_ERR_OOM after `after_allocs` more successful ones (device < 0: never) */
+void wn_mock_fail_pinned_alloc(int device, long after_allocs);
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ std::atomic<long> g_delay_us[64];
 std::atomic<long> g_calls[64];
 std::atomic<int> g_fail_device{-1};
 std::atomic<long> g_fail_after{0};
+std::atomic<int> g_alloc_fail_device{-1};
+std::atomic<long> g_alloc_fail_after{0};
 thread_local std::string t_create_error;
 
 struct ResultSet {
@@ -416,6 +418,9 @@ int wn_components(wn_ctx* c, float thr, const int32_t** labels, const wn_compone
 int wn_host_alloc_pinned(wn_ctx* c, size_t bytes, void** p)
 {
     if (!c || !p) return WN_ERR_BAD_ARG;
+    *p = nullptr;
+    if (g_alloc_fail_device.load() == c->device && g_alloc_fail_after.fetch_sub(1) <= 0)
+        return fail(c, WN_ERR_OOM, "wn_mock: injected pinned allocation failure");
     *p = std::malloc(bytes ? bytes : 1);
     if (!*p) return fail(c, WN_ERR_OOM, "wn_mock: malloc");
     std::memset(*p, 0xCD, bytes);
@@ -468,5 +473,7 @@ int wn_stats_reduce(wn_ctx* c, wn_frame_stats* table, int64_t n)
 void wn_mock_set_delay_us(int device, long us_per_frame) { g_delay_us[device & 63].store(us_per_frame); }
 long wn_mock_batch_calls(int device) { return g_calls[device & 63].load(); }
 void wn_mock_fail_batches(int device, long after_calls) { g_fail_after.store(after_calls + g_calls[device < 0 ? 0 : (device & 63)].load()); g_fail_device.store(device); }
+
+void wn_mock_fail_pinned_alloc(int device, long after_allocs) { g_alloc_fail_after.store(after_allocs); g_alloc_fail_device.store(device); }
 
 }  // extern "C"
