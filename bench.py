@@ -576,6 +576,22 @@ def run_own(args):
                     e2e_cpp = {"error": (pr.stderr or "no output")[-300:]}
             except Exception as exc:        # noqa: BLE001 -- the leg is informative, not the headline
                 e2e_cpp = {"error": str(exc)[-300:]}
+            # the same drop-in with what PCIe allows at best: the 12-byte result layout ({j, length, cosine}; the energy
+            # is a function of the last two, include/wn_energy.h recomputes it on demand on the host) and a producer that
+            # decodes straight into the pinned staging buffer (stage() + commit(), no host copy per frame).  Its own
+            # process with its own time limit: nothing here can disturb the numbers above.
+            try:
+                pr = subprocess.run([exe, "-waters", str(n_waters), "-batch", str(F), "-batches", "12", "-warmup", "2",
+                                     "-layout", "12", "-mode", "stage", "-find", "0"], capture_output=True, text=True, timeout=300)
+                if pr.returncode == 0 and pr.stdout.strip():
+                    d12 = json.loads(pr.stdout.strip().splitlines()[-1])
+                    e2e_cpp["csr12_stage"] = {k: d12.get(k) for k in ("e2e_cpp", "unit", "mode", "layout_bytes_per_edge", "timed_frames",
+                                                                      "timed_s", "d2h_bytes_per_frame", "in_frame_order", "last_call")}
+                else:
+                    e2e_cpp["csr12_stage"] = {"error": (pr.stderr or "no output")[-300:]}
+            except Exception as exc:        # noqa: BLE001
+                if isinstance(e2e_cpp, dict):
+                    e2e_cpp["csr12_stage"] = {"error": str(exc)[-300:]}
 
     # ---- host frames in -> component labels out: the edge list never crosses PCIe (results_on_device),
     # only 4 bytes per site and 16 per frame come back.  A different result than the headline e2e (labels and
