@@ -208,16 +208,21 @@ def check_protein_and_water(exe, tmp_path, bug_compat, extra=()):
     frames = np.zeros((nf, natoms, 3), np.float32)
     box = float(sb.box)
     for f in range(nf):
-        # heavy atoms on a loose random walk inside the box, hydrogens 0.1 nm from the atom before them
+        # heavy atoms on a jittered 0.3 nm grid in a slab just outside the +x face of the water box (a dense water box
+        # has no cavity for them): 0.26 nm or more from every water oxygen and from each other, so the energies stay
+        # inside the 8-character text field (its overflow glues two columns together in the reference's format);
+        # hydrogens 0.1 nm from the atom before them
         pos = np.zeros((n_p, 3))
-        cur = rng.uniform(0.3 * box, 0.7 * box, size=3)
+        slots = [(box + 0.28 + 0.3 * ix, 0.25 + 0.3 * iy, 0.25 + 0.3 * iz) for ix in range(3) for iy in range(4) for iz in range(4)]
+        order = rng.permutation(len(slots))
+        k = 0
         for a in range(n_p):
-            d = rng.normal(size=3); d /= np.linalg.norm(d)
             if names[a].lstrip("0123456789").startswith("H"):
+                d = rng.normal(size=3); d /= np.linalg.norm(d)
                 pos[a] = pos[a - 1] + 0.1 * d
             else:
-                cur = cur + 0.15 * d
-                pos[a] = cur
+                pos[a] = np.array(slots[order[k]]) + rng.uniform(-0.02, 0.02, size=3)
+                k += 1
         frames[f, :n_p] = pos
         frames[f, n_p:] = wframes[f]
     gro = str(tmp_path / "traj.gro")

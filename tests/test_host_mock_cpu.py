@@ -171,3 +171,54 @@ def test_gromacs_module_runs_and_equals_the_driver(mock_build, tmp_path, pbc, ba
     import driver_cases
     driver_cases.check_gromacs_module_equals_driver(os.path.join(mock_build, "wn_gmx_module_mock"),
                                                     os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, pbc, batch)
+
+
+def test_driver_files_feed_the_reference_downstream_script(mock_build, tmp_path):
+    """The files the drop-in writes are the input of the reference's python/network-analysis.py.  Its own reader
+    (read_node_list, :62-76), its edge-row loop (main, :146-178: skip the header, '#' lines separate frames,
+    whitespace split, weight = |energy|) and its two filters (filter_edge_by_weight :16-24, remove_node_degree :26-35)
+    -- the function texts taken from the reference file itself, which needs matplotlib as a whole and cannot be
+    imported here -- run on the nodes/edges files of a protein-in-water trajectory; the connected components networkx
+    finds per frame equal the rows the driver's own -components writes (threshold 0.0 on the 4-decimal text == 5e-5 on
+    the binary energy: no float lies between (float)5e-5 and 5e-5)."""
+    import ast
+    import driver_cases
+    script = "/root/reference/python/network-analysis.py"
+    if not os.path.exists(script):
+        pytest.skip("reference tree absent")
+    nx = pytest.importorskip("networkx")
+    tree = ast.parse(open(script).read())
+    wanted = {"filter_edge_by_weight", "remove_node_degree", "read_node_list"}
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {f.name for f in fns} == wanted
+    ns = {"nx": nx}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), script, "exec"), ns)
+
+    exe = os.path.join(mock_build, "wn_waternetwork_mock")
+    driver_cases.check_protein_and_water(exe, tmp_path, True, ["-components", "5e-5", "-ocomp", str(tmp_path / "comp.xvg")])
+    with open(str(tmp_path / "nodes.dat")) as fh:
+        nodes, residues = ns["read_node_list"](fh)
+    assert len(nodes) > 125 and residues["OW 4"] in nodes and "NZ 1" in residues and nodes[residues["NZ 1"]] == "NZ 1 LYS"
+    rows = []
+    with open(str(tmp_path / "edges.dat")) as fh:
+        next(fh)                                                   # :147
+        G, started = nx.Graph(), False
+
+        def close_frame(G):
+            G = ns["filter_edge_by_weight"](G, threshold=0.0)
+            G = ns["remove_node_degree"](G)
+            comps = list(nx.connected_components(G))
+            rows.append((len(comps), max((len(c) for c in comps), default=0), G.number_of_nodes(), G.number_of_edges()))
+
+        for line in fh:
+            if line[0] == "#":                                     # :151
+                if started:
+                    close_frame(G)
+                G, started = nx.Graph(), True
+                continue
+            f = line.split()                                       # :176-178
+            assert all(int(f[k]) in nodes for k in (0, 1))         # every printed id is a node of the nodes file
+            G.add_edge(int(f[0]), int(f[1]), weight=abs(float(f[2])), length=float(f[3]), angle=float(f[4]))
+        close_frame(G)
+    got = [tuple(int(v) for v in l.split()[1:]) for l in open(str(tmp_path / "comp.xvg")).read().splitlines()]
+    assert len(rows) == 3 and got == rows, (got, rows)
