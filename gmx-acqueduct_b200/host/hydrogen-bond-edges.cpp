@@ -576,9 +576,10 @@ void FrameBatcher::submit()
     }
     // Round-robin over the GPUs by default.  Handing the next batch to the GPU expected to be free first (chooseLane,
     // setDynamicGpuChoice) exists because GPUs behind a shared PCIe uplink are ~1.5x slower end to end: fine on 2 GPUs
-    // and on the CPU stand-in with uneven speeds (tests/cpp/test_batcher_mock.cpp), but the one 8-GPU run of it showed
-    // a single batch call taking 88 s INSIDE the C ABI (below this logic; not understood, no GPU time left to chase
-    // it), so the measured-good static order stays the default.
+    // and on the CPU stand-in with uneven speeds (tests/cpp/test_batcher_mock.cpp).  Its one 8-GPU run showed single
+    // batch calls of 88 s -- since explained as the benchmark committing never-written (all-zero) staging buffers, i.e.
+    // frames with every site at one point, not this logic -- but it has not been measured again,
+    // so the static order measured at 2/4/8 GPUs stays the default.
     cur_ = dynamic_ && async ? chooseLane() : (cur_ + 1) % (int)lanes_.size();
     while (lanes_[cur_]->have_ready && !pending_.empty()) deliverOldest();
 }
