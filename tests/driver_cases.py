@@ -310,3 +310,42 @@ def check_gromacs_module_equals_driver(module_exe, driver_exe, tmp_path, pbc=Fal
     assert rows(str(m / "ohb.xvg")) == rows(str(tmp_path / "ohb.xvg"))
     assert rows(str(m / "obw.xvg")) == rows(str(tmp_path / "obw.xvg"))
     assert len(rows(str(m / "ohb.xvg"))) == 3
+
+
+def check_triclinic_box_line(exe, tmp_path, extra=()):
+    """-pbc with a triclinic .gro box line (v1(x) v2(y) v3(z) v1(y) v1(z) v2(x) v2(z) v3(x) v3(y), rows of the GROMACS
+    matrix = box vectors): the edge file equals the triclinic oracle on the matrix the nine numbers stand for."""
+    import numpy as np
+    import wn_oracle_py as o
+    n, nf = 125, 2
+    sb = o.synth_box(n, model=o.MODEL_SPC)
+    frames = o.synth_frames(sb, 0, nf)
+    L = float(sb.box)
+    ax, by, cz, bx, cx, cy = L, L, L, 0.4, -0.3, 0.5
+    gro = str(tmp_path / "traj.gro")
+    with open(gro, "w") as fh:
+        for f in range(nf):
+            fh.write("skewed cell t= %9.5f\n" % float(f))
+            fh.write("%5d\n" % (3 * n))
+            for a in range(3 * n):
+                fh.write("%5d%-5s%5s%5d%8.3f%8.3f%8.3f\n" % (a // 3 + 1, "SOL", ("OW", "HW1", "HW2")[a % 3], a + 1, *frames[f, a]))
+            fh.write("%10.5f%10.5f%10.5f%10.5f%10.5f%10.5f%10.5f%10.5f%10.5f\n" % (ax, by, cz, 0.0, 0.0, bx, 0.0, cx, cy))
+    r = subprocess.run([exe, "-f", gro, "-edges", str(tmp_path / "edges"), "-nodes", "", "-ohb", str(tmp_path / "ohb.xvg"), "-obw", "",
+                        "-batch", "2", "-pbc"] + list(extra), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    f32 = lambda v: np.float32(np.float64("%10.5f" % v))
+    box9 = np.array([f32(ax), 0, 0, f32(bx), f32(by), 0, f32(cx), f32(cy), f32(cz)], np.float32)
+    parsed = parse_back(frames)
+    sa, ha, ty = o.water_site_table(n)
+    want = EDGE_HEADER
+    n_rect = n_tric = 0
+    for f in range(nf):
+        e, st, _, _ = o.frame_hbonds_tric(parsed[f], sa, ha, ty, box9)
+        n_tric += len(e)
+        n_rect += len(o.frame_hbonds_pbc(parsed[f], sa, ha, ty, np.array([f32(L)] * 3, np.float32))[0])
+        want += "#--- frame %d ---\n" % f
+        want += "".join("%6d%6d%8.4f%8.4f%8.4f\n" % (a + 2, b + 2, en, ln, cs)
+                        for a, b, en, ln, cs in zip(e["i"], e["j"], e["energy"].astype(np.float64),
+                                                    e["length"].astype(np.float64), e["cosine"].astype(np.float64)))
+    assert n_tric != n_rect                                   # the off-diagonal numbers matter
+    assert open(str(tmp_path / "edges.dat")).read() == want

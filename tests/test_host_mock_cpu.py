@@ -222,3 +222,9 @@ def test_driver_files_feed_the_reference_downstream_script(mock_build, tmp_path)
         close_frame(G)
     got = [tuple(int(v) for v in l.split()[1:]) for l in open(str(tmp_path / "comp.xvg")).read().splitlines()]
     assert len(rows) == 3 and got == rows, (got, rows)
+
+
+@pytest.mark.parametrize("extra", [[], ["-gpus", "2"], ["-gpu-text", "0"]])
+def test_standalone_driver_triclinic_box_line(mock_build, tmp_path, extra):
+    import driver_cases
+    driver_cases.check_triclinic_box_line(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, extra)
