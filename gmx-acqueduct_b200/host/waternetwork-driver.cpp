@@ -20,6 +20,12 @@
 //                   [-solvent SOL,WAT,HOH,TIP3] [-buried lists.txt] [-pbc] [-batch 256] [-device 0] [-gpus N]
 //                   [-don 5.5] [-doff 6.5] [-aon 0.25] [-aoff 0.0] [-bug-compat 0|1] [-gpu-text 1|0]
 //                   [-components threshold [-ocomp components-num.xvg]]
+//                   [-b t0] [-e t1] [-dt step] [-frnr0 n] [-append 1]
+// -b/-e/-dt: the frame selection GROMACS' runner gives every analysis tool (first / last time to analyse, only
+// frames whose time is a multiple of -dt after the first frame's); frames are numbered among the ANALYSED frames, from
+// -frnr0 (default 0), as analyzeFrame's frnr is.  -append 1 continues the files of an earlier run (no headers, no
+// nodes file, rows appended): outputs are per frame, so "-e t" followed by "-b t' -frnr0 n -append 1" writes the same
+// bytes as one run over everything (the restart lever the reference inherits from the runner).
 // -components: per frame, the connected components of the network after dropping the edges with
 // |energy| <= threshold (the first step of python/network-analysis.py, computed on the GPU): one row
 // "time components largest sites edges" per frame.
@@ -123,6 +129,9 @@ struct Options {
     double don = 5.5, doff = 6.5, aon = 0.25, aoff = 0.0;
     bool components = false;
     double compThreshold = 0.0;
+    double begin = -1.0e300, end = 1.0e300, dt = 0.0;
+    int frnr0 = 0;
+    bool append = false;
 };
 
 Options parse(int argc, char** argv)
@@ -152,6 +161,11 @@ Options parse(int argc, char** argv)
         else if (a == "-gpu-text") o.gpuText = std::atoi(val().c_str()) != 0;
         else if (a == "-components") { o.components = true; o.compThreshold = std::atof(val().c_str()); }
         else if (a == "-ocomp") o.ocomp = val();
+        else if (a == "-b") o.begin = std::atof(val().c_str());
+        else if (a == "-e") o.end = std::atof(val().c_str());
+        else if (a == "-dt") o.dt = std::atof(val().c_str());
+        else if (a == "-frnr0") o.frnr0 = std::atoi(val().c_str());
+        else if (a == "-append") o.append = std::atoi(val().c_str()) != 0;
         else if (a == "-solvent") {
             o.solvent.clear();
             std::istringstream ss(val());
@@ -237,7 +251,8 @@ int main(int argc, char** argv)
         for (const SiteInfo& s : table) ids.push_back(s.id);
 
         // ---- nodes file (:461-482) and edges header (:485-499)
-        if (!opt.nodes.empty()) {
+        const std::ios::openmode mode = opt.append ? std::ios::out | std::ios::app : std::ios::out;
+        if (!opt.nodes.empty() && !opt.append) {
             std::ofstream nf(opt.nodes + ".dat");
             EdgeFileWriter::writeNodesHeader(nf);
             for (const SiteInfo& s : proteinSites) EdgeFileWriter::writeNode(nf, s);
@@ -246,13 +261,13 @@ int main(int argc, char** argv)
         std::ofstream ef;
         EdgeFileWriter* writer = nullptr;
         if (!opt.edges.empty()) {
-            ef.open(opt.edges + ".dat");
+            ef.open(opt.edges + ".dat", mode);
             writer = new EdgeFileWriter(ef, ids);
-            writer->writeHeader();
+            if (!opt.append) writer->writeHeader();
         }
         std::ofstream ohb, obw;
-        if (!opt.ohb.empty()) ohb.open(opt.ohb);
-        if (!opt.obw.empty()) obw.open(opt.obw);
+        if (!opt.ohb.empty()) ohb.open(opt.ohb, mode);
+        if (!opt.obw.empty()) obw.open(opt.obw, mode);
 
         // ---- optional per-frame water lists (what as_->locate leaves in filteredPoints, :533)
         std::ifstream buried;
@@ -279,19 +294,19 @@ int main(int argc, char** argv)
                 if (writer && !batch_text_done) {                                   // :638-652 (host formatter)
                     if (buried.is_open()) {
                         /* edge indices are positions in this frame's site list: back to table rows for the ids */
-                        const std::vector<int32_t>& rows = frameRows[(size_t)frnr];
+                        const std::vector<int32_t>& rows = frameRows[(size_t)(frnr - opt.frnr0)];
                         std::vector<wn_edge> mapped(e, e + n);
                         for (wn_edge& m : mapped) { m.i = rows[(size_t)m.i]; m.j = rows[(size_t)m.j]; }
                         writer->writeFrame(frnr, mapped.data(), n);
-                        std::vector<int32_t>().swap(frameRows[(size_t)frnr]);
+                        std::vector<int32_t>().swap(frameRows[(size_t)(frnr - opt.frnr0)]);
                     } else {
                         writer->writeFrame(frnr, e, n);
                     }
                 }
                 total_edges += n;
-                const double t = times[(size_t)frnr];
+                const double t = times[(size_t)(frnr - opt.frnr0)];
                 if (obw.is_open()) {                                                 // :654-657
-                    std::snprintf(row, sizeof row, " %11.3f %8.3f %8.3f\n", t, (double)filtered[(size_t)frnr], 0.0);
+                    std::snprintf(row, sizeof row, " %11.3f %8.3f %8.3f\n", t, (double)filtered[(size_t)(frnr - opt.frnr0)], 0.0);
                     obw << row;
                 }
                 if (ohb.is_open() && !sharded) {                                     // :659-666
@@ -315,13 +330,13 @@ int main(int argc, char** argv)
         // edge rows of a whole batch from the GPU formatter (same bytes); a batch with a field wider than its
         // column (ids over 6 digits, values over 8 characters) goes through the host writer instead
         std::ofstream ocomp;
-        if (opt.components && !opt.ocomp.empty()) ocomp.open(opt.ocomp);
+        if (opt.components && !opt.ocomp.empty()) ocomp.open(opt.ocomp, mode);
         if (!sharded) batcher.setBatchHook([&](const std::vector<int>& frameNumbers, const HydrogenBondBatch&) {
             if (ocomp.is_open()) {
                 const int32_t* labels = nullptr; const wn_component_stats* cs = nullptr;
                 hb.componentsOfLastBatch((float)opt.compThreshold, &labels, &cs);
                 for (size_t k = 0; k < frameNumbers.size(); ++k) {
-                    std::snprintf(row, sizeof row, " %11.3f %8d %8d %8d %8d\n", times[(size_t)frameNumbers[k]], cs[k].n_components,
+                    std::snprintf(row, sizeof row, " %11.3f %8d %8d %8d %8d\n", times[(size_t)(frameNumbers[k] - opt.frnr0)], cs[k].n_components,
                                   cs[k].largest, cs[k].n_nodes, cs[k].n_edges);
                     ocomp << row;
                 }
@@ -336,14 +351,28 @@ int main(int argc, char** argv)
             }
         });
 
-        int frnr = 0;
+        int frnr = opt.frnr0;
+        long fileFrame = -1;
+        double tFirst = 0.0;
         do {
             if ((int)(fr.xyz.size() / 3) != natoms) throw std::runtime_error(".gro: atom count changes between frames");
-            times.push_back(fr.has_time ? fr.time : (double)frnr);
+            ++fileFrame;
+            // frame selection of the GROMACS runner (-b, -e, -dt); a file without times counts frames
+            const double tFrame = fr.has_time ? fr.time : (double)fileFrame;
+            if (fileFrame == 0) tFirst = tFrame;
+            std::string buriedLine;
+            if (buried.is_open() && !std::getline(buried, buriedLine)) throw std::runtime_error("-buried: fewer lines than frames");
+            if (tFrame > opt.end) break;
+            bool use = tFrame >= opt.begin;
+            if (use && opt.dt > 0.0) {
+                const double q = (tFrame - tFirst) / opt.dt;
+                use = std::fabs(q - std::floor(q + 0.5)) < 1e-6;
+            }
+            if (!use) continue;
+            times.push_back(tFrame);
             const float (*box)[3] = opt.pbc ? fr.box : nullptr;
             if (buried.is_open()) {
-                std::string line;
-                if (!std::getline(buried, line)) throw std::runtime_error("-buried: fewer lines than frames");
+                const std::string& line = buriedLine;
                 std::vector<int32_t> rows;
                 for (size_t s = 0; s < nP; ++s) rows.push_back((int32_t)s);
                 std::istringstream ls(line);
@@ -353,8 +382,8 @@ int main(int argc, char** argv)
                     rows.push_back((int32_t)(nP + (size_t)w));
                 }
                 filtered.push_back(cnt);
-                frameRows.resize((size_t)frnr + 1);
-                frameRows[(size_t)frnr] = rows;
+                frameRows.resize((size_t)(frnr - opt.frnr0) + 1);
+                frameRows[(size_t)(frnr - opt.frnr0)] = rows;
                 batcher.push(frnr, fr.xyz.data(), box, rows);
             } else {
                 filtered.push_back(nW);
@@ -373,7 +402,7 @@ int main(int argc, char** argv)
             }
         }
         delete writer;
-        std::clog << frnr << " frames, " << total_edges << " hydrogen bonds" << std::endl;
+        std::clog << frnr - opt.frnr0 << " frames, " << total_edges << " hydrogen bonds" << std::endl;
         return 0;
     } catch (const std::exception& e) {
         std::cerr << "wn_waternetwork: " << e.what() << std::endl;

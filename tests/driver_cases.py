@@ -349,3 +349,47 @@ def check_triclinic_box_line(exe, tmp_path, extra=()):
                                                     e["length"].astype(np.float64), e["cosine"].astype(np.float64)))
     assert n_tric != n_rect                                   # the off-diagonal numbers matter
     assert open(str(tmp_path / "edges.dat")).read() == want
+
+
+def check_frame_selection_and_resume(exe, tmp_path, extra=()):
+    """-b / -e / -dt (the GROMACS runner's frame selection) and -frnr0 / -append (continue an earlier run): a run split in
+    two writes the same bytes as one run over everything; -dt keeps every second frame, numbered among the analysed
+    frames as analyzeFrame's frnr is."""
+    import wn_oracle_py as o
+    n, nf = 125, 9
+    sb = o.synth_box(n, model=o.MODEL_SPC)
+    frames = o.synth_frames(sb, 0, nf)
+    gro = str(tmp_path / "traj.gro")
+    write_gro(gro, frames, float(sb.box))                       # t = 0, 2, 4, ... 16
+
+    def run(tag, more, fresh=True):
+        d = tmp_path / tag
+        if fresh:
+            d.mkdir()
+        r = subprocess.run([exe, "-f", gro, "-edges", str(d / "edges"), "-nodes", str(d / "nodes"), "-ohb", str(d / "ohb.xvg"),
+                            "-obw", str(d / "obw.xvg"), "-batch", "2"] + more + list(extra), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return {k: open(str(d / k)).read() for k in ("edges.dat", "nodes.dat", "ohb.xvg", "obw.xvg")}, r.stderr
+
+    whole, _ = run("whole", [])
+    assert whole["edges.dat"].count("#--- frame") == nf
+    first, err = run("split", ["-e", "7.0"])                    # t = 0..6: four frames
+    assert "4 frames," in err and first["edges.dat"].count("#--- frame") == 4
+    both, err = run("split", ["-b", "7.5", "-frnr0", "4", "-append", "1"], fresh=False)
+    assert "5 frames," in err
+    assert both == whole                                        # every file, byte for byte
+    # every second frame: the analysed frames are numbered 0, 1, 2, ... and carry the times 0, 4, 8, ...
+    sel, err = run("dt", ["-dt", "4.0"])
+    assert "5 frames," in err
+
+    def split_frames(text):
+        parts = text.split("#--- frame ")[1:]
+        return [p.split(" ---\n", 1) for p in parts]
+
+    w, s2 = split_frames(whole["edges.dat"]), split_frames(sel["edges.dat"])
+    assert [int(h) for h, _ in s2] == [0, 1, 2, 3, 4]
+    assert [rows for _, rows in s2] == [w[k][1] for k in (0, 2, 4, 6, 8)]
+    assert [float(l.split()[0]) for l in sel["ohb.xvg"].splitlines()] == [0.0, 4.0, 8.0, 12.0, 16.0]
+    # a window in the middle
+    mid, err = run("mid", ["-b", "4.0", "-e", "8.0"])
+    assert [rows for _, rows in split_frames(mid["edges.dat"])] == [w[k][1] for k in (2, 3, 4)]

@@ -228,3 +228,10 @@ def test_driver_files_feed_the_reference_downstream_script(mock_build, tmp_path)
 def test_standalone_driver_triclinic_box_line(mock_build, tmp_path, extra):
     import driver_cases
     driver_cases.check_triclinic_box_line(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, extra)
+
+
+@pytest.mark.parametrize("extra", [[], ["-gpus", "3"], ["-gpu-text", "0", "-pbc"]])
+def test_standalone_driver_frame_selection_and_resume(mock_build, tmp_path, extra):
+    """SURVEY 5 (checkpoint / resume = the runner's -b/-e/-dt; outputs are per frame, so a resumed run appends)."""
+    import driver_cases
+    driver_cases.check_frame_selection_and_resume(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, extra)
