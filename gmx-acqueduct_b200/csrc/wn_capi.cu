@@ -1661,7 +1661,8 @@ static void* nccl_open(std::string* why)
         void* h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
         if (h) return h;
     }
-    if (why) *why = dlerror() ? dlerror() : "libnccl.so.2 not found";
+    const char* e = dlerror();                  /* one call: dlerror() clears the message it returns */
+    if (why) *why = e ? e : "libnccl.so.2 not found";
     return nullptr;
 }
 
