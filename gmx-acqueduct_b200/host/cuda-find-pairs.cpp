@@ -5,6 +5,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <system_error>
 #include <thread>
 #ifdef __linux__
 #include <sys/mman.h>
@@ -54,7 +55,9 @@ void split_bytes(size_t bytes, unsigned parts, F fn)       // fn(lo, hi) on equa
     std::vector<std::thread> ts;
     for (unsigned k = 1; k < parts; ++k) {
         const size_t lo = std::min(bytes, each * k), hi = k + 1 == parts ? bytes : std::min(bytes, each * (k + 1));
-        if (hi > lo) ts.emplace_back([=]() { fn(lo, hi); });
+        if (hi <= lo) continue;
+        try { ts.emplace_back([=]() { fn(lo, hi); }); }
+        catch (const std::system_error&) { fn(lo, hi); }       // no thread to be had: this thread takes the part as well
     }
     fn((size_t)0, std::min(bytes, each));
     for (std::thread& t : ts) t.join();
