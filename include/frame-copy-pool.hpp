@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstring>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -25,7 +26,9 @@ public:
     // helpers = threads besides the caller (0: plain memcpy on the caller's thread)
     explicit FrameCopyPool(int helpers) : gen_(0), remaining_(0), quit_(false), dst_(nullptr), src_(nullptr), bytes_(0), parts_(1)
     {
-        for (int k = 0; k < helpers; ++k) threads_.emplace_back([this, k]() { run(k + 1); });
+        // fewer helpers than asked for if the system has no more threads to give: the ones that started are used
+        try { for (int k = 0; k < helpers; ++k) threads_.emplace_back([this, k]() { run(k + 1); }); }
+        catch (const std::system_error&) {}
     }
     ~FrameCopyPool()
     {
