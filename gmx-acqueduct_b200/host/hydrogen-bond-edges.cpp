@@ -409,8 +409,10 @@ void FrameBatcher::setCopyThreads(int n)
 void FrameBatcher::push(int frnr, const float* xyz)
 {
     const size_t bytes = (size_t)natoms_ * 3 * sizeof(float);
-    if (copy_pool_) copy_pool_->copy(stage(), xyz, bytes);
-    else std::memcpy(stage(), xyz, bytes);
+    if (bytes) {                                    // a frame without atoms: nothing to copy (and xyz may be null)
+        if (copy_pool_) copy_pool_->copy(stage(), xyz, bytes);
+        else std::memcpy(stage(), xyz, bytes);
+    }
     commit(frnr);
 }
 

@@ -194,6 +194,7 @@ int main(int argc, char** argv)
         std::vector<int> resNr;
         if (!readGroFrame(in, fr, &atomName, &resNameAtom, &resNr)) throw std::runtime_error("empty trajectory");
         const int natoms = (int)atomName.size();
+        if (natoms == 0) throw std::runtime_error(".gro: the first frame has no atoms");
         TopologyView top;
         top.atomName = atomName;
         top.element.resize((size_t)natoms);
@@ -259,10 +260,10 @@ int main(int argc, char** argv)
             for (const SiteInfo& s : solventSites) EdgeFileWriter::writeNode(nf, s);
         }
         std::ofstream ef;
-        EdgeFileWriter* writer = nullptr;
+        std::unique_ptr<EdgeFileWriter> writer;
         if (!opt.edges.empty()) {
             ef.open(opt.edges + ".dat", mode);
-            writer = new EdgeFileWriter(ef, ids);
+            writer.reset(new EdgeFileWriter(ef, ids));
             if (!opt.append) writer->writeHeader();
         }
         std::ofstream ohb, obw;
@@ -401,7 +402,6 @@ int main(int argc, char** argv)
                 ohb << row;
             }
         }
-        delete writer;
         std::clog << frnr - opt.frnr0 << " frames, " << total_edges << " hydrogen bonds" << std::endl;
         return 0;
     } catch (const std::exception& e) {

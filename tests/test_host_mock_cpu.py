@@ -235,3 +235,44 @@ def test_standalone_driver_frame_selection_and_resume(mock_build, tmp_path, extr
     """SURVEY 5 (checkpoint / resume = the runner's -b/-e/-dt; outputs are per frame, so a resumed run appends)."""
     import driver_cases
     driver_cases.check_frame_selection_and_resume(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path, extra)
+
+
+def test_standalone_driver_rejects_malformed_input_cleanly(mock_build, tmp_path):
+    """Malformed trajectories and option values end the driver with exit code 1 and a message -- no crash, no
+    out-of-bounds read (the AddressSanitizer/UBSan build of the driver is used where the runtime exists)."""
+    exe = os.path.join(mock_build, "wn_waternetwork_mock")
+    if _sanitizer_links("-fsanitize=address"):
+        subprocess.check_call(["make", "-s", "-C", MOCK, "build/wn_waternetwork_asan"])
+        exe = os.path.join(mock_build, "wn_waternetwork_asan")
+    atom = "    1SOL     OW    1   0.100   0.100   0.100\n    1SOL    HW1    2   0.190   0.100   0.100\n    1SOL    HW2    3   0.070   0.190   0.100\n"
+    good = "w t= 0.0\n    3\n" + atom + "   1.00000   1.00000   1.00000\n"
+    cases = {
+        "empty": "",
+        "only_title": "title\n",
+        "negative_count": "w\n   -3\n",
+        "short_atom_line": "w\n    3\n    1SOL     OW    1   0.1\n",
+        "ends_inside_frame": "w\n    3\n" + atom[:len(atom) // 2],
+        "missing_box": "w\n    3\n" + atom,
+        "count_changes": good + "w t= 1.0\n    6\n" + atom + atom.replace("    1SOL", "    2SOL") + "   1.00000   1.00000   1.00000\n",
+        "not_whole_waters": "w\n    2\n" + "".join(atom.splitlines(True)[:2]) + "   1.00000   1.00000   1.00000\n",
+        "huge_count": "w\n99999999\n" + atom + "   1.00000   1.00000   1.00000\n",
+        "binary_garbage": "\x00\x01\x02\xff\n\x7f\x00\n" * 20,
+    }
+    for name, text in cases.items():
+        p = tmp_path / (name + ".gro")
+        p.write_bytes(text.encode("latin-1"))
+        r = subprocess.run([exe, "-f", str(p), "-edges", str(tmp_path / "e"), "-nodes", str(tmp_path / "n"), "-ohb", "", "-obw", ""],
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1 and "wn_waternetwork:" in r.stderr, (name, r.returncode, r.stderr[-400:])
+        assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, (name, r.stderr[-2000:])
+    ok = tmp_path / "ok.gro"
+    ok.write_text(good)
+    for bad_args in (["-nosuchoption", "1"], ["-batch"], ["-buried", str(tmp_path / "missing.txt")], ["-gpus", "2", "-components", "0.1"],
+                     ["-gpus", "99"]):
+        r = subprocess.run([exe, "-f", str(ok), "-edges", str(tmp_path / "e"), "-nodes", "", "-ohb", "", "-obw", ""] + bad_args,
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1 and "wn_waternetwork:" in r.stderr, (bad_args, r.returncode, r.stderr[-400:])
+        assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, (bad_args, r.stderr[-2000:])
+    # a well-formed one-water trajectory runs (no pairs, no edges)
+    r = subprocess.run([exe, "-f", str(ok), "-edges", str(tmp_path / "e"), "-nodes", "", "-ohb", "", "-obw", ""], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "1 frames, 0 hydrogen bonds" in r.stderr, r.stderr
