@@ -276,3 +276,25 @@ def test_standalone_driver_rejects_malformed_input_cleanly(mock_build, tmp_path)
     # a well-formed one-water trajectory runs (no pairs, no edges)
     r = subprocess.run([exe, "-f", str(ok), "-edges", str(tmp_path / "e"), "-nodes", "", "-ohb", "", "-obw", ""], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "1 frames, 0 hydrogen bonds" in r.stderr, r.stderr
+
+
+def test_driver_module_and_bench_under_address_sanitizer(mock_build, tmp_path):
+    """The standalone driver (sharded, site lists, frame selection + append), the GROMACS module on the API miniature
+    and wn_bench (several GPUs, dynamic order, unpipelined) under AddressSanitizer + UBSan: same outputs, no report."""
+    if not _sanitizer_links("-fsanitize=address"):
+        pytest.skip("no AddressSanitizer runtime with this compiler")
+    import driver_cases
+    subprocess.check_call(["make", "-s", "-j4", "-C", MOCK, "asan"])
+    drv, mod, bench = (os.path.join(mock_build, n) for n in ("wn_waternetwork_asan", "wn_gmx_module_asan", "wn_bench_asan"))
+    for k, fn in enumerate((lambda d: driver_cases.check_gromacs_module_equals_driver(mod, drv, d, False, 2),
+                            lambda d: driver_cases.check_frame_sharding(drv, d, 4),
+                            lambda d: driver_cases.check_buried_lists(drv, d, ["-gpus", "3", "-batch", "1"]),
+                            lambda d: driver_cases.check_frame_selection_and_resume(drv, d, []))):
+        d = tmp_path / ("case%d" % k)
+        d.mkdir()
+        fn(d)
+    for extra in (["-layout", "16", "-mode", "push"], ["-layout", "12", "-mode", "stage", "-gpus", "4", "-dynamic", "1"],
+                  ["-layout", "20", "-mode", "push", "-gpus", "2", "-pipelined", "0"]):
+        r = subprocess.run([bench, "-waters", "300", "-batch", "4", "-batches", "3", "-warmup", "2", "-ring", "8"] + extra,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "Sanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
