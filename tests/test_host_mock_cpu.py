@@ -298,3 +298,8 @@ def test_driver_module_and_bench_under_address_sanitizer(mock_build, tmp_path):
         r = subprocess.run([bench, "-waters", "300", "-batch", "4", "-batches", "3", "-warmup", "2", "-ring", "8"] + extra,
                            capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "Sanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
+
+
+def test_make_sites_on_random_topologies_through_the_driver(mock_build, tmp_path):
+    import driver_cases
+    driver_cases.check_random_topologies(os.path.join(mock_build, "wn_waternetwork_mock"), tmp_path)
