@@ -19,7 +19,7 @@ BUILD = os.path.join(MOCK, "build")
 
 @pytest.fixture(scope="module")
 def mock_build():
-    subprocess.check_call(["make", "-s", "-j4", "-C", MOCK, "all"])
+    subprocess.check_call(["make", "-s", "-j8", "-C", MOCK, "all"])
     return BUILD
 
 
@@ -60,7 +60,7 @@ def test_frame_batcher_under_thread_sanitizer(mock_build):
     state: the stress test under ThreadSanitizer reports no data race."""
     if not _sanitizer_links("-fsanitize=thread"):
         pytest.skip("no ThreadSanitizer runtime with this compiler")
-    subprocess.check_call(["make", "-s", "-C", MOCK, "tsan"])
+    subprocess.check_call(["make", "-s", "-j8", "-C", MOCK, "tsan"])
     r = _run(os.path.join(mock_build, "test_batcher_tsan"), env={"TSAN_OPTIONS": "halt_on_error=1 exitcode=66"})
     assert r.returncode == 0 and "test_batcher_mock OK" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stdout + r.stderr[-3000:]
 
@@ -70,7 +70,7 @@ def test_host_mirror_under_address_sanitizer(mock_build):
     re-assigns its buffers exactly then, so a host that reads an expired result trips AddressSanitizer."""
     if not _sanitizer_links("-fsanitize=address"):
         pytest.skip("no AddressSanitizer runtime with this compiler")
-    subprocess.check_call(["make", "-s", "-j2", "-C", MOCK, "asan"])
+    subprocess.check_call(["make", "-s", "-j8", "-C", MOCK, "asan"])
     for exe, ok in (("test_batcher_asan", "test_batcher_mock OK"), ("test_host_asan", "test_host OK")):
         r = _run(os.path.join(mock_build, exe), env={"ASAN_OPTIONS": "detect_leaks=1"})
         assert r.returncode == 0 and ok in r.stdout, exe + ": " + r.stdout + r.stderr[-3000:]
@@ -284,7 +284,7 @@ def test_driver_module_and_bench_under_address_sanitizer(mock_build, tmp_path):
     if not _sanitizer_links("-fsanitize=address"):
         pytest.skip("no AddressSanitizer runtime with this compiler")
     import driver_cases
-    subprocess.check_call(["make", "-s", "-j4", "-C", MOCK, "asan"])
+    subprocess.check_call(["make", "-s", "-j8", "-C", MOCK, "asan"])
     drv, mod, bench = (os.path.join(mock_build, n) for n in ("wn_waternetwork_asan", "wn_gmx_module_asan", "wn_bench_asan"))
     for k, fn in enumerate((lambda d: driver_cases.check_gromacs_module_equals_driver(mod, drv, d, False, 2),
                             lambda d: driver_cases.check_frame_sharding(drv, d, 4),
